@@ -1,0 +1,476 @@
+"""Batched front-ends of the two fused CUDA engines.
+
+``SharedSpM``           -- pattern B: many SpM problems sharing one (s, P, C); the reference reaches
+                           this only through ``PartialDiagonalMatrix`` packing (matrix.py:301-401),
+                           which makes mu and the stopping test batch-global (``batch_wide=True``).
+                           ``batch_wide=False`` is the per-problem mode (every column behaves like
+                           its own ``SimpleOptimizer`` instance).
+``BatchedBasisPursuit`` -- pattern A: independent problems, each with its own A (M x N).
+
+Host code is orchestration only: it owns torch device buffers, fills the C structs of
+``include/admm_b200.h`` and enqueues kernels on the current CUDA stream.  All arithmetic of the
+solve loop runs in ``libadmm_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BpBuffers, SpmBuffers, SpmDims, call, ptr, stream
+
+__all__ = ["SharedSpM", "BatchedBasisPursuit"]
+
+_F64 = torch.float64
+_C128 = torch.complex128
+
+
+def _dev_tensor(a, device, dtype=None) -> torch.Tensor:
+    if isinstance(a, torch.Tensor):
+        t = a.to(device=device)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _pad_L(L: int) -> int:
+    for cand in (16, 40, 64):
+        if L <= cand:
+            return cand
+    raise NotImplementedError(f"SpM engine supports basis sizes up to 64, got L={L}")
+
+
+class SharedSpM:
+    """Pattern B on the GPU.
+
+    minimise   alpha ||y - A x0||^2 + lam |x1|_1    s.t.  C x0 = D,  x0 = x1,  P x0 = x2 >= 0
+
+    with real operators (A^H A = ``G0`` is L x L real, P is Nw x L real, C is 1 x L real) and
+    real or complex data.  Construct either from the SpM form (``s``, ``g``: A = -diag(s), y = g)
+    or from precomputed ``G0 = alpha A^H A`` and ``b0 = alpha A^H y`` (``from_operators``).
+    """
+
+    CACHE_SLOTS = 64
+
+    def __init__(self, s, P, C_, D, g, lam: float, mu: float = 0.1, alpha: float = 1.0,
+                 batch_wide: bool = False, max_mu: float = 1e3, nsplit: Optional[int] = None,
+                 group=None, force_complex: Optional[bool] = None):
+        dev = _lib.require_cuda()
+        s_t = _dev_tensor(s, dev, _F64)
+        g_t = _dev_tensor(g, dev)
+        if g_t.ndim == 1:
+            g_t = g_t[:, None]
+        g_t = g_t.contiguous()
+        G0 = torch.diag(alpha * s_t * s_t)
+        # b0 = alpha A^H y with A = -diag(s):  diag kernel, then scale
+        L, nb = g_t.shape
+        cplx = g_t.is_complex()
+        gv = g_t if cplx else g_t.to(_F64)
+        b0 = torch.empty_like(gv)
+        sd = (-alpha * s_t).to(gv.dtype)
+        call("admm_diag_mul", int(cplx), L, L, nb, ptr(sd), ptr(gv), nb, ptr(b0), nb, stream())
+        self._init_common(G0, b0, P, C_, D, lam, mu, mu, batch_wide, max_mu, nsplit, group, force_complex)
+        self._s = s_t
+        self._g = gv
+        self._alpha = alpha
+
+    @classmethod
+    def from_operators(cls, G0, b0, P, C_, D, lam: float, mu10: float, mu20: float,
+                       batch_wide: bool = True, max_mu: float = 1e3, nsplit: Optional[int] = None,
+                       group=None, force_complex: Optional[bool] = None) -> "SharedSpM":
+        self = cls.__new__(cls)
+        dev = _lib.require_cuda()
+        b0_t = _dev_tensor(b0, dev)
+        if b0_t.ndim == 1:
+            b0_t = b0_t[:, None].contiguous()
+        self._init_common(_dev_tensor(G0, dev, _F64), b0_t, P, C_, D, lam, mu10, mu20, batch_wide, max_mu,
+                          nsplit, group, force_complex)
+        self._s = None
+        self._g = None
+        self._alpha = None
+        return self
+
+    # ------------------------------------------------------------------ setup
+    def _init_common(self, G0, b0, P, C_, D, lam, mu10, mu20, batch_wide, max_mu, nsplit, group, force_complex):
+        dev = _lib.require_cuda()
+        self.device = dev
+        self.group = group
+        P_t = _dev_tensor(P, dev, _F64)
+        Nw, L = P_t.shape
+        assert b0.shape[0] == L and G0.shape == (L, L)
+        nb = b0.shape[1]
+        D_t = _dev_tensor(np.asarray(D) if not isinstance(D, torch.Tensor) else D, dev).reshape(-1)
+        if D_t.numel() == 1:
+            D_t = D_t.expand(nb)
+        assert D_t.numel() == nb
+        cplx = bool(b0.is_complex() or D_t.is_complex())
+        if force_complex is not None:
+            cplx = bool(force_complex) or cplx
+        self.L, self.Nw, self.nb = L, Nw, nb
+        self.is_complex = cplx
+        Lp = _pad_L(L)
+        ldp = ((Lp + 15) // 16) * 16
+        nrt = ((Nw + 7) // 8 + 3) // 4 * 4
+        npt = (nb + 7) // 8
+        nplanes = 2 if cplx else 1
+        nchunks = nrt // 4
+        if nsplit is None:
+            col_ctas = (npt + 3) // 4
+            nsplit = max(1, min(nchunks, -(-444 // col_ctas)))
+        nsplit = max(1, min(nsplit, nchunks))
+        self.dims = SpmDims(L, Lp, ldp, Nw, nrt, nb, npt, nplanes, nsplit, int(batch_wide))
+        self.batch_wide = bool(batch_wide)
+        self.lam, self.max_mu = float(lam), float(max_mu)
+        nprob = 8 * npt
+        nct = npt * nplanes
+        NT = Lp // 8
+        z = lambda *shape, dtype=_F64: torch.zeros(*shape, dtype=dtype, device=dev)
+        dref = C.byref(self.dims)
+
+        # shared operators
+        self.Psw = z(8 * nrt * ldp)
+        call("admm_spm_prepare_P", dref, ptr(P_t), L, ptr(self.Psw), stream())
+        self.P = P_t
+        self.PtP = z(Lp, Lp)
+        ptp = z(L, L)
+        call("admm_gemm", 0, _lib.OP_T, L, L, Nw, ptr(P_t), L, ptr(P_t), L, ptr(ptp), L, stream())
+        self.PtP[:L, :L] = ptp
+        self.G0 = z(Lp, Lp)
+        self.G0[:L, :L] = G0
+        Cv = _dev_tensor(np.asarray(C_) if not isinstance(C_, torch.Tensor) else C_, dev, _F64).reshape(-1)
+        assert Cv.numel() == L, "the fused SpM engine supports a single constraint row (C is 1 x L)"
+        self.Cvec = z(Lp)
+        self.Cvec[:L] = Cv
+        self.Ginv_cache = z(self.CACHE_SLOTS, Lp, Lp)
+        self.w_cache = z(self.CACHE_SLOTS, Lp)
+        self.sigma_cache = z(self.CACHE_SLOTS)
+        self._slot_of = {}
+        # per problem
+        self.slot = torch.zeros(nprob, dtype=torch.int32, device=dev)
+        self.mu10 = torch.full((nprob,), float(mu10), dtype=_F64, device=dev)
+        self.mu20 = torch.full((nprob,), float(mu20), dtype=_F64, device=dev)
+        self.mu20_used = self.mu20.clone()
+        self.done = torch.zeros(nprob, dtype=torch.int32, device=dev)
+        self.done[nb:] = 1
+        self.iters = torch.zeros(nprob, dtype=torch.int32, device=dev)
+        self.last_res = z(nprob, 2)
+        self.Dre = z(nplanes, nprob)
+        self.Dre[0, :nb] = D_t.real if D_t.is_complex() else D_t.to(_F64)
+        if cplx and D_t.is_complex():
+            self.Dre[1, :nb] = D_t.imag
+        # fragment-layout arrays
+        fl = nct * NT * 64
+        self.b0 = z(fl)
+        call("admm_spm_pack_L", dref, ptr(b0.contiguous()), int(b0.is_complex()), ptr(self.b0), stream())
+        self.x0f, self.x1f, self.h10f = z(fl), z(fl), z(fl)
+        self.V, self.Vx = z(nsplit * fl), z(nsplit * fl)
+        self.S = z(npt * nrt * nplanes * 64)
+        self.normsA = z(nct * 8 * 8)
+        self.normsB = z(nsplit * nct * 8 * 4)
+        self.gsum = z(16)
+        self.gpart = z(256 * 16)
+        self.iter_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.flags = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.history = None
+        self._v_state = "none"
+        self.primal_residual = []
+        self.dual_residual = []
+        self.bufs = SpmBuffers()
+        self._fill_bufs(1e-12)
+        self._refresh_slots(initial=True)
+
+    def _fill_bufs(self, rtol, fact_incr=2.0, th_change=10.0):
+        b = self.bufs
+        for name, t in (("Psw", self.Psw), ("PtP", self.PtP), ("Cvec", self.Cvec), ("Ginv_cache", self.Ginv_cache),
+                        ("w_cache", self.w_cache), ("sigma_cache", self.sigma_cache), ("slot", self.slot),
+                        ("mu10", self.mu10), ("mu20", self.mu20), ("mu20_used", self.mu20_used), ("done", self.done),
+                        ("iters", self.iters), ("last_res", self.last_res), ("Dre", self.Dre), ("b0", self.b0),
+                        ("x0", self.x0f), ("x1", self.x1f), ("h10", self.h10f), ("V", self.V), ("Vx", self.Vx),
+                        ("S", self.S), ("normsA", self.normsA), ("normsB", self.normsB), ("gsum", self.gsum),
+                        ("gpart", self.gpart), ("iter_counter", self.iter_counter), ("flags", self.flags)):
+            setattr(b, name, t.data_ptr())
+        b.history = self.history.data_ptr() if self.history is not None else None
+        b.hist_cap = int(self.history.shape[0]) if self.history is not None else 0
+        b.lam, b.rtol, b.max_mu = self.lam, float(rtol), self.max_mu
+        b.fact_incr, b.th_change = float(fact_incr), float(th_change)
+
+    # ------------------------------------------------------------------ factor cache
+    def _refresh_slots(self, initial: bool = False) -> None:
+        """Map every problem's (mu10, mu20) to a factor-cache row; factor the new pairs."""
+        nb = self.nb
+        if self.batch_wide or nb == 1:
+            pairs = torch.stack([self.mu10[:1], self.mu20[:1]], dim=1).cpu().numpy()
+            inverse = None
+        else:
+            stacked = torch.stack([self.mu10[:nb], self.mu20[:nb]], dim=1)
+            uniq, inverse = torch.unique(stacked, dim=0, return_inverse=True)
+            pairs = uniq.cpu().numpy()
+        new = [(float(a), float(b)) for a, b in pairs if (float(a), float(b)) not in self._slot_of]
+        if len(self._slot_of) + len(new) > self.CACHE_SLOTS:
+            # evict everything not currently needed
+            needed = {(float(a), float(b)) for a, b in pairs}
+            self._slot_of = {k: v for k, v in self._slot_of.items() if k in needed}
+            new = [k for k in needed if k not in self._slot_of]
+            if len(self._slot_of) + len(new) > self.CACHE_SLOTS:
+                raise _lib.AdmmError("SpM factor cache exhausted: too many distinct (mu10, mu20) pairs")
+        if new:
+            free = [i for i in range(self.CACHE_SLOTS) if i not in set(self._slot_of.values())]
+            slots = free[:len(new)]
+            for k, sl in zip(new, slots):
+                self._slot_of[k] = sl
+            dev = self.device
+            sl_t = torch.tensor(slots, dtype=torch.int32, device=dev)
+            m10 = torch.tensor([k[0] for k in new], dtype=_F64, device=dev)
+            m20 = torch.tensor([k[1] for k in new], dtype=_F64, device=dev)
+            info = torch.zeros(len(new), dtype=torch.int32, device=dev)
+            call("admm_spm_factor", C.byref(self.dims), len(new), ptr(sl_t), ptr(m10), ptr(m20), ptr(self.G0),
+                 ptr(self.PtP), ptr(self.Cvec), ptr(self.Ginv_cache), ptr(self.w_cache), ptr(self.sigma_cache),
+                 ptr(info), stream())
+            if int(info.max().item()) != 0:
+                raise _lib.AdmmError("alpha A^H A + mu is not positive definite")
+        if inverse is None:
+            self.slot.fill_(self._slot_of[(float(pairs[0][0]), float(pairs[0][1]))])
+        else:
+            lut = torch.tensor([self._slot_of[(float(a), float(b))] for a, b in pairs], dtype=torch.int32,
+                               device=self.device)
+            self.slot[:nb] = lut[inverse]
+
+    # ------------------------------------------------------------------ state import / export
+    def set_state(self, x0=None, x1=None, x2=None, h10=None, h20=None) -> None:
+        """Load canonical (rows x nb) state (complex or real).  Raises ``NotImplementedError`` if
+        (h20, x2) is not representable by the implicit complementarity form."""
+        dref = C.byref(self.dims)
+        for src, dst in ((x0, self.x0f), (x1, self.x1f), (h10, self.h10f)):
+            if src is not None:
+                t = _dev_tensor(src, self.device).reshape(self.L, self.nb).contiguous()
+                if not self.is_complex and t.is_complex():
+                    if float(t.imag.abs().max().item()) != 0.0:
+                        raise NotImplementedError("complex state on a real-data SpM plan")
+                    t = t.real.contiguous()
+                call("admm_spm_pack_L", dref, ptr(t), int(t.is_complex()), ptr(dst), stream())
+        if x2 is not None or h20 is not None:
+            zer = lambda: torch.zeros(self.Nw, self.nb, dtype=_F64, device=self.device)
+            h = _dev_tensor(h20, self.device).reshape(self.Nw, self.nb) if h20 is not None else zer()
+            x = _dev_tensor(x2, self.device).reshape(self.Nw, self.nb) if x2 is not None else zer()
+            cp = h.is_complex() or x.is_complex()
+            if cp:
+                h, x = h.to(_C128).contiguous(), x.to(_C128).contiguous()
+            flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            call("admm_spm_pack_state", dref, ptr(h), ptr(x), int(cp), ptr(self.mu20), ptr(self.S), ptr(flag), stream())
+            if int(flag.item()) != 0:
+                raise NotImplementedError("(h20, x2) state is not complementary; use the generic executor")
+            self.mu20_used.copy_(self.mu20)
+        self._v_state = "none"
+
+    def _unpack_L(self, frag) -> np.ndarray:
+        out = torch.empty(self.L, self.nb, dtype=_C128, device=self.device)
+        call("admm_spm_unpack_L", C.byref(self.dims), ptr(frag), ptr(out), 1, stream())
+        return out.cpu().numpy()
+
+    def x0(self) -> np.ndarray:
+        return self._unpack_L(self.x0f)
+
+    def x1(self) -> np.ndarray:
+        return self._unpack_L(self.x1f)
+
+    def h10(self) -> np.ndarray:
+        return self._unpack_L(self.h10f)
+
+    def _unpack_state(self):
+        h = torch.empty(self.Nw, self.nb, dtype=_C128, device=self.device)
+        x = torch.empty(self.Nw, self.nb, dtype=_C128, device=self.device)
+        call("admm_spm_unpack_state", C.byref(self.dims), ptr(self.S), ptr(self.mu20_used), ptr(h), ptr(x), 1, stream())
+        return h, x
+
+    def x2(self) -> np.ndarray:
+        return self._unpack_state()[1].cpu().numpy()
+
+    def h20(self) -> np.ndarray:
+        return self._unpack_state()[0].cpu().numpy()
+
+    def x0_device(self) -> torch.Tensor:
+        """(L, nb) complex128 result on the device (no host copy)."""
+        out = torch.empty(self.L, self.nb, dtype=_C128, device=self.device)
+        call("admm_spm_unpack_L", C.byref(self.dims), ptr(self.x0f), ptr(out), 1, stream())
+        return out
+
+    def set_mu(self, mu10, mu20) -> None:
+        """Overwrite the penalties (scalars or per-problem arrays); re-encodes the implicit state."""
+        h, x = self._unpack_state()
+        self.mu10[:self.nb] = torch.as_tensor(mu10, dtype=_F64, device=self.device)
+        self.mu20[:self.nb] = torch.as_tensor(mu20, dtype=_F64, device=self.device)
+        self.set_state(h20=h, x2=x)
+        self._refresh_slots()
+
+    # ------------------------------------------------------------------ iteration
+    def _iteration(self, do_update_mu: bool) -> None:
+        dref, bref, st = C.byref(self.dims), C.byref(self.bufs), stream()
+        if self._v_state == "none":
+            call("admm_spm_pass", dref, bref, 2, st)
+            self._v_state = "split"
+        call("admm_spm_xupdate", dref, bref, int(self._v_state == "split"), st)
+        call("admm_spm_pass", dref, bref, 1 if do_update_mu else 0, st)
+        self._v_state = "split" if do_update_mu else "plain"
+        if self.batch_wide:
+            call("admm_spm_reduce", dref, bref, st)
+            if self.group is not None:
+                torch.distributed.all_reduce(self.gsum, group=self.group)
+        call("admm_spm_decide", dref, bref, int(do_update_mu), st)
+
+    def solve(self, niter: int = 10000, interval_update_mu: int = 100, rtol: float = 1e-12,
+              callback=None, keep_history: Optional[bool] = None) -> int:
+        """Run up to ``niter`` iterations with the ordering of ``SimpleOptimizer.solve``
+        (optimizer.py:302-320).  Returns the number of iterations launched."""
+        nb = self.nb
+        self.iters.zero_()
+        self.done[:nb] = 0
+        self.flags.zero_()
+        self.iter_counter.zero_()
+        track = (self.batch_wide or nb == 1) if keep_history is None else keep_history
+        self.history = torch.zeros(max(niter, 1), 2, dtype=_F64, device=self.device) if track else None
+        self._fill_bufs(rtol)
+        launched = 0
+        for it in range(niter):
+            upd = (it % interval_update_mu == 0)
+            self._iteration(upd)
+            launched += 1
+            if callback is not None:
+                callback()
+            if upd or callback is not None or it == niter - 1:
+                fl = self.flags.cpu()
+                if int(fl[1]) >= nb:
+                    break
+                if int(fl[0]) != 0:
+                    self.flags[0] = 0
+                    self._refresh_slots()
+        if track:
+            ndone = int(self.iters[0].item())
+            hist = self.history[:ndone].cpu().numpy()
+            self.primal_residual.extend(hist[:, 0].tolist())
+            self.dual_residual.extend(hist[:, 1].tolist())
+        return launched
+
+    # ------------------------------------------------------------------ objective
+    def objective(self) -> float:
+        """alpha ||g + s x0||^2 + lam |x1|_1 summed over the batch (SpM form only)."""
+        if self._s is None:
+            raise NotImplementedError("objective() needs the SpM form (s, g)")
+        x0 = self.x0_device()
+        cplx = self._g.is_complex()
+        xs = x0 if cplx else x0.real.contiguous()
+        sx = torch.empty_like(xs)
+        sd = self._s.to(xs.dtype)
+        call("admm_diag_mul", int(cplx), self.L, self.L, self.nb, ptr(sd), ptr(xs), self.nb, ptr(sx), self.nb, stream())
+        n = sx.numel() * (2 if cplx else 1)
+        msx = torch.empty_like(sx)
+        call("admm_axpby", n, -1.0, ptr(sx), 0.0, None, ptr(msx), stream())
+        out = torch.zeros(1, dtype=_F64, device=self.device)
+        scratch = torch.zeros(1024, dtype=_F64, device=self.device)
+        call("admm_sumsq", n, ptr(self._g), ptr(msx), ptr(out), ptr(scratch), stream())
+        l1 = float(np.abs(self.x1()).sum())
+        return float(self._alpha * out.item() + self.lam * l1)
+
+
+class BatchedBasisPursuit:
+    """Pattern A on the GPU: ``nb`` independent problems
+    ``alpha ||y_b - A_b x0||^2 + lam |x1|_1  s.t. x0 = x1``, each with its own penalty and
+    stopping test (one ``SimpleOptimizer`` instance per problem in the reference)."""
+
+    def __init__(self, A, y, alpha: float = 1.0, lam: float = 0.1, mu: float = 1.0, max_mu: float = 1e3,
+                 keep_history: bool = False):
+        dev = _lib.require_cuda()
+        self.device = dev
+        A_t = _dev_tensor(A, dev, _F64)
+        y_t = _dev_tensor(y, dev, _F64)
+        if A_t.ndim == 2:
+            A_t, y_t = A_t[None], y_t[None]
+        self.A, self.y = A_t.contiguous(), y_t.contiguous()
+        nb, M, N = self.A.shape
+        self.nb, self.M, self.N = nb, M, N
+        self.woodbury = M < N
+        nk = M if self.woodbury else N
+        self.nk = nk
+        self.alpha, self.lam, self.max_mu = float(alpha), float(lam), float(max_mu)
+        z = lambda *shape, dtype=_F64: torch.zeros(*shape, dtype=dtype, device=dev)
+        self.aty, self.gram, self.Kinv = z(nb, N), z(nb, nk, nk), z(nb, nk, nk)
+        self._x0, self._x1, self._h = z(nb, N), z(nb, N), z(nb, N)
+        self.mu = torch.full((nb,), float(mu), dtype=_F64, device=dev)
+        self.need_factor = torch.ones(nb, dtype=torch.int32, device=dev)
+        self.done = torch.zeros(nb, dtype=torch.int32, device=dev)
+        self.iters = torch.zeros(nb, dtype=torch.int32, device=dev)
+        self.last_res = z(nb, 2)
+        self.info = torch.zeros(nb, dtype=torch.int32, device=dev)
+        self.keep_history = keep_history
+        self.history = None
+        self.primal_residual = [[] for _ in range(nb)] if keep_history else None
+        self.dual_residual = [[] for _ in range(nb)] if keep_history else None
+        self.bufs = BpBuffers()
+        self._fill(1e-12, 100)
+        call("admm_bp_setup", C.byref(self.bufs), ptr(self.y), ptr(self.aty), ptr(self.gram), stream())
+
+    def _fill(self, rtol, interval, fact_incr=2.0, th_change=10.0):
+        b = self.bufs
+        b.nb, b.M, b.N, b.woodbury, b.nk = self.nb, self.M, self.N, int(self.woodbury), self.nk
+        for name, t in (("A", self.A), ("aty", self.aty), ("gram", self.gram), ("Kinv", self.Kinv), ("x0", self._x0),
+                        ("x1", self._x1), ("h", self._h), ("mu", self.mu), ("need_factor", self.need_factor),
+                        ("done", self.done), ("iters", self.iters), ("last_res", self.last_res)):
+            setattr(b, name, t.data_ptr())
+        b.history = self.history.data_ptr() if self.history is not None else None
+        b.hist_cap = int(self.history.shape[1]) if self.history is not None else 0
+        b.alpha, b.lam, b.rtol, b.max_mu = self.alpha, self.lam, float(rtol), self.max_mu
+        b.fact_incr, b.th_change, b.interval_update_mu = float(fact_incr), float(th_change), int(interval)
+
+    def set_state(self, x0=None, x1=None, h=None, mu=None) -> None:
+        for src, dst in ((x0, self._x0), (x1, self._x1), (h, self._h)):
+            if src is not None:
+                dst.copy_(_dev_tensor(src, self.device, _F64).reshape(self.nb, self.N))
+        if mu is not None:
+            self.mu[:] = torch.as_tensor(mu, dtype=_F64, device=self.device)
+            self.need_factor.fill_(1)
+
+    def solve(self, niter: int = 10000, interval_update_mu: int = 100, rtol: float = 1e-12) -> None:
+        """All iterations of every problem on the device; no host synchronisation inside."""
+        self.iters.zero_()
+        self.done.zero_()
+        self.history = (torch.zeros(self.nb, max(niter, 1), 2, dtype=_F64, device=self.device)
+                        if self.keep_history else None)
+        self._fill(rtol, interval_update_mu)
+        bref, st = C.byref(self.bufs), stream()
+        rounds = -(-niter // interval_update_mu) + 1
+        for _ in range(rounds):
+            call("admm_bp_factor", bref, ptr(self.info), st)
+            call("admm_bp_iterate", bref, int(niter), st)
+        # a factor may still be pending for the next solve() call (mu changed on the last iteration)
+        if self.keep_history:
+            it = self.iters.cpu().numpy()
+            hist = self.history.cpu().numpy()
+            for b in range(self.nb):
+                self.primal_residual[b].extend(hist[b, :it[b], 0].tolist())
+                self.dual_residual[b].extend(hist[b, :it[b], 1].tolist())
+
+    def x0(self) -> np.ndarray:
+        return self._x0.cpu().numpy()
+
+    def x1(self) -> np.ndarray:
+        return self._x1.cpu().numpy()
+
+    def h(self) -> np.ndarray:
+        return self._h.cpu().numpy()
+
+    def objective(self) -> np.ndarray:
+        """alpha ||y - A x0||^2 + lam |x1|_1 per problem."""
+        out = np.empty(self.nb)
+        r = torch.empty(self.M, 1, dtype=_F64, device=self.device)
+        acc = torch.zeros(1, dtype=_F64, device=self.device)
+        scratch = torch.zeros(1024, dtype=_F64, device=self.device)
+        l1 = self._x1.abs().sum(dim=1).cpu().numpy()
+        for b in range(self.nb):
+            call("admm_gemm", 0, _lib.OP_N, self.M, 1, self.N, ptr(self.A[b]), self.N, ptr(self._x0[b]), 1, ptr(r), 1, stream())
+            call("admm_sumsq", self.M, ptr(self.y[b]), ptr(r), ptr(acc), ptr(scratch), stream())
+            out[b] = self.alpha * acc.item() + self.lam * l1[b]
+        return out

@@ -1,0 +1,321 @@
+// Pattern A engine (basis pursuit / LASSO): every problem has its own real A (M x N).
+// One CTA per problem keeps x0, x1, h, A^T y and the work vectors in shared memory and runs all
+// iterations of SimpleOptimizer.solve (optimizer.py:302-341) without returning to the host; the
+// x-update uses a cached inverse (Woodbury M x M when M < N, direct N x N otherwise).
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace admm {
+
+// ---------------------------------------------------------------------------------------------
+// setup: aty = alpha A^T y ; gram = A A^T (woodbury) or A^T A
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bp_aty_kernel(admm_bp_buffers b, const double* __restrict__ y, double* __restrict__ aty) {
+  const int prob = blockIdx.y;
+  const double* A = b.A + (size_t)prob * b.M * b.N;
+  const double* yv = y + (size_t)prob * b.M;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < b.N; n += gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int m = 0; m < b.M; ++m) acc += A[(size_t)m * b.N + n] * yv[m];
+    aty[(size_t)prob * b.N + n] = b.alpha * acc;
+  }
+}
+
+// C = A A^T (WOOD) : C[i][j] = sum_n A[i][n] A[j][n]   (nk = M, inner = N)
+// C = A^T A        : C[i][j] = sum_m A[m][i] A[m][j]   (nk = N, inner = M)
+template <bool WOOD>
+__global__ void __launch_bounds__(256) bp_gram_kernel(admm_bp_buffers b, double* __restrict__ gram) {
+  __shared__ double As[32][33];
+  __shared__ double Bs[32][33];
+  const int prob = blockIdx.z;
+  const double* A = b.A + (size_t)prob * b.M * b.N;
+  const int nk = b.nk, inner = WOOD ? b.N : b.M;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int row0 = blockIdx.y * 32, col0 = blockIdx.x * 32;
+  if (col0 > row0) return;  // lower triangle tiles only; mirrored on store
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int k0 = 0; k0 < inner; k0 += 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty + 8 * i;
+      double a = 0.0, c = 0.0;
+      if (WOOD) {
+        if (row0 + r < nk && k0 + tx < inner) a = A[(size_t)(row0 + r) * b.N + k0 + tx];
+        if (col0 + r < nk && k0 + tx < inner) c = A[(size_t)(col0 + r) * b.N + k0 + tx];
+        As[r][tx] = a;   // As[i][kk]
+        Bs[r][tx] = c;   // Bs[j][kk]
+      } else {
+        if (k0 + r < inner && row0 + tx < nk) a = A[(size_t)(k0 + r) * b.N + row0 + tx];
+        if (k0 + r < inner && col0 + tx < nk) c = A[(size_t)(k0 + r) * b.N + col0 + tx];
+        As[tx][r] = a;
+        Bs[tx][r] = c;
+      }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < 32; ++kk) {
+      const double c = Bs[tx][kk];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] += As[ty + 8 * i][kk] * c;
+    }
+    __syncthreads();
+  }
+  double* G = gram + (size_t)prob * nk * nk;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row0 + ty + 8 * i, c = col0 + tx;
+    if (r < nk && c < nk) {
+      G[(size_t)r * nk + c] = acc[i];
+      G[(size_t)c * nk + r] = acc[i];
+    }
+  }
+}
+
+// Kinv <- gram shifted by the current mu, for flagged problems (then inverted in place)
+__global__ void __launch_bounds__(256) bp_shift_kernel(admm_bp_buffers b) {
+  const int prob = blockIdx.y;
+  if (!b.need_factor[prob]) return;
+  const int nk = b.nk;
+  const double mu = b.mu[prob];
+  const double* G = b.gram + (size_t)prob * nk * nk;
+  double* K = b.Kinv + (size_t)prob * nk * nk;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nk * nk; idx += gridDim.x * blockDim.x) {
+    const int i = idx / nk, j = idx - i * nk;
+    double v = G[idx];
+    if (b.woodbury) {
+      if (i == j) v += mu / b.alpha;
+    } else {
+      v = b.alpha * v + (i == j ? mu : 0.0);
+    }
+    K[idx] = v;
+  }
+}
+
+__global__ void bp_clear_flag_kernel(admm_bp_buffers b) {
+  const int prob = blockIdx.x * blockDim.x + threadIdx.x;
+  if (prob < b.nb) b.need_factor[prob] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// persistent per-problem iteration kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int BP_THREADS = 256;
+
+__global__ void __launch_bounds__(BP_THREADS) bp_iterate_kernel(admm_bp_buffers b, int iter_end) {
+  extern __shared__ double sm[];
+  const int prob = blockIdx.x;
+  if (b.done[prob] || b.need_factor[prob]) return;
+  int it = b.iters[prob];
+  if (it >= iter_end) return;
+  const int M = b.M, N = b.N, nk = b.nk;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = BP_THREADS / 32;
+  double* aty = sm;          // N
+  double* x0 = aty + N;      // N
+  double* xo = x0 + N;       // N
+  double* x1 = xo + N;       // N
+  double* h = x1 + N;        // N
+  double* r = h + N;         // N
+  double* tv = r + N;        // nk
+  double* sv = tv + nk;      // nk
+  double* scratch = sv + nk; // 5*32
+  const double* A = b.A + (size_t)prob * M * N;
+  const double* Kinv = b.Kinv + (size_t)prob * nk * nk;
+  for (int n = tid; n < N; n += BP_THREADS) {
+    aty[n] = b.aty[(size_t)prob * N + n];
+    x0[n] = b.x0[(size_t)prob * N + n];
+    x1[n] = b.x1[(size_t)prob * N + n];
+    h[n] = b.h[(size_t)prob * N + n];
+  }
+  double mu = b.mu[prob];
+  int done = 0, need = 0;
+  double primal = 0.0, dual = 0.0;
+  __syncthreads();
+
+  while (it < iter_end) {
+    for (int n = tid; n < N; n += BP_THREADS) {
+      xo[n] = x0[n];
+      r[n] = aty[n] + h[n] + mu * x1[n];
+    }
+    __syncthreads();
+    if (b.woodbury) {
+      // t = A r : one warp per row, lanes stride the row (coalesced)
+      for (int m = warp; m < M; m += NW) {
+        const double* row = A + (size_t)m * N;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int n = lane;
+        for (; n + 96 < N; n += 128) {
+          a0 += row[n] * r[n];
+          a1 += row[n + 32] * r[n + 32];
+          a2 += row[n + 64] * r[n + 64];
+          a3 += row[n + 96] * r[n + 96];
+        }
+        for (; n < N; n += 32) a0 += row[n] * r[n];
+        const double s = warp_sum((a0 + a1) + (a2 + a3));
+        if (lane == 0) tv[m] = s;
+      }
+      __syncthreads();
+      // s = Kinv t
+      for (int m = warp; m < M; m += NW) {
+        const double* row = Kinv + (size_t)m * M;
+        double a0 = 0.0;
+        for (int j = lane; j < M; j += 32) a0 += row[j] * tv[j];
+        a0 = warp_sum(a0);
+        if (lane == 0) sv[m] = a0;
+      }
+      __syncthreads();
+      // x0 = (r - A^T s) / mu : one thread per column (coalesced across threads)
+      for (int n = tid; n < N; n += BP_THREADS) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int m = 0;
+        for (; m + 3 < M; m += 4) {
+          a0 += A[(size_t)m * N + n] * sv[m];
+          a1 += A[(size_t)(m + 1) * N + n] * sv[m + 1];
+          a2 += A[(size_t)(m + 2) * N + n] * sv[m + 2];
+          a3 += A[(size_t)(m + 3) * N + n] * sv[m + 3];
+        }
+        for (; m < M; ++m) a0 += A[(size_t)m * N + n] * sv[m];
+        x0[n] = (r[n] - ((a0 + a1) + (a2 + a3))) / mu;
+      }
+    } else {
+      // x0 = Ginv r  (N x N)
+      for (int n = warp; n < N; n += NW) {
+        const double* row = Kinv + (size_t)n * N;
+        double a0 = 0.0;
+        for (int j = lane; j < N; j += 32) a0 += row[j] * r[j];
+        a0 = warp_sum(a0);
+        if (lane == 0) x0[n] = a0;
+      }
+    }
+    __syncthreads();
+    // z-update (soft threshold), dual ascent, norms
+    const double thr = 0.5 * b.lam / mu;
+    double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int n = tid; n < N; n += BP_THREADS) {
+      const double xv = x0[n], hv = h[n], xov = xo[n];
+      const double yv = -((hv - mu * xv) / mu);
+      double z = 0.0;
+      if (yv > thr) z = yv - thr;
+      if (yv < -thr) z = yv + thr;
+      x1[n] = z;
+      h[n] = hv + mu * (z - xv);
+      v[0] += (xv - z) * (xv - z);
+      v[1] += xv * xv;
+      v[2] += z * z;
+      v[3] += (xv - xov) * (xv - xov);
+      v[4] += xov * xov;
+    }
+    block_sum<5>(v, scratch);
+    const double p = sqrt(v[0]), nx0 = sqrt(v[1]), nx1 = sqrt(v[2]), nd = sqrt(v[3]), nxo = sqrt(v[4]);
+    primal = p;
+    dual = mu * nd;
+    if (b.history && it < b.hist_cap && tid == 0) {
+      b.history[((size_t)prob * b.hist_cap + it) * 2] = primal;
+      b.history[((size_t)prob * b.hist_cap + it) * 2 + 1] = dual;
+    }
+    const int this_it = it;
+    ++it;
+    const bool conv = (p / fmax(nx0, nx1) < b.rtol) && (dual / fmax(mu * nx0, mu * nxo) < b.rtol);
+    if (conv) {
+      done = 1;
+      break;
+    }
+    if (this_it % b.interval_update_mu == 0) {
+      double m2 = mu;
+      if (primal > b.th_change * dual) m2 *= b.fact_incr;
+      if (dual > b.th_change * primal) m2 /= b.fact_incr;
+      m2 = fmin(m2, b.max_mu);
+      if (m2 != mu) {
+        mu = m2;
+        need = 1;
+        break;
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int n = tid; n < N; n += BP_THREADS) {
+    b.x0[(size_t)prob * N + n] = x0[n];
+    b.x1[(size_t)prob * N + n] = x1[n];
+    b.h[(size_t)prob * N + n] = h[n];
+  }
+  if (tid == 0) {
+    b.mu[prob] = mu;
+    b.iters[prob] = it;
+    b.done[prob] = done;
+    b.need_factor[prob] = need;
+    b.last_res[2 * prob] = primal;
+    b.last_res[2 * prob + 1] = dual;
+  }
+}
+
+static int check_bp(const admm_bp_buffers* b, const char* who) {
+  ADMM_REQUIRE(b != nullptr, ADMM_EINVAL, "%s: null buffers", who);
+  ADMM_REQUIRE(b->nb >= 1 && b->M >= 1 && b->N >= 1, ADMM_EINVAL, "%s: bad dims", who);
+  ADMM_REQUIRE(b->nk == (b->woodbury ? b->M : b->N), ADMM_EINVAL, "%s: nk inconsistent with woodbury flag", who);
+  ADMM_REQUIRE(b->interval_update_mu >= 1, ADMM_EINVAL, "%s: interval_update_mu must be >= 1", who);
+  return ADMM_OK;
+}
+
+static size_t bp_smem_bytes(const admm_bp_buffers* b) { return (size_t)(6 * b->N + 2 * b->nk + 5 * 32) * sizeof(double); }
+
+}  // namespace admm
+
+using namespace admm;
+
+extern "C" {
+
+int admm_bp_setup(const admm_bp_buffers* b, const double* y, double* aty, double* gram, admm_stream_t stream) {
+  if (int rc = check_bp(b, "admm_bp_setup")) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ADMM_REQUIRE(b->nb <= 65535 * 1024, ADMM_EINVAL, "admm_bp_setup: batch too large");
+  for (int p0 = 0; p0 < b->nb; p0 += 65535) {
+    admm_bp_buffers bb = *b;
+    const int cnt = std::min(65535, b->nb - p0);
+    bb.A = b->A + (size_t)p0 * b->M * b->N;
+    dim3 g1(ceil_div(b->N, 256), cnt);
+    bp_aty_kernel<<<g1, 256, 0, s>>>(bb, y + (size_t)p0 * b->M, aty + (size_t)p0 * b->N);
+    const int tiles = ceil_div(b->nk, 32);
+    dim3 g2(tiles, tiles, cnt);
+    double* gp = gram + (size_t)p0 * b->nk * b->nk;
+    if (b->woodbury) bp_gram_kernel<true><<<g2, 256, 0, s>>>(bb, gp);
+    else bp_gram_kernel<false><<<g2, 256, 0, s>>>(bb, gp);
+  }
+  return check_launch("admm_bp_setup");
+}
+
+int admm_bp_factor(const admm_bp_buffers* b, int* info, admm_stream_t stream) {
+  if (int rc = check_bp(b, "admm_bp_factor")) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nk = b->nk;
+  for (int p0 = 0; p0 < b->nb; p0 += 65535) {
+    admm_bp_buffers bb = *b;
+    const int cnt = std::min(65535, b->nb - p0);
+    bb.need_factor = b->need_factor + p0;
+    bb.mu = b->mu + p0;
+    bb.gram = b->gram + (size_t)p0 * nk * nk;
+    bb.Kinv = b->Kinv + (size_t)p0 * nk * nk;
+    dim3 g(std::max(1, std::min(8, ceil_div(nk * nk, 256))), cnt);
+    bp_shift_kernel<<<g, 256, 0, s>>>(bb);
+  }
+  if (int rc = check_launch("admm_bp_factor(shift)")) return rc;
+  if (int rc = admm_spd_inverse_batched(nk, b->nb, b->Kinv, (long long)nk * nk, nk, b->need_factor, info, stream)) return rc;
+  bp_clear_flag_kernel<<<ceil_div(b->nb, 256), 256, 0, s>>>(*b);
+  return check_launch("admm_bp_factor");
+}
+
+int admm_bp_iterate(const admm_bp_buffers* b, int iter_end, admm_stream_t stream) {
+  if (int rc = check_bp(b, "admm_bp_iterate")) return rc;
+  const size_t smem = bp_smem_bytes(b);
+  ADMM_REQUIRE(smem <= 220 * 1024, ADMM_EUNSUPPORTED, "admm_bp_iterate: N=%d too large for the shared-memory resident path", b->N);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaFuncSetAttribute(bp_iterate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  bp_iterate_kernel<<<b->nb, BP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(*b, iter_end);
+  return check_launch("admm_bp_iterate");
+}
+
+}  // extern "C"

@@ -1,0 +1,449 @@
+// Structured-matrix primitives of the generic executor (FP64 / complex128).
+// These are the device replacements of the NumPy calls in the reference's matrix.py and of the
+// vector algebra in optimizer.py; the two fused engines (spm.cu, bp.cu) carry the hot paths.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+
+namespace admm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return ADMM_ECUDA;
+  }
+  return ADMM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// complex helpers
+// ---------------------------------------------------------------------------------------------
+struct cplx {
+  double x, y;
+};
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ cplx cconj(cplx a) { return {a.x, -a.y}; }
+__device__ __forceinline__ double cabs2(cplx a) { return a.x * a.x + a.y * a.y; }
+__device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
+  // Smith's algorithm (what NumPy/LAPACK use) to avoid overflow
+  if (fabs(b.x) >= fabs(b.y)) {
+    double r = b.y / b.x, den = b.x + b.y * r;
+    return {(a.x + a.y * r) / den, (a.y - a.x * r) / den};
+  } else {
+    double r = b.x / b.y, den = b.y + b.x * r;
+    return {(a.x * r + a.y) / den, (a.y * r - a.x) / den};
+  }
+}
+
+template <typename T> struct num;
+template <> struct num<double> {
+  static __device__ __forceinline__ double zero() { return 0.0; }
+  static __device__ __forceinline__ double one() { return 1.0; }
+  static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
+  static __device__ __forceinline__ double add(double a, double b) { return a + b; }
+  static __device__ __forceinline__ double sub(double a, double b) { return a - b; }
+  static __device__ __forceinline__ double div(double a, double b) { return a / b; }
+  static __device__ __forceinline__ double conj(double a) { return a; }
+  static __device__ __forceinline__ double abs2(double a) { return a * a; }
+};
+template <> struct num<cplx> {
+  static __device__ __forceinline__ cplx zero() { return {0.0, 0.0}; }
+  static __device__ __forceinline__ cplx one() { return {1.0, 0.0}; }
+  static __device__ __forceinline__ cplx mul(cplx a, cplx b) { return cmul(a, b); }
+  static __device__ __forceinline__ cplx add(cplx a, cplx b) { return cadd(a, b); }
+  static __device__ __forceinline__ cplx sub(cplx a, cplx b) { return csub(a, b); }
+  static __device__ __forceinline__ cplx div(cplx a, cplx b) { return cdiv(a, b); }
+  static __device__ __forceinline__ cplx conj(cplx a) { return cconj(a); }
+  static __device__ __forceinline__ double abs2(cplx a) { return cabs2(a); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// GEMM: C = op(A) B, 32x32 output tile, 32-deep K slabs in shared memory, 256 threads
+// ---------------------------------------------------------------------------------------------
+template <typename T, int OP>
+__global__ void __launch_bounds__(256) gemm_kernel(int m, int n, int k, const T* __restrict__ A, int lda,
+                                                   const T* __restrict__ B, int ldb, T* __restrict__ C, int ldc) {
+  __shared__ T As[32][33];
+  __shared__ T Bs[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // ty in 0..7
+  const int row0 = blockIdx.y * 32, col0 = blockIdx.x * 32;
+  T acc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] = num<T>::zero();
+  for (int k0 = 0; k0 < k; k0 += 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty + 8 * i;
+      // As[r][tx] = op(A)[row0 + r][k0 + tx]
+      T a = num<T>::zero();
+      if (OP == ADMM_OP_N) {
+        if (row0 + r < m && k0 + tx < k) a = A[(size_t)(row0 + r) * lda + k0 + tx];
+        As[r][tx] = a;
+      } else {
+        // stored k x m: element op(A)[i][kk] = A[kk][i]; read coalesced along i
+        if (k0 + r < k && row0 + tx < m) a = A[(size_t)(k0 + r) * lda + row0 + tx];
+        if (OP == ADMM_OP_H) a = num<T>::conj(a);
+        As[tx][r] = a;
+      }
+      T b = num<T>::zero();
+      if (k0 + r < k && col0 + tx < n) b = B[(size_t)(k0 + r) * ldb + col0 + tx];
+      Bs[r][tx] = b;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < 32; ++kk) {
+      const T b = Bs[kk][tx];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = num<T>::add(acc[i], num<T>::mul(As[ty + 8 * i][kk], b));
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row0 + ty + 8 * i, c = col0 + tx;
+    if (r < m && c < n) C[(size_t)r * ldc + c] = acc[i];
+  }
+}
+
+template <typename T>
+static int launch_gemm(int op, int m, int n, int k, const void* A, int lda, const void* B, int ldb, void* C,
+                       int ldc, cudaStream_t s) {
+  dim3 grid(ceil_div(n, 32), ceil_div(m, 32));
+  const T* a = static_cast<const T*>(A);
+  const T* b = static_cast<const T*>(B);
+  T* c = static_cast<T*>(C);
+  if (op == ADMM_OP_N)
+    gemm_kernel<T, ADMM_OP_N><<<grid, 256, 0, s>>>(m, n, k, a, lda, b, ldb, c, ldc);
+  else if (op == ADMM_OP_T)
+    gemm_kernel<T, ADMM_OP_T><<<grid, 256, 0, s>>>(m, n, k, a, lda, b, ldb, c, ldc);
+  else
+    gemm_kernel<T, ADMM_OP_H><<<grid, 256, 0, s>>>(m, n, k, a, lda, b, ldb, c, ldc);
+  return check_launch("admm_gemm");
+}
+
+// ---------------------------------------------------------------------------------------------
+// elementwise kernels
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void diag_mul_kernel(int rows_out, int nd, int ncols, const T* __restrict__ d, const T* __restrict__ V,
+                                int ldv, T* __restrict__ out, int ldo) {
+  const long long total = (long long)rows_out * ncols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = int(idx / ncols), j = int(idx % ncols);
+    T v = num<T>::zero();
+    if (i < nd) v = num<T>::mul(d[i], V[(size_t)i * ldv + j]);
+    out[(size_t)i * ldo + j] = v;
+  }
+}
+
+__global__ void axpby_kernel(long long n, double a, const double* x, double b,
+                             const double* y, double* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double v = a * x[i];
+    if (y) v += b * y[i];
+    out[i] = v;
+  }
+}
+
+__global__ void prox_l1_kernel(long long n, const double* __restrict__ h, int hs, const double* __restrict__ mud,
+                               double alpha, double* __restrict__ out, int os) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double mu = mud[i];
+    const double y = -(h[i * hs] / mu);
+    const double lam = 0.5 * alpha / mu;
+    double r = 0.0;
+    if (y > lam) r = y - lam;
+    if (y < -lam) r = y + lam;
+    out[i * os] = r;
+    if (os == 2) out[i * 2 + 1] = 0.0;
+  }
+}
+
+__global__ void prox_nonneg_kernel(long long n, const double* __restrict__ h, int hs, const double* __restrict__ mud,
+                                   double* __restrict__ out, int os) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double v = -(h[i * hs] / mud[i]);
+    if (v < 0) v = 0.0;
+    out[i * os] = v;
+    if (os == 2) out[i * 2 + 1] = 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(256) sumsq_stage1(long long n, const double* __restrict__ x,
+                                                    const double* __restrict__ y, double* __restrict__ part) {
+  __shared__ double scratch[32];
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long b0 = per * blockIdx.x, b1 = min(n, b0 + per);
+  double v[1] = {0.0};
+  for (long long i = b0 + threadIdx.x; i < b1; i += blockDim.x) {
+    double t = x[i];
+    if (y) t -= y[i];
+    v[0] += t * t;
+  }
+  block_sum<1>(v, scratch);
+  if (threadIdx.x == 0) part[blockIdx.x] = v[0];
+}
+
+__global__ void __launch_bounds__(256) sumsq_stage2(int nparts, const double* __restrict__ part, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  double v[1] = {0.0};
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) v[0] += part[i];
+  block_sum<1>(v, scratch);
+  if (threadIdx.x == 0) out[0] = v[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// general inverse: Gauss-Jordan with partial pivoting on the augmented matrix [A | I], one CTA
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024) inverse_kernel(int n, const T* __restrict__ A, int lda, T* __restrict__ Ainv,
+                                                       int ldi, T* __restrict__ W, int* __restrict__ info) {
+  extern __shared__ unsigned char smem_raw[];
+  T* colk = reinterpret_cast<T*>(smem_raw);  // n
+  __shared__ double s_best[32];
+  __shared__ int s_idx[32];
+  __shared__ int s_piv;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int w2 = 2 * n;
+  for (int idx = tid; idx < n * w2; idx += nt) {
+    const int i = idx / w2, j = idx % w2;
+    T v = num<T>::zero();
+    if (j < n) v = A[(size_t)i * lda + j];
+    else if (j - n == i) v = num<T>::one();
+    W[idx] = v;
+  }
+  if (tid == 0) info[0] = 0;
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    // pivot search: argmax |W[i][k]|, i >= k (ties -> smallest i, as LAPACK's idamax)
+    double best = -1.0;
+    int bi = k;
+    for (int i = k + tid; i < n; i += nt) {
+      const double a = num<T>::abs2(W[(size_t)i * w2 + k]);
+      if (a > best) { best = a; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if ((tid & 31) == 0) { s_best[tid >> 5] = best; s_idx[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      double b = s_best[0];
+      int ix = s_idx[0];
+      for (int w = 1; w < (nt + 31) / 32; ++w)
+        if (s_best[w] > b || (s_best[w] == b && s_idx[w] < ix)) { b = s_best[w]; ix = s_idx[w]; }
+      s_piv = ix;
+      if (!(b > 0.0)) info[0] = k + 1;
+    }
+    __syncthreads();
+    const int p = s_piv;
+    if (p != k) {
+      for (int j = tid; j < w2; j += nt) {
+        const T a = W[(size_t)k * w2 + j];
+        W[(size_t)k * w2 + j] = W[(size_t)p * w2 + j];
+        W[(size_t)p * w2 + j] = a;
+      }
+    }
+    __syncthreads();
+    const T piv = W[(size_t)k * w2 + k];
+    for (int i = tid; i < n; i += nt) colk[i] = W[(size_t)i * w2 + k];
+    __syncthreads();
+    for (int j = tid; j < w2; j += nt) W[(size_t)k * w2 + j] = num<T>::div(W[(size_t)k * w2 + j], piv);
+    __syncthreads();
+    // eliminate column k from every other row; columns < k of the left half are already e_j
+    for (int idx = tid; idx < n * (w2 - k); idx += nt) {
+      const int i = idx / (w2 - k), j = k + idx % (w2 - k);
+      if (i == k) continue;
+      const size_t o = (size_t)i * w2 + j;
+      W[o] = num<T>::sub(W[o], num<T>::mul(colk[i], W[(size_t)k * w2 + j]));
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < n * n; idx += nt) {
+    const int i = idx / n, j = idx % n;
+    Ainv[(size_t)i * ldi + j] = W[(size_t)i * w2 + n + j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched in-place inverse of real SPD matrices (Gauss-Jordan without pivoting), one CTA each
+// ---------------------------------------------------------------------------------------------
+template <bool IN_SMEM>
+__global__ void __launch_bounds__(512) spd_inverse_kernel(int n, double* __restrict__ Aall, long long bstride, int lda,
+                                                          const int* __restrict__ mask, int* __restrict__ info) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.x;
+  if (mask && mask[b] == 0) return;
+  double* Ag = Aall + (size_t)b * bstride;
+  double* rowk = sm;          // n
+  double* colk = sm + n;      // n
+  double* a = IN_SMEM ? (sm + 2 * n) : Ag;
+  const int ld = IN_SMEM ? n : lda;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (IN_SMEM) {
+    for (int idx = tid; idx < n * n; idx += nt) a[idx] = Ag[(size_t)(idx / n) * lda + idx % n];
+  }
+  __syncthreads();
+  int bad = 0;
+  for (int k = 0; k < n; ++k) {
+    const double p = a[(size_t)k * ld + k];
+    if (!(p > 0.0)) bad = k + 1;
+    const double ip = 1.0 / p;
+    for (int j = tid; j < n; j += nt) {
+      rowk[j] = (j == k ? 1.0 : a[(size_t)k * ld + j]) * ip;
+      colk[j] = (j == k ? 0.0 : a[(size_t)j * ld + k]);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += nt) {
+      const int i = idx / n, j = idx - i * n;
+      const size_t o = (size_t)i * ld + j;
+      if (i == k) {
+        a[o] = rowk[j];
+      } else {
+        const double base = (j == k) ? 0.0 : a[o];
+        a[o] = base - colk[i] * rowk[j];
+      }
+    }
+    __syncthreads();
+  }
+  if (IN_SMEM) {
+    // symmetrise (the exact inverse is symmetric; rounding is not) and write back
+    for (int idx = tid; idx < n * n; idx += nt) {
+      const int i = idx / n, j = idx - i * n;
+      Ag[(size_t)i * lda + j] = 0.5 * (a[(size_t)i * n + j] + a[(size_t)j * n + i]);
+    }
+  }
+  if (tid == 0 && info) info[b] = bad;
+}
+
+}  // namespace admm
+
+using namespace admm;
+
+extern "C" {
+
+int admm_abi_version(void) { return ADMM_ABI_VERSION; }
+
+const char* admm_last_error(void) { return admm::g_err; }
+
+int admm_device_info(int* sm_count, int* cc_major, int* cc_minor, int* smem_optin_bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDevice: %s", cudaGetErrorString(e));
+    return ADMM_ECUDA;
+  }
+  cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev);
+  cudaDeviceGetAttribute(smem_optin_bytes, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  return ADMM_OK;
+}
+
+int admm_gemm(int is_complex, int op_a, int m, int n, int k, const void* A, int lda, const void* B, int ldb,
+              void* C, int ldc, admm_stream_t stream) {
+  ADMM_REQUIRE(m >= 0 && n >= 0 && k >= 0 && op_a >= 0 && op_a <= 2, ADMM_EINVAL, "admm_gemm: bad dims/op");
+  if (m == 0 || n == 0) return ADMM_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return is_complex ? launch_gemm<cplx>(op_a, m, n, k, A, lda, B, ldb, C, ldc, s)
+                    : launch_gemm<double>(op_a, m, n, k, A, lda, B, ldb, C, ldc, s);
+}
+
+static int ew_grid(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 16)); }
+
+int admm_diag_mul(int is_complex, int rows_out, int nd, int ncols, const void* d, const void* V, int ldv, void* out,
+                  int ldo, admm_stream_t stream) {
+  ADMM_REQUIRE(rows_out >= 0 && nd >= 0 && ncols >= 0, ADMM_EINVAL, "admm_diag_mul: bad dims");
+  if (rows_out == 0 || ncols == 0) return ADMM_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int g = ew_grid((long long)rows_out * ncols);
+  if (is_complex)
+    diag_mul_kernel<cplx><<<g, 256, 0, s>>>(rows_out, nd, ncols, (const cplx*)d, (const cplx*)V, ldv, (cplx*)out, ldo);
+  else
+    diag_mul_kernel<double><<<g, 256, 0, s>>>(rows_out, nd, ncols, (const double*)d, (const double*)V, ldv,
+                                               (double*)out, ldo);
+  return check_launch("admm_diag_mul");
+}
+
+int admm_axpby(long long n, double a, const double* x, double b, const double* y, double* out, admm_stream_t stream) {
+  if (n <= 0) return ADMM_OK;
+  axpby_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, a, x, b, y, out);
+  return check_launch("admm_axpby");
+}
+
+int admm_prox_l1(long long n, const double* h, int h_stride, const double* mu_diag, double alpha, double* out,
+                 int out_stride, admm_stream_t stream) {
+  ADMM_REQUIRE(alpha > 0, ADMM_EINVAL, "admm_prox_l1: alpha must be > 0");
+  if (n <= 0) return ADMM_OK;
+  prox_l1_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, h, h_stride, mu_diag, alpha, out,
+                                                                           out_stride);
+  return check_launch("admm_prox_l1");
+}
+
+int admm_prox_nonneg(long long n, const double* h, int h_stride, const double* mu_diag, double* out, int out_stride,
+                     admm_stream_t stream) {
+  if (n <= 0) return ADMM_OK;
+  prox_nonneg_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, h, h_stride, mu_diag, out,
+                                                                               out_stride);
+  return check_launch("admm_prox_nonneg");
+}
+
+int admm_sumsq(long long n, const double* x, const double* y, double* out, double* scratch, admm_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int parts = (int)std::max<long long>(1, std::min<long long>((n + 4095) / 4096, 1024));
+  sumsq_stage1<<<parts, 256, 0, s>>>(n, x, y, scratch);
+  sumsq_stage2<<<1, 256, 0, s>>>(parts, scratch, out);
+  return check_launch("admm_sumsq");
+}
+
+int admm_inverse(int is_complex, int n, const void* A, int lda, void* Ainv, int ldi, void* work, int* info,
+                 admm_stream_t stream) {
+  ADMM_REQUIRE(n > 0 && n <= 2048, ADMM_EINVAL, "admm_inverse: n=%d out of range (1..2048)", n);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int threads = n <= 32 ? 256 : 1024;
+  if (is_complex)
+    inverse_kernel<cplx><<<1, threads, n * sizeof(cplx), s>>>(n, (const cplx*)A, lda, (cplx*)Ainv, ldi, (cplx*)work, info);
+  else
+    inverse_kernel<double><<<1, threads, n * sizeof(double), s>>>(n, (const double*)A, lda, (double*)Ainv, ldi,
+                                                                  (double*)work, info);
+  return check_launch("admm_inverse");
+}
+
+int admm_spd_inverse_batched(int n, int nbatch, double* A, long long batch_stride, int lda, const int* mask, int* info,
+                             admm_stream_t stream) {
+  ADMM_REQUIRE(n > 0 && n <= 4096 && nbatch >= 0 && lda >= n, ADMM_EINVAL, "admm_spd_inverse_batched: bad dims");
+  if (nbatch == 0) return ADMM_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (n <= 128) {
+    const size_t smem = (size_t)(n * n + 2 * n) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(spd_inverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
+      attr_set = true;
+    }
+    const int threads = n <= 16 ? 64 : (n <= 48 ? 256 : 512);
+    spd_inverse_kernel<true><<<nbatch, threads, smem, s>>>(n, A, batch_stride, lda, mask, info);
+  } else {
+    spd_inverse_kernel<false><<<nbatch, 512, 2 * n * sizeof(double), s>>>(n, A, batch_stride, lda, mask, info);
+  }
+  return check_launch("admm_spd_inverse_batched");
+}
+
+}  // extern "C"

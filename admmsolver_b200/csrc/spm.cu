@@ -1,0 +1,819 @@
+// Pattern B engine (SpM): many problems sharing s, P, C.   See include/admm_b200.h and DESIGN.md.
+//
+// One ADMM iteration is   xupdate  ->  pass  -> [reduce] -> decide .
+//   * pass streams the implicit (h20, x2) state once (16 B read + 16 B written per sampling point
+//     and complex problem) and runs both skinny GEMMs (Q = P x0, V = P^T u) on the FP64 tensor
+//     cores (mma.sync m8n8k4 -> SASS DMMA.8x8x4) chained through registers;
+//   * xupdate does the L x L work (cached inverse, KKT correction, soft threshold, dual ascent);
+//   * decide evaluates residual()/check_convergence()/update_mu() on device.
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace admm {
+
+// ---------------------------------------------------------------------------------------------
+// layout helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t frag_index(int ct, int NT, int j, int lane) {
+  return ((size_t)(ct * NT + j) * 32 + lane) * 2;
+}
+
+__global__ void prepare_P_kernel(admm_spm_dims d, const double* __restrict__ P, int ldP, double* __restrict__ Psw) {
+  const long long total = (long long)d.nrt * 8 * d.ldp;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = int(idx / d.ldp), c = int(idx % d.ldp);
+    const int l = c ^ p_swz(r);
+    double v = 0.0;
+    if (r < d.Nw && l < d.L) v = P[(size_t)r * ldP + l];
+    Psw[idx] = v;
+  }
+}
+
+// canonical (L x nb) -> fragment layout
+__global__ void pack_L_kernel(admm_spm_dims d, const double* __restrict__ canon, int src_cplx, double* __restrict__ frag) {
+  const int NT = d.Lp / 8;
+  const long long total = (long long)d.npt * d.nplanes * NT * 64;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int e = int(idx & 1), lane = int((idx >> 1) & 31);
+    const long long q = idx >> 6;
+    const int j = int(q % NT), ct = int(q / NT);
+    const int pt = ct / d.nplanes, pl = ct % d.nplanes;
+    const int g = lane >> 2, t = lane & 3;
+    const int l = 8 * j + 2 * t + e, prob = 8 * pt + g;
+    double v = 0.0;
+    if (l < d.L && prob < d.nb) {
+      const size_t o = (size_t)l * d.nb + prob;
+      if (src_cplx) v = canon[2 * o + pl];
+      else if (pl == 0) v = canon[o];
+    }
+    frag[idx] = v;
+  }
+}
+
+__global__ void unpack_L_kernel(admm_spm_dims d, const double* __restrict__ frag, double* __restrict__ canon, int dst_cplx) {
+  const int NT = d.Lp / 8;
+  const long long total = (long long)d.L * d.nb;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int l = int(idx / d.nb), prob = int(idx % d.nb);
+    const int pt = prob >> 3, g = prob & 7;
+    const int j = l >> 3, t = (l & 7) >> 1, e = l & 1;
+    const int lane = 4 * g + t;
+    const double re = frag[frag_index(pt * d.nplanes, NT, j, lane) + e];
+    const double im = d.nplanes == 2 ? frag[frag_index(pt * d.nplanes + 1, NT, j, lane) + e] : 0.0;
+    if (dst_cplx) {
+      canon[2 * idx] = re;
+      canon[2 * idx + 1] = im;
+    } else {
+      canon[idx] = re;
+    }
+  }
+}
+
+__device__ __forceinline__ size_t state_index(const admm_spm_dims& d, int pt, int rt, int pl, int lane) {
+  return ((((size_t)pt * d.nrt + rt) * d.nplanes + pl) * 32 + lane) * 2;
+}
+
+__global__ void pack_state_kernel(admm_spm_dims d, const double* __restrict__ h20, const double* __restrict__ x2,
+                                  int src_cplx, const double* __restrict__ mu20, double* __restrict__ S,
+                                  int* __restrict__ flag) {
+  const long long total = (long long)d.npt * d.nrt * d.nplanes * 64;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int e = int(idx & 1), lane = int((idx >> 1) & 31);
+    long long q = idx >> 6;
+    const int pl = int(q % d.nplanes);
+    q /= d.nplanes;
+    const int rt = int(q % d.nrt), pt = int(q / d.nrt);
+    const int g = lane >> 2, t = lane & 3;
+    const int r = 8 * rt + 2 * t + e, prob = 8 * pt + g;
+    double v = 0.0;
+    if (r < d.Nw && prob < d.nb) {
+      const size_t o = (size_t)r * d.nb + prob;
+      const double hre = src_cplx ? h20[2 * o] : h20[o];
+      const double him = src_cplx ? h20[2 * o + 1] : 0.0;
+      const double xre = src_cplx ? x2[2 * o] : x2[o];
+      const double xim = src_cplx ? x2[2 * o + 1] : 0.0;
+      if (pl == 0) {
+        v = hre - mu20[prob] * xre;
+        if (xre < 0.0 || xim != 0.0 || hre < 0.0 || (hre != 0.0 && xre != 0.0)) flag[0] = 1;
+        if (d.nplanes == 1 && him != 0.0) flag[0] = 1;
+      } else {
+        v = him;
+      }
+    }
+    S[idx] = v;
+  }
+}
+
+__global__ void unpack_state_kernel(admm_spm_dims d, const double* __restrict__ S, const double* __restrict__ mu20_used,
+                                    double* __restrict__ h20, double* __restrict__ x2, int dst_cplx) {
+  const long long total = (long long)d.Nw * d.nb;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = int(idx / d.nb), prob = int(idx % d.nb);
+    const int pt = prob >> 3, g = prob & 7, rt = r >> 3, t = (r & 7) >> 1, e = r & 1;
+    const int lane = 4 * g + t;
+    const double s = S[state_index(d, pt, rt, 0, lane) + e];
+    const double him = d.nplanes == 2 ? S[state_index(d, pt, rt, 1, lane) + e] : 0.0;
+    const double hre = s > 0.0 ? s : 0.0;
+    const double xv = s < 0.0 ? (-s) / mu20_used[prob] : 0.0;
+    if (dst_cplx) {
+      h20[2 * idx] = hre;
+      h20[2 * idx + 1] = him;
+      x2[2 * idx] = xv;
+      x2[2 * idx + 1] = 0.0;
+    } else {
+      h20[idx] = hre;
+      x2[idx] = xv;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// factor: Ginv = (G0 + mu10 I + mu20 PtP)^-1 by in-place Gauss-Jordan in shared memory
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) spm_factor_kernel(admm_spm_dims d, const int* __restrict__ slots,
+                                                         const double* __restrict__ mu10s, const double* __restrict__ mu20s,
+                                                         const double* __restrict__ G0, const double* __restrict__ PtP,
+                                                         const double* __restrict__ Cvec, double* __restrict__ Ginv_cache,
+                                                         double* __restrict__ w_cache, double* __restrict__ sigma_cache,
+                                                         int* __restrict__ info) {
+  extern __shared__ double sm[];
+  const int n = d.L, Lp = d.Lp;
+  double* a = sm;               // n x n
+  double* rowk = a + n * n;     // n
+  double* colk = rowk + n;      // n
+  double* wv = colk + n;        // n
+  __shared__ double red[32];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int slot = slots[blockIdx.x];
+  const double mu10 = mu10s[blockIdx.x], mu20 = mu20s[blockIdx.x];
+  for (int idx = tid; idx < n * n; idx += nt) {
+    const int i = idx / n, j = idx - i * n;
+    a[idx] = G0[(size_t)i * Lp + j] + (i == j ? mu10 : 0.0) + mu20 * PtP[(size_t)i * Lp + j];
+  }
+  __syncthreads();
+  int bad = 0;
+  for (int k = 0; k < n; ++k) {
+    const double p = a[k * n + k];
+    if (!(p > 0.0)) bad = k + 1;
+    const double ip = 1.0 / p;
+    for (int j = tid; j < n; j += nt) {
+      rowk[j] = (j == k ? 1.0 : a[k * n + j]) * ip;
+      colk[j] = (j == k ? 0.0 : a[j * n + k]);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += nt) {
+      const int i = idx / n, j = idx - i * n;
+      if (i == k) {
+        a[idx] = rowk[j];
+      } else {
+        const double base = (j == k) ? 0.0 : a[idx];
+        a[idx] = base - colk[i] * rowk[j];
+      }
+    }
+    __syncthreads();
+  }
+  double* Gi = Ginv_cache + (size_t)slot * Lp * Lp;
+  for (int idx = tid; idx < Lp * Lp; idx += nt) {
+    const int i = idx / Lp, j = idx - i * Lp;
+    Gi[idx] = (i < n && j < n) ? 0.5 * (a[i * n + j] + a[j * n + i]) : 0.0;
+  }
+  __syncthreads();
+  // w = Ginv C^T (symmetrised Ginv), sigma = C w
+  for (int i = tid; i < n; i += nt) {
+    double acc = 0.0;
+    for (int j = 0; j < n; ++j) acc += 0.5 * (a[i * n + j] + a[j * n + i]) * Cvec[j];
+    wv[i] = acc;
+  }
+  __syncthreads();
+  for (int i = tid; i < Lp; i += nt) w_cache[(size_t)slot * Lp + i] = i < n ? wv[i] : 0.0;
+  double v[1] = {0.0};
+  for (int i = tid; i < n; i += nt) v[0] += Cvec[i] * wv[i];
+  block_sum<1>(v, red);
+  if (tid == 0) {
+    sigma_cache[slot] = v[0];
+    if (info) info[blockIdx.x] = bad;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// x-update: one warp per tile of 8 real columns, everything in fragment layout
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ void frag_gemm(double (&out)[NT][2], const double (&a)[NT][2], const double* __restrict__ Bm,
+                                          int ldb, int g, int t) {
+  // out[c][l'] = sum_l a[c][l] * Bm[l][l'],  k-slot (jk,e): l = 8*jk + 2*t + e
+#pragma unroll
+  for (int jn = 0; jn < NT; ++jn) out[jn][0] = out[jn][1] = 0.0;
+#pragma unroll
+  for (int jk = 0; jk < NT; ++jk) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const double* brow = Bm + (size_t)(8 * jk + 2 * t + e) * ldb + g;
+#pragma unroll
+      for (int jn = 0; jn < NT; ++jn) dmma(out[jn][0], out[jn][1], a[jk][e], __ldg(brow + 8 * jn));
+    }
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(128) spm_xupdate_kernel(admm_spm_dims d, admm_spm_buffers b, int v_split) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nct = d.npt * d.nplanes;
+  if (warp >= nct) return;
+  const int ct = warp, pt = ct / d.nplanes, pl = ct % d.nplanes;
+  const int prob = 8 * pt + g;
+  const int is_done = b.done[prob];
+  if (__all_sync(0xffffffffu, is_done)) return;
+  const double mu10 = b.mu10[prob], mu20 = b.mu20[prob];
+  const int slot = b.slot[prob];
+  const int Lp = d.Lp;
+  const size_t vstride = (size_t)nct * NT * 64;
+
+  double rhs[NT][2], x0o[NT][2], h10[NT][2];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const size_t o = frag_index(ct, NT, j, lane);
+    const double2 b0 = *reinterpret_cast<const double2*>(b.b0 + o);
+    const double2 hh = *reinterpret_cast<const double2*>(b.h10 + o);
+    const double2 x1 = *reinterpret_cast<const double2*>(b.x1 + o);
+    const double2 xo = *reinterpret_cast<const double2*>(b.x0 + o);
+    double2 v = make_double2(0.0, 0.0);
+    for (int sp = 0; sp < d.nsplit; ++sp) {
+      const double2 p = *reinterpret_cast<const double2*>(b.V + sp * vstride + o);
+      v.x += p.x;
+      v.y += p.y;
+    }
+    if (v_split && pl == 0) {
+      double2 vx = make_double2(0.0, 0.0);
+      for (int sp = 0; sp < d.nsplit; ++sp) {
+        const double2 p = *reinterpret_cast<const double2*>(b.Vx + sp * vstride + o);
+        vx.x += p.x;
+        vx.y += p.y;
+      }
+      v.x += mu20 * vx.x;
+      v.y += mu20 * vx.y;
+    }
+    rhs[j][0] = b0.x + hh.x + mu10 * x1.x + v.x;
+    rhs[j][1] = b0.y + hh.y + mu10 * x1.y + v.y;
+    x0o[j][0] = xo.x;
+    x0o[j][1] = xo.y;
+    h10[j][0] = hh.x;
+    h10[j][1] = hh.y;
+  }
+
+  // xi1 = Ginv rhs, one tensor-core GEMM per distinct factor slot in the tile
+  double xi[NT][2];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) xi[j][0] = xi[j][1] = 0.0;
+  unsigned remaining = __ballot_sync(0xffffffffu, !is_done);
+  while (remaining) {
+    const int leader = __ffs(remaining) - 1;
+    const int cur = __shfl_sync(0xffffffffu, slot, leader);
+    const bool match = (!is_done) && (slot == cur);
+    double acc[NT][2];
+    frag_gemm<NT>(acc, rhs, b.Ginv_cache + (size_t)cur * Lp * Lp, Lp, g, t);
+    if (match) {
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        xi[j][0] = acc[j][0];
+        xi[j][1] = acc[j][1];
+      }
+    }
+    remaining &= ~__ballot_sync(0xffffffffu, match);
+  }
+
+  // KKT correction enforcing C x0 = D   (objectivefunc.py:148-157)
+  double cxi = 0.0;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    cxi += b.Cvec[8 * j + 2 * t] * xi[j][0] + b.Cvec[8 * j + 2 * t + 1] * xi[j][1];
+  }
+  cxi = quad_sum(cxi);
+  const double sigma = b.sigma_cache[slot];
+  const double Dv = b.Dre[(size_t)pl * 8 * d.npt + prob];
+  const double nu = (Dv - cxi) / sigma;
+  double x0[NT][2], dd[NT][2];
+  const double* wv = b.w_cache + (size_t)slot * Lp;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      x0[j][e] = xi[j][e] + wv[8 * j + 2 * t + e] * nu;
+      dd[j][e] = x0[j][e] - x0o[j][e];
+    }
+  }
+
+  // Gram-form norms of pair (2,0):  |P d|^2 = d^T (P^T P) d,  |P x0_old|^2
+  double nPd, nPxo;
+  {
+    double y[NT][2];
+    frag_gemm<NT>(y, dd, b.PtP, Lp, g, t);
+    nPd = 0.0;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) nPd += y[j][0] * dd[j][0] + y[j][1] * dd[j][1];
+    frag_gemm<NT>(y, x0o, b.PtP, Lp, g, t);
+    nPxo = 0.0;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) nPxo += y[j][0] * x0o[j][0] + y[j][1] * x0o[j][1];
+  }
+
+  // L1 z-update (real plane only; the imaginary part of x1 is identically zero) + dual ascent
+  const double thr = 0.5 * b.lam / mu10;
+  double n_p = 0.0, n_x0 = 0.0, n_x1 = 0.0, n_d = 0.0, n_xo = 0.0;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    double2 x1n, hn, x0n;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const double xv = x0[j][e], hv = h10[j][e];
+      double z = 0.0;
+      if (pl == 0) {
+        const double yv = -((hv - mu10 * xv) / mu10);
+        if (yv > thr) z = yv - thr;
+        if (yv < -thr) z = yv + thr;
+      }
+      const double hnew = hv + mu10 * (z - xv);
+      n_p += (xv - z) * (xv - z);
+      n_x0 += xv * xv;
+      n_x1 += z * z;
+      n_d += dd[j][e] * dd[j][e];
+      n_xo += x0o[j][e] * x0o[j][e];
+      if (e == 0) { x1n.x = z; hn.x = hnew; x0n.x = xv; }
+      else { x1n.y = z; hn.y = hnew; x0n.y = xv; }
+    }
+    if (!is_done) {
+      const size_t o = frag_index(ct, NT, j, lane);
+      *reinterpret_cast<double2*>(b.x0 + o) = x0n;
+      *reinterpret_cast<double2*>(b.x1 + o) = x1n;
+      *reinterpret_cast<double2*>(b.h10 + o) = hn;
+    }
+  }
+  n_p = quad_sum(n_p);
+  n_x0 = quad_sum(n_x0);
+  n_x1 = quad_sum(n_x1);
+  n_d = quad_sum(n_d);
+  n_xo = quad_sum(n_xo);
+  nPd = quad_sum(nPd);
+  nPxo = quad_sum(nPxo);
+  if (t == 0 && !is_done) {
+    double* o = b.normsA + ((size_t)ct * 8 + g) * 8;
+    o[0] = n_p;
+    o[1] = n_x0;
+    o[2] = n_x1;
+    o[3] = n_d;
+    o[4] = n_xo;
+    o[5] = nPd > 0.0 ? nPd : 0.0;
+    o[6] = nPxo > 0.0 ? nPxo : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass: the streaming sweep with both skinny GEMMs on the FP64 tensor cores
+// ---------------------------------------------------------------------------------------------
+constexpr int PASS_WARPS = 4;     // warps per CTA; each warp owns one tile of 8 problems
+constexpr int PASS_STAGES = 3;    // cp.async ring depth for P chunks
+constexpr int PASS_CHUNK_RT = 4;  // 8-row tiles per P chunk (32 rows)
+
+template <int NT, int NPL, int MODE>
+__global__ void __launch_bounds__(PASS_WARPS * 32) spm_pass_kernel(admm_spm_dims d, admm_spm_buffers b) {
+  extern __shared__ __align__(16) double Pst[];  // [PASS_STAGES][32 * ldp]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int ldp = d.ldp;
+  const int chunk_elems = PASS_CHUNK_RT * 8 * ldp;
+  const int nchunks_total = d.nrt / PASS_CHUNK_RT;
+  const int cps = (nchunks_total + d.nsplit - 1) / d.nsplit;  // chunks per split
+  const int sp = blockIdx.y;
+  const int c_begin = sp * cps, c_end = min(nchunks_total, c_begin + cps);
+  const int nchunks = max(0, c_end - c_begin);
+
+  const int pt = blockIdx.x * PASS_WARPS + warp;
+  const bool in_range = pt < d.npt;
+  const int prob = 8 * (in_range ? pt : 0) + g;
+  const int dn = in_range ? b.done[prob] : 1;
+  const bool active = !__all_sync(0xffffffffu, dn);
+  const double mu20 = b.mu20[prob];
+  const double inv_mu20 = 1.0 / mu20;
+
+  // A fragments of GEMM1': x0 in fragment layout (k-slot (j,e) of lane (g,t) <-> l = 8j+2t+e)
+  double xa[NPL][NT][2];
+  double acc[NPL][NT][2];
+  double accx[NT][2];
+#pragma unroll
+  for (int p = 0; p < NPL; ++p)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      double2 v = make_double2(0.0, 0.0);
+      if (active) v = *reinterpret_cast<const double2*>(b.x0 + frag_index(pt * NPL + p, NT, j, lane));
+      xa[p][j][0] = v.x;
+      xa[p][j][1] = v.y;
+      acc[p][j][0] = acc[p][j][1] = 0.0;
+    }
+#pragma unroll
+  for (int j = 0; j < NT; ++j) accx[j][0] = accx[j][1] = 0.0;
+  double n_diff = 0.0, n_x2 = 0.0, n_q = 0.0, n_qi = 0.0;
+
+  auto load_chunk = [&](int c, int buf) {
+    const double* src = b.Psw + (size_t)(c_begin + c) * chunk_elems;
+    double* dst = Pst + (size_t)buf * chunk_elems;
+    for (int i = tid * 2; i < chunk_elems; i += PASS_WARPS * 32 * 2) cp_async16(dst + i, src + i);
+  };
+#pragma unroll
+  for (int s = 0; s < PASS_STAGES - 1; ++s) {
+    if (s < nchunks) load_chunk(s, s);
+    cp_async_commit();
+  }
+
+  const int swg = p_swz(g);
+  const int sw0 = p_swz(2 * t), sw1 = p_swz(2 * t + 1);
+
+  // software prefetch of the state of the next 8-row tile
+  double2 st_nxt[NPL];
+  auto load_state = [&](int rt) {
+#pragma unroll
+    for (int p = 0; p < NPL; ++p) st_nxt[p] = ld_stream2(b.S + state_index(d, pt, rt, p, lane));
+  };
+  if (active && nchunks > 0) load_state(c_begin * PASS_CHUNK_RT);
+
+  for (int c = 0; c < nchunks; ++c) {
+    cp_async_wait<PASS_STAGES - 2>();
+    __syncthreads();
+    if (c + PASS_STAGES - 1 < nchunks) load_chunk(c + PASS_STAGES - 1, (c + PASS_STAGES - 1) % PASS_STAGES);
+    cp_async_commit();
+    if (!active) continue;
+    const double* Pc = Pst + (size_t)(c % PASS_STAGES) * chunk_elems;
+#pragma unroll 1
+    for (int r4 = 0; r4 < PASS_CHUNK_RT; ++r4) {
+      const int rt = (c_begin + c) * PASS_CHUNK_RT + r4;
+      const double* Pb = Pc + r4 * 8 * ldp;
+      double2 st[NPL];
+#pragma unroll
+      for (int p = 0; p < NPL; ++p) st[p] = st_nxt[p];
+      const bool last = (c == nchunks - 1) && (r4 == PASS_CHUNK_RT - 1);
+      if (!last) load_state(rt + 1);
+
+      // ---- GEMM1': q[c][r] = sum_l x0[l][c] P[r][l]
+      double q[NPL][2];
+#pragma unroll
+      for (int p = 0; p < NPL; ++p) q[p][0] = q[p][1] = 0.0;
+      {
+        const double* prow = Pb + g * ldp;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const double2 bb = *reinterpret_cast<const double2*>(prow + ((8 * j + 2 * t) ^ swg));
+#pragma unroll
+          for (int p = 0; p < NPL; ++p) {
+            dmma(q[p][0], q[p][1], xa[p][j][0], bb.x);
+            dmma(q[p][0], q[p][1], xa[p][j][1], bb.y);
+          }
+        }
+      }
+
+      // ---- elementwise: non-negative z-update, dual ascent, residual partials
+      double u[NPL][2], ux[2];
+      {
+        double sn[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double s_old = e == 0 ? st[0].x : st[0].y;
+          const double hre = s_old > 0.0 ? s_old : 0.0;
+          const double qv = q[0][e];
+          if (MODE == 2) {
+            sn[e] = s_old;
+            u[0][e] = hre;
+            ux[e] = s_old < 0.0 ? (-s_old) * inv_mu20 : 0.0;
+          } else {
+            const double a = qv - hre * inv_mu20;
+            const double x2 = a < 0.0 ? 0.0 : a;
+            const double s_new = x2 > 0.0 ? -(mu20 * x2) : hre - mu20 * qv;
+            const double df = qv - x2;
+            n_diff += df * df;
+            n_x2 += x2 * x2;
+            n_q += qv * qv;
+            sn[e] = dn ? s_old : s_new;
+            if (MODE == 1) {
+              u[0][e] = s_new > 0.0 ? s_new : 0.0;
+              ux[e] = x2;
+            } else {
+              u[0][e] = fabs(s_new);
+              ux[e] = 0.0;
+            }
+          }
+        }
+        if (MODE != 2) st_stream2(b.S + state_index(d, pt, rt, 0, lane), make_double2(sn[0], sn[1]));
+      }
+      if (NPL == 2) {
+        double hn[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double h_old = e == 0 ? st[NPL - 1].x : st[NPL - 1].y;
+          const double qv = q[NPL - 1][e];
+          if (MODE == 2) {
+            hn[e] = h_old;
+          } else {
+            const double h_new = h_old - mu20 * qv;
+            n_qi += qv * qv;
+            hn[e] = dn ? h_old : h_new;
+          }
+          u[NPL - 1][e] = hn[e];
+        }
+        if (MODE != 2) st_stream2(b.S + state_index(d, pt, rt, NPL - 1, lane), make_double2(hn[0], hn[1]));
+      }
+
+      // ---- GEMM2': V[c][l] += sum_r u[c][r] P[r][l],  k-slot t <-> row 2t+e
+      {
+        const double* prow0 = Pb + (2 * t) * ldp;
+        const double* prow1 = prow0 + ldp;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const double b0 = prow0[(8 * j + g) ^ sw0];
+          const double b1 = prow1[(8 * j + g) ^ sw1];
+#pragma unroll
+          for (int p = 0; p < NPL; ++p) {
+            dmma(acc[p][j][0], acc[p][j][1], u[p][0], b0);
+            dmma(acc[p][j][0], acc[p][j][1], u[p][1], b1);
+          }
+          if (MODE != 0) {
+            dmma(accx[j][0], accx[j][1], ux[0], b0);
+            dmma(accx[j][0], accx[j][1], ux[1], b1);
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  if (!active) return;
+
+  // ---- epilogue: partial V (fragment layout) and per-column norm partials
+  const int nct = d.npt * NPL;
+  const size_t vstride = (size_t)nct * NT * 64;
+#pragma unroll
+  for (int p = 0; p < NPL; ++p)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const size_t o = sp * vstride + frag_index(pt * NPL + p, NT, j, lane);
+      *reinterpret_cast<double2*>(b.V + o) = make_double2(acc[p][j][0], acc[p][j][1]);
+      if (MODE != 0)
+        *reinterpret_cast<double2*>(b.Vx + o) =
+            p == 0 ? make_double2(accx[j][0], accx[j][1]) : make_double2(0.0, 0.0);
+    }
+  if (MODE != 2) {
+    n_diff = quad_sum(n_diff);
+    n_x2 = quad_sum(n_x2);
+    n_q = quad_sum(n_q);
+    if (NPL == 2) n_qi = quad_sum(n_qi);
+    if (t == 0 && !dn) {
+      double* o = b.normsB + ((size_t)sp * nct * 8 + (size_t)(pt * NPL) * 8 + g) * 4;
+      o[0] = n_diff;
+      o[1] = n_x2;
+      o[2] = n_q;
+      if (NPL == 2) {
+        double* oi = o + 8 * 4;
+        oi[0] = n_qi;
+        oi[1] = 0.0;
+        oi[2] = n_qi;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// norms -> residual / convergence / mu
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gather_problem(const admm_spm_dims& d, const admm_spm_buffers& b, int prob, double (&s)[10]) {
+  const int pt = prob >> 3, g = prob & 7;
+  const int nct = d.npt * d.nplanes;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) s[i] = 0.0;
+  for (int pl = 0; pl < d.nplanes; ++pl) {
+    const size_t col = (size_t)(pt * d.nplanes + pl) * 8 + g;
+    const double* a = b.normsA + col * 8;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) s[i] += a[i];
+    for (int sp = 0; sp < d.nsplit; ++sp) {
+      const double* bb = b.normsB + ((size_t)sp * nct * 8 + col) * 4;
+      s[7] += bb[0];
+      s[8] += bb[1];
+      s[9] += bb[2];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) spm_reduce_stage1(admm_spm_dims d, admm_spm_buffers b) {
+  __shared__ double scratch[10 * 32];
+  const int per = (d.nb + gridDim.x - 1) / gridDim.x;
+  const int p0 = per * blockIdx.x, p1 = min(d.nb, p0 + per);
+  double v[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) v[i] = 0.0;
+  for (int prob = p0 + threadIdx.x; prob < p1; prob += blockDim.x) {
+    double s[10];
+    gather_problem(d, b, prob, s);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) v[i] += s[i];
+  }
+  block_sum<10>(v, scratch);
+  if (threadIdx.x < 10) b.gpart[blockIdx.x * 16 + threadIdx.x] = v[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256) spm_reduce_stage2(int nparts, admm_spm_buffers b) {
+  __shared__ double scratch[10 * 32];
+  double v[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) v[i] = 0.0;
+  for (int p = threadIdx.x; p < nparts; p += blockDim.x) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) v[i] += b.gpart[p * 16 + i];
+  }
+  block_sum<10>(v, scratch);
+  if (threadIdx.x < 10) b.gsum[threadIdx.x] = v[threadIdx.x];
+}
+
+__device__ __forceinline__ double mu_step(double mu, double primal, double dual, const admm_spm_buffers& b) {
+  if (primal > b.th_change * dual) mu *= b.fact_incr;
+  if (dual > b.th_change * primal) mu /= b.fact_incr;
+  return fmin(mu, b.max_mu);
+}
+
+__global__ void __launch_bounds__(128) spm_decide_kernel(admm_spm_dims d, admm_spm_buffers b, int do_update_mu) {
+  const int prob = blockIdx.x * blockDim.x + threadIdx.x;
+  if (prob >= d.nb) return;
+  if (b.done[prob]) return;
+  double s[10];
+  if (d.batch_wide) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) s[i] = b.gsum[i];
+  } else {
+    gather_problem(d, b, prob, s);
+  }
+  const double mu10 = b.mu10[prob], mu20 = b.mu20[prob];
+  const double p10 = sqrt(s[0]), nx0 = sqrt(s[1]), nx1 = sqrt(s[2]), nd = sqrt(s[3]), nxo = sqrt(s[4]);
+  const double nPd = sqrt(s[5]), nPxo = sqrt(s[6]), p20 = sqrt(s[7]), nx2 = sqrt(s[8]), nPx0 = sqrt(s[9]);
+  const double d10 = mu10 * nd, d20 = mu20 * nPd;
+  const double primal = p10 + p20, dual = d10 + d20;
+  b.last_res[2 * prob] = primal;
+  b.last_res[2 * prob + 1] = dual;
+  const int it = b.iters[prob];
+  b.iters[prob] = it + 1;
+  b.mu20_used[prob] = mu20;
+  if (prob == 0) {
+    if (b.history && it < b.hist_cap) {
+      b.history[2 * it] = primal;
+      b.history[2 * it + 1] = dual;
+    }
+    b.iter_counter[0] = it + 1;
+  }
+  // check_convergence (optimizer.py:232-249): 0/0 -> NaN -> not converged
+  const bool conv = (p10 / fmax(nx0, nx1) < b.rtol) && (d10 / fmax(mu10 * nx0, mu10 * nxo) < b.rtol) &&
+                    (p20 / fmax(nPx0, nx2) < b.rtol) && (d20 / fmax(mu20 * nPx0, mu20 * nPxo) < b.rtol);
+  if (conv) {
+    b.done[prob] = 1;
+    atomicAdd(&b.flags[1], 1);
+    return;
+  }
+  if (do_update_mu) {
+    const double m10 = mu_step(mu10, p10, d10, b), m20 = mu_step(mu20, p20, d20, b);
+    if (m10 != mu10 || m20 != mu20) {
+      b.mu10[prob] = m10;
+      b.mu20[prob] = m20;
+      b.flags[0] = 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+static int check_dims(const admm_spm_dims* d, const char* who) {
+  ADMM_REQUIRE(d != nullptr, ADMM_EINVAL, "%s: null dims", who);
+  ADMM_REQUIRE(d->L >= 1 && (d->Lp == 16 || d->Lp == 40 || d->Lp == 64) && d->Lp >= d->L, ADMM_EUNSUPPORTED,
+               "%s: L=%d Lp=%d unsupported (Lp must be 16, 40 or 64 and >= L)", who, d->L, d->Lp);
+  ADMM_REQUIRE(d->ldp % 16 == 0 && d->ldp >= d->Lp, ADMM_EINVAL, "%s: ldp=%d must be a multiple of 16 >= Lp", who, d->ldp);
+  ADMM_REQUIRE(d->nrt % PASS_CHUNK_RT == 0 && d->nrt * 8 >= d->Nw && d->Nw >= 1, ADMM_EINVAL,
+               "%s: nrt=%d must be a multiple of %d covering Nw=%d", who, d->nrt, PASS_CHUNK_RT, d->Nw);
+  ADMM_REQUIRE(d->nb >= 1 && d->npt * 8 >= d->nb, ADMM_EINVAL, "%s: bad nb/npt", who);
+  ADMM_REQUIRE(d->nplanes == 1 || d->nplanes == 2, ADMM_EINVAL, "%s: nplanes must be 1 or 2", who);
+  ADMM_REQUIRE(d->nsplit >= 1 && d->nsplit <= d->nrt / PASS_CHUNK_RT, ADMM_EINVAL, "%s: bad nsplit=%d", who, d->nsplit);
+  return ADMM_OK;
+}
+
+static int ew_grid(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 16)); }
+
+template <int NT, int NPL>
+static int launch_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, cudaStream_t s) {
+  dim3 grid(ceil_div(d->npt, PASS_WARPS), d->nsplit);
+  const size_t smem = (size_t)PASS_STAGES * PASS_CHUNK_RT * 8 * d->ldp * sizeof(double);
+  auto k0 = spm_pass_kernel<NT, NPL, 0>;
+  auto k1 = spm_pass_kernel<NT, NPL, 1>;
+  auto k2 = spm_pass_kernel<NT, NPL, 2>;
+  auto k = mode == 0 ? k0 : (mode == 1 ? k1 : k2);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k<<<grid, PASS_WARPS * 32, smem, s>>>(*d, *b);
+  return check_launch("admm_spm_pass");
+}
+
+template <int NT>
+static int launch_pass_nt(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, cudaStream_t s) {
+  return d->nplanes == 2 ? launch_pass<NT, 2>(d, b, mode, s) : launch_pass<NT, 1>(d, b, mode, s);
+}
+
+}  // namespace admm
+
+using namespace admm;
+
+extern "C" {
+
+int admm_spm_prepare_P(const admm_spm_dims* d, const double* P, int ldP, double* Psw, admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_prepare_P")) return rc;
+  prepare_P_kernel<<<ew_grid((long long)d->nrt * 8 * d->ldp), 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, P, ldP, Psw);
+  return check_launch("admm_spm_prepare_P");
+}
+
+int admm_spm_pack_L(const admm_spm_dims* d, const void* canon, int src_is_complex, double* frag, admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_pack_L")) return rc;
+  const long long total = (long long)d->npt * d->nplanes * (d->Lp / 8) * 64;
+  pack_L_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, (const double*)canon, src_is_complex, frag);
+  return check_launch("admm_spm_pack_L");
+}
+
+int admm_spm_unpack_L(const admm_spm_dims* d, const double* frag, void* canon, int dst_is_complex, admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_unpack_L")) return rc;
+  unpack_L_kernel<<<ew_grid((long long)d->L * d->nb), 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, frag, (double*)canon,
+                                                                                                dst_is_complex);
+  return check_launch("admm_spm_unpack_L");
+}
+
+int admm_spm_pack_state(const admm_spm_dims* d, const void* h20, const void* x2, int src_is_complex, const double* mu20,
+                        double* S, int* flag, admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_pack_state")) return rc;
+  const long long total = (long long)d->npt * d->nrt * d->nplanes * 64;
+  pack_state_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, (const double*)h20, (const double*)x2,
+                                                                                 src_is_complex, mu20, S, flag);
+  return check_launch("admm_spm_pack_state");
+}
+
+int admm_spm_unpack_state(const admm_spm_dims* d, const double* S, const double* mu20_used, void* h20, void* x2,
+                          int dst_is_complex, admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_unpack_state")) return rc;
+  unpack_state_kernel<<<ew_grid((long long)d->Nw * d->nb), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      *d, S, mu20_used, (double*)h20, (double*)x2, dst_is_complex);
+  return check_launch("admm_spm_unpack_state");
+}
+
+int admm_spm_factor(const admm_spm_dims* d, int nslots, const int* slots, const double* mu10s, const double* mu20s,
+                    const double* G0, const double* PtP, const double* Cvec, double* Ginv_cache, double* w_cache,
+                    double* sigma_cache, int* info, admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_factor")) return rc;
+  if (nslots <= 0) return ADMM_OK;
+  const size_t smem = (size_t)(d->L * d->L + 3 * d->L) * sizeof(double);
+  spm_factor_kernel<<<nslots, 256, smem, static_cast<cudaStream_t>(stream)>>>(*d, slots, mu10s, mu20s, G0, PtP, Cvec,
+                                                                             Ginv_cache, w_cache, sigma_cache, info);
+  return check_launch("admm_spm_factor");
+}
+
+int admm_spm_xupdate(const admm_spm_dims* d, const admm_spm_buffers* b, int v_split, admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_xupdate")) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nct = d->npt * d->nplanes;
+  const int grid = ceil_div(nct, 4);
+  switch (d->Lp / 8) {
+    case 2: spm_xupdate_kernel<2><<<grid, 128, 0, s>>>(*d, *b, v_split); break;
+    case 5: spm_xupdate_kernel<5><<<grid, 128, 0, s>>>(*d, *b, v_split); break;
+    default: spm_xupdate_kernel<8><<<grid, 128, 0, s>>>(*d, *b, v_split); break;
+  }
+  return check_launch("admm_spm_xupdate");
+}
+
+int admm_spm_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_pass")) return rc;
+  ADMM_REQUIRE(mode >= 0 && mode <= 2, ADMM_EINVAL, "admm_spm_pass: mode must be 0, 1 or 2");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (d->Lp / 8) {
+    case 2: return launch_pass_nt<2>(d, b, mode, s);
+    case 5: return launch_pass_nt<5>(d, b, mode, s);
+    default: return launch_pass_nt<8>(d, b, mode, s);
+  }
+}
+
+int admm_spm_reduce(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_reduce")) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int parts = std::max(1, std::min(256, ceil_div(d->nb, 256)));
+  spm_reduce_stage1<<<parts, 256, 0, s>>>(*d, *b);
+  spm_reduce_stage2<<<1, 256, 0, s>>>(parts, *b);
+  return check_launch("admm_spm_reduce");
+}
+
+int admm_spm_decide(const admm_spm_dims* d, const admm_spm_buffers* b, int do_update_mu, admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_decide")) return rc;
+  spm_decide_kernel<<<ceil_div(d->nb, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(*d, *b, do_update_mu);
+  return check_launch("admm_spm_decide");
+}
+
+}  // extern "C"

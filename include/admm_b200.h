@@ -1,0 +1,256 @@
+/*
+ * libadmm_b200 -- C ABI of the B200-native ADMM engine (drop-in for the solve loop of
+ * SpM-lab/admmsolver).  Plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ * its name ends in `_host`.  All work is enqueued on the caller's CUDA stream (`stream` is a
+ * `cudaStream_t` passed as void*); nothing here synchronises the device.  The caller owns every
+ * buffer; the library is stateless (no handles, no hidden allocations) and therefore re-entrant.
+ * Every function returns 0 on success, non-zero on error (`admm_last_error()` has the text).
+ *
+ * The reference has no FFI: its boundary is the Python API.  Each entry
+ * point below names the reference code (file:line under /root/reference/src/admmsolver) whose
+ * arithmetic it replaces.  The Python mirror that binds them is admmsolver_b200/_lib.py.
+ *
+ * Layout conventions
+ *   - dense matrices are row-major with an explicit leading dimension (elements, not bytes);
+ *   - complex128 is interleaved (re, im) like NumPy/torch; `is_complex` selects the kernels;
+ *   - "fragment layout" (SpM engine): an (Lp x ncol) real array stored as
+ *       F[ct][j][lane][e],  ct = column tile of 8 columns, j = 8-wide slice of L, lane = 4*g+t,
+ *       element = (row l = 8*j + 2*t + e, column c = 8*ct + g)                (see DESIGN.md).
+ */
+#ifndef ADMM_B200_H
+#define ADMM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADMM_ABI_VERSION 1
+
+enum admm_status { ADMM_OK = 0, ADMM_EINVAL = 1, ADMM_ECUDA = 2, ADMM_EUNSUPPORTED = 3 };
+enum admm_op { ADMM_OP_N = 0, ADMM_OP_T = 1, ADMM_OP_H = 2 };
+
+typedef void* admm_stream_t;
+
+/* ------------------------------------------------------------------------------------------ */
+/* library                                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+int admm_abi_version(void);
+const char* admm_last_error(void);
+/* SM count, compute capability and opt-in shared memory of the current device. */
+int admm_device_info(int* sm_count, int* cc_major, int* cc_minor, int* smem_optin_bytes);
+
+/* ------------------------------------------------------------------------------------------ */
+/* structured-matrix primitives (generic executor; replace the NumPy calls of matrix.py)       */
+/* ------------------------------------------------------------------------------------------ */
+/* C[m x n] = op(A)[m x k] @ B[k x n].  Replaces `DenseMatrix.__matmul__` (matrix.py:100-118),
+ * `_matvec_impl`'s tensordot (matrix.py:392-397) and the matrix-matrix products of
+ * `Model.__init__` (optimizer.py:71-76).  op(A)=A (lda>=k), A^T or A^H (A stored k x m, lda>=m). */
+int admm_gemm(int is_complex, int op_a, int m, int n, int k, const void* A, int lda,
+              const void* B, int ldb, void* C, int ldc, admm_stream_t stream);
+
+/* out[i, :] = d[i] * V[i, :] for i < nd, zero rows for nd <= i < rows_out (rectangular diagonal,
+ * zero padded / truncated).  Replaces `DiagonalMatrix.__matmul__` (matrix.py:255-274). */
+int admm_diag_mul(int is_complex, int rows_out, int nd, int ncols, const void* d, const void* V,
+                  int ldv, void* out, int ldo, admm_stream_t stream);
+
+/* out[i] = a * x[i] + b * y[i] over n doubles (complex vectors: pass 2n); y may be NULL (b
+ * ignored).  Replaces the vector algebra of `_hk`/`one_sweep` (optimizer.py:175-207,334-341). */
+int admm_axpby(long long n, double a, const double* x, double b, const double* y, double* out,
+               admm_stream_t stream);
+
+/* L1 prox: out = soft(-Re(h)/mu_diag, 0.5*alpha/mu_diag), strict comparisons.  h has stride
+ * h_stride doubles (2 for complex h: the imaginary part is dropped), out has stride out_stride
+ * (2: the imaginary slot is zeroed).  Replaces `L1Regularizer.solve` + `_softmax`
+ * (objectivefunc.py:174-195,335-355). */
+int admm_prox_l1(long long n, const double* h, int h_stride, const double* mu_diag, double alpha,
+                 double* out, int out_stride, admm_stream_t stream);
+
+/* Non-negative projection: out = max(0, -Re(h)/mu_diag).  Replaces `NonNegativePenalty.solve` +
+ * `_project_plus` (objectivefunc.py:256-271,330-333). */
+int admm_prox_nonneg(long long n, const double* h, int h_stride, const double* mu_diag,
+                     double* out, int out_stride, admm_stream_t stream);
+
+/* out[0] = sum_i x[i]^2 (y == NULL) or sum_i (x[i]-y[i])^2 over n doubles; deterministic
+ * two-stage reduction; `scratch` needs 1024 doubles.  Replaces `np.linalg.norm`
+ * (util.py:40, optimizer.py:261,267,284,289). */
+int admm_sumsq(long long n, const double* x, const double* y, double* out, double* scratch,
+               admm_stream_t stream);
+
+/* General inverse by Gauss-Jordan with partial pivoting (one CTA).  `work` is n x 2n elements.
+ * info[0] != 0 if a zero pivot was met.  Replaces `np.linalg.inv` (matrix.py:77-78). */
+int admm_inverse(int is_complex, int n, const void* A, int lda, void* Ainv, int ldi, void* work,
+                 int* info, admm_stream_t stream);
+
+/* Batched inverse of real symmetric positive-definite matrices, in place, one CTA per matrix
+ * (shared memory when n <= 128, global memory otherwise).  `mask` (may be NULL) selects the
+ * matrices to process (mask[b] != 0).  Used for (alpha A^H A + mu)^-1 (objectivefunc.py:89-96). */
+int admm_spd_inverse_batched(int n, int nbatch, double* A, long long batch_stride, int lda,
+                             const int* mask, int* info, admm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Pattern B engine: SpM  [ConstrainedLeastSquares, L1Regularizer, NonNegativePenalty] with     */
+/* conditions (0,1,I,I), (0,2,P,I); many problems share s, P, C (PartialDiagonalMatrix packing).*/
+/* One ADMM iteration = admm_spm_xupdate + admm_spm_pass (+ admm_spm_reduce) + admm_spm_decide. */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct admm_spm_dims {
+  int L;        /* basis size (size_x of terms 0 and 1)                                        */
+  int Lp;       /* L padded to 16, 40 or 64 (the instantiated tensor-core tile counts)         */
+  int ldp;      /* row stride of the swizzled P, multiple of 16, >= Lp                         */
+  int Nw;       /* number of sampling points (size_x of term 2)                                */
+  int nrt;      /* number of 8-row tiles, ceil(Nw / 8) rounded up to a multiple of 4           */
+  int nb;       /* number of problems                                                          */
+  int npt;      /* number of 8-problem tiles = ceil(nb / 8)                                    */
+  int nplanes;  /* 1: real data (imaginary parts identically zero), 2: complex128 state        */
+  int nsplit;   /* row splits of the pass kernel (partial V sums)                              */
+  int batch_wide; /* 1: mu and the stopping test use norms over the whole batch (packed
+                     reference semantics), 0: per-problem mu / stopping                        */
+} admm_spm_dims;
+
+/* P (Nw x L, row-major, ld = ldP) -> Psw (8*nrt x ldp) zero padded, columns XOR-swizzled per row. */
+int admm_spm_prepare_P(const admm_spm_dims* d, const double* P, int ldP, double* Psw,
+                       admm_stream_t stream);
+
+/* canonical (rows x nb) complex128 or float64 (batch index fastest) <-> fragment layout.
+ * `src_is_complex`: canonical array is interleaved complex.  For nplanes == 1 only real parts
+ * move.  pack zero-fills padding rows/columns. */
+int admm_spm_pack_L(const admm_spm_dims* d, const void* canon, int src_is_complex, double* frag,
+                    admm_stream_t stream);
+int admm_spm_unpack_L(const admm_spm_dims* d, const double* frag, void* canon, int dst_is_complex,
+                      admm_stream_t stream);
+
+/* (h20, x2) canonical (Nw x nb) <-> implicit state S[pt][rt][plane][lane][2]:
+ *   plane 0: s = Re(h20) - mu20 * x2  (complementarity: Re(h20) = max(0,s), mu20*x2 = max(0,-s))
+ *   plane 1: Im(h20).
+ * pack sets flag[0] = 1 if the given state is not representable (x2 < 0 or Re(h20)*x2 != 0). */
+int admm_spm_pack_state(const admm_spm_dims* d, const void* h20, const void* x2, int src_is_complex,
+                        const double* mu20, double* S, int* flag, admm_stream_t stream);
+int admm_spm_unpack_state(const admm_spm_dims* d, const double* S, const double* mu20_used,
+                          void* h20, void* x2, int dst_is_complex, admm_stream_t stream);
+
+/* Factor cache entry for `nslots` (mu10, mu20) pairs: G = G0 + mu10 I + mu20 PtP; Ginv = G^-1
+ * (Lp x Lp, zero padded), w = Ginv C^T (Lp), sigma = C w.  G0 = alpha A^H A (L x L, ld Lp).
+ * Replaces `_get_B` and the per-iteration `B @ Ch`, `inv(C @ xi2)` of
+ * `ConstrainedLeastSquares.solve` (objectivefunc.py:89-96,148-153).  slots[i] is the cache row
+ * to fill for the pair (mu10s[i], mu20s[i]). */
+int admm_spm_factor(const admm_spm_dims* d, int nslots, const int* slots, const double* mu10s,
+                    const double* mu20s, const double* G0, const double* PtP, const double* Cvec,
+                    double* Ginv_cache, double* w_cache, double* sigma_cache, int* info,
+                    admm_stream_t stream);
+
+typedef struct admm_spm_buffers {
+  /* shared operators */
+  const double* Psw;      /* 8*nrt x ldp swizzled P                                            */
+  const double* PtP;      /* Lp x Lp                                                           */
+  const double* Cvec;     /* Lp                                                                */
+  const double* Ginv_cache; /* nslot x Lp x Lp                                                 */
+  const double* w_cache;    /* nslot x Lp                                                      */
+  const double* sigma_cache;/* nslot                                                           */
+  /* per problem (length 8*npt) */
+  const int* slot;        /* factor-cache row of the problem's current (mu10, mu20)            */
+  double* mu10;
+  double* mu20;
+  double* mu20_used;      /* mu20 of the last executed pass (needed to decode x2 from S)       */
+  int* done;              /* 1: converged / padding -> frozen                                  */
+  int* iters;             /* iterations executed                                               */
+  double* last_res;       /* [8*npt][2] primal, dual residual of the last executed iteration   */
+  const double* Dre;      /* [nplanes][8*npt] right-hand side of C x0 = D                      */
+  /* fragment-layout arrays, (Lp x 8*npt*nplanes), column tile ct = pt*nplanes + plane */
+  const double* b0;       /* alpha A^H y                                                       */
+  double* x0;
+  double* x1;
+  double* h10;
+  double* V;              /* [nsplit][ncolumn tiles][Lp/8][32][2]  P^T(h20 + mu20 x2) partials  */
+  double* Vx;             /* same shape: P^T x2 partials (split form, valid after a split pass) */
+  /* implicit (h20, x2) state */
+  double* S;              /* [npt][nrt][nplanes][32][2]                                        */
+  /* norms */
+  double* normsA;         /* [8*npt*nplanes][8] from xupdate                                   */
+  double* normsB;         /* [nsplit][8*npt*nplanes][4] from pass                              */
+  double* gsum;           /* [16] batch-wide sums (reduce), only batch_wide                    */
+  double* gpart;          /* [256][16] scratch of the two-stage reduce                         */
+  /* control */
+  int* iter_counter;      /* device scalar: iterations launched so far in this solve call      */
+  int* flags;             /* [4]: 0 any mu changed, 1 number not done, 2 reserved, 3 reserved  */
+  double* history;        /* [hist_cap][2] primal/dual per iteration (batch_wide or nb==1), or NULL */
+  int hist_cap;
+  double lam;             /* L1 weight                                                         */
+  double rtol;
+  double max_mu;
+  double fact_incr;
+  double th_change;
+} admm_spm_buffers;
+
+/* x-update (term 0, `ConstrainedLeastSquares.solve`, objectivefunc.py:138-157, with
+ * `_hk`/`_mu_k`, optimizer.py:175-230), L1 z-update (objectivefunc.py:174-195) and dual ascent of
+ * pair (1,0) (optimizer.py:334-341); norms of pair (1,0) and the Gram-form dual norms of pair
+ * (2,0).  v_split != 0: V is in split form (V + mu20 * Vx). */
+int admm_spm_xupdate(const admm_spm_dims* d, const admm_spm_buffers* b, int v_split,
+                     admm_stream_t stream);
+
+/* One streaming sweep over the implicit (h20, x2) state: Q = P x0 (FP64 tensor cores), the
+ * non-negative z-update (objectivefunc.py:256-271), dual ascent of pair (2,0)
+ * (optimizer.py:334-341), residual partial sums (optimizer.py:251-274) and V = P^T(h20 + mu20 x2)
+ * for the next x-update (optimizer.py:194-200), all in one read+write of the state.
+ * mode 0: normal, 1: also emit the split form (V = P^T h20, Vx = P^T x2) -- used on iterations
+ * that may change mu, 2: init (no update; emit split form from the current state). */
+int admm_spm_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode,
+                  admm_stream_t stream);
+
+/* Batch-wide norms: deterministic two-stage sum over all problems into gsum[16].  The caller
+ * all-reduces gsum across ranks (NCCL) before admm_spm_decide when the batch is sharded. */
+int admm_spm_reduce(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream_t stream);
+
+/* residual() / check_convergence() / update_mu() (optimizer.py:232-299) per problem or
+ * batch-wide; increments iter_counter; appends to history. */
+int admm_spm_decide(const admm_spm_dims* d, const admm_spm_buffers* b, int do_update_mu,
+                    admm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Pattern A engine: basis pursuit / LASSO  [LeastSquares, L1Regularizer], condition (1,0,I,I);  */
+/* every problem has its own real A (M x N).  One CTA per problem runs all iterations.           */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct admm_bp_buffers {
+  int nb, M, N;
+  int woodbury;           /* 1: M < N, factor K = A A^T + (mu/alpha) I (M x M); 0: G = alpha A^T A + mu I */
+  int nk;                 /* order of the factor (M or N)                                      */
+  const double* A;        /* [nb][M][N] row-major                                              */
+  const double* aty;      /* [nb][N]   alpha A^T y                                             */
+  const double* gram;     /* [nb][nk][nk]  A A^T or A^T A                                      */
+  double* Kinv;           /* [nb][nk][nk]                                                      */
+  double* x0;             /* [nb][N]                                                           */
+  double* x1;             /* [nb][N]                                                           */
+  double* h;              /* [nb][N]                                                           */
+  double* mu;             /* [nb]                                                              */
+  int* need_factor;       /* [nb] 1: Kinv stale for the current mu                             */
+  int* done;              /* [nb]                                                              */
+  int* iters;             /* [nb] iterations executed in this solve call                       */
+  double* last_res;       /* [nb][2]                                                           */
+  double* history;        /* [nb][hist_cap][2] or NULL                                         */
+  int hist_cap;
+  double alpha, lam, rtol, max_mu, fact_incr, th_change;
+  int interval_update_mu;
+} admm_bp_buffers;
+
+/* aty = alpha A^T y and gram = A A^T (woodbury) or A^T A.  Replaces `LeastSquares.__init__`
+ * (objectivefunc.py:76-77) and the per-call `Ac @ y` (objectivefunc.py:108). */
+int admm_bp_setup(const admm_bp_buffers* b, const double* y, double* aty, double* gram,
+                  admm_stream_t stream);
+
+/* Kinv = (gram + (mu/alpha) I)^-1 or (alpha gram + mu I)^-1 for problems with need_factor set;
+ * clears the flag.  Replaces `_get_B` (objectivefunc.py:89-96). */
+int admm_bp_factor(const admm_bp_buffers* b, int* info, admm_stream_t stream);
+
+/* Runs iterations [iter_begin, iter_end) of `SimpleOptimizer.solve` (optimizer.py:302-341) for
+ * every problem that is neither done nor waiting for a factor: x-update by the cached inverse
+ * (Woodbury or direct), soft threshold, dual ascent, residuals, convergence test, and -- when
+ * (iter % interval_update_mu == 0) -- update_mu.  A problem whose mu changed sets need_factor
+ * and stops; the caller runs admm_bp_factor and calls again with the same iter_end. */
+int admm_bp_iterate(const admm_bp_buffers* b, int iter_end, admm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADMM_B200_H */

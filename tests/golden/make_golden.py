@@ -1,0 +1,187 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference.
+
+Run in the build container only (the reference is not on the GPU box):
+
+    python tests/golden/make_golden.py            # reads /root/reference/src
+
+The reference package is imported from ``/root/reference/src`` under its own name
+``admmsolver``; inputs come from ``admmsolver_b200/problems.py`` (loaded by path, so
+that the product package -- which needs the CUDA library -- is not imported).
+Every ``.npz`` holds the outputs of the reference after a fixed iteration count
+(x, h, mu, residual histories, objective) and, where the inputs depend on a
+BLAS-computed SVD, the inputs too.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("ADMM_REFERENCE_SRC", "/root/reference/src")
+sys.path.insert(0, REF)
+
+from admmsolver.matrix import (DenseMatrix, DiagonalMatrix, PartialDiagonalMatrix,  # noqa: E402
+                               ScaledIdentityMatrix, identity)
+from admmsolver.objectivefunc import (ConstrainedLeastSquares, L1Regularizer,  # noqa: E402
+                                      LeastSquares, NonNegativePenalty)
+from admmsolver.optimizer import Model, SimpleOptimizer  # noqa: E402
+
+spec = importlib.util.spec_from_file_location("problems", os.path.join(ROOT, "admmsolver_b200", "problems.py"))
+problems = importlib.util.module_from_spec(spec)
+sys.modules["problems"] = problems
+spec.loader.exec_module(problems)
+
+
+def _mu_hist_cb(opt, pairs, store):
+    def cb():
+        store.append([opt._mu[i, j] for (i, j) in pairs])
+    return cb
+
+
+def run_bp(A, y, lam, niter, alpha=1.0, **kw):
+    N = A.shape[1]
+    lstsq = LeastSquares(alpha, A, y)
+    l1 = L1Regularizer(lam, N)
+    opt = SimpleOptimizer(Model([lstsq, l1], [(1, 0, identity(N), identity(N))]))
+    hist = []
+    opt.solve(niter, callback=_mu_hist_cb(opt, [(1, 0)], hist), **kw)
+    return dict(x0=opt.x[0], x1=opt.x[1], h10=opt._h[1, 0], mu10=opt._mu[1, 0],
+                primal=np.array(opt._primal_residual), dual=np.array(opt._dual_residual),
+                mu_seen=np.array(hist), objective=opt(opt.x))
+
+
+def run_spm(p, g, D, niter, packed_nb=None, **kw):
+    """Single problem (packed_nb None) or the packed PartialDiagonalMatrix formulation."""
+    L, Nw = p.s.size, p.P.shape[0]
+    if packed_nb is None:
+        lstsq = ConstrainedLeastSquares(1.0, -DiagonalMatrix(p.s), g, p.C, D)
+        l1 = L1Regularizer(p.lam, L)
+        nn = NonNegativePenalty(Nw)
+        conds = [(0, 1, identity(L), identity(L)), (0, 2, p.P, identity(Nw))]
+    else:
+        nb = packed_nb
+        rest = (nb,)
+        A = PartialDiagonalMatrix(-DiagonalMatrix(p.s), rest)
+        Cm = PartialDiagonalMatrix(p.C, rest)
+        lstsq = ConstrainedLeastSquares(1.0, A, g.ravel(), Cm, D.astype(float))
+        l1 = L1Regularizer(p.lam, L * nb)
+        nn = NonNegativePenalty(Nw * nb)
+        conds = [(0, 1, identity(L * nb), identity(L * nb)),
+                 (0, 2, PartialDiagonalMatrix(p.P, rest), identity(Nw * nb))]
+    opt = SimpleOptimizer(Model([lstsq, l1, nn], conds), mu=p.mu)
+    hist = []
+    opt.solve(niter, callback=_mu_hist_cb(opt, [(1, 0), (2, 0)], hist), **kw)
+    return dict(x0=opt.x[0], x1=opt.x[1], x2=opt.x[2], h10=opt._h[1, 0], h20=opt._h[2, 0],
+                mu10=opt._mu[1, 0], mu20=opt._mu[2, 0],
+                primal=np.array(opt._primal_residual), dual=np.array(opt._dual_residual),
+                mu_seen=np.array(hist), objective=opt(opt.x))
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrs)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def main():
+    # ---- cfg1a: the notebook / test instance, known-answer vector of basis_pursuit.ipynb:137-138
+    A, y, xa = problems.basis_pursuit_instance(100, 1000, 20, 1234)
+    r = run_bp(A, y, 0.1, 100)
+    print("known answer:", np.abs(xa).max(), np.abs(xa - r["x0"]).max())
+    save("bp_notebook", y=y, xanswer=xa, **r)
+
+    # ---- cfg1b: BASELINE config 1 (200x1000, 10-sparse, 1000 iterations)
+    A, y, xa = problems.basis_pursuit_instance(200, 1000, 10, 0)
+    save("bp_cfg1", y=y, xanswer=xa, **run_bp(A, y, 0.1, 1000))
+
+    # ---- cfg4 samples: 128x512, seeds 0..3, 300 iterations
+    for b in range(4):
+        A, y, xa = problems.basis_pursuit_instance(128, 512, 10, b)
+        save(f"bp_cfg4_seed{b}", y=y, xanswer=xa, **run_bp(A, y, 0.1, 300))
+
+    # ---- tiny LASSO of test_optimizer.py:13-50 (int inputs there; float here)
+    Al = np.array([[2.0, 1.0]])
+    yl = np.array([2.0])
+    save("lasso_1x2", A=Al, y=yl, **run_bp(Al, yl, 0.1, 100))
+
+    # ---- tall basis pursuit (M > N) exercising the direct N x N path
+    rs = np.random.RandomState(7)
+    At = rs.randn(96, 40)
+    xt = np.zeros(40)
+    xt[:5] = rs.randn(5)
+    yt = At @ xt + 1e-3 * rs.randn(96)
+    save("bp_tall", A=At, y=yt, **run_bp(At, yt, 0.05, 250, alpha=0.7))
+
+    # ---- cfg2: SpM single, full size L=39, Nw=2000 (inputs regenerated by the recipe; y & C stored)
+    basis = problems.ir_basis()
+    p = problems.spm_single(basis, Nw=2000)
+    r = run_spm(p, p.g, p.D, 1000)
+    save("spm_cfg2", s=p.s, C=p.C, g=p.g, **r)
+
+    # ---- SpM reduced grid with ALL inputs stored (SVD-independent parity)
+    p = problems.spm_single(basis, Nw=192)
+    r = run_spm(p, p.g, p.D, 700)
+    save("spm_small", s=p.s, C=p.C, g=p.g, P=p.P, lam=p.lam, mu=p.mu, **r)
+
+    # ---- packed batch (batch-wide mu / stopping): nb=6 complex spectra, Nw=192
+    pb = problems.spm_batch(6, basis, Nw=192, seed=3)
+    r = run_spm(pb, pb.g, pb.D, 400, packed_nb=6)
+    save("spm_packed", s=pb.s, C=pb.C, g=pb.g, P=pb.P, lam=pb.lam, mu=pb.mu, **r)
+
+    # ---- the same six spectra as independent reference instances (per-problem mode)
+    outs = [run_spm(pb, pb.g[:, b].copy(), np.array([1.0]), 400) for b in range(6)]
+    save("spm_independent", s=pb.s, C=pb.C, g=pb.g, P=pb.P, lam=pb.lam, mu=pb.mu,
+         **{k: np.stack([o[k] for o in outs], axis=-1) for k in ("x0", "x1", "x2", "h10", "h20")},
+         mu10=np.array([o["mu10"] for o in outs]), mu20=np.array([o["mu20"] for o in outs]),
+         primal=np.stack([o["primal"] for o in outs], axis=-1),
+         dual=np.stack([o["dual"] for o in outs], axis=-1),
+         objective=np.array([o["objective"] for o in outs]))
+
+    # ---- term-level solves (objectivefunc.py): LeastSquares with dense HPD mu (complex), partial, CLS
+    rs = np.random.RandomState(100)
+    cr = lambda *sh: rs.randn(*sh) + 1j * rs.randn(*sh)
+    N1, N2 = 4, 2
+    y = cr(N1)
+    A = cr(N1, N2)
+    h = cr(N2)
+    mu = cr(N2, N2)
+    mu = mu @ mu.T.conjugate()
+    x = LeastSquares(2.0, A, y).solve(h, DenseMatrix(mu))
+    C = cr(1, N2)
+    D = cr(1)
+    xc = ConstrainedLeastSquares(2.0, A, y, C, D).solve(h, DenseMatrix(mu))
+    a2 = cr(2, 1)
+    y2 = cr(2 * 20)
+    h2 = cr(20)
+    mu2 = ScaledIdentityMatrix(20, 1.5)
+    xp = LeastSquares(0.3, PartialDiagonalMatrix(a2, (20,)), y2).solve(h2, mu2)
+    hl = rs.randn(7)
+    xl1 = L1Regularizer(0.3, 7).solve(hl, DiagonalMatrix(np.linspace(0.5, 2.0, 7)))
+    xnn = NonNegativePenalty(7).solve(hl + 0.1j, ScaledIdentityMatrix(7, 0.7))
+    save("terms", y=y, A=A, h=h, mu=mu, x_ls=x, C=C, D=D, x_cls=xc, a2=a2, y2=y2, h2=h2, x_partial=xp,
+         hl=hl, x_l1=xl1, x_nn=xnn)
+
+    # ---- generic 3-term model with dense rectangular couplings (exercises the generic executor)
+    rs = np.random.RandomState(5)
+    n0, n1, n2 = 6, 5, 4
+    Ag = rs.randn(8, n0)
+    yg = rs.randn(8)
+    E10a = rs.randn(5, n0)
+    lst = LeastSquares(1.3, Ag, yg)
+    l1 = L1Regularizer(0.2, n1)
+    nn = NonNegativePenalty(n2)
+    Pg = rs.randn(n2, n0)
+    conds = [(0, 1, E10a, identity(n1)), (0, 2, Pg, DiagonalMatrix(np.linspace(1.0, 2.0, n2)))]
+    opt = SimpleOptimizer(Model([lst, l1, nn], conds), mu=0.7)
+    opt.solve(150, interval_update_mu=20)
+    save("generic3", A=Ag, y=yg, E1=E10a, P=Pg, x0=opt.x[0], x1=opt.x[1], x2=opt.x[2],
+         h10=opt._h[1, 0], h20=opt._h[2, 0], mu10=opt._mu[1, 0], mu20=opt._mu[2, 0],
+         primal=np.array(opt._primal_residual), dual=np.array(opt._dual_residual),
+         objective=opt(opt.x))
+
+
+if __name__ == "__main__":
+    main()

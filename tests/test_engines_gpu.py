@@ -1,0 +1,203 @@
+"""Parity of the two fused CUDA engines against the CPU oracle and the reference's golden outputs.
+
+Tolerance (BASELINE.json north_star): relative 1e-10 on x and on the objective, FP64, after a
+fixed iteration count; additionally identical iteration counts and mu histories.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def eng(build_lib):
+    from admmsolver_b200 import batch, problems
+    assert torch.cuda.is_available()
+    return batch, problems
+
+
+# ------------------------------------------------------------------ pattern A
+def test_bp_notebook_known_answer(eng):
+    """basis_pursuit.ipynb:137-138: max|xanswer| = 1.4312955709975443, max|xanswer - x0| = 0.00540701076..."""
+    batch, problems = eng
+    A, y, xa = problems.basis_pursuit_instance(100, 1000, 20, 1234)
+    g = golden("bp_notebook")
+    e = batch.BatchedBasisPursuit(A, g["y"], 1.0, 0.1, keep_history=True)
+    e.solve(100)
+    x0 = e.x0()[0]
+    assert abs(np.abs(xa).max() - 1.4312955709975443) < 1e-15
+    assert abs(np.abs(xa - x0).max() - 0.0054070107628211295) < 1e-9
+    assert rel(x0, g["x0"].real) < TOL
+    assert rel(e.x1()[0], g["x1"].real) < TOL
+    assert abs(e.objective()[0] - g["objective"]) / g["objective"] < TOL
+    assert float(e.mu[0]) == float(g["mu10"])
+    assert rel(e.primal_residual[0], g["primal"]) < 1e-8
+    assert rel(e.dual_residual[0], g["dual"]) < 1e-8
+
+
+def test_bp_cfg1_golden(eng):
+    batch, problems = eng
+    A, y, xa = problems.basis_pursuit_instance(200, 1000, 10, 0)
+    g = golden("bp_cfg1")
+    e = batch.BatchedBasisPursuit(A, g["y"], 1.0, 0.1, keep_history=True)
+    e.solve(1000)
+    assert int(e.iters[0]) == len(g["primal"]) == 1000
+    assert float(e.mu[0]) == float(g["mu10"]) == 16.0
+    assert rel(e.x0()[0], g["x0"].real) < TOL
+    assert rel(e.x1()[0], g["x1"].real) < TOL
+    assert abs(e.objective()[0] - g["objective"]) / g["objective"] < TOL
+    assert rel(e.primal_residual[0], g["primal"]) < 1e-8
+
+
+def test_bp_cfg4_batch_golden(eng):
+    """Four cfg4 problems (128x512) in one launch against four reference instances."""
+    batch, problems = eng
+    A, y, xa = problems.basis_pursuit_batch(4, 128, 512, 10, 0)
+    gs = [golden(f"bp_cfg4_seed{b}") for b in range(4)]
+    yy = np.stack([g["y"] for g in gs])
+    e = batch.BatchedBasisPursuit(A, yy, 1.0, 0.1)
+    e.solve(300)
+    x0, x1, obj = e.x0(), e.x1(), e.objective()
+    for b, g in enumerate(gs):
+        assert rel(x0[b], g["x0"].real) < TOL
+        assert rel(x1[b], g["x1"].real) < TOL
+        assert abs(obj[b] - g["objective"]) / g["objective"] < TOL
+        assert float(e.mu[b]) == float(g["mu10"])
+
+
+def test_bp_tall_direct_and_lasso(eng):
+    batch, problems = eng
+    g = golden("bp_tall")
+    e = batch.BatchedBasisPursuit(g["A"], g["y"], 0.7, 0.05)
+    e.solve(250)
+    assert rel(e.x0()[0], g["x0"].real) < TOL
+    assert float(e.mu[0]) == float(g["mu10"])
+    g = golden("lasso_1x2")
+    e = batch.BatchedBasisPursuit(g["A"], g["y"], 1.0, 0.1, keep_history=True)
+    e.solve(100)
+    assert int(e.iters[0]) == len(g["primal"])       # early exit at the same iteration (41)
+    assert int(e.done[0]) == 1
+    assert rel(e.x0()[0], g["x0"].real) < TOL
+
+
+def test_bp_resume_and_ragged_oracle(eng):
+    """solve(60) + solve(60) continues like the reference; odd sizes vs the oracle."""
+    from oracle import flat
+    batch, problems = eng
+    rs = np.random.RandomState(3)
+    A = rs.randn(3, 37, 75)
+    xs = np.zeros((3, 75))
+    xs[:, :6] = rs.randn(3, 6)
+    y = np.einsum("bmn,bn->bm", A, xs)
+    e = batch.BatchedBasisPursuit(A, y, 0.9, 0.07)
+    e.solve(60, interval_update_mu=25)
+    e.solve(60, interval_update_mu=25)
+    for b in range(3):
+        st = flat.bp_solve(A[b], y[b], 0.9, 0.07, 60, interval_update_mu=25)
+        st = flat.bp_solve(A[b], y[b], 0.9, 0.07, 60, interval_update_mu=25, state=st)
+        assert rel(e.x0()[b], st.x0.real) < TOL
+        assert float(e.mu[b]) == st.mu
+
+
+# ------------------------------------------------------------------ pattern B
+def _spm_from_golden(batch, g, **kw):
+    return batch.SharedSpM(g["s"], g["P"], g["C"], kw.pop("D"), g["g"], lam=float(g["lam"]), mu=float(g["mu"]), **kw)
+
+
+def test_spm_small_golden(eng):
+    batch, problems = eng
+    g = golden("spm_small")
+    e = _spm_from_golden(batch, g, D=np.array([1.0]), batch_wide=True)
+    e.solve(700)
+    assert rel(e.x0()[:, 0], g["x0"]) < TOL
+    assert rel(e.x1()[:, 0], g["x1"]) < TOL
+    assert rel(e.x2()[:, 0], g["x2"]) < TOL
+    assert rel(e.h20()[:, 0], g["h20"]) < 1e-8
+    assert float(e.mu10[0]) == float(g["mu10"]) and float(e.mu20[0]) == float(g["mu20"])
+    assert abs(e.objective() - g["objective"]) / g["objective"] < TOL
+    assert rel(e.primal_residual, g["primal"]) < 1e-8
+    assert rel(e.dual_residual, g["dual"]) < 1e-8
+    # sum rule enforced exactly (spm.ipynb:270)
+    assert abs((g["C"] @ e.x0()[:, 0])[0] - 1.0) < 1e-12
+
+
+def test_spm_packed_batchwide_golden(eng):
+    """Packed PartialDiagonalMatrix reference (batch-global mu / stopping), complex128."""
+    batch, problems = eng
+    g = golden("spm_packed")
+    e = _spm_from_golden(batch, g, D=np.ones(6), batch_wide=True)
+    e.solve(400)
+    assert rel(e.x0().ravel(), g["x0"]) < TOL
+    assert rel(e.x1().ravel(), g["x1"]) < TOL
+    assert rel(e.x2().ravel(), g["x2"]) < TOL
+    assert float(e.mu10[0]) == float(g["mu10"]) and float(e.mu20[0]) == float(g["mu20"])
+    assert abs(e.objective() - g["objective"]) / g["objective"] < TOL
+    assert rel(e.primal_residual, g["primal"]) < 1e-8
+
+
+def test_spm_independent_golden(eng):
+    """Per-problem mode: six columns == six independent reference instances (different mu histories)."""
+    batch, problems = eng
+    g = golden("spm_independent")
+    e = _spm_from_golden(batch, g, D=np.ones(6), batch_wide=False)
+    e.solve(400)
+    x0, x2 = e.x0(), e.x2()
+    for b in range(6):
+        assert rel(x0[:, b], g["x0"][:, b]) < TOL
+        assert rel(x2[:, b], g["x2"][:, b]) < TOL
+        assert float(e.mu10[b]) == float(g["mu10"][b]) and float(e.mu20[b]) == float(g["mu20"][b])
+    assert len(set(np.asarray(g["mu20"]).tolist())) > 1      # the fixture really has diverging mu
+
+
+def test_spm_cfg2_full_size(eng, ir_basis):
+    """cfg2 (L=39, Nw=2000, 1000 it): golden outputs of the reference + the oracle on regenerated inputs."""
+    from oracle import flat
+    batch, problems = eng
+    p = problems.spm_single(ir_basis, Nw=2000)
+    g = golden("spm_cfg2")
+    e = batch.SharedSpM(p.s, p.P, p.C, p.D, g["g"], lam=p.lam, mu=p.mu, batch_wide=True)
+    e.solve(1000)
+    st = flat.spm_solve(p.s, p.P, p.C, p.D, g["g"], p.lam, 1000, mu=p.mu)
+    assert rel(e.x0()[:, 0], st.x0) < TOL and rel(e.x2()[:, 0], st.x2) < TOL
+    if rel(p.C, g["C"]) < 1e-13:      # same SVD bits as the build container: compare with the reference itself
+        assert rel(e.x0()[:, 0], g["x0"]) < TOL
+        assert abs(e.objective() - g["objective"]) / g["objective"] < TOL
+
+
+def test_spm_real_plan_and_resume(eng, ir_basis):
+    """Real data (single plane), ragged batch (nb=11), solve() twice == oracle resumed."""
+    from oracle import flat
+    batch, problems = eng
+    p = problems.spm_batch(11, ir_basis, Nw=100, seed=5, complex_noise=False)
+    gr = p.g.real.copy()
+    e = batch.SharedSpM(p.s, p.P, p.C, p.D, gr, lam=p.lam, mu=p.mu, batch_wide=True)
+    assert e.dims.nplanes == 1
+    e.solve(130, interval_update_mu=50)
+    e.solve(70, interval_update_mu=50)
+    st = flat.spm_solve(p.s, p.P, p.C, p.D, gr, p.lam, 130, mu=p.mu, interval_update_mu=50)
+    st = flat.spm_solve(p.s, p.P, p.C, p.D, gr, p.lam, 70, mu=p.mu, interval_update_mu=50, state=st)
+    assert rel(e.x0(), st.x0) < TOL and rel(e.x1(), st.x1) < TOL and rel(e.x2(), st.x2) < TOL
+    assert float(e.mu10[0]) == st.mu10 and float(e.mu20[0]) == st.mu20
+
+
+def test_spm_larger_batch_vs_oracle(eng, ir_basis):
+    """nb=200 complex, Nw=2000, several row splits and column CTAs; per-problem mode on a sample."""
+    from oracle import flat
+    batch, problems = eng
+    p = problems.spm_batch(200, ir_basis, Nw=2000, seed=9)
+    e = batch.SharedSpM(p.s, p.P, p.C, p.D, p.g, lam=p.lam, mu=p.mu, batch_wide=True)
+    e.solve(120)
+    st = flat.spm_solve(p.s, p.P, p.C, p.D, p.g, p.lam, 120, mu=p.mu)
+    assert rel(e.x0(), st.x0) < TOL and rel(e.x2(), st.x2) < TOL
+    assert abs(e.objective() - st.objective(p.s, p.g, p.lam)) / st.objective(p.s, p.g, p.lam) < TOL
+    e2 = batch.SharedSpM(p.s, p.P, p.C, p.D, p.g, lam=p.lam, mu=p.mu, batch_wide=False)
+    e2.solve(120)
+    x0 = e2.x0()
+    for b in (0, 7, 8, 63, 199):
+        sb = flat.spm_solve(p.s, p.P, p.C, np.array([1.0]), p.g[:, b], p.lam, 120, mu=p.mu)
+        assert rel(x0[:, b], sb.x0) < TOL
+        assert float(e2.mu20[b]) == sb.mu20

@@ -72,6 +72,7 @@ _SIGS = {
     "admm_gemm": ([_I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P], _I),
     "admm_diag_mul": ([_I, _I, _I, _I, _P, _P, _I, _P, _I, _P], _I),
     "admm_axpby": ([_LL, _D, _P, _D, _P, _P, _P], _I),
+    "admm_ewise_unary": ([_I, _I, _LL, _P, _P, _P], _I),
     "admm_prox_l1": ([_LL, _P, _I, _P, _D, _P, _I, _P], _I),
     "admm_prox_nonneg": ([_LL, _P, _I, _P, _P, _I, _P], _I),
     "admm_sumsq": ([_LL, _P, _P, _P, _P, _P], _I),

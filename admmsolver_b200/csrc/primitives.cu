@@ -159,6 +159,13 @@ __global__ void axpby_kernel(long long n, double a, const double* x, double b,
   }
 }
 
+template <typename T, int OPC>
+__global__ void ewise_unary_kernel(long long n, const T* x, T* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    out[i] = OPC == 0 ? num<T>::div(num<T>::one(), x[i]) : num<T>::conj(x[i]);
+  }
+}
+
 __global__ void prox_l1_kernel(long long n, const double* __restrict__ h, int hs, const double* __restrict__ mud,
                                double alpha, double* __restrict__ out, int os) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -386,6 +393,21 @@ int admm_axpby(long long n, double a, const double* x, double b, const double* y
   if (n <= 0) return ADMM_OK;
   axpby_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, a, x, b, y, out);
   return check_launch("admm_axpby");
+}
+
+int admm_ewise_unary(int op, int is_complex, long long n, const void* x, void* out, admm_stream_t stream) {
+  ADMM_REQUIRE(op == 0 || op == 1, ADMM_EINVAL, "admm_ewise_unary: op must be 0 (reciprocal) or 1 (conjugate)");
+  if (n <= 0) return ADMM_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int g = ew_grid(n);
+  if (is_complex) {
+    if (op == 0) ewise_unary_kernel<cplx, 0><<<g, 256, 0, s>>>(n, (const cplx*)x, (cplx*)out);
+    else ewise_unary_kernel<cplx, 1><<<g, 256, 0, s>>>(n, (const cplx*)x, (cplx*)out);
+  } else {
+    if (op == 0) ewise_unary_kernel<double, 0><<<g, 256, 0, s>>>(n, (const double*)x, (double*)out);
+    else ewise_unary_kernel<double, 1><<<g, 256, 0, s>>>(n, (const double*)x, (double*)out);
+  }
+  return check_launch("admm_ewise_unary");
 }
 
 int admm_prox_l1(long long n, const double* h, int h_stride, const double* mu_diag, double alpha, double* out,

@@ -61,6 +61,11 @@ int admm_diag_mul(int is_complex, int rows_out, int nd, int ncols, const void* d
 int admm_axpby(long long n, double a, const double* x, double b, const double* y, double* out,
                admm_stream_t stream);
 
+/* out[i] = 1 / x[i] (op 0) or conj(x[i]) (op 1) over n elements.  Replaces `DiagonalMatrix.inv`
+ * and `.conjugate()` (matrix.py:223-226,239-240). */
+int admm_ewise_unary(int op, int is_complex, long long n, const void* x, void* out,
+                     admm_stream_t stream);
+
 /* L1 prox: out = soft(-Re(h)/mu_diag, 0.5*alpha/mu_diag), strict comparisons.  h has stride
  * h_stride doubles (2 for complex h: the imaginary part is dropped), out has stride out_stride
  * (2: the imaginary slot is zeroed).  Replaces `L1Regularizer.solve` + `_softmax`

@@ -119,7 +119,8 @@ def main():
     basis = problems.ir_basis()
     p = problems.spm_single(basis, Nw=2000)
     r = run_spm(p, p.g, p.D, 1000)
-    save("spm_cfg2", s=p.s, C=p.C, g=p.g, **r)
+    # P_probe: every 97th row of P, so a test can tell whether its regenerated P has the same bits
+    save("spm_cfg2", s=p.s, C=p.C, g=p.g, P_probe=p.P[::97].copy(), **r)
 
     # ---- SpM reduced grid with ALL inputs stored (SVD-independent parity)
     p = problems.spm_single(basis, Nw=192)

@@ -163,7 +163,9 @@ def test_spm_cfg2_full_size(eng, ir_basis):
     e.solve(1000)
     st = flat.spm_solve(p.s, p.P, p.C, p.D, g["g"], p.lam, 1000, mu=p.mu)
     assert rel(e.x0()[:, 0], st.x0) < TOL and rel(e.x2()[:, 0], st.x2) < TOL
-    if rel(p.C, g["C"]) < 1e-13:      # same SVD bits as the build container: compare with the reference itself
+    # The singular vectors of the tiny singular values are ill-conditioned, so P depends on the BLAS
+    # kernels of the host CPU; compare with the reference's own output only when P has the same bits.
+    if np.array_equal(p.P[::97], g["P_probe"]):
         assert rel(e.x0()[:, 0], g["x0"]) < TOL
         assert abs(e.objective() - g["objective"]) / g["objective"] < TOL
 

@@ -177,6 +177,7 @@ class SharedSpM:
         self.iter_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.flags = torch.zeros(4, dtype=torch.int32, device=dev)
         self.history = None
+        self.pass_events = None      # bench.py: list collecting (start, stop) CUDA events around the pass kernel
         self._v_state = "none"
         self.primal_residual = []
         self.dual_residual = []
@@ -239,6 +240,35 @@ class SharedSpM:
             lut = torch.tensor([self._slot_of[(float(a), float(b))] for a, b in pairs], dtype=torch.int32,
                                device=self.device)
             self.slot[:nb] = lut[inverse]
+
+    # ------------------------------------------------------------------ data reload (same operators)
+    def reset(self, g=None, mu: Optional[float] = None) -> None:
+        """Zero the ADMM state (x, h), optionally load new data ``g`` (L x nb, device or host) and
+        reset the penalties -- lets one plan serve many batches without re-allocating."""
+        for t in (self.x0f, self.x1f, self.h10f, self.S, self.V, self.Vx):
+            t.zero_()
+        if mu is not None:
+            self.mu10.fill_(float(mu))
+            self.mu20.fill_(float(mu))
+            self.mu20_used.fill_(float(mu))
+            self._refresh_slots()
+        if g is not None:
+            if self._s is None:
+                raise NotImplementedError("reset(g=...) needs the SpM form (s, g)")
+            g_t = _dev_tensor(g, self.device)
+            if g_t.ndim == 1:
+                g_t = g_t[:, None]
+            g_t = g_t.contiguous()
+            cplx = g_t.is_complex()
+            assert g_t.shape == (self.L, self.nb) and (self.is_complex or not cplx)
+            gv = g_t if cplx else g_t.to(_F64)
+            b0 = torch.empty_like(gv)
+            sd = (-self._alpha * self._s).to(gv.dtype)
+            call("admm_diag_mul", int(cplx), self.L, self.L, self.nb, ptr(sd), ptr(gv), self.nb, ptr(b0), self.nb, stream())
+            call("admm_spm_pack_L", C.byref(self.dims), ptr(b0), int(cplx), ptr(self.b0), stream())
+            self._g = gv
+        self._v_state = "none"
+        self.primal_residual, self.dual_residual = [], []
 
     # ------------------------------------------------------------------ state import / export
     def set_state(self, x0=None, x1=None, x2=None, h10=None, h20=None) -> None:
@@ -314,7 +344,14 @@ class SharedSpM:
             call("admm_spm_pass", dref, bref, 2, st)
             self._v_state = "split"
         call("admm_spm_xupdate", dref, bref, int(self._v_state == "split"), st)
-        call("admm_spm_pass", dref, bref, 1 if do_update_mu else 0, st)
+        if self.pass_events is not None and not do_update_mu:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            call("admm_spm_pass", dref, bref, 0, st)
+            e1.record()
+            self.pass_events.append((e0, e1))
+        else:
+            call("admm_spm_pass", dref, bref, 1 if do_update_mu else 0, st)
         self._v_state = "split" if do_update_mu else "plain"
         if self.batch_wide:
             call("admm_spm_reduce", dref, bref, st)

@@ -1,0 +1,471 @@
+#!/usr/bin/env python
+"""bench.py -- FP64 ADMM problem-iterations/s on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload spm_sweep|spm_cfg3|bp_cfg4|bp_cfg1|spm_cfg2]
+    python bench.py --impl reference ...        # the reference's own CPU implementation, bounded sample
+
+One "step" is one ``solve(niter)`` over the whole resident batch (``--niter`` ADMM iterations,
+default 100 = one mu-update interval).  Default workload: BASELINE config 5, the 2^20-problem
+complex128 SpM sweep sharing one basis, batch-sharded over the N ranks (strong scaling) with the
+batch-wide stopping criterion (NCCL all-reduce of the residual partial sums every iteration).
+Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "fp64_admm_problem_iters_per_sec"
+UNIT = "problem-iters/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="spm_sweep",
+                    choices=["spm_sweep", "spm_cfg3", "bp_cfg4", "bp_cfg1", "spm_cfg2"])
+    ap.add_argument("--nb", type=int, default=None, help="total number of problems (default: per workload)")
+    ap.add_argument("--niter", type=int, default=None, help="ADMM iterations per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--per-problem", action="store_true", help="SpM: per-problem mu/stopping (no collective)")
+    return ap.parse_args()
+
+
+WORKLOADS = {
+    # name: (default total nb, default niter, description)
+    "spm_sweep": (1 << 20, 100, "cfg5: 2^20 SpM problems sharing one IR basis (L=39, Nw=2000), complex128"),
+    "spm_cfg3": (4096, 100, "cfg3: 4096 SpM problems sharing one A (L=39, Nw=2000), complex128"),
+    "bp_cfg4": (65536, 100, "cfg4: 65536 independent basis-pursuit problems, own 128x512 A each"),
+    "bp_cfg1": (1, 1000, "cfg1: basis pursuit 200x1000, 10-sparse, single problem"),
+    "spm_cfg2": (1, 1000, "cfg2: SpM single problem L=39, Nw=2000"),
+}
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baselines (the reference's own implementation on the host cores; bounded samples)
+# ----------------------------------------------------------------------------------------------
+def _import_reference():
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref, "admmsolver")):
+        sys.path.insert(0, ref)
+        import admmsolver  # noqa: F401
+        return "reference"
+    return "port"
+
+
+def cpu_spm_sample(nb_s: int, niter: int, Nw: int = 2000, seed: int = 0):
+    """Packed PartialDiagonalMatrix formulation of the reference (batch-wide), nb_s problems."""
+    from admmsolver_b200 import problems
+    kind = _import_reference()
+    basis = problems.ir_basis()
+    p = problems.spm_batch(nb_s, basis, Nw=Nw, seed=seed) if nb_s > 1 else problems.spm_single(basis, Nw=Nw)
+    if kind == "reference":
+        from admmsolver.matrix import DiagonalMatrix, PartialDiagonalMatrix, identity
+        from admmsolver.objectivefunc import ConstrainedLeastSquares, L1Regularizer, NonNegativePenalty
+        from admmsolver.optimizer import Model, SimpleOptimizer
+        L = p.s.size
+        if nb_s > 1:
+            rest = (nb_s,)
+            lstsq = ConstrainedLeastSquares(1.0, PartialDiagonalMatrix(-DiagonalMatrix(p.s), rest), p.g.ravel(),
+                                            PartialDiagonalMatrix(p.C, rest), p.D.astype(float))
+            conds = [(0, 1, identity(L * nb_s), identity(L * nb_s)),
+                     (0, 2, PartialDiagonalMatrix(p.P, rest), identity(Nw * nb_s))]
+        else:
+            lstsq = ConstrainedLeastSquares(1.0, -DiagonalMatrix(p.s), p.g, p.C, p.D)
+            conds = [(0, 1, identity(L), identity(L)), (0, 2, p.P, identity(Nw))]
+        opt = SimpleOptimizer(Model([lstsq, L1Regularizer(p.lam, L * nb_s), NonNegativePenalty(Nw * nb_s)], conds),
+                              mu=p.mu)
+        t0 = time.perf_counter()
+        opt.solve(niter)
+        dt = time.perf_counter() - t0
+    else:
+        from oracle import flat
+        t0 = time.perf_counter()
+        flat.spm_solve(p.s, p.P, p.C, p.D, p.g, p.lam, niter, mu=p.mu)
+        dt = time.perf_counter() - t0
+    return nb_s * niter / dt, kind, f"{nb_s} packed problems x {niter} iterations (L={p.s.size}, Nw={Nw}), {dt:.2f} s"
+
+
+def cpu_bp_sample(nb_s: int, niter: int, M: int, N: int, K: int):
+    from admmsolver_b200 import problems
+    kind = _import_reference()
+    A, y, _ = problems.basis_pursuit_batch(nb_s, M, N, K, 0)
+    t0 = time.perf_counter()
+    if kind == "reference":
+        from admmsolver.matrix import identity
+        from admmsolver.objectivefunc import L1Regularizer, LeastSquares
+        from admmsolver.optimizer import Model, SimpleOptimizer
+        for b in range(nb_s):
+            opt = SimpleOptimizer(Model([LeastSquares(1.0, A[b], y[b]), L1Regularizer(0.1, N)],
+                                        [(1, 0, identity(N), identity(N))]))
+            opt.solve(niter)
+    else:
+        from oracle import flat
+        for b in range(nb_s):
+            flat.bp_solve(A[b], y[b], 1.0, 0.1, niter)
+    dt = time.perf_counter() - t0
+    return nb_s * niter / dt, kind, f"{nb_s} problems {M}x{N} x {niter} iterations, sequential instances, {dt:.2f} s"
+
+
+def cpu_baseline_for(workload: str):
+    if workload in ("spm_sweep", "spm_cfg3"):
+        return cpu_spm_sample(1024, 20)
+    if workload == "spm_cfg2":
+        return cpu_spm_sample(1, 400)
+    if workload == "bp_cfg4":
+        return cpu_bp_sample(16, 400, 128, 512, 10)
+    return cpu_bp_sample(1, 600, 200, 1000, 10)
+
+
+def host_threads() -> int:
+    try:
+        from threadpoolctl import threadpool_info
+        n = [i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"]
+        if n:
+            return int(max(n))
+    except Exception:
+        pass
+    return len(os.sched_getaffinity(0))
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm
+# ----------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nb_def, niter_def, desc = WORKLOADS[args.workload]
+    # import numpy-side generators without touching CUDA
+    vals, sample, kind = [], "", "port"
+    for i in range(args.warmup + args.steps):
+        v, kind, sample = cpu_baseline_for(args.workload)
+        if i >= args.warmup:
+            vals.append(v)
+    v = float(np.mean(vals))
+    cores = host_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def measure_fp64_peak(torch, seconds: float = 1.5):
+    """cuBLAS DGEMM 8192^3 via torch.matmul: burst (best of 5) and sustained (back-to-back)."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    c = torch.empty_like(a)
+    torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    burst = 2 * n ** 3 / (best * 1e-3) / 1e12
+    reps = max(3, int(seconds / (best * 1e-3)))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        torch.matmul(a, b, out=c)
+    e1.record()
+    torch.cuda.synchronize()
+    sustained = 2 * n ** 3 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    del a, b, c
+    torch.cuda.empty_cache()
+    return burst, sustained
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        group = dist.group.WORLD
+
+    from admmsolver_b200 import _lib, batch, problems
+
+    nb_def, niter_def, desc = WORKLOADS[args.workload]
+    nb_total = args.nb or nb_def
+    niter = args.niter or niter_def
+    is_spm = args.workload.startswith("spm")
+    nb_local = nb_total // world if nb_total >= world else nb_total
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback"
+
+    fp64_burst = fp64_sus = None
+    if rank == 0:
+        fp64_burst, fp64_sus = measure_fp64_peak(torch)
+
+    h2d = d2h = 0
+    if is_spm:
+        basis = problems.ir_basis()
+        Nw = 2000
+        L = basis.size
+        # synthetic spectra: rank r owns the contiguous batch slab [r*nb_local, (r+1)*nb_local)
+        gen_nb = min(nb_local, 4096)
+        p = problems.spm_batch(gen_nb, basis, Nw=Nw, seed=1000 + rank) if nb_total > 1 else \
+            problems.spm_single(basis, Nw=Nw)
+        g_small = p.g.reshape(L, -1).astype(np.complex128)
+        reps = -(-nb_local // g_small.shape[1])
+        g_host = torch.from_numpy(np.tile(g_small, (1, reps))[:, :nb_local].copy()).pin_memory()
+        out_host = torch.empty(L, nb_local, dtype=torch.complex128).pin_memory()
+        g_dev = g_host.to("cuda", non_blocking=True)
+        batch_wide = not args.per_problem
+        eng = batch.SharedSpM(p.s, p.P, p.C, np.ones(nb_local), g_dev, lam=p.lam, mu=p.mu,
+                              batch_wide=batch_wide, group=group if batch_wide else None)
+
+        def step():
+            eng.solve(niter)
+
+        def e2e_step():
+            g_dev.copy_(g_host, non_blocking=True)
+            eng.reset(g=g_dev, mu=p.mu)
+            eng.solve(niter)
+            out_host.copy_(eng.x0_device(), non_blocking=True)
+
+        h2d = g_host.numel() * 16
+        d2h = out_host.numel() * 16
+        flops_per_unit = 8.0 * L * Nw            # pass kernel: both skinny GEMMs, complex state / real operators
+        bytes_per_unit = 32.0 * Nw               # implicit (h20, x2) state: 16 B read + 16 B written per point
+        kernel_name = "spm_pass_kernel<5,2,0>"
+        bound = "tensor"
+    else:
+        if args.workload == "bp_cfg4":
+            M, N, K = 128, 512, 10
+        else:
+            M, N, K = 200, 1000, 10
+        # generate on the host in slabs (identical bits for the sampled oracle problems), tile beyond 256
+        gen_nb = min(nb_local, 256)
+        A_s, y_s, _ = problems.basis_pursuit_batch(gen_nb, M, N, K, seed0=rank * gen_nb)
+        reps = -(-nb_local // gen_nb)
+        A_dev = torch.from_numpy(A_s).cuda().repeat(reps, 1, 1)[:nb_local].contiguous()
+        y_host = torch.from_numpy(np.tile(y_s, (reps, 1))[:nb_local].copy()).pin_memory()
+        out_host = torch.empty(nb_local, N, dtype=torch.float64).pin_memory()
+        y_dev = y_host.cuda()
+        eng = batch.BatchedBasisPursuit(A_dev, y_dev, 1.0, 0.1)
+        zeros = torch.zeros(nb_local, N, dtype=torch.float64, device="cuda")
+
+        def reset_state():
+            eng.set_state(x0=zeros, x1=zeros, h=zeros, mu=1.0)
+
+        def step():
+            reset_state()
+            eng.solve(niter)
+
+        def e2e_step():
+            # A stays resident (the operator); per step the data y travels in and x0 travels out
+            y_dev.copy_(y_host, non_blocking=True)
+            _lib.call("admm_bp_setup", __import__("ctypes").byref(eng.bufs), _lib.ptr(y_dev), _lib.ptr(eng.aty),
+                      _lib.ptr(eng.gram), _lib.stream())
+            reset_state()
+            eng.solve(niter)
+            out_host.copy_(eng._x0, non_blocking=True)
+
+        h2d = y_host.numel() * 8
+        d2h = out_host.numel() * 8
+        flops_per_unit = 4.0 * M * N + 2.0 * M * M
+        bytes_per_unit = 2.0 * 8 * M * N + 8.0 * M * M + 8.0 * 6 * N
+        kernel_name = "bp_iterate_kernel"
+        bound = "hbm"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, nsteps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(nsteps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count
+    if is_spm:
+        eng.pass_events = []
+    total_ms = timed(step, args.steps)
+    launches = _lib.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    units = float(nb_local * world) * niter * args.steps
+    value = units / (total_ms * 1e-3)
+
+    # dominant-kernel duration (CUDA events on the launching stream, inside the timed region)
+    if is_spm:
+        durs = [a.elapsed_time(b) for a, b in eng.pass_events]
+        eng.pass_events = None
+        k_ms = float(np.mean(durs)) if durs else None
+        units_per_launch = nb_local
+    else:
+        # the persistent kernel runs all iterations: time = step time / launches that do work
+        k_ms = total_ms / args.steps
+        units_per_launch = nb_local * niter
+
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        ms = timed(e2e_step, args.steps)
+        e2e = {"value": units / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    roof = None
+    if k_ms:
+        if bound == "tensor":
+            ach = flops_per_unit * units_per_launch / (k_ms * 1e-3) / 1e12
+            peak = fp64_sus
+            roof = {"bound": "tensor", "kernel": kernel_name, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                    "frac": ach / peak, "traffic": None,
+                    "peak_source": "measured live: cuBLAS DGEMM 8192^3 via torch.matmul, sustained (burst %.1f)" % fp64_burst,
+                    "avg_launch_ms": k_ms,
+                    "hbm_achieved_gbs": bytes_per_unit * units_per_launch / (k_ms * 1e-3) / 1e9,
+                    "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
+                    "hbm_frac": bytes_per_unit * units_per_launch / (k_ms * 1e-3) / 1e9 / hbm_peak}
+        else:
+            ach = bytes_per_unit * units_per_launch / (k_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": kernel_name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src, "avg_launch_ms": k_ms,
+                    "fp64_tflops": flops_per_unit * units_per_launch / (k_ms * 1e-3) / 1e12,
+                    "fp64_peak_tflops": fp64_sus}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, kind, sample = cpu_baseline_for(args.workload)
+        cpu = {"value": v, "unit": UNIT, "cores": host_threads(), "kind": kind, "sample": sample}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if nb_total >= world else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "problems_total": nb_local * world,
+                   "problems_per_gpu": nb_local, "iterations_per_step": niter,
+                   "criterion": ("batch-wide (NCCL all-reduce)" if (is_spm and not args.per_problem) else "per-problem"),
+                   "l2": "working set per iteration >> L2 (126 MB)" if nb_local * bytes_per_unit > 2.5e8 else
+                         "working set fits L2; no flush (the solver iterates on resident state by design)"},
+        "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "fp64_peak_tflops": {"burst": fp64_burst, "sustained": fp64_sus},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

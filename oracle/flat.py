@@ -168,7 +168,7 @@ class SpMState:
 def spm_solve(s: np.ndarray, P: np.ndarray, C: np.ndarray, D: np.ndarray, g: np.ndarray,
               lam: float, niter: int, mu: float = 0.1, alpha: float = 1.0, max_mu: float = 1e3,
               interval_update_mu: int = 100, rtol: float = 1e-12, update_h: bool = True,
-              state: Optional[SpMState] = None) -> SpMState:
+              state: Optional[SpMState] = None, allreduce=None) -> SpMState:
     """Pattern B.  ``g`` is (L,) for one problem or (L, nb) for a packed batch.
 
     In the packed case every norm runs over the whole packed vector, so mu and
@@ -179,6 +179,10 @@ def spm_solve(s: np.ndarray, P: np.ndarray, C: np.ndarray, D: np.ndarray, g: np.
     ``A = -diag(s)``; x1: L1 prox; x2: ``NonNegativePenalty.solve``
     (objectivefunc.py:256-271); residuals optimizer.py:251-274; convergence
     optimizer.py:232-249; mu update optimizer.py:277-299.
+
+    ``allreduce``: optional callable summing a float64 vector over ranks.  When the batch is
+    sharded, every rank passes its slab of ``g`` and the ten squared-norm partials are summed
+    across ranks before the square roots -- the multi-GPU batch-wide criterion.
     """
     L = s.size
     Nw = P.shape[0]
@@ -224,17 +228,26 @@ def spm_solve(s: np.ndarray, P: np.ndarray, C: np.ndarray, D: np.ndarray, g: np.
             st.h10 = st.h10 + st.mu10 * (st.x1 - st.x0)
             st.h20 = st.h20 + st.mu20 * (st.x2 - Px0)
         Px0_old = P @ x0_old
-        p10 = _nrm(st.x0 - st.x1)
-        d10 = _nrm(st.mu10 * (st.x0 - x0_old))
-        p20 = _nrm(Px0 - st.x2)
-        d20 = _nrm(st.mu20 * (Px0 - Px0_old))
+        if allreduce is None:
+            p10 = _nrm(st.x0 - st.x1)
+            d10 = _nrm(st.mu10 * (st.x0 - x0_old))
+            p20 = _nrm(Px0 - st.x2)
+            d20 = _nrm(st.mu20 * (Px0 - Px0_old))
+            nx0, nx1, nxo = _nrm(st.x0), _nrm(st.x1), _nrm(x0_old)
+            nPx0, nx2, nPxo = _nrm(Px0), _nrm(st.x2), _nrm(Px0_old)
+        else:
+            sq = np.array([_nrm(v) ** 2 for v in (st.x0 - st.x1, st.x0 - x0_old, Px0 - st.x2, Px0 - Px0_old,
+                                                  st.x0, st.x1, x0_old, Px0, st.x2, Px0_old)])
+            sq = np.sqrt(allreduce(sq))
+            p10, d10, p20, d20 = sq[0], st.mu10 * sq[1], sq[2], st.mu20 * sq[3]
+            nx0, nx1, nxo, nPx0, nx2, nPxo = sq[4:]
         st.primal.append(p10 + p20)
         st.dual.append(d10 + d20)
         st.niter_done += 1
-        conv = _rel_lt(p10, _nrm(st.x0), _nrm(st.x1), rtol) and \
-            _rel_lt(d10, _nrm(st.mu10 * st.x0), _nrm(st.mu10 * x0_old), rtol) and \
-            _rel_lt(p20, _nrm(Px0), _nrm(st.x2), rtol) and \
-            _rel_lt(d20, _nrm(st.mu20 * Px0), _nrm(st.mu20 * Px0_old), rtol)
+        conv = _rel_lt(p10, nx0, nx1, rtol) and \
+            _rel_lt(d10, st.mu10 * nx0, st.mu10 * nxo, rtol) and \
+            _rel_lt(p20, nPx0, nx2, rtol) and \
+            _rel_lt(d20, st.mu20 * nPx0, st.mu20 * nPxo, rtol)
         if conv:
             st.converged = True
             st.mu_hist.append((st.mu10, st.mu20))

@@ -1,0 +1,63 @@
+"""CPU: the C-ABI library loads and exports every symbol include/admm_b200.h declares; the ctypes
+mirror covers them all; the product package has no import path into the oracle."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "admm_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(admm_[A-Za-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported(build_lib):
+    lib = ctypes.CDLL(os.path.join(ROOT, "admmsolver_b200", "libadmm_b200.so"))
+    names = _declared()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/admm_b200.h but not exported"
+    lib.admm_abi_version.restype = ctypes.c_int
+    assert lib.admm_abi_version() == 1
+
+
+def test_ctypes_mirror_complete(build_lib):
+    from admmsolver_b200 import _lib
+    assert sorted(_lib._SIGS) == _declared()
+
+
+def test_struct_layout_matches_header(build_lib):
+    """Field order of the ctypes structs == field order of the C structs."""
+    from admmsolver_b200 import _lib
+    txt = open(os.path.join(ROOT, "include", "admm_b200.h")).read()
+    for cname, cls in (("admm_spm_dims", _lib.SpmDims), ("admm_spm_buffers", _lib.SpmBuffers),
+                       ("admm_bp_buffers", _lib.BpBuffers)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), txt, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                fields.append(re.findall(r"[A-Za-z_0-9]+", part)[-1])
+        assert fields == [f[0] for f in cls._fields_], cname
+
+
+def test_no_cpu_fallback_and_no_oracle_import(build_lib):
+    """The product never imports oracle/ and refuses to compute without a CUDA device."""
+    import torch
+    pkg = os.path.join(ROOT, "admmsolver_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("the oracle", "").replace("oracle problems", "") or fn == "problems.py", fn
+            assert "import oracle" not in src and "from oracle" not in src, fn
+    if not torch.cuda.is_available():
+        import numpy as np
+        import pytest
+        from admmsolver_b200 import _lib, batch
+        with pytest.raises(_lib.AdmmError):
+            batch.BatchedBasisPursuit(np.eye(2), np.ones(2))

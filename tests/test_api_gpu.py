@@ -1,0 +1,281 @@
+"""GPU: the drop-in Python API (matrix / objectivefunc / optimizer) against dense NumPy equivalents
+and the reference's golden outputs.  Test cases follow the reference's own suites
+(/root/reference/test/test_matrix.py, test_objectivefunc.py, test_optimizer.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def api(build_lib):
+    assert torch.cuda.is_available()
+    import admmsolver_b200.matrix as M
+    import admmsolver_b200.objectivefunc as F
+    import admmsolver_b200.optimizer as O
+    return M, F, O
+
+
+def _rc(rs, *shape):
+    return rs.randn(*shape) + 1j * rs.randn(*shape)
+
+
+# ------------------------------------------------------------------ matrix.py
+def test_matmul_all_pairs(api):
+    """test_matrix.py:11-57."""
+    M, F, O = api
+    rs = np.random.RandomState(100)
+    n1, n2, n3 = 12, 12, 4
+    left = [M.DiagonalMatrix(np.ones(n1)), M.ScaledIdentityMatrix(n1, 1 + 1j),
+            M.PartialDiagonalMatrix(_rc(rs, 3, 3), rest_dims=(4,)), M.DenseMatrix(_rc(rs, n1, n2))]
+    right = [M.DenseMatrix(_rc(rs, n2, n3)), M.ScaledIdentityMatrix((n2, n3), 1 + 1j),
+             M.PartialDiagonalMatrix(_rc(rs, 3, 1), rest_dims=(4,))]
+    for l in left:
+        for r in right:
+            lr = l @ r
+            assert isinstance(lr, M.MatrixBase)
+            np.testing.assert_allclose(lr.asmatrix(), l.asmatrix() @ r.asmatrix(), atol=1e-13)
+    n1, n2, n3 = 4, 12, 12
+    left = [M.DenseMatrix(_rc(rs, n1, n2)), M.PartialDiagonalMatrix(_rc(rs, 1, 3), rest_dims=(4,))]
+    right = [M.DiagonalMatrix(np.ones(n3)), M.ScaledIdentityMatrix(n3, 1 + 1j),
+             M.PartialDiagonalMatrix(_rc(rs, 3, 3), rest_dims=(4,)), M.DenseMatrix(_rc(rs, n2, n3))]
+    for l in left:
+        for r in right:
+            lr = l @ r
+            assert isinstance(lr, M.MatrixBase)
+            np.testing.assert_allclose(lr.asmatrix(), l.asmatrix() @ r.asmatrix(), atol=1e-13)
+
+
+def test_mul_transpose_conj_add_inv(api):
+    """test_matrix.py:60-166."""
+    M, F, O = api
+    rs = np.random.RandomState(100)
+    n = 4
+    mats = [M.DiagonalMatrix(_rc(rs, n)), M.ScaledIdentityMatrix(n, 1 + 1j), M.PartialDiagonalMatrix(_rc(rs, 2, 2), (2,)),
+            M.DenseMatrix(_rc(rs, n, n)), M.DiagonalMatrix(_rc(rs, 2), shape=(4, 2)), M.ScaledIdentityMatrix((2, 4), 2.0)]
+    for m in mats:
+        d = m.asmatrix()
+        np.testing.assert_allclose((m * (2.0 + 1j)).asmatrix(), d * (2.0 + 1j), atol=1e-14)
+        np.testing.assert_allclose((3.0 * m).asmatrix(), 3.0 * d, atol=1e-14)
+        np.testing.assert_allclose(m.T.asmatrix(), d.T, atol=1e-14)
+        np.testing.assert_allclose(m.conj().asmatrix(), d.conj(), atol=1e-14)
+        np.testing.assert_allclose((-m).asmatrix(), -d, atol=1e-14)
+    sq = mats[:4]
+    for a in sq:
+        for b in sq:
+            np.testing.assert_allclose((a + b).asmatrix(), a.asmatrix() + b.asmatrix(), atol=1e-13)
+            np.testing.assert_allclose((a - b).asmatrix(), a.asmatrix() - b.asmatrix(), atol=1e-13)
+    for m in sq:
+        inv_m = m.inv()
+        assert isinstance(inv_m, M.MatrixBase)
+        np.testing.assert_allclose(inv_m.asmatrix() @ m.asmatrix(), np.identity(n), rtol=0, atol=1e-12)
+    with pytest.raises(RuntimeError):
+        M.ScaledIdentityMatrix((2, 4), 2.0).inv()
+    with pytest.raises(AssertionError):
+        M.ScaledIdentityMatrix(3, 1)               # int coefficients are rejected (matrix.py:134-135)
+
+
+def test_structure_preservation(api):
+    """test_matrix.py:110-150: Diagonal (+|@) PartialDiagonal stays PartialDiagonal when constant along rest."""
+    M, F, O = api
+    rs = np.random.RandomState(1)
+    a = M.DiagonalMatrix(np.repeat(rs.randn(3), 4))
+    b = M.PartialDiagonalMatrix(rs.randn(3, 3), (4,))
+    for r in (a + b, a @ b, b + b, b @ b):
+        assert isinstance(r, M.PartialDiagonalMatrix)
+    np.testing.assert_allclose((a + b).asmatrix(), a.asmatrix() + b.asmatrix(), atol=1e-14)
+    np.testing.assert_allclose((a @ b).asmatrix(), a.asmatrix() @ b.asmatrix(), atol=1e-14)
+    c = M.DiagonalMatrix(rs.randn(12))
+    assert isinstance(c + b, M.DenseMatrix)
+    np.testing.assert_allclose((c + b).asmatrix(), c.asmatrix() + b.asmatrix(), atol=1e-14)
+
+
+@pytest.mark.parametrize("n,m", [(4, 4), (2, 4), (4, 2)])
+def test_matvec_and_batched(api, n, m):
+    """test_matrix.py:169-233 incl. rectangular and (m, nbatch) right-hand sides."""
+    M, F, O = api
+    rs = np.random.RandomState(100)
+    mats = [M.DiagonalMatrix(np.ones(min(n, m)), shape=(n, m)), M.ScaledIdentityMatrix((n, m), 1 + 1j),
+            M.PartialDiagonalMatrix(_rc(rs, n // 2, m // 2), (2,)),
+            M.PartialDiagonalMatrix(M.DiagonalMatrix(_rc(rs, min(n // 2, m // 2)), (n // 2, m // 2)), (2,)),
+            M.DenseMatrix(_rc(rs, n, m))]
+    if n == m:
+        mats.append(M.PartialDiagonalMatrix(M.ScaledIdentityMatrix(n // 2, 1.0), (2,)))
+    for v in (np.ones(m), _rc(rs, m, 3)):
+        for mat in mats:
+            mv = mat @ v
+            assert isinstance(mv, np.ndarray)
+            np.testing.assert_allclose(mv, mat.asmatrix() @ v, atol=1e-14)
+            dv = mat @ torch.from_numpy(np.asarray(v, dtype=complex)).cuda()
+            assert isinstance(dv, torch.Tensor) and dv.is_cuda
+            np.testing.assert_allclose(dv.cpu().numpy(), mat.asmatrix() @ v, atol=1e-14)
+
+
+def test_rectangular_diagonal_product_and_helpers(api):
+    """test_matrix.py:236-257."""
+    M, F, O = api
+    rs = np.random.RandomState(100)
+    a = M.DiagonalMatrix(rs.randn(2), shape=(4, 2))
+    b = M.DiagonalMatrix(rs.randn(2), shape=(2, 4))
+    ab = a @ b
+    ref = np.zeros(4)
+    ref[:2] = a.diagonals * b.diagonals
+    np.testing.assert_allclose(ab.diagonals, ref)
+    np.testing.assert_allclose(M._vecprod(np.ones(1), np.ones(2), 3), [1, 0, 0])
+    np.testing.assert_allclose(M._pad_by_zero(np.ones(1), 3), [1, 0, 0])
+    assert M.matrix_hash(M.DenseMatrix(np.eye(2))) == M.matrix_hash(np.eye(2))
+    assert M.identity(3).coeff == 1.0 and isinstance(M.asmatrixtype(np.eye(2)), M.DenseMatrix)
+
+
+# ------------------------------------------------------------------ objectivefunc.py
+def test_terms_golden(api):
+    """test_objectivefunc.py:34-144 cases; expected values from the reference itself."""
+    M, F, O = api
+    g = golden("terms")
+    x = F.LeastSquares(2.0, g["A"], g["y"]).solve(g["h"], M.DenseMatrix(g["mu"]))
+    assert rel(x, g["x_ls"]) < TOL
+    cls = F.ConstrainedLeastSquares(2.0, g["A"], g["y"], g["C"], g["D"])
+    xc = cls.solve(g["h"], M.DenseMatrix(g["mu"]))
+    assert rel(xc, g["x_cls"]) < TOL
+    assert np.abs(g["C"] @ xc - g["D"]).max() < 1e-10             # test_objectivefunc.py:101
+    xp = F.LeastSquares(0.3, M.PartialDiagonalMatrix(g["a2"], (20,)), g["y2"]).solve(g["h2"], M.ScaledIdentityMatrix(20, 1.5))
+    assert rel(xp, g["x_partial"]) < TOL
+    xl = F.L1Regularizer(0.3, 7).solve(g["hl"], M.DiagonalMatrix(np.linspace(0.5, 2.0, 7)))
+    assert xl.dtype == np.float64 and np.array_equal(xl == 0, g["x_l1"] == 0) and rel(xl, g["x_l1"]) < 1e-14
+    xn = F.NonNegativePenalty(7).solve(g["hl"] + 0.1j, M.ScaledIdentityMatrix(7, 0.7))
+    assert rel(xn, g["x_nn"]) < 1e-14 and (xn >= 0).all()
+    with pytest.raises(AssertionError):
+        F.L1Regularizer(0.3, 7).solve(g["hl"], M.DenseMatrix(np.eye(7)))
+    # objective values
+    ls = F.LeastSquares(2.0, g["A"], g["y"])
+    assert abs(ls(x) - 2.0 * np.linalg.norm(g["y"] - g["A"] @ x) ** 2) < 1e-12
+    assert abs(F.L1Regularizer(0.3, 7)(xl) - 0.3 * np.abs(xl).sum()) < 1e-14
+
+
+def test_ridge_with_l2(api):
+    """test_optimizer.py:85-109 (L2Regularizer)."""
+    M, F, O = api
+    rs = np.random.RandomState(100)
+    y, A, B = _rc(rs, 2), _rc(rs, 2, 2), _rc(rs, 1, 2)
+    model = O.Model([F.LeastSquares(1.0, A, y), F.L2Regularizer(1, B)], [(1, 0, M.identity(2), M.identity(2))])
+    opt = O.SimpleOptimizer(model)
+    opt.solve(niter=100, update_h=True)
+    x_ref = np.linalg.inv(A.conj().T @ A + B.conj().T @ B) @ A.conj().T @ y
+    np.testing.assert_allclose(opt.x[0], x_ref, atol=np.abs(x_ref).max() * 1e-8)
+
+
+# ------------------------------------------------------------------ optimizer.py
+def test_lasso_and_basis_pursuit_dropin(api):
+    """test_optimizer.py:13-82 through the drop-in API (fused pattern A engine)."""
+    M, F, O = api
+    from admmsolver_b200 import problems
+    g = golden("lasso_1x2")
+    opt = O.SimpleOptimizer(O.Model([F.LeastSquares(1.0, g["A"], g["y"]), F.L1Regularizer(0.1, 2)],
+                                    [(1, 0, M.identity(2), M.identity(2))]))
+    assert opt._plan_kind == "bp"
+    opt.solve(100)
+    assert len(opt._primal_residual) == len(g["primal"])
+    for k, name in enumerate(("x0", "x1")):
+        assert rel(opt.x[k], g[name]) < TOL
+    A, y, xa = problems.basis_pursuit_instance(100, 1000, 20, 1234)
+    g = golden("bp_notebook")
+    opt = O.SimpleOptimizer(O.Problem([F.LeastSquares(1.0, A, g["y"]), F.L1Regularizer(1e-1, 1000)],
+                                      [O.EqualityCondition(1, 0, M.identity(1000), M.identity(1000))]))
+    opt.solve(100)
+    np.testing.assert_allclose(opt.x[0], xa, atol=1e-2 * np.abs(xa).max(), rtol=0)
+    assert opt.x[0].dtype == np.complex128
+    assert rel(opt.x[0], g["x0"]) < TOL and rel(opt._h[1, 0], g["h10"]) < 1e-8
+    assert abs(opt(opt.x) - g["objective"]) / g["objective"] < TOL
+    assert opt._mu[1, 0] == g["mu10"]
+    assert rel(opt._primal_residual, g["primal"]) < 1e-8 and rel(opt._dual_residual, g["dual"]) < 1e-8
+
+
+def test_generic_executor_equals_fused_and_golden(api):
+    """The generic device executor (callback forces it) walks the same trajectory as the reference."""
+    M, F, O = api
+    g = golden("bp_tall")
+    mk = lambda: O.SimpleOptimizer(O.Model([F.LeastSquares(0.7, g["A"], g["y"]), F.L1Regularizer(0.05, 40)],
+                                           [(1, 0, M.identity(40), M.identity(40))]))
+    calls = []
+    opt = mk()
+    opt.solve(250, callback=lambda: calls.append(1))
+    assert len(calls) == 250
+    assert rel(opt.x[0], g["x0"]) < TOL and rel(opt.x[1], g["x1"]) < TOL and opt._mu[1, 0] == g["mu10"]
+    assert rel(opt._primal_residual, g["primal"]) < 1e-8
+    # step-wise public methods
+    opt2 = mk()
+    with pytest.raises(AttributeError):
+        opt2.residual()
+    for it in range(3):
+        opt2.one_sweep(update_h=True)
+        p, d = opt2.residual()
+        assert abs(p - g["primal"][it]) / g["primal"][it] < 1e-9
+        opt2.check_convergence(1e-12)
+        if it % 100 == 0:
+            opt2.update_mu()
+
+
+def test_generic_three_term_dense_couplings(api):
+    """Dense rectangular E, rectangular diagonal partner: not a fused pattern -> generic executor."""
+    M, F, O = api
+    g = golden("generic3")
+    lst, l1, nn = F.LeastSquares(1.3, g["A"], g["y"]), F.L1Regularizer(0.2, 5), F.NonNegativePenalty(4)
+    conds = [(0, 1, g["E1"], M.identity(5)), (0, 2, g["P"], M.DiagonalMatrix(np.linspace(1.0, 2.0, 4)))]
+    opt = O.SimpleOptimizer(O.Model([lst, l1, nn], conds), mu=0.7)
+    assert opt._plan_kind is None
+    opt.solve(150, interval_update_mu=20)
+    for k in range(3):
+        assert rel(opt.x[k], g[f"x{k}"]) < 1e-9
+    assert opt._mu[1, 0] == g["mu10"] and opt._mu[2, 0] == g["mu20"]
+    assert rel(opt._primal_residual, g["primal"]) < 1e-8
+    assert abs(opt(opt.x) - g["objective"]) / g["objective"] < 1e-9
+
+
+def test_spm_notebook_flow_dropin(api):
+    """spm.ipynb:243-259 through the drop-in API: single problem (fused pattern B engine)."""
+    M, F, O = api
+    g = golden("spm_small")
+    L, Nw = g["s"].size, g["P"].shape[0]
+    lstsq = F.ConstrainedLeastSquares(1.0, -M.DiagonalMatrix(g["s"]), g["g"], g["C"], np.array([1]))
+    conds = [(0, 1, M.identity(L), M.identity(L)), (0, 2, g["P"], M.identity(Nw))]
+    opt = O.SimpleOptimizer(O.Problem([lstsq, F.L1Regularizer(float(g["lam"]), L), F.NonNegativePenalty(Nw)], conds), mu=0.1)
+    assert opt._plan_kind == "spm"
+    opt.solve(700)
+    for k in range(3):
+        assert rel(opt.x[k], g[f"x{k}"]) < TOL
+    assert rel(opt._h[2, 0], g["h20"]) < 1e-8
+    assert abs((g["C"] @ opt.x[0])[0] - 1) < 1e-12                 # spm.ipynb:270
+    assert abs(opt(opt.x) - g["objective"]) / g["objective"] < TOL
+    assert len(opt._primal_residual) == 700 and rel(opt._primal_residual, g["primal"]) < 1e-8
+
+
+def test_spm_packed_partialdiagonal_dropin(api):
+    """The reference's own batching: PartialDiagonalMatrix-packed operators -> fused engine, batch-wide mu."""
+    M, F, O = api
+    g = golden("spm_packed")
+    nb, L, Nw = 6, g["s"].size, g["P"].shape[0]
+    rest = (nb,)
+    lstsq = F.ConstrainedLeastSquares(1.0, M.PartialDiagonalMatrix(-M.DiagonalMatrix(g["s"]), rest), g["g"].ravel(),
+                                      M.PartialDiagonalMatrix(g["C"], rest), np.ones(nb))
+    conds = [(0, 1, M.identity(L * nb), M.identity(L * nb)),
+             (0, 2, M.PartialDiagonalMatrix(g["P"], rest), M.identity(Nw * nb))]
+    opt = O.SimpleOptimizer(O.Model([lstsq, F.L1Regularizer(float(g["lam"]), L * nb), F.NonNegativePenalty(Nw * nb)], conds),
+                            mu=float(g["mu"]))
+    assert opt._plan_kind == "spm"
+    opt.solve(250)
+    opt.solve(150)                                                 # resume like the reference
+    # two calls restart the `iter % interval` phase: compare with the oracle doing the same
+    from oracle import flat
+    st = flat.spm_solve(g["s"], g["P"], g["C"], np.ones(nb), g["g"], float(g["lam"]), 250, mu=float(g["mu"]))
+    st = flat.spm_solve(g["s"], g["P"], g["C"], np.ones(nb), g["g"], float(g["lam"]), 150, mu=float(g["mu"]), state=st)
+    assert rel(opt.x[0], st.x0.ravel()) < TOL and rel(opt.x[2], st.x2.ravel()) < TOL
+    assert opt._mu[1, 0] == st.mu10 and opt._mu[2, 0] == st.mu20
+    # and the generic executor on the same packed model (callback) follows the reference golden
+    opt2 = O.SimpleOptimizer(O.Model([lstsq, F.L1Regularizer(float(g["lam"]), L * nb), F.NonNegativePenalty(Nw * nb)], conds),
+                             mu=float(g["mu"]))
+    opt2.solve(30, callback=lambda: None)
+    assert rel(opt2._primal_residual, g["primal"][:30]) < 1e-8

@@ -31,7 +31,7 @@ class AdmmError(RuntimeError):
 
 class SpmDims(C.Structure):
     _fields_ = [(n, C.c_int) for n in
-                ("L", "Lp", "ldp", "Nw", "nrt", "nb", "npt", "nplanes", "nsplit", "batch_wide")]
+                ("L", "Lp", "ldp", "Nw", "nrt", "nb", "npt", "nplanes", "nsplit", "mt", "batch_wide")]
 
 
 _P = C.c_void_p
@@ -42,7 +42,7 @@ class SpmBuffers(C.Structure):
         ("Psw", _P), ("PtP", _P), ("Cvec", _P), ("Ginv_cache", _P), ("w_cache", _P), ("sigma_cache", _P),
         ("slot", _P), ("mu10", _P), ("mu20", _P), ("mu20_used", _P), ("done", _P), ("iters", _P),
         ("last_res", _P), ("Dre", _P),
-        ("b0", _P), ("x0", _P), ("x1", _P), ("h10", _P), ("V", _P), ("Vx", _P),
+        ("b0", _P), ("x0", _P), ("x1", _P), ("h10", _P), ("V", _P), ("Vx", _P), ("aim", _P),
         ("S", _P),
         ("normsA", _P), ("normsB", _P), ("gsum", _P), ("gpart", _P),
         ("iter_counter", _P), ("flags", _P), ("history", _P), ("hist_cap", C.c_int),
@@ -82,7 +82,7 @@ _SIGS = {
     "admm_spm_pack_L": ([C.POINTER(SpmDims), _P, _I, _P, _P], _I),
     "admm_spm_unpack_L": ([C.POINTER(SpmDims), _P, _P, _I, _P], _I),
     "admm_spm_pack_state": ([C.POINTER(SpmDims), _P, _P, _I, _P, _P, _P, _P], _I),
-    "admm_spm_unpack_state": ([C.POINTER(SpmDims), _P, _P, _P, _P, _I, _P], _I),
+    "admm_spm_unpack_state": ([C.POINTER(SpmDims), _P, _P, _P, _P, _P, _I, _P], _I),
     "admm_spm_factor": ([C.POINTER(SpmDims), _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "admm_spm_xupdate": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
     "admm_spm_pass": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),

@@ -119,11 +119,12 @@ class SharedSpM:
         npt = (nb + 7) // 8
         nplanes = 2 if cplx else 1
         nchunks = nrt // 4
+        mt = 2 if npt >= 64 else 1                   # problem tiles per warp in the pass kernel
         if nsplit is None:
-            col_ctas = (npt + 3) // 4
+            col_ctas = -(-npt // (4 * mt))
             nsplit = max(1, min(nchunks, -(-444 // col_ctas)))
         nsplit = max(1, min(nsplit, nchunks))
-        self.dims = SpmDims(L, Lp, ldp, Nw, nrt, nb, npt, nplanes, nsplit, int(batch_wide))
+        self.dims = SpmDims(L, Lp, ldp, Nw, nrt, nb, npt, nplanes, nsplit, mt, int(batch_wide))
         self.batch_wide = bool(batch_wide)
         self.lam, self.max_mu = float(lam), float(max_mu)
         nprob = 8 * npt
@@ -169,7 +170,9 @@ class SharedSpM:
         call("admm_spm_pack_L", dref, ptr(b0.contiguous()), int(b0.is_complex()), ptr(self.b0), stream())
         self.x0f, self.x1f, self.h10f = z(fl), z(fl), z(fl)
         self.V, self.Vx = z(nsplit * fl), z(nsplit * fl)
-        self.S = z(npt * nrt * nplanes * 64)
+        self.aim = z(fl)                  # sum_k mu20_k Im(x0_k)  (imaginary-plane tiles only)
+        self._him_base = None             # Im(h20) at the time of set_state (None == 0)
+        self.S = z(npt * nrt * 64)
         self.normsA = z(nct * 8 * 8)
         self.normsB = z(nsplit * nct * 8 * 4)
         self.gsum = z(16)
@@ -192,7 +195,7 @@ class SharedSpM:
                         ("mu10", self.mu10), ("mu20", self.mu20), ("mu20_used", self.mu20_used), ("done", self.done),
                         ("iters", self.iters), ("last_res", self.last_res), ("Dre", self.Dre), ("b0", self.b0),
                         ("x0", self.x0f), ("x1", self.x1f), ("h10", self.h10f), ("V", self.V), ("Vx", self.Vx),
-                        ("S", self.S), ("normsA", self.normsA), ("normsB", self.normsB), ("gsum", self.gsum),
+                        ("aim", self.aim), ("S", self.S), ("normsA", self.normsA), ("normsB", self.normsB), ("gsum", self.gsum),
                         ("gpart", self.gpart), ("iter_counter", self.iter_counter), ("flags", self.flags)):
             setattr(b, name, t.data_ptr())
         b.history = self.history.data_ptr() if self.history is not None else None
@@ -245,8 +248,9 @@ class SharedSpM:
     def reset(self, g=None, mu: Optional[float] = None) -> None:
         """Zero the ADMM state (x, h), optionally load new data ``g`` (L x nb, device or host) and
         reset the penalties -- lets one plan serve many batches without re-allocating."""
-        for t in (self.x0f, self.x1f, self.h10f, self.S, self.V, self.Vx):
+        for t in (self.x0f, self.x1f, self.h10f, self.S, self.V, self.Vx, self.aim):
             t.zero_()
+        self._him_base = None
         if mu is not None:
             self.mu10.fill_(float(mu))
             self.mu20.fill_(float(mu))
@@ -295,7 +299,29 @@ class SharedSpM:
             if int(flag.item()) != 0:
                 raise NotImplementedError("(h20, x2) state is not complementary; use the generic executor")
             self.mu20_used.copy_(self.mu20)
+            # imaginary part of h20: kept as a base plane + the L-space accumulators (z, a)
+            self.aim.zero_()
+            him = h.imag.contiguous() if cp else None
+            if him is not None and float(him.abs().max().item()) == 0.0:
+                him = None
+            self._him_base = him
+            if self.is_complex:
+                zc = torch.zeros(self.L, self.nb, dtype=_C128, device=self.device)
+                if him is not None:
+                    zr = torch.empty(self.L, self.nb, dtype=_F64, device=self.device)
+                    call("admm_gemm", 0, _lib.OP_T, self.L, self.nb, self.Nw, ptr(self.P), self.L, ptr(him), self.nb,
+                         ptr(zr), self.nb, stream())
+                    zc = torch.complex(torch.zeros_like(zr), zr)
+                self._set_imag_tiles(self.V, zc)
         self._v_state = "none"
+
+    def _set_imag_tiles(self, frag_arr: torch.Tensor, canon_c: torch.Tensor) -> None:
+        """Write Im(canon_c) (L x nb) into the imaginary-plane tiles of a fragment array (split 0)."""
+        NT = self.dims.Lp // 8
+        fl = self.dims.npt * self.dims.nplanes * NT * 64
+        tmp = torch.empty(fl, dtype=_F64, device=self.device)
+        call("admm_spm_pack_L", C.byref(self.dims), ptr(canon_c.contiguous()), 1, ptr(tmp), stream())
+        frag_arr[:fl].view(self.dims.npt, 2, NT * 64)[:, 1, :] = tmp.view(self.dims.npt, 2, NT * 64)[:, 1, :]
 
     def _unpack_L(self, frag) -> np.ndarray:
         out = torch.empty(self.L, self.nb, dtype=_C128, device=self.device)
@@ -314,7 +340,24 @@ class SharedSpM:
     def _unpack_state(self):
         h = torch.empty(self.Nw, self.nb, dtype=_C128, device=self.device)
         x = torch.empty(self.Nw, self.nb, dtype=_C128, device=self.device)
-        call("admm_spm_unpack_state", C.byref(self.dims), ptr(self.S), ptr(self.mu20_used), ptr(h), ptr(x), 1, stream())
+        him = None
+        if self.is_complex:
+            # Im(h20) = Im(h20)_base - P a,   a = sum_k mu20_k Im(x0_k)
+            a_c = torch.empty(self.L, self.nb, dtype=_C128, device=self.device)
+            call("admm_spm_unpack_L", C.byref(self.dims), ptr(self.aim), ptr(a_c), 1, stream())
+            a_im = a_c.imag.contiguous()
+            Pa = torch.empty(self.Nw, self.nb, dtype=_F64, device=self.device)
+            call("admm_gemm", 0, _lib.OP_N, self.Nw, self.nb, self.L, ptr(self.P), self.L, ptr(a_im), self.nb,
+                 ptr(Pa), self.nb, stream())
+            him = torch.empty_like(Pa)
+            base = self._him_base
+            n = Pa.numel()
+            if base is None:
+                call("admm_axpby", n, -1.0, ptr(Pa), 0.0, None, ptr(him), stream())
+            else:
+                call("admm_axpby", n, -1.0, ptr(Pa), 1.0, ptr(base), ptr(him), stream())
+        call("admm_spm_unpack_state", C.byref(self.dims), ptr(self.S), ptr(self.mu20_used), ptr(him), ptr(h), ptr(x), 1,
+             stream())
         return h, x
 
     def x2(self) -> np.ndarray:

@@ -73,20 +73,20 @@ __global__ void unpack_L_kernel(admm_spm_dims d, const double* __restrict__ frag
   }
 }
 
-__device__ __forceinline__ size_t state_index(const admm_spm_dims& d, int pt, int rt, int pl, int lane) {
-  return ((((size_t)pt * d.nrt + rt) * d.nplanes + pl) * 32 + lane) * 2;
+// implicit (h20, x2) state: ONE real plane S[pt][rt][lane][2]  (the imaginary part of h20 never
+// leaves L-space: see xupdate)
+__device__ __forceinline__ size_t state_index(const admm_spm_dims& d, int pt, int rt, int lane) {
+  return (((size_t)pt * d.nrt + rt) * 32 + lane) * 2;
 }
 
 __global__ void pack_state_kernel(admm_spm_dims d, const double* __restrict__ h20, const double* __restrict__ x2,
                                   int src_cplx, const double* __restrict__ mu20, double* __restrict__ S,
                                   int* __restrict__ flag) {
-  const long long total = (long long)d.npt * d.nrt * d.nplanes * 64;
+  const long long total = (long long)d.npt * d.nrt * 64;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int e = int(idx & 1), lane = int((idx >> 1) & 31);
-    long long q = idx >> 6;
-    const int pl = int(q % d.nplanes);
-    q /= d.nplanes;
+    const long long q = idx >> 6;
     const int rt = int(q % d.nrt), pt = int(q / d.nrt);
     const int g = lane >> 2, t = lane & 3;
     const int r = 8 * rt + 2 * t + e, prob = 8 * pt + g;
@@ -97,28 +97,25 @@ __global__ void pack_state_kernel(admm_spm_dims d, const double* __restrict__ h2
       const double him = src_cplx ? h20[2 * o + 1] : 0.0;
       const double xre = src_cplx ? x2[2 * o] : x2[o];
       const double xim = src_cplx ? x2[2 * o + 1] : 0.0;
-      if (pl == 0) {
-        v = hre - mu20[prob] * xre;
-        if (xre < 0.0 || xim != 0.0 || hre < 0.0 || (hre != 0.0 && xre != 0.0)) flag[0] = 1;
-        if (d.nplanes == 1 && him != 0.0) flag[0] = 1;
-      } else {
-        v = him;
-      }
+      v = hre - mu20[prob] * xre;
+      if (xre < 0.0 || xim != 0.0 || hre < 0.0 || (hre != 0.0 && xre != 0.0)) flag[0] = 1;
+      if (d.nplanes == 1 && him != 0.0) flag[0] = 1;
     }
     S[idx] = v;
   }
 }
 
 __global__ void unpack_state_kernel(admm_spm_dims d, const double* __restrict__ S, const double* __restrict__ mu20_used,
-                                    double* __restrict__ h20, double* __restrict__ x2, int dst_cplx) {
+                                    const double* __restrict__ him_all, double* __restrict__ h20, double* __restrict__ x2,
+                                    int dst_cplx) {
   const long long total = (long long)d.Nw * d.nb;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int r = int(idx / d.nb), prob = int(idx % d.nb);
     const int pt = prob >> 3, g = prob & 7, rt = r >> 3, t = (r & 7) >> 1, e = r & 1;
     const int lane = 4 * g + t;
-    const double s = S[state_index(d, pt, rt, 0, lane) + e];
-    const double him = d.nplanes == 2 ? S[state_index(d, pt, rt, 1, lane) + e] : 0.0;
+    const double s = S[state_index(d, pt, rt, lane) + e];
+    const double him = him_all ? him_all[idx] : 0.0;
     const double hre = s > 0.0 ? s : 0.0;
     const double xv = s < 0.0 ? (-s) / mu20_used[prob] : 0.0;
     if (dst_cplx) {
@@ -236,7 +233,7 @@ __global__ void __launch_bounds__(128) spm_xupdate_kernel(admm_spm_dims d, admm_
   const int Lp = d.Lp;
   const size_t vstride = (size_t)nct * NT * 64;
 
-  double rhs[NT][2], x0o[NT][2], h10[NT][2];
+  double rhs[NT][2], x0o[NT][2], h10[NT][2], zv[NT][2];
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
     const size_t o = frag_index(ct, NT, j, lane);
@@ -245,7 +242,10 @@ __global__ void __launch_bounds__(128) spm_xupdate_kernel(admm_spm_dims d, admm_
     const double2 x1 = *reinterpret_cast<const double2*>(b.x1 + o);
     const double2 xo = *reinterpret_cast<const double2*>(b.x0 + o);
     double2 v = make_double2(0.0, 0.0);
-    for (int sp = 0; sp < d.nsplit; ++sp) {
+    // real plane: partial sums of P^T(h20 + mu20 x2) from the pass kernel's row splits;
+    // imaginary plane: z = P^T Im(h20), kept in slot 0 by this kernel (never touched by pass)
+    const int nsp = pl == 0 ? d.nsplit : 1;
+    for (int sp = 0; sp < nsp; ++sp) {
       const double2 p = *reinterpret_cast<const double2*>(b.V + sp * vstride + o);
       v.x += p.x;
       v.y += p.y;
@@ -260,6 +260,8 @@ __global__ void __launch_bounds__(128) spm_xupdate_kernel(admm_spm_dims d, admm_
       v.x += mu20 * vx.x;
       v.y += mu20 * vx.y;
     }
+    zv[j][0] = v.x;
+    zv[j][1] = v.y;
     rhs[j][0] = b0.x + hh.x + mu10 * x1.x + v.x;
     rhs[j][1] = b0.y + hh.y + mu10 * x1.y + v.y;
     x0o[j][0] = xo.x;
@@ -310,18 +312,36 @@ __global__ void __launch_bounds__(128) spm_xupdate_kernel(admm_spm_dims d, admm_
     }
   }
 
-  // Gram-form norms of pair (2,0):  |P d|^2 = d^T (P^T P) d,  |P x0_old|^2
-  double nPd, nPxo;
+  // Gram-form norms of pair (2,0):  |P d|^2 = d^T (P^T P) d,  |P x0_old|^2  (and, for the
+  // imaginary plane, |P x0|^2 and z <- z - mu20 P^T P x0: Im(h20) only ever enters through
+  // P^T Im(h20), so the imaginary half of the state never leaves L-space)
+  double nPd, nPxo, nPx = 0.0;
   {
-    double y[NT][2];
-    frag_gemm<NT>(y, dd, b.PtP, Lp, g, t);
+    double yd[NT][2], yo[NT][2];
+    frag_gemm<NT>(yd, dd, b.PtP, Lp, g, t);
+    frag_gemm<NT>(yo, x0o, b.PtP, Lp, g, t);
     nPd = 0.0;
-#pragma unroll
-    for (int j = 0; j < NT; ++j) nPd += y[j][0] * dd[j][0] + y[j][1] * dd[j][1];
-    frag_gemm<NT>(y, x0o, b.PtP, Lp, g, t);
     nPxo = 0.0;
 #pragma unroll
-    for (int j = 0; j < NT; ++j) nPxo += y[j][0] * x0o[j][0] + y[j][1] * x0o[j][1];
+    for (int j = 0; j < NT; ++j) {
+      nPd += yd[j][0] * dd[j][0] + yd[j][1] * dd[j][1];
+      nPxo += yo[j][0] * x0o[j][0] + yo[j][1] * x0o[j][1];
+    }
+    if (pl == 1) {
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const double y0 = yd[j][0] + yo[j][0], y1 = yd[j][1] + yo[j][1];   // P^T P x0 (linear)
+        nPx += y0 * x0[j][0] + y1 * x0[j][1];
+        if (!is_done) {
+          const size_t o = frag_index(ct, NT, j, lane);
+          *reinterpret_cast<double2*>(b.V + o) = make_double2(zv[j][0] - mu20 * y0, zv[j][1] - mu20 * y1);
+          double2 av = *reinterpret_cast<const double2*>(b.aim + o);
+          av.x += mu20 * x0[j][0];
+          av.y += mu20 * x0[j][1];
+          *reinterpret_cast<double2*>(b.aim + o) = av;
+        }
+      }
+    }
   }
 
   // L1 z-update (real plane only; the imaginary part of x1 is identically zero) + dual ascent
@@ -362,6 +382,7 @@ __global__ void __launch_bounds__(128) spm_xupdate_kernel(admm_spm_dims d, admm_
   n_xo = quad_sum(n_xo);
   nPd = quad_sum(nPd);
   nPxo = quad_sum(nPxo);
+  nPx = quad_sum(nPx);
   if (t == 0 && !is_done) {
     double* o = b.normsA + ((size_t)ct * 8 + g) * 8;
     o[0] = n_p;
@@ -371,18 +392,19 @@ __global__ void __launch_bounds__(128) spm_xupdate_kernel(admm_spm_dims d, admm_
     o[4] = n_xo;
     o[5] = nPd > 0.0 ? nPd : 0.0;
     o[6] = nPxo > 0.0 ? nPxo : 0.0;
+    o[7] = nPx > 0.0 ? nPx : 0.0;     // imaginary plane only: |P Im(x0)|^2
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // pass: the streaming sweep with both skinny GEMMs on the FP64 tensor cores
 // ---------------------------------------------------------------------------------------------
-constexpr int PASS_WARPS = 4;     // warps per CTA; each warp owns one tile of 8 problems
+constexpr int PASS_WARPS = 4;     // warps per CTA; each warp owns MT tiles of 8 problems
 constexpr int PASS_STAGES = 3;    // cp.async ring depth for P chunks
 constexpr int PASS_CHUNK_RT = 4;  // 8-row tiles per P chunk (32 rows)
 
-template <int NT, int NPL, int MODE>
-__global__ void __launch_bounds__(PASS_WARPS * 32) spm_pass_kernel(admm_spm_dims d, admm_spm_buffers b) {
+template <int NT, int MT, int MODE>
+__global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4) spm_pass_kernel(admm_spm_dims d, admm_spm_buffers b) {
   extern __shared__ __align__(16) double Pst[];  // [PASS_STAGES][32 * ldp]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int ldp = d.ldp;
@@ -392,32 +414,44 @@ __global__ void __launch_bounds__(PASS_WARPS * 32) spm_pass_kernel(admm_spm_dims
   const int sp = blockIdx.y;
   const int c_begin = sp * cps, c_end = min(nchunks_total, c_begin + cps);
   const int nchunks = max(0, c_end - c_begin);
+  const int npl = d.nplanes;
 
-  const int pt = blockIdx.x * PASS_WARPS + warp;
-  const bool in_range = pt < d.npt;
-  const int prob = 8 * (in_range ? pt : 0) + g;
-  const int dn = in_range ? b.done[prob] : 1;
-  const bool active = !__all_sync(0xffffffffu, dn);
-  const double mu20 = b.mu20[prob];
-  const double inv_mu20 = 1.0 / mu20;
+  // this warp's MT problem tiles (real plane only)
+  int pt[MT];
+  bool inr[MT];
+  int dn[MT];
+  double mu20[MT], inv_mu20[MT];
+  bool all_done = true;
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    pt[m] = (blockIdx.x * PASS_WARPS + warp) * MT + m;
+    inr[m] = pt[m] < d.npt;
+    const int prob = 8 * (inr[m] ? pt[m] : 0) + g;
+    dn[m] = inr[m] ? b.done[prob] : 1;
+    mu20[m] = b.mu20[prob];
+    inv_mu20[m] = 1.0 / mu20[m];
+    all_done = all_done && dn[m];
+  }
+  const bool active = !__all_sync(0xffffffffu, all_done);
 
   // A fragments of GEMM1': x0 in fragment layout (k-slot (j,e) of lane (g,t) <-> l = 8j+2t+e)
-  double xa[NPL][NT][2];
-  double acc[NPL][NT][2];
-  double accx[NT][2];
+  double xa[MT][NT][2];
+  double acc[MT][NT][2];
+  double accx[MODE != 0 ? MT : 1][NT][2];
 #pragma unroll
-  for (int p = 0; p < NPL; ++p)
+  for (int m = 0; m < MT; ++m)
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       double2 v = make_double2(0.0, 0.0);
-      if (active) v = *reinterpret_cast<const double2*>(b.x0 + frag_index(pt * NPL + p, NT, j, lane));
-      xa[p][j][0] = v.x;
-      xa[p][j][1] = v.y;
-      acc[p][j][0] = acc[p][j][1] = 0.0;
+      if (active && inr[m]) v = *reinterpret_cast<const double2*>(b.x0 + frag_index(pt[m] * npl, NT, j, lane));
+      xa[m][j][0] = v.x;
+      xa[m][j][1] = v.y;
+      acc[m][j][0] = acc[m][j][1] = 0.0;
+      if (MODE != 0) accx[m][j][0] = accx[m][j][1] = 0.0;
     }
+  double n_diff[MT], n_x2[MT], n_q[MT];
 #pragma unroll
-  for (int j = 0; j < NT; ++j) accx[j][0] = accx[j][1] = 0.0;
-  double n_diff = 0.0, n_x2 = 0.0, n_q = 0.0, n_qi = 0.0;
+  for (int m = 0; m < MT; ++m) n_diff[m] = n_x2[m] = n_q[m] = 0.0;
 
   auto load_chunk = [&](int c, int buf) {
     const double* src = b.Psw + (size_t)(c_begin + c) * chunk_elems;
@@ -434,10 +468,11 @@ __global__ void __launch_bounds__(PASS_WARPS * 32) spm_pass_kernel(admm_spm_dims
   const int sw0 = p_swz(2 * t), sw1 = p_swz(2 * t + 1);
 
   // software prefetch of the state of the next 8-row tile
-  double2 st_nxt[NPL];
+  double2 st_nxt[MT];
   auto load_state = [&](int rt) {
 #pragma unroll
-    for (int p = 0; p < NPL; ++p) st_nxt[p] = ld_stream2(b.S + state_index(d, pt, rt, p, lane));
+    for (int m = 0; m < MT; ++m)
+      st_nxt[m] = inr[m] ? ld_stream2(b.S + state_index(d, pt[m], rt, lane)) : make_double2(0.0, 0.0);
   };
   if (active && nchunks > 0) load_state(c_begin * PASS_CHUNK_RT);
 
@@ -452,78 +487,62 @@ __global__ void __launch_bounds__(PASS_WARPS * 32) spm_pass_kernel(admm_spm_dims
     for (int r4 = 0; r4 < PASS_CHUNK_RT; ++r4) {
       const int rt = (c_begin + c) * PASS_CHUNK_RT + r4;
       const double* Pb = Pc + r4 * 8 * ldp;
-      double2 st[NPL];
+      double2 st[MT];
 #pragma unroll
-      for (int p = 0; p < NPL; ++p) st[p] = st_nxt[p];
+      for (int m = 0; m < MT; ++m) st[m] = st_nxt[m];
       const bool last = (c == nchunks - 1) && (r4 == PASS_CHUNK_RT - 1);
       if (!last) load_state(rt + 1);
 
-      // ---- GEMM1': q[c][r] = sum_l x0[l][c] P[r][l]
-      double q[NPL][2];
+      // ---- GEMM1': q[c][r] = sum_l x0[l][c] P[r][l]   (two independent accumulation chains per tile)
+      double q[MT][2], q2[MT][2];
 #pragma unroll
-      for (int p = 0; p < NPL; ++p) q[p][0] = q[p][1] = 0.0;
+      for (int m = 0; m < MT; ++m) q[m][0] = q[m][1] = q2[m][0] = q2[m][1] = 0.0;
       {
         const double* prow = Pb + g * ldp;
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
           const double2 bb = *reinterpret_cast<const double2*>(prow + ((8 * j + 2 * t) ^ swg));
 #pragma unroll
-          for (int p = 0; p < NPL; ++p) {
-            dmma(q[p][0], q[p][1], xa[p][j][0], bb.x);
-            dmma(q[p][0], q[p][1], xa[p][j][1], bb.y);
+          for (int m = 0; m < MT; ++m) {
+            dmma(q[m][0], q[m][1], xa[m][j][0], bb.x);
+            dmma(q2[m][0], q2[m][1], xa[m][j][1], bb.y);
           }
         }
       }
 
       // ---- elementwise: non-negative z-update, dual ascent, residual partials
-      double u[NPL][2], ux[2];
-      {
+      double u[MT][2], ux[MT][2];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
         double sn[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const double s_old = e == 0 ? st[0].x : st[0].y;
+          const double s_old = e == 0 ? st[m].x : st[m].y;
           const double hre = s_old > 0.0 ? s_old : 0.0;
-          const double qv = q[0][e];
+          const double qv = q[m][e] + q2[m][e];
           if (MODE == 2) {
             sn[e] = s_old;
-            u[0][e] = hre;
-            ux[e] = s_old < 0.0 ? (-s_old) * inv_mu20 : 0.0;
+            u[m][e] = hre;
+            ux[m][e] = s_old < 0.0 ? (-s_old) * inv_mu20[m] : 0.0;
           } else {
-            const double a = qv - hre * inv_mu20;
+            const double a = qv - hre * inv_mu20[m];
             const double x2 = a < 0.0 ? 0.0 : a;
-            const double s_new = x2 > 0.0 ? -(mu20 * x2) : hre - mu20 * qv;
+            const double s_new = x2 > 0.0 ? -(mu20[m] * x2) : hre - mu20[m] * qv;
             const double df = qv - x2;
-            n_diff += df * df;
-            n_x2 += x2 * x2;
-            n_q += qv * qv;
-            sn[e] = dn ? s_old : s_new;
+            n_diff[m] += df * df;
+            n_x2[m] += x2 * x2;
+            n_q[m] += qv * qv;
+            sn[e] = dn[m] ? s_old : s_new;
             if (MODE == 1) {
-              u[0][e] = s_new > 0.0 ? s_new : 0.0;
-              ux[e] = x2;
+              u[m][e] = s_new > 0.0 ? s_new : 0.0;
+              ux[m][e] = x2;
             } else {
-              u[0][e] = fabs(s_new);
-              ux[e] = 0.0;
+              u[m][e] = fabs(s_new);
+              ux[m][e] = 0.0;
             }
           }
         }
-        if (MODE != 2) st_stream2(b.S + state_index(d, pt, rt, 0, lane), make_double2(sn[0], sn[1]));
-      }
-      if (NPL == 2) {
-        double hn[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const double h_old = e == 0 ? st[NPL - 1].x : st[NPL - 1].y;
-          const double qv = q[NPL - 1][e];
-          if (MODE == 2) {
-            hn[e] = h_old;
-          } else {
-            const double h_new = h_old - mu20 * qv;
-            n_qi += qv * qv;
-            hn[e] = dn ? h_old : h_new;
-          }
-          u[NPL - 1][e] = hn[e];
-        }
-        if (MODE != 2) st_stream2(b.S + state_index(d, pt, rt, NPL - 1, lane), make_double2(hn[0], hn[1]));
+        if (MODE != 2 && inr[m]) st_stream2(b.S + state_index(d, pt[m], rt, lane), make_double2(sn[0], sn[1]));
       }
 
       // ---- GEMM2': V[c][l] += sum_r u[c][r] P[r][l],  k-slot t <-> row 2t+e
@@ -535,13 +554,14 @@ __global__ void __launch_bounds__(PASS_WARPS * 32) spm_pass_kernel(admm_spm_dims
           const double b0 = prow0[(8 * j + g) ^ sw0];
           const double b1 = prow1[(8 * j + g) ^ sw1];
 #pragma unroll
-          for (int p = 0; p < NPL; ++p) {
-            dmma(acc[p][j][0], acc[p][j][1], u[p][0], b0);
-            dmma(acc[p][j][0], acc[p][j][1], u[p][1], b1);
+          for (int m = 0; m < MT; ++m) {
+            dmma(acc[m][j][0], acc[m][j][1], u[m][0], b0);
+            if (MODE != 0) dmma(accx[m][j][0], accx[m][j][1], ux[m][0], b0);
           }
-          if (MODE != 0) {
-            dmma(accx[j][0], accx[j][1], ux[0], b0);
-            dmma(accx[j][0], accx[j][1], ux[1], b1);
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            dmma(acc[m][j][0], acc[m][j][1], u[m][1], b1);
+            if (MODE != 0) dmma(accx[m][j][0], accx[m][j][1], ux[m][1], b1);
           }
         }
       }
@@ -551,33 +571,24 @@ __global__ void __launch_bounds__(PASS_WARPS * 32) spm_pass_kernel(admm_spm_dims
   if (!active) return;
 
   // ---- epilogue: partial V (fragment layout) and per-column norm partials
-  const int nct = d.npt * NPL;
+  const int nct = d.npt * npl;
   const size_t vstride = (size_t)nct * NT * 64;
 #pragma unroll
-  for (int p = 0; p < NPL; ++p)
+  for (int m = 0; m < MT; ++m) {
+    if (!inr[m]) continue;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      const size_t o = sp * vstride + frag_index(pt * NPL + p, NT, j, lane);
-      *reinterpret_cast<double2*>(b.V + o) = make_double2(acc[p][j][0], acc[p][j][1]);
-      if (MODE != 0)
-        *reinterpret_cast<double2*>(b.Vx + o) =
-            p == 0 ? make_double2(accx[j][0], accx[j][1]) : make_double2(0.0, 0.0);
+      const size_t o = sp * vstride + frag_index(pt[m] * npl, NT, j, lane);
+      *reinterpret_cast<double2*>(b.V + o) = make_double2(acc[m][j][0], acc[m][j][1]);
+      if (MODE != 0) *reinterpret_cast<double2*>(b.Vx + o) = make_double2(accx[m][j][0], accx[m][j][1]);
     }
-  if (MODE != 2) {
-    n_diff = quad_sum(n_diff);
-    n_x2 = quad_sum(n_x2);
-    n_q = quad_sum(n_q);
-    if (NPL == 2) n_qi = quad_sum(n_qi);
-    if (t == 0 && !dn) {
-      double* o = b.normsB + ((size_t)sp * nct * 8 + (size_t)(pt * NPL) * 8 + g) * 4;
-      o[0] = n_diff;
-      o[1] = n_x2;
-      o[2] = n_q;
-      if (NPL == 2) {
-        double* oi = o + 8 * 4;
-        oi[0] = n_qi;
-        oi[1] = 0.0;
-        oi[2] = n_qi;
+    if (MODE != 2) {
+      const double s0 = quad_sum(n_diff[m]), s1 = quad_sum(n_x2[m]), s2 = quad_sum(n_q[m]);
+      if (t == 0 && !dn[m]) {
+        double* o = b.normsB + ((size_t)sp * nct * 8 + (size_t)(pt[m] * npl) * 8 + g) * 4;
+        o[0] = s0;
+        o[1] = s1;
+        o[2] = s2;
       }
     }
   }
@@ -596,11 +607,16 @@ __device__ __forceinline__ void gather_problem(const admm_spm_dims& d, const adm
     const double* a = b.normsA + col * 8;
 #pragma unroll
     for (int i = 0; i < 7; ++i) s[i] += a[i];
-    for (int sp = 0; sp < d.nsplit; ++sp) {
-      const double* bb = b.normsB + ((size_t)sp * nct * 8 + col) * 4;
-      s[7] += bb[0];
-      s[8] += bb[1];
-      s[9] += bb[2];
+    if (pl == 0) {
+      for (int sp = 0; sp < d.nsplit; ++sp) {
+        const double* bb = b.normsB + ((size_t)sp * nct * 8 + col) * 4;
+        s[7] += bb[0];
+        s[8] += bb[1];
+        s[9] += bb[2];
+      }
+    } else {
+      s[7] += a[7];      // |P Im(x0) - 0|^2
+      s[9] += a[7];      // |P Im(x0)|^2
     }
   }
 }
@@ -699,19 +715,20 @@ static int check_dims(const admm_spm_dims* d, const char* who) {
                "%s: nrt=%d must be a multiple of %d covering Nw=%d", who, d->nrt, PASS_CHUNK_RT, d->Nw);
   ADMM_REQUIRE(d->nb >= 1 && d->npt * 8 >= d->nb, ADMM_EINVAL, "%s: bad nb/npt", who);
   ADMM_REQUIRE(d->nplanes == 1 || d->nplanes == 2, ADMM_EINVAL, "%s: nplanes must be 1 or 2", who);
+  ADMM_REQUIRE(d->mt == 1 || d->mt == 2, ADMM_EINVAL, "%s: mt must be 1 or 2", who);
   ADMM_REQUIRE(d->nsplit >= 1 && d->nsplit <= d->nrt / PASS_CHUNK_RT, ADMM_EINVAL, "%s: bad nsplit=%d", who, d->nsplit);
   return ADMM_OK;
 }
 
 static int ew_grid(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 16)); }
 
-template <int NT, int NPL>
+template <int NT, int MT>
 static int launch_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, cudaStream_t s) {
-  dim3 grid(ceil_div(d->npt, PASS_WARPS), d->nsplit);
+  dim3 grid(ceil_div(d->npt, PASS_WARPS * MT), d->nsplit);
   const size_t smem = (size_t)PASS_STAGES * PASS_CHUNK_RT * 8 * d->ldp * sizeof(double);
-  auto k0 = spm_pass_kernel<NT, NPL, 0>;
-  auto k1 = spm_pass_kernel<NT, NPL, 1>;
-  auto k2 = spm_pass_kernel<NT, NPL, 2>;
+  auto k0 = spm_pass_kernel<NT, MT, 0>;
+  auto k1 = spm_pass_kernel<NT, MT, 1>;
+  auto k2 = spm_pass_kernel<NT, MT, 2>;
   auto k = mode == 0 ? k0 : (mode == 1 ? k1 : k2);
   if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k<<<grid, PASS_WARPS * 32, smem, s>>>(*d, *b);
@@ -720,7 +737,7 @@ static int launch_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mo
 
 template <int NT>
 static int launch_pass_nt(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, cudaStream_t s) {
-  return d->nplanes == 2 ? launch_pass<NT, 2>(d, b, mode, s) : launch_pass<NT, 1>(d, b, mode, s);
+  return d->mt == 2 ? launch_pass<NT, 2>(d, b, mode, s) : launch_pass<NT, 1>(d, b, mode, s);
 }
 
 }  // namespace admm
@@ -752,17 +769,17 @@ int admm_spm_unpack_L(const admm_spm_dims* d, const double* frag, void* canon, i
 int admm_spm_pack_state(const admm_spm_dims* d, const void* h20, const void* x2, int src_is_complex, const double* mu20,
                         double* S, int* flag, admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_pack_state")) return rc;
-  const long long total = (long long)d->npt * d->nrt * d->nplanes * 64;
+  const long long total = (long long)d->npt * d->nrt * 64;
   pack_state_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, (const double*)h20, (const double*)x2,
                                                                                  src_is_complex, mu20, S, flag);
   return check_launch("admm_spm_pack_state");
 }
 
-int admm_spm_unpack_state(const admm_spm_dims* d, const double* S, const double* mu20_used, void* h20, void* x2,
-                          int dst_is_complex, admm_stream_t stream) {
+int admm_spm_unpack_state(const admm_spm_dims* d, const double* S, const double* mu20_used, const double* him,
+                          void* h20, void* x2, int dst_is_complex, admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_unpack_state")) return rc;
   unpack_state_kernel<<<ew_grid((long long)d->Nw * d->nb), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      *d, S, mu20_used, (double*)h20, (double*)x2, dst_is_complex);
+      *d, S, mu20_used, him, (double*)h20, (double*)x2, dst_is_complex);
   return check_launch("admm_spm_unpack_state");
 }
 

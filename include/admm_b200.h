@@ -110,6 +110,7 @@ typedef struct admm_spm_dims {
   int npt;      /* number of 8-problem tiles = ceil(nb / 8)                                    */
   int nplanes;  /* 1: real data (imaginary parts identically zero), 2: complex128 state        */
   int nsplit;   /* row splits of the pass kernel (partial V sums)                              */
+  int mt;       /* problem tiles per warp in the pass kernel (1 or 2)                          */
   int batch_wide; /* 1: mu and the stopping test use norms over the whole batch (packed
                      reference semantics), 0: per-problem mu / stopping                        */
 } admm_spm_dims;
@@ -126,14 +127,18 @@ int admm_spm_pack_L(const admm_spm_dims* d, const void* canon, int src_is_comple
 int admm_spm_unpack_L(const admm_spm_dims* d, const double* frag, void* canon, int dst_is_complex,
                       admm_stream_t stream);
 
-/* (h20, x2) canonical (Nw x nb) <-> implicit state S[pt][rt][plane][lane][2]:
- *   plane 0: s = Re(h20) - mu20 * x2  (complementarity: Re(h20) = max(0,s), mu20*x2 = max(0,-s))
- *   plane 1: Im(h20).
+/* (h20, x2) canonical (Nw x nb) <-> implicit state S[pt][rt][lane][2]:
+ *   s = Re(h20) - mu20 * x2   (complementarity: Re(h20) = max(0,s), mu20*x2 = max(0,-s)).
+ * Im(h20) is not part of S: it only ever enters the iteration through P^T Im(h20), which the
+ * x-update maintains in L-space (z <- z - mu20 P^T P Im(x0)); the caller reconstructs
+ * Im(h20) = Im(h20)_initial - P a, a = sum_k mu20_k Im(x0_k) (buffer `aim`), and passes it to unpack
+ * as `him` (Nw x nb real, may be NULL = 0).
  * pack sets flag[0] = 1 if the given state is not representable (x2 < 0 or Re(h20)*x2 != 0). */
 int admm_spm_pack_state(const admm_spm_dims* d, const void* h20, const void* x2, int src_is_complex,
                         const double* mu20, double* S, int* flag, admm_stream_t stream);
 int admm_spm_unpack_state(const admm_spm_dims* d, const double* S, const double* mu20_used,
-                          void* h20, void* x2, int dst_is_complex, admm_stream_t stream);
+                          const double* him, void* h20, void* x2, int dst_is_complex,
+                          admm_stream_t stream);
 
 /* Factor cache entry for `nslots` (mu10, mu20) pairs: G = G0 + mu10 I + mu20 PtP; Ginv = G^-1
  * (Lp x Lp, zero padded), w = Ginv C^T (Lp), sigma = C w.  G0 = alpha A^H A (L x L, ld Lp).
@@ -167,13 +172,15 @@ typedef struct admm_spm_buffers {
   double* x0;
   double* x1;
   double* h10;
-  double* V;              /* [nsplit][ncolumn tiles][Lp/8][32][2]  P^T(h20 + mu20 x2) partials  */
+  double* V;              /* [nsplit][ncolumn tiles][Lp/8][32][2]  P^T(h20 + mu20 x2) partials;
+                             imaginary-plane tiles: z = P^T Im(h20) in split 0 (owned by xupdate)    */
   double* Vx;             /* same shape: P^T x2 partials (split form, valid after a split pass) */
+  double* aim;            /* fragment layout; imaginary-plane tiles accumulate sum_k mu20_k Im(x0_k) */
   /* implicit (h20, x2) state */
-  double* S;              /* [npt][nrt][nplanes][32][2]                                        */
+  double* S;              /* [npt][nrt][32][2]                                                 */
   /* norms */
   double* normsA;         /* [8*npt*nplanes][8] from xupdate                                   */
-  double* normsB;         /* [nsplit][8*npt*nplanes][4] from pass                              */
+  double* normsB;         /* [nsplit][8*npt*nplanes][4] from pass (real-plane columns only)    */
   double* gsum;           /* [16] batch-wide sums (reduce), only batch_wide                    */
   double* gpart;          /* [256][16] scratch of the two-stage reduce                         */
   /* control */
@@ -195,7 +202,7 @@ typedef struct admm_spm_buffers {
 int admm_spm_xupdate(const admm_spm_dims* d, const admm_spm_buffers* b, int v_split,
                      admm_stream_t stream);
 
-/* One streaming sweep over the implicit (h20, x2) state: Q = P x0 (FP64 tensor cores), the
+/* One streaming sweep over the implicit (Re h20, x2) state: Q = P Re(x0) (FP64 tensor cores), the
  * non-negative z-update (objectivefunc.py:256-271), dual ascent of pair (2,0)
  * (optimizer.py:334-341), residual partial sums (optimizer.py:251-274) and V = P^T(h20 + mu20 x2)
  * for the next x-update (optimizer.py:194-200), all in one read+write of the state.

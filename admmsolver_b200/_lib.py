@@ -21,7 +21,7 @@ if not os.path.exists(LIB_PATH):
 
 lib = C.CDLL(LIB_PATH)
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OP_N, OP_T, OP_H = 0, 1, 2
 
 
@@ -31,7 +31,7 @@ class AdmmError(RuntimeError):
 
 class SpmDims(C.Structure):
     _fields_ = [(n, C.c_int) for n in
-                ("L", "Lp", "ldp", "Nw", "nrt", "nb", "npt", "nplanes", "nsplit", "mt", "batch_wide")]
+                ("L", "Lp", "Nw", "nrt", "nb", "npt", "nplanes", "nsplit", "mt", "batch_wide")]
 
 
 _P = C.c_void_p
@@ -39,10 +39,10 @@ _P = C.c_void_p
 
 class SpmBuffers(C.Structure):
     _fields_ = [
-        ("Psw", _P), ("PtP", _P), ("Cvec", _P), ("Ginv_cache", _P), ("w_cache", _P), ("sigma_cache", _P),
+        ("Pf", _P), ("PtP", _P), ("Cvec", _P), ("Ginv_cache", _P), ("w_cache", _P), ("sigma_cache", _P),
         ("slot", _P), ("mu10", _P), ("mu20", _P), ("mu20_used", _P), ("done", _P), ("iters", _P),
         ("last_res", _P), ("Dre", _P),
-        ("b0", _P), ("x0", _P), ("x1", _P), ("h10", _P), ("V", _P), ("Vx", _P), ("aim", _P),
+        ("b0", _P), ("x0", _P), ("x1", _P), ("h10", _P), ("V", _P), ("aim", _P),
         ("S", _P),
         ("normsA", _P), ("normsB", _P), ("gsum", _P), ("gpart", _P),
         ("iter_counter", _P), ("flags", _P), ("history", _P), ("hist_cap", C.c_int),
@@ -86,6 +86,7 @@ _SIGS = {
     "admm_spm_factor": ([C.POINTER(SpmDims), _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "admm_spm_xupdate": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
     "admm_spm_pass": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
+    "admm_spm_step": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
     "admm_spm_reduce": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _P], _I),
     "admm_spm_decide": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
     "admm_bp_setup": ([C.POINTER(BpBuffers), _P, _P, _P, _P], _I),

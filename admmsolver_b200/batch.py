@@ -114,28 +114,30 @@ class SharedSpM:
         self.L, self.Nw, self.nb = L, Nw, nb
         self.is_complex = cplx
         Lp = _pad_L(L)
-        ldp = ((Lp + 15) // 16) * 16
         nrt = ((Nw + 7) // 8 + 3) // 4 * 4
         npt = (nb + 7) // 8
         nplanes = 2 if cplx else 1
         nchunks = nrt // 4
-        mt = 2 if npt >= 64 else 1                   # problem tiles per warp in the pass kernel
+        NT = Lp // 8
+        # problem tiles per warp in the pass kernel; one CTA = 4 warps = 4*mt tiles of 8 problems
+        mt = 2 if (npt >= 8 * 444 and Lp <= 40) else 1
         if nsplit is None:
+            # fill the 148 SMs x 3 resident CTAs in ONE wave: split the sampling points over
+            # several CTAs only when the batch alone cannot (then the x-update is a separate kernel)
             col_ctas = -(-npt // (4 * mt))
-            nsplit = max(1, min(nchunks, -(-444 // col_ctas)))
+            nsplit = max(1, min(nchunks, 444 // col_ctas))
         nsplit = max(1, min(nsplit, nchunks))
-        self.dims = SpmDims(L, Lp, ldp, Nw, nrt, nb, npt, nplanes, nsplit, mt, int(batch_wide))
+        self.dims = SpmDims(L, Lp, Nw, nrt, nb, npt, nplanes, nsplit, mt, int(batch_wide))
         self.batch_wide = bool(batch_wide)
         self.lam, self.max_mu = float(lam), float(max_mu)
         nprob = 8 * npt
         nct = npt * nplanes
-        NT = Lp // 8
         z = lambda *shape, dtype=_F64: torch.zeros(*shape, dtype=dtype, device=dev)
         dref = C.byref(self.dims)
 
         # shared operators
-        self.Psw = z(8 * nrt * ldp)
-        call("admm_spm_prepare_P", dref, ptr(P_t), L, ptr(self.Psw), stream())
+        self.Pf = z(nrt * 2 * NT * 64)
+        call("admm_spm_prepare_P", dref, ptr(P_t), L, ptr(self.Pf), stream())
         self.P = P_t
         self.PtP = z(Lp, Lp)
         ptp = z(L, L)
@@ -169,19 +171,21 @@ class SharedSpM:
         self.b0 = z(fl)
         call("admm_spm_pack_L", dref, ptr(b0.contiguous()), int(b0.is_complex()), ptr(self.b0), stream())
         self.x0f, self.x1f, self.h10f = z(fl), z(fl), z(fl)
-        self.V, self.Vx = z(nsplit * fl), z(nsplit * fl)
+        self.V = z(nsplit * fl)
         self.aim = z(fl)                  # sum_k mu20_k Im(x0_k)  (imaginary-plane tiles only)
         self._him_base = None             # Im(h20) at the time of set_state (None == 0)
         self.S = z(npt * nrt * 64)
         self.normsA = z(nct * 8 * 8)
-        self.normsB = z(nsplit * nct * 8 * 4)
+        self.normsB = z(nsplit * nct * 8 * 2)
         self.gsum = z(16)
         self.gpart = z(256 * 16)
         self.iter_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.flags = torch.zeros(4, dtype=torch.int32, device=dev)
         self.history = None
         self.pass_events = None      # bench.py: list collecting (start, stop) CUDA events around the pass kernel
-        self._v_state = "none"
+        self._v_valid = False        # V = P^T(h20 + mu20 x2) matches the current state and mu20
+        self._fresh = True           # next x-update must recompute |P x0_old|^2
+        self._graphs = {}            # CUDA graphs of runs of plain iterations, keyed by (length, baked args)
         self.primal_residual = []
         self.dual_residual = []
         self.bufs = SpmBuffers()
@@ -190,11 +194,11 @@ class SharedSpM:
 
     def _fill_bufs(self, rtol, fact_incr=2.0, th_change=10.0):
         b = self.bufs
-        for name, t in (("Psw", self.Psw), ("PtP", self.PtP), ("Cvec", self.Cvec), ("Ginv_cache", self.Ginv_cache),
+        for name, t in (("Pf", self.Pf), ("PtP", self.PtP), ("Cvec", self.Cvec), ("Ginv_cache", self.Ginv_cache),
                         ("w_cache", self.w_cache), ("sigma_cache", self.sigma_cache), ("slot", self.slot),
                         ("mu10", self.mu10), ("mu20", self.mu20), ("mu20_used", self.mu20_used), ("done", self.done),
                         ("iters", self.iters), ("last_res", self.last_res), ("Dre", self.Dre), ("b0", self.b0),
-                        ("x0", self.x0f), ("x1", self.x1f), ("h10", self.h10f), ("V", self.V), ("Vx", self.Vx),
+                        ("x0", self.x0f), ("x1", self.x1f), ("h10", self.h10f), ("V", self.V),
                         ("aim", self.aim), ("S", self.S), ("normsA", self.normsA), ("normsB", self.normsB), ("gsum", self.gsum),
                         ("gpart", self.gpart), ("iter_counter", self.iter_counter), ("flags", self.flags)):
             setattr(b, name, t.data_ptr())
@@ -248,7 +252,7 @@ class SharedSpM:
     def reset(self, g=None, mu: Optional[float] = None) -> None:
         """Zero the ADMM state (x, h), optionally load new data ``g`` (L x nb, device or host) and
         reset the penalties -- lets one plan serve many batches without re-allocating."""
-        for t in (self.x0f, self.x1f, self.h10f, self.S, self.V, self.Vx, self.aim):
+        for t in (self.x0f, self.x1f, self.h10f, self.S, self.V, self.aim):
             t.zero_()
         self._him_base = None
         if mu is not None:
@@ -271,7 +275,8 @@ class SharedSpM:
             call("admm_diag_mul", int(cplx), self.L, self.L, self.nb, ptr(sd), ptr(gv), self.nb, ptr(b0), self.nb, stream())
             call("admm_spm_pack_L", C.byref(self.dims), ptr(b0), int(cplx), ptr(self.b0), stream())
             self._g = gv
-        self._v_state = "none"
+        self._v_valid = True          # all-zero state: V = 0
+        self._fresh = True
         self.primal_residual, self.dual_residual = [], []
 
     # ------------------------------------------------------------------ state import / export
@@ -313,7 +318,8 @@ class SharedSpM:
                          ptr(zr), self.nb, stream())
                     zc = torch.complex(torch.zeros_like(zr), zr)
                 self._set_imag_tiles(self.V, zc)
-        self._v_state = "none"
+            self._v_valid = False
+        self._fresh = True
 
     def _set_imag_tiles(self, frag_arr: torch.Tensor, canon_c: torch.Tensor) -> None:
         """Write Im(canon_c) (L x nb) into the imaginary-plane tiles of a fragment array (split 0)."""
@@ -383,57 +389,119 @@ class SharedSpM:
     # ------------------------------------------------------------------ iteration
     def _iteration(self, do_update_mu: bool) -> None:
         dref, bref, st = C.byref(self.dims), C.byref(self.bufs), stream()
-        if self._v_state == "none":
-            call("admm_spm_pass", dref, bref, 2, st)
-            self._v_state = "split"
-        call("admm_spm_xupdate", dref, bref, int(self._v_state == "split"), st)
-        if self.pass_events is not None and not do_update_mu:
+        if not self._v_valid:
+            # V = P^T(h20 + mu20 x2) from the current state (after set_state or a change of mu20)
+            call("admm_spm_pass", dref, bref, 1, st)
+            self._v_valid = True
+        fresh = int(self._fresh)
+        self._fresh = False
+        timed = self.pass_events is not None and not do_update_mu
+        if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+        if self.dims.nsplit == 1:
+            if timed:
+                e0.record()
+            call("admm_spm_step", dref, bref, fresh, st)
+        else:
+            call("admm_spm_xupdate", dref, bref, fresh, st)
+            if timed:
+                e0.record()
             call("admm_spm_pass", dref, bref, 0, st)
+        if timed:
             e1.record()
             self.pass_events.append((e0, e1))
-        else:
-            call("admm_spm_pass", dref, bref, 1 if do_update_mu else 0, st)
-        self._v_state = "split" if do_update_mu else "plain"
         if self.batch_wide:
             call("admm_spm_reduce", dref, bref, st)
             if self.group is not None:
                 torch.distributed.all_reduce(self.gsum, group=self.group)
         call("admm_spm_decide", dref, bref, int(do_update_mu), st)
 
+    def _after_update_iteration(self) -> bool:
+        """Host look at the device flags after an iteration that may have changed mu or finished
+        problems.  Returns True when every problem is done."""
+        fl = self.flags.cpu()
+        if int(fl[1]) >= self.nb:
+            return True
+        if int(fl[0]) != 0:
+            self.flags[0] = 0
+            self._refresh_slots()
+            self._v_valid = False      # V was built with the old mu20
+        return False
+
     def solve(self, niter: int = 10000, interval_update_mu: int = 100, rtol: float = 1e-12,
-              callback=None, keep_history: Optional[bool] = None) -> int:
+              callback=None, keep_history: Optional[bool] = None, use_graph: Optional[bool] = None) -> int:
         """Run up to ``niter`` iterations with the ordering of ``SimpleOptimizer.solve``
-        (optimizer.py:302-320).  Returns the number of iterations launched."""
+        (optimizer.py:302-320).  Returns the number of iterations launched.
+
+        The iterations between two mu updates are data-independent launch sequences: they are
+        captured once in a CUDA graph and replayed (``use_graph``; default: on when no callback
+        is given and no bench timing events are being collected)."""
         nb = self.nb
         self.iters.zero_()
         self.done[:nb] = 0
         self.flags.zero_()
         self.iter_counter.zero_()
         track = (self.batch_wide or nb == 1) if keep_history is None else keep_history
-        self.history = torch.zeros(max(niter, 1), 2, dtype=_F64, device=self.device) if track else None
+        if track:
+            if self.history is None or self.history.shape[0] < niter:
+                self.history = torch.zeros(max(niter, 1), 2, dtype=_F64, device=self.device)
+        elif self.history is not None:
+            self.history = None
         self._fill_bufs(rtol)
+        key = (float(rtol), self.bufs.history, self.bufs.hist_cap)     # everything a captured launch bakes in
+        if use_graph is None:
+            use_graph = callback is None and self.pass_events is None
         launched = 0
-        for it in range(niter):
+        it = 0
+        while it < niter:
             upd = (it % interval_update_mu == 0)
-            self._iteration(upd)
-            launched += 1
+            run = 1 if upd else min(niter, (it // interval_update_mu + 1) * interval_update_mu) - it
+            if upd or callback is not None or not use_graph or run < 4:
+                self._iteration(upd)
+                run = 1
+            else:
+                self._replay_plain(run, key)
+            launched += run
+            it += run
             if callback is not None:
                 callback()
-            if upd or callback is not None or it == niter - 1:
-                fl = self.flags.cpu()
-                if int(fl[1]) >= nb:
+            if upd or callback is not None or it >= niter:
+                if self._after_update_iteration():
                     break
-                if int(fl[0]) != 0:
-                    self.flags[0] = 0
-                    self._refresh_slots()
         if track:
             ndone = int(self.iters[0].item())
             hist = self.history[:ndone].cpu().numpy()
             self.primal_residual.extend(hist[:, 0].tolist())
             self.dual_residual.extend(hist[:, 1].tolist())
         return launched
+
+    def _replay_plain(self, run: int, key) -> None:
+        """``run`` iterations without mu update as one CUDA-graph launch (captured on first use)."""
+        if self._fresh:
+            self._iteration(False)
+            run -= 1
+        elif not self._v_valid:
+            # one-off launch, kept outside the graph: V from the state with the new mu20
+            call("admm_spm_pass", C.byref(self.dims), C.byref(self.bufs), 1, stream())
+            self._v_valid = True
+        if run == 0:
+            return
+        graph = self._graphs.get((run, key))
+        if graph is None:
+            if len(self._graphs) >= 8:
+                self._graphs.clear()
+            graph = torch.cuda.CUDAGraph()
+            before = _lib.launch_count
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                for _ in range(run):
+                    self._iteration(False)
+            _lib.launch_count = before          # capture enqueues nothing
+            self._graphs[(run, key)] = graph
+        graph.replay()
+        _lib.launch_count += run * self._launches_per_iteration()
+
+    def _launches_per_iteration(self) -> int:
+        return (1 if self.dims.nsplit == 1 else 2) + (2 if self.batch_wide else 0) + 1
 
     # ------------------------------------------------------------------ objective
     def objective(self) -> float:

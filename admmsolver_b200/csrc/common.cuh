@@ -58,9 +58,10 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch) {
 // FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).  SASS: DMMA.8x8x4 on sm_100a.
 // Fragment ownership (lane = 4*g + t):  a = A[g][t],  b = B[t][g],  c0/c1 = C[g][2t], C[g][2t+1].
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
+  // not volatile: a pure function of its operands, the compiler may schedule it freely
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
 }
 
 // 16-byte async global->shared copy (LDGSTS)
@@ -84,11 +85,41 @@ __device__ __forceinline__ void st_stream2(double* p, double2 v) {
   asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};\n" ::"l"(p), "d"(v.x), "d"(v.y));
 }
 
-// XOR swizzle of the padded P operand (see DESIGN.md "P layout"): column offset for row r
-__host__ __device__ __forceinline__ int p_swz(int r) {
-  // sw = [0,2,1,3,2,0,3,1][r & 7]  (in units of 4 doubles)
-  const int sw = ((r >> 1) & 1) | (((r & 1) ^ ((r >> 2) & 1)) << 1);
-  return 4 * sw;
+// ---- mbarrier + TMA bulk copy (global -> shared, SASS UBLKCP) ---------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// contiguous `bytes` (multiple of 16, both addresses 16-byte aligned) global -> shared; completion
+// is signalled on `bar` (complete_tx)
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 inline int ceil_div(long long a, long long b) { return int((a + b - 1) / b); }

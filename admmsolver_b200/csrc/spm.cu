@@ -1,9 +1,12 @@
 // Pattern B engine (SpM): many problems sharing s, P, C.   See include/admm_b200.h and DESIGN.md.
 //
-// One ADMM iteration is   xupdate  ->  pass  -> [reduce] -> decide .
-//   * pass streams the implicit (h20, x2) state once (16 B read + 16 B written per sampling point
-//     and complex problem) and runs both skinny GEMMs (Q = P x0, V = P^T u) on the FP64 tensor
-//     cores (mma.sync m8n8k4 -> SASS DMMA.8x8x4) chained through registers;
+// One ADMM iteration is   step (= x-update + pass, one kernel)  -> [reduce] -> decide
+// (or  xupdate -> pass -> [reduce] -> decide  when the batch is too small to fill the GPU and the
+// sampling points are split over several CTAs).
+//   * pass streams the implicit (Re h20, x2) state once (8 B read + 8 B written per sampling point
+//     and problem) and runs both skinny GEMMs (s' = h - mu P x0,  V = P^T |s'|) on the FP64 tensor
+//     cores (mma.sync m8n8k4 -> SASS DMMA.8x8x4) chained through registers; P arrives in
+//     fragment-major chunks by TMA bulk copies (UBLKCP) behind an mbarrier ring;
 //   * xupdate does the L x L work (cached inverse, KKT correction, soft threshold, dual ascent);
 //   * decide evaluates residual()/check_convergence()/update_mu() on device.
 #include "common.cuh"
@@ -19,15 +22,27 @@ __device__ __forceinline__ size_t frag_index(int ct, int NT, int j, int lane) {
   return ((size_t)(ct * NT + j) * 32 + lane) * 2;
 }
 
-__global__ void prepare_P_kernel(admm_spm_dims d, const double* __restrict__ P, int ldP, double* __restrict__ Psw) {
-  const long long total = (long long)d.nrt * 8 * d.ldp;
+// P (Nw x L) -> fragment-major Pf[rt][which][j][lane][e]  (zero padded):
+//   which 0 (GEMM1' B operand):  P[8 rt + g      ][8 j + 2 t + e]
+//   which 1 (GEMM2' B operand):  P[8 rt + 2 t + e][8 j + g      ]
+// so that every operand fetch of the pass kernel is one conflict-free 16-byte load at
+// (lane * 16 + immediate).
+__global__ void prepare_P_kernel(admm_spm_dims d, const double* __restrict__ P, int ldP, double* __restrict__ Pf) {
+  const int NT = d.Lp / 8;
+  const long long total = (long long)d.nrt * 2 * NT * 64;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int r = int(idx / d.ldp), c = int(idx % d.ldp);
-    const int l = c ^ p_swz(r);
+    const int e = int(idx & 1), lane = int((idx >> 1) & 31);
+    long long q = idx >> 6;
+    const int j = int(q % NT);
+    q /= NT;
+    const int which = int(q & 1), rt = int(q >> 1);
+    const int g = lane >> 2, t = lane & 3;
+    const int r = which == 0 ? 8 * rt + g : 8 * rt + 2 * t + e;
+    const int l = which == 0 ? 8 * j + 2 * t + e : 8 * j + g;
     double v = 0.0;
     if (r < d.Nw && l < d.L) v = P[(size_t)r * ldP + l];
-    Psw[idx] = v;
+    Pf[idx] = v;
   }
 }
 
@@ -199,7 +214,7 @@ __global__ void __launch_bounds__(256) spm_factor_kernel(admm_spm_dims d, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// x-update: one warp per tile of 8 real columns, everything in fragment layout
+// x-update of ONE column tile (8 problems x one plane) by one warp, everything in fragment layout
 // ---------------------------------------------------------------------------------------------
 template <int NT>
 __device__ __forceinline__ void frag_gemm(double (&out)[NT][2], const double (&a)[NT][2], const double* __restrict__ Bm,
@@ -219,61 +234,57 @@ __device__ __forceinline__ void frag_gemm(double (&out)[NT][2], const double (&a
 }
 
 template <int NT>
-__global__ void __launch_bounds__(128) spm_xupdate_kernel(admm_spm_dims d, admm_spm_buffers b, int v_split) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int nct = d.npt * d.nplanes;
-  if (warp >= nct) return;
-  const int ct = warp, pt = ct / d.nplanes, pl = ct % d.nplanes;
+__device__ __forceinline__ double frag_dot(const double (&a)[NT][2], const double (&b)[NT][2]) {
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) s += a[j][0] * b[j][0] + a[j][1] * b[j][1];
+  return s;
+}
+
+// Term 0 solve (ConstrainedLeastSquares with the cached inverse and KKT correction), L1 z-update,
+// dual ascent of pair (1,0), Gram-form norms of pair (2,0) and -- imaginary plane only -- the
+// L-space recursion of z = P^T Im(h20).  x0 (new) is returned in registers.
+// `fresh` != 0: |P x0_old|^2 is recomputed (first iteration after a state change); otherwise it
+// is the |P x0|^2 this function left in normsA[7] on the previous iteration.
+// Returns false when every problem of the tile is frozen (nothing was touched, x0 not loaded).
+template <int NT>
+__device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_spm_buffers& b, int pt, int pl, int fresh,
+                                             int lane, double (&x0)[NT][2]) {
+  const int g = lane >> 2, t = lane & 3;
+  const int ct = pt * d.nplanes + pl;
   const int prob = 8 * pt + g;
   const int is_done = b.done[prob];
-  if (__all_sync(0xffffffffu, is_done)) return;
+  if (__all_sync(0xffffffffu, is_done)) return false;
   const double mu10 = b.mu10[prob], mu20 = b.mu20[prob];
   const int slot = b.slot[prob];
   const int Lp = d.Lp;
-  const size_t vstride = (size_t)nct * NT * 64;
+  const size_t vstride = (size_t)d.npt * d.nplanes * NT * 64;
+  double* nrm = b.normsA + ((size_t)ct * 8 + g) * 8;
 
-  double rhs[NT][2], x0o[NT][2], h10[NT][2], zv[NT][2];
+  // ---- rhs = alpha A^H y + h10 + mu10 x1 + P^T(h20 + mu20 x2)
+  double rhs[NT][2], zv[NT][2];
+  const int nsp = pl == 0 ? d.nsplit : 1;   // imaginary plane: z lives in split 0, owned by this function
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
     const size_t o = frag_index(ct, NT, j, lane);
     const double2 b0 = *reinterpret_cast<const double2*>(b.b0 + o);
     const double2 hh = *reinterpret_cast<const double2*>(b.h10 + o);
     const double2 x1 = *reinterpret_cast<const double2*>(b.x1 + o);
-    const double2 xo = *reinterpret_cast<const double2*>(b.x0 + o);
-    double2 v = make_double2(0.0, 0.0);
-    // real plane: partial sums of P^T(h20 + mu20 x2) from the pass kernel's row splits;
-    // imaginary plane: z = P^T Im(h20), kept in slot 0 by this kernel (never touched by pass)
-    const int nsp = pl == 0 ? d.nsplit : 1;
-    for (int sp = 0; sp < nsp; ++sp) {
+    double2 v = *reinterpret_cast<const double2*>(b.V + o);
+    for (int sp = 1; sp < nsp; ++sp) {
       const double2 p = *reinterpret_cast<const double2*>(b.V + sp * vstride + o);
       v.x += p.x;
       v.y += p.y;
-    }
-    if (v_split && pl == 0) {
-      double2 vx = make_double2(0.0, 0.0);
-      for (int sp = 0; sp < d.nsplit; ++sp) {
-        const double2 p = *reinterpret_cast<const double2*>(b.Vx + sp * vstride + o);
-        vx.x += p.x;
-        vx.y += p.y;
-      }
-      v.x += mu20 * vx.x;
-      v.y += mu20 * vx.y;
     }
     zv[j][0] = v.x;
     zv[j][1] = v.y;
     rhs[j][0] = b0.x + hh.x + mu10 * x1.x + v.x;
     rhs[j][1] = b0.y + hh.y + mu10 * x1.y + v.y;
-    x0o[j][0] = xo.x;
-    x0o[j][1] = xo.y;
-    h10[j][0] = hh.x;
-    h10[j][1] = hh.y;
   }
 
-  // xi1 = Ginv rhs, one tensor-core GEMM per distinct factor slot in the tile
-  double xi[NT][2];
+  // ---- xi1 = Ginv rhs, one tensor-core GEMM per distinct factor slot in the tile
 #pragma unroll
-  for (int j = 0; j < NT; ++j) xi[j][0] = xi[j][1] = 0.0;
+  for (int j = 0; j < NT; ++j) x0[j][0] = x0[j][1] = 0.0;
   unsigned remaining = __ballot_sync(0xffffffffu, !is_done);
   while (remaining) {
     const int leader = __ffs(remaining) - 1;
@@ -284,95 +295,99 @@ __global__ void __launch_bounds__(128) spm_xupdate_kernel(admm_spm_dims d, admm_
     if (match) {
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        xi[j][0] = acc[j][0];
-        xi[j][1] = acc[j][1];
+        x0[j][0] = acc[j][0];
+        x0[j][1] = acc[j][1];
       }
     }
     remaining &= ~__ballot_sync(0xffffffffu, match);
   }
 
-  // KKT correction enforcing C x0 = D   (objectivefunc.py:148-157)
-  double cxi = 0.0;
+  // ---- KKT correction enforcing C x0 = D   (objectivefunc.py:148-157)
+  {
+    double cxi = 0.0;
 #pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    cxi += b.Cvec[8 * j + 2 * t] * xi[j][0] + b.Cvec[8 * j + 2 * t + 1] * xi[j][1];
-  }
-  cxi = quad_sum(cxi);
-  const double sigma = b.sigma_cache[slot];
-  const double Dv = b.Dre[(size_t)pl * 8 * d.npt + prob];
-  const double nu = (Dv - cxi) / sigma;
-  double x0[NT][2], dd[NT][2];
-  const double* wv = b.w_cache + (size_t)slot * Lp;
+    for (int j = 0; j < NT; ++j) cxi += b.Cvec[8 * j + 2 * t] * x0[j][0] + b.Cvec[8 * j + 2 * t + 1] * x0[j][1];
+    cxi = quad_sum(cxi);
+    const double nu = (b.Dre[(size_t)pl * 8 * d.npt + prob] - cxi) / b.sigma_cache[slot];
+    const double* wv = b.w_cache + (size_t)slot * Lp;
 #pragma unroll
-  for (int j = 0; j < NT; ++j) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      x0[j][e] = xi[j][e] + wv[8 * j + 2 * t + e] * nu;
-      dd[j][e] = x0[j][e] - x0o[j][e];
+    for (int j = 0; j < NT; ++j) {
+      x0[j][0] += wv[8 * j + 2 * t] * nu;
+      x0[j][1] += wv[8 * j + 2 * t + 1] * nu;
     }
   }
 
-  // Gram-form norms of pair (2,0):  |P d|^2 = d^T (P^T P) d,  |P x0_old|^2  (and, for the
-  // imaginary plane, |P x0|^2 and z <- z - mu20 P^T P x0: Im(h20) only ever enters through
-  // P^T Im(h20), so the imaginary half of the state never leaves L-space)
-  double nPd, nPxo, nPx = 0.0;
+  // ---- norms of the x0 change, plain and in Gram form  (|P d|^2 = d^T (P^T P) d)
+  double n_d, n_xo, nPd, nPxo;
   {
-    double yd[NT][2], yo[NT][2];
-    frag_gemm<NT>(yd, dd, b.PtP, Lp, g, t);
-    frag_gemm<NT>(yo, x0o, b.PtP, Lp, g, t);
-    nPd = 0.0;
-    nPxo = 0.0;
+    double xo[NT][2], dd[NT][2], yd[NT][2];
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      nPd += yd[j][0] * dd[j][0] + yd[j][1] * dd[j][1];
-      nPxo += yo[j][0] * x0o[j][0] + yo[j][1] * x0o[j][1];
+      const double2 v = *reinterpret_cast<const double2*>(b.x0 + frag_index(ct, NT, j, lane));
+      xo[j][0] = v.x;
+      xo[j][1] = v.y;
+      dd[j][0] = x0[j][0] - v.x;
+      dd[j][1] = x0[j][1] - v.y;
     }
-    if (pl == 1) {
+    n_d = frag_dot<NT>(dd, dd);
+    n_xo = frag_dot<NT>(xo, xo);
+    frag_gemm<NT>(yd, dd, b.PtP, Lp, g, t);
+    nPd = frag_dot<NT>(yd, dd);
+    if (fresh) {
+      frag_gemm<NT>(yd, xo, b.PtP, Lp, g, t);
+      nPxo = frag_dot<NT>(yd, xo);
+    } else {
+      nPxo = (t == 0) ? nrm[7] : 0.0;     // quad-summed below
+    }
+  }
+
+  // ---- y = P^T P x0:  |P x0|^2 (the primal norm of pair (2,0) needs it for both planes), and for
+  // the imaginary plane  z <- z - mu20 y,  a += mu20 x0   (Im(h20) never leaves L-space)
+  double nPx;
+  {
+    double y[NT][2];
+    frag_gemm<NT>(y, x0, b.PtP, Lp, g, t);
+    nPx = frag_dot<NT>(y, x0);
+    if (pl == 1 && !is_done) {
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        const double y0 = yd[j][0] + yo[j][0], y1 = yd[j][1] + yo[j][1];   // P^T P x0 (linear)
-        nPx += y0 * x0[j][0] + y1 * x0[j][1];
-        if (!is_done) {
-          const size_t o = frag_index(ct, NT, j, lane);
-          *reinterpret_cast<double2*>(b.V + o) = make_double2(zv[j][0] - mu20 * y0, zv[j][1] - mu20 * y1);
-          double2 av = *reinterpret_cast<const double2*>(b.aim + o);
-          av.x += mu20 * x0[j][0];
-          av.y += mu20 * x0[j][1];
-          *reinterpret_cast<double2*>(b.aim + o) = av;
-        }
+        const size_t o = frag_index(ct, NT, j, lane);
+        *reinterpret_cast<double2*>(b.V + o) = make_double2(zv[j][0] - mu20 * y[j][0], zv[j][1] - mu20 * y[j][1]);
+        double2 av = *reinterpret_cast<const double2*>(b.aim + o);
+        av.x += mu20 * x0[j][0];
+        av.y += mu20 * x0[j][1];
+        *reinterpret_cast<double2*>(b.aim + o) = av;
       }
     }
   }
 
-  // L1 z-update (real plane only; the imaginary part of x1 is identically zero) + dual ascent
+  // ---- L1 z-update (real plane only; the imaginary part of x1 is identically zero) + dual ascent
   const double thr = 0.5 * b.lam / mu10;
-  double n_p = 0.0, n_x0 = 0.0, n_x1 = 0.0, n_d = 0.0, n_xo = 0.0;
+  double n_p = 0.0, n_x0 = 0.0, n_x1 = 0.0;
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
-    double2 x1n, hn, x0n;
+    const size_t o = frag_index(ct, NT, j, lane);
+    const double2 hh = *reinterpret_cast<const double2*>(b.h10 + o);
+    double zz[2], hn[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const double xv = x0[j][e], hv = h10[j][e];
+      const double xv = x0[j][e], hv = e == 0 ? hh.x : hh.y;
       double z = 0.0;
       if (pl == 0) {
         const double yv = -((hv - mu10 * xv) / mu10);
         if (yv > thr) z = yv - thr;
         if (yv < -thr) z = yv + thr;
       }
-      const double hnew = hv + mu10 * (z - xv);
+      hn[e] = hv + mu10 * (z - xv);
+      zz[e] = z;
       n_p += (xv - z) * (xv - z);
       n_x0 += xv * xv;
       n_x1 += z * z;
-      n_d += dd[j][e] * dd[j][e];
-      n_xo += x0o[j][e] * x0o[j][e];
-      if (e == 0) { x1n.x = z; hn.x = hnew; x0n.x = xv; }
-      else { x1n.y = z; hn.y = hnew; x0n.y = xv; }
     }
     if (!is_done) {
-      const size_t o = frag_index(ct, NT, j, lane);
-      *reinterpret_cast<double2*>(b.x0 + o) = x0n;
-      *reinterpret_cast<double2*>(b.x1 + o) = x1n;
-      *reinterpret_cast<double2*>(b.h10 + o) = hn;
+      *reinterpret_cast<double2*>(b.x0 + o) = make_double2(x0[j][0], x0[j][1]);
+      *reinterpret_cast<double2*>(b.x1 + o) = make_double2(zz[0], zz[1]);
+      *reinterpret_cast<double2*>(b.h10 + o) = make_double2(hn[0], hn[1]);
     }
   }
   n_p = quad_sum(n_p);
@@ -384,190 +399,242 @@ __global__ void __launch_bounds__(128) spm_xupdate_kernel(admm_spm_dims d, admm_
   nPxo = quad_sum(nPxo);
   nPx = quad_sum(nPx);
   if (t == 0 && !is_done) {
-    double* o = b.normsA + ((size_t)ct * 8 + g) * 8;
-    o[0] = n_p;
-    o[1] = n_x0;
-    o[2] = n_x1;
-    o[3] = n_d;
-    o[4] = n_xo;
-    o[5] = nPd > 0.0 ? nPd : 0.0;
-    o[6] = nPxo > 0.0 ? nPxo : 0.0;
-    o[7] = nPx > 0.0 ? nPx : 0.0;     // imaginary plane only: |P Im(x0)|^2
+    nrm[0] = n_p;
+    nrm[1] = n_x0;
+    nrm[2] = n_x1;
+    nrm[3] = n_d;
+    nrm[4] = n_xo;
+    nrm[5] = nPd > 0.0 ? nPd : 0.0;
+    nrm[6] = nPxo > 0.0 ? nPxo : 0.0;
+    nrm[7] = nPx > 0.0 ? nPx : 0.0;     // |P x0|^2 of this plane; next iteration's |P x0_old|^2
   }
+  return true;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(128) spm_xupdate_kernel(admm_spm_dims d, admm_spm_buffers b, int fresh) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nct = d.npt * d.nplanes;
+  if (warp >= nct) return;
+  double x0[NT][2];
+  xupdate_tile<NT>(d, b, warp / d.nplanes, warp % d.nplanes, fresh, lane, x0);
 }
 
 // ---------------------------------------------------------------------------------------------
 // pass: the streaming sweep with both skinny GEMMs on the FP64 tensor cores
 // ---------------------------------------------------------------------------------------------
 constexpr int PASS_WARPS = 4;     // warps per CTA; each warp owns MT tiles of 8 problems
-constexpr int PASS_STAGES = 3;    // cp.async ring depth for P chunks
+constexpr int PASS_STAGES = 3;    // TMA ring depth for P chunks
 constexpr int PASS_CHUNK_RT = 4;  // 8-row tiles per P chunk (32 rows)
 
-template <int NT, int MT, int MODE>
-__global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4) spm_pass_kernel(admm_spm_dims d, admm_spm_buffers b) {
-  extern __shared__ __align__(16) double Pst[];  // [PASS_STAGES][32 * ldp]
+enum { PASS_STEP = 0, PASS_VINIT = 1 };
+
+// sign-bit helpers on the integer pipe (the FP64 pipe is shared with DMMA: keep it for the MMAs)
+__device__ __forceinline__ bool is_neg(double v) { return __double2hiint(v) < 0; }
+
+template <int NT, int MT, int MODE, bool FUSED>
+__global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
+    spm_pass_kernel(admm_spm_dims d, admm_spm_buffers b, int fresh) {
+  constexpr int TILE_D = 2 * NT * 64;                   // doubles of Pf per 8-row tile
+  constexpr int CHUNK_D = PASS_CHUNK_RT * TILE_D;       // doubles per chunk
+  constexpr unsigned CHUNK_BYTES = CHUNK_D * sizeof(double);
+  extern __shared__ __align__(128) double Pst[];        // [PASS_STAGES][CHUNK_D], then barriers
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(Pst + PASS_STAGES * CHUNK_D);
+  uint64_t* empty_bar = full_bar + PASS_STAGES;
+  unsigned* ticket = reinterpret_cast<unsigned*>(empty_bar + PASS_STAGES);
+
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int ldp = d.ldp;
-  const int chunk_elems = PASS_CHUNK_RT * 8 * ldp;
   const int nchunks_total = d.nrt / PASS_CHUNK_RT;
   const int cps = (nchunks_total + d.nsplit - 1) / d.nsplit;  // chunks per split
   const int sp = blockIdx.y;
   const int c_begin = sp * cps, c_end = min(nchunks_total, c_begin + cps);
   const int nchunks = max(0, c_end - c_begin);
   const int npl = d.nplanes;
+  const double* Pf_src = b.Pf + (size_t)c_begin * CHUNK_D;
 
-  // this warp's MT problem tiles (real plane only)
+  // ---- barrier ring + first P chunks in flight before anything else
+  if (tid == 0) {
+    for (int s = 0; s < PASS_STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, PASS_WARPS);
+      ticket[s] = 0;
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < PASS_STAGES && s < nchunks; ++s) {
+      mbar_expect_tx(full_bar + s, CHUNK_BYTES);
+      tma_bulk_g2s(Pst + s * CHUNK_D, Pf_src + (size_t)s * CHUNK_D, CHUNK_BYTES, full_bar + s);
+    }
+  }
+
+  // ---- this warp's MT problem tiles (real plane only: the imaginary plane lives in L-space)
   int pt[MT];
   bool inr[MT];
   int dn[MT];
-  double mu20[MT], inv_mu20[MT];
+  double mu20[MT];
+  double xa[MT][NT][2];      // A fragments of GEMM1': -mu20 * Re(x0)   (k-slot (j,e) of lane (g,t) <-> l = 8j+2t+e)
+  double acc[MT][NT][2];     // C fragments of GEMM2': V
   bool all_done = true;
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
     pt[m] = (blockIdx.x * PASS_WARPS + warp) * MT + m;
     inr[m] = pt[m] < d.npt;
-    const int prob = 8 * (inr[m] ? pt[m] : 0) + g;
+    if (!inr[m]) pt[m] = d.npt - 1;        // clamp: loads stay in range, stores are suppressed
+    bool live = false;
+    if (FUSED) {
+      // x-update of both planes of this tile right here: x0 never makes a round trip
+      if (inr[m]) {
+        if (npl == 2) {
+          double xim[NT][2];
+          xupdate_tile<NT>(d, b, pt[m], 1, fresh, lane, xim);
+        }
+        live = xupdate_tile<NT>(d, b, pt[m], 0, fresh, lane, xa[m]);
+      }
+    }
+    const int prob = 8 * pt[m] + g;
     dn[m] = inr[m] ? b.done[prob] : 1;
     mu20[m] = b.mu20[prob];
-    inv_mu20[m] = 1.0 / mu20[m];
+    if (!FUSED || !live) {
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const double2 v = *reinterpret_cast<const double2*>(b.x0 + frag_index(pt[m] * npl, NT, j, lane));
+        xa[m][j][0] = v.x;
+        xa[m][j][1] = v.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      xa[m][j][0] *= -mu20[m];
+      xa[m][j][1] *= -mu20[m];
+      acc[m][j][0] = acc[m][j][1] = 0.0;
+    }
     all_done = all_done && dn[m];
   }
   const bool active = !__all_sync(0xffffffffu, all_done);
 
-  // A fragments of GEMM1': x0 in fragment layout (k-slot (j,e) of lane (g,t) <-> l = 8j+2t+e)
-  double xa[MT][NT][2];
-  double acc[MT][NT][2];
-  double accx[MODE != 0 ? MT : 1][NT][2];
+  double n_dh[MT], n_xm[MT], ratio[MT];
 #pragma unroll
-  for (int m = 0; m < MT; ++m)
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      double2 v = make_double2(0.0, 0.0);
-      if (active && inr[m]) v = *reinterpret_cast<const double2*>(b.x0 + frag_index(pt[m] * npl, NT, j, lane));
-      xa[m][j][0] = v.x;
-      xa[m][j][1] = v.y;
-      acc[m][j][0] = acc[m][j][1] = 0.0;
-      if (MODE != 0) accx[m][j][0] = accx[m][j][1] = 0.0;
-    }
-  double n_diff[MT], n_x2[MT], n_q[MT];
-#pragma unroll
-  for (int m = 0; m < MT; ++m) n_diff[m] = n_x2[m] = n_q[m] = 0.0;
-
-  auto load_chunk = [&](int c, int buf) {
-    const double* src = b.Psw + (size_t)(c_begin + c) * chunk_elems;
-    double* dst = Pst + (size_t)buf * chunk_elems;
-    for (int i = tid * 2; i < chunk_elems; i += PASS_WARPS * 32 * 2) cp_async16(dst + i, src + i);
-  };
-#pragma unroll
-  for (int s = 0; s < PASS_STAGES - 1; ++s) {
-    if (s < nchunks) load_chunk(s, s);
-    cp_async_commit();
+  for (int m = 0; m < MT; ++m) {
+    n_dh[m] = n_xm[m] = 0.0;
+    ratio[m] = MODE == PASS_VINIT ? mu20[m] / b.mu20_used[8 * pt[m] + g] : 1.0;
   }
 
-  const int swg = p_swz(g);
-  const int sw0 = p_swz(2 * t), sw1 = p_swz(2 * t + 1);
-
-  // software prefetch of the state of the next 8-row tile
+  // state pointers (this lane's two values of the current 8-row tile) + one-tile software prefetch
+  double* Sp[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) Sp[m] = b.S + state_index(d, pt[m], c_begin * PASS_CHUNK_RT, lane);
+  const int ntiles = nchunks * PASS_CHUNK_RT;
   double2 st_nxt[MT];
-  auto load_state = [&](int rt) {
 #pragma unroll
-    for (int m = 0; m < MT; ++m)
-      st_nxt[m] = inr[m] ? ld_stream2(b.S + state_index(d, pt[m], rt, lane)) : make_double2(0.0, 0.0);
-  };
-  if (active && nchunks > 0) load_state(c_begin * PASS_CHUNK_RT);
+  for (int m = 0; m < MT; ++m) st_nxt[m] = (active && ntiles > 0) ? ld_stream2(Sp[m]) : make_double2(0.0, 0.0);
 
+  int stage = 0;
+  unsigned parity = 0;
   for (int c = 0; c < nchunks; ++c) {
-    cp_async_wait<PASS_STAGES - 2>();
-    __syncthreads();
-    if (c + PASS_STAGES - 1 < nchunks) load_chunk(c + PASS_STAGES - 1, (c + PASS_STAGES - 1) % PASS_STAGES);
-    cp_async_commit();
-    if (!active) continue;
-    const double* Pc = Pst + (size_t)(c % PASS_STAGES) * chunk_elems;
-#pragma unroll 1
-    for (int r4 = 0; r4 < PASS_CHUNK_RT; ++r4) {
-      const int rt = (c_begin + c) * PASS_CHUNK_RT + r4;
-      const double* Pb = Pc + r4 * 8 * ldp;
-      double2 st[MT];
+    if (active) {
+      mbar_wait(full_bar + stage, parity);
+      const double* Pc = Pst + stage * CHUNK_D + lane * 2;
 #pragma unroll
-      for (int m = 0; m < MT; ++m) st[m] = st_nxt[m];
-      const bool last = (c == nchunks - 1) && (r4 == PASS_CHUNK_RT - 1);
-      if (!last) load_state(rt + 1);
+      for (int r4 = 0; r4 < PASS_CHUNK_RT; ++r4) {
+        const double* P1 = Pc + r4 * TILE_D;        // GEMM1' operand: [j][lane][2]
+        const double* P2 = P1 + NT * 64;            // GEMM2' operand: [j][lane][2]
+        double2 st[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) st[m] = st_nxt[m];
+        {
+          // prefetch the next tile's state (the last tile re-reads itself)
+          const int step = (c * PASS_CHUNK_RT + r4 + 1 < ntiles) ? 64 : 0;
+#pragma unroll
+          for (int m = 0; m < MT; ++m) st_nxt[m] = ld_stream2(Sp[m] + r4 * 64 + step);
+        }
 
-      // ---- GEMM1': q[c][r] = sum_l x0[l][c] P[r][l]   (two independent accumulation chains per tile)
-      double q[MT][2], q2[MT][2];
-#pragma unroll
-      for (int m = 0; m < MT; ++m) q[m][0] = q[m][1] = q2[m][0] = q2[m][1] = 0.0;
-      {
-        const double* prow = Pb + g * ldp;
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          const double2 bb = *reinterpret_cast<const double2*>(prow + ((8 * j + 2 * t) ^ swg));
+        double u[MT][2];
+        if (MODE == PASS_STEP) {
+          // ---- GEMM1': s' = max(0,s) - mu20 * (P x0)   (accumulator starts at Re h20 = max(0,s))
+          double q[MT][2], q2[MT][2], hre[MT][2];
 #pragma unroll
           for (int m = 0; m < MT; ++m) {
-            dmma(q[m][0], q[m][1], xa[m][j][0], bb.x);
-            dmma(q2[m][0], q2[m][1], xa[m][j][1], bb.y);
+            hre[m][0] = is_neg(st[m].x) ? 0.0 : st[m].x;
+            hre[m][1] = is_neg(st[m].y) ? 0.0 : st[m].y;
+            q[m][0] = hre[m][0];
+            q[m][1] = hre[m][1];
+            q2[m][0] = q2[m][1] = 0.0;
           }
-        }
-      }
-
-      // ---- elementwise: non-negative z-update, dual ascent, residual partials
-      double u[MT][2], ux[MT][2];
 #pragma unroll
-      for (int m = 0; m < MT; ++m) {
-        double sn[2];
+          for (int j = 0; j < NT; ++j) {
+            const double2 bb = *reinterpret_cast<const double2*>(P1 + j * 64);
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const double s_old = e == 0 ? st[m].x : st[m].y;
-          const double hre = s_old > 0.0 ? s_old : 0.0;
-          const double qv = q[m][e] + q2[m][e];
-          if (MODE == 2) {
-            sn[e] = s_old;
-            u[m][e] = hre;
-            ux[m][e] = s_old < 0.0 ? (-s_old) * inv_mu20[m] : 0.0;
-          } else {
-            const double a = qv - hre * inv_mu20[m];
-            const double x2 = a < 0.0 ? 0.0 : a;
-            const double s_new = x2 > 0.0 ? -(mu20[m] * x2) : hre - mu20[m] * qv;
-            const double df = qv - x2;
-            n_diff[m] += df * df;
-            n_x2[m] += x2 * x2;
-            n_q[m] += qv * qv;
-            sn[e] = dn[m] ? s_old : s_new;
-            if (MODE == 1) {
-              u[m][e] = s_new > 0.0 ? s_new : 0.0;
-              ux[m][e] = x2;
-            } else {
-              u[m][e] = fabs(s_new);
-              ux[m][e] = 0.0;
+            for (int m = 0; m < MT; ++m) {
+              if (MT == 1) {      // a single tile per warp: two chains hide the DMMA latency
+                dmma(q[m][0], q[m][1], xa[m][j][0], bb.x);
+                dmma(q2[m][0], q2[m][1], xa[m][j][1], bb.y);
+              } else {
+                dmma(q[m][0], q[m][1], xa[m][j][0], bb.x);
+                dmma(q[m][0], q[m][1], xa[m][j][1], bb.y);
+              }
             }
           }
+          // ---- elementwise: s' encodes both the dual ascent and the non-negative projection
+          //   Re h20' = max(0, s'),  mu20 x2' = max(0, -s'),  mu20 (P x0 - x2') = Re h20 - Re h20'
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            double sn[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const double s_new = MT == 1 ? q[m][e] + q2[m][e] : q[m][e];
+              const bool neg = is_neg(s_new);
+              const double hnew = neg ? 0.0 : s_new;
+              const double xm = neg ? s_new : 0.0;
+              const double dh = hre[m][e] - hnew;
+              n_dh[m] += dh * dh;
+              n_xm[m] += xm * xm;
+              u[m][e] = fabs(s_new);
+              sn[e] = dn[m] ? (e == 0 ? st[m].x : st[m].y) : s_new;
+            }
+            if (inr[m]) st_stream2(Sp[m] + r4 * 64, make_double2(sn[0], sn[1]));
+          }
+        } else {
+          // V from the current state, no step:  u = Re h20 + mu20 x2  with x2 decoded by mu20_used
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            u[m][0] = is_neg(st[m].x) ? -st[m].x * ratio[m] : st[m].x;
+            u[m][1] = is_neg(st[m].y) ? -st[m].y * ratio[m] : st[m].y;
+          }
         }
-        if (MODE != 2 && inr[m]) st_stream2(b.S + state_index(d, pt[m], rt, lane), make_double2(sn[0], sn[1]));
-      }
 
-      // ---- GEMM2': V[c][l] += sum_r u[c][r] P[r][l],  k-slot t <-> row 2t+e
-      {
-        const double* prow0 = Pb + (2 * t) * ldp;
-        const double* prow1 = prow0 + ldp;
+        // ---- GEMM2': V[c][l] += sum_r u[c][r] P[r][l],  k-slot t of step e <-> row 2t+e
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
-          const double b0 = prow0[(8 * j + g) ^ sw0];
-          const double b1 = prow1[(8 * j + g) ^ sw1];
+          const double2 bb = *reinterpret_cast<const double2*>(P2 + j * 64);
 #pragma unroll
-          for (int m = 0; m < MT; ++m) {
-            dmma(acc[m][j][0], acc[m][j][1], u[m][0], b0);
-            if (MODE != 0) dmma(accx[m][j][0], accx[m][j][1], ux[m][0], b0);
-          }
+          for (int m = 0; m < MT; ++m) dmma(acc[m][j][0], acc[m][j][1], u[m][0], bb.x);
 #pragma unroll
-          for (int m = 0; m < MT; ++m) {
-            dmma(acc[m][j][0], acc[m][j][1], u[m][1], b1);
-            if (MODE != 0) dmma(accx[m][j][0], accx[m][j][1], ux[m][1], b1);
-          }
+          for (int m = 0; m < MT; ++m) dmma(acc[m][j][0], acc[m][j][1], u[m][1], bb.y);
         }
       }
+#pragma unroll
+      for (int m = 0; m < MT; ++m) Sp[m] += PASS_CHUNK_RT * 64;
+    }
+
+    // ---- release the stage; the warp that arrives last refills it with chunk c + PASS_STAGES
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(empty_bar + stage);
+      const unsigned tk = atomicAdd(ticket + stage, 1u);
+      if ((tk & (PASS_WARPS - 1)) == PASS_WARPS - 1 && c + PASS_STAGES < nchunks) {
+        mbar_wait(empty_bar + stage, parity);
+        mbar_expect_tx(full_bar + stage, CHUNK_BYTES);
+        tma_bulk_g2s(Pst + stage * CHUNK_D, Pf_src + (size_t)(c + PASS_STAGES) * CHUNK_D, CHUNK_BYTES, full_bar + stage);
+      }
+    }
+    if (++stage == PASS_STAGES) {
+      stage = 0;
+      parity ^= 1u;
     }
   }
-  cp_async_wait<0>();
   if (!active) return;
 
   // ---- epilogue: partial V (fragment layout) and per-column norm partials
@@ -580,15 +647,14 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4) spm_pass_ker
     for (int j = 0; j < NT; ++j) {
       const size_t o = sp * vstride + frag_index(pt[m] * npl, NT, j, lane);
       *reinterpret_cast<double2*>(b.V + o) = make_double2(acc[m][j][0], acc[m][j][1]);
-      if (MODE != 0) *reinterpret_cast<double2*>(b.Vx + o) = make_double2(accx[m][j][0], accx[m][j][1]);
     }
-    if (MODE != 2) {
-      const double s0 = quad_sum(n_diff[m]), s1 = quad_sum(n_x2[m]), s2 = quad_sum(n_q[m]);
+    if (MODE == PASS_STEP) {
+      const double inv = 1.0 / mu20[m];
+      const double s0 = quad_sum(n_dh[m]) * inv * inv, s1 = quad_sum(n_xm[m]) * inv * inv;
       if (t == 0 && !dn[m]) {
-        double* o = b.normsB + ((size_t)sp * nct * 8 + (size_t)(pt[m] * npl) * 8 + g) * 4;
-        o[0] = s0;
-        o[1] = s1;
-        o[2] = s2;
+        double* o = b.normsB + ((size_t)sp * nct * 8 + (size_t)(pt[m] * npl) * 8 + g) * 2;
+        o[0] = s0;      // |P Re(x0) - x2|^2
+        o[1] = s1;      // |x2|^2
       }
     }
   }
@@ -607,16 +673,15 @@ __device__ __forceinline__ void gather_problem(const admm_spm_dims& d, const adm
     const double* a = b.normsA + col * 8;
 #pragma unroll
     for (int i = 0; i < 7; ++i) s[i] += a[i];
+    s[9] += a[7];                                // |P x0|^2 (Gram form), both planes
     if (pl == 0) {
       for (int sp = 0; sp < d.nsplit; ++sp) {
-        const double* bb = b.normsB + ((size_t)sp * nct * 8 + col) * 4;
+        const double* bb = b.normsB + ((size_t)sp * nct * 8 + col) * 2;
         s[7] += bb[0];
         s[8] += bb[1];
-        s[9] += bb[2];
       }
     } else {
-      s[7] += a[7];      // |P Im(x0) - 0|^2
-      s[9] += a[7];      // |P Im(x0)|^2
+      s[7] += a[7];                              // |P Im(x0) - 0|^2
     }
   }
 }
@@ -710,34 +775,50 @@ static int check_dims(const admm_spm_dims* d, const char* who) {
   ADMM_REQUIRE(d != nullptr, ADMM_EINVAL, "%s: null dims", who);
   ADMM_REQUIRE(d->L >= 1 && (d->Lp == 16 || d->Lp == 40 || d->Lp == 64) && d->Lp >= d->L, ADMM_EUNSUPPORTED,
                "%s: L=%d Lp=%d unsupported (Lp must be 16, 40 or 64 and >= L)", who, d->L, d->Lp);
-  ADMM_REQUIRE(d->ldp % 16 == 0 && d->ldp >= d->Lp, ADMM_EINVAL, "%s: ldp=%d must be a multiple of 16 >= Lp", who, d->ldp);
   ADMM_REQUIRE(d->nrt % PASS_CHUNK_RT == 0 && d->nrt * 8 >= d->Nw && d->Nw >= 1, ADMM_EINVAL,
                "%s: nrt=%d must be a multiple of %d covering Nw=%d", who, d->nrt, PASS_CHUNK_RT, d->Nw);
   ADMM_REQUIRE(d->nb >= 1 && d->npt * 8 >= d->nb, ADMM_EINVAL, "%s: bad nb/npt", who);
   ADMM_REQUIRE(d->nplanes == 1 || d->nplanes == 2, ADMM_EINVAL, "%s: nplanes must be 1 or 2", who);
-  ADMM_REQUIRE(d->mt == 1 || d->mt == 2, ADMM_EINVAL, "%s: mt must be 1 or 2", who);
+  ADMM_REQUIRE(d->mt == 1 || (d->mt == 2 && d->Lp <= 40), ADMM_EINVAL, "%s: mt must be 1, or 2 with Lp <= 40", who);
   ADMM_REQUIRE(d->nsplit >= 1 && d->nsplit <= d->nrt / PASS_CHUNK_RT, ADMM_EINVAL, "%s: bad nsplit=%d", who, d->nsplit);
   return ADMM_OK;
 }
 
 static int ew_grid(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 16)); }
 
-template <int NT, int MT>
-static int launch_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, cudaStream_t s) {
+template <int NT, int MT, int MODE, bool FUSED>
+static int launch_pass_k(const admm_spm_dims* d, const admm_spm_buffers* b, int fresh, cudaStream_t s) {
   dim3 grid(ceil_div(d->npt, PASS_WARPS * MT), d->nsplit);
-  const size_t smem = (size_t)PASS_STAGES * PASS_CHUNK_RT * 8 * d->ldp * sizeof(double);
-  auto k0 = spm_pass_kernel<NT, MT, 0>;
-  auto k1 = spm_pass_kernel<NT, MT, 1>;
-  auto k2 = spm_pass_kernel<NT, MT, 2>;
-  auto k = mode == 0 ? k0 : (mode == 1 ? k1 : k2);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k<<<grid, PASS_WARPS * 32, smem, s>>>(*d, *b);
-  return check_launch("admm_spm_pass");
+  const size_t smem = (size_t)PASS_STAGES * PASS_CHUNK_RT * 2 * NT * 64 * sizeof(double) + 2 * PASS_STAGES * sizeof(uint64_t) +
+                      PASS_STAGES * sizeof(unsigned) + 16;
+  auto k = spm_pass_kernel<NT, MT, MODE, FUSED>;
+  static bool configured = false;     // per instantiation
+  if (!configured) {
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  k<<<grid, PASS_WARPS * 32, smem, s>>>(*d, *b, fresh);
+  return check_launch(FUSED ? "admm_spm_step" : "admm_spm_pass");
 }
 
-template <int NT>
-static int launch_pass_nt(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, cudaStream_t s) {
-  return d->mt == 2 ? launch_pass<NT, 2>(d, b, mode, s) : launch_pass<NT, 1>(d, b, mode, s);
+template <int NT, int MT>
+static int launch_pass_mode(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, bool fused, int fresh,
+                            cudaStream_t s) {
+  if (fused) return launch_pass_k<NT, MT, PASS_STEP, true>(d, b, fresh, s);
+  if (mode == PASS_STEP) return launch_pass_k<NT, MT, PASS_STEP, false>(d, b, 0, s);
+  return launch_pass_k<NT, MT, PASS_VINIT, false>(d, b, 0, s);
+}
+
+static int launch_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, bool fused, int fresh, cudaStream_t s) {
+  switch (d->Lp / 8) {
+    case 2:
+      return d->mt == 2 ? launch_pass_mode<2, 2>(d, b, mode, fused, fresh, s) : launch_pass_mode<2, 1>(d, b, mode, fused, fresh, s);
+    case 5:
+      return d->mt == 2 ? launch_pass_mode<5, 2>(d, b, mode, fused, fresh, s) : launch_pass_mode<5, 1>(d, b, mode, fused, fresh, s);
+    default:
+      return launch_pass_mode<8, 1>(d, b, mode, fused, fresh, s);
+  }
 }
 
 }  // namespace admm
@@ -746,9 +827,9 @@ using namespace admm;
 
 extern "C" {
 
-int admm_spm_prepare_P(const admm_spm_dims* d, const double* P, int ldP, double* Psw, admm_stream_t stream) {
+int admm_spm_prepare_P(const admm_spm_dims* d, const double* P, int ldP, double* Pf, admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_prepare_P")) return rc;
-  prepare_P_kernel<<<ew_grid((long long)d->nrt * 8 * d->ldp), 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, P, ldP, Psw);
+  prepare_P_kernel<<<ew_grid((long long)d->nrt * 2 * d->Lp * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, P, ldP, Pf);
   return check_launch("admm_spm_prepare_P");
 }
 
@@ -794,28 +875,29 @@ int admm_spm_factor(const admm_spm_dims* d, int nslots, const int* slots, const 
   return check_launch("admm_spm_factor");
 }
 
-int admm_spm_xupdate(const admm_spm_dims* d, const admm_spm_buffers* b, int v_split, admm_stream_t stream) {
+int admm_spm_xupdate(const admm_spm_dims* d, const admm_spm_buffers* b, int fresh, admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_xupdate")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int nct = d->npt * d->nplanes;
   const int grid = ceil_div(nct, 4);
   switch (d->Lp / 8) {
-    case 2: spm_xupdate_kernel<2><<<grid, 128, 0, s>>>(*d, *b, v_split); break;
-    case 5: spm_xupdate_kernel<5><<<grid, 128, 0, s>>>(*d, *b, v_split); break;
-    default: spm_xupdate_kernel<8><<<grid, 128, 0, s>>>(*d, *b, v_split); break;
+    case 2: spm_xupdate_kernel<2><<<grid, 128, 0, s>>>(*d, *b, fresh); break;
+    case 5: spm_xupdate_kernel<5><<<grid, 128, 0, s>>>(*d, *b, fresh); break;
+    default: spm_xupdate_kernel<8><<<grid, 128, 0, s>>>(*d, *b, fresh); break;
   }
   return check_launch("admm_spm_xupdate");
 }
 
 int admm_spm_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_pass")) return rc;
-  ADMM_REQUIRE(mode >= 0 && mode <= 2, ADMM_EINVAL, "admm_spm_pass: mode must be 0, 1 or 2");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  switch (d->Lp / 8) {
-    case 2: return launch_pass_nt<2>(d, b, mode, s);
-    case 5: return launch_pass_nt<5>(d, b, mode, s);
-    default: return launch_pass_nt<8>(d, b, mode, s);
-  }
+  ADMM_REQUIRE(mode == PASS_STEP || mode == PASS_VINIT, ADMM_EINVAL, "admm_spm_pass: mode must be 0 (step) or 1 (V from state)");
+  return launch_pass(d, b, mode, false, 0, static_cast<cudaStream_t>(stream));
+}
+
+int admm_spm_step(const admm_spm_dims* d, const admm_spm_buffers* b, int fresh, admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_step")) return rc;
+  ADMM_REQUIRE(d->nsplit == 1, ADMM_EINVAL, "admm_spm_step: the fused x-update + pass needs nsplit == 1 (got %d)", d->nsplit);
+  return launch_pass(d, b, PASS_STEP, true, fresh, static_cast<cudaStream_t>(stream));
 }
 
 int admm_spm_reduce(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream_t stream) {

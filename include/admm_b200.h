@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ADMM_ABI_VERSION 1
+#define ADMM_ABI_VERSION 2
 
 enum admm_status { ADMM_OK = 0, ADMM_EINVAL = 1, ADMM_ECUDA = 2, ADMM_EUNSUPPORTED = 3 };
 enum admm_op { ADMM_OP_N = 0, ADMM_OP_T = 1, ADMM_OP_H = 2 };
@@ -103,7 +103,6 @@ int admm_spd_inverse_batched(int n, int nbatch, double* A, long long batch_strid
 typedef struct admm_spm_dims {
   int L;        /* basis size (size_x of terms 0 and 1)                                        */
   int Lp;       /* L padded to 16, 40 or 64 (the instantiated tensor-core tile counts)         */
-  int ldp;      /* row stride of the swizzled P, multiple of 16, >= Lp                         */
   int Nw;       /* number of sampling points (size_x of term 2)                                */
   int nrt;      /* number of 8-row tiles, ceil(Nw / 8) rounded up to a multiple of 4           */
   int nb;       /* number of problems                                                          */
@@ -115,8 +114,11 @@ typedef struct admm_spm_dims {
                      reference semantics), 0: per-problem mu / stopping                        */
 } admm_spm_dims;
 
-/* P (Nw x L, row-major, ld = ldP) -> Psw (8*nrt x ldp) zero padded, columns XOR-swizzled per row. */
-int admm_spm_prepare_P(const admm_spm_dims* d, const double* P, int ldP, double* Psw,
+/* P (Nw x L, row-major, ld = ldP) -> Pf[nrt][2][Lp/8][32][2], zero padded, fragment-major: per
+ * 8-row tile first the B operand of Q = P x0 (element (lane=4g+t, e) of slice j = P[8rt+g][8j+2t+e]),
+ * then the B operand of V = P^T u (P[8rt+2t+e][8j+g]); the pass kernel pulls 4-tile chunks of it
+ * into shared memory with TMA bulk copies and reads them with conflict-free 16-byte loads. */
+int admm_spm_prepare_P(const admm_spm_dims* d, const double* P, int ldP, double* Pf,
                        admm_stream_t stream);
 
 /* canonical (rows x nb) complex128 or float64 (batch index fastest) <-> fragment layout.
@@ -152,7 +154,7 @@ int admm_spm_factor(const admm_spm_dims* d, int nslots, const int* slots, const 
 
 typedef struct admm_spm_buffers {
   /* shared operators */
-  const double* Psw;      /* 8*nrt x ldp swizzled P                                            */
+  const double* Pf;       /* [nrt][2][Lp/8][32][2] fragment-major P (admm_spm_prepare_P)        */
   const double* PtP;      /* Lp x Lp                                                           */
   const double* Cvec;     /* Lp                                                                */
   const double* Ginv_cache; /* nslot x Lp x Lp                                                 */
@@ -174,13 +176,14 @@ typedef struct admm_spm_buffers {
   double* h10;
   double* V;              /* [nsplit][ncolumn tiles][Lp/8][32][2]  P^T(h20 + mu20 x2) partials;
                              imaginary-plane tiles: z = P^T Im(h20) in split 0 (owned by xupdate)    */
-  double* Vx;             /* same shape: P^T x2 partials (split form, valid after a split pass) */
   double* aim;            /* fragment layout; imaginary-plane tiles accumulate sum_k mu20_k Im(x0_k) */
   /* implicit (h20, x2) state */
   double* S;              /* [npt][nrt][32][2]                                                 */
   /* norms */
-  double* normsA;         /* [8*npt*nplanes][8] from xupdate                                   */
-  double* normsB;         /* [nsplit][8*npt*nplanes][4] from pass (real-plane columns only)    */
+  double* normsA;         /* [8*npt*nplanes][8] from xupdate; slot 7 = |P x0|^2 of the column,
+                             read back on the next iteration as |P x0_old|^2                   */
+  double* normsB;         /* [nsplit][8*npt*nplanes][2] from pass (real-plane columns only):
+                             |P Re(x0) - x2|^2, |x2|^2                                         */
   double* gsum;           /* [16] batch-wide sums (reduce), only batch_wide                    */
   double* gpart;          /* [256][16] scratch of the two-stage reduce                         */
   /* control */
@@ -197,18 +200,26 @@ typedef struct admm_spm_buffers {
 
 /* x-update (term 0, `ConstrainedLeastSquares.solve`, objectivefunc.py:138-157, with
  * `_hk`/`_mu_k`, optimizer.py:175-230), L1 z-update (objectivefunc.py:174-195) and dual ascent of
- * pair (1,0) (optimizer.py:334-341); norms of pair (1,0) and the Gram-form dual norms of pair
- * (2,0).  v_split != 0: V is in split form (V + mu20 * Vx). */
-int admm_spm_xupdate(const admm_spm_dims* d, const admm_spm_buffers* b, int v_split,
+ * pair (1,0) (optimizer.py:334-341); norms of pair (1,0) and the Gram-form norms of pair (2,0)
+ * (|P v|^2 = v^T (P^T P) v).  fresh != 0: first iteration after the state was (re)loaded --
+ * |P x0_old|^2 is recomputed instead of being taken from normsA[.][7]. */
+int admm_spm_xupdate(const admm_spm_dims* d, const admm_spm_buffers* b, int fresh,
                      admm_stream_t stream);
 
-/* One streaming sweep over the implicit (Re h20, x2) state: Q = P Re(x0) (FP64 tensor cores), the
- * non-negative z-update (objectivefunc.py:256-271), dual ascent of pair (2,0)
- * (optimizer.py:334-341), residual partial sums (optimizer.py:251-274) and V = P^T(h20 + mu20 x2)
- * for the next x-update (optimizer.py:194-200), all in one read+write of the state.
- * mode 0: normal, 1: also emit the split form (V = P^T h20, Vx = P^T x2) -- used on iterations
- * that may change mu, 2: init (no update; emit split form from the current state). */
+/* One streaming sweep over the implicit (Re h20, x2) state: s' = Re h20 - mu20 P Re(x0) (FP64
+ * tensor cores; the accumulator starts at Re h20), which encodes the non-negative z-update
+ * (objectivefunc.py:256-271) and the dual ascent of pair (2,0) (optimizer.py:334-341) at once;
+ * residual partial sums (optimizer.py:251-274) and V = P^T(h20 + mu20 x2) = P^T |s'| for the next
+ * x-update (optimizer.py:194-200), all in one read+write of the state.
+ * mode 0: step.  mode 1: no step; V = P^T(Re h20 + mu20 x2) from the current state with x2 decoded
+ * by mu20_used -- run after the state or mu20 changed (set_state, update_mu). */
 int admm_spm_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode,
+                  admm_stream_t stream);
+
+/* admm_spm_xupdate + admm_spm_pass(mode 0) in ONE kernel: every warp first does the x-update of
+ * its own problem tiles (both planes) and then streams their state, so x0 goes from the
+ * x-update to the tensor-core operand registers without a round trip.  Needs nsplit == 1. */
+int admm_spm_step(const admm_spm_dims* d, const admm_spm_buffers* b, int fresh,
                   admm_stream_t stream);
 
 /* Batch-wide norms: deterministic two-stage sum over all problems into gsum[16].  The caller

@@ -39,10 +39,10 @@ _P = C.c_void_p
 
 class SpmBuffers(C.Structure):
     _fields_ = [
-        ("Pf", _P), ("PtP", _P), ("Cvec", _P), ("Ginv_cache", _P), ("w_cache", _P), ("sigma_cache", _P),
+        ("Pf", _P), ("PtPf", _P), ("Cvec", _P), ("Ginv_cache", _P), ("w_cache", _P), ("sigma_cache", _P),
         ("slot", _P), ("mu10", _P), ("mu20", _P), ("mu20_used", _P), ("done", _P), ("iters", _P),
         ("last_res", _P), ("Dre", _P),
-        ("b0", _P), ("x0", _P), ("x1", _P), ("h10", _P), ("V", _P), ("aim", _P),
+        ("b0", _P), ("x0", _P), ("x1", _P), ("h10", _P), ("y0", _P), ("V", _P), ("aim", _P),
         ("S", _P),
         ("normsA", _P), ("normsB", _P), ("gsum", _P), ("gpart", _P),
         ("iter_counter", _P), ("flags", _P), ("history", _P), ("hist_cap", C.c_int),
@@ -79,14 +79,16 @@ _SIGS = {
     "admm_inverse": ([_I, _I, _P, _I, _P, _I, _P, _P, _P], _I),
     "admm_spd_inverse_batched": ([_I, _I, _P, _LL, _I, _P, _P, _P], _I),
     "admm_spm_prepare_P": ([C.POINTER(SpmDims), _P, _I, _P, _P], _I),
+    "admm_spm_pack_operator": ([C.POINTER(SpmDims), _P, _P, _P], _I),
     "admm_spm_pack_L": ([C.POINTER(SpmDims), _P, _I, _P, _P], _I),
     "admm_spm_unpack_L": ([C.POINTER(SpmDims), _P, _P, _I, _P], _I),
     "admm_spm_pack_state": ([C.POINTER(SpmDims), _P, _P, _I, _P, _P, _P, _P], _I),
     "admm_spm_unpack_state": ([C.POINTER(SpmDims), _P, _P, _P, _P, _P, _I, _P], _I),
     "admm_spm_factor": ([C.POINTER(SpmDims), _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
-    "admm_spm_xupdate": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
+    "admm_spm_xupdate": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _P], _I),
+    "admm_spm_refresh_y": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _P], _I),
     "admm_spm_pass": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
-    "admm_spm_step": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
+    "admm_spm_step": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _P], _I),
     "admm_spm_reduce": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _P], _I),
     "admm_spm_decide": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
     "admm_bp_setup": ([C.POINTER(BpBuffers), _P, _P, _P, _P], _I),

@@ -143,6 +143,8 @@ class SharedSpM:
         ptp = z(L, L)
         call("admm_gemm", 0, _lib.OP_T, L, L, Nw, ptr(P_t), L, ptr(P_t), L, ptr(ptp), L, stream())
         self.PtP[:L, :L] = ptp
+        self.PtPf = z(Lp * Lp)
+        call("admm_spm_pack_operator", dref, ptr(self.PtP), ptr(self.PtPf), stream())
         self.G0 = z(Lp, Lp)
         self.G0[:L, :L] = G0
         Cv = _dev_tensor(np.asarray(C_) if not isinstance(C_, torch.Tensor) else C_, dev, _F64).reshape(-1)
@@ -170,7 +172,7 @@ class SharedSpM:
         fl = nct * NT * 64
         self.b0 = z(fl)
         call("admm_spm_pack_L", dref, ptr(b0.contiguous()), int(b0.is_complex()), ptr(self.b0), stream())
-        self.x0f, self.x1f, self.h10f = z(fl), z(fl), z(fl)
+        self.x0f, self.x1f, self.h10f, self.y0f = z(fl), z(fl), z(fl), z(fl)
         self.V = z(nsplit * fl)
         self.aim = z(fl)                  # sum_k mu20_k Im(x0_k)  (imaginary-plane tiles only)
         self._him_base = None             # Im(h20) at the time of set_state (None == 0)
@@ -184,7 +186,7 @@ class SharedSpM:
         self.history = None
         self.pass_events = None      # bench.py: list collecting (start, stop) CUDA events around the pass kernel
         self._v_valid = False        # V = P^T(h20 + mu20 x2) matches the current state and mu20
-        self._fresh = True           # next x-update must recompute |P x0_old|^2
+        self._fresh = True           # y0 = P^T P x0 must be recomputed before the next x-update
         self._graphs = {}            # CUDA graphs of runs of plain iterations, keyed by (length, baked args)
         self.primal_residual = []
         self.dual_residual = []
@@ -194,11 +196,11 @@ class SharedSpM:
 
     def _fill_bufs(self, rtol, fact_incr=2.0, th_change=10.0):
         b = self.bufs
-        for name, t in (("Pf", self.Pf), ("PtP", self.PtP), ("Cvec", self.Cvec), ("Ginv_cache", self.Ginv_cache),
+        for name, t in (("Pf", self.Pf), ("PtPf", self.PtPf), ("Cvec", self.Cvec), ("Ginv_cache", self.Ginv_cache),
                         ("w_cache", self.w_cache), ("sigma_cache", self.sigma_cache), ("slot", self.slot),
                         ("mu10", self.mu10), ("mu20", self.mu20), ("mu20_used", self.mu20_used), ("done", self.done),
                         ("iters", self.iters), ("last_res", self.last_res), ("Dre", self.Dre), ("b0", self.b0),
-                        ("x0", self.x0f), ("x1", self.x1f), ("h10", self.h10f), ("V", self.V),
+                        ("x0", self.x0f), ("x1", self.x1f), ("h10", self.h10f), ("y0", self.y0f), ("V", self.V),
                         ("aim", self.aim), ("S", self.S), ("normsA", self.normsA), ("normsB", self.normsB), ("gsum", self.gsum),
                         ("gpart", self.gpart), ("iter_counter", self.iter_counter), ("flags", self.flags)):
             setattr(b, name, t.data_ptr())
@@ -393,17 +395,18 @@ class SharedSpM:
             # V = P^T(h20 + mu20 x2) from the current state (after set_state or a change of mu20)
             call("admm_spm_pass", dref, bref, 1, st)
             self._v_valid = True
-        fresh = int(self._fresh)
-        self._fresh = False
+        if self._fresh:
+            call("admm_spm_refresh_y", dref, bref, st)      # y0 = P^T P x0 for the loaded x0
+            self._fresh = False
         timed = self.pass_events is not None and not do_update_mu
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if self.dims.nsplit == 1:
             if timed:
                 e0.record()
-            call("admm_spm_step", dref, bref, fresh, st)
+            call("admm_spm_step", dref, bref, st)
         else:
-            call("admm_spm_xupdate", dref, bref, fresh, st)
+            call("admm_spm_xupdate", dref, bref, st)
             if timed:
                 e0.record()
             call("admm_spm_pass", dref, bref, 0, st)

@@ -58,10 +58,11 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch) {
 // FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).  SASS: DMMA.8x8x4 on sm_100a.
 // Fragment ownership (lane = 4*g + t):  a = A[g][t],  b = B[t][g],  c0/c1 = C[g][2t], C[g][2t+1].
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  // not volatile: a pure function of its operands, the compiler may schedule it freely
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-      : "+d"(c0), "+d"(c1)
-      : "d"(a), "d"(b));
+  // volatile: keeps the MMAs in program order relative to the (volatile) streaming loads/stores, so
+  // a software prefetch issued before a GEMM really is issued before it
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
 }
 
 // 16-byte async global->shared copy (LDGSTS)
@@ -112,6 +113,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+}
+// bulk prefetch of `bytes` (multiple of 16) of global memory into L2 (SASS UBLKPF): no register or
+// shared-memory cost, the later LDG hits L2 instead of HBM
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gsrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 // contiguous `bytes` (multiple of 16, both addresses 16-byte aligned) global -> shared; completion
 // is signalled on `bar` (complete_tx)

@@ -22,6 +22,14 @@ __device__ __forceinline__ size_t frag_index(int ct, int NT, int j, int lane) {
   return ((size_t)(ct * NT + j) * 32 + lane) * 2;
 }
 
+// fragment-major L x L operand:  Bf[jk][jn][lane][e] = B[8 jk + 2 t + e][8 jn + g]   (lane = 4 g + t)
+__host__ __device__ __forceinline__ size_t bfrag_index(int NT, int jk, int jn, int lane) {
+  return ((size_t)(jk * NT + jn) * 32 + lane) * 2;
+}
+__host__ __device__ __forceinline__ size_t bfrag_of(int NT, int row, int col) {
+  return bfrag_index(NT, row >> 3, col >> 3, 4 * (col & 7) + ((row & 7) >> 1)) + (row & 1);
+}
+
 // P (Nw x L) -> fragment-major Pf[rt][which][j][lane][e]  (zero padded):
 //   which 0 (GEMM1' B operand):  P[8 rt + g      ][8 j + 2 t + e]
 //   which 1 (GEMM2' B operand):  P[8 rt + 2 t + e][8 j + g      ]
@@ -145,6 +153,14 @@ __global__ void unpack_state_kernel(admm_spm_dims d, const double* __restrict__ 
   }
 }
 
+// canonical Lp x Lp (row-major) -> fragment-major operand of the x-update GEMMs
+__global__ void pack_operator_kernel(int Lp, const double* __restrict__ canon, double* __restrict__ Bf) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < Lp * Lp; idx += gridDim.x * blockDim.x) {
+    const int i = idx / Lp, j = idx - i * Lp;
+    Bf[bfrag_of(Lp / 8, i, j)] = canon[idx];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // factor: Ginv = (G0 + mu10 I + mu20 PtP)^-1 by in-place Gauss-Jordan in shared memory
 // ---------------------------------------------------------------------------------------------
@@ -190,10 +206,10 @@ __global__ void __launch_bounds__(256) spm_factor_kernel(admm_spm_dims d, const 
     }
     __syncthreads();
   }
-  double* Gi = Ginv_cache + (size_t)slot * Lp * Lp;
+  double* Gi = Ginv_cache + (size_t)slot * Lp * Lp;   // fragment-major (bfrag_of), zero padded
   for (int idx = tid; idx < Lp * Lp; idx += nt) {
     const int i = idx / Lp, j = idx - i * Lp;
-    Gi[idx] = (i < n && j < n) ? 0.5 * (a[i * n + j] + a[j * n + i]) : 0.0;
+    Gi[bfrag_of(Lp / 8, i, j)] = (i < n && j < n) ? 0.5 * (a[i * n + j] + a[j * n + i]) : 0.0;
   }
   __syncthreads();
   // w = Ginv C^T (symmetrised Ginv), sigma = C w
@@ -214,211 +230,242 @@ __global__ void __launch_bounds__(256) spm_factor_kernel(admm_spm_dims d, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// x-update of ONE column tile (8 problems x one plane) by one warp, everything in fragment layout
+// x-update of ONE problem tile (8 problems, all planes) by one warp, everything in fragment layout
 // ---------------------------------------------------------------------------------------------
-template <int NT>
-__device__ __forceinline__ void frag_gemm(double (&out)[NT][2], const double (&a)[NT][2], const double* __restrict__ Bm,
-                                          int ldb, int g, int t) {
-  // out[c][l'] = sum_l a[c][l] * Bm[l][l'],  k-slot (jk,e): l = 8*jk + 2*t + e
+// out[p][c][l'] = sum_l a[p][c][l] * B[l][l']  for NP planes that share the B fragments
+// (k-slot (jk,e) of lane (g,t) <-> l = 8 jk + 2 t + e); NT*NP independent accumulation chains.
+template <int NT, int NP>
+__device__ __forceinline__ void frag_gemm(double (&out)[NP][NT][2], const double (&a)[NP][NT][2],
+                                          const double* __restrict__ Bf, int lane) {
 #pragma unroll
-  for (int jn = 0; jn < NT; ++jn) out[jn][0] = out[jn][1] = 0.0;
+  for (int p = 0; p < NP; ++p)
+#pragma unroll
+    for (int jn = 0; jn < NT; ++jn) out[p][jn][0] = out[p][jn][1] = 0.0;
 #pragma unroll
   for (int jk = 0; jk < NT; ++jk) {
+    double2 bb[NT];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const double* brow = Bm + (size_t)(8 * jk + 2 * t + e) * ldb + g;
+    for (int jn = 0; jn < NT; ++jn) bb[jn] = __ldg(reinterpret_cast<const double2*>(Bf + bfrag_index(NT, jk, jn, lane)));
 #pragma unroll
-      for (int jn = 0; jn < NT; ++jn) dmma(out[jn][0], out[jn][1], a[jk][e], __ldg(brow + 8 * jn));
-    }
+    for (int jn = 0; jn < NT; ++jn)
+#pragma unroll
+      for (int p = 0; p < NP; ++p) dmma(out[p][jn][0], out[p][jn][1], a[p][jk][0], bb[jn].x);
+#pragma unroll
+    for (int jn = 0; jn < NT; ++jn)
+#pragma unroll
+      for (int p = 0; p < NP; ++p) dmma(out[p][jn][0], out[p][jn][1], a[p][jk][1], bb[jn].y);
   }
 }
 
-template <int NT>
-__device__ __forceinline__ double frag_dot(const double (&a)[NT][2], const double (&b)[NT][2]) {
-  double s = 0.0;
-#pragma unroll
-  for (int j = 0; j < NT; ++j) s += a[j][0] * b[j][0] + a[j][1] * b[j][1];
-  return s;
-}
-
 // Term 0 solve (ConstrainedLeastSquares with the cached inverse and KKT correction), L1 z-update,
-// dual ascent of pair (1,0), Gram-form norms of pair (2,0) and -- imaginary plane only -- the
-// L-space recursion of z = P^T Im(h20).  x0 (new) is returned in registers.
-// `fresh` != 0: |P x0_old|^2 is recomputed (first iteration after a state change); otherwise it
-// is the |P x0|^2 this function left in normsA[7] on the previous iteration.
+// dual ascent of pair (1,0), Gram-form norms of pair (2,0) (|P v|^2 = v^T (P^T P) v with
+// y = P^T P x0 cached from iteration to iteration) and -- imaginary plane -- the L-space
+// recursion of z = P^T Im(h20).  Re(x0) (new) is returned in registers for the pass.
+// y0 = P^T P x0_old must be current (spm_refresh_y_kernel after a state change).
 // Returns false when every problem of the tile is frozen (nothing was touched, x0 not loaded).
-template <int NT>
-__device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_spm_buffers& b, int pt, int pl, int fresh,
-                                             int lane, double (&x0)[NT][2]) {
+template <int NT, int NP, bool SPLIT>   // SPLIT: V arrives as d.nsplit partial sums (unfused small-batch path)
+__device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_spm_buffers& b, int pt, int lane) {
   const int g = lane >> 2, t = lane & 3;
-  const int ct = pt * d.nplanes + pl;
   const int prob = 8 * pt + g;
   const int is_done = b.done[prob];
   if (__all_sync(0xffffffffu, is_done)) return false;
   const double mu10 = b.mu10[prob], mu20 = b.mu20[prob];
   const int slot = b.slot[prob];
   const int Lp = d.Lp;
-  const size_t vstride = (size_t)d.npt * d.nplanes * NT * 64;
-  double* nrm = b.normsA + ((size_t)ct * 8 + g) * 8;
+  const int ct0 = pt * NP;
+  const size_t vstride = (size_t)d.npt * NP * NT * 64;
 
   // ---- rhs = alpha A^H y + h10 + mu10 x1 + P^T(h20 + mu20 x2)
-  double rhs[NT][2], zv[NT][2];
-  const int nsp = pl == 0 ? d.nsplit : 1;   // imaginary plane: z lives in split 0, owned by this function
+  double x0[NP][NT][2];
+  {
+    double rhs[NP][NT][2];
 #pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    const size_t o = frag_index(ct, NT, j, lane);
-    const double2 b0 = *reinterpret_cast<const double2*>(b.b0 + o);
-    const double2 hh = *reinterpret_cast<const double2*>(b.h10 + o);
-    const double2 x1 = *reinterpret_cast<const double2*>(b.x1 + o);
-    double2 v = *reinterpret_cast<const double2*>(b.V + o);
-    for (int sp = 1; sp < nsp; ++sp) {
-      const double2 p = *reinterpret_cast<const double2*>(b.V + sp * vstride + o);
-      v.x += p.x;
-      v.y += p.y;
-    }
-    zv[j][0] = v.x;
-    zv[j][1] = v.y;
-    rhs[j][0] = b0.x + hh.x + mu10 * x1.x + v.x;
-    rhs[j][1] = b0.y + hh.y + mu10 * x1.y + v.y;
-  }
-
-  // ---- xi1 = Ginv rhs, one tensor-core GEMM per distinct factor slot in the tile
-#pragma unroll
-  for (int j = 0; j < NT; ++j) x0[j][0] = x0[j][1] = 0.0;
-  unsigned remaining = __ballot_sync(0xffffffffu, !is_done);
-  while (remaining) {
-    const int leader = __ffs(remaining) - 1;
-    const int cur = __shfl_sync(0xffffffffu, slot, leader);
-    const bool match = (!is_done) && (slot == cur);
-    double acc[NT][2];
-    frag_gemm<NT>(acc, rhs, b.Ginv_cache + (size_t)cur * Lp * Lp, Lp, g, t);
-    if (match) {
+    for (int p = 0; p < NP; ++p) {
+      const int nsp = (SPLIT && p == 0) ? d.nsplit : 1;   // imaginary plane: z lives in split 0, owned by this function
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        x0[j][0] = acc[j][0];
-        x0[j][1] = acc[j][1];
+        const size_t o = frag_index(ct0 + p, NT, j, lane);
+        const double2 b0 = *reinterpret_cast<const double2*>(b.b0 + o);
+        const double2 hh = *reinterpret_cast<const double2*>(b.h10 + o);
+        const double2 x1 = *reinterpret_cast<const double2*>(b.x1 + o);
+        double2 v = *reinterpret_cast<const double2*>(b.V + o);
+#pragma unroll 1
+        for (int sp = 1; sp < nsp; ++sp) {
+          const double2 q = *reinterpret_cast<const double2*>(b.V + sp * vstride + o);
+          v.x += q.x;
+          v.y += q.y;
+        }
+        rhs[p][j][0] = b0.x + hh.x + mu10 * x1.x + v.x;
+        rhs[p][j][1] = b0.y + hh.y + mu10 * x1.y + v.y;
       }
     }
-    remaining &= ~__ballot_sync(0xffffffffu, match);
+    // ---- xi1 = Ginv rhs, one tensor-core GEMM per distinct factor slot in the tile (one slot unless
+    // the problems of the tile sit on different (mu10, mu20): per-problem mode only)
+    unsigned remaining = __ballot_sync(0xffffffffu, !is_done);
+#pragma unroll 1
+    do {
+      const int cur = __shfl_sync(0xffffffffu, slot, __ffs(remaining) - 1);
+      double acc[NP][NT][2];
+      frag_gemm<NT, NP>(acc, rhs, b.Ginv_cache + (size_t)cur * Lp * Lp, lane);
+      if (slot == cur) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p)
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            x0[p][j][0] = acc[p][j][0];
+            x0[p][j][1] = acc[p][j][1];
+          }
+      }
+      remaining &= ~__ballot_sync(0xffffffffu, slot == cur);
+    } while (remaining);
   }
 
   // ---- KKT correction enforcing C x0 = D   (objectivefunc.py:148-157)
   {
-    double cxi = 0.0;
-#pragma unroll
-    for (int j = 0; j < NT; ++j) cxi += b.Cvec[8 * j + 2 * t] * x0[j][0] + b.Cvec[8 * j + 2 * t + 1] * x0[j][1];
-    cxi = quad_sum(cxi);
-    const double nu = (b.Dre[(size_t)pl * 8 * d.npt + prob] - cxi) / b.sigma_cache[slot];
     const double* wv = b.w_cache + (size_t)slot * Lp;
+    const double isig = 1.0 / b.sigma_cache[slot];
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      x0[j][0] += wv[8 * j + 2 * t] * nu;
-      x0[j][1] += wv[8 * j + 2 * t + 1] * nu;
-    }
-  }
-
-  // ---- norms of the x0 change, plain and in Gram form  (|P d|^2 = d^T (P^T P) d)
-  double n_d, n_xo, nPd, nPxo;
-  {
-    double xo[NT][2], dd[NT][2], yd[NT][2];
+    for (int p = 0; p < NP; ++p) {
+      double cxi = 0.0;
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      const double2 v = *reinterpret_cast<const double2*>(b.x0 + frag_index(ct, NT, j, lane));
-      xo[j][0] = v.x;
-      xo[j][1] = v.y;
-      dd[j][0] = x0[j][0] - v.x;
-      dd[j][1] = x0[j][1] - v.y;
-    }
-    n_d = frag_dot<NT>(dd, dd);
-    n_xo = frag_dot<NT>(xo, xo);
-    frag_gemm<NT>(yd, dd, b.PtP, Lp, g, t);
-    nPd = frag_dot<NT>(yd, dd);
-    if (fresh) {
-      frag_gemm<NT>(yd, xo, b.PtP, Lp, g, t);
-      nPxo = frag_dot<NT>(yd, xo);
-    } else {
-      nPxo = (t == 0) ? nrm[7] : 0.0;     // quad-summed below
-    }
-  }
-
-  // ---- y = P^T P x0:  |P x0|^2 (the primal norm of pair (2,0) needs it for both planes), and for
-  // the imaginary plane  z <- z - mu20 y,  a += mu20 x0   (Im(h20) never leaves L-space)
-  double nPx;
-  {
-    double y[NT][2];
-    frag_gemm<NT>(y, x0, b.PtP, Lp, g, t);
-    nPx = frag_dot<NT>(y, x0);
-    if (pl == 1 && !is_done) {
+      for (int j = 0; j < NT; ++j) cxi += b.Cvec[8 * j + 2 * t] * x0[p][j][0] + b.Cvec[8 * j + 2 * t + 1] * x0[p][j][1];
+      cxi = quad_sum(cxi);
+      const double nu = (b.Dre[(size_t)p * 8 * d.npt + prob] - cxi) * isig;
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        const size_t o = frag_index(ct, NT, j, lane);
-        *reinterpret_cast<double2*>(b.V + o) = make_double2(zv[j][0] - mu20 * y[j][0], zv[j][1] - mu20 * y[j][1]);
+        x0[p][j][0] += wv[8 * j + 2 * t] * nu;
+        x0[p][j][1] += wv[8 * j + 2 * t + 1] * nu;
+      }
+    }
+  }
+
+  // ---- y = P^T P x0 (both planes in one GEMM)
+  double y[NP][NT][2];
+  frag_gemm<NT, NP>(y, x0, b.PtPf, lane);
+
+  const double thr = 0.5 * b.lam / mu10;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    // ---- norms of the x0 change, plain and in Gram form
+    double n_d = 0.0, n_xo = 0.0, nPd = 0.0, nPxo = 0.0, nPx = 0.0;
+    {
+      double xo[1][NT][2], yo[1][NT][2];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const double2 v = *reinterpret_cast<const double2*>(b.x0 + frag_index(ct0 + p, NT, j, lane));
+        xo[0][j][0] = v.x;
+        xo[0][j][1] = v.y;
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const double2 v = *reinterpret_cast<const double2*>(b.y0 + frag_index(ct0 + p, NT, j, lane));
+        yo[0][j][0] = v.x;
+        yo[0][j][1] = v.y;
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double dd = x0[p][j][e] - xo[0][j][e];
+          n_d += dd * dd;
+          n_xo += xo[0][j][e] * xo[0][j][e];
+          nPd += dd * (y[p][j][e] - yo[0][j][e]);
+          nPxo += xo[0][j][e] * yo[0][j][e];
+          nPx += x0[p][j][e] * y[p][j][e];
+        }
+    }
+    // ---- imaginary plane: z <- z - mu20 y,  a += mu20 x0   (Im(h20) never leaves L-space)
+    if (p == 1 && !is_done) {
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const size_t o = frag_index(ct0 + 1, NT, j, lane);
+        double2 zv = *reinterpret_cast<const double2*>(b.V + o);
+        zv.x -= mu20 * y[1][j][0];
+        zv.y -= mu20 * y[1][j][1];
+        *reinterpret_cast<double2*>(b.V + o) = zv;
         double2 av = *reinterpret_cast<const double2*>(b.aim + o);
-        av.x += mu20 * x0[j][0];
-        av.y += mu20 * x0[j][1];
+        av.x += mu20 * x0[1][j][0];
+        av.y += mu20 * x0[1][j][1];
         *reinterpret_cast<double2*>(b.aim + o) = av;
       }
     }
-  }
-
-  // ---- L1 z-update (real plane only; the imaginary part of x1 is identically zero) + dual ascent
-  const double thr = 0.5 * b.lam / mu10;
-  double n_p = 0.0, n_x0 = 0.0, n_x1 = 0.0;
+    // ---- L1 z-update (real plane only; the imaginary part of x1 is identically zero) + dual ascent
+    double n_p = 0.0, n_x0 = 0.0, n_x1 = 0.0;
 #pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    const size_t o = frag_index(ct, NT, j, lane);
-    const double2 hh = *reinterpret_cast<const double2*>(b.h10 + o);
-    double zz[2], hn[2];
+    for (int j = 0; j < NT; ++j) {
+      const size_t o = frag_index(ct0 + p, NT, j, lane);
+      const double2 hh = *reinterpret_cast<const double2*>(b.h10 + o);
+      double zz[2], hn[2];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const double xv = x0[j][e], hv = e == 0 ? hh.x : hh.y;
-      double z = 0.0;
-      if (pl == 0) {
-        const double yv = -((hv - mu10 * xv) / mu10);
-        if (yv > thr) z = yv - thr;
-        if (yv < -thr) z = yv + thr;
+      for (int e = 0; e < 2; ++e) {
+        const double xv = x0[p][j][e], hv = e == 0 ? hh.x : hh.y;
+        double z = 0.0;
+        if (p == 0) {
+          const double yv = -((hv - mu10 * xv) / mu10);
+          if (yv > thr) z = yv - thr;
+          if (yv < -thr) z = yv + thr;
+        }
+        hn[e] = hv + mu10 * (z - xv);
+        zz[e] = z;
+        n_p += (xv - z) * (xv - z);
+        n_x0 += xv * xv;
+        n_x1 += z * z;
       }
-      hn[e] = hv + mu10 * (z - xv);
-      zz[e] = z;
-      n_p += (xv - z) * (xv - z);
-      n_x0 += xv * xv;
-      n_x1 += z * z;
+      if (!is_done) {
+        *reinterpret_cast<double2*>(b.x0 + o) = make_double2(x0[p][j][0], x0[p][j][1]);
+        *reinterpret_cast<double2*>(b.x1 + o) = make_double2(zz[0], zz[1]);
+        *reinterpret_cast<double2*>(b.h10 + o) = make_double2(hn[0], hn[1]);
+        *reinterpret_cast<double2*>(b.y0 + o) = make_double2(y[p][j][0], y[p][j][1]);
+      }
     }
-    if (!is_done) {
-      *reinterpret_cast<double2*>(b.x0 + o) = make_double2(x0[j][0], x0[j][1]);
-      *reinterpret_cast<double2*>(b.x1 + o) = make_double2(zz[0], zz[1]);
-      *reinterpret_cast<double2*>(b.h10 + o) = make_double2(hn[0], hn[1]);
+    n_p = quad_sum(n_p);
+    n_x0 = quad_sum(n_x0);
+    n_x1 = quad_sum(n_x1);
+    n_d = quad_sum(n_d);
+    n_xo = quad_sum(n_xo);
+    nPd = quad_sum(nPd);
+    nPxo = quad_sum(nPxo);
+    nPx = quad_sum(nPx);
+    if (t == 0 && !is_done) {
+      double* nrm = b.normsA + ((size_t)(ct0 + p) * 8 + g) * 8;
+      nrm[0] = n_p;
+      nrm[1] = n_x0;
+      nrm[2] = n_x1;
+      nrm[3] = n_d;
+      nrm[4] = n_xo;
+      nrm[5] = nPd > 0.0 ? nPd : 0.0;
+      nrm[6] = nPxo > 0.0 ? nPxo : 0.0;
+      nrm[7] = nPx > 0.0 ? nPx : 0.0;     // |P x0|^2 of this plane
     }
-  }
-  n_p = quad_sum(n_p);
-  n_x0 = quad_sum(n_x0);
-  n_x1 = quad_sum(n_x1);
-  n_d = quad_sum(n_d);
-  n_xo = quad_sum(n_xo);
-  nPd = quad_sum(nPd);
-  nPxo = quad_sum(nPxo);
-  nPx = quad_sum(nPx);
-  if (t == 0 && !is_done) {
-    nrm[0] = n_p;
-    nrm[1] = n_x0;
-    nrm[2] = n_x1;
-    nrm[3] = n_d;
-    nrm[4] = n_xo;
-    nrm[5] = nPd > 0.0 ? nPd : 0.0;
-    nrm[6] = nPxo > 0.0 ? nPxo : 0.0;
-    nrm[7] = nPx > 0.0 ? nPx : 0.0;     // |P x0|^2 of this plane; next iteration's |P x0_old|^2
   }
   return true;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(128) spm_xupdate_kernel(admm_spm_dims d, admm_spm_buffers b, int fresh) {
+template <int NT, int NP>
+__global__ void __launch_bounds__(128) spm_xupdate_kernel(admm_spm_dims d, admm_spm_buffers b) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const int nct = d.npt * d.nplanes;
-  if (warp >= nct) return;
-  double x0[NT][2];
-  xupdate_tile<NT>(d, b, warp / d.nplanes, warp % d.nplanes, fresh, lane, x0);
+  if (warp >= d.npt) return;
+  xupdate_tile<NT, NP, true>(d, b, warp, lane);
+}
+
+// y0 = P^T P x0 for every column tile (after the state was loaded from outside)
+template <int NT>
+__global__ void __launch_bounds__(128) spm_refresh_y_kernel(admm_spm_dims d, admm_spm_buffers b) {
+  const int ct = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ct >= d.npt * d.nplanes) return;
+  double x[1][NT][2], y[1][NT][2];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const double2 v = *reinterpret_cast<const double2*>(b.x0 + frag_index(ct, NT, j, lane));
+    x[0][j][0] = v.x;
+    x[0][j][1] = v.y;
+  }
+  frag_gemm<NT, 1>(y, x, b.PtPf, lane);
+#pragma unroll
+  for (int j = 0; j < NT; ++j)
+    *reinterpret_cast<double2*>(b.y0 + frag_index(ct, NT, j, lane)) = make_double2(y[0][j][0], y[0][j][1]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -433,9 +480,9 @@ enum { PASS_STEP = 0, PASS_VINIT = 1 };
 // sign-bit helpers on the integer pipe (the FP64 pipe is shared with DMMA: keep it for the MMAs)
 __device__ __forceinline__ bool is_neg(double v) { return __double2hiint(v) < 0; }
 
-template <int NT, int MT, int MODE, bool FUSED>
+template <int NT, int MT, int MODE, int FNP>   // FNP: 0 = pass only, 1/2 = fused x-update of 1/2 planes
 __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
-    spm_pass_kernel(admm_spm_dims d, admm_spm_buffers b, int fresh) {
+    spm_pass_kernel(admm_spm_dims d, admm_spm_buffers b) {
   constexpr int TILE_D = 2 * NT * 64;                   // doubles of Pf per 8-row tile
   constexpr int CHUNK_D = PASS_CHUNK_RT * TILE_D;       // doubles per chunk
   constexpr unsigned CHUNK_BYTES = CHUNK_D * sizeof(double);
@@ -478,37 +525,28 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
   double xa[MT][NT][2];      // A fragments of GEMM1': -mu20 * Re(x0)   (k-slot (j,e) of lane (g,t) <-> l = 8j+2t+e)
   double acc[MT][NT][2];     // C fragments of GEMM2': V
   bool all_done = true;
+  if (FNP != 0) {
+    // x-update of this warp's tiles right here (all planes): x0 reaches the MMA operand registers
+    // through L1, the pass of the other warps hides the latency of this L x L work
+#pragma unroll 1
+    for (int m = 0; m < MT; ++m) {
+      const int p = (blockIdx.x * PASS_WARPS + warp) * MT + m;
+      if (p < d.npt) xupdate_tile<NT, FNP == 0 ? 1 : FNP, false>(d, b, p, lane);
+    }
+  }
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
     pt[m] = (blockIdx.x * PASS_WARPS + warp) * MT + m;
     inr[m] = pt[m] < d.npt;
     if (!inr[m]) pt[m] = d.npt - 1;        // clamp: loads stay in range, stores are suppressed
-    bool live = false;
-    if (FUSED) {
-      // x-update of both planes of this tile right here: x0 never makes a round trip
-      if (inr[m]) {
-        if (npl == 2) {
-          double xim[NT][2];
-          xupdate_tile<NT>(d, b, pt[m], 1, fresh, lane, xim);
-        }
-        live = xupdate_tile<NT>(d, b, pt[m], 0, fresh, lane, xa[m]);
-      }
-    }
     const int prob = 8 * pt[m] + g;
     dn[m] = inr[m] ? b.done[prob] : 1;
     mu20[m] = b.mu20[prob];
-    if (!FUSED || !live) {
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        const double2 v = *reinterpret_cast<const double2*>(b.x0 + frag_index(pt[m] * npl, NT, j, lane));
-        xa[m][j][0] = v.x;
-        xa[m][j][1] = v.y;
-      }
-    }
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      xa[m][j][0] *= -mu20[m];
-      xa[m][j][1] *= -mu20[m];
+      const double2 v = *reinterpret_cast<const double2*>(b.x0 + frag_index(pt[m] * npl, NT, j, lane));
+      xa[m][j][0] = -mu20[m] * v.x;
+      xa[m][j][1] = -mu20[m] * v.y;
       acc[m][j][0] = acc[m][j][1] = 0.0;
     }
     all_done = all_done && dn[m];
@@ -527,6 +565,13 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
 #pragma unroll
   for (int m = 0; m < MT; ++m) Sp[m] = b.S + state_index(d, pt[m], c_begin * PASS_CHUNK_RT, lane);
   const int ntiles = nchunks * PASS_CHUNK_RT;
+  constexpr int PF_CHUNKS = 2;                                   // L2 prefetch distance of the state, in chunks
+  constexpr unsigned STATE_CHUNK_BYTES = PASS_CHUNK_RT * 64 * sizeof(double);
+  if (active) {
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+      if (lane == m) l2_prefetch_bulk(Sp[m], STATE_CHUNK_BYTES * min(PF_CHUNKS, nchunks));
+  }
   double2 st_nxt[MT];
 #pragma unroll
   for (int m = 0; m < MT; ++m) st_nxt[m] = (active && ntiles > 0) ? ld_stream2(Sp[m]) : make_double2(0.0, 0.0);
@@ -534,7 +579,13 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
   int stage = 0;
   unsigned parity = 0;
   for (int c = 0; c < nchunks; ++c) {
+    if (!active) mbar_wait(full_bar + stage, parity);   // keeps idle warps within the ring too
     if (active) {
+      if (c + PF_CHUNKS < nchunks) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+          if (lane == m) l2_prefetch_bulk(Sp[m] + PF_CHUNKS * PASS_CHUNK_RT * 64, STATE_CHUNK_BYTES);
+      }
       mbar_wait(full_bar + stage, parity);
       const double* Pc = Pst + stage * CHUNK_D + lane * 2;
 #pragma unroll
@@ -786,38 +837,39 @@ static int check_dims(const admm_spm_dims* d, const char* who) {
 
 static int ew_grid(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 16)); }
 
-template <int NT, int MT, int MODE, bool FUSED>
-static int launch_pass_k(const admm_spm_dims* d, const admm_spm_buffers* b, int fresh, cudaStream_t s) {
+template <int NT, int MT, int MODE, int FNP>
+static int launch_pass_k(const admm_spm_dims* d, const admm_spm_buffers* b, cudaStream_t s) {
   dim3 grid(ceil_div(d->npt, PASS_WARPS * MT), d->nsplit);
   const size_t smem = (size_t)PASS_STAGES * PASS_CHUNK_RT * 2 * NT * 64 * sizeof(double) + 2 * PASS_STAGES * sizeof(uint64_t) +
                       PASS_STAGES * sizeof(unsigned) + 16;
-  auto k = spm_pass_kernel<NT, MT, MODE, FUSED>;
+  auto k = spm_pass_kernel<NT, MT, MODE, FNP>;
   static bool configured = false;     // per instantiation
   if (!configured) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
-  k<<<grid, PASS_WARPS * 32, smem, s>>>(*d, *b, fresh);
-  return check_launch(FUSED ? "admm_spm_step" : "admm_spm_pass");
+  k<<<grid, PASS_WARPS * 32, smem, s>>>(*d, *b);
+  return check_launch(FNP ? "admm_spm_step" : "admm_spm_pass");
 }
 
 template <int NT, int MT>
-static int launch_pass_mode(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, bool fused, int fresh,
-                            cudaStream_t s) {
-  if (fused) return launch_pass_k<NT, MT, PASS_STEP, true>(d, b, fresh, s);
-  if (mode == PASS_STEP) return launch_pass_k<NT, MT, PASS_STEP, false>(d, b, 0, s);
-  return launch_pass_k<NT, MT, PASS_VINIT, false>(d, b, 0, s);
+static int launch_pass_mode(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, bool fused, cudaStream_t s) {
+  if (fused) {
+    return d->nplanes == 2 ? launch_pass_k<NT, MT, PASS_STEP, 2>(d, b, s) : launch_pass_k<NT, MT, PASS_STEP, 1>(d, b, s);
+  }
+  if (mode == PASS_STEP) return launch_pass_k<NT, MT, PASS_STEP, 0>(d, b, s);
+  return launch_pass_k<NT, MT, PASS_VINIT, 0>(d, b, s);
 }
 
-static int launch_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, bool fused, int fresh, cudaStream_t s) {
+static int launch_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, bool fused, cudaStream_t s) {
   switch (d->Lp / 8) {
     case 2:
-      return d->mt == 2 ? launch_pass_mode<2, 2>(d, b, mode, fused, fresh, s) : launch_pass_mode<2, 1>(d, b, mode, fused, fresh, s);
+      return d->mt == 2 ? launch_pass_mode<2, 2>(d, b, mode, fused, s) : launch_pass_mode<2, 1>(d, b, mode, fused, s);
     case 5:
-      return d->mt == 2 ? launch_pass_mode<5, 2>(d, b, mode, fused, fresh, s) : launch_pass_mode<5, 1>(d, b, mode, fused, fresh, s);
+      return d->mt == 2 ? launch_pass_mode<5, 2>(d, b, mode, fused, s) : launch_pass_mode<5, 1>(d, b, mode, fused, s);
     default:
-      return launch_pass_mode<8, 1>(d, b, mode, fused, fresh, s);
+      return launch_pass_mode<8, 1>(d, b, mode, fused, s);
   }
 }
 
@@ -831,6 +883,12 @@ int admm_spm_prepare_P(const admm_spm_dims* d, const double* P, int ldP, double*
   if (int rc = check_dims(d, "admm_spm_prepare_P")) return rc;
   prepare_P_kernel<<<ew_grid((long long)d->nrt * 2 * d->Lp * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, P, ldP, Pf);
   return check_launch("admm_spm_prepare_P");
+}
+
+int admm_spm_pack_operator(const admm_spm_dims* d, const double* canon, double* Bf, admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_pack_operator")) return rc;
+  pack_operator_kernel<<<ceil_div(d->Lp * d->Lp, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d->Lp, canon, Bf);
+  return check_launch("admm_spm_pack_operator");
 }
 
 int admm_spm_pack_L(const admm_spm_dims* d, const void* canon, int src_is_complex, double* frag, admm_stream_t stream) {
@@ -875,15 +933,36 @@ int admm_spm_factor(const admm_spm_dims* d, int nslots, const int* slots, const 
   return check_launch("admm_spm_factor");
 }
 
-int admm_spm_xupdate(const admm_spm_dims* d, const admm_spm_buffers* b, int fresh, admm_stream_t stream) {
+int admm_spm_refresh_y(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_refresh_y")) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = ceil_div(d->npt * d->nplanes, 4);
+  switch (d->Lp / 8) {
+    case 2: spm_refresh_y_kernel<2><<<grid, 128, 0, s>>>(*d, *b); break;
+    case 5: spm_refresh_y_kernel<5><<<grid, 128, 0, s>>>(*d, *b); break;
+    default: spm_refresh_y_kernel<8><<<grid, 128, 0, s>>>(*d, *b); break;
+  }
+  return check_launch("admm_spm_refresh_y");
+}
+
+int admm_spm_xupdate(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_xupdate")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int nct = d->npt * d->nplanes;
-  const int grid = ceil_div(nct, 4);
+  const int grid = ceil_div(d->npt, 4);
+  const bool two = d->nplanes == 2;
   switch (d->Lp / 8) {
-    case 2: spm_xupdate_kernel<2><<<grid, 128, 0, s>>>(*d, *b, fresh); break;
-    case 5: spm_xupdate_kernel<5><<<grid, 128, 0, s>>>(*d, *b, fresh); break;
-    default: spm_xupdate_kernel<8><<<grid, 128, 0, s>>>(*d, *b, fresh); break;
+    case 2:
+      if (two) spm_xupdate_kernel<2, 2><<<grid, 128, 0, s>>>(*d, *b);
+      else spm_xupdate_kernel<2, 1><<<grid, 128, 0, s>>>(*d, *b);
+      break;
+    case 5:
+      if (two) spm_xupdate_kernel<5, 2><<<grid, 128, 0, s>>>(*d, *b);
+      else spm_xupdate_kernel<5, 1><<<grid, 128, 0, s>>>(*d, *b);
+      break;
+    default:
+      if (two) spm_xupdate_kernel<8, 2><<<grid, 128, 0, s>>>(*d, *b);
+      else spm_xupdate_kernel<8, 1><<<grid, 128, 0, s>>>(*d, *b);
+      break;
   }
   return check_launch("admm_spm_xupdate");
 }
@@ -891,13 +970,13 @@ int admm_spm_xupdate(const admm_spm_dims* d, const admm_spm_buffers* b, int fres
 int admm_spm_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_pass")) return rc;
   ADMM_REQUIRE(mode == PASS_STEP || mode == PASS_VINIT, ADMM_EINVAL, "admm_spm_pass: mode must be 0 (step) or 1 (V from state)");
-  return launch_pass(d, b, mode, false, 0, static_cast<cudaStream_t>(stream));
+  return launch_pass(d, b, mode, false, static_cast<cudaStream_t>(stream));
 }
 
-int admm_spm_step(const admm_spm_dims* d, const admm_spm_buffers* b, int fresh, admm_stream_t stream) {
+int admm_spm_step(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_step")) return rc;
   ADMM_REQUIRE(d->nsplit == 1, ADMM_EINVAL, "admm_spm_step: the fused x-update + pass needs nsplit == 1 (got %d)", d->nsplit);
-  return launch_pass(d, b, PASS_STEP, true, fresh, static_cast<cudaStream_t>(stream));
+  return launch_pass(d, b, PASS_STEP, true, static_cast<cudaStream_t>(stream));
 }
 
 int admm_spm_reduce(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream_t stream) {

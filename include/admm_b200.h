@@ -121,6 +121,12 @@ typedef struct admm_spm_dims {
 int admm_spm_prepare_P(const admm_spm_dims* d, const double* P, int ldP, double* Pf,
                        admm_stream_t stream);
 
+/* canonical Lp x Lp row-major operator (zero padded) -> fragment-major
+ * Bf[jk][jn][lane][e] = B[8jk+2t+e][8jn+g]: the layout in which the x-update GEMMs read P^T P and
+ * the cached inverses (one coalesced 16-byte load per lane and k-step). */
+int admm_spm_pack_operator(const admm_spm_dims* d, const double* canon, double* Bf,
+                           admm_stream_t stream);
+
 /* canonical (rows x nb) complex128 or float64 (batch index fastest) <-> fragment layout.
  * `src_is_complex`: canonical array is interleaved complex.  For nplanes == 1 only real parts
  * move.  pack zero-fills padding rows/columns. */
@@ -143,7 +149,8 @@ int admm_spm_unpack_state(const admm_spm_dims* d, const double* S, const double*
                           admm_stream_t stream);
 
 /* Factor cache entry for `nslots` (mu10, mu20) pairs: G = G0 + mu10 I + mu20 PtP; Ginv = G^-1
- * (Lp x Lp, zero padded), w = Ginv C^T (Lp), sigma = C w.  G0 = alpha A^H A (L x L, ld Lp).
+ * (Lp x Lp, zero padded, stored fragment-major like admm_spm_pack_operator), w = Ginv C^T (Lp),
+ * sigma = C w.  PtP is canonical (Lp x Lp row-major).  G0 = alpha A^H A (L x L, ld Lp).
  * Replaces `_get_B` and the per-iteration `B @ Ch`, `inv(C @ xi2)` of
  * `ConstrainedLeastSquares.solve` (objectivefunc.py:89-96,148-153).  slots[i] is the cache row
  * to fill for the pair (mu10s[i], mu20s[i]). */
@@ -155,9 +162,9 @@ int admm_spm_factor(const admm_spm_dims* d, int nslots, const int* slots, const 
 typedef struct admm_spm_buffers {
   /* shared operators */
   const double* Pf;       /* [nrt][2][Lp/8][32][2] fragment-major P (admm_spm_prepare_P)        */
-  const double* PtP;      /* Lp x Lp                                                           */
+  const double* PtPf;     /* P^T P, Lp x Lp, fragment-major (admm_spm_pack_operator)            */
   const double* Cvec;     /* Lp                                                                */
-  const double* Ginv_cache; /* nslot x Lp x Lp                                                 */
+  const double* Ginv_cache; /* nslot x (Lp x Lp fragment-major)                                */
   const double* w_cache;    /* nslot x Lp                                                      */
   const double* sigma_cache;/* nslot                                                           */
   /* per problem (length 8*npt) */
@@ -174,14 +181,14 @@ typedef struct admm_spm_buffers {
   double* x0;
   double* x1;
   double* h10;
+  double* y0;             /* P^T P x0 (Gram-form norms of pair (2,0); maintained by the x-update) */
   double* V;              /* [nsplit][ncolumn tiles][Lp/8][32][2]  P^T(h20 + mu20 x2) partials;
                              imaginary-plane tiles: z = P^T Im(h20) in split 0 (owned by xupdate)    */
   double* aim;            /* fragment layout; imaginary-plane tiles accumulate sum_k mu20_k Im(x0_k) */
   /* implicit (h20, x2) state */
   double* S;              /* [npt][nrt][32][2]                                                 */
   /* norms */
-  double* normsA;         /* [8*npt*nplanes][8] from xupdate; slot 7 = |P x0|^2 of the column,
-                             read back on the next iteration as |P x0_old|^2                   */
+  double* normsA;         /* [8*npt*nplanes][8] from xupdate; slot 7 = |P x0|^2 of the column   */
   double* normsB;         /* [nsplit][8*npt*nplanes][2] from pass (real-plane columns only):
                              |P Re(x0) - x2|^2, |x2|^2                                         */
   double* gsum;           /* [16] batch-wide sums (reduce), only batch_wide                    */
@@ -201,10 +208,12 @@ typedef struct admm_spm_buffers {
 /* x-update (term 0, `ConstrainedLeastSquares.solve`, objectivefunc.py:138-157, with
  * `_hk`/`_mu_k`, optimizer.py:175-230), L1 z-update (objectivefunc.py:174-195) and dual ascent of
  * pair (1,0) (optimizer.py:334-341); norms of pair (1,0) and the Gram-form norms of pair (2,0)
- * (|P v|^2 = v^T (P^T P) v).  fresh != 0: first iteration after the state was (re)loaded --
- * |P x0_old|^2 is recomputed instead of being taken from normsA[.][7]. */
-int admm_spm_xupdate(const admm_spm_dims* d, const admm_spm_buffers* b, int fresh,
-                     admm_stream_t stream);
+ * (|P v|^2 = v^T (P^T P) v, with y0 = P^T P x0 carried from iteration to iteration: call
+ * admm_spm_refresh_y once after x0 was loaded from outside). */
+int admm_spm_xupdate(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream_t stream);
+
+/* y0 = P^T P x0 for the current x0 (after set_state / reset). */
+int admm_spm_refresh_y(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream_t stream);
 
 /* One streaming sweep over the implicit (Re h20, x2) state: s' = Re h20 - mu20 P Re(x0) (FP64
  * tensor cores; the accumulator starts at Re h20), which encodes the non-negative z-update
@@ -219,8 +228,7 @@ int admm_spm_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode,
 /* admm_spm_xupdate + admm_spm_pass(mode 0) in ONE kernel: every warp first does the x-update of
  * its own problem tiles (both planes) and then streams their state, so x0 goes from the
  * x-update to the tensor-core operand registers without a round trip.  Needs nsplit == 1. */
-int admm_spm_step(const admm_spm_dims* d, const admm_spm_buffers* b, int fresh,
-                  admm_stream_t stream);
+int admm_spm_step(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream_t stream);
 
 /* Batch-wide norms: deterministic two-stage sum over all problems into gsum[16].  The caller
  * all-reduces gsum across ranks (NCCL) before admm_spm_decide when the batch is sharded. */

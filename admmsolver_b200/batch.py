@@ -176,7 +176,8 @@ class SharedSpM:
         self.V = z(nsplit * fl)
         self.aim = z(fl)                  # sum_k mu20_k Im(x0_k)  (imaginary-plane tiles only)
         self._him_base = None             # Im(h20) at the time of set_state (None == 0)
-        self.S = z(npt * nrt * 64)
+        gt = 4 * mt                       # problem tiles per pass CTA; S is padded to whole CTAs
+        self.S = z(-(-npt // gt) * gt * nrt * 64)
         self.normsA = z(nct * 8 * 8)
         self.normsB = z(nsplit * nct * 8 * 2)
         self.gsum = z(16)

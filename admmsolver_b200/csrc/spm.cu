@@ -96,16 +96,24 @@ __global__ void unpack_L_kernel(admm_spm_dims d, const double* __restrict__ frag
   }
 }
 
-// implicit (h20, x2) state: ONE real plane S[pt][rt][lane][2]  (the imaginary part of h20 never
-// leaves L-space: see xupdate)
-__device__ __forceinline__ size_t state_index(const admm_spm_dims& d, int pt, int rt, int lane) {
-  return (((size_t)pt * d.nrt + rt) * 32 + lane) * 2;
+// implicit (h20, x2) state: ONE real plane (the imaginary part of h20 never leaves L-space: see
+// xupdate), stored chunk-major per CTA tile group so that the 4-row-tile chunk a pass CTA needs is
+// ONE contiguous block (one TMA bulk copy):
+//   S[grp][chunk][tig][r4][lane][2],  grp = pt / GT, tig = pt % GT, GT = 4 * mt tiles per CTA,
+//   chunk = rt / 4, r4 = rt % 4.
+__host__ __device__ __forceinline__ size_t state_index(const admm_spm_dims& d, int pt, int rt, int lane) {
+  const int GT = 4 * d.mt;
+  const int grp = pt / GT, tig = pt - grp * GT;
+  const int chunk = rt >> 2, r4 = rt & 3;
+  return ((((size_t)grp * (d.nrt >> 2) + chunk) * GT + tig) * 4 + r4) * 64 + lane * 2;
 }
 
 __global__ void pack_state_kernel(admm_spm_dims d, const double* __restrict__ h20, const double* __restrict__ x2,
                                   int src_cplx, const double* __restrict__ mu20, double* __restrict__ S,
                                   int* __restrict__ flag) {
-  const long long total = (long long)d.npt * d.nrt * 64;
+  const int GT = 4 * d.mt;
+  const int npt_pad = (d.npt + GT - 1) / GT * GT;
+  const long long total = (long long)npt_pad * d.nrt * 64;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int e = int(idx & 1), lane = int((idx >> 1) & 31);
@@ -124,7 +132,7 @@ __global__ void pack_state_kernel(admm_spm_dims d, const double* __restrict__ h2
       if (xre < 0.0 || xim != 0.0 || hre < 0.0 || (hre != 0.0 && xre != 0.0)) flag[0] = 1;
       if (d.nplanes == 1 && him != 0.0) flag[0] = 1;
     }
-    S[idx] = v;
+    S[state_index(d, pt, rt, lane) + e] = v;
   }
 }
 
@@ -472,22 +480,33 @@ __global__ void __launch_bounds__(128) spm_refresh_y_kernel(admm_spm_dims d, adm
 // pass: the streaming sweep with both skinny GEMMs on the FP64 tensor cores
 // ---------------------------------------------------------------------------------------------
 constexpr int PASS_WARPS = 4;     // warps per CTA; each warp owns MT tiles of 8 problems
-constexpr int PASS_STAGES = 3;    // TMA ring depth for P chunks
-constexpr int PASS_CHUNK_RT = 4;  // 8-row tiles per P chunk (32 rows)
+constexpr int PASS_STAGES = 2;    // TMA ring depth (one stage = a P chunk + the CTA's state chunk)
+constexpr int PASS_CHUNK_RT = 4;  // 8-row tiles per chunk (32 sampling points)
 
 enum { PASS_STEP = 0, PASS_VINIT = 1 };
 
 // sign-bit helpers on the integer pipe (the FP64 pipe is shared with DMMA: keep it for the MMAs)
 __device__ __forceinline__ bool is_neg(double v) { return __double2hiint(v) < 0; }
 
+template <int NT, int MT>
+struct PassSmem {
+  static constexpr int TILE_D = 2 * NT * 64;                          // doubles of Pf per 8-row tile
+  static constexpr int CHUNK_D = PASS_CHUNK_RT * TILE_D;              // P doubles per chunk
+  static constexpr int WARP_STATE_D = MT * PASS_CHUNK_RT * 64;        // state doubles per warp and chunk
+  static constexpr int STATE_D = PASS_WARPS * WARP_STATE_D;           // state doubles per CTA and chunk
+  static constexpr int STAGE_D = CHUNK_D + STATE_D;
+  static constexpr size_t BYTES = (size_t)PASS_STAGES * STAGE_D * sizeof(double) + 2 * PASS_STAGES * sizeof(uint64_t) +
+                                  PASS_STAGES * sizeof(unsigned) + 16;
+};
+
 template <int NT, int MT, int MODE, int FNP>   // FNP: 0 = pass only, 1/2 = fused x-update of 1/2 planes
 __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
     spm_pass_kernel(admm_spm_dims d, admm_spm_buffers b) {
-  constexpr int TILE_D = 2 * NT * 64;                   // doubles of Pf per 8-row tile
-  constexpr int CHUNK_D = PASS_CHUNK_RT * TILE_D;       // doubles per chunk
-  constexpr unsigned CHUNK_BYTES = CHUNK_D * sizeof(double);
-  extern __shared__ __align__(128) double Pst[];        // [PASS_STAGES][CHUNK_D], then barriers
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(Pst + PASS_STAGES * CHUNK_D);
+  using SM = PassSmem<NT, MT>;
+  constexpr int TILE_D = SM::TILE_D, CHUNK_D = SM::CHUNK_D, STATE_D = SM::STATE_D, STAGE_D = SM::STAGE_D;
+  constexpr unsigned CHUNK_BYTES = CHUNK_D * sizeof(double), STATE_BYTES = STATE_D * sizeof(double);
+  extern __shared__ __align__(128) double ring[];       // [PASS_STAGES][P chunk | state chunk], then barriers
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + PASS_STAGES * STAGE_D);
   uint64_t* empty_bar = full_bar + PASS_STAGES;
   unsigned* ticket = reinterpret_cast<unsigned*>(empty_bar + PASS_STAGES);
 
@@ -499,8 +518,15 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
   const int nchunks = max(0, c_end - c_begin);
   const int npl = d.nplanes;
   const double* Pf_src = b.Pf + (size_t)c_begin * CHUNK_D;
+  // the CTA's state chunks are contiguous blocks of S (state_index): [grp = blockIdx.x][chunk][...]
+  double* S_cta = b.S + ((size_t)blockIdx.x * nchunks_total + c_begin) * STATE_D;
 
-  // ---- barrier ring + first P chunks in flight before anything else
+  // ---- barrier ring; the first chunks are in flight before anything else happens
+  auto fill = [&](int stage, int c) {
+    mbar_expect_tx(full_bar + stage, CHUNK_BYTES + STATE_BYTES);
+    tma_bulk_g2s(ring + stage * STAGE_D, Pf_src + (size_t)c * CHUNK_D, CHUNK_BYTES, full_bar + stage);
+    tma_bulk_g2s(ring + stage * STAGE_D + CHUNK_D, S_cta + (size_t)c * STATE_D, STATE_BYTES, full_bar + stage);
+  };
   if (tid == 0) {
     for (int s = 0; s < PASS_STAGES; ++s) {
       mbar_init(full_bar + s, 1);
@@ -511,10 +537,7 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
   }
   __syncthreads();
   if (tid == 0) {
-    for (int s = 0; s < PASS_STAGES && s < nchunks; ++s) {
-      mbar_expect_tx(full_bar + s, CHUNK_BYTES);
-      tma_bulk_g2s(Pst + s * CHUNK_D, Pf_src + (size_t)s * CHUNK_D, CHUNK_BYTES, full_bar + s);
-    }
+    for (int s = 0; s < PASS_STAGES && s < nchunks; ++s) fill(s, s);
   }
 
   // ---- this warp's MT problem tiles (real plane only: the imaginary plane lives in L-space)
@@ -525,18 +548,27 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
   double xa[MT][NT][2];      // A fragments of GEMM1': -mu20 * Re(x0)   (k-slot (j,e) of lane (g,t) <-> l = 8j+2t+e)
   double acc[MT][NT][2];     // C fragments of GEMM2': V
   bool all_done = true;
+  const int wpt0 = (blockIdx.x * PASS_WARPS + warp) * MT;
   if (FNP != 0) {
     // x-update of this warp's tiles right here (all planes): x0 reaches the MMA operand registers
-    // through L1, the pass of the other warps hides the latency of this L x L work
+    // through L1/L2; the pass of the other CTAs of the SM hides the latency of this L x L work.
+    // The L-vectors of the tiles are pulled into L2 up front (one bulk prefetch per vector).
+    constexpr int NPL = FNP == 0 ? 1 : FNP;
+    {
+      const double* vec = lane == 0 ? b.b0 : lane == 1 ? b.h10 : lane == 2 ? b.x1 : lane == 3 ? b.V
+                        : lane == 4 ? b.x0 : lane == 5 ? b.y0 : b.aim;
+      const int ntl = min(MT, d.npt - wpt0);
+      if (lane < 7 && ntl > 0)
+        l2_prefetch_bulk(vec + frag_index(wpt0 * NPL, NT, 0, 0), (unsigned)(ntl * NPL * NT * 64 * sizeof(double)));
+    }
 #pragma unroll 1
     for (int m = 0; m < MT; ++m) {
-      const int p = (blockIdx.x * PASS_WARPS + warp) * MT + m;
-      if (p < d.npt) xupdate_tile<NT, FNP == 0 ? 1 : FNP, false>(d, b, p, lane);
+      if (wpt0 + m < d.npt) xupdate_tile<NT, NPL, false>(d, b, wpt0 + m, lane);
     }
   }
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
-    pt[m] = (blockIdx.x * PASS_WARPS + warp) * MT + m;
+    pt[m] = wpt0 + m;
     inr[m] = pt[m] < d.npt;
     if (!inr[m]) pt[m] = d.npt - 1;        // clamp: loads stay in range, stores are suppressed
     const int prob = 8 * pt[m] + g;
@@ -560,47 +592,24 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
     ratio[m] = MODE == PASS_VINIT ? mu20[m] / b.mu20_used[8 * pt[m] + g] : 1.0;
   }
 
-  // state pointers (this lane's two values of the current 8-row tile) + one-tile software prefetch
-  double* Sp[MT];
-#pragma unroll
-  for (int m = 0; m < MT; ++m) Sp[m] = b.S + state_index(d, pt[m], c_begin * PASS_CHUNK_RT, lane);
-  const int ntiles = nchunks * PASS_CHUNK_RT;
-  constexpr int PF_CHUNKS = 2;                                   // L2 prefetch distance of the state, in chunks
-  constexpr unsigned STATE_CHUNK_BYTES = PASS_CHUNK_RT * 64 * sizeof(double);
-  if (active) {
-#pragma unroll
-    for (int m = 0; m < MT; ++m)
-      if (lane == m) l2_prefetch_bulk(Sp[m], STATE_CHUNK_BYTES * min(PF_CHUNKS, nchunks));
-  }
-  double2 st_nxt[MT];
-#pragma unroll
-  for (int m = 0; m < MT; ++m) st_nxt[m] = (active && ntiles > 0) ? ld_stream2(Sp[m]) : make_double2(0.0, 0.0);
+  // this lane's slot inside a state chunk, in shared memory (read) and in global memory (write back)
+  const int st_off = warp * SM::WARP_STATE_D + lane * 2;
+  double* Sg = S_cta + st_off;
 
   int stage = 0;
   unsigned parity = 0;
   for (int c = 0; c < nchunks; ++c) {
-    if (!active) mbar_wait(full_bar + stage, parity);   // keeps idle warps within the ring too
+    mbar_wait(full_bar + stage, parity);      // idle warps wait too: nobody runs ahead of the ring
     if (active) {
-      if (c + PF_CHUNKS < nchunks) {
-#pragma unroll
-        for (int m = 0; m < MT; ++m)
-          if (lane == m) l2_prefetch_bulk(Sp[m] + PF_CHUNKS * PASS_CHUNK_RT * 64, STATE_CHUNK_BYTES);
-      }
-      mbar_wait(full_bar + stage, parity);
-      const double* Pc = Pst + stage * CHUNK_D + lane * 2;
+      const double* Pc = ring + stage * STAGE_D + lane * 2;
+      const double* Sc = ring + stage * STAGE_D + CHUNK_D + st_off;
 #pragma unroll
       for (int r4 = 0; r4 < PASS_CHUNK_RT; ++r4) {
         const double* P1 = Pc + r4 * TILE_D;        // GEMM1' operand: [j][lane][2]
         const double* P2 = P1 + NT * 64;            // GEMM2' operand: [j][lane][2]
         double2 st[MT];
 #pragma unroll
-        for (int m = 0; m < MT; ++m) st[m] = st_nxt[m];
-        {
-          // prefetch the next tile's state (the last tile re-reads itself)
-          const int step = (c * PASS_CHUNK_RT + r4 + 1 < ntiles) ? 64 : 0;
-#pragma unroll
-          for (int m = 0; m < MT; ++m) st_nxt[m] = ld_stream2(Sp[m] + r4 * 64 + step);
-        }
+        for (int m = 0; m < MT; ++m) st[m] = *reinterpret_cast<const double2*>(Sc + (m * PASS_CHUNK_RT + r4) * 64);
 
         double u[MT][2];
         if (MODE == PASS_STEP) {
@@ -645,7 +654,7 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
               u[m][e] = fabs(s_new);
               sn[e] = dn[m] ? (e == 0 ? st[m].x : st[m].y) : s_new;
             }
-            if (inr[m]) st_stream2(Sp[m] + r4 * 64, make_double2(sn[0], sn[1]));
+            st_stream2(Sg + (m * PASS_CHUNK_RT + r4) * 64, make_double2(sn[0], sn[1]));
           }
         } else {
           // V from the current state, no step:  u = Re h20 + mu20 x2  with x2 decoded by mu20_used
@@ -666,9 +675,8 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
           for (int m = 0; m < MT; ++m) dmma(acc[m][j][0], acc[m][j][1], u[m][1], bb.y);
         }
       }
-#pragma unroll
-      for (int m = 0; m < MT; ++m) Sp[m] += PASS_CHUNK_RT * 64;
     }
+    Sg += STATE_D;
 
     // ---- release the stage; the warp that arrives last refills it with chunk c + PASS_STAGES
     __syncwarp();
@@ -677,8 +685,7 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
       const unsigned tk = atomicAdd(ticket + stage, 1u);
       if ((tk & (PASS_WARPS - 1)) == PASS_WARPS - 1 && c + PASS_STAGES < nchunks) {
         mbar_wait(empty_bar + stage, parity);
-        mbar_expect_tx(full_bar + stage, CHUNK_BYTES);
-        tma_bulk_g2s(Pst + stage * CHUNK_D, Pf_src + (size_t)(c + PASS_STAGES) * CHUNK_D, CHUNK_BYTES, full_bar + stage);
+        fill(stage, c + PASS_STAGES);
       }
     }
     if (++stage == PASS_STAGES) {
@@ -840,8 +847,7 @@ static int ew_grid(long long n) { return (int)std::max<long long>(1, std::min<lo
 template <int NT, int MT, int MODE, int FNP>
 static int launch_pass_k(const admm_spm_dims* d, const admm_spm_buffers* b, cudaStream_t s) {
   dim3 grid(ceil_div(d->npt, PASS_WARPS * MT), d->nsplit);
-  const size_t smem = (size_t)PASS_STAGES * PASS_CHUNK_RT * 2 * NT * 64 * sizeof(double) + 2 * PASS_STAGES * sizeof(uint64_t) +
-                      PASS_STAGES * sizeof(unsigned) + 16;
+  const size_t smem = PassSmem<NT, MT>::BYTES;
   auto k = spm_pass_kernel<NT, MT, MODE, FNP>;
   static bool configured = false;     // per instantiation
   if (!configured) {
@@ -908,7 +914,8 @@ int admm_spm_unpack_L(const admm_spm_dims* d, const double* frag, void* canon, i
 int admm_spm_pack_state(const admm_spm_dims* d, const void* h20, const void* x2, int src_is_complex, const double* mu20,
                         double* S, int* flag, admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_pack_state")) return rc;
-  const long long total = (long long)d->npt * d->nrt * 64;
+  const int GT = 4 * d->mt;
+  const long long total = (long long)((d->npt + GT - 1) / GT * GT) * d->nrt * 64;
   pack_state_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, (const double*)h20, (const double*)x2,
                                                                                  src_is_complex, mu20, S, flag);
   return check_launch("admm_spm_pack_state");

@@ -135,7 +135,12 @@ int admm_spm_pack_L(const admm_spm_dims* d, const void* canon, int src_is_comple
 int admm_spm_unpack_L(const admm_spm_dims* d, const double* frag, void* canon, int dst_is_complex,
                       admm_stream_t stream);
 
-/* (h20, x2) canonical (Nw x nb) <-> implicit state S[pt][rt][lane][2]:
+/* (h20, x2) canonical (Nw x nb) <-> implicit state
+ *   S[grp][chunk][tig][r4][lane][2]   (problem tile pt = grp*GT + tig, GT = 4*mt tiles per pass CTA;
+ *                                      8-row tile rt = 4*chunk + r4; lane = 4*g + t holds problem
+ *                                      8*pt+g, sampling points 8*rt+2t, +1),
+ * chunk-major per CTA tile group so that what one pass CTA needs per chunk is one contiguous block
+ * (one TMA bulk copy).  S has ceil(npt/GT)*GT * nrt * 64 doubles.
  *   s = Re(h20) - mu20 * x2   (complementarity: Re(h20) = max(0,s), mu20*x2 = max(0,-s)).
  * Im(h20) is not part of S: it only ever enters the iteration through P^T Im(h20), which the
  * x-update maintains in L-space (z <- z - mu20 P^T P Im(x0)); the caller reconstructs
@@ -186,7 +191,7 @@ typedef struct admm_spm_buffers {
                              imaginary-plane tiles: z = P^T Im(h20) in split 0 (owned by xupdate)    */
   double* aim;            /* fragment layout; imaginary-plane tiles accumulate sum_k mu20_k Im(x0_k) */
   /* implicit (h20, x2) state */
-  double* S;              /* [npt][nrt][32][2]                                                 */
+  double* S;              /* [ceil(npt/GT)][nrt/4][GT][4][32][2], GT = 4*mt (see pack_state)    */
   /* norms */
   double* normsA;         /* [8*npt*nplanes][8] from xupdate; slot 7 = |P x0|^2 of the column   */
   double* normsB;         /* [nsplit][8*npt*nplanes][2] from pass (real-plane columns only):

@@ -59,7 +59,7 @@ class SharedSpM:
 
     def __init__(self, s, P, C_, D, g, lam: float, mu: float = 0.1, alpha: float = 1.0,
                  batch_wide: bool = False, max_mu: float = 1e3, nsplit: Optional[int] = None,
-                 group=None, force_complex: Optional[bool] = None):
+                 group=None, force_complex: Optional[bool] = None, mt: Optional[int] = None):
         dev = _lib.require_cuda()
         s_t = _dev_tensor(s, dev, _F64)
         g_t = _dev_tensor(g, dev)
@@ -74,7 +74,7 @@ class SharedSpM:
         b0 = torch.empty_like(gv)
         sd = (-alpha * s_t).to(gv.dtype)
         call("admm_diag_mul", int(cplx), L, L, nb, ptr(sd), ptr(gv), nb, ptr(b0), nb, stream())
-        self._init_common(G0, b0, P, C_, D, lam, mu, mu, batch_wide, max_mu, nsplit, group, force_complex)
+        self._init_common(G0, b0, P, C_, D, lam, mu, mu, batch_wide, max_mu, nsplit, group, force_complex, mt)
         self._s = s_t
         self._g = gv
         self._alpha = alpha
@@ -82,21 +82,22 @@ class SharedSpM:
     @classmethod
     def from_operators(cls, G0, b0, P, C_, D, lam: float, mu10: float, mu20: float,
                        batch_wide: bool = True, max_mu: float = 1e3, nsplit: Optional[int] = None,
-                       group=None, force_complex: Optional[bool] = None) -> "SharedSpM":
+                       group=None, force_complex: Optional[bool] = None, mt: Optional[int] = None) -> "SharedSpM":
         self = cls.__new__(cls)
         dev = _lib.require_cuda()
         b0_t = _dev_tensor(b0, dev)
         if b0_t.ndim == 1:
             b0_t = b0_t[:, None].contiguous()
         self._init_common(_dev_tensor(G0, dev, _F64), b0_t, P, C_, D, lam, mu10, mu20, batch_wide, max_mu,
-                          nsplit, group, force_complex)
+                          nsplit, group, force_complex, mt)
         self._s = None
         self._g = None
         self._alpha = None
         return self
 
     # ------------------------------------------------------------------ setup
-    def _init_common(self, G0, b0, P, C_, D, lam, mu10, mu20, batch_wide, max_mu, nsplit, group, force_complex):
+    def _init_common(self, G0, b0, P, C_, D, lam, mu10, mu20, batch_wide, max_mu, nsplit, group, force_complex,
+                     mt=None):
         dev = _lib.require_cuda()
         self.device = dev
         self.group = group
@@ -120,7 +121,9 @@ class SharedSpM:
         nchunks = nrt // 4
         NT = Lp // 8
         # problem tiles per warp in the pass kernel; one CTA = 4 warps = 4*mt tiles of 8 problems
-        mt = 2 if (npt >= 8 * 444 and Lp <= 40) else 1
+        if mt is None:
+            mt = 2 if (npt >= 8 * 444 and Lp <= 40) else 1
+        assert mt in (1, 2) and (mt == 1 or Lp <= 40)
         if nsplit is None:
             # fill the 148 SMs x 3 resident CTAs in ONE wave: split the sampling points over
             # several CTAs only when the batch alone cannot (then the x-update is a separate kernel)

@@ -203,3 +203,51 @@ def test_spm_larger_batch_vs_oracle(eng, ir_basis):
         sb = flat.spm_solve(p.s, p.P, p.C, np.array([1.0]), p.g[:, b], p.lam, 120, mu=p.mu)
         assert rel(x0[:, b], sb.x0) < TOL
         assert float(e2.mu20[b]) == sb.mu20
+
+
+@pytest.mark.parametrize("mt,nsplit", [(1, 1), (2, 1), (1, 3), (2, 2)])
+def test_spm_kernel_variants_vs_oracle(eng, ir_basis, mt, nsplit):
+    """Every launch configuration of the pass kernel -- fused x-update + pass (nsplit == 1) with one
+    or two problem tiles per warp, and the split small-batch path -- against the oracle, on a ragged
+    complex batch (37 problems = 5 tiles, the last CTA partly empty), across mu changes, eager
+    launches and CUDA-graph replay giving identical bits."""
+    from oracle import flat
+    batch, problems = eng
+    p = problems.spm_batch(37, ir_basis, Nw=200, seed=21)
+    st = flat.spm_solve(p.s, p.P, p.C, p.D, p.g, p.lam, 230, mu=p.mu, interval_update_mu=20)
+    assert len(set(st.mu_hist)) > 1                      # the run really crosses a mu change
+    outs = []
+    for use_graph in (False, True):
+        e = batch.SharedSpM(p.s, p.P, p.C, p.D, p.g, lam=p.lam, mu=p.mu, batch_wide=True, mt=mt, nsplit=nsplit)
+        assert e.dims.mt == mt and e.dims.nsplit == nsplit
+        e.solve(230, interval_update_mu=20, use_graph=use_graph)
+        assert rel(e.x0(), st.x0) < TOL and rel(e.x1(), st.x1) < TOL and rel(e.x2(), st.x2) < TOL
+        assert rel(e.h10(), st.h10) < 1e-8 and rel(e.h20(), st.h20) < 1e-8
+        assert float(e.mu10[0]) == st.mu10 and float(e.mu20[0]) == st.mu20
+        assert rel(e.primal_residual, st.primal) < 1e-8 and rel(e.dual_residual, st.dual) < 1e-8
+        outs.append((e.x0(), e.x2()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("mt", [1, 2])
+def test_spm_fused_per_problem_mixed_mu_and_early_stop(eng, ir_basis, mt):
+    """Fused kernel in per-problem mode: problems of one tile end up on different (mu10, mu20)
+    (several factor slots per tile) and stop at different iterations (loose rtol); every column
+    must follow its own independent reference instance, iteration count included."""
+    from oracle import flat
+    batch, problems = eng
+    p = problems.spm_batch(19, ir_basis, Nw=120, seed=33)
+    e = batch.SharedSpM(p.s, p.P, p.C, p.D, p.g, lam=p.lam, mu=p.mu, batch_wide=False, mt=mt, nsplit=1)
+    e.solve(600, interval_update_mu=40, rtol=2e-4)
+    x0, x2 = e.x0(), e.x2()
+    iters = e.iters.cpu().numpy()
+    seen_mu, seen_it = set(), set()
+    for b in range(19):
+        sb = flat.spm_solve(p.s, p.P, p.C, np.array([1.0]), p.g[:, b], p.lam, 600, mu=p.mu, interval_update_mu=40,
+                            rtol=2e-4)
+        assert int(iters[b]) == sb.niter_done, (b, int(iters[b]), sb.niter_done)
+        assert float(e.mu10[b]) == sb.mu10 and float(e.mu20[b]) == sb.mu20
+        assert rel(x0[:, b], sb.x0) < TOL and rel(x2[:, b], sb.x2) < TOL
+        seen_mu.add((sb.mu10, sb.mu20))
+        seen_it.add(sb.niter_done)
+    assert len(seen_mu) > 1 and len(seen_it) > 1

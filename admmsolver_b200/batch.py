@@ -457,7 +457,7 @@ class SharedSpM:
         self._fill_bufs(rtol)
         key = (float(rtol), self.bufs.history, self.bufs.hist_cap)     # everything a captured launch bakes in
         if use_graph is None:
-            use_graph = callback is None and self.pass_events is None
+            use_graph = callback is None and self.pass_events is None and self.group is None
         launched = 0
         it = 0
         while it < niter:

@@ -329,11 +329,17 @@ def run_ours(args):
 
         h2d = g_host.numel() * 16
         d2h = out_host.numel() * 16
-        # pass kernel: both skinny GEMMs on the REAL plane only (4 L Nw flop, 16 B per sampling point);
-        # the imaginary half of the complex state is advanced in L-space by the x-update
-        flops_per_unit = 4.0 * L * Nw
-        bytes_per_unit = 16.0 * Nw
-        kernel_name = "spm_pass_kernel<5,%d,0>" % eng.dims.mt
+        # dominant kernel = one ADMM iteration of the batch.  Large batches: the fused step kernel
+        # (x-update + pass); small batches (row-split path): the pass kernel alone.
+        #   pass: both skinny GEMMs on the REAL plane only, 4 L Nw flop, 8 B read + 8 B written per
+        #         sampling point (the imaginary half of the state is advanced in L-space)
+        #   x-update (fused only): per plane Ginv*rhs and PtP*x0 = 2 * 2 L^2 flop; per plane 6 L-vectors read
+        #         and 4 written, plus z and a of the imaginary plane (2 read, 2 written)
+        fused = eng.dims.nsplit == 1
+        npl = eng.dims.nplanes
+        flops_per_unit = 4.0 * L * Nw + (4.0 * L * L * npl if fused else 0.0)
+        bytes_per_unit = 16.0 * Nw + (8.0 * L * (10 * npl + (4 if npl == 2 else 0)) if fused else 0.0)
+        kernel_name = "spm_pass_kernel<%d,%d,0,%d>" % (eng.dims.Lp // 8, eng.dims.mt, npl if fused else 0)
         bound = "tensor"
     else:
         if args.workload == "bp_cfg4":
@@ -399,7 +405,11 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count
-    if is_spm:
+    # SpM: iterations of >= ~1 ms are launched eagerly with CUDA events around the dominant kernel
+    # inside the timed region; shorter ones are replayed from a CUDA graph (events cannot sit inside a
+    # graph) and the kernel is timed in a separate eager pass over the same resident state.
+    in_region_events = is_spm and nb_local >= 65536
+    if in_region_events:
         eng.pass_events = []
     total_ms = timed(step, args.steps)
     launches = _lib.launch_count - launches0
@@ -407,8 +417,16 @@ def run_ours(args):
     units = float(nb_local * world) * niter * args.steps
     value = units / (total_ms * 1e-3)
 
-    # dominant-kernel duration (CUDA events on the launching stream, inside the timed region)
+    # dominant-kernel duration (CUDA events on the launching stream)
+    kernel_timing = None
     if is_spm:
+        if in_region_events:
+            kernel_timing = "CUDA events around every launch inside the timed region"
+        else:
+            eng.pass_events = []
+            step()
+            barrier()
+            kernel_timing = "separate eager pass after the timed region (timed region replays a CUDA graph)"
         durs = [a.elapsed_time(b) for a, b in eng.pass_events]
         eng.pass_events = None
         k_ms = float(np.mean(durs)) if durs else None
@@ -417,6 +435,7 @@ def run_ours(args):
         # the persistent kernel runs all iterations: time = step time / launches that do work
         k_ms = total_ms / args.steps
         units_per_launch = nb_local * niter
+        kernel_timing = "step time (one persistent launch runs all iterations)"
 
     e2e = None
     if not args.no_e2e:
@@ -430,22 +449,37 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of the
+    # same kernel at the same per-launch size (profiles/traffic.json); null when no capture matches
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tj.get(kernel_name, {}).get(str(units_per_launch))
+        if ent:
+            traffic = float(ent["dram_bytes_read"]) + float(ent["dram_bytes_write"])
+    except Exception:
+        pass
+
     roof = None
     if k_ms:
         if bound == "tensor":
             ach = flops_per_unit * units_per_launch / (k_ms * 1e-3) / 1e12
             peak = fp64_sus
             roof = {"bound": "tensor", "kernel": kernel_name, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": None,
+                    "frac": ach / peak, "traffic": traffic,
                     "peak_source": "measured live: cuBLAS DGEMM 8192^3 via torch.matmul, sustained (burst %.1f)" % fp64_burst,
-                    "avg_launch_ms": k_ms,
+                    "avg_launch_ms": k_ms, "kernel_timing": kernel_timing,
+                    "algorithmic_flops_per_launch": flops_per_unit * units_per_launch,
+                    "algorithmic_bytes_per_launch": bytes_per_unit * units_per_launch,
                     "hbm_achieved_gbs": bytes_per_unit * units_per_launch / (k_ms * 1e-3) / 1e9,
                     "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
                     "hbm_frac": bytes_per_unit * units_per_launch / (k_ms * 1e-3) / 1e9 / hbm_peak}
         else:
             ach = bytes_per_unit * units_per_launch / (k_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": kernel_name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src, "avg_launch_ms": k_ms,
+                    "frac": ach / hbm_peak, "traffic": traffic, "peak_source": hbm_src, "avg_launch_ms": k_ms,
+                    "kernel_timing": kernel_timing,
+                    "algorithmic_bytes_per_launch": bytes_per_unit * units_per_launch,
                     "fp64_tflops": flops_per_unit * units_per_launch / (k_ms * 1e-3) / 1e12,
                     "fp64_peak_tflops": fp64_sus}
 

@@ -54,7 +54,7 @@ class SpmBuffers(C.Structure):
 class BpBuffers(C.Structure):
     _fields_ = [
         ("nb", C.c_int), ("M", C.c_int), ("N", C.c_int), ("woodbury", C.c_int), ("nk", C.c_int),
-        ("A", _P), ("aty", _P), ("gram", _P), ("Kinv", _P), ("x0", _P), ("x1", _P), ("h", _P), ("mu", _P),
+        ("A", _P), ("At", _P), ("aty", _P), ("gram", _P), ("Kinv", _P), ("x0", _P), ("x1", _P), ("h", _P), ("mu", _P),
         ("need_factor", _P), ("done", _P), ("iters", _P), ("last_res", _P), ("history", _P),
         ("hist_cap", C.c_int),
         ("alpha", C.c_double), ("lam", C.c_double), ("rtol", C.c_double), ("max_mu", C.c_double),
@@ -92,6 +92,7 @@ _SIGS = {
     "admm_spm_reduce": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _P], _I),
     "admm_spm_decide": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
     "admm_bp_setup": ([C.POINTER(BpBuffers), _P, _P, _P, _P], _I),
+    "admm_bp_tile_A": ([C.POINTER(BpBuffers), _P, _P], _I),
     "admm_bp_factor": ([C.POINTER(BpBuffers), _P, _P], _I),
     "admm_bp_iterate": ([C.POINTER(BpBuffers), _I, _P], _I),
 }

@@ -537,7 +537,7 @@ class BatchedBasisPursuit:
     stopping test (one ``SimpleOptimizer`` instance per problem in the reference)."""
 
     def __init__(self, A, y, alpha: float = 1.0, lam: float = 0.1, mu: float = 1.0, max_mu: float = 1e3,
-                 keep_history: bool = False):
+                 keep_history: bool = False, tiled: bool = True):
         dev = _lib.require_cuda()
         self.device = dev
         A_t = _dev_tensor(A, dev, _F64)
@@ -564,13 +564,18 @@ class BatchedBasisPursuit:
         self.history = None
         self.primal_residual = [[] for _ in range(nb)] if keep_history else None
         self.dual_residual = [[] for _ in range(nb)] if keep_history else None
+        # tile-major copy of A for the single-sweep kernel (Woodbury path, M <= 256)
+        self.At = z(nb, -(-N // 32), M, 32) if (self.woodbury and M <= 256 and tiled) else None
         self.bufs = BpBuffers()
         self._fill(1e-12, 100)
         call("admm_bp_setup", C.byref(self.bufs), ptr(self.y), ptr(self.aty), ptr(self.gram), stream())
+        if self.At is not None:
+            call("admm_bp_tile_A", C.byref(self.bufs), ptr(self.At), stream())
 
     def _fill(self, rtol, interval, fact_incr=2.0, th_change=10.0):
         b = self.bufs
         b.nb, b.M, b.N, b.woodbury, b.nk = self.nb, self.M, self.N, int(self.woodbury), self.nk
+        b.At = self.At.data_ptr() if self.At is not None else None
         for name, t in (("A", self.A), ("aty", self.aty), ("gram", self.gram), ("Kinv", self.Kinv), ("x0", self._x0),
                         ("x1", self._x1), ("h", self._h), ("mu", self.mu), ("need_factor", self.need_factor),
                         ("done", self.done), ("iters", self.iters), ("last_res", self.last_res)):

@@ -5,6 +5,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace admm {
 
@@ -250,6 +251,260 @@ __global__ void __launch_bounds__(BP_THREADS) bp_iterate_kernel(admm_bp_buffers 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fused single-sweep iteration (Woodbury path): A is streamed ONCE per iteration
+// ---------------------------------------------------------------------------------------------
+// One iteration needs  t = A r  (by rows) and  A^T s  (by columns).  The z-update, the dual ascent
+// and the next right-hand side r' = alpha A^T y + h' + mu x1' are elementwise in the column index,
+// so while a column tile of A is on chip for A^T s, the same tile immediately contributes
+// A[:, tile] r'[tile] to the NEXT iteration's t: one pass over A per iteration instead of two
+// (8 M N + 8 M^2 bytes per problem-iteration instead of 16 M N + 8 M^2).
+//
+// Column tiles (M x 32 doubles) arrive in a 2-stage shared-memory ring by per-row TMA bulk copies
+// (one 256-byte copy per row, issued by M threads, completion on an mbarrier); the stream is
+// continuous across iterations.  Warp w owns rows [16 w, 16 w + 16): it computes s for exactly those
+// rows (K^-1 t, rows of K^-1 from L2/HBM), keeps its 16 x 32 patch of the tile in registers
+// (one column per lane), and accumulates both products from it.
+// A (row-major M x N per problem) -> At[prob][tile][m][32], zero padded: every 32-column tile is one
+// contiguous block (one TMA bulk copy, full DRAM pages) instead of M strided 256-byte row segments.
+__global__ void __launch_bounds__(256) bp_tile_A_kernel(admm_bp_buffers b, double* __restrict__ At) {
+  const int prob = blockIdx.y;
+  const int T = (b.N + 31) / 32;
+  const double* A = b.A + (size_t)prob * b.M * b.N;
+  double* dst = At + (size_t)prob * T * b.M * 32;
+  const long long total = (long long)T * b.M * 32;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = int(idx & 31);
+    const long long q = idx >> 5;
+    const int m = int(q % b.M), k = int(q / b.M);
+    const int n = 32 * k + c;
+    dst[idx] = n < b.N ? A[(size_t)m * b.N + n] : 0.0;
+  }
+}
+
+constexpr int BPF_TN = 32;       // columns per tile (one per lane)
+constexpr int BPF_RW = 16;       // rows per warp
+constexpr int BPF_STAGES = 2;
+
+template <int NW>
+struct BpfSmem {
+  static constexpr int ROWS = NW * BPF_RW;
+  static constexpr int STAGE_D = ROWS * BPF_TN;
+  static size_t bytes(int N) {
+    const int Np = (N + 1) & ~1;
+    return (size_t)(BPF_STAGES * STAGE_D + 5 * Np + ROWS + NW * BPF_TN + BPF_TN + 5 * 32) * sizeof(double) +
+           BPF_STAGES * sizeof(uint64_t) + 16;
+  }
+};
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) bp_fused_kernel(admm_bp_buffers b, int iter_end) {
+  extern __shared__ __align__(128) double sm[];
+  constexpr int ROWS = BpfSmem<NW>::ROWS, STAGE_D = BpfSmem<NW>::STAGE_D, NT_ = NW * 32;
+  const int prob = blockIdx.x;
+  if (b.done[prob] || b.need_factor[prob]) return;
+  int it = b.iters[prob];
+  if (it >= iter_end) return;
+  const int M = b.M, N = b.N, Np = (N + 1) & ~1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* stage = sm;                              // [STAGES][ROWS][TN]
+  double* aty = stage + BPF_STAGES * STAGE_D;      // N
+  double* x0 = aty + Np;                           // N
+  double* x1 = x0 + Np;                            // N
+  double* h = x1 + Np;                             // N
+  double* r = h + Np;                              // N   current right-hand side
+  double* tv = r + Np;                             // ROWS   t = A r
+  double* part = tv + ROWS;                        // NW x TN  per-warp partial column dots
+  double* rn = part + NW * BPF_TN;                 // TN   r' of the current tile
+  double* scratch = rn + BPF_TN;                   // 5*32
+  uint64_t* full = reinterpret_cast<uint64_t*>(scratch + 5 * 32);
+  const double* Kinv = b.Kinv + (size_t)prob * M * M;
+  const int T = (N + BPF_TN - 1) / BPF_TN;          // tiles per sweep
+  const double* At = b.At + (size_t)prob * T * M * BPF_TN;     // tile-major copy of A (bp_tile_A_kernel)
+  const unsigned TILE_BYTES = (unsigned)(M * BPF_TN * sizeof(double));
+
+  // rows >= M and the columns of a ragged last tile are never written by a copy: keep them finite
+  for (int i = tid; i < BPF_STAGES * STAGE_D; i += NT_) stage[i] = 0.0;
+  for (int i = tid; i < ROWS; i += NT_) tv[i] = 0.0;
+  for (int n = tid; n < N; n += NT_) {
+    aty[n] = b.aty[(size_t)prob * N + n];
+    x0[n] = b.x0[(size_t)prob * N + n];
+    x1[n] = b.x1[(size_t)prob * N + n];
+    h[n] = b.h[(size_t)prob * N + n];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < BPF_STAGES; ++s) mbar_init(full + s, 1);
+    fence_barrier_init();
+  }
+  double mu = b.mu[prob];
+  __syncthreads();
+  for (int n = tid; n < N; n += NT_) r[n] = aty[n] + h[n] + mu * x1[n];
+
+  // tile `gt` of the endless stream (sweep after sweep) -> stage gt % STAGES
+  auto issue = [&](int gt) {
+    if (tid == 0) {
+      const int k = gt % T, sidx = gt % BPF_STAGES;
+      fence_proxy_async();
+      mbar_expect_tx(full + sidx, TILE_BYTES);
+      tma_bulk_g2s(stage + sidx * STAGE_D, At + (size_t)k * M * BPF_TN, TILE_BYTES, full + sidx);
+    }
+  };
+  __syncthreads();
+  int gt = 0;                 // next tile to consume; tiles gt .. gt+STAGES-1 are in flight
+  for (int s = 0; s < BPF_STAGES; ++s) issue(s);
+
+  int done = 0, need = 0;
+  double primal = 0.0, dual = 0.0;
+  bool first = true;          // first sweep of this launch: only t = A r
+  while (true) {
+    // ---- s = K^-1 t for this warp's rows (every lane ends up with all 16 values)
+    double sreg[BPF_RW];
+#pragma unroll
+    for (int i = 0; i < BPF_RW; ++i) sreg[i] = 0.0;
+    if (!first) {
+#pragma unroll
+      for (int i = 0; i < BPF_RW; ++i) {
+        const int m = warp * BPF_RW + i;
+        double a0 = 0.0;
+        if (m < M) {
+          const double* row = Kinv + (size_t)m * M;
+          for (int j = lane; j < M; j += 32) a0 += row[j] * tv[j];
+        }
+        sreg[i] = a0;
+      }
+#pragma unroll
+      for (int i = 0; i < BPF_RW; ++i) sreg[i] = warp_sum(sreg[i]);
+      __syncthreads();        // everyone has read tv before it is overwritten below
+    }
+    double acc[BPF_RW];
+#pragma unroll
+    for (int i = 0; i < BPF_RW; ++i) acc[i] = 0.0;
+    double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const double thr = 0.5 * b.lam / mu;
+    // K^-1 is needed again right after this sweep: pull it into L2 meanwhile (16 KB per bulk prefetch)
+    {
+      const size_t kbytes = (size_t)M * M * sizeof(double);
+      const size_t off = (size_t)tid * 16384;
+      if (off < kbytes && (reinterpret_cast<uintptr_t>(Kinv) & 15) == 0) {
+        const unsigned nbytes = (unsigned)min((size_t)16384, (kbytes - off) & ~(size_t)15);
+        if (nbytes) l2_prefetch_bulk(reinterpret_cast<const char*>(Kinv) + off, nbytes);
+      }
+    }
+
+    for (int k = 0; k < T; ++k, ++gt) {
+      const int sidx = gt % BPF_STAGES;
+      mbar_wait(full + sidx, (unsigned)((gt / BPF_STAGES) & 1));
+      const double* tile = stage + sidx * STAGE_D + (warp * BPF_RW) * BPF_TN + lane;
+      double patch[BPF_RW];
+#pragma unroll
+      for (int i = 0; i < BPF_RW; ++i) patch[i] = tile[i * BPF_TN];
+      if (!first) {
+        double pc = 0.0;
+#pragma unroll
+        for (int i = 0; i < BPF_RW; ++i) pc += patch[i] * sreg[i];
+        part[warp * BPF_TN + lane] = pc;
+      }
+      __syncthreads();                     // stage consumed by everyone; partial dots visible
+      issue(gt + BPF_STAGES);
+      double rnv;
+      if (!first) {
+        if (tid < BPF_TN) {
+          const int n = k * BPF_TN + tid;
+          double rnew = 0.0;
+          if (n < N) {
+            double c = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) c += part[w * BPF_TN + tid];
+            // x-update by the Woodbury identity, then z-update / dual ascent as in bp_iterate_kernel
+            const double xov = x0[n], hv = h[n];
+            const double xv = (r[n] - c) / mu;
+            const double yv = -((hv - mu * xv) / mu);
+            double z = 0.0;
+            if (yv > thr) z = yv - thr;
+            if (yv < -thr) z = yv + thr;
+            const double hn = hv + mu * (z - xv);
+            x0[n] = xv;
+            x1[n] = z;
+            h[n] = hn;
+            rnew = aty[n] + hn + mu * z;
+            r[n] = rnew;
+            v[0] += (xv - z) * (xv - z);
+            v[1] += xv * xv;
+            v[2] += z * z;
+            v[3] += (xv - xov) * (xv - xov);
+            v[4] += xov * xov;
+          }
+          rn[tid] = rnew;
+        }
+        __syncthreads();
+        rnv = rn[lane];
+      } else {
+        const int n = k * BPF_TN + lane;
+        rnv = n < N ? r[n] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < BPF_RW; ++i) acc[i] += patch[i] * rnv;
+    }
+    // ---- t' = A r' : rows are owned by warps, columns were spread over lanes and tiles
+#pragma unroll
+    for (int i = 0; i < BPF_RW; ++i) acc[i] = warp_sum(acc[i]);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < BPF_RW; ++i) tv[warp * BPF_RW + i] = acc[i];
+    }
+    if (first) {
+      first = false;
+      __syncthreads();
+      continue;
+    }
+    block_sum<5>(v, scratch);              // (syncs: tv is visible afterwards)
+    const double p = sqrt(v[0]), nx0 = sqrt(v[1]), nx1 = sqrt(v[2]), nd = sqrt(v[3]), nxo = sqrt(v[4]);
+    primal = p;
+    dual = mu * nd;
+    if (b.history && it < b.hist_cap && tid == 0) {
+      b.history[((size_t)prob * b.hist_cap + it) * 2] = primal;
+      b.history[((size_t)prob * b.hist_cap + it) * 2 + 1] = dual;
+    }
+    const int this_it = it;
+    ++it;
+    const bool conv = (p / fmax(nx0, nx1) < b.rtol) && (dual / fmax(mu * nx0, mu * nxo) < b.rtol);
+    if (conv) {
+      done = 1;
+      break;
+    }
+    if (this_it % b.interval_update_mu == 0) {
+      double m2 = mu;
+      if (primal > b.th_change * dual) m2 *= b.fact_incr;
+      if (dual > b.th_change * primal) m2 /= b.fact_incr;
+      m2 = fmin(m2, b.max_mu);
+      if (m2 != mu) {
+        mu = m2;
+        need = 1;
+        break;
+      }
+    }
+    if (it >= iter_end) break;
+    __syncthreads();
+  }
+  // drain the tiles still in flight before the shared memory goes away
+  for (int g2 = gt; g2 < gt + BPF_STAGES; ++g2) mbar_wait(full + g2 % BPF_STAGES, (unsigned)((g2 / BPF_STAGES) & 1));
+  __syncthreads();
+  for (int n = tid; n < N; n += NT_) {
+    b.x0[(size_t)prob * N + n] = x0[n];
+    b.x1[(size_t)prob * N + n] = x1[n];
+    b.h[(size_t)prob * N + n] = h[n];
+  }
+  if (tid == 0) {
+    b.mu[prob] = mu;
+    b.iters[prob] = it;
+    b.done[prob] = done;
+    b.need_factor[prob] = need;
+    b.last_res[2 * prob] = primal;
+    b.last_res[2 * prob + 1] = dual;
+  }
+}
+
 static int check_bp(const admm_bp_buffers* b, const char* who) {
   ADMM_REQUIRE(b != nullptr, ADMM_EINVAL, "%s: null buffers", who);
   ADMM_REQUIRE(b->nb >= 1 && b->M >= 1 && b->N >= 1, ADMM_EINVAL, "%s: bad dims", who);
@@ -285,6 +540,22 @@ int admm_bp_setup(const admm_bp_buffers* b, const double* y, double* aty, double
   return check_launch("admm_bp_setup");
 }
 
+int admm_bp_tile_A(const admm_bp_buffers* b, double* At, admm_stream_t stream) {
+  if (int rc = check_bp(b, "admm_bp_tile_A")) return rc;
+  ADMM_REQUIRE(At != nullptr, ADMM_EINVAL, "admm_bp_tile_A: null destination");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int T = (b->N + 31) / 32;
+  const long long per = (long long)T * b->M * 32;
+  for (int p0 = 0; p0 < b->nb; p0 += 65535) {
+    admm_bp_buffers bb = *b;
+    const int cnt = std::min(65535, b->nb - p0);
+    bb.A = b->A + (size_t)p0 * b->M * b->N;
+    dim3 g((unsigned)std::max<long long>(1, std::min<long long>((per + 255) / 256, 64)), cnt);
+    bp_tile_A_kernel<<<g, 256, 0, s>>>(bb, At + (size_t)p0 * per);
+  }
+  return check_launch("admm_bp_tile_A");
+}
+
 int admm_bp_factor(const admm_bp_buffers* b, int* info, admm_stream_t stream) {
   if (int rc = check_bp(b, "admm_bp_factor")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -307,6 +578,32 @@ int admm_bp_factor(const admm_bp_buffers* b, int* info, admm_stream_t stream) {
 
 int admm_bp_iterate(const admm_bp_buffers* b, int iter_end, admm_stream_t stream) {
   if (int rc = check_bp(b, "admm_bp_iterate")) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // fused single-sweep kernel: Woodbury path with a tile-major copy of A (admm_bp_tile_A), M <= 256
+  // (16 rows per warp, up to 16 warps) and the vectors + 2 tile stages fit in shared memory
+  if (b->woodbury && b->At != nullptr && b->M <= 256 && !getenv("ADMM_BP_TWO_SWEEP")) {
+    const bool small = b->M <= 128;
+    const size_t smem = small ? BpfSmem<8>::bytes(b->N) : BpfSmem<16>::bytes(b->N);
+    if (smem <= 220 * 1024) {
+      static size_t attr8 = 0, attr16 = 0;
+      if (small) {
+        if (smem > attr8) {
+          cudaFuncSetAttribute(bp_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          cudaFuncSetAttribute(bp_fused_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          attr8 = smem;
+        }
+        bp_fused_kernel<8><<<b->nb, 256, smem, st>>>(*b, iter_end);
+      } else {
+        if (smem > attr16) {
+          cudaFuncSetAttribute(bp_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          cudaFuncSetAttribute(bp_fused_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          attr16 = smem;
+        }
+        bp_fused_kernel<16><<<b->nb, 512, smem, st>>>(*b, iter_end);
+      }
+      return check_launch("admm_bp_iterate(fused)");
+    }
+  }
   const size_t smem = bp_smem_bytes(b);
   ADMM_REQUIRE(smem <= 220 * 1024, ADMM_EUNSUPPORTED, "admm_bp_iterate: N=%d too large for the shared-memory resident path", b->N);
   static size_t attr = 0;
@@ -314,7 +611,7 @@ int admm_bp_iterate(const admm_bp_buffers* b, int iter_end, admm_stream_t stream
     cudaFuncSetAttribute(bp_iterate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = smem;
   }
-  bp_iterate_kernel<<<b->nb, BP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(*b, iter_end);
+  bp_iterate_kernel<<<b->nb, BP_THREADS, smem, st>>>(*b, iter_end);
   return check_launch("admm_bp_iterate");
 }
 

@@ -376,8 +376,14 @@ def run_ours(args):
         h2d = y_host.numel() * 8
         d2h = out_host.numel() * 8
         flops_per_unit = 4.0 * M * N + 2.0 * M * M
-        bytes_per_unit = 2.0 * 8 * M * N + 8.0 * M * M + 8.0 * 6 * N
-        kernel_name = "bp_iterate_kernel"
+        if eng.At is not None:
+            # single-sweep kernel: A streamed once per iteration (the column tile that yields A^T s also
+            # feeds the next A r), K^-1 once; the N-vectors never leave shared memory
+            bytes_per_unit = 8.0 * M * N + 8.0 * M * M
+            kernel_name = "bp_fused_kernel<%d>" % (8 if M <= 128 else 16)
+        else:
+            bytes_per_unit = 2.0 * 8 * M * N + 8.0 * M * M + 8.0 * 6 * N
+            kernel_name = "bp_iterate_kernel"
         bound = "hbm"
 
     def barrier():

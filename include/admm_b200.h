@@ -253,6 +253,8 @@ typedef struct admm_bp_buffers {
   int woodbury;           /* 1: M < N, factor K = A A^T + (mu/alpha) I (M x M); 0: G = alpha A^T A + mu I */
   int nk;                 /* order of the factor (M or N)                                      */
   const double* A;        /* [nb][M][N] row-major                                              */
+  const double* At;       /* [nb][ceil(N/32)][M][32] tile-major copy of A (admm_bp_tile_A), zero
+                             padded; NULL: admm_bp_iterate falls back to the two-sweep kernel  */
   const double* aty;      /* [nb][N]   alpha A^T y                                             */
   const double* gram;     /* [nb][nk][nk]  A A^T or A^T A                                      */
   double* Kinv;           /* [nb][nk][nk]                                                      */
@@ -275,6 +277,10 @@ typedef struct admm_bp_buffers {
 int admm_bp_setup(const admm_bp_buffers* b, const double* y, double* aty, double* gram,
                   admm_stream_t stream);
 
+/* At = tile-major copy of A: every 32-column tile of a problem is one contiguous M x 32 block, so
+ * the fused iteration kernel fetches it with one TMA bulk copy (whole DRAM pages). */
+int admm_bp_tile_A(const admm_bp_buffers* b, double* At, admm_stream_t stream);
+
 /* Kinv = (gram + (mu/alpha) I)^-1 or (alpha gram + mu I)^-1 for problems with need_factor set;
  * clears the flag.  Replaces `_get_B` (objectivefunc.py:89-96). */
 int admm_bp_factor(const admm_bp_buffers* b, int* info, admm_stream_t stream);
@@ -282,7 +288,8 @@ int admm_bp_factor(const admm_bp_buffers* b, int* info, admm_stream_t stream);
 /* Runs iterations [iter_begin, iter_end) of `SimpleOptimizer.solve` (optimizer.py:302-341) for
  * every problem that is neither done nor waiting for a factor: x-update by the cached inverse
  * (Woodbury or direct), soft threshold, dual ascent, residuals, convergence test, and -- when
- * (iter % interval_update_mu == 0) -- update_mu.  A problem whose mu changed sets need_factor
+ * (iter % interval_update_mu == 0) -- update_mu.  With At set (Woodbury path, M <= 256) A is streamed
+ * ONCE per iteration: the column tile that yields A^T s also feeds the next iteration's A r'.  A problem whose mu changed sets need_factor
  * and stops; the caller runs admm_bp_factor and calls again with the same iter_end. */
 int admm_bp_iterate(const admm_bp_buffers* b, int iter_end, admm_stream_t stream);
 

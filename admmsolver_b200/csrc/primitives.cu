@@ -3,6 +3,8 @@
 // vector algebra in optimizer.py; the two fused engines (spm.cu, bp.cu) carry the hot paths.
 #include "common.cuh"
 
+#include <cstdlib>
+
 #include <algorithm>
 #include <cstdarg>
 
@@ -340,6 +342,167 @@ __global__ void __launch_bounds__(512) spd_inverse_kernel(int n, double* __restr
   if (tid == 0 && info) info[b] = bad;
 }
 
+// ---------------------------------------------------------------------------------------------
+// batched in-place inverse of real SPD matrices of order n <= 128 on the FP64 tensor cores:
+// block Gauss-Jordan with 8x8 blocks, the whole matrix REGISTER-resident in the CTA.
+//   warp w owns block row w: its 8 x n strip lives in mma C-fragment layout (lane 4g+t holds
+//   (row g, columns 2t, 2t+1) of every 8x8 tile), 2*NB doubles per lane.
+//   step k:  P = A_kk^-1 (warp k, in-warp shuffles);  T_w = A_wk P;  A_wj -= T_w A_kj (j != k);
+//            A_kj = P A_kj;  A_wk = -T_w;  A_kk = P.
+//   The C fragment of a tile is reused as the A operand of the next MMA by permuting the k index
+//   (k-slot (e, t) <-> column 2t+e), so nothing is transposed: the row panel A_k travels through
+//   shared memory once per step in the two operand layouts the MMAs need.
+// One CTA (NB warps) per matrix, 2 __syncthreads per block step.  No pivoting (SPD).
+// ---------------------------------------------------------------------------------------------
+constexpr int SPDI_MAXB = 16;     // up to 16 block rows of 8 -> n <= 128
+
+__global__ void __launch_bounds__(SPDI_MAXB * 32, 1)
+    spd_inverse_dmma_kernel(int n, double* __restrict__ Aall, long long bstride, int lda, const int* __restrict__ mask,
+                            int* __restrict__ info) {
+  __shared__ __align__(16) double panF[SPDI_MAXB * 64];      // row panel, fragment-major: [j][lane][e] = A_k[2t+e][8j+g]
+  __shared__ double panC[8 * (8 * SPDI_MAXB + 4)];           // row panel, canonical, row pitch 8*NBmax+4 (conflict-free column reads)
+  __shared__ __align__(16) double Psm[64];                    // P = A_kk^-1, canonical 8x8
+  __shared__ int bad_sm;
+  constexpr int PITCH = 8 * SPDI_MAXB + 4;
+  const int b = blockIdx.x;
+  if (mask && mask[b] == 0) return;
+  double* Ag = Aall + (size_t)b * bstride;
+  const int NB = (n + 7) >> 3;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+  if (tid == 0) bad_sm = 0;
+
+  // ---- load the strip (identity on the padding keeps the padded matrix SPD)
+  double c[SPDI_MAXB][2];
+  const int row = 8 * w + g;
+#pragma unroll
+  for (int j = 0; j < SPDI_MAXB; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = 8 * j + 2 * t + e;
+      double v = (row == col) ? 1.0 : 0.0;
+      if (j < NB && row < n && col < n) v = Ag[(size_t)row * lda + col];
+      c[j][e] = v;
+    }
+  }
+  __syncthreads();
+
+  for (int k = 0; k < NB; ++k) {
+    if (w == k) {
+      // ---- publish the (old) row panel in both operand layouts
+#pragma unroll
+      for (int j = 0; j < SPDI_MAXB; ++j) {
+        if (j < NB) {
+          // canonical: rows g, columns 8j+2t+e
+          panC[g * PITCH + 8 * j + 2 * t] = c[j][0];
+          panC[g * PITCH + 8 * j + 2 * t + 1] = c[j][1];
+        }
+      }
+      // ---- P = A_kk^-1 by in-place Gauss-Jordan on the C fragment (lane holds (g, 2t), (g, 2t+1))
+      double a0, a1;
+      {
+        double akk[SPDI_MAXB][2];
+#pragma unroll
+        for (int j = 0; j < SPDI_MAXB; ++j) { akk[j][0] = c[j][0]; akk[j][1] = c[j][1]; }
+        a0 = 0.0; a1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < SPDI_MAXB; ++j) if (j == k) { a0 = akk[j][0]; a1 = akk[j][1]; }
+      }
+      int bad = 0;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int src_pp = 4 * p + (p >> 1);                  // lane holding (p, p)
+        const double piv = __shfl_sync(0xffffffffu, (p & 1) ? a1 : a0, src_pp);
+        if (!(piv > 0.0)) bad = 8 * k + p + 1;
+        const double ip = 1.0 / piv;
+        // pivot row, my two columns; pivot column, my row
+        double r0 = __shfl_sync(0xffffffffu, a0, 4 * p + t);
+        double r1 = __shfl_sync(0xffffffffu, a1, 4 * p + t);
+        double cg = __shfl_sync(0xffffffffu, (p & 1) ? a1 : a0, 4 * g + (p >> 1));
+        if (2 * t == p) r0 = 1.0;
+        if (2 * t + 1 == p) r1 = 1.0;
+        r0 *= ip;
+        r1 *= ip;
+        if (g == p) {
+          a0 = r0;
+          a1 = r1;
+        } else {
+          const double b0 = (2 * t == p) ? 0.0 : a0;
+          const double b1 = (2 * t + 1 == p) ? 0.0 : a1;
+          a0 = b0 - cg * r0;
+          a1 = b1 - cg * r1;
+        }
+      }
+      Psm[g * 8 + 2 * t] = a0;
+      Psm[g * 8 + 2 * t + 1] = a1;
+      if (bad && lane == 0) bad_sm = bad;
+    }
+    __syncthreads();
+    // fragment-major copy of the panel (cooperative): panF[j][lane'][e] = A_k[2t'+e][8j+g']
+    for (int idx = tid; idx < NB * 64; idx += blockDim.x) {
+      const int e = idx & 1, ln = (idx >> 1) & 31, j = idx >> 6;
+      panF[idx] = panC[(2 * (ln & 3) + e) * PITCH + 8 * j + (ln >> 2)];
+    }
+    __syncthreads();
+
+    if (w < NB) {
+      if (w != k) {
+        // ---- T = A_wk P   (A operand: my C fragment of tile (w,k), k-slot (e,t) <-> column 2t+e)
+        double ak0 = 0.0, ak1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < SPDI_MAXB; ++j) if (j == k) { ak0 = c[j][0]; ak1 = c[j][1]; }
+        double T0 = 0.0, T1 = 0.0;
+        dmma(T0, T1, ak0, Psm[(2 * t) * 8 + g]);
+        dmma(T0, T1, ak1, Psm[(2 * t + 1) * 8 + g]);
+        const double nT0 = -T0, nT1 = -T1;
+        // ---- A_wj -= T A_kj  for j != k;  A_wk = -T
+#pragma unroll
+        for (int j = 0; j < SPDI_MAXB; ++j) {
+          if (j < NB) {
+            if (j == k) {
+              c[j][0] = nT0;
+              c[j][1] = nT1;
+            } else {
+              const double2 bb = *reinterpret_cast<const double2*>(panF + (j * 32 + lane) * 2);
+              dmma(c[j][0], c[j][1], nT0, bb.x);
+              dmma(c[j][0], c[j][1], nT1, bb.y);
+            }
+          }
+        }
+      } else {
+        // ---- row k:  A_kj = P A_kj (j != k),  A_kk = P     (A operand: P[g][4s+t]; B: A_k[4s+t][8j+g])
+        const double p0 = Psm[g * 8 + t], p1 = Psm[g * 8 + 4 + t];
+#pragma unroll
+        for (int j = 0; j < SPDI_MAXB; ++j) {
+          if (j < NB) {
+            if (j == k) {
+              c[j][0] = Psm[g * 8 + 2 * t];
+              c[j][1] = Psm[g * 8 + 2 * t + 1];
+            } else {
+              double d0 = 0.0, d1 = 0.0;
+              dmma(d0, d1, p0, panC[t * PITCH + 8 * j + g]);
+              dmma(d0, d1, p1, panC[(4 + t) * PITCH + 8 * j + g]);
+              c[j][0] = d0;
+              c[j][1] = d1;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();     // the panel buffers are rewritten in the next step
+  }
+
+  // ---- write back (the exact inverse is symmetric; rounding differences stay at the 1e-16 level)
+#pragma unroll
+  for (int j = 0; j < SPDI_MAXB; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = 8 * j + 2 * t + e;
+      if (j < NB && row < n && col < n) Ag[(size_t)row * lda + col] = c[j][e];
+    }
+  }
+  if (tid == 0 && info) info[b] = bad_sm;
+}
+
 }  // namespace admm
 
 using namespace admm;
@@ -453,7 +616,10 @@ int admm_spd_inverse_batched(int n, int nbatch, double* A, long long batch_strid
   ADMM_REQUIRE(n > 0 && n <= 4096 && nbatch >= 0 && lda >= n, ADMM_EINVAL, "admm_spd_inverse_batched: bad dims");
   if (nbatch == 0) return ADMM_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (n <= 128) {
+  if (n <= 8 * SPDI_MAXB && !getenv("ADMM_SPD_SCALAR")) {
+    const int NB = (n + 7) / 8;
+    spd_inverse_dmma_kernel<<<nbatch, 32 * NB, 0, s>>>(n, A, batch_stride, lda, mask, info);
+  } else if (n <= 128) {
     const size_t smem = (size_t)(n * n + 2 * n) * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {

@@ -1,0 +1,53 @@
+"""Device primitives behind the C ABI against NumPy/LAPACK (float64, tolerance in each test)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [1, 5, 8, 37, 64, 100, 128, 150])
+def test_spd_inverse_batched(build_lib, n):
+    """admm_spd_inverse_batched: tensor-core block Gauss-Jordan (n <= 128) and the scalar fallback (n > 128)
+    vs np.linalg.inv on K = A A^T + mu I (the Woodbury matrix of basis pursuit), masked batch, info flags.
+    Replaces np.linalg.inv at matrix.py:77-78 via objectivefunc.py:89-96."""
+    from admmsolver_b200 import _lib
+    rs = np.random.RandomState(n)
+    nbatch = 7
+    mats = []
+    for b in range(nbatch):
+        A = rs.randn(n, 3 * n + 2)
+        mats.append(A @ A.T + (0.5 + b) * np.eye(n))
+    K = np.stack(mats)
+    lda = n + 3                                        # non-trivial leading dimension
+    buf = np.zeros((nbatch, n, lda))
+    buf[:, :, :n] = K
+    d = torch.from_numpy(buf).cuda()
+    mask = torch.tensor([1, 1, 0, 1, 1, 1, 1], dtype=torch.int32, device="cuda")
+    info = torch.full((nbatch,), -1, dtype=torch.int32, device="cuda")
+    _lib.call("admm_spd_inverse_batched", n, nbatch, _lib.ptr(d), n * lda, lda, _lib.ptr(mask), _lib.ptr(info), _lib.stream())
+    out = d.cpu().numpy()
+    inf = info.cpu().numpy()
+    for b in range(nbatch):
+        if b == 2:                                     # masked out: untouched
+            assert np.array_equal(out[b], buf[b]) and inf[b] == -1
+            continue
+        ref = np.linalg.inv(K[b])
+        err = np.linalg.norm(out[b, :, :n] - ref) / np.linalg.norm(ref)
+        assert err < 1e-12, (n, b, err)
+        assert np.array_equal(out[b, :, n:], buf[b, :, n:])          # padding columns untouched
+        assert inf[b] == 0
+        # K^-1 K = I to working precision (test_matrix.py:153 uses atol 1e-12 on inv @ m)
+        assert np.abs(out[b, :, :n] @ K[b] - np.eye(n)).max() < 1e-10
+
+
+def test_spd_inverse_flags_indefinite(build_lib):
+    from admmsolver_b200 import _lib
+    K = np.eye(16)
+    K[5, 5] = -1.0
+    d = torch.from_numpy(K.copy()).cuda()
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.call("admm_spd_inverse_batched", 16, 1, _lib.ptr(d), 256, 16, None, _lib.ptr(info), _lib.stream())
+    assert int(info.item()) == 6                       # 1-based index of the first non-positive pivot

@@ -293,7 +293,7 @@ struct BpfSmem {
   static constexpr int STAGE_D = ROWS * BPF_TN;
   static size_t bytes(int N) {
     const int Np = (N + 1) & ~1;
-    return (size_t)(BPF_STAGES * STAGE_D + 5 * Np + ROWS + NW * BPF_TN + BPF_TN + 5 * 32) * sizeof(double) +
+    return (size_t)(BPF_STAGES * STAGE_D + 5 * Np + 2 * ROWS + NW * BPF_TN + BPF_TN + 5 * 32) * sizeof(double) +
            BPF_STAGES * sizeof(uint64_t) + 16;
   }
 };
@@ -315,7 +315,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) bp_fused_kernel(admm
   double* h = x1 + Np;                             // N
   double* r = h + Np;                              // N   current right-hand side
   double* tv = r + Np;                             // ROWS   t = A r
-  double* part = tv + ROWS;                        // NW x TN  per-warp partial column dots
+  double* sv = tv + ROWS;                          // ROWS   s = K^-1 t
+  double* part = sv + ROWS;                        // NW x TN  per-warp partial column dots
   double* rn = part + NW * BPF_TN;                 // TN   r' of the current tile
   double* scratch = rn + BPF_TN;                   // 5*32
   uint64_t* full = reinterpret_cast<uint64_t*>(scratch + 5 * 32);
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) bp_fused_kernel(admm
 
   // rows >= M and the columns of a ragged last tile are never written by a copy: keep them finite
   for (int i = tid; i < BPF_STAGES * STAGE_D; i += NT_) stage[i] = 0.0;
-  for (int i = tid; i < ROWS; i += NT_) tv[i] = 0.0;
+  for (int i = tid; i < 2 * ROWS; i += NT_) tv[i] = 0.0;      // tv and sv
   for (int n = tid; n < N; n += NT_) {
     aty[n] = b.aty[(size_t)prob * N + n];
     x0[n] = b.x0[(size_t)prob * N + n];
@@ -358,30 +359,49 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) bp_fused_kernel(admm
   double primal = 0.0, dual = 0.0;
   bool first = true;          // first sweep of this launch: only t = A r
   while (true) {
-    // ---- s = K^-1 t for this warp's rows (every lane ends up with all 16 values)
-    double sreg[BPF_RW];
-#pragma unroll
-    for (int i = 0; i < BPF_RW; ++i) sreg[i] = 0.0;
+    // ---- s = K^-1 t for this warp's rows, kept in shared memory (only this warp reads them back).
+    // The loads of 8 rows are issued together: two L2 round trips per iteration instead of sixteen.
     if (!first) {
 #pragma unroll
-      for (int i = 0; i < BPF_RW; ++i) {
-        const int m = warp * BPF_RW + i;
-        double a0 = 0.0;
-        if (m < M) {
-          const double* row = Kinv + (size_t)m * M;
-          for (int j = lane; j < M; j += 32) a0 += row[j] * tv[j];
-        }
-        sreg[i] = a0;
-      }
+      for (int half = 0; half < 2; ++half) {
+        double kv[8][4];
 #pragma unroll
-      for (int i = 0; i < BPF_RW; ++i) sreg[i] = warp_sum(sreg[i]);
-      __syncthreads();        // everyone has read tv before it is overwritten below
+        for (int i = 0; i < 8; ++i) {
+          const int m = warp * BPF_RW + half * 8 + i;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = lane + 32 * q;
+            kv[i][q] = (m < M && j < M) ? __ldg(Kinv + (size_t)m * M + j) : 0.0;
+          }
+        }
+        double a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          a[i] = 0.0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) a[i] += kv[i][q] * tv[lane + 32 * q];
+        }
+        for (int j0 = 128; j0 < M; j0 += 32) {        // M > 128 (16-warp variant): remaining columns
+          const int j = j0 + lane;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = warp * BPF_RW + half * 8 + i;
+            if (m < M && j < M) a[i] += __ldg(Kinv + (size_t)m * M + j) * tv[j];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const double sres = warp_sum(a[i]);
+          if (lane == 0) sv[warp * BPF_RW + half * 8 + i] = sres;
+        }
+      }
+      __syncthreads();        // everyone has read tv before it is overwritten below; sv visible
     }
     double acc[BPF_RW];
 #pragma unroll
     for (int i = 0; i < BPF_RW; ++i) acc[i] = 0.0;
     double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    const double thr = 0.5 * b.lam / mu;
+    const double thr = 0.5 * b.lam / mu, inv_mu = 1.0 / mu;
     // K^-1 is needed again right after this sweep: pull it into L2 meanwhile (16 KB per bulk prefetch)
     {
       const size_t kbytes = (size_t)M * M * sizeof(double);
@@ -400,10 +420,15 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) bp_fused_kernel(admm
 #pragma unroll
       for (int i = 0; i < BPF_RW; ++i) patch[i] = tile[i * BPF_TN];
       if (!first) {
-        double pc = 0.0;
+        const double* sw = sv + warp * BPF_RW;
+        double pc0 = 0.0, pc1 = 0.0;
 #pragma unroll
-        for (int i = 0; i < BPF_RW; ++i) pc += patch[i] * sreg[i];
-        part[warp * BPF_TN + lane] = pc;
+        for (int i = 0; i < BPF_RW; i += 2) {
+          const double2 s2 = *reinterpret_cast<const double2*>(sw + i);     // broadcast
+          pc0 += patch[i] * s2.x;
+          pc1 += patch[i + 1] * s2.y;
+        }
+        part[warp * BPF_TN + lane] = pc0 + pc1;
       }
       __syncthreads();                     // stage consumed by everyone; partial dots visible
       issue(gt + BPF_STAGES);
@@ -413,13 +438,19 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) bp_fused_kernel(admm
           const int n = k * BPF_TN + tid;
           double rnew = 0.0;
           if (n < N) {
-            double c = 0.0;
+            double cw[NW];
 #pragma unroll
-            for (int w = 0; w < NW; ++w) c += part[w * BPF_TN + tid];
+            for (int w = 0; w < NW; ++w) cw[w] = part[w * BPF_TN + tid];
+#pragma unroll
+            for (int st = NW / 2; st > 0; st >>= 1)
+#pragma unroll
+              for (int w = 0; w < st; ++w) cw[w] += cw[w + st];
+            const double c = cw[0];
             // x-update by the Woodbury identity, then z-update / dual ascent as in bp_iterate_kernel
+            // (this is the serial section of a tile: multiply by 1/mu instead of dividing twice)
             const double xov = x0[n], hv = h[n];
-            const double xv = (r[n] - c) / mu;
-            const double yv = -((hv - mu * xv) / mu);
+            const double xv = (r[n] - c) * inv_mu;
+            const double yv = xv - hv * inv_mu;
             double z = 0.0;
             if (yv > thr) z = yv - thr;
             if (yv < -thr) z = yv + thr;

@@ -472,6 +472,10 @@ def run_ours(args):
         ent = tj.get(kernel_name, {}).get(str(units_per_launch))
         if ent:
             traffic = float(ent["dram_bytes_read"]) + float(ent["dram_bytes_write"])
+        else:
+            ent = tj.get(kernel_name, {}).get("per_unit")
+            if ent:     # capture of a smaller launch, traffic proportional to the units of the launch
+                traffic = (float(ent["dram_bytes_read"]) + float(ent["dram_bytes_write"])) * units_per_launch
     except Exception:
         pass
 

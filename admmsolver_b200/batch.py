@@ -221,9 +221,13 @@ class SharedSpM:
             pairs = torch.stack([self.mu10[:1], self.mu20[:1]], dim=1).cpu().numpy()
             inverse = None
         else:
-            stacked = torch.stack([self.mu10[:nb], self.mu20[:nb]], dim=1)
-            uniq, inverse = torch.unique(stacked, dim=0, return_inverse=True)
-            pairs = uniq.cpu().numpy()
+            # distinct (mu10, mu20) pairs through three 1-D sorts (torch.unique(dim=0) on a (nb, 2) array is
+            # orders of magnitude slower and this runs once per interval on up to 2^20 problems)
+            u10, i10 = torch.unique(self.mu10[:nb], return_inverse=True)
+            u20, i20 = torch.unique(self.mu20[:nb], return_inverse=True)
+            n20 = u20.numel()
+            uk, inverse = torch.unique(i10 * n20 + i20, return_inverse=True)
+            pairs = torch.stack([u10[uk // n20], u20[uk % n20]], dim=1).cpu().numpy()
         new = [(float(a), float(b)) for a, b in pairs if (float(a), float(b)) not in self._slot_of]
         if len(self._slot_of) + len(new) > self.CACHE_SLOTS:
             # evict everything not currently needed

@@ -251,3 +251,21 @@ def test_spm_fused_per_problem_mixed_mu_and_early_stop(eng, ir_basis, mt):
         seen_mu.add((sb.mu10, sb.mu20))
         seen_it.add(sb.niter_done)
     assert len(seen_mu) > 1 and len(seen_it) > 1
+
+
+@pytest.mark.parametrize("eps,L_expect,mt,nsplit", [(1e-2, 14, 1, 1), (1e-2, 14, 2, 1), (1e-2, 14, 1, 2),
+                                                     (1e-10, 52, 1, 1), (1e-10, 52, 1, 3)])
+def test_spm_other_basis_sizes(eng, eps, L_expect, mt, nsplit):
+    """The Lp = 16 and Lp = 64 instantiations of the kernels (L = 14 and L = 52 bases), fused and split."""
+    from oracle import flat
+    batch, problems = eng
+    basis = problems.ir_basis(eps=eps)
+    assert basis.size == L_expect
+    p = problems.spm_batch(21, basis, Nw=136, seed=4)
+    e = batch.SharedSpM(p.s, p.P, p.C, p.D, p.g, lam=p.lam, mu=p.mu, batch_wide=True, mt=mt, nsplit=nsplit)
+    assert e.dims.Lp == (16 if L_expect <= 16 else 64)
+    e.solve(160, interval_update_mu=30)
+    st = flat.spm_solve(p.s, p.P, p.C, p.D, p.g, p.lam, 160, mu=p.mu, interval_update_mu=30)
+    assert rel(e.x0(), st.x0) < TOL and rel(e.x1(), st.x1) < TOL and rel(e.x2(), st.x2) < TOL
+    assert float(e.mu10[0]) == st.mu10 and float(e.mu20[0]) == st.mu20
+    assert rel(e.primal_residual, st.primal) < 1e-8

@@ -165,6 +165,25 @@ def prox_l1(h: torch.Tensor, mu_diag: torch.Tensor, alpha: float, complex_out: b
     return out
 
 
+def prox_psd(h: torch.Tensor, mu_diag: torch.Tensor, shape, axis: int, complex_out: bool) -> torch.Tensor:
+    """Per-slice PSD projection of -Re(h)/mu reshaped to the 3-way ``shape`` (C order); the matrices are
+    the slices along ``axis`` (rows / columns = the two remaining axes in order)."""
+    s0, s1, s2 = (int(v) for v in shape)
+    strides = (s1 * s2, s2, 1)
+    rest = [a for a in range(3) if a != axis % 3]
+    dims = (s0, s1, s2)
+    n = dims[rest[0]]
+    assert dims[rest[1]] == n, "SemiPositiveDefinitePenalty needs square slices"
+    nb = dims[axis % 3]
+    total = s0 * s1 * s2
+    h = h.contiguous()
+    assert h.numel() == total and mu_diag.numel() == total
+    out = torch.empty(total, dtype=C128 if complex_out else F64, device=h.device)
+    call("admm_prox_psd", n, nb, strides[axis % 3], strides[rest[0]], strides[rest[1]], ptr(h), ncomp(h),
+         ptr(mu_diag.contiguous()), ptr(out), 2 if complex_out else 1, stream())
+    return out
+
+
 def prox_nonneg(h: torch.Tensor, mu_diag: torch.Tensor, complex_out: bool) -> torch.Tensor:
     n = h.numel()
     h = h.contiguous()

@@ -75,6 +75,7 @@ _SIGS = {
     "admm_ewise_unary": ([_I, _I, _LL, _P, _P, _P], _I),
     "admm_prox_l1": ([_LL, _P, _I, _P, _D, _P, _I, _P], _I),
     "admm_prox_nonneg": ([_LL, _P, _I, _P, _P, _I, _P], _I),
+    "admm_prox_psd": ([_I, _LL, _LL, _LL, _LL, _P, _I, _P, _P, _I, _P], _I),
     "admm_sumsq": ([_LL, _P, _P, _P, _P, _P], _I),
     "admm_inverse": ([_I, _I, _P, _I, _P, _I, _P, _P, _P], _I),
     "admm_spd_inverse_batched": ([_I, _I, _P, _LL, _I, _P, _P, _P], _I),

@@ -192,6 +192,100 @@ __global__ void prox_nonneg_kernel(long long n, const double* __restrict__ h, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// PSD-cone projection of many small real symmetric matrices (SemiPositiveDefinitePenalty.solve,
+// objectivefunc.py:294-327): X = -Re(h)/mu elementwise, then per matrix (LOWER triangle, like
+// np.linalg.eigh) X <- sum_{lambda_k >= 0} lambda_k u_k u_k^T.  One warp per matrix, cyclic Jacobi
+// in shared memory (lane k owns row/column k of the rotations), n <= 32.
+// Matrix m, element (p, q) sits at flat index m*sb + p*sr + q*sc of the term's vector.
+// ---------------------------------------------------------------------------------------------
+constexpr int PSD_WARPS = 2;
+
+__global__ void __launch_bounds__(PSD_WARPS * 32) prox_psd_kernel(int n, long long nbatch, long long sb, long long sr,
+                                                                  long long sc, const double* __restrict__ h, int hs,
+                                                                  const double* __restrict__ mud, double* __restrict__ out,
+                                                                  int os) {
+  extern __shared__ double psd_sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pitch = n | 1;
+  double* A = psd_sm + (size_t)warp * 2 * n * pitch;
+  double* V = A + (size_t)n * pitch;
+  for (long long m = (long long)blockIdx.x * PSD_WARPS + warp; m < nbatch; m += (long long)gridDim.x * PSD_WARPS) {
+    // ---- load: symmetric matrix from the lower triangle of -Re(h)/mu
+    for (int p = 0; p < n; ++p) {
+      if (lane < n) {
+        const int r = p > lane ? p : lane, c = p > lane ? lane : p;
+        const long long off = m * sb + r * sr + c * sc;
+        A[p * pitch + lane] = -(h[off * hs] / mud[off]);
+        V[p * pitch + lane] = (p == lane) ? 1.0 : 0.0;
+      }
+    }
+    __syncwarp();
+    double fro = 0.0;
+    if (lane < n)
+      for (int q = 0; q < n; ++q) fro += A[lane * pitch + q] * A[lane * pitch + q];
+    fro = warp_sum(fro);
+    // ---- cyclic Jacobi sweeps
+    for (int sweep = 0; sweep < 40; ++sweep) {
+      double off2 = 0.0;
+      if (lane < n)
+        for (int q = 0; q < n; ++q)
+          if (q != lane) off2 += A[lane * pitch + q] * A[lane * pitch + q];
+      off2 = warp_sum(off2);
+      if (!(off2 > 1e-31 * fro)) break;
+      for (int p = 0; p < n - 1; ++p) {
+        for (int q = p + 1; q < n; ++q) {
+          const double apq = A[p * pitch + q];
+          if (apq != 0.0) {
+            const double app = A[p * pitch + p], aqq = A[q * pitch + q];
+            const double theta = (aqq - app) / (2.0 * apq);
+            const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+            __syncwarp();
+            if (lane < n) {
+              const int k = lane;
+              const double vkp = V[k * pitch + p], vkq = V[k * pitch + q];
+              V[k * pitch + p] = c * vkp - sn * vkq;
+              V[k * pitch + q] = sn * vkp + c * vkq;
+              if (k != p && k != q) {
+                const double akp = A[k * pitch + p], akq = A[k * pitch + q];
+                const double np_ = c * akp - sn * akq, nq_ = sn * akp + c * akq;
+                A[k * pitch + p] = np_;
+                A[p * pitch + k] = np_;
+                A[k * pitch + q] = nq_;
+                A[q * pitch + k] = nq_;
+              }
+            }
+            __syncwarp();
+            if (lane == 0) {
+              A[p * pitch + p] = app - t * apq;
+              A[q * pitch + q] = aqq + t * apq;
+              A[p * pitch + q] = 0.0;
+              A[q * pitch + p] = 0.0;
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+    // ---- X+ = V diag(max(lambda, 0)) V^T : lane i writes row i
+    if (lane < n) {
+      const int i = lane;
+      for (int j = 0; j < n; ++j) {
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) {
+          const double lam = A[k * pitch + k];
+          if (lam > 0.0) acc += lam * V[i * pitch + k] * V[j * pitch + k];
+        }
+        const long long off = m * sb + i * sr + j * sc;
+        out[off * os] = acc;
+        if (os == 2) out[off * 2 + 1] = 0.0;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(256) sumsq_stage1(long long n, const double* __restrict__ x,
                                                     const double* __restrict__ y, double* __restrict__ part) {
   __shared__ double scratch[32];
@@ -588,6 +682,18 @@ int admm_prox_nonneg(long long n, const double* h, int h_stride, const double* m
   prox_nonneg_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, h, h_stride, mu_diag, out,
                                                                                out_stride);
   return check_launch("admm_prox_nonneg");
+}
+
+int admm_prox_psd(int n, long long nbatch, long long stride_batch, long long stride_row, long long stride_col,
+                  const double* h, int h_stride, const double* mu_diag, double* out, int out_stride, admm_stream_t stream) {
+  ADMM_REQUIRE(n >= 1 && n <= 32, ADMM_EUNSUPPORTED, "admm_prox_psd: matrix order %d not supported (1..32)", n);
+  if (nbatch <= 0) return ADMM_OK;
+  const size_t smem = (size_t)PSD_WARPS * 2 * n * (n | 1) * sizeof(double);
+  const int grid = (int)std::max<long long>(1, std::min<long long>((nbatch + PSD_WARPS - 1) / PSD_WARPS, 148LL * 16));
+  prox_psd_kernel<<<grid, PSD_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(n, nbatch, stride_batch, stride_row,
+                                                                                    stride_col, h, h_stride, mu_diag, out,
+                                                                                    out_stride);
+  return check_launch("admm_prox_psd");
 }
 
 int admm_sumsq(long long n, const double* x, const double* y, double* out, double* scratch, admm_stream_t stream) {

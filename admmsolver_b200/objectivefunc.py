@@ -236,17 +236,43 @@ class NonNegativePenalty(ObjectiveFunctionBase):
 
 
 class SemiPositiveDefinitePenalty(ObjectiveFunctionBase):
-    """Out of scope this round (needs a batched Hermitian eigensolver on
-    the device).  Kept so that imports succeed; using it raises, there is no CPU fallback."""
+    """Penalty for negative eigenvalues (objectivefunc.py:274-327): x is reshaped to a three-way tensor
+    and every slice along ``axis`` is projected onto the PSD cone.  SURVEY.md 8(f) row f2: the per-slice
+    ``np.linalg.eigh`` loop of the reference is one batched Jacobi kernel (``admm_prox_psd``, one warp
+    per slice, slices up to 32 x 32)."""
 
     def __init__(self, shape, axis: int):
         assert len(shape) == 3
         super().__init__(int(np.prod(shape)))
-        self._shape = shape
+        self._shape = tuple(int(v) for v in shape)
         self._axis = axis
 
     def __call__(self, x):
         return 0.0
 
-    def solve(self, h=None, mu=None):
-        raise NotImplementedError("SemiPositiveDefinitePenalty has no CUDA implementation yet (SURVEY.md 8(f) f2)")
+    def _diagonals(self, mu: MatrixBase) -> torch.Tensor:
+        """mu as a vector of diagonal entries (objectivefunc.py:296-311)."""
+        assert isinstance(mu, (DiagonalMatrix, ScaledIdentityMatrix)) or \
+            (isinstance(mu, PartialDiagonalMatrix) and isinstance(mu.matrix, (ScaledIdentityMatrix, DiagonalMatrix)))
+        if isinstance(mu, (DiagonalMatrix, ScaledIdentityMatrix)):
+            d = mu._diag_dev()
+        else:
+            inner = mu.matrix._diag_dev()
+            rest = int(np.prod(mu.rest_dims))
+            d = inner.reshape(-1, 1).expand(inner.numel(), rest).reshape(-1)      # einsum('i,j->ij', diag, ones).ravel()
+        if d.is_complex():
+            d = d.real
+        d = d.contiguous()
+        assert d.ndim == 1 and d.numel() == self.size_x
+        return d
+
+    def solve(self, h: Optional[Vec] = None, mu: Optional[MatrixBase] = None):
+        """Works only if mu is (partially) diagonal; the imaginary part of h is dropped like in the reference."""
+        assert isinstance(h, (np.ndarray, torch.Tensor))
+        if mu is None:
+            raise ValueError("mu must not be None!")
+        hd = D.as_dev(h)
+        return _ret(D.prox_psd(hd, self._diagonals(mu), self._shape, self._axis, complex_out=False), h)
+
+    def _solve_complex(self, h: torch.Tensor, mu: MatrixBase) -> torch.Tensor:
+        return D.prox_psd(h, self._diagonals(mu), self._shape, self._axis, complex_out=True)

@@ -78,6 +78,15 @@ int admm_prox_l1(long long n, const double* h, int h_stride, const double* mu_di
 int admm_prox_nonneg(long long n, const double* h, int h_stride, const double* mu_diag,
                      double* out, int out_stride, admm_stream_t stream);
 
+/* PSD-cone projection of `nbatch` real symmetric n x n matrices (n <= 32) embedded in one vector:
+ * element (p, q) of matrix m is entry m*stride_batch + p*stride_row + q*stride_col.  X = -Re(h)/mu_diag
+ * elementwise; per matrix the LOWER triangle defines the symmetric matrix (as np.linalg.eigh does) and
+ * the negative eigenvalues are removed.  One warp per matrix, cyclic Jacobi in shared memory.
+ * Replaces `SemiPositiveDefinitePenalty.solve` (objectivefunc.py:294-327). */
+int admm_prox_psd(int n, long long nbatch, long long stride_batch, long long stride_row,
+                  long long stride_col, const double* h, int h_stride, const double* mu_diag,
+                  double* out, int out_stride, admm_stream_t stream);
+
 /* out[0] = sum_i x[i]^2 (y == NULL) or sum_i (x[i]-y[i])^2 over n doubles; deterministic
  * two-stage reduction; `scratch` needs 1024 doubles.  Replaces `np.linalg.norm`
  * (util.py:40, optimizer.py:261,267,284,289). */

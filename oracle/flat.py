@@ -267,3 +267,18 @@ def spm_solve_independent(s, P, C, D, g, lam, niter, **kw) -> List[SpMState]:
     nb = g.shape[1]
     Dv = np.broadcast_to(np.asarray(D, dtype=float).ravel(), (nb,))
     return [spm_solve(s, P, C, np.array([Dv[b]]), g[:, b], lam, niter, **kw) for b in range(nb)]
+
+
+def psd_project(h: np.ndarray, diagonals: np.ndarray, shape, axis: int) -> np.ndarray:
+    """``SemiPositiveDefinitePenalty.solve`` (objectivefunc.py:312-327): x = -Re(h)/mu reshaped to the
+    3-way ``shape``; every slice along ``axis`` is replaced by its projection onto the PSD cone, the
+    symmetric matrix being defined by the LOWER triangle of the slice (``np.linalg.eigh`` default)."""
+    x = (-(np.real(h) / diagonals)).reshape(shape)
+    x = np.moveaxis(x, axis, 0).copy()
+    for i in range(x.shape[0]):
+        lo = np.tril(x[i])
+        sym = lo + np.tril(x[i], -1).T
+        ev, U = np.linalg.eigh(sym)
+        keep = ev >= 0
+        x[i] = (U[:, keep] * ev[keep]) @ U[:, keep].T
+    return np.moveaxis(x, 0, axis).ravel()

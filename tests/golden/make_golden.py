@@ -26,7 +26,7 @@ sys.path.insert(0, REF)
 from admmsolver.matrix import (DenseMatrix, DiagonalMatrix, PartialDiagonalMatrix,  # noqa: E402
                                ScaledIdentityMatrix, identity)
 from admmsolver.objectivefunc import (ConstrainedLeastSquares, L1Regularizer,  # noqa: E402
-                                      LeastSquares, NonNegativePenalty)
+                                      LeastSquares, NonNegativePenalty, SemiPositiveDefinitePenalty)
 from admmsolver.optimizer import Model, SimpleOptimizer  # noqa: E402
 
 spec = importlib.util.spec_from_file_location("problems", os.path.join(ROOT, "admmsolver_b200", "problems.py"))
@@ -184,5 +184,50 @@ def main():
          objective=opt(opt.x))
 
 
+def main_psd():
+    """SemiPositiveDefinitePenalty: term-level solves for every axis / mu type and one
+    model through the reference's loop.  `python tests/golden/make_golden.py psd`."""
+    rs = np.random.RandomState(100)
+    cr = lambda *sh: rs.randn(*sh) + 1j * rs.randn(*sh)
+    N, K = 10, 20
+    h = cr(N * N * K)
+    out = dict(h=h)
+    out["x_identity"] = SemiPositiveDefinitePenalty((N, N, K), axis=2).solve(h, identity(N * N * K))
+    out["x_partial"] = SemiPositiveDefinitePenalty((N, N, K), axis=2).solve(
+        h, PartialDiagonalMatrix(ScaledIdentityMatrix(N * N, 1.7), (K,)))
+    dvar = np.linspace(0.5, 2.5, N * N)
+    out["dvar"] = dvar
+    out["x_partial_diag"] = SemiPositiveDefinitePenalty((N, N, K), axis=2).solve(
+        h, PartialDiagonalMatrix(DiagonalMatrix(dvar), (K,)))
+    dfull = np.linspace(0.3, 3.0, N * N * K)
+    out["dfull"] = dfull
+    out["x_diag"] = SemiPositiveDefinitePenalty((N, N, K), axis=2).solve(h, DiagonalMatrix(dfull))
+    h0 = cr(6 * 7 * 7)
+    out["h_axis0"] = h0
+    out["x_axis0"] = SemiPositiveDefinitePenalty((6, 7, 7), axis=0).solve(h0, ScaledIdentityMatrix(6 * 7 * 7, 0.8))
+    h1 = cr(5 * 4 * 5)
+    out["h_axis1"] = h1
+    out["x_axis1"] = SemiPositiveDefinitePenalty((5, 4, 5), axis=1).solve(h1, ScaledIdentityMatrix(5 * 4 * 5, 1.3))
+    h32 = rs.randn(32 * 32 * 3)
+    out["h_n32"] = h32
+    out["x_n32"] = SemiPositiveDefinitePenalty((3, 32, 32), axis=0).solve(h32, ScaledIdentityMatrix(32 * 32 * 3, 1.0))
+    # matrix-valued least squares with a PSD constraint through SimpleOptimizer.solve
+    n, k = 4, 3
+    nx = n * n * k
+    Am = rs.randn(2 * nx, nx)
+    ym = rs.randn(2 * nx)
+    opt = SimpleOptimizer(Model([LeastSquares(0.9, Am, ym), SemiPositiveDefinitePenalty((n, n, k), axis=2)],
+                                [(0, 1, identity(nx), identity(nx))]), mu=0.5)
+    opt.solve(120, interval_update_mu=25)
+    out.update(loop_A=Am, loop_y=ym, loop_x0=opt.x[0], loop_x1=opt.x[1], loop_h10=opt._h[1, 0], loop_mu10=opt._mu[1, 0],
+               loop_primal=np.array(opt._primal_residual), loop_dual=np.array(opt._dual_residual),
+               loop_objective=opt(opt.x))
+    save("psd", **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "psd":
+        main_psd()
+    else:
+        main()
+        main_psd()

@@ -279,3 +279,49 @@ def test_spm_packed_partialdiagonal_dropin(api):
                              mu=float(g["mu"]))
     opt2.solve(30, callback=lambda: None)
     assert rel(opt2._primal_residual, g["primal"][:30]) < 1e-8
+
+
+def test_semi_positive_definite_penalty_golden(build_lib):
+    """SemiPositiveDefinitePenalty.solve (objectivefunc.py:294-327) for every axis and
+    mu type against the reference's outputs (tests/golden/psd.npz), plus the reference's own acceptance
+    check (test_objectivefunc.py:169-185: all eigenvalues > -1e-10)."""
+    from admmsolver_b200.matrix import DiagonalMatrix, PartialDiagonalMatrix, ScaledIdentityMatrix, identity
+    from admmsolver_b200.objectivefunc import SemiPositiveDefinitePenalty
+    g = golden("psd")
+    N, K = 10, 20
+    h = g["h"]
+    p = SemiPositiveDefinitePenalty((N, N, K), axis=2)
+    cases = [("x_identity", identity(N * N * K)),
+             ("x_partial", PartialDiagonalMatrix(ScaledIdentityMatrix(N * N, 1.7), (K,))),
+             ("x_partial_diag", PartialDiagonalMatrix(DiagonalMatrix(g["dvar"]), (K,))),
+             ("x_diag", DiagonalMatrix(g["dfull"]))]
+    for key, mu in cases:
+        res = p.solve(h, mu)
+        assert isinstance(res, np.ndarray) and res.dtype == np.float64
+        assert rel(res, g[key]) < 1e-10, key
+        x = res.reshape(N, N, K)
+        for k in range(K):
+            assert np.linalg.eigvalsh(x[:, :, k]).min() > -1e-10
+    assert rel(SemiPositiveDefinitePenalty((6, 7, 7), axis=0).solve(g["h_axis0"], ScaledIdentityMatrix(6 * 7 * 7, 0.8)),
+               g["x_axis0"]) < 1e-10
+    assert rel(SemiPositiveDefinitePenalty((5, 4, 5), axis=1).solve(g["h_axis1"], ScaledIdentityMatrix(5 * 4 * 5, 1.3)),
+               g["x_axis1"]) < 1e-10
+    assert rel(SemiPositiveDefinitePenalty((3, 32, 32), axis=0).solve(g["h_n32"], ScaledIdentityMatrix(32 * 32 * 3, 1.0)),
+               g["x_n32"]) < 1e-10
+
+
+def test_semi_positive_definite_model_golden(build_lib):
+    """Matrix-valued least squares with a PSD constraint through SimpleOptimizer.solve (generic executor)."""
+    from admmsolver_b200.matrix import identity
+    from admmsolver_b200.objectivefunc import LeastSquares, SemiPositiveDefinitePenalty
+    from admmsolver_b200.optimizer import Model, SimpleOptimizer
+    g = golden("psd")
+    n, k = 4, 3
+    nx = n * n * k
+    opt = SimpleOptimizer(Model([LeastSquares(0.9, g["loop_A"], g["loop_y"]), SemiPositiveDefinitePenalty((n, n, k), axis=2)],
+                                [(0, 1, identity(nx), identity(nx))]), mu=0.5)
+    opt.solve(120, interval_update_mu=25)
+    assert rel(opt.x[0], g["loop_x0"]) < 1e-10 and rel(opt.x[1], g["loop_x1"]) < 1e-10
+    assert float(opt._mu[1, 0]) == float(g["loop_mu10"])
+    assert abs(opt(opt.x) - g["loop_objective"]) / abs(g["loop_objective"]) < 1e-10
+    assert rel(opt._primal_residual, g["loop_primal"]) < 1e-8

@@ -325,3 +325,25 @@ def test_semi_positive_definite_model_golden(build_lib):
     assert float(opt._mu[1, 0]) == float(g["loop_mu10"])
     assert abs(opt(opt.x) - g["loop_objective"]) / abs(g["loop_objective"]) < 1e-10
     assert rel(opt._primal_residual, g["loop_primal"]) < 1e-8
+
+
+def test_notebook_examples(build_lib):
+    """examples/basis_pursuit.py and examples/spm.py: the two notebooks of the reference through the drop-in
+    API.  Known answers: basis_pursuit.ipynb:137-138; spm.ipynb:270 (sum rule = 1)."""
+    import importlib.util
+    import os
+    from conftest import ROOT
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "examples", name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    xanswer, x0, opt = load("basis_pursuit").main(verbose=False)
+    assert abs(np.abs(xanswer).max() - 1.4312955709975443) < 1e-15
+    assert abs(np.abs(xanswer - x0).max() - 0.0054070107628211295) < 1e-9
+    r = load("spm").main(niter=3000, verbose=False)
+    assert r["L"] == 39 and abs(r["sum_rule"] - 1.0) < 1e-10       # spm.ipynb:214,270
+    assert np.abs(r["rho_rec"] - r["rho"]).max() < 0.15 * r["rho"].max()      # the spectrum is recovered (noise 1e-4: the sharp peak is smoothed)
+    assert r["rho_rec"].min() > -1e-3                               # and non-negative up to the ADMM residual

@@ -31,7 +31,7 @@ class AdmmError(RuntimeError):
 
 class SpmDims(C.Structure):
     _fields_ = [(n, C.c_int) for n in
-                ("L", "Lp", "Nw", "nrt", "nb", "npt", "nplanes", "nsplit", "mt", "batch_wide")]
+                ("L", "Lp", "Nw", "nrt", "nb", "npt", "nplanes", "nsplit", "mt", "nbal", "batch_wide")]
 
 
 _P = C.c_void_p
@@ -91,6 +91,7 @@ _SIGS = {
     "admm_spm_pass": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
     "admm_spm_step": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _P], _I),
     "admm_spm_reduce": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _P], _I),
+    "admm_spm_reduce_decide": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
     "admm_spm_decide": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
     "admm_bp_setup": ([C.POINTER(BpBuffers), _P, _P, _P, _P], _I),
     "admm_bp_tile_A": ([C.POINTER(BpBuffers), _P, _P], _I),
@@ -107,7 +108,7 @@ if lib.admm_abi_version() != ABI_VERSION:
 
 #: number of kernel launches issued through this binding (bench.py reports it as gpu_launches)
 launch_count = 0
-_LAUNCHES_PER_CALL = {"admm_sumsq": 2, "admm_spm_reduce": 2, "admm_bp_factor": 3, "admm_bp_setup": 2}
+_LAUNCHES_PER_CALL = {"admm_sumsq": 2, "admm_spm_reduce": 2, "admm_spm_reduce_decide": 2, "admm_bp_factor": 3, "admm_bp_setup": 2}
 
 
 def check(rc: int) -> None:

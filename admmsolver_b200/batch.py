@@ -124,13 +124,21 @@ class SharedSpM:
         if mt is None:
             mt = 2 if (npt >= 8 * 444 and Lp <= 40) else 1
         assert mt in (1, 2) and (mt == 1 or Lp <= 40)
+        nbal = 0
         if nsplit is None:
-            # fill the 148 SMs x 3 resident CTAs in ONE wave: split the sampling points over
-            # several CTAs only when the batch alone cannot (then the x-update is a separate kernel)
-            col_ctas = -(-npt // (4 * mt))
-            nsplit = max(1, min(nchunks, 444 // col_ctas))
-        nsplit = max(1, min(nsplit, nchunks))
-        self.dims = SpmDims(L, Lp, Nw, nrt, nb, npt, nplanes, nsplit, mt, int(batch_wide))
+            # whole columns per CTA (fused x-update + pass) when the batch alone fills the 148 SMs x 3
+            # resident CTAs; otherwise the balanced decomposition: the group-chunks are cut into equal
+            # contiguous pieces, one per resident CTA slot (then the x-update is a separate kernel)
+            ngroups = -(-npt // (4 * mt))
+            if ngroups >= 444:
+                nsplit = 1
+            else:
+                total = ngroups * nchunks
+                nbal = min(444, total)
+                nsplit = -(-nchunks * nbal // total) + 1
+        else:
+            nsplit = max(1, min(nsplit, nchunks))
+        self.dims = SpmDims(L, Lp, Nw, nrt, nb, npt, nplanes, nsplit, mt, nbal, int(batch_wide))
         self.batch_wide = bool(batch_wide)
         self.lam, self.max_mu = float(lam), float(max_mu)
         nprob = 8 * npt
@@ -409,7 +417,7 @@ class SharedSpM:
         timed = self.pass_events is not None and not do_update_mu
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if self.dims.nsplit == 1:
+        if self.dims.nsplit == 1 and self.dims.nbal == 0:
             if timed:
                 e0.record()
             call("admm_spm_step", dref, bref, st)
@@ -421,10 +429,12 @@ class SharedSpM:
         if timed:
             e1.record()
             self.pass_events.append((e0, e1))
+        if self.batch_wide and self.group is None:
+            call("admm_spm_reduce_decide", dref, bref, int(do_update_mu), st)
+            return
         if self.batch_wide:
             call("admm_spm_reduce", dref, bref, st)
-            if self.group is not None:
-                torch.distributed.all_reduce(self.gsum, group=self.group)
+            torch.distributed.all_reduce(self.gsum, group=self.group)
         call("admm_spm_decide", dref, bref, int(do_update_mu), st)
 
     def _after_update_iteration(self) -> bool:
@@ -512,7 +522,10 @@ class SharedSpM:
         _lib.launch_count += run * self._launches_per_iteration()
 
     def _launches_per_iteration(self) -> int:
-        return (1 if self.dims.nsplit == 1 else 2) + (2 if self.batch_wide else 0) + 1
+        data = 1 if (self.dims.nsplit == 1 and self.dims.nbal == 0) else 2
+        if self.batch_wide and self.group is None:
+            return data + 2
+        return data + (2 if self.batch_wide else 0) + 1
 
     # ------------------------------------------------------------------ objective
     def objective(self) -> float:

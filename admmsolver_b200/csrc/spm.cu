@@ -271,8 +271,10 @@ __device__ __forceinline__ void frag_gemm(double (&out)[NP][NT][2], const double
 // recursion of z = P^T Im(h20).  Re(x0) (new) is returned in registers for the pass.
 // y0 = P^T P x0_old must be current (spm_refresh_y_kernel after a state change).
 // Returns false when every problem of the tile is frozen (nothing was touched, x0 not loaded).
+// Handles planes p0 .. p0+NP-1 of the tile (plane 0 = real, plane 1 = imaginary parts).
 template <int NT, int NP, bool SPLIT>   // SPLIT: V arrives as d.nsplit partial sums (unfused small-batch path)
-__device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_spm_buffers& b, int pt, int lane) {
+__device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_spm_buffers& b, int pt, int lane,
+                                             int p0 = 0) {
   const int g = lane >> 2, t = lane & 3;
   const int prob = 8 * pt + g;
   const int is_done = b.done[prob];
@@ -280,8 +282,8 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
   const double mu10 = b.mu10[prob], mu20 = b.mu20[prob];
   const int slot = b.slot[prob];
   const int Lp = d.Lp;
-  const int ct0 = pt * NP;
-  const size_t vstride = (size_t)d.npt * NP * NT * 64;
+  const int ct0 = pt * d.nplanes + p0;
+  const size_t vstride = (size_t)d.npt * d.nplanes * NT * 64;
 
   // ---- rhs = alpha A^H y + h10 + mu10 x1 + P^T(h20 + mu20 x2)
   double x0[NP][NT][2];
@@ -289,7 +291,7 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
     double rhs[NP][NT][2];
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-      const int nsp = (SPLIT && p == 0) ? d.nsplit : 1;   // imaginary plane: z lives in split 0, owned by this function
+      const int nsp = (SPLIT && p0 + p == 0) ? d.nsplit : 1;   // imaginary plane: z lives in split 0, owned by this function
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         const size_t o = frag_index(ct0 + p, NT, j, lane);
@@ -338,7 +340,7 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
 #pragma unroll
       for (int j = 0; j < NT; ++j) cxi += b.Cvec[8 * j + 2 * t] * x0[p][j][0] + b.Cvec[8 * j + 2 * t + 1] * x0[p][j][1];
       cxi = quad_sum(cxi);
-      const double nu = (b.Dre[(size_t)p * 8 * d.npt + prob] - cxi) * isig;
+      const double nu = (b.Dre[(size_t)(p0 + p) * 8 * d.npt + prob] - cxi) * isig;
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         x0[p][j][0] += wv[8 * j + 2 * t] * nu;
@@ -383,17 +385,17 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
         }
     }
     // ---- imaginary plane: z <- z - mu20 y,  a += mu20 x0   (Im(h20) never leaves L-space)
-    if (p == 1 && !is_done) {
+    if (p0 + p == 1 && !is_done) {
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        const size_t o = frag_index(ct0 + 1, NT, j, lane);
+        const size_t o = frag_index(ct0 + p, NT, j, lane);
         double2 zv = *reinterpret_cast<const double2*>(b.V + o);
-        zv.x -= mu20 * y[1][j][0];
-        zv.y -= mu20 * y[1][j][1];
+        zv.x -= mu20 * y[p][j][0];
+        zv.y -= mu20 * y[p][j][1];
         *reinterpret_cast<double2*>(b.V + o) = zv;
         double2 av = *reinterpret_cast<const double2*>(b.aim + o);
-        av.x += mu20 * x0[1][j][0];
-        av.y += mu20 * x0[1][j][1];
+        av.x += mu20 * x0[p][j][0];
+        av.y += mu20 * x0[p][j][1];
         *reinterpret_cast<double2*>(b.aim + o) = av;
       }
     }
@@ -408,7 +410,7 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
       for (int e = 0; e < 2; ++e) {
         const double xv = x0[p][j][e], hv = e == 0 ? hh.x : hh.y;
         double z = 0.0;
-        if (p == 0) {
+        if (p0 + p == 0) {
           const double yv = -((hv - mu10 * xv) / mu10);
           if (yv > thr) z = yv - thr;
           if (yv < -thr) z = yv + thr;
@@ -449,12 +451,14 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
   return true;
 }
 
-template <int NT, int NP>
+// Stand-alone x-update (small batches): one warp per (problem tile, plane) -- the kernel is a chain of
+// dependent loads and two small GEMMs, so more, shorter warps finish sooner than fewer, longer ones.
+template <int NT>
 __global__ void __launch_bounds__(128) spm_xupdate_kernel(admm_spm_dims d, admm_spm_buffers b) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= d.npt) return;
-  xupdate_tile<NT, NP, true>(d, b, warp, lane);
+  if (warp >= d.npt * d.nplanes) return;
+  xupdate_tile<NT, 1, true>(d, b, warp / d.nplanes, lane, warp % d.nplanes);
 }
 
 // y0 = P^T P x0 for every column tile (after the state was loaded from outside)
@@ -499,33 +503,49 @@ struct PassSmem {
                                   PASS_STAGES * sizeof(unsigned) + 16;
 };
 
+// Work decomposition.  The unit is a "group-chunk": one chunk (32 sampling points) of one CTA tile
+// group (4*MT problem tiles); the state layout makes group-chunks of consecutive linear index
+// gc = group * nchunks + chunk consecutive 16 KB blocks.  A CTA processes the linear range
+// [g_begin, g_end):
+//   * classic grid (d.nbal == 0): blockIdx.x = group, blockIdx.y = split (equal chunk ranges);
+//   * balanced (d.nbal > 0, small batches): the T = ngroups * nchunks group-chunks are cut into d.nbal
+//     equal pieces, one per CTA, so that one wave of CTAs fills every SM equally; a CTA's range may
+//     straddle a group boundary, then it finishes the first group (epilogue) and starts the next.
+// Either way the partial V / norm sums of (group, piece) go to split slot `piece`; slots a group does
+// not use stay zero, the x-update sums all d.nsplit of them.
 template <int NT, int MT, int MODE, int FNP>   // FNP: 0 = pass only, 1/2 = fused x-update of 1/2 planes
 __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
     spm_pass_kernel(admm_spm_dims d, admm_spm_buffers b) {
   using SM = PassSmem<NT, MT>;
   constexpr int TILE_D = SM::TILE_D, CHUNK_D = SM::CHUNK_D, STATE_D = SM::STATE_D, STAGE_D = SM::STAGE_D;
   constexpr unsigned CHUNK_BYTES = CHUNK_D * sizeof(double), STATE_BYTES = STATE_D * sizeof(double);
+  constexpr int GT = PASS_WARPS * MT;
   extern __shared__ __align__(128) double ring[];       // [PASS_STAGES][P chunk | state chunk], then barriers
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + PASS_STAGES * STAGE_D);
   uint64_t* empty_bar = full_bar + PASS_STAGES;
   unsigned* ticket = reinterpret_cast<unsigned*>(empty_bar + PASS_STAGES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int nchunks_total = d.nrt / PASS_CHUNK_RT;
-  const int cps = (nchunks_total + d.nsplit - 1) / d.nsplit;  // chunks per split
-  const int sp = blockIdx.y;
-  const int c_begin = sp * cps, c_end = min(nchunks_total, c_begin + cps);
-  const int nchunks = max(0, c_end - c_begin);
+  const int nct = d.nrt / PASS_CHUNK_RT;                 // chunks per group
   const int npl = d.nplanes;
-  const double* Pf_src = b.Pf + (size_t)c_begin * CHUNK_D;
-  // the CTA's state chunks are contiguous blocks of S (state_index): [grp = blockIdx.x][chunk][...]
-  double* S_cta = b.S + ((size_t)blockIdx.x * nchunks_total + c_begin) * STATE_D;
+  long long g_begin, g_end;
+  if (d.nbal > 0) {
+    const long long T = (long long)((d.npt + GT - 1) / GT) * nct;
+    g_begin = (long long)blockIdx.x * T / d.nbal;
+    g_end = (long long)(blockIdx.x + 1) * T / d.nbal;
+  } else {
+    const int cps = (nct + d.nsplit - 1) / d.nsplit;     // chunks per split
+    const int c_begin = min(nct, (int)blockIdx.y * cps), c_end = min(nct, c_begin + cps);
+    g_begin = (long long)blockIdx.x * nct + c_begin;
+    g_end = (long long)blockIdx.x * nct + c_end;
+  }
+  const int nchunks = (int)(g_end - g_begin);
 
   // ---- barrier ring; the first chunks are in flight before anything else happens
-  auto fill = [&](int stage, int c) {
+  auto fill = [&](int stage, long long gc) {
     mbar_expect_tx(full_bar + stage, CHUNK_BYTES + STATE_BYTES);
-    tma_bulk_g2s(ring + stage * STAGE_D, Pf_src + (size_t)c * CHUNK_D, CHUNK_BYTES, full_bar + stage);
-    tma_bulk_g2s(ring + stage * STAGE_D + CHUNK_D, S_cta + (size_t)c * STATE_D, STATE_BYTES, full_bar + stage);
+    tma_bulk_g2s(ring + stage * STAGE_D, b.Pf + (size_t)(gc % nct) * CHUNK_D, CHUNK_BYTES, full_bar + stage);
+    tma_bulk_g2s(ring + stage * STAGE_D + CHUNK_D, b.S + (size_t)gc * STATE_D, STATE_BYTES, full_bar + stage);
   };
   if (tid == 0) {
     for (int s = 0; s < PASS_STAGES; ++s) {
@@ -537,23 +557,15 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
   }
   __syncthreads();
   if (tid == 0) {
-    for (int s = 0; s < PASS_STAGES && s < nchunks; ++s) fill(s, s);
+    for (int s = 0; s < PASS_STAGES && s < nchunks; ++s) fill(s, g_begin + s);
   }
 
-  // ---- this warp's MT problem tiles (real plane only: the imaginary plane lives in L-space)
-  int pt[MT];
-  bool inr[MT];
-  int dn[MT];
-  double mu20[MT];
-  double xa[MT][NT][2];      // A fragments of GEMM1': -mu20 * Re(x0)   (k-slot (j,e) of lane (g,t) <-> l = 8j+2t+e)
-  double acc[MT][NT][2];     // C fragments of GEMM2': V
-  bool all_done = true;
-  const int wpt0 = (blockIdx.x * PASS_WARPS + warp) * MT;
   if (FNP != 0) {
     // x-update of this warp's tiles right here (all planes): x0 reaches the MMA operand registers
     // through L1/L2; the pass of the other CTAs of the SM hides the latency of this L x L work.
     // The L-vectors of the tiles are pulled into L2 up front (one bulk prefetch per vector).
     constexpr int NPL = FNP == 0 ? 1 : FNP;
+    const int wpt0 = (blockIdx.x * PASS_WARPS + warp) * MT;
     {
       const double* vec = lane == 0 ? b.b0 : lane == 1 ? b.h10 : lane == 2 ? b.x1 : lane == 3 ? b.V
                         : lane == 4 ? b.x0 : lane == 5 ? b.y0 : b.aim;
@@ -563,156 +575,183 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
     }
 #pragma unroll 1
     for (int m = 0; m < MT; ++m) {
-      if (wpt0 + m < d.npt) xupdate_tile<NT, NPL, false>(d, b, wpt0 + m, lane);
+      if (wpt0 + m < d.npt) xupdate_tile<NT, NPL, false>(d, b, wpt0 + m, lane, 0);
     }
-  }
-#pragma unroll
-  for (int m = 0; m < MT; ++m) {
-    pt[m] = wpt0 + m;
-    inr[m] = pt[m] < d.npt;
-    if (!inr[m]) pt[m] = d.npt - 1;        // clamp: loads stay in range, stores are suppressed
-    const int prob = 8 * pt[m] + g;
-    dn[m] = inr[m] ? b.done[prob] : 1;
-    mu20[m] = b.mu20[prob];
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      const double2 v = *reinterpret_cast<const double2*>(b.x0 + frag_index(pt[m] * npl, NT, j, lane));
-      xa[m][j][0] = -mu20[m] * v.x;
-      xa[m][j][1] = -mu20[m] * v.y;
-      acc[m][j][0] = acc[m][j][1] = 0.0;
-    }
-    all_done = all_done && dn[m];
-  }
-  const bool active = !__all_sync(0xffffffffu, all_done);
-
-  double n_dh[MT], n_xm[MT], ratio[MT];
-#pragma unroll
-  for (int m = 0; m < MT; ++m) {
-    n_dh[m] = n_xm[m] = 0.0;
-    ratio[m] = MODE == PASS_VINIT ? mu20[m] / b.mu20_used[8 * pt[m] + g] : 1.0;
   }
 
   // this lane's slot inside a state chunk, in shared memory (read) and in global memory (write back)
   const int st_off = warp * SM::WARP_STATE_D + lane * 2;
-  double* Sg = S_cta + st_off;
+  const int nctc = d.npt * npl;
+  const size_t vstride = (size_t)nctc * NT * 64;
 
   int stage = 0;
   unsigned parity = 0;
-  for (int c = 0; c < nchunks; ++c) {
-    mbar_wait(full_bar + stage, parity);      // idle warps wait too: nobody runs ahead of the ring
-    if (active) {
-      const double* Pc = ring + stage * STAGE_D + lane * 2;
-      const double* Sc = ring + stage * STAGE_D + CHUNK_D + st_off;
-#pragma unroll
-      for (int r4 = 0; r4 < PASS_CHUNK_RT; ++r4) {
-        const double* P1 = Pc + r4 * TILE_D;        // GEMM1' operand: [j][lane][2]
-        const double* P2 = P1 + NT * 64;            // GEMM2' operand: [j][lane][2]
-        double2 st[MT];
-#pragma unroll
-        for (int m = 0; m < MT; ++m) st[m] = *reinterpret_cast<const double2*>(Sc + (m * PASS_CHUNK_RT + r4) * 64);
+  long long gc = g_begin;
+#pragma unroll 1
+  while (gc < g_end) {
+    // ================= one segment: chunks [gc, seg_end) of tile group `grp` =================
+    const int grp = (int)(gc / nct);
+    const long long seg_end = min(g_end, (long long)(grp + 1) * nct);
+    int piece;                                           // split slot of this (group, range)
+    if (d.nbal > 0) {
+      const long long T = (long long)((d.npt + GT - 1) / GT) * nct;
+      const long long x = (long long)grp * nct;          // first group-chunk of the group
+      piece = (int)blockIdx.x - (int)(((x + 1) * d.nbal - 1) / T);
+    } else {
+      piece = blockIdx.y;
+    }
 
-        double u[MT][2];
-        if (MODE == PASS_STEP) {
-          // ---- GEMM1': s' = max(0,s) - mu20 * (P x0)   (accumulator starts at Re h20 = max(0,s))
-          double q[MT][2], q2[MT][2], hre[MT][2];
+    // ---- this warp's MT problem tiles (real plane only: the imaginary plane lives in L-space)
+    int pt[MT];
+    bool inr[MT];
+    int dn[MT];
+    double mu20[MT];
+    double xa[MT][NT][2];      // A fragments of GEMM1': -mu20 * Re(x0)   (k-slot (j,e) of lane (g,t) <-> l = 8j+2t+e)
+    double acc[MT][NT][2];     // C fragments of GEMM2': V
+    bool all_done = true;
 #pragma unroll
-          for (int m = 0; m < MT; ++m) {
-            hre[m][0] = is_neg(st[m].x) ? 0.0 : st[m].x;
-            hre[m][1] = is_neg(st[m].y) ? 0.0 : st[m].y;
-            q[m][0] = hre[m][0];
-            q[m][1] = hre[m][1];
-            q2[m][0] = q2[m][1] = 0.0;
-          }
+    for (int m = 0; m < MT; ++m) {
+      pt[m] = (grp * PASS_WARPS + warp) * MT + m;
+      inr[m] = pt[m] < d.npt;
+      if (!inr[m]) pt[m] = d.npt - 1;        // clamp: loads stay in range, stores are suppressed
+      const int prob = 8 * pt[m] + g;
+      dn[m] = inr[m] ? b.done[prob] : 1;
+      mu20[m] = b.mu20[prob];
 #pragma unroll
-          for (int j = 0; j < NT; ++j) {
-            const double2 bb = *reinterpret_cast<const double2*>(P1 + j * 64);
+      for (int j = 0; j < NT; ++j) {
+        const double2 v = *reinterpret_cast<const double2*>(b.x0 + frag_index(pt[m] * npl, NT, j, lane));
+        xa[m][j][0] = -mu20[m] * v.x;
+        xa[m][j][1] = -mu20[m] * v.y;
+        acc[m][j][0] = acc[m][j][1] = 0.0;
+      }
+      all_done = all_done && dn[m];
+    }
+    const bool active = !__all_sync(0xffffffffu, all_done);
+
+    double n_dh[MT], n_xm[MT], ratio[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      n_dh[m] = n_xm[m] = 0.0;
+      ratio[m] = MODE == PASS_VINIT ? mu20[m] / b.mu20_used[8 * pt[m] + g] : 1.0;
+    }
+    double* Sg = b.S + (size_t)gc * STATE_D + st_off;
+
+#pragma unroll 1
+    for (; gc < seg_end; ++gc) {
+      mbar_wait(full_bar + stage, parity);      // idle warps wait too: nobody runs ahead of the ring
+      if (active) {
+        const double* Pc = ring + stage * STAGE_D + lane * 2;
+        const double* Sc = ring + stage * STAGE_D + CHUNK_D + st_off;
+#pragma unroll
+        for (int r4 = 0; r4 < PASS_CHUNK_RT; ++r4) {
+          const double* P1 = Pc + r4 * TILE_D;        // GEMM1' operand: [j][lane][2]
+          const double* P2 = P1 + NT * 64;            // GEMM2' operand: [j][lane][2]
+          double2 st[MT];
+#pragma unroll
+          for (int m = 0; m < MT; ++m) st[m] = *reinterpret_cast<const double2*>(Sc + (m * PASS_CHUNK_RT + r4) * 64);
+
+          double u[MT][2];
+          if (MODE == PASS_STEP) {
+            // ---- GEMM1': s' = max(0,s) - mu20 * (P x0)   (accumulator starts at Re h20 = max(0,s))
+            double q[MT][2], q2[MT][2], hre[MT][2];
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
-              if (MT == 1) {      // a single tile per warp: two chains hide the DMMA latency
-                dmma(q[m][0], q[m][1], xa[m][j][0], bb.x);
-                dmma(q2[m][0], q2[m][1], xa[m][j][1], bb.y);
-              } else {
-                dmma(q[m][0], q[m][1], xa[m][j][0], bb.x);
-                dmma(q[m][0], q[m][1], xa[m][j][1], bb.y);
+              hre[m][0] = is_neg(st[m].x) ? 0.0 : st[m].x;
+              hre[m][1] = is_neg(st[m].y) ? 0.0 : st[m].y;
+              q[m][0] = hre[m][0];
+              q[m][1] = hre[m][1];
+              q2[m][0] = q2[m][1] = 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+              const double2 bb = *reinterpret_cast<const double2*>(P1 + j * 64);
+#pragma unroll
+              for (int m = 0; m < MT; ++m) {
+                if (MT == 1) {      // a single tile per warp: two chains hide the DMMA latency
+                  dmma(q[m][0], q[m][1], xa[m][j][0], bb.x);
+                  dmma(q2[m][0], q2[m][1], xa[m][j][1], bb.y);
+                } else {
+                  dmma(q[m][0], q[m][1], xa[m][j][0], bb.x);
+                  dmma(q[m][0], q[m][1], xa[m][j][1], bb.y);
+                }
               }
             }
-          }
-          // ---- elementwise: s' encodes both the dual ascent and the non-negative projection
-          //   Re h20' = max(0, s'),  mu20 x2' = max(0, -s'),  mu20 (P x0 - x2') = Re h20 - Re h20'
+            // ---- elementwise: s' encodes both the dual ascent and the non-negative projection
+            //   Re h20' = max(0, s'),  mu20 x2' = max(0, -s'),  mu20 (P x0 - x2') = Re h20 - Re h20'
 #pragma unroll
-          for (int m = 0; m < MT; ++m) {
-            double sn[2];
+            for (int m = 0; m < MT; ++m) {
+              double sn[2];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const double s_new = MT == 1 ? q[m][e] + q2[m][e] : q[m][e];
-              const bool neg = is_neg(s_new);
-              const double hnew = neg ? 0.0 : s_new;
-              const double xm = neg ? s_new : 0.0;
-              const double dh = hre[m][e] - hnew;
-              n_dh[m] += dh * dh;
-              n_xm[m] += xm * xm;
-              u[m][e] = fabs(s_new);
-              sn[e] = dn[m] ? (e == 0 ? st[m].x : st[m].y) : s_new;
+              for (int e = 0; e < 2; ++e) {
+                const double s_new = MT == 1 ? q[m][e] + q2[m][e] : q[m][e];
+                const bool neg = is_neg(s_new);
+                const double hnew = neg ? 0.0 : s_new;
+                const double xm = neg ? s_new : 0.0;
+                const double dh = hre[m][e] - hnew;
+                n_dh[m] += dh * dh;
+                n_xm[m] += xm * xm;
+                u[m][e] = fabs(s_new);
+                sn[e] = dn[m] ? (e == 0 ? st[m].x : st[m].y) : s_new;
+              }
+              st_stream2(Sg + (m * PASS_CHUNK_RT + r4) * 64, make_double2(sn[0], sn[1]));
             }
-            st_stream2(Sg + (m * PASS_CHUNK_RT + r4) * 64, make_double2(sn[0], sn[1]));
-          }
-        } else {
-          // V from the current state, no step:  u = Re h20 + mu20 x2  with x2 decoded by mu20_used
+          } else {
+            // V from the current state, no step:  u = Re h20 + mu20 x2  with x2 decoded by mu20_used
 #pragma unroll
-          for (int m = 0; m < MT; ++m) {
-            u[m][0] = is_neg(st[m].x) ? -st[m].x * ratio[m] : st[m].x;
-            u[m][1] = is_neg(st[m].y) ? -st[m].y * ratio[m] : st[m].y;
+            for (int m = 0; m < MT; ++m) {
+              u[m][0] = is_neg(st[m].x) ? -st[m].x * ratio[m] : st[m].x;
+              u[m][1] = is_neg(st[m].y) ? -st[m].y * ratio[m] : st[m].y;
+            }
+          }
+
+          // ---- GEMM2': V[c][l] += sum_r u[c][r] P[r][l],  k-slot t of step e <-> row 2t+e
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            const double2 bb = *reinterpret_cast<const double2*>(P2 + j * 64);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) dmma(acc[m][j][0], acc[m][j][1], u[m][0], bb.x);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) dmma(acc[m][j][0], acc[m][j][1], u[m][1], bb.y);
           }
         }
+      }
+      Sg += STATE_D;
 
-        // ---- GEMM2': V[c][l] += sum_r u[c][r] P[r][l],  k-slot t of step e <-> row 2t+e
+      // ---- release the stage; the warp that arrives last refills it with chunk gc + PASS_STAGES
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(empty_bar + stage);
+        const unsigned tk = atomicAdd(ticket + stage, 1u);
+        if ((tk & (PASS_WARPS - 1)) == PASS_WARPS - 1 && gc + PASS_STAGES < g_end) {
+          mbar_wait(empty_bar + stage, parity);
+          fill(stage, gc + PASS_STAGES);
+        }
+      }
+      if (++stage == PASS_STAGES) {
+        stage = 0;
+        parity ^= 1u;
+      }
+    }
+
+    // ---- epilogue of the segment: partial V (fragment layout) and per-column norm partials
+    if (active) {
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        if (!inr[m]) continue;
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
-          const double2 bb = *reinterpret_cast<const double2*>(P2 + j * 64);
-#pragma unroll
-          for (int m = 0; m < MT; ++m) dmma(acc[m][j][0], acc[m][j][1], u[m][0], bb.x);
-#pragma unroll
-          for (int m = 0; m < MT; ++m) dmma(acc[m][j][0], acc[m][j][1], u[m][1], bb.y);
+          const size_t o = piece * vstride + frag_index(pt[m] * npl, NT, j, lane);
+          *reinterpret_cast<double2*>(b.V + o) = make_double2(acc[m][j][0], acc[m][j][1]);
         }
-      }
-    }
-    Sg += STATE_D;
-
-    // ---- release the stage; the warp that arrives last refills it with chunk c + PASS_STAGES
-    __syncwarp();
-    if (lane == 0) {
-      mbar_arrive(empty_bar + stage);
-      const unsigned tk = atomicAdd(ticket + stage, 1u);
-      if ((tk & (PASS_WARPS - 1)) == PASS_WARPS - 1 && c + PASS_STAGES < nchunks) {
-        mbar_wait(empty_bar + stage, parity);
-        fill(stage, c + PASS_STAGES);
-      }
-    }
-    if (++stage == PASS_STAGES) {
-      stage = 0;
-      parity ^= 1u;
-    }
-  }
-  if (!active) return;
-
-  // ---- epilogue: partial V (fragment layout) and per-column norm partials
-  const int nct = d.npt * npl;
-  const size_t vstride = (size_t)nct * NT * 64;
-#pragma unroll
-  for (int m = 0; m < MT; ++m) {
-    if (!inr[m]) continue;
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      const size_t o = sp * vstride + frag_index(pt[m] * npl, NT, j, lane);
-      *reinterpret_cast<double2*>(b.V + o) = make_double2(acc[m][j][0], acc[m][j][1]);
-    }
-    if (MODE == PASS_STEP) {
-      const double inv = 1.0 / mu20[m];
-      const double s0 = quad_sum(n_dh[m]) * inv * inv, s1 = quad_sum(n_xm[m]) * inv * inv;
-      if (t == 0 && !dn[m]) {
-        double* o = b.normsB + ((size_t)sp * nct * 8 + (size_t)(pt[m] * npl) * 8 + g) * 2;
-        o[0] = s0;      // |P Re(x0) - x2|^2
-        o[1] = s1;      // |x2|^2
+        if (MODE == PASS_STEP) {
+          const double inv = 1.0 / mu20[m];
+          const double s0 = quad_sum(n_dh[m]) * inv * inv, s1 = quad_sum(n_xm[m]) * inv * inv;
+          if (t == 0 && !dn[m]) {
+            double* o = b.normsB + ((size_t)piece * nctc * 8 + (size_t)(pt[m] * npl) * 8 + g) * 2;
+            o[0] = s0;      // |P Re(x0) - x2|^2
+            o[1] = s1;      // |x2|^2
+          }
+        }
       }
     }
   }
@@ -780,17 +819,9 @@ __device__ __forceinline__ double mu_step(double mu, double primal, double dual,
   return fmin(mu, b.max_mu);
 }
 
-__global__ void __launch_bounds__(128) spm_decide_kernel(admm_spm_dims d, admm_spm_buffers b, int do_update_mu) {
-  const int prob = blockIdx.x * blockDim.x + threadIdx.x;
-  if (prob >= d.nb) return;
-  if (b.done[prob]) return;
-  double s[10];
-  if (d.batch_wide) {
-#pragma unroll
-    for (int i = 0; i < 10; ++i) s[i] = b.gsum[i];
-  } else {
-    gather_problem(d, b, prob, s);
-  }
+// residual() / check_convergence() / update_mu() of ONE problem from its ten squared norms
+__device__ __forceinline__ void decide_one(const admm_spm_dims& d, const admm_spm_buffers& b, int prob, const double (&s)[10],
+                                           int do_update_mu) {
   const double mu10 = b.mu10[prob], mu20 = b.mu20[prob];
   const double p10 = sqrt(s[0]), nx0 = sqrt(s[1]), nx1 = sqrt(s[2]), nd = sqrt(s[3]), nxo = sqrt(s[4]);
   const double nPd = sqrt(s[5]), nPxo = sqrt(s[6]), p20 = sqrt(s[7]), nx2 = sqrt(s[8]), nPx0 = sqrt(s[9]);
@@ -826,6 +857,32 @@ __global__ void __launch_bounds__(128) spm_decide_kernel(admm_spm_dims d, admm_s
   }
 }
 
+// nparts > 0 (batch-wide, unsharded): gsum has not been formed yet -- every CTA adds the nparts
+// stage-1 partials itself, in the same fixed order (saves the stage-2 launch of a short iteration).
+__global__ void __launch_bounds__(128) spm_decide_kernel(admm_spm_dims d, admm_spm_buffers b, int do_update_mu, int nparts) {
+  __shared__ double gs[10];
+  if (nparts > 0) {
+    if (threadIdx.x < 10) {
+      double a = 0.0;
+      for (int p = 0; p < nparts; ++p) a += b.gpart[p * 16 + threadIdx.x];
+      gs[threadIdx.x] = a;
+      if (blockIdx.x == 0) b.gsum[threadIdx.x] = a;
+    }
+    __syncthreads();
+  }
+  const int prob = blockIdx.x * blockDim.x + threadIdx.x;
+  if (prob >= d.nb) return;
+  if (b.done[prob]) return;
+  double s[10];
+  if (d.batch_wide) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) s[i] = nparts > 0 ? gs[i] : b.gsum[i];
+  } else {
+    gather_problem(d, b, prob, s);
+  }
+  decide_one(d, b, prob, s, do_update_mu);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
@@ -838,7 +895,15 @@ static int check_dims(const admm_spm_dims* d, const char* who) {
   ADMM_REQUIRE(d->nb >= 1 && d->npt * 8 >= d->nb, ADMM_EINVAL, "%s: bad nb/npt", who);
   ADMM_REQUIRE(d->nplanes == 1 || d->nplanes == 2, ADMM_EINVAL, "%s: nplanes must be 1 or 2", who);
   ADMM_REQUIRE(d->mt == 1 || (d->mt == 2 && d->Lp <= 40), ADMM_EINVAL, "%s: mt must be 1, or 2 with Lp <= 40", who);
-  ADMM_REQUIRE(d->nsplit >= 1 && d->nsplit <= d->nrt / PASS_CHUNK_RT, ADMM_EINVAL, "%s: bad nsplit=%d", who, d->nsplit);
+  ADMM_REQUIRE(d->nsplit >= 1 && (d->nbal > 0 || d->nsplit <= d->nrt / PASS_CHUNK_RT), ADMM_EINVAL, "%s: bad nsplit=%d", who,
+               d->nsplit);
+  if (d->nbal > 0) {
+    const long long T = (long long)ceil_div(d->npt, 4 * d->mt) * (d->nrt / PASS_CHUNK_RT);
+    ADMM_REQUIRE(d->nbal <= T, ADMM_EINVAL, "%s: nbal=%d exceeds the %lld group-chunks", who, d->nbal, T);
+    const long long kmax = ((long long)(d->nrt / PASS_CHUNK_RT) * d->nbal + T - 1) / T + 1;
+    ADMM_REQUIRE(d->nsplit >= kmax, ADMM_EINVAL, "%s: balanced decomposition needs nsplit >= %lld (got %d)", who, kmax,
+                 d->nsplit);
+  }
   return ADMM_OK;
 }
 
@@ -846,7 +911,7 @@ static int ew_grid(long long n) { return (int)std::max<long long>(1, std::min<lo
 
 template <int NT, int MT, int MODE, int FNP>
 static int launch_pass_k(const admm_spm_dims* d, const admm_spm_buffers* b, cudaStream_t s) {
-  dim3 grid(ceil_div(d->npt, PASS_WARPS * MT), d->nsplit);
+  const dim3 grid = d->nbal > 0 ? dim3(d->nbal, 1) : dim3(ceil_div(d->npt, PASS_WARPS * MT), d->nsplit);
   const size_t smem = PassSmem<NT, MT>::BYTES;
   auto k = spm_pass_kernel<NT, MT, MODE, FNP>;
   static bool configured = false;     // per instantiation
@@ -955,21 +1020,11 @@ int admm_spm_refresh_y(const admm_spm_dims* d, const admm_spm_buffers* b, admm_s
 int admm_spm_xupdate(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_xupdate")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int grid = ceil_div(d->npt, 4);
-  const bool two = d->nplanes == 2;
+  const int grid = ceil_div(d->npt * d->nplanes, 4);
   switch (d->Lp / 8) {
-    case 2:
-      if (two) spm_xupdate_kernel<2, 2><<<grid, 128, 0, s>>>(*d, *b);
-      else spm_xupdate_kernel<2, 1><<<grid, 128, 0, s>>>(*d, *b);
-      break;
-    case 5:
-      if (two) spm_xupdate_kernel<5, 2><<<grid, 128, 0, s>>>(*d, *b);
-      else spm_xupdate_kernel<5, 1><<<grid, 128, 0, s>>>(*d, *b);
-      break;
-    default:
-      if (two) spm_xupdate_kernel<8, 2><<<grid, 128, 0, s>>>(*d, *b);
-      else spm_xupdate_kernel<8, 1><<<grid, 128, 0, s>>>(*d, *b);
-      break;
+    case 2: spm_xupdate_kernel<2><<<grid, 128, 0, s>>>(*d, *b); break;
+    case 5: spm_xupdate_kernel<5><<<grid, 128, 0, s>>>(*d, *b); break;
+    default: spm_xupdate_kernel<8><<<grid, 128, 0, s>>>(*d, *b); break;
   }
   return check_launch("admm_spm_xupdate");
 }
@@ -982,14 +1037,17 @@ int admm_spm_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, a
 
 int admm_spm_step(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_step")) return rc;
-  ADMM_REQUIRE(d->nsplit == 1, ADMM_EINVAL, "admm_spm_step: the fused x-update + pass needs nsplit == 1 (got %d)", d->nsplit);
+  ADMM_REQUIRE(d->nsplit == 1 && d->nbal == 0, ADMM_EINVAL,
+               "admm_spm_step: the fused x-update + pass needs whole columns per CTA (nsplit == 1, nbal == 0)");
   return launch_pass(d, b, PASS_STEP, true, static_cast<cudaStream_t>(stream));
 }
+
+static int reduce_parts(const admm_spm_dims* d) { return std::max(1, std::min(256, ceil_div(d->nb, 256))); }
 
 int admm_spm_reduce(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_reduce")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int parts = std::max(1, std::min(256, ceil_div(d->nb, 256)));
+  const int parts = reduce_parts(d);
   spm_reduce_stage1<<<parts, 256, 0, s>>>(*d, *b);
   spm_reduce_stage2<<<1, 256, 0, s>>>(parts, *b);
   return check_launch("admm_spm_reduce");
@@ -997,8 +1055,18 @@ int admm_spm_reduce(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stre
 
 int admm_spm_decide(const admm_spm_dims* d, const admm_spm_buffers* b, int do_update_mu, admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_decide")) return rc;
-  spm_decide_kernel<<<ceil_div(d->nb, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(*d, *b, do_update_mu);
+  spm_decide_kernel<<<ceil_div(d->nb, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(*d, *b, do_update_mu, 0);
   return check_launch("admm_spm_decide");
+}
+
+int admm_spm_reduce_decide(const admm_spm_dims* d, const admm_spm_buffers* b, int do_update_mu, admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_reduce_decide")) return rc;
+  ADMM_REQUIRE(d->batch_wide, ADMM_EINVAL, "admm_spm_reduce_decide: batch-wide criterion only");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int parts = reduce_parts(d);
+  spm_reduce_stage1<<<parts, 256, 0, s>>>(*d, *b);
+  spm_decide_kernel<<<ceil_div(d->nb, 128), 128, 0, s>>>(*d, *b, do_update_mu, parts);
+  return check_launch("admm_spm_reduce_decide");
 }
 
 }  // extern "C"

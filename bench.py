@@ -335,7 +335,7 @@ def run_ours(args):
         #         sampling point (the imaginary half of the state is advanced in L-space)
         #   x-update (fused only): per plane Ginv*rhs and PtP*x0 = 2 * 2 L^2 flop; per plane 6 L-vectors read
         #         and 4 written, plus z and a of the imaginary plane (2 read, 2 written)
-        fused = eng.dims.nsplit == 1
+        fused = eng.dims.nsplit == 1 and eng.dims.nbal == 0
         npl = eng.dims.nplanes
         flops_per_unit = 4.0 * L * Nw + (4.0 * L * L * npl if fused else 0.0)
         bytes_per_unit = 16.0 * Nw + (8.0 * L * (10 * npl + (4 if npl == 2 else 0)) if fused else 0.0)

@@ -117,8 +117,12 @@ typedef struct admm_spm_dims {
   int nb;       /* number of problems                                                          */
   int npt;      /* number of 8-problem tiles = ceil(nb / 8)                                    */
   int nplanes;  /* 1: real data (imaginary parts identically zero), 2: complex128 state        */
-  int nsplit;   /* row splits of the pass kernel (partial V sums)                              */
+  int nsplit;   /* number of partial-sum slots of V / normsB per problem tile: the row splits of the
+                   classic grid, or the bound on pieces per tile group of the balanced one       */
   int mt;       /* problem tiles per warp in the pass kernel (1 or 2)                          */
+  int nbal;     /* 0: classic grid (tile groups x nsplit equal row ranges).  > 0: balanced decomposition
+                   for small batches -- the ceil(npt/(4 mt)) * (nrt/4) group-chunks are cut into nbal
+                   equal contiguous pieces, one CTA each (one wave that loads every SM equally)   */
   int batch_wide; /* 1: mu and the stopping test use norms over the whole batch (packed
                      reference semantics), 0: per-problem mu / stopping                        */
 } admm_spm_dims;
@@ -247,6 +251,12 @@ int admm_spm_step(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream
 /* Batch-wide norms: deterministic two-stage sum over all problems into gsum[16].  The caller
  * all-reduces gsum across ranks (NCCL) before admm_spm_decide when the batch is sharded. */
 int admm_spm_reduce(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream_t stream);
+
+/* admm_spm_reduce + admm_spm_decide for an unsharded batch with the batch-wide criterion in two
+ * launches instead of three: every CTA of the decide kernel adds the stage-1 partials itself (same
+ * fixed order).  The sharded case needs gsum in memory for the NCCL all-reduce: use the two calls. */
+int admm_spm_reduce_decide(const admm_spm_dims* d, const admm_spm_buffers* b, int do_update_mu,
+                           admm_stream_t stream);
 
 /* residual() / check_convergence() / update_mu() (optimizer.py:232-299) per problem or
  * batch-wide; increments iter_counter; appends to history. */

@@ -134,7 +134,7 @@ class SharedSpM:
                 nsplit = 1
             else:
                 total = ngroups * nchunks
-                nbal = min(444, total)
+                nbal = min(444, total, 16 * ngroups)      # at most ~16 partial sums per tile for the x-update
                 nsplit = -(-nchunks * nbal // total) + 1
         else:
             nsplit = max(1, min(nsplit, nchunks))

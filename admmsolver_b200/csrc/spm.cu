@@ -299,7 +299,7 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
         const double2 hh = *reinterpret_cast<const double2*>(b.h10 + o);
         const double2 x1 = *reinterpret_cast<const double2*>(b.x1 + o);
         double2 v = *reinterpret_cast<const double2*>(b.V + o);
-#pragma unroll 1
+#pragma unroll 4
         for (int sp = 1; sp < nsp; ++sp) {
           const double2 q = *reinterpret_cast<const double2*>(b.V + sp * vstride + o);
           v.x += q.x;

@@ -4,8 +4,12 @@
 // x-update uses a cached inverse (Woodbury M x M when M < N, direct N x N otherwise).
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstdlib>
+
+namespace cg = cooperative_groups;
 
 namespace admm {
 
@@ -293,16 +297,22 @@ struct BpfSmem {
   static constexpr int STAGE_D = ROWS * BPF_TN;
   static size_t bytes(int N) {
     const int Np = (N + 1) & ~1;
-    return (size_t)(BPF_STAGES * STAGE_D + 5 * Np + 2 * ROWS + NW * BPF_TN + BPF_TN + 5 * 32) * sizeof(double) +
+    return (size_t)(BPF_STAGES * STAGE_D + 5 * Np + 2 * ROWS + NW * BPF_TN + BPF_TN + 5 * 32 + 2 * (ROWS + 8)) * sizeof(double) +
            BPF_STAGES * sizeof(uint64_t) + 16;
   }
 };
 
-template <int NW>
+// CS > 1: ONE problem is spread over a thread-block cluster of CS CTAs (few problems, many idle SMs):
+// CTA c streams the column tiles k = c, c+CS, ... and owns those columns of x0 / x1 / h; per iteration
+// the partial t = A r' vectors and the five norm partials are exchanged through distributed shared
+// memory (each CTA sums the CS partial buffers of its peers in fixed rank order, so every CTA holds
+// bit-identical t and norms and takes the same decisions) with one cluster barrier.
+template <int NW, int CS>
 __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) bp_fused_kernel(admm_bp_buffers b, int iter_end) {
   extern __shared__ __align__(128) double sm[];
   constexpr int ROWS = BpfSmem<NW>::ROWS, STAGE_D = BpfSmem<NW>::STAGE_D, NT_ = NW * 32;
-  const int prob = blockIdx.x;
+  const int prob = CS > 1 ? blockIdx.x / CS : blockIdx.x;
+  const int crank = CS > 1 ? (int)(blockIdx.x % CS) : 0;
   if (b.done[prob] || b.need_factor[prob]) return;
   int it = b.iters[prob];
   if (it >= iter_end) return;
@@ -319,9 +329,11 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) bp_fused_kernel(admm
   double* part = sv + ROWS;                        // NW x TN  per-warp partial column dots
   double* rn = part + NW * BPF_TN;                 // TN   r' of the current tile
   double* scratch = rn + BPF_TN;                   // 5*32
-  uint64_t* full = reinterpret_cast<uint64_t*>(scratch + 5 * 32);
+  double* xch = scratch + 5 * 32;                  // [2][ROWS + 8] partial t and norms for the cluster exchange
+  uint64_t* full = reinterpret_cast<uint64_t*>(xch + 2 * (ROWS + 8));
   const double* Kinv = b.Kinv + (size_t)prob * M * M;
   const int T = (N + BPF_TN - 1) / BPF_TN;          // tiles per sweep
+  const int Tl = CS > 1 ? (T - crank + CS - 1) / CS : T;      // tiles of this CTA: k = crank + j*CS
   const double* At = b.At + (size_t)prob * T * M * BPF_TN;     // tile-major copy of A (bp_tile_A_kernel)
   const unsigned TILE_BYTES = (unsigned)(M * BPF_TN * sizeof(double));
 
@@ -344,8 +356,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) bp_fused_kernel(admm
 
   // tile `gt` of the endless stream (sweep after sweep) -> stage gt % STAGES
   auto issue = [&](int gt) {
-    if (tid == 0) {
-      const int k = gt % T, sidx = gt % BPF_STAGES;
+    if (tid == 0 && Tl > 0) {
+      const int k = crank + (gt % Tl) * CS, sidx = gt % BPF_STAGES;
       fence_proxy_async();
       mbar_expect_tx(full + sidx, TILE_BYTES);
       tma_bulk_g2s(stage + sidx * STAGE_D, At + (size_t)k * M * BPF_TN, TILE_BYTES, full + sidx);
@@ -358,6 +370,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) bp_fused_kernel(admm
   int done = 0, need = 0;
   double primal = 0.0, dual = 0.0;
   bool first = true;          // first sweep of this launch: only t = A r
+  int xphase = 0;             // ping-pong index of the cluster exchange buffer
   while (true) {
     // ---- s = K^-1 t for this warp's rows, kept in shared memory (only this warp reads them back).
     // The loads of 8 rows are issued together: two L2 round trips per iteration instead of sixteen.
@@ -412,7 +425,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) bp_fused_kernel(admm
       }
     }
 
-    for (int k = 0; k < T; ++k, ++gt) {
+    for (int kl = 0; kl < Tl; ++kl, ++gt) {
+      const int k = crank + kl * CS;
       const int sidx = gt % BPF_STAGES;
       mbar_wait(full + sidx, (unsigned)((gt / BPF_STAGES) & 1));
       const double* tile = stage + sidx * STAGE_D + (warp * BPF_RW) * BPF_TN + lane;
@@ -480,20 +494,48 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) bp_fused_kernel(admm
     // ---- t' = A r' : rows are owned by warps, columns were spread over lanes and tiles
 #pragma unroll
     for (int i = 0; i < BPF_RW; ++i) acc[i] = warp_sum(acc[i]);
-    if (lane == 0) {
+    if (CS == 1) {
+      if (lane == 0) {
 #pragma unroll
-      for (int i = 0; i < BPF_RW; ++i) tv[warp * BPF_RW + i] = acc[i];
-    }
-    if (first) {
-      first = false;
+        for (int i = 0; i < BPF_RW; ++i) tv[warp * BPF_RW + i] = acc[i];
+      }
+      if (first) {
+        first = false;
+        __syncthreads();
+        continue;
+      }
+      block_sum<5>(v, scratch);              // (syncs: tv is visible afterwards)
+    } else {
+      // cluster exchange: my partial t and norm partials -> xch[xphase]; everyone sums all CS buffers
+      double* mine = xch + xphase * (ROWS + 8);
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < BPF_RW; ++i) mine[warp * BPF_RW + i] = acc[i];
+      }
+      block_sum<5>(v, scratch);
+      if (tid < 5) mine[ROWS + tid] = v[tid];
+      cg::cluster_group cluster = cg::this_cluster();
+      cluster.sync();
+      for (int i = tid; i < ROWS + 5; i += NT_) {
+        double a = 0.0;
+#pragma unroll
+        for (int c = 0; c < CS; ++c) a += cluster.map_shared_rank(mine, c)[i];
+        if (i < ROWS) tv[i] = a;
+        else scratch[i - ROWS] = a;
+      }
+      xphase ^= 1;
       __syncthreads();
-      continue;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) v[i] = scratch[i];
+      if (first) {
+        first = false;
+        continue;
+      }
     }
-    block_sum<5>(v, scratch);              // (syncs: tv is visible afterwards)
     const double p = sqrt(v[0]), nx0 = sqrt(v[1]), nx1 = sqrt(v[2]), nd = sqrt(v[3]), nxo = sqrt(v[4]);
     primal = p;
     dual = mu * nd;
-    if (b.history && it < b.hist_cap && tid == 0) {
+    if (b.history && it < b.hist_cap && tid == 0 && crank == 0) {
       b.history[((size_t)prob * b.hist_cap + it) * 2] = primal;
       b.history[((size_t)prob * b.hist_cap + it) * 2 + 1] = dual;
     }
@@ -519,14 +561,17 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) bp_fused_kernel(admm
     __syncthreads();
   }
   // drain the tiles still in flight before the shared memory goes away
-  for (int g2 = gt; g2 < gt + BPF_STAGES; ++g2) mbar_wait(full + g2 % BPF_STAGES, (unsigned)((g2 / BPF_STAGES) & 1));
+  if (Tl > 0)
+    for (int g2 = gt; g2 < gt + BPF_STAGES; ++g2) mbar_wait(full + g2 % BPF_STAGES, (unsigned)((g2 / BPF_STAGES) & 1));
   __syncthreads();
+  if (CS > 1) cg::this_cluster().sync();     // nobody leaves while a peer may still read its exchange buffer
   for (int n = tid; n < N; n += NT_) {
+    if (CS > 1 && ((n / BPF_TN) % CS) != crank) continue;      // every CTA writes the columns it owns
     b.x0[(size_t)prob * N + n] = x0[n];
     b.x1[(size_t)prob * N + n] = x1[n];
     b.h[(size_t)prob * N + n] = h[n];
   }
-  if (tid == 0) {
+  if (tid == 0 && crank == 0) {
     b.mu[prob] = mu;
     b.iters[prob] = it;
     b.done[prob] = done;
@@ -616,23 +661,37 @@ int admm_bp_iterate(const admm_bp_buffers* b, int iter_end, admm_stream_t stream
     const bool small = b->M <= 128;
     const size_t smem = small ? BpfSmem<8>::bytes(b->N) : BpfSmem<16>::bytes(b->N);
     if (smem <= 220 * 1024) {
-      static size_t attr8 = 0, attr16 = 0;
-      if (small) {
-        if (smem > attr8) {
-          cudaFuncSetAttribute(bp_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          cudaFuncSetAttribute(bp_fused_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-          attr8 = smem;
+      // few problems: spread each over a cluster of 8 CTAs (distributed shared memory exchange)
+      const bool clustered = b->nb * 8 <= 148 && !getenv("ADMM_BP_NO_CLUSTER");
+      auto launch = [&](auto kern, int threads, int cs) -> int {
+        static size_t attr[4] = {0, 0, 0, 0};
+        size_t& a = attr[(threads == 256 ? 0 : 1) + (cs > 1 ? 2 : 0)];
+        if (smem > a) {
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          a = smem;
         }
-        bp_fused_kernel<8><<<b->nb, 256, smem, st>>>(*b, iter_end);
-      } else {
-        if (smem > attr16) {
-          cudaFuncSetAttribute(bp_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          cudaFuncSetAttribute(bp_fused_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-          attr16 = smem;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(b->nb * cs);
+        cfg.blockDim = dim3(threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = cs > 1 ? 1 : 0;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *b, iter_end);
+        if (e != cudaSuccess) {
+          set_error("admm_bp_iterate(fused): %s", cudaGetErrorString(e));
+          return ADMM_ECUDA;
         }
-        bp_fused_kernel<16><<<b->nb, 512, smem, st>>>(*b, iter_end);
-      }
-      return check_launch("admm_bp_iterate(fused)");
+        return check_launch("admm_bp_iterate(fused)");
+      };
+      if (small) return clustered ? launch(bp_fused_kernel<8, 8>, 256, 8) : launch(bp_fused_kernel<8, 1>, 256, 1);
+      return clustered ? launch(bp_fused_kernel<16, 8>, 512, 8) : launch(bp_fused_kernel<16, 1>, 512, 1);
     }
   }
   const size_t smem = bp_smem_bytes(b);

@@ -59,7 +59,7 @@ class SharedSpM:
 
     def __init__(self, s, P, C_, D, g, lam: float, mu: float = 0.1, alpha: float = 1.0,
                  batch_wide: bool = False, max_mu: float = 1e3, nsplit: Optional[int] = None,
-                 group=None, force_complex: Optional[bool] = None, mt: Optional[int] = None):
+                 group=None, force_complex: Optional[bool] = None, mt: Optional[int] = None, nbal: Optional[int] = None):
         dev = _lib.require_cuda()
         s_t = _dev_tensor(s, dev, _F64)
         g_t = _dev_tensor(g, dev)
@@ -74,7 +74,7 @@ class SharedSpM:
         b0 = torch.empty_like(gv)
         sd = (-alpha * s_t).to(gv.dtype)
         call("admm_diag_mul", int(cplx), L, L, nb, ptr(sd), ptr(gv), nb, ptr(b0), nb, stream())
-        self._init_common(G0, b0, P, C_, D, lam, mu, mu, batch_wide, max_mu, nsplit, group, force_complex, mt)
+        self._init_common(G0, b0, P, C_, D, lam, mu, mu, batch_wide, max_mu, nsplit, group, force_complex, mt, nbal)
         self._s = s_t
         self._g = gv
         self._alpha = alpha
@@ -97,7 +97,7 @@ class SharedSpM:
 
     # ------------------------------------------------------------------ setup
     def _init_common(self, G0, b0, P, C_, D, lam, mu10, mu20, batch_wide, max_mu, nsplit, group, force_complex,
-                     mt=None):
+                     mt=None, nbal_req=None):
         dev = _lib.require_cuda()
         self.device = dev
         self.group = group
@@ -121,23 +121,38 @@ class SharedSpM:
         nchunks = nrt // 4
         NT = Lp // 8
         # problem tiles per warp in the pass kernel; one CTA = 4 warps = 4*mt tiles of 8 problems
-        if mt is None:
-            mt = 2 if (npt >= 8 * 444 and Lp <= 40) else 1
-        assert mt in (1, 2) and (mt == 1 or Lp <= 40)
+        # ---- launch configuration (measured on B200, tools/cfg3_sweep.py)
+        #  * fused x-update + pass, whole columns per CTA, 2 tiles per warp: when the batch gives many
+        #    (nearly) full waves of 444 CTAs;
+        #  * otherwise the balanced decomposition: the group-chunks are cut into equal contiguous pieces,
+        #    one per resident CTA slot, the x-update is a separate kernel that sums the partial V slots
+        #    (so the pieces per tile group are capped: every slot costs the x-update a dependent load).
+        SLOTS = 444                                     # 148 SMs x 3 resident CTAs
         nbal = 0
-        if nsplit is None:
-            # whole columns per CTA (fused x-update + pass) when the batch alone fills the 148 SMs x 3
-            # resident CTAs; otherwise the balanced decomposition: the group-chunks are cut into equal
-            # contiguous pieces, one per resident CTA slot (then the x-update is a separate kernel)
+        if nsplit is None and nbal_req is None:
+            waves = -(-npt // 8) / SLOTS
+            fused_ok = Lp <= 40 and waves >= 1.0 and waves / np.ceil(waves) >= 0.85
+            if mt is None:
+                mt = 2 if (Lp <= 40 and (fused_ok or npt >= 1024)) else 1
             ngroups = -(-npt // (4 * mt))
-            if ngroups >= 444:
+            if fused_ok and mt == 2:
                 nsplit = 1
             else:
                 total = ngroups * nchunks
-                nbal = min(444, total, 16 * ngroups)      # at most ~16 partial sums per tile for the x-update
+                cap = 8 if ngroups <= 16 else 4         # pieces per tile group (measured optimum)
+                nbal = max(1, min(SLOTS, total, cap * ngroups))
                 nsplit = -(-nchunks * nbal // total) + 1
         else:
-            nsplit = max(1, min(nsplit, nchunks))
+            if mt is None:
+                mt = 1
+            ngroups = -(-npt // (4 * mt))
+            if nbal_req is not None:
+                total = ngroups * nchunks
+                nbal = max(1, min(int(nbal_req), total))
+                nsplit = -(-nchunks * nbal // total) + 1
+            else:
+                nsplit = max(1, min(nsplit, nchunks))
+        assert mt in (1, 2) and (mt == 1 or Lp <= 40)
         self.dims = SpmDims(L, Lp, Nw, nrt, nb, npt, nplanes, nsplit, mt, nbal, int(batch_wide))
         self.batch_wide = bool(batch_wide)
         self.lam, self.max_mu = float(lam), float(max_mu)

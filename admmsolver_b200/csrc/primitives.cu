@@ -120,6 +120,91 @@ __global__ void __launch_bounds__(256) gemm_kernel(int m, int n, int k, const T*
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// real FP64 GEMM on the tensor cores (DMMA.8x8x4):  C[m x n] = op(A)[m x k] * B[k x n]
+//   CTA tile 64 x 64, k-step 16, 4 warps in a 2 x 2 arrangement, each 32 x 32 = 4 x 4 mma tiles
+//   (32 accumulator doubles per lane).  Global -> registers -> shared memory with the next k-step
+//   prefetched into registers while the current one is multiplied; shared pitches 20 / 68 doubles
+//   (= 4 mod 16) make both fragment loads conflict free.  Edges are zero-filled.
+// This is the x-update GEMM of a generic LeastSquares term whose right-hand sides share one A
+// (PartialDiagonalMatrix packing): B = (alpha A^H A + mu)^-1 times an (N x nbatch) block.
+// ---------------------------------------------------------------------------------------------
+template <int OP>
+__global__ void __launch_bounds__(128) gemm_dmma_kernel(int m, int n, int k, const double* __restrict__ A, int lda,
+                                                        const double* __restrict__ B, int ldb, double* __restrict__ C,
+                                                        int ldc) {
+  constexpr int BM = 64, BN = 64, BK = 16, PA = BK + 4, PB = BN + 4;
+  __shared__ double As[BM * PA];      // As[i][kk] = op(A)[row0 + i][k0 + kk]
+  __shared__ double Bs[BK * PB];      // Bs[kk][j] = B[k0 + kk][col0 + j]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int row0 = blockIdx.y * BM, col0 = blockIdx.x * BN;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  double ra[8], rb[8];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int idx = tid + 128 * q;            // 0 .. 1023
+      double a = 0.0;
+      if (OP == ADMM_OP_N) {
+        const int i = idx >> 4, kk = idx & 15;  // coalesced along k
+        if (row0 + i < m && k0 + kk < k) a = A[(size_t)(row0 + i) * lda + k0 + kk];
+      } else {
+        const int kk = idx >> 6, i = idx & 63;  // A stored k x m: coalesced along m
+        if (row0 + i < m && k0 + kk < k) a = A[(size_t)(k0 + kk) * lda + row0 + i];
+      }
+      ra[q] = a;
+      const int kb = idx >> 6, j = idx & 63;    // coalesced along n
+      rb[q] = (k0 + kb < k && col0 + j < n) ? B[(size_t)(k0 + kb) * ldb + col0 + j] : 0.0;
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int idx = tid + 128 * q;
+      if (OP == ADMM_OP_N) As[(idx >> 4) * PA + (idx & 15)] = ra[q];
+      else As[(idx & 63) * PA + (idx >> 6)] = ra[q];
+      Bs[(idx >> 6) * PB + (idx & 63)] = rb[q];
+    }
+  };
+  load_tiles(0);
+  for (int k0 = 0; k0 < k; k0 += BK) {
+    __syncthreads();                 // previous k-step consumed
+    store_tiles();
+    __syncthreads();
+    if (k0 + BK < k) load_tiles(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[(wm + 8 * i + g) * PA + kk + t];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[(kk + t) * PB + wn + 8 * j + g];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row0 + wm + 8 * i + g;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = col0 + wn + 8 * j + 2 * t;
+      if (r < m) {
+        if (c < n) C[(size_t)r * ldc + c] = acc[i][j][0];
+        if (c + 1 < n) C[(size_t)r * ldc + c + 1] = acc[i][j][1];
+      }
+    }
+  }
+}
+
 template <typename T>
 static int launch_gemm(int op, int m, int n, int k, const void* A, int lda, const void* B, int ldb, void* C,
                        int ldc, cudaStream_t s) {
@@ -626,6 +711,16 @@ int admm_gemm(int is_complex, int op_a, int m, int n, int k, const void* A, int 
   ADMM_REQUIRE(m >= 0 && n >= 0 && k >= 0 && op_a >= 0 && op_a <= 2, ADMM_EINVAL, "admm_gemm: bad dims/op");
   if (m == 0 || n == 0) return ADMM_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!is_complex && m >= 32 && n >= 32 && k >= 16 && !getenv("ADMM_GEMM_SCALAR")) {
+    // tensor-core path (real data; a conjugate transpose of a real matrix is its transpose)
+    dim3 grid(ceil_div(n, 64), ceil_div(m, 64));
+    const double* a = static_cast<const double*>(A);
+    const double* b = static_cast<const double*>(B);
+    double* c = static_cast<double*>(C);
+    if (op_a == ADMM_OP_N) gemm_dmma_kernel<ADMM_OP_N><<<grid, 128, 0, s>>>(m, n, k, a, lda, b, ldb, c, ldc);
+    else gemm_dmma_kernel<ADMM_OP_T><<<grid, 128, 0, s>>>(m, n, k, a, lda, b, ldb, c, ldc);
+    return check_launch("admm_gemm(dmma)");
+  }
   return is_complex ? launch_gemm<cplx>(op_a, m, n, k, A, lda, B, ldb, C, ldc, s)
                     : launch_gemm<double>(op_a, m, n, k, A, lda, B, ldb, C, ldc, s);
 }

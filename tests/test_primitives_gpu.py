@@ -51,3 +51,25 @@ def test_spd_inverse_flags_indefinite(build_lib):
     info = torch.zeros(1, dtype=torch.int32, device="cuda")
     _lib.call("admm_spd_inverse_batched", 16, 1, _lib.ptr(d), 256, 16, None, _lib.ptr(info), _lib.stream())
     assert int(info.item()) == 6                       # 1-based index of the first non-positive pivot
+
+
+@pytest.mark.parametrize("m,n,k", [(64, 64, 16), (70, 100, 33), (1000, 4096, 1000), (39, 2000, 39), (33, 32, 16), (257, 65, 129)])
+@pytest.mark.parametrize("op", [0, 1])
+def test_gemm_tensor_core(build_lib, m, n, k, op):
+    """admm_gemm, real FP64 on the tensor cores (DMMA) incl. ragged edges and the transposed-A form, vs NumPy.
+    Replaces DenseMatrix.__matmul__ / the tensordot of _matvec_impl (matrix.py:100-118,392-397)."""
+    from admmsolver_b200 import _lib
+    rs = np.random.RandomState(m + n + k + op)
+    A = rs.randn(m, k) if op == 0 else rs.randn(k, m)
+    B = rs.randn(k, n)
+    ref = (A if op == 0 else A.T) @ B
+    lda, ldb, ldc = A.shape[1] + 3, n + 1, n + 5
+    Ad = torch.zeros(A.shape[0], lda, dtype=torch.float64, device="cuda")
+    Ad[:, :A.shape[1]] = torch.from_numpy(A).cuda()
+    Bd = torch.zeros(k, ldb, dtype=torch.float64, device="cuda")
+    Bd[:, :n] = torch.from_numpy(B).cuda()
+    Cd = torch.full((m, ldc), 7.0, dtype=torch.float64, device="cuda")
+    _lib.call("admm_gemm", 0, op, m, n, k, _lib.ptr(Ad), lda, _lib.ptr(Bd), ldb, _lib.ptr(Cd), ldc, _lib.stream())
+    out = Cd.cpu().numpy()
+    assert np.abs(out[:, :n] - ref).max() <= 1e-12 * np.abs(A).max() * np.abs(B).max() * k
+    assert np.all(out[:, n:] == 7.0)                  # nothing written outside the m x n block

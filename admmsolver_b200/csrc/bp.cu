@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <map>
 
 namespace cg = cooperative_groups;
 
@@ -661,11 +662,17 @@ int admm_bp_iterate(const admm_bp_buffers* b, int iter_end, admm_stream_t stream
     const bool small = b->M <= 128;
     const size_t smem = small ? BpfSmem<8>::bytes(b->N) : BpfSmem<16>::bytes(b->N);
     if (smem <= 220 * 1024) {
-      // few problems: spread each over a cluster of 8 CTAs (distributed shared memory exchange)
-      const bool clustered = b->nb * 8 <= 148 && !getenv("ADMM_BP_NO_CLUSTER");
+      // few problems: spread each over a cluster of 8, 4 or 2 CTAs (distributed shared memory exchange)
+      // so that the clusters still fit the 148 SMs in one wave
+      int cs = 1;
+      if (!getenv("ADMM_BP_NO_CLUSTER")) {
+        const int slots = small ? 296 : 148;          // resident CTAs of this kernel
+        for (int c = 8; c >= 2; c >>= 1)
+          if (b->nb * c <= slots / 2) { cs = c; break; }
+      }
       auto launch = [&](auto kern, int threads, int cs) -> int {
-        static size_t attr[4] = {0, 0, 0, 0};
-        size_t& a = attr[(threads == 256 ? 0 : 1) + (cs > 1 ? 2 : 0)];
+        static std::map<const void*, size_t> configured;     // largest smem size configured per kernel
+        size_t& a = configured[reinterpret_cast<const void*>(kern)];
         if (smem > a) {
           cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
           cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -690,8 +697,20 @@ int admm_bp_iterate(const admm_bp_buffers* b, int iter_end, admm_stream_t stream
         }
         return check_launch("admm_bp_iterate(fused)");
       };
-      if (small) return clustered ? launch(bp_fused_kernel<8, 8>, 256, 8) : launch(bp_fused_kernel<8, 1>, 256, 1);
-      return clustered ? launch(bp_fused_kernel<16, 8>, 512, 8) : launch(bp_fused_kernel<16, 1>, 512, 1);
+      if (small) {
+        switch (cs) {
+          case 8: return launch(bp_fused_kernel<8, 8>, 256, 8);
+          case 4: return launch(bp_fused_kernel<8, 4>, 256, 4);
+          case 2: return launch(bp_fused_kernel<8, 2>, 256, 2);
+          default: return launch(bp_fused_kernel<8, 1>, 256, 1);
+        }
+      }
+      switch (cs) {
+        case 8: return launch(bp_fused_kernel<16, 8>, 512, 8);
+        case 4: return launch(bp_fused_kernel<16, 4>, 512, 4);
+        case 2: return launch(bp_fused_kernel<16, 2>, 512, 2);
+        default: return launch(bp_fused_kernel<16, 1>, 512, 1);
+      }
     }
   }
   const size_t smem = bp_smem_bytes(b);

@@ -138,6 +138,19 @@ def sumsq(x: torch.Tensor, y: torch.Tensor = None) -> float:
     return float(out.item())
 
 
+def sumsq_into(out: torch.Tensor, slot: int, x: torch.Tensor, y: torch.Tensor = None) -> None:
+    """out[slot] = ||x||^2 or ||x - y||^2 without a host synchronisation (stream ordered)."""
+    if y is not None and x.is_complex() != y.is_complex():
+        x, y = x.to(C128), y.to(C128)
+    x = x.contiguous()
+    dev = x.device
+    if dev not in _scratch:
+        _scratch[dev] = (torch.zeros(1024, dtype=F64, device=dev), torch.zeros(1, dtype=F64, device=dev))
+    scratch = _scratch[dev][0]
+    call("admm_sumsq", x.numel() * ncomp(x), ptr(x), ptr(y.contiguous()) if y is not None else None,
+         ptr(out[slot:slot + 1]), ptr(scratch), stream())
+
+
 def norm(x: torch.Tensor, y: torch.Tensor = None) -> float:
     return float(np.sqrt(sumsq(x, y)))
 

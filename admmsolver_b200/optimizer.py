@@ -362,22 +362,27 @@ class SimpleOptimizer(object):
         self._download()
 
     def _sweep_dev(self, update_h: bool) -> None:
+        """One Gauss-Seidel sweep + dual ascent (optimizer.py:322-341) on the device state, updated IN
+        PLACE: the state tensors keep their addresses, so a sweep can be captured in a CUDA graph."""
         model = self._model
-        self._xd_old = [t.clone() for t in self._xd]
+        if self._xd_old is None or any(o.shape != t.shape for o, t in zip(self._xd_old, self._xd)):
+            self._xd_old = [torch.empty_like(t) for t in self._xd]
+        for o, t in zip(self._xd_old, self._xd):
+            o.copy_(t)
         for k in range(model.num_func):
             f = model.functions[k]
             h, mu = self._hk_dev(k), self._mu_k(k)
             if hasattr(f, "_solve_complex"):
-                self._xd[k] = f._solve_complex(h, mu)
+                xk = f._solve_complex(h, mu)
             else:
                 xk = f.solve(h, mu)
                 if isinstance(xk, np.ndarray):        # user-defined term working on NumPy
                     xk = D.as_dev(xk)
-                self._xd[k] = xk.to(D.C128)
+            self._xd[k].copy_(xk)                     # (casts real results to the complex128 state)
         if update_h:
             for (i, j) in self._pairs:
                 p1, p2 = self._pair_vectors(i, j)
-                self._hd[(i, j)] = D.axpby(1.0, self._hd[(i, j)], float(self._mu[i, j]), D.axpby(1.0, p2, -1.0, p1))
+                self._hd[(i, j)].copy_(D.axpby(1.0, self._hd[(i, j)], float(self._mu[i, j]), D.axpby(1.0, p2, -1.0, p1)))
 
     def _need_old(self) -> None:
         if self._xd_old is None:
@@ -441,21 +446,86 @@ class SimpleOptimizer(object):
                 self._plan_kind = None        # state not representable by the fused engine
         self._solve_generic(niter, callback, interval_update_mu, update_h, rtol)
 
+    def _launch_norms(self, buf: torch.Tensor) -> None:
+        """The six norms per coupled pair that residual(), check_convergence() and update_mu() need
+        (optimizer.py:232-299), each pair/dual vector formed ONCE, squared norms into ``buf`` (no host
+        synchronisation).  Row per pair: |p1-p2|, |p1|, |p2|, |d1-d2|, |d1|, |d2|."""
+        for n, (i, j) in enumerate(self._pairs):
+            p1, p2 = self._pair_vectors(i, j)
+            d1, d2 = self._dual_vectors(i, j, p1)
+            D.sumsq_into(buf, 6 * n + 0, p1, p2)
+            D.sumsq_into(buf, 6 * n + 1, p1)
+            D.sumsq_into(buf, 6 * n + 2, p2)
+            D.sumsq_into(buf, 6 * n + 3, d1, d2)
+            D.sumsq_into(buf, 6 * n + 4, d1)
+            D.sumsq_into(buf, 6 * n + 5, d2)
+
+    def _graphable(self) -> bool:
+        """Every term runs on the device (a user-defined NumPy term cannot be captured in a CUDA graph)."""
+        return all(hasattr(f, "_solve_complex") or type(f).__module__.startswith("admmsolver_b200")
+                   for f in self._model.functions)
+
     def _solve_generic(self, niter, callback, interval_update_mu, update_h, rtol) -> None:
+        """Same order of operations as the reference loop; without a callback the residuals, the stopping
+        test and update_mu() of an iteration share one set of norms (one host synchronisation per iteration
+        instead of one per norm; the reference recomputes every E @ x for each of the three)."""
         self._upload()
+        nbuf = torch.zeros(6 * max(1, len(self._pairs)), dtype=D.F64, device=self._xd[0].device)
+        graphable = callback is None and self._graphable()
+        graph = graph_key = warm_key = None
         for it in range(niter):
-            self._sweep_dev(update_h)
-            primal, dual = self.residual()
-            self._primal_residual.append(primal)
-            self._dual_residual.append(dual)
             if callback is not None:
+                self._sweep_dev(update_h)
+                primal, dual = self.residual()
+                self._primal_residual.append(primal)
+                self._dual_residual.append(dual)
                 self._download()
                 callback()
                 self._upload()
-            if self.check_convergence(rtol):
+                if self.check_convergence(rtol):
+                    break
+                if it % interval_update_mu == 0:
+                    self.update_mu()
+                continue
+            # sweep + norms: eagerly the first time for every set of penalties (fills the adjoint / mu_k /
+            # inverse caches outside any capture), then captured once and replayed as ONE graph launch
+            key = tuple(float(self._mu[p]) for p in self._pairs) + (bool(update_h),)
+            if graph is not None and graph_key == key:
+                graph.replay()
+            else:
+                graph = None
+                self._sweep_dev(update_h)
+                self._launch_norms(nbuf)
+                if graphable and warm_key == key:
+                    before = D._lib.launch_count
+                    try:
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                            self._sweep_dev(update_h)
+                            self._launch_norms(nbuf)
+                        graph, graph_key = g, key
+                    except Exception:                 # something in the model synchronises: stay eager
+                        graphable = False
+                        torch.cuda.synchronize()
+                    D._lib.launch_count = before
+                warm_key = key
+            nr = np.sqrt(nbuf.cpu().numpy()).reshape(len(self._pairs), 6)
+            self._primal_residual.append(float(sum(float(v) for v in nr[:, 0])))
+            self._dual_residual.append(float(sum(float(v) for v in nr[:, 3])))
+            with np.errstate(all="ignore"):
+                conv = all(bool(r[0] / max(r[1], r[2]) < rtol) and bool(r[3] / max(r[4], r[5]) < rtol) for r in nr)
+            if conv:
                 break
             if it % interval_update_mu == 0:
-                self.update_mu()
+                for n, (i, j) in enumerate(self._pairs):
+                    primal, dual = float(nr[n, 0]), float(nr[n, 3])
+                    if primal > 10.0 * dual:
+                        self._mu[i, j] *= 2.0
+                    if dual > 10.0 * primal:
+                        self._mu[i, j] /= 2.0
+                    self._mu[i, j] = min(self._mu[i, j], self._max_mu)
+                if self._snapshot is not None:
+                    self._snapshot = (self._snapshot[0], self._snapshot[1], self._mu.copy())
         self._download()
 
     # ---- fused engines

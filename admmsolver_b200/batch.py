@@ -617,6 +617,13 @@ class BatchedBasisPursuit:
         b.alpha, b.lam, b.rtol, b.max_mu = self.alpha, self.lam, float(rtol), self.max_mu
         b.fact_incr, b.th_change, b.interval_update_mu = float(fact_incr), float(th_change), int(interval)
 
+    def set_data(self, y) -> None:
+        """New right-hand sides y (nb x M, device or host) for the same operators A: only alpha A^T y is
+        recomputed (the Gram matrices and cached inverses depend on A and mu alone)."""
+        y_t = _dev_tensor(y, self.device, _F64).reshape(self.nb, self.M).contiguous()
+        self.y = y_t
+        call("admm_bp_setup", C.byref(self.bufs), ptr(self.y), ptr(self.aty), None, stream())
+
     def set_state(self, x0=None, x1=None, h=None, mu=None) -> None:
         for src, dst in ((x0, self._x0), (x1, self._x1), (h, self._h)):
             if src is not None:

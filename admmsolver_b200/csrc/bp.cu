@@ -606,13 +606,17 @@ int admm_bp_setup(const admm_bp_buffers* b, const double* y, double* aty, double
     admm_bp_buffers bb = *b;
     const int cnt = std::min(65535, b->nb - p0);
     bb.A = b->A + (size_t)p0 * b->M * b->N;
-    dim3 g1(ceil_div(b->N, 256), cnt);
-    bp_aty_kernel<<<g1, 256, 0, s>>>(bb, y + (size_t)p0 * b->M, aty + (size_t)p0 * b->N);
-    const int tiles = ceil_div(b->nk, 32);
-    dim3 g2(tiles, tiles, cnt);
-    double* gp = gram + (size_t)p0 * b->nk * b->nk;
-    if (b->woodbury) bp_gram_kernel<true><<<g2, 256, 0, s>>>(bb, gp);
-    else bp_gram_kernel<false><<<g2, 256, 0, s>>>(bb, gp);
+    if (y != nullptr && aty != nullptr) {
+      dim3 g1(ceil_div(b->N, 256), cnt);
+      bp_aty_kernel<<<g1, 256, 0, s>>>(bb, y + (size_t)p0 * b->M, aty + (size_t)p0 * b->N);
+    }
+    if (gram != nullptr) {
+      const int tiles = ceil_div(b->nk, 32);
+      dim3 g2(tiles, tiles, cnt);
+      double* gp = gram + (size_t)p0 * b->nk * b->nk;
+      if (b->woodbury) bp_gram_kernel<true><<<g2, 256, 0, s>>>(bb, gp);
+      else bp_gram_kernel<false><<<g2, 256, 0, s>>>(bb, gp);
+    }
   }
   return check_launch("admm_bp_setup");
 }

@@ -367,8 +367,7 @@ def run_ours(args):
         def e2e_step():
             # A stays resident (the operator); per step the data y travels in and x0 travels out
             y_dev.copy_(y_host, non_blocking=True)
-            _lib.call("admm_bp_setup", __import__("ctypes").byref(eng.bufs), _lib.ptr(y_dev), _lib.ptr(eng.aty),
-                      _lib.ptr(eng.gram), _lib.stream())
+            eng.set_data(y_dev)
             reset_state()
             eng.solve(niter)
             out_host.copy_(eng._x0, non_blocking=True)

@@ -292,7 +292,8 @@ typedef struct admm_bp_buffers {
 } admm_bp_buffers;
 
 /* aty = alpha A^T y and gram = A A^T (woodbury) or A^T A.  Replaces `LeastSquares.__init__`
- * (objectivefunc.py:76-77) and the per-call `Ac @ y` (objectivefunc.py:108). */
+ * (objectivefunc.py:76-77) and the per-call `Ac @ y` (objectivefunc.py:108).  Either output may be
+ * NULL: new data y for the same operators needs only aty (y, aty non-NULL, gram NULL). */
 int admm_bp_setup(const admm_bp_buffers* b, const double* y, double* aty, double* gram,
                   admm_stream_t stream);
 

@@ -269,3 +269,20 @@ def test_spm_other_basis_sizes(eng, eps, L_expect, mt, nsplit):
     assert rel(e.x0(), st.x0) < TOL and rel(e.x1(), st.x1) < TOL and rel(e.x2(), st.x2) < TOL
     assert float(e.mu10[0]) == st.mu10 and float(e.mu20[0]) == st.mu20
     assert rel(e.primal_residual, st.primal) < 1e-8
+
+
+def test_bp_set_data_reuses_operators(eng):
+    """New right-hand sides for the same A: set_data + state reset == a fresh engine (only alpha A^T y is redone)."""
+    batch, problems = eng
+    A, y, _ = problems.basis_pursuit_batch(5, 64, 160, 6, seed0=40)
+    rs = np.random.RandomState(1)
+    y2 = y + 0.1 * rs.randn(*y.shape)
+    e = batch.BatchedBasisPursuit(A, y, 1.0, 0.1)
+    e.solve(150)
+    z = torch.zeros(5, 160, dtype=torch.float64, device="cuda")
+    e.set_data(y2)
+    e.set_state(x0=z, x1=z, h=z, mu=1.0)
+    e.solve(150)
+    f = batch.BatchedBasisPursuit(A, y2, 1.0, 0.1)
+    f.solve(150)
+    assert np.array_equal(e.x0(), f.x0()) and np.array_equal(e.mu.cpu().numpy(), f.mu.cpu().numpy())

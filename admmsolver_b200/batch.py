@@ -127,7 +127,7 @@ class SharedSpM:
         #  * otherwise the balanced decomposition: the group-chunks are cut into equal contiguous pieces,
         #    one per resident CTA slot, the x-update is a separate kernel that sums the partial V slots
         #    (so the pieces per tile group are capped: every slot costs the x-update a dependent load).
-        SLOTS = 444                                     # 148 SMs x 3 resident CTAs
+        SLOTS = 3 * _lib.device_info()[0]               # resident CTAs of the pass kernel: 3 per SM (444 on B200)
         nbal = 0
         if nsplit is None and nbal_req is None:
             waves = -(-npt // 8) / SLOTS

@@ -670,7 +670,13 @@ int admm_bp_iterate(const admm_bp_buffers* b, int iter_end, admm_stream_t stream
       // so that the clusters still fit the 148 SMs in one wave
       int cs = 1;
       if (!getenv("ADMM_BP_NO_CLUSTER")) {
-        const int slots = small ? 296 : 148;          // resident CTAs of this kernel
+        static int sm_count = 0;
+        if (sm_count == 0) {
+          int dev = 0;
+          cudaGetDevice(&dev);
+          cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        }
+        const int slots = (small ? 2 : 1) * sm_count;   // resident CTAs of this kernel (296 / 148 on B200)
         for (int c = 8; c >= 2; c >>= 1)
           if (b->nb * c <= slots / 2) { cs = c; break; }
       }

@@ -195,9 +195,11 @@ class _SpMPlan:
         if packed:
             if not (isinstance(A, PartialDiagonalMatrix) and isinstance(Cm, PartialDiagonalMatrix)):
                 return None
-            if not (len(P.rest_dims) == 1 and tuple(P.rest_dims) == tuple(A.rest_dims) == tuple(Cm.rest_dims)):
+            # any number of batch axes (k-points x orbitals ...): the packed vector is C-ordered, so the
+            # flattened rest index is the batch index
+            if not (len(P.rest_dims) >= 1 and tuple(P.rest_dims) == tuple(A.rest_dims) == tuple(Cm.rest_dims)):
                 return None
-            nb = int(P.rest_dims[0])
+            nb = int(np.prod(P.rest_dims))
             P, A, Cm = P.matrix, A.matrix, Cm.matrix
         else:
             nb = 1

@@ -281,6 +281,24 @@ def test_spm_packed_partialdiagonal_dropin(api):
     assert rel(opt2._primal_residual, g["primal"][:30]) < 1e-8
 
 
+def test_spm_packed_two_batch_axes(api):
+    """rest_dims = (3, 2) (k-points x orbitals) is the same packed batch as rest_dims = (6,): fused engine, golden."""
+    M, F, O = api
+    g = golden("spm_packed")
+    nb, L, Nw = 6, g["s"].size, g["P"].shape[0]
+    rest = (3, 2)
+    lstsq = F.ConstrainedLeastSquares(1.0, M.PartialDiagonalMatrix(-M.DiagonalMatrix(g["s"]), rest), g["g"].ravel(),
+                                      M.PartialDiagonalMatrix(g["C"], rest), np.ones(nb))
+    conds = [(0, 1, M.identity(L * nb), M.identity(L * nb)),
+             (0, 2, M.PartialDiagonalMatrix(g["P"], rest), M.identity(Nw * nb))]
+    opt = O.SimpleOptimizer(O.Model([lstsq, F.L1Regularizer(float(g["lam"]), L * nb), F.NonNegativePenalty(Nw * nb)], conds),
+                            mu=float(g["mu"]))
+    assert opt._plan_kind == "spm"
+    opt.solve(400)
+    assert rel(opt.x[0], g["x0"]) < TOL and rel(opt.x[1], g["x1"]) < TOL and rel(opt.x[2], g["x2"]) < TOL
+    assert opt._mu[1, 0] == float(g["mu10"]) and opt._mu[2, 0] == float(g["mu20"])
+
+
 def test_semi_positive_definite_penalty_golden(build_lib):
     """SemiPositiveDefinitePenalty.solve (objectivefunc.py:294-327) for every axis and
     mu type against the reference's outputs (tests/golden/psd.npz), plus the reference's own acceptance

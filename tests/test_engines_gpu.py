@@ -286,3 +286,19 @@ def test_bp_set_data_reuses_operators(eng):
     f = batch.BatchedBasisPursuit(A, y2, 1.0, 0.1)
     f.solve(150)
     assert np.array_equal(e.x0(), f.x0()) and np.array_equal(e.mu.cpu().numpy(), f.mu.cpu().numpy())
+
+
+@pytest.mark.parametrize("nb", [24, 50, 100])
+def test_bp_cluster_sizes_vs_oracle(eng, nb):
+    """The basis-pursuit kernel spread over thread-block clusters of 4 (nb = 24) and 2 (nb = 50) CTAs per
+    problem and on single CTAs (nb = 100); every cluster size gives the oracle's iterates."""
+    from oracle import flat
+    batch, problems = eng
+    A, y, _ = problems.basis_pursuit_batch(nb, 48, 200, 6, seed0=900)
+    e = batch.BatchedBasisPursuit(A, y, 1.0, 0.1)
+    e.solve(160, interval_update_mu=40)
+    x0 = e.x0()
+    for b in (0, 1, nb // 2, nb - 1):
+        st = flat.bp_solve(A[b], y[b], 1.0, 0.1, 160, interval_update_mu=40)
+        assert rel(x0[b], st.x0.real) < TOL
+        assert float(e.mu[b]) == st.mu

@@ -302,3 +302,25 @@ def test_bp_cluster_sizes_vs_oracle(eng, nb):
         st = flat.bp_solve(A[b], y[b], 1.0, 0.1, 160, interval_update_mu=40)
         assert rel(x0[b], st.x0.real) < TOL
         assert float(e.mu[b]) == st.mu
+
+
+@pytest.mark.parametrize("nb,Nw,mt,nbal", [(70, 136, 1, 5), (70, 136, 2, 7), (130, 104, 1, 13), (9, 330, 1, 4),
+                                            (33, 72, 2, 3), (260, 40, 1, 9)])
+def test_spm_balanced_decomposition_shapes(eng, ir_basis, nb, Nw, mt, nbal):
+    """Balanced decomposition with pieces that straddle tile-group boundaries, ragged last groups and
+    uneven piece lengths (per-problem and batch-wide), against the oracle."""
+    from oracle import flat
+    batch, problems = eng
+    p = problems.spm_batch(nb, ir_basis, Nw=Nw, seed=nb + Nw)
+    e = batch.SharedSpM(p.s, p.P, p.C, p.D, p.g, lam=p.lam, mu=p.mu, batch_wide=True, mt=mt, nbal=nbal)
+    assert e.dims.nbal == nbal and e.dims.mt == mt
+    e.solve(90, interval_update_mu=20)
+    st = flat.spm_solve(p.s, p.P, p.C, p.D, p.g, p.lam, 90, mu=p.mu, interval_update_mu=20)
+    assert rel(e.x0(), st.x0) < TOL and rel(e.x2(), st.x2) < TOL and rel(e.h20(), st.h20) < 1e-8
+    assert float(e.mu10[0]) == st.mu10 and float(e.mu20[0]) == st.mu20
+    e2 = batch.SharedSpM(p.s, p.P, p.C, p.D, p.g, lam=p.lam, mu=p.mu, batch_wide=False, mt=mt, nbal=nbal)
+    e2.solve(90, interval_update_mu=20)
+    x0 = e2.x0()
+    for b in (0, nb // 2, nb - 1):
+        sb = flat.spm_solve(p.s, p.P, p.C, np.array([1.0]), p.g[:, b], p.lam, 90, mu=p.mu, interval_update_mu=20)
+        assert rel(x0[:, b], sb.x0) < TOL and float(e2.mu20[b]) == sb.mu20

@@ -682,6 +682,128 @@ __global__ void __launch_bounds__(SPDI_MAXB * 32, 1)
   if (tid == 0 && info) info[b] = bad_sm;
 }
 
+// ---------------------------------------------------------------------------------------------
+// the same block Gauss-Jordan for 128 < n <= 512: the matrix stays in global memory (L2-resident:
+// <= 2 MB), one CTA of 16 warps per matrix, warp w owns block rows w, w+16, ...; every block step
+// streams the strips it updates through the mma C fragments (load, 2 DMMAs per tile, store).
+// ---------------------------------------------------------------------------------------------
+constexpr int SPDG_MAXB = 64;      // up to 64 block rows of 8 -> n <= 512
+constexpr int SPDG_WARPS = 16;
+
+__global__ void __launch_bounds__(SPDG_WARPS * 32, 1)
+    spd_inverse_dmma_global_kernel(int n, double* __restrict__ Aall, long long bstride, int lda,
+                                   const int* __restrict__ mask, int* __restrict__ info) {
+  extern __shared__ __align__(16) double spdg_sm[];
+  constexpr int PITCH = 8 * SPDG_MAXB + 4;
+  double* panF = spdg_sm;                          // [NB][32][2]   row panel, fragment-major
+  double* panC = panF + SPDG_MAXB * 64;            // [8][PITCH]    row panel, canonical
+  double* Psm = panC + 8 * PITCH;                  // [64]          P = A_kk^-1
+  __shared__ int bad_sm;
+  const int b = blockIdx.x;
+  if (mask && mask[b] == 0) return;
+  double* Ag = Aall + (size_t)b * bstride;
+  const int NB = (n + 7) >> 3;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+  if (tid == 0) bad_sm = 0;
+  __syncthreads();
+  // element (r, c) of the padded matrix (identity on the padding)
+  auto ld = [&](int r, int c) -> double {
+    return (r < n && c < n) ? Ag[(size_t)r * lda + c] : (r == c ? 1.0 : 0.0);
+  };
+  auto st = [&](int r, int c, double v) {
+    if (r < n && c < n) Ag[(size_t)r * lda + c] = v;
+  };
+
+  for (int k = 0; k < NB; ++k) {
+    // ---- (old) row panel -> shared memory, canonical layout (all warps cooperate)
+    for (int idx = tid; idx < 8 * 8 * NB; idx += blockDim.x) {
+      const int r = idx / (8 * NB), c = idx - r * (8 * NB);
+      panC[r * PITCH + c] = ld(8 * k + r, c);
+    }
+    __syncthreads();
+    if (w == 0) {
+      // ---- P = A_kk^-1 by in-place Gauss-Jordan on the C fragment (lane holds (g, 2t), (g, 2t+1))
+      double a0 = panC[g * PITCH + 8 * k + 2 * t], a1 = panC[g * PITCH + 8 * k + 2 * t + 1];
+      int bad = 0;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const double piv = __shfl_sync(0xffffffffu, (p & 1) ? a1 : a0, 4 * p + (p >> 1));
+        if (!(piv > 0.0)) bad = 8 * k + p + 1;
+        const double ip = 1.0 / piv;
+        double r0 = __shfl_sync(0xffffffffu, a0, 4 * p + t);
+        double r1 = __shfl_sync(0xffffffffu, a1, 4 * p + t);
+        const double cg = __shfl_sync(0xffffffffu, (p & 1) ? a1 : a0, 4 * g + (p >> 1));
+        if (2 * t == p) r0 = 1.0;
+        if (2 * t + 1 == p) r1 = 1.0;
+        r0 *= ip;
+        r1 *= ip;
+        if (g == p) {
+          a0 = r0;
+          a1 = r1;
+        } else {
+          const double b0 = (2 * t == p) ? 0.0 : a0;
+          const double b1 = (2 * t + 1 == p) ? 0.0 : a1;
+          a0 = b0 - cg * r0;
+          a1 = b1 - cg * r1;
+        }
+      }
+      Psm[g * 8 + 2 * t] = a0;
+      Psm[g * 8 + 2 * t + 1] = a1;
+      if (bad && lane == 0) bad_sm = bad;
+    }
+    // fragment-major copy of the panel: panF[j][lane'][e] = A_k[2t'+e][8j+g']
+    for (int idx = tid; idx < NB * 64; idx += blockDim.x) {
+      const int e = idx & 1, ln = (idx >> 1) & 31, j = idx >> 6;
+      panF[idx] = panC[(2 * (ln & 3) + e) * PITCH + 8 * j + (ln >> 2)];
+    }
+    __syncthreads();
+
+    for (int i = w; i < NB; i += SPDG_WARPS) {
+      const int row = 8 * i + g;
+      if (i != k) {
+        // T = A_ik P, then A_ij -= T A_kj (j != k), A_ik = -T
+        const double ak0 = ld(row, 8 * k + 2 * t), ak1 = ld(row, 8 * k + 2 * t + 1);
+        double T0 = 0.0, T1 = 0.0;
+        dmma(T0, T1, ak0, Psm[(2 * t) * 8 + g]);
+        dmma(T0, T1, ak1, Psm[(2 * t + 1) * 8 + g]);
+        const double nT0 = -T0, nT1 = -T1;
+        for (int j = 0; j < NB; ++j) {
+          const int col = 8 * j + 2 * t;
+          if (j == k) {
+            st(row, col, nT0);
+            st(row, col + 1, nT1);
+          } else {
+            double c0 = ld(row, col), c1 = ld(row, col + 1);
+            const double2 bb = *reinterpret_cast<const double2*>(panF + (j * 32 + lane) * 2);
+            dmma(c0, c1, nT0, bb.x);
+            dmma(c0, c1, nT1, bb.y);
+            st(row, col, c0);
+            st(row, col + 1, c1);
+          }
+        }
+      } else {
+        // row k:  A_kj = P A_kj (j != k),  A_kk = P
+        const double p0 = Psm[g * 8 + t], p1 = Psm[g * 8 + 4 + t];
+        for (int j = 0; j < NB; ++j) {
+          const int col = 8 * j + 2 * t;
+          if (j == k) {
+            st(row, col, Psm[g * 8 + 2 * t]);
+            st(row, col + 1, Psm[g * 8 + 2 * t + 1]);
+          } else {
+            double d0 = 0.0, d1 = 0.0;
+            dmma(d0, d1, p0, panC[t * PITCH + 8 * j + g]);
+            dmma(d0, d1, p1, panC[(4 + t) * PITCH + 8 * j + g]);
+            st(row, col, d0);
+            st(row, col + 1, d1);
+          }
+        }
+      }
+    }
+    __syncthreads();     // the strips are in memory before the next panel is read
+  }
+  if (tid == 0 && info) info[b] = bad_sm;
+}
+
 }  // namespace admm
 
 using namespace admm;
@@ -820,6 +942,14 @@ int admm_spd_inverse_batched(int n, int nbatch, double* A, long long batch_strid
   if (n <= 8 * SPDI_MAXB && !getenv("ADMM_SPD_SCALAR")) {
     const int NB = (n + 7) / 8;
     spd_inverse_dmma_kernel<<<nbatch, 32 * NB, 0, s>>>(n, A, batch_stride, lda, mask, info);
+  } else if (n <= 8 * SPDG_MAXB && !getenv("ADMM_SPD_SCALAR")) {
+    const size_t smem = (size_t)(SPDG_MAXB * 64 + 8 * (8 * SPDG_MAXB + 4) + 64) * sizeof(double);
+    static bool attr_g = false;
+    if (!attr_g) {
+      cudaFuncSetAttribute(spd_inverse_dmma_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_g = true;
+    }
+    spd_inverse_dmma_global_kernel<<<nbatch, SPDG_WARPS * 32, smem, s>>>(n, A, batch_stride, lda, mask, info);
   } else if (n <= 128) {
     const size_t smem = (size_t)(n * n + 2 * n) * sizeof(double);
     static bool attr_set = false;

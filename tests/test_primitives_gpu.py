@@ -8,9 +8,10 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("n", [1, 5, 8, 37, 64, 100, 128, 150])
+@pytest.mark.parametrize("n", [1, 5, 8, 37, 64, 100, 128, 150, 200, 256, 300, 512, 520])
 def test_spd_inverse_batched(build_lib, n):
-    """admm_spd_inverse_batched: tensor-core block Gauss-Jordan (n <= 128) and the scalar fallback (n > 128)
+    """admm_spd_inverse_batched: tensor-core block Gauss-Jordan (register resident for n <= 128, L2 resident for n <= 512) and the scalar
+    fallback (n > 512)
     vs np.linalg.inv on K = A A^T + mu I (the Woodbury matrix of basis pursuit), masked batch, info flags.
     Replaces np.linalg.inv at matrix.py:77-78 via objectivefunc.py:89-96."""
     from admmsolver_b200 import _lib

@@ -155,6 +155,18 @@ def norm(x: torch.Tensor, y: torch.Tensor = None) -> float:
     return float(np.sqrt(sumsq(x, y)))
 
 
+def spd_inverse(A: torch.Tensor):
+    """Inverse of a real symmetric positive definite matrix on the tensor cores (n <= 512 stays on the
+    DMMA kernels); returns None when a non-positive pivot shows up (caller falls back to `inverse`)."""
+    n = A.shape[0]
+    out = A.contiguous().clone()
+    info = torch.zeros(1, dtype=torch.int32, device=A.device)
+    call("admm_spd_inverse_batched", n, 1, ptr(out), n * n, n, None, ptr(info), stream())
+    if int(info.item()) != 0:
+        return None
+    return out
+
+
 def inverse(A: torch.Tensor) -> torch.Tensor:
     """General inverse (Gauss-Jordan with partial pivoting on the device)."""
     n = A.shape[0]

@@ -29,6 +29,21 @@ __all__ = ["ObjectiveFunctionBase", "LeastSquares", "ConstrainedLeastSquares", "
 Vec = Union[np.ndarray, torch.Tensor]
 
 
+def _inv_hpd(G: MatrixBase) -> MatrixBase:
+    """(alpha A^H A + mu)^-1.  A real dense G of this form is symmetric; when it is also positive definite
+    (mu >= 0, the case of every ADMM penalty) the batched tensor-core SPD inverse does it, otherwise --
+    complex, structured or indefinite G -- the matrix type's own inv()."""
+    if isinstance(G, DenseMatrix):
+        g = G._dense_dev()
+        if not g.is_complex() and g.shape[0] == g.shape[1] and g.shape[0] <= 512:
+            sym = bool(torch.equal(g, g.t())) or float((g - g.t()).abs().max()) <= 1e-13 * float(g.abs().max())
+            if sym:
+                out = D.spd_inverse(g)
+                if out is not None:
+                    return DenseMatrix(out)
+    return G.inv()
+
+
 def _assert_optional_types(obj, types):
     assert obj is None or isinstance(obj, tuple(types))
 
@@ -87,7 +102,7 @@ class LeastSquares(ObjectiveFunctionBase):
         """B = (alpha A^H A + mu)^-1, re-inverted only when mu changes (objectivefunc.py:89-96)."""
         hash_ = (type(mu).__name__, matrix_hash(mu))
         if self._B_cache[0] != hash_:
-            self._B_cache = (hash_, ((self._alpha * self._AcA) + mu).inv())
+            self._B_cache = (hash_, _inv_hpd((self._alpha * self._AcA) + mu))
             self._on_new_B()
         return self._B_cache[1]
 
@@ -202,7 +217,7 @@ class L2Regularizer(ObjectiveFunctionBase):
     def _get_B(self, mu: MatrixBase):
         hash_ = (type(mu).__name__, matrix_hash(mu))
         if self._B_cache[0] != hash_:
-            self._B_cache = (hash_, ((self._alpha * self._AcA) + mu).inv())
+            self._B_cache = (hash_, _inv_hpd((self._alpha * self._AcA) + mu))
         return self._B_cache[1]
 
     def solve(self, h: Optional[Vec] = None, mu: Optional[MatrixBase] = None):

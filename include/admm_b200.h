@@ -98,16 +98,20 @@ int admm_sumsq(long long n, const double* x, const double* y, double* out, doubl
 int admm_inverse(int is_complex, int n, const void* A, int lda, void* Ainv, int ldi, void* work,
                  int* info, admm_stream_t stream);
 
-/* Batched inverse of real symmetric positive-definite matrices, in place, one CTA per matrix
- * (shared memory when n <= 128, global memory otherwise).  `mask` (may be NULL) selects the
- * matrices to process (mask[b] != 0).  Used for (alpha A^H A + mu)^-1 (objectivefunc.py:89-96). */
+/* Batched inverse of real symmetric positive-definite matrices, in place, one CTA per matrix:
+ * block Gauss-Jordan with 8x8 blocks on the FP64 tensor cores -- the matrix register-resident for
+ * n <= 128, streamed from L2 for n <= 512 -- and a scalar Gauss-Jordan beyond.  `mask` (may be NULL)
+ * selects the matrices to process (mask[b] != 0); info[b] = 1-based index of the first non-positive
+ * pivot, 0 if none.  Used for (alpha A^H A + mu)^-1 (objectivefunc.py:89-96): the factor that is
+ * cached per mu. */
 int admm_spd_inverse_batched(int n, int nbatch, double* A, long long batch_stride, int lda,
                              const int* mask, int* info, admm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Pattern B engine: SpM  [ConstrainedLeastSquares, L1Regularizer, NonNegativePenalty] with     */
 /* conditions (0,1,I,I), (0,2,P,I); many problems share s, P, C (PartialDiagonalMatrix packing).*/
-/* One ADMM iteration = admm_spm_xupdate + admm_spm_pass (+ admm_spm_reduce) + admm_spm_decide. */
+/* One ADMM iteration = admm_spm_step (or admm_spm_xupdate + admm_spm_pass for small batches),     */
+/* then admm_spm_reduce_decide (or admm_spm_reduce + NCCL all-reduce + admm_spm_decide).          */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct admm_spm_dims {
   int L;        /* basis size (size_x of terms 0 and 1)                                        */
@@ -213,7 +217,7 @@ typedef struct admm_spm_buffers {
   double* gpart;          /* [256][16] scratch of the two-stage reduce                         */
   /* control */
   int* iter_counter;      /* device scalar: iterations launched so far in this solve call      */
-  int* flags;             /* [4]: 0 any mu changed, 1 number not done, 2 reserved, 3 reserved  */
+  int* flags;             /* [4]: 0 any mu changed, 1 number of problems done, 2 reserved, 3 reserved */
   double* history;        /* [hist_cap][2] primal/dual per iteration (batch_wide or nb==1), or NULL */
   int hist_cap;
   double lam;             /* L1 weight                                                         */
@@ -245,7 +249,8 @@ int admm_spm_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode,
 
 /* admm_spm_xupdate + admm_spm_pass(mode 0) in ONE kernel: every warp first does the x-update of
  * its own problem tiles (both planes) and then streams their state, so x0 goes from the
- * x-update to the tensor-core operand registers without a round trip.  Needs nsplit == 1. */
+ * x-update to the tensor-core operand registers without a round trip.  Needs whole columns per CTA
+ * (nsplit == 1, nbal == 0). */
 int admm_spm_step(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream_t stream);
 
 /* Batch-wide norms: deterministic two-stage sum over all problems into gsum[16].  The caller

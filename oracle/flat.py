@@ -32,7 +32,7 @@ from typing import List, Optional
 import numpy as np
 from scipy.linalg import cho_factor, cho_solve
 
-__all__ = ["soft_threshold", "project_plus", "bp_solve", "spm_solve", "spm_solve_independent",
+__all__ = ["soft_threshold", "project_plus", "bp_solve", "spm_solve", "spm_solve_independent", "psd_project",
            "BPState", "SpMState"]
 
 

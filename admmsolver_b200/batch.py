@@ -464,10 +464,17 @@ class SharedSpM:
             self._v_valid = False      # V was built with the old mu20
         return False
 
+    #: largest batch the cluster-resident single-launch solve is used for (one 8-CTA cluster per problem)
+    SOLO_MAX_NB = 16
+
     def solve(self, niter: int = 10000, interval_update_mu: int = 100, rtol: float = 1e-12,
-              callback=None, keep_history: Optional[bool] = None, use_graph: Optional[bool] = None) -> int:
+              callback=None, keep_history: Optional[bool] = None, use_graph: Optional[bool] = None,
+              use_solo: Optional[bool] = None) -> int:
         """Run up to ``niter`` iterations with the ordering of ``SimpleOptimizer.solve``
         (optimizer.py:302-320).  Returns the number of iterations launched.
+
+        A single problem (or a handful with the per-problem criterion) and no callback: the whole
+        loop is ONE launch of the cluster-resident kernel (``admm_spm_solo``; ``use_solo``).
 
         The iterations between two mu updates are data-independent launch sequences: they are
         captured once in a CUDA graph and replayed (``use_graph``; default: on when no callback
@@ -487,8 +494,28 @@ class SharedSpM:
         key = (float(rtol), self.bufs.history, self.bufs.hist_cap)     # everything a captured launch bakes in
         if use_graph is None:
             use_graph = callback is None and self.pass_events is None and self.group is None
+        solo_ok = (callback is None and self.pass_events is None and self.group is None and nb <= self.SOLO_MAX_NB
+                   and (nb == 1 or not self.batch_wide)
+                   and _lib.lib.admm_spm_solo_supported(C.byref(self.dims)) != 0)
+        if use_solo is None:
+            use_solo = solo_ok and use_graph
+        elif use_solo and not solo_ok:
+            raise NotImplementedError("the cluster-resident solve needs nb <= %d, the per-problem criterion (or one "
+                                      "problem), no callback and an operator that fits the cluster" % self.SOLO_MAX_NB)
         launched = 0
         it = 0
+        if use_solo:
+            call("admm_spm_solo", C.byref(self.dims), C.byref(self.bufs), ptr(self.G0), int(niter),
+                 int(interval_update_mu), stream())
+            self._v_valid, self._fresh = True, False
+            fl = self.flags.cpu()
+            if int(fl[2]) != 0:
+                raise _lib.AdmmError("alpha A^H A + mu is not positive definite")
+            if int(fl[0]) != 0:
+                self.flags[0] = 0
+                self._refresh_slots()
+            launched = int(self.iters[:nb].max().item())
+            it = niter
         while it < niter:
             upd = (it % interval_update_mu == 0)
             run = 1 if upd else min(niter, (it // interval_update_mu + 1) * interval_update_mu) - it

@@ -11,7 +11,11 @@
 //   * decide evaluates residual()/check_convergence()/update_mu() on device.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
+
+namespace cg = cooperative_groups;
 
 namespace admm {
 
@@ -884,6 +888,443 @@ __global__ void __launch_bounds__(128) spm_decide_kernel(admm_spm_dims d, admm_s
 }
 
 // ---------------------------------------------------------------------------------------------
+// solo: a handful of problems, each on its own thread-block cluster, the WHOLE solve in one launch
+// ---------------------------------------------------------------------------------------------
+// A single SpM problem (spm.ipynb) has 2 x 156 kflop of work per iteration: launch latency and the
+// round trips through L2 between the kernels of an iteration are all that is left to optimise.  Here
+// the CS CTAs of a cluster keep one problem resident for the whole solve:
+//   * every CTA owns Nw/CS sampling points: its rows of P and of the implicit (h20, x2) state stay in
+//     shared memory;
+//   * the L-space work (cached inverse, KKT correction, P^T P x0, soft threshold, dual ascent, norms,
+//     residual()/check_convergence()/update_mu(), even the re-inversion after a change of mu) is done
+//     redundantly by every CTA -- same inputs, same order, bit-identical results, identical decisions;
+//   * the only exchange per iteration is the partial V = P^T|s'| (L doubles) and two norm partials,
+//     pulled from the peers' shared memory (DSMEM) after ONE cluster barrier.
+// Warps 0-3 hold the L-vectors in registers (thread = (plane, l)); warps 4-11 own the sampling points.
+constexpr int SOLO_THREADS = 384;
+constexpr int SOLO_LWARPS = 4;
+constexpr int SOLO_RTHREADS = SOLO_THREADS - 32 * SOLO_LWARPS;
+
+struct SoloLayout {      // offsets in doubles into the dynamic shared memory
+  int P, Gi, PtP, rhs, xn, w, Cv, us, ss, xch, nA, nB, nBt, rowk, colk, total;
+};
+__host__ __device__ inline SoloLayout solo_layout(int L, int R, int npl) {
+  SoloLayout o;
+  int at = 0;
+  auto take = [&](int n) { const int r = at; at += (n + 1) & ~1; return r; };
+  o.P = take(L * R);
+  o.Gi = take(L * L);
+  o.PtP = take(L * L);
+  o.rhs = take(npl * L);
+  o.xn = take(npl * L);
+  o.w = take(L);
+  o.Cv = take(L);
+  o.us = take(R);
+  o.ss = take(R);
+  o.xch = take(2 * (L + 2));
+  o.nA = take(SOLO_LWARPS * 8);
+  o.nB = take((SOLO_THREADS / 32 - SOLO_LWARPS) * 2);
+  o.nBt = take(2);
+  o.rowk = take(L);
+  o.colk = take(L);
+  o.total = at;
+  return o;
+}
+
+// Gi <- (G0 + mu10 I + mu20 PtP)^-1 (in-place Gauss-Jordan, symmetrised), w = Gi C^T; returns sigma = C w
+// (objectivefunc.py:89-96,148-157).  All threads of the CTA; ends with the shared data visible.
+__device__ __forceinline__ double solo_factor(int L, int Lp, double mu10, double mu20, const double* __restrict__ G0,
+                                              const double* PtPs, double* Gi, double* wv, const double* Cv, double* rowk,
+                                              double* colk, int* bad) {
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < L * L; idx += SOLO_THREADS) {
+    const int i = idx / L, j = idx - i * L;
+    Gi[idx] = G0[(size_t)i * Lp + j] + (i == j ? mu10 : 0.0) + mu20 * PtPs[idx];
+  }
+  __syncthreads();
+  for (int k = 0; k < L; ++k) {
+    const double pv = Gi[k * L + k];
+    if (!(pv > 0.0)) *bad = k + 1;
+    const double ip = 1.0 / pv;
+    for (int j = tid; j < L; j += SOLO_THREADS) {
+      rowk[j] = (j == k ? 1.0 : Gi[k * L + j]) * ip;
+      colk[j] = (j == k ? 0.0 : Gi[j * L + k]);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < L * L; idx += SOLO_THREADS) {
+      const int i = idx / L, j = idx - i * L;
+      if (i == k) {
+        Gi[idx] = rowk[j];
+      } else {
+        const double base = (j == k) ? 0.0 : Gi[idx];
+        Gi[idx] = base - colk[i] * rowk[j];
+      }
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < L * L; idx += SOLO_THREADS) {
+    const int i = idx / L, j = idx - i * L;
+    if (i < j) {
+      const double v = 0.5 * (Gi[i * L + j] + Gi[j * L + i]);
+      Gi[i * L + j] = v;
+      Gi[j * L + i] = v;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < L; i += SOLO_THREADS) {
+    double a = 0.0;
+    for (int j = 0; j < L; ++j) a += Gi[i * L + j] * Cv[j];
+    wv[i] = a;
+  }
+  __syncthreads();
+  double sigma = 0.0;
+  for (int i = 0; i < L; ++i) sigma += Cv[i] * wv[i];
+  return sigma;
+}
+
+template <int CS>
+__global__ void __launch_bounds__(SOLO_THREADS, 1)
+    spm_solo_kernel(admm_spm_dims d, admm_spm_buffers b, const double* __restrict__ G0, int budget, int interval) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = CS > 1 ? (int)cluster.block_rank() : 0;
+  const int prob = blockIdx.x / CS;
+  if (b.done[prob]) return;                                 // uniform over the cluster
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = d.L, Lp = d.Lp, NT = d.Lp / 8, npl = d.nplanes;
+  const int pt = prob >> 3, g = prob & 7;
+  const int Nwp = d.nrt * 8;
+  const int R = (Nwp + CS - 1) / CS;                        // sampling points per CTA
+  const int row0 = crank * R, nrow = max(0, min(R, Nwp - row0));
+  extern __shared__ __align__(16) double sm[];
+  const SoloLayout lay = solo_layout(L, R, npl);
+  double* Psm = sm + lay.P;        // [l][i]: P[row0 + i][l]
+  double* Gi = sm + lay.Gi;        // [L][L], symmetric
+  double* PtPs = sm + lay.PtP;     // [L][L], symmetric
+  double* rhs = sm + lay.rhs;      // [plane][l]
+  double* xn = sm + lay.xn;        // [plane][l]: the new x0
+  double* wv = sm + lay.w;
+  double* Cv = sm + lay.Cv;
+  double* us = sm + lay.us;        // [i]: operand of V = P^T u
+  double* ss = sm + lay.ss;        // [i]: implicit state  s = Re h20 - mu20 x2
+  double* xch = sm + lay.xch;      // [2][L + 2]: my partial V and norm partials (ping-pong)
+  double* nA = sm + lay.nA;        // [L-space warp][8]
+  double* nB = sm + lay.nB;        // [row warp][2]
+  double* nBt = sm + lay.nBt;      // [2] cluster totals
+  __shared__ int bad_sh;
+
+  // ---- one-time loads
+  if (tid == 0) bad_sh = 0;
+  for (int idx = tid; idx < L * R; idx += SOLO_THREADS) {
+    const int l = idx / R, i = idx - l * R;
+    const int row = row0 + i;
+    double v = 0.0;
+    if (i < nrow) v = b.Pf[((size_t)(row >> 3) * 2 * NT + (l >> 3)) * 64 + (4 * (row & 7) + ((l & 7) >> 1)) * 2 + (l & 1)];
+    Psm[idx] = v;
+  }
+  const int slot = b.slot[prob];
+  for (int idx = tid; idx < L * L; idx += SOLO_THREADS) {
+    const int i = idx / L, j = idx - i * L;
+    const size_t o = bfrag_of(NT, i, j);
+    Gi[idx] = b.Ginv_cache[(size_t)slot * Lp * Lp + o];
+    PtPs[idx] = b.PtPf[o];
+  }
+  for (int i = tid; i < L; i += SOLO_THREADS) {
+    wv[i] = b.w_cache[(size_t)slot * Lp + i];
+    Cv[i] = b.Cvec[i];
+  }
+  for (int i = tid; i < R; i += SOLO_THREADS) {
+    const int row = row0 + i;
+    ss[i] = i < nrow ? b.S[state_index(d, pt, row >> 3, 4 * g + ((row & 7) >> 1)) + (row & 1)] : 0.0;
+  }
+  double sigma = b.sigma_cache[slot];
+  double mu10 = b.mu10[prob], mu20 = b.mu20[prob];
+  double mu20_enc = b.mu20_used[prob];            // the mu20 the negative part of s is scaled with
+  int it = b.iters[prob];
+
+  // L-space threads: (plane, l) and their vector elements, in registers for the whole solve
+  const bool lth = warp < SOLO_LWARPS;
+  const int pl = tid >> 6, l = tid & 63;
+  const bool lact = lth && pl < npl && l < L;
+  const size_t fo = lact ? frag_index(pt * npl + pl, NT, l >> 3, 4 * g + ((l & 7) >> 1)) + (l & 1) : 0;
+  double r_b0 = 0.0, r_h10 = 0.0, r_x1 = 0.0, r_x0 = 0.0, r_y0 = 0.0, r_V = 0.0, r_aim = 0.0, Dp = 0.0;
+  if (lact) {
+    r_b0 = b.b0[fo];
+    r_h10 = b.h10[fo];
+    r_x1 = b.x1[fo];
+    r_x0 = b.x0[fo];
+    r_aim = b.aim[fo];
+    if (pl == 1) r_V = b.V[fo];                   // z = P^T Im(h20): state, not derived
+    Dp = b.Dre[(size_t)pl * 8 * d.npt + prob];
+    xn[pl * L + l] = r_x0;
+  }
+  __syncthreads();
+  if (lact) {                                     // y0 = P^T P x0
+    double a = 0.0;
+    for (int j = 0; j < L; ++j) a += PtPs[j * L + l] * xn[pl * L + j];
+    r_y0 = a;
+  }
+
+  int phase = 0;
+  bool need_v = true;          // V (real plane) has to be rebuilt from the state (start, change of mu20)
+  bool mu_changed = false;
+  int conv = 0;
+  double primal = 0.0, dual = 0.0;
+
+  // partial V of my sampling points from us[], exchange, total into r_V of the (0, l) threads; the two
+  // norm partials ride along
+  auto exchange = [&](double nb0, double nb1) {
+    double* mine = xch + phase * (L + 2);
+    constexpr int NW = SOLO_THREADS / 32;
+    for (int l0 = warp; l0 < L; l0 += 4 * NW) {
+      double a[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int i = lane; i < R; i += 32) {
+        const double u = us[i];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int lq = l0 + q * NW;
+          if (lq < L) a[q] += u * Psm[lq * R + i];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[q] = warp_sum(a[q]);
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (l0 + q * NW < L) mine[l0 + q * NW] = a[q];
+      }
+    }
+    if (tid == 0) {
+      mine[L] = nb0;
+      mine[L + 1] = nb1;
+    }
+    if (CS > 1) cluster.sync(); else __syncthreads();
+    if (lact && pl == 0) {
+      double a = 0.0;
+#pragma unroll
+      for (int c = 0; c < CS; ++c) a += (CS > 1 ? cluster.map_shared_rank(mine, c) : mine)[l];
+      r_V = a;
+    }
+    if (warp == SOLO_LWARPS && lane < 2) {
+      double a = 0.0;
+#pragma unroll
+      for (int c = 0; c < CS; ++c) a += (CS > 1 ? cluster.map_shared_rank(mine, c) : mine)[L + lane];
+      nBt[lane] = a;
+    }
+    phase ^= 1;
+    __syncthreads();
+  };
+
+  for (int k = 0;; ++k) {
+    if (need_v) {
+      // u = Re h20 + mu20 x2 with x2 decoded by the mu20 it was encoded with
+      const double ratio = mu20 / mu20_enc;
+      for (int i = tid; i < R; i += SOLO_THREADS) {
+        const double s = ss[i];
+        us[i] = is_neg(s) ? -s * ratio : s;
+      }
+      __syncthreads();
+      exchange(0.0, 0.0);
+      need_v = false;
+    }
+    if (k >= budget) break;
+
+    // ---- term 0: rhs, cached inverse, KKT correction (C Gi rhs = w . rhs because Gi is symmetric)
+    if (lact) rhs[pl * L + l] = r_b0 + r_h10 + mu10 * r_x1 + r_V;
+    __syncthreads();
+    double xv = 0.0;
+    if (lact) {
+      double a0 = 0.0, a1 = 0.0, c0 = 0.0, c1 = 0.0;
+      const double* rp = rhs + pl * L;
+      int j = 0;
+      for (; j + 1 < L; j += 2) {
+        a0 += Gi[j * L + l] * rp[j];
+        a1 += Gi[(j + 1) * L + l] * rp[j + 1];
+        c0 += wv[j] * rp[j];
+        c1 += wv[j + 1] * rp[j + 1];
+      }
+      if (j < L) {
+        a0 += Gi[j * L + l] * rp[j];
+        c0 += wv[j] * rp[j];
+      }
+      const double nu = (Dp - (c0 + c1)) / sigma;
+      xv = (a0 + a1) + wv[l] * nu;
+      xn[pl * L + l] = xv;
+    }
+    __syncthreads();
+
+    if (lth) {
+      // ---- y = P^T P x0, norms, L1 z-update, dual ascent of pair (1,0), imaginary-plane recursion
+      double n[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      if (lact) {
+        double y0a = 0.0, y1a = 0.0;
+        const double* xp = xn + pl * L;
+        int j = 0;
+        for (; j + 1 < L; j += 2) {
+          y0a += PtPs[j * L + l] * xp[j];
+          y1a += PtPs[(j + 1) * L + l] * xp[j + 1];
+        }
+        if (j < L) y0a += PtPs[j * L + l] * xp[j];
+        const double y = y0a + y1a;
+        const double dd = xv - r_x0;
+        n[3] = dd * dd;
+        n[4] = r_x0 * r_x0;
+        n[5] = dd * (y - r_y0);
+        n[6] = r_x0 * r_y0;
+        n[7] = xv * y;
+        double z = 0.0;
+        if (pl == 0) {
+          const double thr = 0.5 * b.lam / mu10;
+          const double yv = -((r_h10 - mu10 * xv) / mu10);
+          if (yv > thr) z = yv - thr;
+          if (yv < -thr) z = yv + thr;
+        } else {
+          r_V -= mu20 * y;
+          r_aim += mu20 * xv;
+        }
+        r_h10 += mu10 * (z - xv);
+        n[0] = (xv - z) * (xv - z);
+        n[1] = xv * xv;
+        n[2] = z * z;
+        r_x0 = xv;
+        r_x1 = z;
+        r_y0 = y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) n[i] = warp_sum(n[i]);
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nA[warp * 8 + i] = n[i];
+      }
+    } else {
+      // ---- my sampling points: s' = Re h20 - mu20 (P Re x0) encodes dual ascent and projection
+      double n_dh = 0.0, n_xm = 0.0;
+      for (int i = tid - 32 * SOLO_LWARPS; i < R; i += SOLO_RTHREADS) {
+        double q0 = 0.0, q1 = 0.0;
+        int j = 0;
+        for (; j + 1 < L; j += 2) {
+          q0 += Psm[j * R + i] * xn[j];
+          q1 += Psm[(j + 1) * R + i] * xn[j + 1];
+        }
+        if (j < L) q0 += Psm[j * R + i] * xn[j];
+        const double s = ss[i];
+        const double hre = is_neg(s) ? 0.0 : s;
+        const double s_new = hre - mu20 * (q0 + q1);
+        const bool neg = is_neg(s_new);
+        const double hnew = neg ? 0.0 : s_new;
+        const double xm = neg ? s_new : 0.0;
+        const double dh = hre - hnew;
+        n_dh += dh * dh;
+        n_xm += xm * xm;
+        us[i] = fabs(s_new);
+        ss[i] = s_new;
+      }
+      n_dh = warp_sum(n_dh);
+      n_xm = warp_sum(n_xm);
+      if (lane == 0) {
+        nB[(warp - SOLO_LWARPS) * 2] = n_dh;
+        nB[(warp - SOLO_LWARPS) * 2 + 1] = n_xm;
+      }
+    }
+    mu20_enc = mu20;
+    __syncthreads();
+    {
+      double nb0 = 0.0, nb1 = 0.0;
+      if (tid == 0) {
+        for (int w2 = 0; w2 < SOLO_THREADS / 32 - SOLO_LWARPS; ++w2) {
+          nb0 += nB[w2 * 2];
+          nb1 += nB[w2 * 2 + 1];
+        }
+        const double inv = 1.0 / mu20;
+        nb0 *= inv * inv;
+        nb1 *= inv * inv;
+      }
+      exchange(nb0, nb1);
+    }
+
+    // ---- residual() / check_convergence() / update_mu(): every thread, identical numbers
+    double s[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) s[i] = 0.0;
+    for (int p2 = 0; p2 < npl; ++p2) {
+      double a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = nA[(2 * p2) * 8 + i] + nA[(2 * p2 + 1) * 8 + i];
+#pragma unroll
+      for (int i = 5; i < 8; ++i) a[i] = a[i] > 0.0 ? a[i] : 0.0;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) s[i] += a[i];
+      s[9] += a[7];
+      if (p2 == 1) s[7] += a[7];
+    }
+    s[7] += nBt[0];
+    s[8] += nBt[1];
+    const double p10 = sqrt(s[0]), nx0 = sqrt(s[1]), nx1 = sqrt(s[2]), nd = sqrt(s[3]), nxo = sqrt(s[4]);
+    const double nPd = sqrt(s[5]), nPxo = sqrt(s[6]), p20 = sqrt(s[7]), nx2 = sqrt(s[8]), nPx0 = sqrt(s[9]);
+    const double d10 = mu10 * nd, d20 = mu20 * nPd;
+    primal = p10 + p20;
+    dual = d10 + d20;
+    if (crank == 0 && tid == 0 && prob == 0 && b.history && it < b.hist_cap) {
+      b.history[2 * it] = primal;
+      b.history[2 * it + 1] = dual;
+    }
+    const int this_it = it;
+    ++it;
+    const bool cv = (p10 / fmax(nx0, nx1) < b.rtol) && (d10 / fmax(mu10 * nx0, mu10 * nxo) < b.rtol) &&
+                    (p20 / fmax(nPx0, nx2) < b.rtol) && (d20 / fmax(mu20 * nPx0, mu20 * nPxo) < b.rtol);
+    if (cv) {
+      conv = 1;
+      break;
+    }
+    if (interval > 0 && this_it % interval == 0) {
+      const double m10 = mu_step(mu10, p10, d10, b), m20 = mu_step(mu20, p20, d20, b);
+      if (m10 != mu10 || m20 != mu20) {
+        mu10 = m10;
+        mu20 = m20;
+        mu_changed = true;
+        need_v = true;
+        sigma = solo_factor(L, Lp, mu10, mu20, G0, PtPs, Gi, wv, Cv, sm + lay.rowk, sm + lay.colk, &bad_sh);
+      }
+    }
+  }
+
+  // ---- write the state back in the layouts of the batch kernels
+  if (crank == 0 && lact) {
+    b.x0[fo] = r_x0;
+    b.x1[fo] = r_x1;
+    b.h10[fo] = r_h10;
+    b.y0[fo] = r_y0;
+    b.aim[fo] = r_aim;
+    b.V[fo] = r_V;
+    if (pl == 0) {
+      const size_t vstride = (size_t)d.npt * npl * NT * 64;
+      for (int sp = 1; sp < d.nsplit; ++sp) b.V[sp * vstride + fo] = 0.0;
+    }
+  }
+  for (int i = tid; i < nrow; i += SOLO_THREADS) {
+    const int row = row0 + i;
+    b.S[state_index(d, pt, row >> 3, 4 * g + ((row & 7) >> 1)) + (row & 1)] = ss[i];
+  }
+  if (crank == 0 && tid == 0) {
+    b.mu10[prob] = mu10;
+    b.mu20[prob] = mu20;
+    b.mu20_used[prob] = mu20_enc;
+    if (it != b.iters[prob]) {
+      b.last_res[2 * prob] = primal;
+      b.last_res[2 * prob + 1] = dual;
+    }
+    b.iters[prob] = it;
+    if (prob == 0) b.iter_counter[0] = it;
+    if (conv) {
+      b.done[prob] = 1;
+      atomicAdd(&b.flags[1], 1);
+    }
+    if (mu_changed) b.flags[0] = 1;
+    if (bad_sh) b.flags[2] = bad_sh;
+  }
+  if (CS > 1) cluster.sync();      // nobody leaves while a peer may still read its exchange buffer
+}
+
+// ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
 static int check_dims(const admm_spm_dims* d, const char* who) {
@@ -1067,6 +1508,51 @@ int admm_spm_reduce_decide(const admm_spm_dims* d, const admm_spm_buffers* b, in
   spm_reduce_stage1<<<parts, 256, 0, s>>>(*d, *b);
   spm_decide_kernel<<<ceil_div(d->nb, 128), 128, 0, s>>>(*d, *b, do_update_mu, parts);
   return check_launch("admm_spm_reduce_decide");
+}
+
+static size_t solo_smem_bytes(const admm_spm_dims* d, int cs) {
+  const int R = (d->nrt * 8 + cs - 1) / cs;
+  return (size_t)solo_layout(d->L, R, d->nplanes).total * sizeof(double);
+}
+
+int admm_spm_solo_supported(const admm_spm_dims* d) {
+  if (d == nullptr || d->L < 1 || d->L > 64 || d->nb < 1) return 0;
+  return solo_smem_bytes(d, 8) <= 200 * 1024 ? 8 : 0;
+}
+
+int admm_spm_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const double* G0, int niter, int interval_update_mu,
+                  admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_solo")) return rc;
+  ADMM_REQUIRE(!d->batch_wide || d->nb == 1, ADMM_EINVAL, "admm_spm_solo: per-problem criterion only (or a single problem)");
+  ADMM_REQUIRE(admm_spm_solo_supported(d) != 0, ADMM_EUNSUPPORTED,
+               "admm_spm_solo: L=%d, Nw=%d do not fit the shared memory of an 8-CTA cluster", d->L, d->Nw);
+  ADMM_REQUIRE(G0 != nullptr && niter >= 0 && interval_update_mu >= 0, ADMM_EINVAL, "admm_spm_solo: bad arguments");
+  constexpr int CS = 8;
+  const size_t smem = solo_smem_bytes(d, CS);
+  auto kern = spm_solo_kernel<CS>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(d->nb * CS);
+  cfg.blockDim = dim3(SOLO_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *d, *b, G0, niter, interval_update_mu);
+  if (e != cudaSuccess) {
+    set_error("admm_spm_solo: %s", cudaGetErrorString(e));
+    return ADMM_ECUDA;
+  }
+  return check_launch("admm_spm_solo");
 }
 
 }  // extern "C"

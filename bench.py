@@ -318,7 +318,13 @@ def run_ours(args):
         eng = batch.SharedSpM(p.s, p.P, p.C, np.ones(nb_local), g_dev, lam=p.lam, mu=p.mu,
                               batch_wide=batch_wide, group=group if batch_wide else None)
 
+        # a handful of problems: the cluster-resident single-launch solve (admm_spm_solo); every step
+        # starts from the zero state so that it really runs `niter` iterations
+        solo = nb_local <= eng.SOLO_MAX_NB and (nb_local == 1 or not batch_wide) and group is None
+
         def step():
+            if solo:
+                eng.reset(mu=p.mu)
             eng.solve(niter)
 
         def e2e_step():
@@ -340,6 +346,10 @@ def run_ours(args):
         flops_per_unit = 4.0 * L * Nw + (4.0 * L * L * npl if fused else 0.0)
         bytes_per_unit = 16.0 * Nw + (8.0 * L * (10 * npl + (4 if npl == 2 else 0)) if fused else 0.0)
         kernel_name = "spm_pass_kernel<%d,%d,0,%d>" % (eng.dims.Lp // 8, eng.dims.mt, npl if fused else 0)
+        if solo:
+            flops_per_unit = 4.0 * L * Nw + 4.0 * L * L * npl
+            bytes_per_unit = 0.0          # P, the state and the factor stay in shared memory / registers
+            kernel_name = "spm_solo_kernel<8>"
         bound = "tensor"
     else:
         if args.workload == "bp_cfg4":
@@ -433,7 +443,11 @@ def run_ours(args):
 
     # dominant-kernel duration (CUDA events on the launching stream)
     kernel_timing = None
-    if is_spm:
+    if is_spm and solo:
+        k_ms = total_ms / args.steps
+        units_per_launch = nb_local * niter
+        kernel_timing = "step time (one cluster-resident launch runs all iterations; latency-bound, not a roofline case)"
+    elif is_spm:
         if in_region_events:
             kernel_timing = "CUDA events around every launch inside the timed region"
         else:

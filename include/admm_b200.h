@@ -217,7 +217,7 @@ typedef struct admm_spm_buffers {
   double* gpart;          /* [256][16] scratch of the two-stage reduce                         */
   /* control */
   int* iter_counter;      /* device scalar: iterations launched so far in this solve call      */
-  int* flags;             /* [4]: 0 any mu changed, 1 number of problems done, 2 reserved, 3 reserved */
+  int* flags;             /* [4]: 0 any mu changed, 1 number of problems done, 2 first non-positive pivot of an in-kernel re-inversion (admm_spm_solo), 3 reserved */
   double* history;        /* [hist_cap][2] primal/dual per iteration (batch_wide or nb==1), or NULL */
   int hist_cap;
   double lam;             /* L1 weight                                                         */
@@ -267,6 +267,22 @@ int admm_spm_reduce_decide(const admm_spm_dims* d, const admm_spm_buffers* b, in
  * batch-wide; increments iter_counter; appends to history. */
 int admm_spm_decide(const admm_spm_dims* d, const admm_spm_buffers* b, int do_update_mu,
                     admm_stream_t stream);
+
+/* A handful of problems (spm.ipynb: ONE), the whole SimpleOptimizer.solve loop (optimizer.py:302-320)
+ * in ONE launch: every problem is kept resident by a thread-block cluster of 8 CTAs (each owns
+ * Nw/8 sampling points: its rows of P and of the state live in shared memory, the L-vectors in
+ * registers); per iteration the CTAs exchange their partial P^T|s'| through distributed shared
+ * memory behind one cluster barrier and take the residual / convergence / mu decisions -- including
+ * the re-inversion of alpha A^H A + mu after update_mu -- redundantly and identically.  Runs up to
+ * `niter` iterations per problem (stops at convergence), mu update every `interval_update_mu`
+ * iterations (0: never).  G0 = alpha A^H A (Lp x Lp, row-major, as for admm_spm_factor).  Reads and
+ * writes the same buffers as the batch kernels (state in, state out; V, y0, mu20_used consistent),
+ * sets flags[0] when a mu changed (the caller re-maps its factor cache), flags[1] += converged
+ * problems, flags[2] = first non-positive pivot.  Per-problem criterion (or nb == 1).
+ * admm_spm_solo_supported: cluster size used (8) if L, Nw fit the cluster's shared memory, else 0. */
+int admm_spm_solo_supported(const admm_spm_dims* d);
+int admm_spm_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const double* G0, int niter,
+                  int interval_update_mu, admm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Pattern A engine: basis pursuit / LASSO  [LeastSquares, L1Regularizer], condition (1,0,I,I);  */

@@ -324,3 +324,58 @@ def test_spm_balanced_decomposition_shapes(eng, ir_basis, nb, Nw, mt, nbal):
     for b in (0, nb // 2, nb - 1):
         sb = flat.spm_solve(p.s, p.P, p.C, np.array([1.0]), p.g[:, b], p.lam, 90, mu=p.mu, interval_update_mu=20)
         assert rel(x0[:, b], sb.x0) < TOL and float(e2.mu20[b]) == sb.mu20
+
+
+# ------------------------------------------------------------------ cluster-resident single-launch solve
+@pytest.mark.parametrize("nb,Nw,eps,cplx", [(1, 2000, 1e-7, False), (1, 330, 1e-7, True), (5, 200, 1e-7, True),
+                                            (13, 136, 1e-2, True), (3, 264, 1e-10, True), (16, 97, 1e-7, False)])
+def test_spm_solo_cluster_solve(eng, nb, Nw, eps, cplx):
+    """admm_spm_solo (one 8-CTA cluster per problem, the whole solve in one launch, in-kernel mu update and
+    re-inversion): every problem == its own reference instance (oracle) incl. iteration count and mu, and
+    == the classic multi-kernel path; real and complex data, the three basis sizes, ragged Nw."""
+    from oracle import flat
+    batch, problems = eng
+    basis = problems.ir_basis(eps=eps)
+    p = problems.spm_batch(nb, basis, Nw=Nw, seed=40 + nb, complex_noise=cplx)
+    g = p.g if cplx else p.g.real.copy()
+    kw = dict(lam=p.lam, mu=p.mu, batch_wide=False)
+    e = batch.SharedSpM(p.s, p.P, p.C, p.D, g, **kw)
+    n = e.solve(330, interval_update_mu=30, rtol=1e-5, use_solo=True)
+    c = batch.SharedSpM(p.s, p.P, p.C, p.D, g, **kw)
+    c.solve(330, interval_update_mu=30, rtol=1e-5, use_solo=False)
+    x0, x1, x2, h10, h20 = e.x0(), e.x1(), e.x2(), e.h10(), e.h20()
+    iters = e.iters.cpu().numpy()
+    assert n == int(iters[:nb].max())
+    seen = set()
+    for b in range(nb):
+        sb = flat.spm_solve(p.s, p.P, p.C, np.array([1.0]), g[:, b], p.lam, 330, mu=p.mu, interval_update_mu=30, rtol=1e-5)
+        assert int(iters[b]) == sb.niter_done, (b, int(iters[b]), sb.niter_done)
+        assert float(e.mu10[b]) == sb.mu10 and float(e.mu20[b]) == sb.mu20
+        assert rel(x0[:, b], sb.x0) < TOL and rel(x1[:, b], sb.x1) < TOL and rel(x2[:, b], sb.x2) < TOL
+        assert rel(h10[:, b], sb.h10) < 1e-8 and rel(h20[:, b], sb.h20) < 1e-8
+        seen.add((sb.mu10, sb.mu20, sb.niter_done))
+    assert any(m10 != p.mu or m20 != p.mu for m10, m20, _ in seen)        # mu really changed in-kernel
+    assert rel(x0, c.x0()) < 1e-11 and rel(x2, c.x2()) < 1e-11
+    assert np.array_equal(iters[:nb], c.iters.cpu().numpy()[:nb])
+    if nb == 1:
+        sb = flat.spm_solve(p.s, p.P, p.C, np.array([1.0]), g[:, 0], p.lam, 330, mu=p.mu, interval_update_mu=30, rtol=1e-5)
+        assert rel(e.primal_residual, sb.primal) < 1e-8 and rel(e.dual_residual, sb.dual) < 1e-8
+
+
+def test_spm_solo_resume_and_handover(eng, ir_basis):
+    """Solo solve twice == oracle resumed; solo -> classic kernels -> solo on the same plan keeps the
+    state consistent (V, y0, mu20_used, factor slots) across the hand-overs, also right after a mu change."""
+    from oracle import flat
+    batch, problems = eng
+    p = problems.spm_batch(2, ir_basis, Nw=500, seed=77)
+    e = batch.SharedSpM(p.s, p.P, p.C, p.D, p.g, lam=p.lam, mu=p.mu, batch_wide=False)
+    kw = dict(mu=p.mu, interval_update_mu=25)
+    sts = [None, None]
+    for n, solo in ((26, True), (40, False), (1, True), (75, True), (30, False)):
+        e.solve(n, interval_update_mu=25, use_solo=solo)
+        for b in range(2):
+            sts[b] = flat.spm_solve(p.s, p.P, p.C, np.array([1.0]), p.g[:, b], p.lam, n, state=sts[b], **kw)
+            assert rel(e.x0()[:, b], sts[b].x0) < TOL and rel(e.x2()[:, b], sts[b].x2) < TOL, (n, solo, b)
+            assert rel(e.h20()[:, b], sts[b].h20) < 1e-8
+            assert float(e.mu10[b]) == sts[b].mu10 and float(e.mu20[b]) == sts[b].mu20
+    assert sts[0].mu20 != p.mu or sts[0].mu10 != p.mu

@@ -906,58 +906,62 @@ constexpr int SOLO_LWARPS = 4;
 constexpr int SOLO_RTHREADS = SOLO_THREADS - 32 * SOLO_LWARPS;
 
 struct SoloLayout {      // offsets in doubles into the dynamic shared memory
-  int P, Gi, PtP, rhs, xn, w, Cv, us, ss, xch, nA, nB, nBt, rowk, colk, total;
+  int R, P, Gi, PtP, rhs, xn, w, Cv, us, ss, xch, nA, nB, nBt, rowk, colk, total;
 };
-__host__ __device__ inline SoloLayout solo_layout(int L, int R, int npl) {
+// LP = padded L (d.Lp: 16, 40 or 64): every L-dimension is zero padded to LP so that the inner loops
+// have compile-time trip counts; R = sampling points per CTA, padded to a multiple of 32
+__host__ __device__ inline SoloLayout solo_layout(int LP, int Nwp, int cs, int npl) {
   SoloLayout o;
+  o.R = (((Nwp + cs - 1) / cs) + 31) & ~31;
   int at = 0;
   auto take = [&](int n) { const int r = at; at += (n + 1) & ~1; return r; };
-  o.P = take(L * R);
-  o.Gi = take(L * L);
-  o.PtP = take(L * L);
-  o.rhs = take(npl * L);
-  o.xn = take(npl * L);
-  o.w = take(L);
-  o.Cv = take(L);
-  o.us = take(R);
-  o.ss = take(R);
-  o.xch = take(2 * (L + 2));
+  o.P = take(LP * o.R);
+  o.Gi = take(LP * LP);
+  o.PtP = take(LP * LP);
+  o.rhs = take(npl * LP);
+  o.xn = take(npl * LP);
+  o.w = take(LP);
+  o.Cv = take(LP);
+  o.us = take(o.R);
+  o.ss = take(o.R);
+  o.xch = take(2 * (LP + 2));
   o.nA = take(SOLO_LWARPS * 8);
   o.nB = take((SOLO_THREADS / 32 - SOLO_LWARPS) * 2);
   o.nBt = take(2);
-  o.rowk = take(L);
-  o.colk = take(L);
+  o.rowk = take(LP);
+  o.colk = take(LP);
   o.total = at;
   return o;
 }
 
-// Gi <- (G0 + mu10 I + mu20 PtP)^-1 (in-place Gauss-Jordan, symmetrised), w = Gi C^T; returns sigma = C w
-// (objectivefunc.py:89-96,148-157).  All threads of the CTA; ends with the shared data visible.
-__device__ __forceinline__ double solo_factor(int L, int Lp, double mu10, double mu20, const double* __restrict__ G0,
+// Gi <- (G0 + mu10 I + mu20 PtP)^-1 (in-place Gauss-Jordan on the leading L x L block of the LP-pitched
+// array, symmetrised), w = Gi C^T; returns sigma = C w  (objectivefunc.py:89-96,148-157).  All threads of
+// the CTA; ends with the shared data visible.
+__device__ __forceinline__ double solo_factor(int L, int LP, double mu10, double mu20, const double* __restrict__ G0,
                                               const double* PtPs, double* Gi, double* wv, const double* Cv, double* rowk,
                                               double* colk, int* bad) {
   const int tid = threadIdx.x;
   for (int idx = tid; idx < L * L; idx += SOLO_THREADS) {
     const int i = idx / L, j = idx - i * L;
-    Gi[idx] = G0[(size_t)i * Lp + j] + (i == j ? mu10 : 0.0) + mu20 * PtPs[idx];
+    Gi[i * LP + j] = G0[(size_t)i * LP + j] + (i == j ? mu10 : 0.0) + mu20 * PtPs[i * LP + j];
   }
   __syncthreads();
   for (int k = 0; k < L; ++k) {
-    const double pv = Gi[k * L + k];
+    const double pv = Gi[k * LP + k];
     if (!(pv > 0.0)) *bad = k + 1;
     const double ip = 1.0 / pv;
     for (int j = tid; j < L; j += SOLO_THREADS) {
-      rowk[j] = (j == k ? 1.0 : Gi[k * L + j]) * ip;
-      colk[j] = (j == k ? 0.0 : Gi[j * L + k]);
+      rowk[j] = (j == k ? 1.0 : Gi[k * LP + j]) * ip;
+      colk[j] = (j == k ? 0.0 : Gi[j * LP + k]);
     }
     __syncthreads();
     for (int idx = tid; idx < L * L; idx += SOLO_THREADS) {
       const int i = idx / L, j = idx - i * L;
       if (i == k) {
-        Gi[idx] = rowk[j];
+        Gi[i * LP + j] = rowk[j];
       } else {
-        const double base = (j == k) ? 0.0 : Gi[idx];
-        Gi[idx] = base - colk[i] * rowk[j];
+        const double base = (j == k) ? 0.0 : Gi[i * LP + j];
+        Gi[i * LP + j] = base - colk[i] * rowk[j];
       }
     }
     __syncthreads();
@@ -965,15 +969,15 @@ __device__ __forceinline__ double solo_factor(int L, int Lp, double mu10, double
   for (int idx = tid; idx < L * L; idx += SOLO_THREADS) {
     const int i = idx / L, j = idx - i * L;
     if (i < j) {
-      const double v = 0.5 * (Gi[i * L + j] + Gi[j * L + i]);
-      Gi[i * L + j] = v;
-      Gi[j * L + i] = v;
+      const double v = 0.5 * (Gi[i * LP + j] + Gi[j * LP + i]);
+      Gi[i * LP + j] = v;
+      Gi[j * LP + i] = v;
     }
   }
   __syncthreads();
   for (int i = tid; i < L; i += SOLO_THREADS) {
     double a = 0.0;
-    for (int j = 0; j < L; ++j) a += Gi[i * L + j] * Cv[j];
+    for (int j = 0; j < L; ++j) a += Gi[i * LP + j] * Cv[j];
     wv[i] = a;
   }
   __syncthreads();
@@ -982,39 +986,56 @@ __device__ __forceinline__ double solo_factor(int L, int Lp, double mu10, double
   return sigma;
 }
 
-template <int CS>
+// out = sum_j M[j * LP + l] * v[j]  (M symmetric, LP-pitched, zero padded; v zero padded): four chains
+template <int LP>
+__device__ __forceinline__ double solo_matvec(const double* __restrict__ Mcol, const double* __restrict__ v) {
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int j = 0; j < LP; j += 4) {
+    const double2 v01 = *reinterpret_cast<const double2*>(v + j);
+    const double2 v23 = *reinterpret_cast<const double2*>(v + j + 2);
+    a[0] += Mcol[(j + 0) * LP] * v01.x;
+    a[1] += Mcol[(j + 1) * LP] * v01.y;
+    a[2] += Mcol[(j + 2) * LP] * v23.x;
+    a[3] += Mcol[(j + 3) * LP] * v23.y;
+  }
+  return (a[0] + a[1]) + (a[2] + a[3]);
+}
+
+template <int CS, int LP>
 __global__ void __launch_bounds__(SOLO_THREADS, 1)
     spm_solo_kernel(admm_spm_dims d, admm_spm_buffers b, const double* __restrict__ G0, int budget, int interval) {
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = CS > 1 ? (int)cluster.block_rank() : 0;
   const int prob = blockIdx.x / CS;
   if (b.done[prob]) return;                                 // uniform over the cluster
+  constexpr int NT = LP / 8, NW = SOLO_THREADS / 32, NRW = NW - SOLO_LWARPS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int L = d.L, Lp = d.Lp, NT = d.Lp / 8, npl = d.nplanes;
+  const int L = d.L, npl = d.nplanes;
   const int pt = prob >> 3, g = prob & 7;
   const int Nwp = d.nrt * 8;
-  const int R = (Nwp + CS - 1) / CS;                        // sampling points per CTA
-  const int row0 = crank * R, nrow = max(0, min(R, Nwp - row0));
   extern __shared__ __align__(16) double sm[];
-  const SoloLayout lay = solo_layout(L, R, npl);
+  const SoloLayout lay = solo_layout(LP, Nwp, CS, npl);
+  const int R = lay.R;                                      // sampling points per CTA (padded)
+  const int row0 = crank * R, nrow = max(0, min(R, Nwp - row0));
   double* Psm = sm + lay.P;        // [l][i]: P[row0 + i][l]
-  double* Gi = sm + lay.Gi;        // [L][L], symmetric
-  double* PtPs = sm + lay.PtP;     // [L][L], symmetric
-  double* rhs = sm + lay.rhs;      // [plane][l]
-  double* xn = sm + lay.xn;        // [plane][l]: the new x0
+  double* Gi = sm + lay.Gi;        // [LP][LP], symmetric
+  double* PtPs = sm + lay.PtP;     // [LP][LP], symmetric
+  double* rhs = sm + lay.rhs;      // [plane][LP]
+  double* xn = sm + lay.xn;        // [plane][LP]: the new x0
   double* wv = sm + lay.w;
   double* Cv = sm + lay.Cv;
   double* us = sm + lay.us;        // [i]: operand of V = P^T u
   double* ss = sm + lay.ss;        // [i]: implicit state  s = Re h20 - mu20 x2
-  double* xch = sm + lay.xch;      // [2][L + 2]: my partial V and norm partials (ping-pong)
+  double* xch = sm + lay.xch;      // [2][LP + 2]: my partial V and norm partials (ping-pong)
   double* nA = sm + lay.nA;        // [L-space warp][8]
   double* nB = sm + lay.nB;        // [row warp][2]
   double* nBt = sm + lay.nBt;      // [2] cluster totals
   __shared__ int bad_sh;
 
-  // ---- one-time loads
+  // ---- one-time loads (everything zero padded)
   if (tid == 0) bad_sh = 0;
-  for (int idx = tid; idx < L * R; idx += SOLO_THREADS) {
+  for (int idx = tid; idx < LP * R; idx += SOLO_THREADS) {
     const int l = idx / R, i = idx - l * R;
     const int row = row0 + i;
     double v = 0.0;
@@ -1022,24 +1043,27 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
     Psm[idx] = v;
   }
   const int slot = b.slot[prob];
-  for (int idx = tid; idx < L * L; idx += SOLO_THREADS) {
-    const int i = idx / L, j = idx - i * L;
+  for (int idx = tid; idx < LP * LP; idx += SOLO_THREADS) {
+    const int i = idx / LP, j = idx - i * LP;
     const size_t o = bfrag_of(NT, i, j);
-    Gi[idx] = b.Ginv_cache[(size_t)slot * Lp * Lp + o];
+    Gi[idx] = b.Ginv_cache[(size_t)slot * LP * LP + o];
     PtPs[idx] = b.PtPf[o];
   }
-  for (int i = tid; i < L; i += SOLO_THREADS) {
-    wv[i] = b.w_cache[(size_t)slot * Lp + i];
+  for (int i = tid; i < LP; i += SOLO_THREADS) {
+    wv[i] = b.w_cache[(size_t)slot * LP + i];
     Cv[i] = b.Cvec[i];
   }
+  for (int i = tid; i < npl * LP; i += SOLO_THREADS) rhs[i] = xn[i] = 0.0;
   for (int i = tid; i < R; i += SOLO_THREADS) {
     const int row = row0 + i;
     ss[i] = i < nrow ? b.S[state_index(d, pt, row >> 3, 4 * g + ((row & 7) >> 1)) + (row & 1)] : 0.0;
+    us[i] = 0.0;
   }
   double sigma = b.sigma_cache[slot];
   double mu10 = b.mu10[prob], mu20 = b.mu20[prob];
   double mu20_enc = b.mu20_used[prob];            // the mu20 the negative part of s is scaled with
   int it = b.iters[prob];
+  __syncthreads();
 
   // L-space threads: (plane, l) and their vector elements, in registers for the whole solve
   const bool lth = warp < SOLO_LWARPS;
@@ -1055,47 +1079,57 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
     r_aim = b.aim[fo];
     if (pl == 1) r_V = b.V[fo];                   // z = P^T Im(h20): state, not derived
     Dp = b.Dre[(size_t)pl * 8 * d.npt + prob];
-    xn[pl * L + l] = r_x0;
+    xn[pl * LP + l] = r_x0;
   }
   __syncthreads();
-  if (lact) {                                     // y0 = P^T P x0
-    double a = 0.0;
-    for (int j = 0; j < L; ++j) a += PtPs[j * L + l] * xn[pl * L + j];
-    r_y0 = a;
-  }
+  if (lact) r_y0 = solo_matvec<LP>(PtPs + l, xn + pl * LP);     // y0 = P^T P x0
 
   int phase = 0;
   bool need_v = true;          // V (real plane) has to be rebuilt from the state (start, change of mu20)
   bool mu_changed = false;
   int conv = 0;
-  double primal = 0.0, dual = 0.0;
+  // uniform reciprocals (FP64 division and square root are long instruction sequences on the pipe the
+  // whole CTA shares: they are kept out of the per-iteration path)
+  double inv_mu10 = 1.0 / mu10, inv_sigma = 1.0 / sigma, inv_mu20sq = 1.0 / (mu20 * mu20), thr = 0.5 * b.lam / mu10;
+  const double rtol2 = b.rtol * b.rtol;
+  double sq[4] = {0.0, 0.0, 0.0, 0.0};     // |x0-x1|^2, |P x0-x2|^2, |dx0|^2, |P dx0|^2 of the last iteration
+  double mu10_res = mu10, mu20_res = mu20; // the mu they are to be scaled with
+  bool hist_pending = false;
+  int hist_it = 0;
 
   // partial V of my sampling points from us[], exchange, total into r_V of the (0, l) threads; the two
-  // norm partials ride along
-  auto exchange = [&](double nb0, double nb1) {
-    double* mine = xch + phase * (L + 2);
-    constexpr int NW = SOLO_THREADS / 32;
-    for (int l0 = warp; l0 < L; l0 += 4 * NW) {
-      double a[4] = {0.0, 0.0, 0.0, 0.0};
-      for (int i = lane; i < R; i += 32) {
-        const double u = us[i];
+  // norm partials ride along.  Warp w sums the columns l = w, w + NW, ... (at most 4 for L <= 48, else 6).
+  constexpr int NQ = (LP + NW - 1) / NW;
+  auto exchange = [&](bool with_norms) {
+    double* mine = xch + phase * (LP + 2);
+    {
+      double a[NQ];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int lq = l0 + q * NW;
-          if (lq < L) a[q] += u * Psm[lq * R + i];
-        }
+      for (int q = 0; q < NQ; ++q) a[q] = 0.0;
+      const double* pc = Psm + min(warp, LP - 1) * R + lane;   // (clamped: unused columns are skipped below)
+#pragma unroll 4
+      for (int i = 0; i < R; i += 32) {
+        const double u = us[i + lane];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+          if (warp + q * NW < LP) a[q] += u * pc[q * NW * R + i];
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) a[q] = warp_sum(a[q]);
+      for (int q = 0; q < NQ; ++q) a[q] = warp_sum(a[q]);
       if (lane == 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (l0 + q * NW < L) mine[l0 + q * NW] = a[q];
+        for (int q = 0; q < NQ; ++q)
+          if (warp + q * NW < LP) mine[warp + q * NW] = a[q];
       }
     }
-    if (tid == 0) {
-      mine[L] = nb0;
-      mine[L + 1] = nb1;
+    if (tid < 2) {
+      double a = 0.0;
+      if (with_norms) {
+#pragma unroll
+        for (int w2 = 0; w2 < NRW; ++w2) a += nB[w2 * 2 + tid];
+        a *= inv_mu20sq;
+      }
+      mine[LP + tid] = a;
     }
     if (CS > 1) cluster.sync(); else __syncthreads();
     if (lact && pl == 0) {
@@ -1107,7 +1141,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
     if (warp == SOLO_LWARPS && lane < 2) {
       double a = 0.0;
 #pragma unroll
-      for (int c = 0; c < CS; ++c) a += (CS > 1 ? cluster.map_shared_rank(mine, c) : mine)[L + lane];
+      for (int c = 0; c < CS; ++c) a += (CS > 1 ? cluster.map_shared_rank(mine, c) : mine)[LP + lane];
       nBt[lane] = a;
     }
     phase ^= 1;
@@ -1123,32 +1157,39 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
         us[i] = is_neg(s) ? -s * ratio : s;
       }
       __syncthreads();
-      exchange(0.0, 0.0);
+      exchange(false);
       need_v = false;
     }
     if (k >= budget) break;
 
     // ---- term 0: rhs, cached inverse, KKT correction (C Gi rhs = w . rhs because Gi is symmetric)
-    if (lact) rhs[pl * L + l] = r_b0 + r_h10 + mu10 * r_x1 + r_V;
+    if (lact) rhs[pl * LP + l] = r_b0 + r_h10 + mu10 * r_x1 + r_V;
     __syncthreads();
+    if (hist_pending && warp == NW - 1) {
+      // residual() of the previous iteration (this warp idles while the L-space warps solve term 0)
+      if (crank == 0 && lane == 0 && prob == 0 && b.history && hist_it < b.hist_cap) {
+        b.history[2 * hist_it] = sqrt(sq[0]) + sqrt(sq[1]);
+        b.history[2 * hist_it + 1] = mu10_res * sqrt(sq[2]) + mu20_res * sqrt(sq[3]);
+      }
+    }
+    hist_pending = false;
     double xv = 0.0;
     if (lact) {
-      double a0 = 0.0, a1 = 0.0, c0 = 0.0, c1 = 0.0;
-      const double* rp = rhs + pl * L;
-      int j = 0;
-      for (; j + 1 < L; j += 2) {
-        a0 += Gi[j * L + l] * rp[j];
-        a1 += Gi[(j + 1) * L + l] * rp[j + 1];
-        c0 += wv[j] * rp[j];
-        c1 += wv[j + 1] * rp[j + 1];
+      const double* rp = rhs + pl * LP;
+      const double xi = solo_matvec<LP>(Gi + l, rp);
+      double c[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int j = 0; j < LP; j += 4) {
+        const double2 r01 = *reinterpret_cast<const double2*>(rp + j), r23 = *reinterpret_cast<const double2*>(rp + j + 2);
+        const double2 w01 = *reinterpret_cast<const double2*>(wv + j), w23 = *reinterpret_cast<const double2*>(wv + j + 2);
+        c[0] += w01.x * r01.x;
+        c[1] += w01.y * r01.y;
+        c[2] += w23.x * r23.x;
+        c[3] += w23.y * r23.y;
       }
-      if (j < L) {
-        a0 += Gi[j * L + l] * rp[j];
-        c0 += wv[j] * rp[j];
-      }
-      const double nu = (Dp - (c0 + c1)) / sigma;
-      xv = (a0 + a1) + wv[l] * nu;
-      xn[pl * L + l] = xv;
+      const double nu = (Dp - ((c[0] + c[1]) + (c[2] + c[3]))) * inv_sigma;
+      xv = xi + wv[l] * nu;
+      xn[pl * LP + l] = xv;
     }
     __syncthreads();
 
@@ -1156,15 +1197,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
       // ---- y = P^T P x0, norms, L1 z-update, dual ascent of pair (1,0), imaginary-plane recursion
       double n[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       if (lact) {
-        double y0a = 0.0, y1a = 0.0;
-        const double* xp = xn + pl * L;
-        int j = 0;
-        for (; j + 1 < L; j += 2) {
-          y0a += PtPs[j * L + l] * xp[j];
-          y1a += PtPs[(j + 1) * L + l] * xp[j + 1];
-        }
-        if (j < L) y0a += PtPs[j * L + l] * xp[j];
-        const double y = y0a + y1a;
+        const double y = solo_matvec<LP>(PtPs + l, xn + pl * LP);
         const double dd = xv - r_x0;
         n[3] = dd * dd;
         n[4] = r_x0 * r_x0;
@@ -1173,8 +1206,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
         n[7] = xv * y;
         double z = 0.0;
         if (pl == 0) {
-          const double thr = 0.5 * b.lam / mu10;
-          const double yv = -((r_h10 - mu10 * xv) / mu10);
+          const double yv = -((r_h10 - mu10 * xv) * inv_mu10);
           if (yv > thr) z = yv - thr;
           if (yv < -thr) z = yv + thr;
         } else {
@@ -1199,16 +1231,19 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
       // ---- my sampling points: s' = Re h20 - mu20 (P Re x0) encodes dual ascent and projection
       double n_dh = 0.0, n_xm = 0.0;
       for (int i = tid - 32 * SOLO_LWARPS; i < R; i += SOLO_RTHREADS) {
-        double q0 = 0.0, q1 = 0.0;
-        int j = 0;
-        for (; j + 1 < L; j += 2) {
-          q0 += Psm[j * R + i] * xn[j];
-          q1 += Psm[(j + 1) * R + i] * xn[j + 1];
+        double q[4] = {0.0, 0.0, 0.0, 0.0};
+        const double* pr = Psm + i;
+#pragma unroll
+        for (int j = 0; j < LP; j += 4) {
+          const double2 x01 = *reinterpret_cast<const double2*>(xn + j), x23 = *reinterpret_cast<const double2*>(xn + j + 2);
+          q[0] += pr[(j + 0) * R] * x01.x;
+          q[1] += pr[(j + 1) * R] * x01.y;
+          q[2] += pr[(j + 2) * R] * x23.x;
+          q[3] += pr[(j + 3) * R] * x23.y;
         }
-        if (j < L) q0 += Psm[j * R + i] * xn[j];
         const double s = ss[i];
         const double hre = is_neg(s) ? 0.0 : s;
-        const double s_new = hre - mu20 * (q0 + q1);
+        const double s_new = hre - mu20 * ((q[0] + q[1]) + (q[2] + q[3]));
         const bool neg = is_neg(s_new);
         const double hnew = neg ? 0.0 : s_new;
         const double xm = neg ? s_new : 0.0;
@@ -1227,19 +1262,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
     }
     mu20_enc = mu20;
     __syncthreads();
-    {
-      double nb0 = 0.0, nb1 = 0.0;
-      if (tid == 0) {
-        for (int w2 = 0; w2 < SOLO_THREADS / 32 - SOLO_LWARPS; ++w2) {
-          nb0 += nB[w2 * 2];
-          nb1 += nB[w2 * 2 + 1];
-        }
-        const double inv = 1.0 / mu20;
-        nb0 *= inv * inv;
-        nb1 *= inv * inv;
-      }
-      exchange(nb0, nb1);
-    }
+    exchange(true);
 
     // ---- residual() / check_convergence() / update_mu(): every thread, identical numbers
     double s[10];
@@ -1258,33 +1281,44 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
     }
     s[7] += nBt[0];
     s[8] += nBt[1];
-    const double p10 = sqrt(s[0]), nx0 = sqrt(s[1]), nx1 = sqrt(s[2]), nd = sqrt(s[3]), nxo = sqrt(s[4]);
-    const double nPd = sqrt(s[5]), nPxo = sqrt(s[6]), p20 = sqrt(s[7]), nx2 = sqrt(s[8]), nPx0 = sqrt(s[9]);
-    const double d10 = mu10 * nd, d20 = mu20 * nPd;
-    primal = p10 + p20;
-    dual = d10 + d20;
-    if (crank == 0 && tid == 0 && prob == 0 && b.history && it < b.hist_cap) {
-      b.history[2 * it] = primal;
-      b.history[2 * it + 1] = dual;
-    }
+    // check_convergence (optimizer.py:232-249) on the squared norms: p / max(a, b) < rtol  <=>
+    // p^2 < rtol^2 max(a^2, b^2)  (mu > 0 cancels in the dual tests; 0/0 and x/0 stay "not converged")
+    sq[0] = s[0];
+    sq[1] = s[7];
+    sq[2] = s[3];
+    sq[3] = s[5];
+    mu10_res = mu10;
+    mu20_res = mu20;
+    hist_pending = true;
+    hist_it = it;
     const int this_it = it;
     ++it;
-    const bool cv = (p10 / fmax(nx0, nx1) < b.rtol) && (d10 / fmax(mu10 * nx0, mu10 * nxo) < b.rtol) &&
-                    (p20 / fmax(nPx0, nx2) < b.rtol) && (d20 / fmax(mu20 * nPx0, mu20 * nPxo) < b.rtol);
+    const bool cv = (s[0] < rtol2 * fmax(s[1], s[2])) && (s[3] < rtol2 * fmax(s[1], s[4])) &&
+                    (s[7] < rtol2 * fmax(s[9], s[8])) && (s[5] < rtol2 * fmax(s[9], s[6]));
     if (cv) {
       conv = 1;
       break;
     }
     if (interval > 0 && this_it % interval == 0) {
+      const double p10 = sqrt(s[0]), p20 = sqrt(s[7]), d10 = mu10 * sqrt(s[3]), d20 = mu20 * sqrt(s[5]);
       const double m10 = mu_step(mu10, p10, d10, b), m20 = mu_step(mu20, p20, d20, b);
       if (m10 != mu10 || m20 != mu20) {
         mu10 = m10;
         mu20 = m20;
         mu_changed = true;
         need_v = true;
-        sigma = solo_factor(L, Lp, mu10, mu20, G0, PtPs, Gi, wv, Cv, sm + lay.rowk, sm + lay.colk, &bad_sh);
+        sigma = solo_factor(L, LP, mu10, mu20, G0, PtPs, Gi, wv, Cv, sm + lay.rowk, sm + lay.colk, &bad_sh);
+        inv_mu10 = 1.0 / mu10;
+        inv_sigma = 1.0 / sigma;
+        inv_mu20sq = 1.0 / (mu20 * mu20);
+        thr = 0.5 * b.lam / mu10;
       }
     }
+  }
+  const double primal = sqrt(sq[0]) + sqrt(sq[1]), dual = mu10_res * sqrt(sq[2]) + mu20_res * sqrt(sq[3]);
+  if (hist_pending && crank == 0 && tid == 0 && prob == 0 && b.history && hist_it < b.hist_cap) {
+    b.history[2 * hist_it] = primal;
+    b.history[2 * hist_it + 1] = dual;
   }
 
   // ---- write the state back in the layouts of the batch kernels
@@ -1383,6 +1417,40 @@ static int launch_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mo
     default:
       return launch_pass_mode<8, 1>(d, b, mode, fused, s);
   }
+}
+
+static size_t solo_smem_bytes(const admm_spm_dims* d, int cs) {
+  return (size_t)solo_layout(d->Lp, d->nrt * 8, cs, d->nplanes).total * sizeof(double);
+}
+
+template <int CS, int LP>
+static int launch_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const double* G0, int niter, int interval,
+                       cudaStream_t st) {
+  const size_t smem = solo_smem_bytes(d, CS);
+  auto kern = spm_solo_kernel<CS, LP>;
+  static size_t configured = 0;     // per instantiation
+  if (smem > configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(d->nb * CS);
+  cfg.blockDim = dim3(SOLO_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *d, *b, G0, niter, interval);
+  if (e != cudaSuccess) {
+    set_error("admm_spm_solo: %s", cudaGetErrorString(e));
+    return ADMM_ECUDA;
+  }
+  return check_launch("admm_spm_solo");
 }
 
 }  // namespace admm
@@ -1510,13 +1578,8 @@ int admm_spm_reduce_decide(const admm_spm_dims* d, const admm_spm_buffers* b, in
   return check_launch("admm_spm_reduce_decide");
 }
 
-static size_t solo_smem_bytes(const admm_spm_dims* d, int cs) {
-  const int R = (d->nrt * 8 + cs - 1) / cs;
-  return (size_t)solo_layout(d->L, R, d->nplanes).total * sizeof(double);
-}
-
 int admm_spm_solo_supported(const admm_spm_dims* d) {
-  if (d == nullptr || d->L < 1 || d->L > 64 || d->nb < 1) return 0;
+  if (d == nullptr || d->L < 1 || (d->Lp != 16 && d->Lp != 40 && d->Lp != 64) || d->nb < 1) return 0;
   return solo_smem_bytes(d, 8) <= 200 * 1024 ? 8 : 0;
 }
 
@@ -1527,32 +1590,12 @@ int admm_spm_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const doubl
   ADMM_REQUIRE(admm_spm_solo_supported(d) != 0, ADMM_EUNSUPPORTED,
                "admm_spm_solo: L=%d, Nw=%d do not fit the shared memory of an 8-CTA cluster", d->L, d->Nw);
   ADMM_REQUIRE(G0 != nullptr && niter >= 0 && interval_update_mu >= 0, ADMM_EINVAL, "admm_spm_solo: bad arguments");
-  constexpr int CS = 8;
-  const size_t smem = solo_smem_bytes(d, CS);
-  auto kern = spm_solo_kernel<CS>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (d->Lp) {
+    case 16: return launch_solo<8, 16>(d, b, G0, niter, interval_update_mu, st);
+    case 40: return launch_solo<8, 40>(d, b, G0, niter, interval_update_mu, st);
+    default: return launch_solo<8, 64>(d, b, G0, niter, interval_update_mu, st);
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(d->nb * CS);
-  cfg.blockDim = dim3(SOLO_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = static_cast<cudaStream_t>(stream);
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CS;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *d, *b, G0, niter, interval_update_mu);
-  if (e != cudaSuccess) {
-    set_error("admm_spm_solo: %s", cudaGetErrorString(e));
-    return ADMM_ECUDA;
-  }
-  return check_launch("admm_spm_solo");
 }
 
 }  // extern "C"

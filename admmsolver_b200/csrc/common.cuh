@@ -129,6 +129,33 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
                : "memory");
 }
 
+// ---- distributed shared memory push: remote store that signals the DESTINATION CTA's mbarrier ----
+__device__ __forceinline__ unsigned mapa_u32(unsigned smem_addr, unsigned cta_rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+  return r;
+}
+// 8-byte store into a peer CTA's shared memory; completes 8 tx-bytes on the peer's mbarrier (SASS: ST.ASYNC... /
+// UBLKCP-free DSMEM path): the receiver only waits on its own barrier -- no cluster barrier, no fence
+__device__ __forceinline__ void st_async_f64(unsigned remote_addr, double v, unsigned remote_bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];\n" ::"r"(remote_addr),
+               "l"(__double_as_longlong(v)), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 inline int ceil_div(long long a, long long b) { return int((a + b - 1) / b); }
 
 }  // namespace admm

@@ -906,25 +906,27 @@ constexpr int SOLO_LWARPS = 4;
 constexpr int SOLO_RTHREADS = SOLO_THREADS - 32 * SOLO_LWARPS;
 
 struct SoloLayout {      // offsets in doubles into the dynamic shared memory
-  int R, P, Gi, PtP, rhs, xn, w, Cv, us, ss, xch, nA, nB, nBt, rowk, colk, total;
+  int R, P, Gi, PtP, rhs, xn, w, Cv, us, ss, xch, vp, nA, nB, nBt, rowk, colk, total;
 };
 // LP = padded L (d.Lp: 16, 40 or 64): every L-dimension is zero padded to LP so that the inner loops
 // have compile-time trip counts; R = sampling points per CTA, padded to a multiple of 32
-__host__ __device__ inline SoloLayout solo_layout(int LP, int Nwp, int cs, int npl) {
+// regp: P, the state and u live in the registers of the sampling-point threads (needs R <= SOLO_RTHREADS)
+__host__ __device__ inline SoloLayout solo_layout(int LP, int Nwp, int cs, int npl, bool regp) {
   SoloLayout o;
   o.R = (((Nwp + cs - 1) / cs) + 31) & ~31;
   int at = 0;
   auto take = [&](int n) { const int r = at; at += (n + 1) & ~1; return r; };
-  o.P = take(LP * o.R);
+  o.P = take(regp ? 0 : LP * o.R);
   o.Gi = take(LP * LP);
   o.PtP = take(LP * LP);
   o.rhs = take(npl * LP);
   o.xn = take(npl * LP);
   o.w = take(LP);
   o.Cv = take(LP);
-  o.us = take(o.R);
-  o.ss = take(o.R);
-  o.xch = take(2 * (LP + 2));
+  o.us = take(regp ? 0 : o.R);
+  o.ss = take(regp ? 0 : o.R);
+  o.xch = take(2 * cs * (LP + 2) + 2);          // [2][cs][LP + 2] receive slots + two mbarriers
+  o.vp = take(regp ? (SOLO_THREADS / 32 - SOLO_LWARPS) * LP : 0);
   o.nA = take(SOLO_LWARPS * 8);
   o.nB = take((SOLO_THREADS / 32 - SOLO_LWARPS) * 2);
   o.nBt = take(2);
@@ -1002,7 +1004,35 @@ __device__ __forceinline__ double solo_matvec(const double* __restrict__ Mcol, c
   return (a[0] + a[1]) + (a[2] + a[3]);
 }
 
-template <int CS, int LP>
+// Sum each of W (power of two <= 32) per-lane values over the 32 lanes of the warp with W - 1 + (5 - log2 W)
+// shuffles instead of 5 W: every halving step trades half of the values with the partner lane.  Afterwards
+// v[0] of lane `lane` is the complete sum of value index  lane >> (5 - log2 W).
+template <int W>
+__device__ __forceinline__ void solo_treduce(double (&v)[W], int lane) {
+  int o = 16;
+#pragma unroll
+  for (int n = W / 2; n >= 1; n /= 2, o /= 2) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int k = 0; k < n; ++k) {
+      const double send = up ? v[k] : v[k + n];
+      const double keep = up ? v[k + n] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+#pragma unroll
+  for (; o >= 1; o /= 2) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+}
+
+#ifdef SOLO_TRACE   // tools only: clock64 stamps of warps 0 and 4 of CTA 0 for iterations 10..13 into b.gpart
+#define SOLO_STAMP(idx)                                                                                   \
+  if (crank == 0 && lane == 0 && (warp == 0 || warp == SOLO_LWARPS) && k >= 10 && k < 14)                 \
+    reinterpret_cast<long long*>(b.gpart)[((k - 10) * 2 + (warp != 0)) * 16 + (idx)] = clock64();
+#else
+#define SOLO_STAMP(idx)
+#endif
+
+template <int CS, int LP, bool REGP>
 __global__ void __launch_bounds__(SOLO_THREADS, 1)
     spm_solo_kernel(admm_spm_dims d, admm_spm_buffers b, const double* __restrict__ G0, int budget, int interval) {
   cg::cluster_group cluster = cg::this_cluster();
@@ -1015,7 +1045,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
   const int pt = prob >> 3, g = prob & 7;
   const int Nwp = d.nrt * 8;
   extern __shared__ __align__(16) double sm[];
-  const SoloLayout lay = solo_layout(LP, Nwp, CS, npl);
+  const SoloLayout lay = solo_layout(LP, Nwp, CS, npl, REGP);
   const int R = lay.R;                                      // sampling points per CTA (padded)
   const int row0 = crank * R, nrow = max(0, min(R, Nwp - row0));
   double* Psm = sm + lay.P;        // [l][i]: P[row0 + i][l]
@@ -1027,7 +1057,9 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
   double* Cv = sm + lay.Cv;
   double* us = sm + lay.us;        // [i]: operand of V = P^T u
   double* ss = sm + lay.ss;        // [i]: implicit state  s = Re h20 - mu20 x2
-  double* xch = sm + lay.xch;      // [2][LP + 2]: my partial V and norm partials (ping-pong)
+  double* xch = sm + lay.xch;      // [2][CS][LP + 2]: partial V and norm partials pushed by every CTA of the cluster
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(xch + 2 * CS * (LP + 2));   // [2]
+  double* vp = sm + lay.vp;        // [row warp][LP]: per-warp partial V (REGP)
   double* nA = sm + lay.nA;        // [L-space warp][8]
   double* nB = sm + lay.nB;        // [row warp][2]
   double* nBt = sm + lay.nBt;      // [2] cluster totals
@@ -1035,12 +1067,29 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
 
   // ---- one-time loads (everything zero padded)
   if (tid == 0) bad_sh = 0;
-  for (int idx = tid; idx < LP * R; idx += SOLO_THREADS) {
-    const int l = idx / R, i = idx - l * R;
-    const int row = row0 + i;
-    double v = 0.0;
-    if (i < nrow) v = b.Pf[((size_t)(row >> 3) * 2 * NT + (l >> 3)) * 64 + (4 * (row & 7) + ((l & 7) >> 1)) * 2 + (l & 1)];
-    Psm[idx] = v;
+  // sampling-point thread rt owns point row0 + rt (REGP: its row of P, s and u never leave the registers)
+  const int rt = tid - 32 * SOLO_LWARPS;
+  // Kreg: row of P (sampling-point threads) or column l of the cached inverse (L-space threads): ONE array,
+  // the two roles never meet in a thread
+  double Kreg[REGP ? LP : 1], s_reg = 0.0, u_reg = 0.0;
+  if (REGP) {
+#pragma unroll
+    for (int j = 0; j < (REGP ? LP : 1); ++j) Kreg[j] = 0.0;
+    if (rt >= 0 && rt < nrow) {
+      const int row = row0 + rt;
+      const double* pf = b.Pf + (size_t)(row >> 3) * 2 * NT * 64 + 4 * (row & 7) * 2;
+#pragma unroll
+      for (int j = 0; j < (REGP ? LP : 1); ++j) Kreg[j] = pf[(j >> 3) * 64 + ((j & 7) >> 1) * 2 + (j & 1)];
+      s_reg = b.S[state_index(d, pt, row >> 3, 4 * g + ((row & 7) >> 1)) + (row & 1)];
+    }
+  } else {
+    for (int idx = tid; idx < LP * R; idx += SOLO_THREADS) {
+      const int l = idx / R, i = idx - l * R;
+      const int row = row0 + i;
+      double v = 0.0;
+      if (i < nrow) v = b.Pf[((size_t)(row >> 3) * 2 * NT + (l >> 3)) * 64 + (4 * (row & 7) + ((l & 7) >> 1)) * 2 + (l & 1)];
+      Psm[idx] = v;
+    }
   }
   const int slot = b.slot[prob];
   for (int idx = tid; idx < LP * LP; idx += SOLO_THREADS) {
@@ -1054,16 +1103,36 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
     Cv[i] = b.Cvec[i];
   }
   for (int i = tid; i < npl * LP; i += SOLO_THREADS) rhs[i] = xn[i] = 0.0;
-  for (int i = tid; i < R; i += SOLO_THREADS) {
-    const int row = row0 + i;
-    ss[i] = i < nrow ? b.S[state_index(d, pt, row >> 3, 4 * g + ((row & 7) >> 1)) + (row & 1)] : 0.0;
-    us[i] = 0.0;
+  if (!REGP) {
+    for (int i = tid; i < R; i += SOLO_THREADS) {
+      const int row = row0 + i;
+      ss[i] = i < nrow ? b.S[state_index(d, pt, row >> 3, 4 * g + ((row & 7) >> 1)) + (row & 1)] : 0.0;
+      us[i] = 0.0;
+    }
   }
   double sigma = b.sigma_cache[slot];
   double mu10 = b.mu10[prob], mu20 = b.mu20[prob];
   double mu20_enc = b.mu20_used[prob];            // the mu20 the negative part of s is scaled with
   int it = b.iters[prob];
-  __syncthreads();
+  // receive barriers: armed for the first use of each buffer; nobody pushes before every CTA is set up
+  constexpr unsigned XBYTES = CS * (LP + 2) * sizeof(double);
+  if (tid == 0) {
+    mbar_init(xbar, 1);
+    mbar_init(xbar + 1, 1);
+    fence_barrier_init();
+    mbar_expect_tx(xbar, XBYTES);
+    mbar_expect_tx(xbar + 1, XBYTES);
+  }
+  cluster.sync();
+  unsigned xpar = 0u;      // bit p: parity of the next completion of receive barrier p
+  const unsigned xch_u32 = smem_u32(xch), xbar_u32 = smem_u32(xbar);
+  // push value `v` of entry `e` (column or norm slot) of exchange buffer `ph` to every CTA of the cluster
+  auto push_all = [&](int ph, int e, double v) {
+    const unsigned slot = xch_u32 + ((ph * CS + crank) * (LP + 2) + e) * (unsigned)sizeof(double);
+    const unsigned bar = xbar_u32 + ph * (unsigned)sizeof(uint64_t);
+#pragma unroll
+    for (int c = 0; c < CS; ++c) st_async_f64(mapa_u32(slot, c), v, mapa_u32(bar, c));
+  };
 
   // L-space threads: (plane, l) and their vector elements, in registers for the whole solve
   const bool lth = warp < SOLO_LWARPS;
@@ -1083,6 +1152,13 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
   }
   __syncthreads();
   if (lact) r_y0 = solo_matvec<LP>(PtPs + l, xn + pl * LP);     // y0 = P^T P x0
+  auto load_gcol = [&]() {                                      // column l of the cached inverse
+    if (REGP && lth) {
+#pragma unroll
+      for (int j = 0; j < (REGP ? LP : 1); ++j) Kreg[j] = lact ? Gi[j * LP + l] : 0.0;
+    }
+  };
+  load_gcol();
 
   int phase = 0;
   bool need_v = true;          // V (real plane) has to be rebuilt from the state (start, change of mu20)
@@ -1096,13 +1172,43 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
   double mu10_res = mu10, mu20_res = mu20; // the mu they are to be scaled with
   bool hist_pending = false;
   int hist_it = 0;
+  int until_upd = interval > 0 ? (interval - it % interval) % interval : -1;   // iterations until the next update_mu
 
   // partial V of my sampling points from us[], exchange, total into r_V of the (0, l) threads; the two
   // norm partials ride along.  Warp w sums the columns l = w, w + NW, ... (at most 4 for L <= 48, else 6).
   constexpr int NQ = (LP + NW - 1) / NW;
+  int k = 0;
   auto exchange = [&](bool with_norms) {
-    double* mine = xch + phase * (LP + 2);
-    {
+    const double* slots = xch + phase * CS * (LP + 2);
+    if (REGP) {
+      // per-warp partial V by transposed warp reductions of u * P[row][:] (16 or 8 columns at a time)
+      if (!lth) {
+        double* vw = vp + (warp - SOLO_LWARPS) * LP;
+#pragma unroll
+        for (int base = 0; base < (REGP ? LP : 0); base += 16) {
+          if (LP - base >= 16) {
+            double v[16];
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) v[k2] = u_reg * Kreg[REGP ? base + k2 : 0];
+            solo_treduce<16>(v, lane);
+            if ((lane & 1) == 0) vw[base + (lane >> 1)] = v[0];
+          } else {
+            double v[8];
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) v[k2] = u_reg * Kreg[REGP ? base + k2 : 0];
+            solo_treduce<8>(v, lane);
+            if ((lane & 3) == 0) vw[base + (lane >> 2)] = v[0];
+          }
+        }
+      }
+      __syncthreads();
+      if (tid < LP) {
+        double a = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < NRW; ++w2) a += vp[w2 * LP + tid];
+        push_all(phase, tid, a);
+      }
+    } else {
       double a[NQ];
 #pragma unroll
       for (int q = 0; q < NQ; ++q) a[q] = 0.0;
@@ -1119,52 +1225,66 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
       if (lane == 0) {
 #pragma unroll
         for (int q = 0; q < NQ; ++q)
-          if (warp + q * NW < LP) mine[warp + q * NW] = a[q];
+          if (warp + q * NW < LP) push_all(phase, warp + q * NW, a[q]);
       }
     }
-    if (tid < 2) {
+    if (tid >= 64 && tid < 66) {
       double a = 0.0;
       if (with_norms) {
 #pragma unroll
-        for (int w2 = 0; w2 < NRW; ++w2) a += nB[w2 * 2 + tid];
+        for (int w2 = 0; w2 < NRW; ++w2) a += nB[w2 * 2 + tid - 64];
         a *= inv_mu20sq;
       }
-      mine[LP + tid] = a;
+      push_all(phase, LP + tid - 64, a);
     }
-    if (CS > 1) cluster.sync(); else __syncthreads();
+    SOLO_STAMP(6)
+    mbar_wait_cluster(xbar + phase, (xpar >> phase) & 1u);
+    xpar ^= 1u << phase;
+    SOLO_STAMP(7)
     if (lact && pl == 0) {
       double a = 0.0;
 #pragma unroll
-      for (int c = 0; c < CS; ++c) a += (CS > 1 ? cluster.map_shared_rank(mine, c) : mine)[l];
+      for (int c = 0; c < CS; ++c) a += slots[c * (LP + 2) + l];
       r_V = a;
     }
     if (warp == SOLO_LWARPS && lane < 2) {
       double a = 0.0;
 #pragma unroll
-      for (int c = 0; c < CS; ++c) a += (CS > 1 ? cluster.map_shared_rank(mine, c) : mine)[LP + lane];
+      for (int c = 0; c < CS; ++c) a += slots[c * (LP + 2) + LP + lane];
       nBt[lane] = a;
     }
-    phase ^= 1;
+    SOLO_STAMP(8)
     __syncthreads();
+    // everybody has read this buffer: re-arm its barrier for the exchange after the next (no peer can push
+    // into it before it has received this CTA's NEXT push, which comes later in program order)
+    if (tid == 0) mbar_expect_tx(xbar + phase, XBYTES);
+    phase ^= 1;
+    SOLO_STAMP(9)
   };
 
-  for (int k = 0;; ++k) {
+  for (k = 0;; ++k) {
     if (need_v) {
       // u = Re h20 + mu20 x2 with x2 decoded by the mu20 it was encoded with
       const double ratio = mu20 / mu20_enc;
-      for (int i = tid; i < R; i += SOLO_THREADS) {
-        const double s = ss[i];
-        us[i] = is_neg(s) ? -s * ratio : s;
+      if (REGP) {
+        u_reg = is_neg(s_reg) ? -s_reg * ratio : s_reg;
+      } else {
+        for (int i = tid; i < R; i += SOLO_THREADS) {
+          const double s = ss[i];
+          us[i] = is_neg(s) ? -s * ratio : s;
+        }
+        __syncthreads();
       }
-      __syncthreads();
       exchange(false);
       need_v = false;
     }
     if (k >= budget) break;
+    SOLO_STAMP(0)
 
     // ---- term 0: rhs, cached inverse, KKT correction (C Gi rhs = w . rhs because Gi is symmetric)
     if (lact) rhs[pl * LP + l] = r_b0 + r_h10 + mu10 * r_x1 + r_V;
     __syncthreads();
+    SOLO_STAMP(1)
     if (hist_pending && warp == NW - 1) {
       // residual() of the previous iteration (this warp idles while the L-space warps solve term 0)
       if (crank == 0 && lane == 0 && prob == 0 && b.history && hist_it < b.hist_cap) {
@@ -1176,7 +1296,21 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
     double xv = 0.0;
     if (lact) {
       const double* rp = rhs + pl * LP;
-      const double xi = solo_matvec<LP>(Gi + l, rp);
+      double xi;
+      if (REGP) {
+        double a[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < LP; j += 4) {
+          const double2 r01 = *reinterpret_cast<const double2*>(rp + j), r23 = *reinterpret_cast<const double2*>(rp + j + 2);
+          a[0] += Kreg[REGP ? j : 0] * r01.x;
+          a[1] += Kreg[REGP ? j + 1 : 0] * r01.y;
+          a[2] += Kreg[REGP ? j + 2 : 0] * r23.x;
+          a[3] += Kreg[REGP ? j + 3 : 0] * r23.y;
+        }
+        xi = (a[0] + a[1]) + (a[2] + a[3]);
+      } else {
+        xi = solo_matvec<LP>(Gi + l, rp);
+      }
       double c[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
       for (int j = 0; j < LP; j += 4) {
@@ -1191,7 +1325,9 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
       xv = xi + wv[l] * nu;
       xn[pl * LP + l] = xv;
     }
+    SOLO_STAMP(2)
     __syncthreads();
+    SOLO_STAMP(3)
 
     if (lth) {
       // ---- y = P^T P x0, norms, L1 z-update, dual ascent of pair (1,0), imaginary-plane recursion
@@ -1230,7 +1366,28 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
     } else {
       // ---- my sampling points: s' = Re h20 - mu20 (P Re x0) encodes dual ascent and projection
       double n_dh = 0.0, n_xm = 0.0;
-      for (int i = tid - 32 * SOLO_LWARPS; i < R; i += SOLO_RTHREADS) {
+      if (REGP) {
+        double q[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < LP; j += 4) {
+          const double2 x01 = *reinterpret_cast<const double2*>(xn + j), x23 = *reinterpret_cast<const double2*>(xn + j + 2);
+          q[0] += Kreg[REGP ? j : 0] * x01.x;
+          q[1] += Kreg[REGP ? j + 1 : 0] * x01.y;
+          q[2] += Kreg[REGP ? j + 2 : 0] * x23.x;
+          q[3] += Kreg[REGP ? j + 3 : 0] * x23.y;
+        }
+        const double hre = is_neg(s_reg) ? 0.0 : s_reg;
+        const double s_new = hre - mu20 * ((q[0] + q[1]) + (q[2] + q[3]));
+        const bool neg = is_neg(s_new);
+        const double hnew = neg ? 0.0 : s_new;
+        const double xm = neg ? s_new : 0.0;
+        const double dh = hre - hnew;
+        n_dh = dh * dh;
+        n_xm = xm * xm;
+        u_reg = fabs(s_new);
+        s_reg = s_new;
+      }
+      for (int i = REGP ? R : rt; i < R; i += SOLO_RTHREADS) {
         double q[4] = {0.0, 0.0, 0.0, 0.0};
         const double* pr = Psm + i;
 #pragma unroll
@@ -1261,8 +1418,11 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
       }
     }
     mu20_enc = mu20;
+    SOLO_STAMP(4)
     __syncthreads();
+    SOLO_STAMP(5)
     exchange(true);
+    SOLO_STAMP(10)
 
     // ---- residual() / check_convergence() / update_mu(): every thread, identical numbers
     double s[10];
@@ -1271,7 +1431,12 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
     for (int p2 = 0; p2 < npl; ++p2) {
       double a[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = nA[(2 * p2) * 8 + i] + nA[(2 * p2 + 1) * 8 + i];
+      for (int i = 0; i < 8; i += 2) {
+        const double2 v0 = *reinterpret_cast<const double2*>(nA + (2 * p2) * 8 + i);
+        const double2 v1 = *reinterpret_cast<const double2*>(nA + (2 * p2 + 1) * 8 + i);
+        a[i] = v0.x + v1.x;
+        a[i + 1] = v0.y + v1.y;
+      }
 #pragma unroll
       for (int i = 5; i < 8; ++i) a[i] = a[i] > 0.0 ? a[i] : 0.0;
 #pragma unroll
@@ -1291,15 +1456,17 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
     mu20_res = mu20;
     hist_pending = true;
     hist_it = it;
-    const int this_it = it;
     ++it;
     const bool cv = (s[0] < rtol2 * fmax(s[1], s[2])) && (s[3] < rtol2 * fmax(s[1], s[4])) &&
                     (s[7] < rtol2 * fmax(s[9], s[8])) && (s[5] < rtol2 * fmax(s[9], s[6]));
+    SOLO_STAMP(11)
     if (cv) {
       conv = 1;
       break;
     }
-    if (interval > 0 && this_it % interval == 0) {
+    const bool upd = until_upd == 0;
+    until_upd = (upd ? interval : until_upd) - 1;
+    if (upd) {
       const double p10 = sqrt(s[0]), p20 = sqrt(s[7]), d10 = mu10 * sqrt(s[3]), d20 = mu20 * sqrt(s[5]);
       const double m10 = mu_step(mu10, p10, d10, b), m20 = mu_step(mu20, p20, d20, b);
       if (m10 != mu10 || m20 != mu20) {
@@ -1308,6 +1475,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
         mu_changed = true;
         need_v = true;
         sigma = solo_factor(L, LP, mu10, mu20, G0, PtPs, Gi, wv, Cv, sm + lay.rowk, sm + lay.colk, &bad_sh);
+        load_gcol();
         inv_mu10 = 1.0 / mu10;
         inv_sigma = 1.0 / sigma;
         inv_mu20sq = 1.0 / (mu20 * mu20);
@@ -1334,9 +1502,16 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
       for (int sp = 1; sp < d.nsplit; ++sp) b.V[sp * vstride + fo] = 0.0;
     }
   }
-  for (int i = tid; i < nrow; i += SOLO_THREADS) {
-    const int row = row0 + i;
-    b.S[state_index(d, pt, row >> 3, 4 * g + ((row & 7) >> 1)) + (row & 1)] = ss[i];
+  if (REGP) {
+    if (rt >= 0 && rt < nrow) {
+      const int row = row0 + rt;
+      b.S[state_index(d, pt, row >> 3, 4 * g + ((row & 7) >> 1)) + (row & 1)] = s_reg;
+    }
+  } else {
+    for (int i = tid; i < nrow; i += SOLO_THREADS) {
+      const int row = row0 + i;
+      b.S[state_index(d, pt, row >> 3, 4 * g + ((row & 7) >> 1)) + (row & 1)] = ss[i];
+    }
   }
   if (crank == 0 && tid == 0) {
     b.mu10[prob] = mu10;
@@ -1419,15 +1594,18 @@ static int launch_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mo
   }
 }
 
+static bool solo_regp(const admm_spm_dims* d, int cs) {
+  return d->Lp <= 40 && solo_layout(d->Lp, d->nrt * 8, cs, d->nplanes, false).R <= SOLO_RTHREADS && !getenv("ADMM_SOLO_SMEM");
+}
 static size_t solo_smem_bytes(const admm_spm_dims* d, int cs) {
-  return (size_t)solo_layout(d->Lp, d->nrt * 8, cs, d->nplanes).total * sizeof(double);
+  return (size_t)solo_layout(d->Lp, d->nrt * 8, cs, d->nplanes, solo_regp(d, cs)).total * sizeof(double);
 }
 
-template <int CS, int LP>
+template <int CS, int LP, bool REGP>
 static int launch_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const double* G0, int niter, int interval,
                        cudaStream_t st) {
   const size_t smem = solo_smem_bytes(d, CS);
-  auto kern = spm_solo_kernel<CS, LP>;
+  auto kern = spm_solo_kernel<CS, LP, REGP>;
   static size_t configured = 0;     // per instantiation
   if (smem > configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1591,10 +1769,14 @@ int admm_spm_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const doubl
                "admm_spm_solo: L=%d, Nw=%d do not fit the shared memory of an 8-CTA cluster", d->L, d->Nw);
   ADMM_REQUIRE(G0 != nullptr && niter >= 0 && interval_update_mu >= 0, ADMM_EINVAL, "admm_spm_solo: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // sampling points per CTA <= 256: P, the state and the cached inverse stay in registers
+  const bool regp = solo_regp(d, 8);
   switch (d->Lp) {
-    case 16: return launch_solo<8, 16>(d, b, G0, niter, interval_update_mu, st);
-    case 40: return launch_solo<8, 40>(d, b, G0, niter, interval_update_mu, st);
-    default: return launch_solo<8, 64>(d, b, G0, niter, interval_update_mu, st);
+    case 16: return regp ? launch_solo<8, 16, true>(d, b, G0, niter, interval_update_mu, st)
+                         : launch_solo<8, 16, false>(d, b, G0, niter, interval_update_mu, st);
+    case 40: return regp ? launch_solo<8, 40, true>(d, b, G0, niter, interval_update_mu, st)
+                         : launch_solo<8, 40, false>(d, b, G0, niter, interval_update_mu, st);
+    default: return launch_solo<8, 64, false>(d, b, G0, niter, interval_update_mu, st);   // 64 doubles per row: shared memory
   }
 }
 

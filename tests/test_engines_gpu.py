@@ -328,7 +328,8 @@ def test_spm_balanced_decomposition_shapes(eng, ir_basis, nb, Nw, mt, nbal):
 
 # ------------------------------------------------------------------ cluster-resident single-launch solve
 @pytest.mark.parametrize("nb,Nw,eps,cplx", [(1, 2000, 1e-7, False), (1, 330, 1e-7, True), (5, 200, 1e-7, True),
-                                            (13, 136, 1e-2, True), (3, 264, 1e-10, True), (16, 97, 1e-7, False)])
+                                            (13, 136, 1e-2, True), (3, 264, 1e-10, True), (16, 97, 1e-7, False),
+                                            (2, 2500, 1e-7, True)])
 def test_spm_solo_cluster_solve(eng, nb, Nw, eps, cplx):
     """admm_spm_solo (one 8-CTA cluster per problem, the whole solve in one launch, in-kernel mu update and
     re-inversion): every problem == its own reference instance (oracle) incl. iteration count and mu, and

@@ -621,6 +621,8 @@ class BatchedBasisPursuit:
         self.info = torch.zeros(nb, dtype=torch.int32, device=dev)
         self.keep_history = keep_history
         self.history = None
+        self._kcache = {}            # nb == 1: mu -> (Kinv, ready event, info, keep-alive)
+        self._side = None            # side stream of the speculative factorisations
         self.primal_residual = [[] for _ in range(nb)] if keep_history else None
         self.dual_residual = [[] for _ in range(nb)] if keep_history else None
         # tile-major copy of A for the single-sweep kernel (Woodbury path, M <= 256)
@@ -659,19 +661,86 @@ class BatchedBasisPursuit:
             self.mu[:] = torch.as_tensor(mu, dtype=_F64, device=self.device)
             self.need_factor.fill_(1)
 
+    # ------------------------------------------------------------------ single problem: factor cache by mu
+    def _kinv_entry(self, mu: float, speculative: bool):
+        """(alpha A A^T + mu)^-1-type factor of the ONE problem for penalty ``mu`` from the per-mu cache (the
+        reference's ``_B_cache``, objectivefunc.py:89-96).  A missing entry is computed on the current stream,
+        or -- ``speculative`` -- on a side stream while the iterations run: ``update_mu`` can only move mu to
+        ``mu * fact_incr`` or ``mu / fact_incr``, and a single problem leaves most of the GPU idle."""
+        main = torch.cuda.current_stream()
+        ent = self._kcache.get(mu)
+        if ent is None:
+            if len(self._kcache) >= 12:
+                torch.cuda.synchronize()
+                self._kcache.clear()
+            if speculative:
+                if self._side is None:
+                    self._side = torch.cuda.Stream()
+                self._side.wait_stream(main)
+            s_ = self._side if speculative else main
+            with torch.cuda.stream(s_):
+                K = torch.empty(1, self.nk, self.nk, dtype=_F64, device=self.device)
+                mu_t = torch.full((1,), float(mu), dtype=_F64, device=self.device)
+                nf = torch.ones(1, dtype=torch.int32, device=self.device)
+                info = torch.zeros(1, dtype=torch.int32, device=self.device)
+                sh = BpBuffers.from_buffer_copy(self.bufs)
+                sh.mu, sh.need_factor, sh.Kinv = mu_t.data_ptr(), nf.data_ptr(), K.data_ptr()
+                call("admm_bp_factor", C.byref(sh), ptr(info), C.c_void_p(s_.cuda_stream))
+                ev = torch.cuda.Event()
+                ev.record(s_)
+            ent = (K, ev, info, (mu_t, nf))
+            self._kcache[mu] = ent
+        if not speculative:
+            main.wait_event(ent[1])
+        return ent
+
+    def _solve_single(self, niter: int) -> None:
+        """nb == 1: one read-back per interval; the factor for the current mu comes from the cache, the two
+        factors ``update_mu`` can ask for next are computed meanwhile on idle SMs."""
+        bref, st = C.byref(self.bufs), stream()
+        mu = float(self.mu[0].item())
+        while True:
+            ent = self._kinv_entry(mu, speculative=False)
+            self.bufs.Kinv = ent[0].data_ptr()
+            self.need_factor.zero_()
+            for m2 in (min(mu * 2.0, self.max_mu), mu / 2.0):
+                if m2 != mu:
+                    self._kinv_entry(m2, speculative=True)
+            call("admm_bp_iterate", bref, int(niter), st)
+            fl = torch.stack([self.iters.to(_F64), self.done.to(_F64), self.mu]).cpu()
+            if int(ent[2].item()) != 0:
+                raise _lib.AdmmError("alpha A^H A + mu is not positive definite")
+            if int(fl[0, 0]) >= niter or int(fl[1, 0]) != 0:
+                break
+            mu = float(fl[2, 0])
+
     def solve(self, niter: int = 10000, interval_update_mu: int = 100, rtol: float = 1e-12) -> None:
-        """All iterations of every problem on the device; no host synchronisation inside."""
+        """All iterations of every problem on the device; no host synchronisation inside (a single problem:
+        one small read-back per mu interval, see ``_solve_single``)."""
         self.iters.zero_()
         self.done.zero_()
         self.history = (torch.zeros(self.nb, max(niter, 1), 2, dtype=_F64, device=self.device)
                         if self.keep_history else None)
         self._fill(rtol, interval_update_mu)
+        if self.nb == 1 and niter > 0:
+            self._solve_single(niter)
+            self._collect_history()
+            return
         bref, st = C.byref(self.bufs), stream()
         rounds = -(-niter // interval_update_mu) + 1
         for _ in range(rounds):
             call("admm_bp_factor", bref, ptr(self.info), st)
             call("admm_bp_iterate", bref, int(niter), st)
+            if self.nb <= 8:
+                # a handful of problems (latency-bound): one small read-back per round instead of enqueueing
+                # all ceil(niter / interval) + 1 rounds blindly -- mu changes only a few times per solve
+                fl = torch.stack([self.iters, self.done]).cpu()
+                if bool(((fl[0] >= niter) | (fl[1] != 0)).all()):
+                    break
         # a factor may still be pending for the next solve() call (mu changed on the last iteration)
+        self._collect_history()
+
+    def _collect_history(self) -> None:
         if self.keep_history:
             it = self.iters.cpu().numpy()
             hist = self.history.cpu().numpy()

@@ -582,6 +582,338 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) bp_fused_kernel(admm
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// solo: ONE problem (or a handful) resident in the shared memory of a thread-block cluster
+// ---------------------------------------------------------------------------------------------
+// The notebook / test instance of the reference (basis_pursuit.ipynb, test_optimizer.py:52-82: one
+// 100..200 x 1000 problem) is pure latency for the batch kernels: A has to be streamed from L2 every
+// iteration by a few CTAs.  Here a cluster of CS CTAs keeps the problem on chip for the whole solve:
+//   * CTA c owns N/CS columns: its slice of A (column-major, odd pitch: conflict-free in both
+//     products) stays in shared memory, x0 / x1 / h / alpha A^T y / r of a column in the registers of
+//     one thread; it also owns M/CS rows of K^-1 (shared memory);
+//   * per iteration  c = A^T s  (own columns), x-update + soft threshold + dual ascent (registers),
+//     partial t' = A r' (all M rows, own columns), REDUCE-SCATTER of t' (CTA c sums rows c M/CS ...) with the
+//     five norm partials riding along, ALL-GATHER of t', the own rows of s = K^-1 t', ALL-GATHER of s;
+//   * the exchanges are DSMEM pushes (st.async + complete_tx on the receiver's mbarrier, ping-pong
+//     buffers armed one use ahead): no cluster barrier, no fence in the loop.  Every CTA sums the
+//     partials in rank order, so all CTAs hold bit-identical t, s and norms and take identical decisions.
+constexpr int BPS_THREADS = 512;
+constexpr int BPS_PARTS = 8;       // row parts of the A^T s product
+
+struct BpsLayout {      // offsets in doubles
+  int Nc, Ncp, Mr, Mp, pitch, XW, nparts3, A, K, s, t, rs, cp, tp, nrm, nrmt, x1, bars, total;
+};
+__host__ __device__ inline BpsLayout bps_layout(int M, int N, int cs) {
+  BpsLayout o;
+  o.Nc = (N + cs - 1) / cs;             // columns per CTA
+  o.Ncp = (o.Nc + 31) & ~31;
+  o.Mr = (M + cs - 1) / cs;             // rows of K^-1 per CTA
+  o.Mp = (M + 31) & ~31;
+  o.pitch = M | 1;
+  o.XW = (o.Mr + 5 + 1) & ~1;           // slot pitch of the reduce-scatter: my Mr rows of the partial t' + 5 norm partials
+  o.nparts3 = BPS_THREADS / o.Mp > 0 ? BPS_THREADS / o.Mp : 1;
+  int at = 0;
+  auto take = [&](int n) { const int r = at; at += (n + 1) & ~1; return r; };
+  o.A = take(o.Nc * o.pitch);
+  o.K = take(o.Mr * M);
+  o.s = take(2 * o.Mp);                 // all-gather receive buffers (ping-pong)
+  o.t = take(o.Mp);
+  o.rs = take(o.Ncp);
+  o.cp = take(BPS_PARTS * o.Ncp);
+  o.tp = take(o.nparts3 * o.Mp);
+  o.nrm = take((BPS_THREADS / 32) * 5);
+  o.nrmt = take(6);
+  o.x1 = take(2 * cs * o.XW);           // reduce-scatter receive slots (ping-pong)
+  o.bars = take(6);
+  o.total = at;
+  return o;
+}
+
+#ifdef SOLO_TRACE   // tools only: clock64 stamps of warp 0 of CTA 0 for iterations 10..13 into b.last_res + 16
+#define BPS_STAMP(idx)                                                                        \
+  if (crank == 0 && tid == 0 && it >= 3000 && it < 3004 && !first)                                \
+    reinterpret_cast<long long*>(b.history)[4096 + (it - 3000) * 16 + (idx)] = clock64();
+#else
+#define BPS_STAMP(idx)
+#endif
+
+template <int CS>
+__global__ void __launch_bounds__(BPS_THREADS, 1) bp_solo_kernel(admm_bp_buffers b, int iter_end) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int prob = blockIdx.x / CS;
+  if (b.done[prob] || b.need_factor[prob]) return;          // uniform over the cluster
+  int it = b.iters[prob];
+  if (it >= iter_end) return;
+  constexpr int NW = BPS_THREADS / 32;
+  const int M = b.M, N = b.N;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  extern __shared__ __align__(128) double sm[];
+  const BpsLayout lay = bps_layout(M, N, CS);
+  const int Nc = lay.Nc, Ncp = lay.Ncp, Mr = lay.Mr, Mp = lay.Mp, pitch = lay.pitch, XW = lay.XW;
+  double* As = sm + lay.A;          // [nl][pitch]: A[m][n0 + nl]
+  double* Ks = sm + lay.K;          // [rl][M]: K^-1[m0 + rl][:]
+  double* sbuf = sm + lay.s;        // [2][Mp]
+  double* tfull = sm + lay.t;       // [Mp]
+  double* rs = sm + lay.rs;         // [Ncp]: r of my columns
+  double* cp = sm + lay.cp;         // [part][Ncp]
+  double* tp = sm + lay.tp;         // [part3][Mp]
+  double* nrm = sm + lay.nrm;       // [warp][5]
+  double* nrmt = sm + lay.nrmt;     // [5] cluster totals
+  double* x1s = sm + lay.x1;        // [2][CS][XW]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + lay.bars);   // 0,1: reduce-scatter; 2,3: all-gather of s; 4: all-gather of t
+  const int n0 = crank * Nc, ncol = max(0, min(Nc, N - n0));
+  const int m0 = crank * Mr, nrowK = max(0, min(Mr, M - m0));
+  const double* A = b.A + (size_t)prob * M * N;
+  const double* Kinv = b.Kinv + (size_t)prob * M * M;
+
+  for (int idx = tid; idx < Nc * pitch; idx += BPS_THREADS) As[idx] = 0.0;
+  for (int i = tid; i < 2 * Mp; i += BPS_THREADS) sbuf[i] = 0.0;
+  for (int i = tid; i < Mp; i += BPS_THREADS) tfull[i] = 0.0;
+  for (int i = tid; i < Ncp; i += BPS_THREADS) rs[i] = 0.0;
+  for (int i = tid; i < BPS_PARTS * Ncp; i += BPS_THREADS) cp[i] = 0.0;
+  for (int i = tid; i < NW * 5; i += BPS_THREADS) nrm[i] = 0.0;
+  __syncthreads();
+  for (int idx = tid; idx < M * Nc; idx += BPS_THREADS) {
+    const int m = idx / Nc, nl = idx - m * Nc;
+    if (nl < ncol) As[nl * pitch + m] = A[(size_t)m * N + n0 + nl];
+  }
+  for (int idx = tid; idx < nrowK * M; idx += BPS_THREADS) Ks[idx] = Kinv[(size_t)m0 * M + idx];
+  double mu = b.mu[prob];
+  // my column (thread tid < ncol): everything of size N lives in registers
+  const bool own = tid < ncol;
+  double c_aty = 0.0, c_x0 = 0.0, c_x1 = 0.0, c_h = 0.0, c_r = 0.0;
+  if (own) {
+    const size_t o = (size_t)prob * N + n0 + tid;
+    c_aty = b.aty[o];
+    c_x0 = b.x0[o];
+    c_x1 = b.x1[o];
+    c_h = b.h[o];
+    c_r = c_aty + c_h + mu * c_x1;
+    rs[tid] = c_r;
+  }
+  const unsigned X1BYTES = (unsigned)(CS * (nrowK + 5) * sizeof(double)), X2BYTES = (unsigned)(M * sizeof(double));
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) mbar_init(bars + i, 1);
+    fence_barrier_init();
+    mbar_expect_tx(bars + 0, X1BYTES);
+    mbar_expect_tx(bars + 1, X1BYTES);
+    mbar_expect_tx(bars + 2, X2BYTES);
+    mbar_expect_tx(bars + 3, X2BYTES);
+    mbar_expect_tx(bars + 4, X2BYTES);
+  }
+  cluster.sync();                  // barriers armed everywhere before anybody pushes; shared data visible
+  const unsigned x1_u32 = smem_u32(x1s), s_u32 = smem_u32(sbuf), t_u32 = smem_u32(tfull), bar_u32 = smem_u32(bars);
+  unsigned par = 0u;               // bit i: parity of the next completion of barrier i
+  int ph1 = 0, ph2 = 0;            // buffers of the NEXT all-reduce / all-gather
+  const double rtol2 = b.rtol * b.rtol;
+  double thr = 0.5 * b.lam / mu, inv_mu = 1.0 / mu;
+  int done = 0, need = 0;
+  double sq_p = 0.0, sq_d = 0.0, mu_res = mu;
+  bool first = true;               // first pass of this launch: only t = A r, s = K^-1 t
+  const int Mq = (M + BPS_PARTS - 1) / BPS_PARTS;
+  const int Cq = (Nc + lay.nparts3 - 1) / lay.nparts3;
+
+  while (true) {
+    BPS_STAMP(0)
+    if (!first) {
+      // ---- c = A^T s for my columns: warp = (row part, block of 32 columns)
+      const double* sf = sbuf + (ph2 ^ 1) * Mp;             // the s received last
+      const int part = warp & (BPS_PARTS - 1);
+      const int mlo = part * Mq, mhi = min(M, mlo + Mq);
+      for (int blk = warp / BPS_PARTS; blk * 32 < Nc; blk += NW / BPS_PARTS) {
+        const int nl = blk * 32 + lane;
+        const double* ac = As + min(nl, Nc - 1) * pitch;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int m = mlo;
+        for (; m + 3 < mhi; m += 4) {
+          a0 += ac[m] * sf[m];
+          a1 += ac[m + 1] * sf[m + 1];
+          a2 += ac[m + 2] * sf[m + 2];
+          a3 += ac[m + 3] * sf[m + 3];
+        }
+        for (; m < mhi; ++m) a0 += ac[m] * sf[m];
+        if (nl < Nc) cp[part * Ncp + nl] = (a0 + a1) + (a2 + a3);
+      }
+      BPS_STAMP(1)
+      __syncthreads();
+      BPS_STAMP(2)
+      // everybody has read this s buffer: re-arm its barrier for the all-gather after the next
+      if (tid == 0) {
+        mbar_expect_tx(bars + 2 + (ph2 ^ 1), X2BYTES);
+        mbar_expect_tx(bars + 4, X2BYTES);      // t was consumed by the K^-1 rows of the previous iteration
+      }
+      // ---- x-update by the Woodbury identity, soft threshold, dual ascent (optimizer.py:322-341)
+      double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      if (own) {
+        double c = 0.0;
+#pragma unroll
+        for (int q = 0; q < BPS_PARTS; ++q) c += cp[q * Ncp + tid];
+        const double xov = c_x0;
+        const double xv = (c_r - c) * inv_mu;
+        const double yv = xv - c_h * inv_mu;
+        double z = 0.0;
+        if (yv > thr) z = yv - thr;
+        if (yv < -thr) z = yv + thr;
+        c_h = c_h + mu * (z - xv);
+        c_x0 = xv;
+        c_x1 = z;
+        c_r = c_aty + c_h + mu * z;
+        rs[tid] = c_r;
+        v[0] = (xv - z) * (xv - z);
+        v[1] = xv * xv;
+        v[2] = z * z;
+        v[3] = (xv - xov) * (xv - xov);
+        v[4] = xov * xov;
+      }
+      if (warp * 32 < Nc) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) v[i] = warp_sum(v[i]);
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < 5; ++i) nrm[warp * 5 + i] = v[i];
+        }
+      }
+      BPS_STAMP(3)
+      __syncthreads();
+      BPS_STAMP(4)
+    }
+    // ---- partial t' = A r' over my columns: thread = (column part, row)
+    {
+      const int q = tid / Mp, m = tid - q * Mp;
+      if (q < lay.nparts3 && m < M) {
+        const int clo = q * Cq, chi = min(Nc, clo + Cq);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const double* ar = As + m;
+        int nl = clo;
+        for (; nl + 3 < chi; nl += 4) {
+          a0 += ar[nl * pitch] * rs[nl];
+          a1 += ar[(nl + 1) * pitch] * rs[nl + 1];
+          a2 += ar[(nl + 2) * pitch] * rs[nl + 2];
+          a3 += ar[(nl + 3) * pitch] * rs[nl + 3];
+        }
+        for (; nl < chi; ++nl) a0 += ar[nl * pitch] * rs[nl];
+        tp[q * Mp + m] = (a0 + a1) + (a2 + a3);
+      }
+    }
+    BPS_STAMP(5)
+    __syncthreads();
+    BPS_STAMP(6)
+    // ---- reduce-scatter (push): row m of the partial t' goes to the CTA that owns it; the five norm partials to all
+    if (tid < M + 5) {
+      const unsigned bar = bar_u32 + (unsigned)(ph1 * sizeof(uint64_t));
+      if (tid < M) {
+        double a = 0.0;
+        for (int q = 0; q < lay.nparts3; ++q) a += tp[q * Mp + tid];
+        const int dst = tid / Mr, e = tid - dst * Mr;
+        const unsigned slot = x1_u32 + (unsigned)(((ph1 * CS + crank) * XW + e) * sizeof(double));
+        st_async_f64(mapa_u32(slot, dst), a, mapa_u32(bar, dst));
+      } else {
+        double a = 0.0;
+        if (!first)
+          for (int w = 0; w * 32 < Nc; ++w) a += nrm[w * 5 + tid - M];
+        const unsigned slot = x1_u32 + (unsigned)(((ph1 * CS + crank) * XW + Mr + tid - M) * sizeof(double));
+#pragma unroll
+        for (int c = 0; c < CS; ++c) st_async_f64(mapa_u32(slot, c), a, mapa_u32(bar, c));
+      }
+    }
+    BPS_STAMP(7)
+    mbar_wait_cluster(bars + ph1, (par >> ph1) & 1u);
+    par ^= 1u << ph1;
+    BPS_STAMP(8)
+    // ---- my rows of t' complete -> all-gather (push); norm totals
+    if (tid < nrowK || (tid >= Mr && tid < Mr + 5)) {
+      const double* sl = x1s + (size_t)ph1 * CS * XW + tid;
+      double a = 0.0;
+#pragma unroll
+      for (int c = 0; c < CS; ++c) a += sl[c * XW];
+      if (tid < nrowK) {
+        const unsigned slot = t_u32 + (unsigned)((m0 + tid) * sizeof(double));
+        const unsigned bar = bar_u32 + (unsigned)(4 * sizeof(uint64_t));
+#pragma unroll
+        for (int c = 0; c < CS; ++c) st_async_f64(mapa_u32(slot, c), a, mapa_u32(bar, c));
+      } else {
+        nrmt[tid - Mr] = a;
+      }
+    }
+    BPS_STAMP(9)
+    __syncthreads();
+    BPS_STAMP(10)
+    if (tid == 0) mbar_expect_tx(bars + ph1, X1BYTES);      // consumed by everybody: re-arm for the use after the next
+    ph1 ^= 1;
+
+    if (!first) {
+      // ---- residual() / check_convergence() / update_mu() (optimizer.py:232-299) on squared norms
+      const double v0 = nrmt[0], v1 = nrmt[1], v2 = nrmt[2], v3 = nrmt[3], v4 = nrmt[4];
+      sq_p = v0;
+      sq_d = v3;
+      mu_res = mu;
+      if (b.history && it < b.hist_cap && tid == 0 && crank == 0) {
+        b.history[((size_t)prob * b.hist_cap + it) * 2] = sqrt(v0);
+        b.history[((size_t)prob * b.hist_cap + it) * 2 + 1] = mu * sqrt(v3);
+      }
+      const int this_it = it;
+      ++it;
+      const bool conv = (v0 < rtol2 * fmax(v1, v2)) && (v3 < rtol2 * fmax(v1, v4));
+      if (conv) {
+        done = 1;
+        break;
+      }
+      if (this_it % b.interval_update_mu == 0) {
+        const double primal = sqrt(v0), dual = mu * sqrt(v3);
+        double m2 = mu;
+        if (primal > b.th_change * dual) m2 *= b.fact_incr;
+        if (dual > b.th_change * primal) m2 /= b.fact_incr;
+        m2 = fmin(m2, b.max_mu);
+        if (m2 != mu) {
+          mu = m2;
+          need = 1;
+          break;
+        }
+      }
+      if (it >= iter_end) break;
+    }
+    BPS_STAMP(11)
+    // ---- my rows of s = K^-1 t' (t' complete once every owner's rows have arrived), all-gather (push)
+    mbar_wait_cluster(bars + 4, (par >> 4) & 1u);
+    par ^= 1u << 4;
+    for (int rl = warp; rl < nrowK; rl += NW) {
+      const double* kr = Ks + rl * M;
+      double a = 0.0;
+      for (int j = lane; j < M; j += 32) a += kr[j] * tfull[j];
+      a = warp_sum(a);
+      if (lane < CS) {
+        const unsigned slot = s_u32 + (unsigned)((ph2 * Mp + m0 + rl) * sizeof(double));
+        const unsigned bar = bar_u32 + (unsigned)((2 + ph2) * sizeof(uint64_t));
+        st_async_f64(mapa_u32(slot, lane), a, mapa_u32(bar, lane));
+      }
+    }
+    BPS_STAMP(12)
+    mbar_wait_cluster(bars + 2 + ph2, (par >> (2 + ph2)) & 1u);
+    BPS_STAMP(13)
+    par ^= 1u << (2 + ph2);
+    ph2 ^= 1;
+    first = false;
+  }
+
+  // ---- state back to global memory (every CTA its columns)
+  if (own) {
+    const size_t o = (size_t)prob * N + n0 + tid;
+    b.x0[o] = c_x0;
+    b.x1[o] = c_x1;
+    b.h[o] = c_h;
+  }
+  if (tid == 0 && crank == 0) {
+    b.mu[prob] = mu;
+    b.iters[prob] = it;
+    b.done[prob] = done;
+    b.need_factor[prob] = need;
+    b.last_res[2 * prob] = sqrt(sq_p);
+    b.last_res[2 * prob + 1] = mu_res * sqrt(sq_d);
+  }
+  cluster.sync();                  // nobody leaves while a peer may still push into its shared memory
+}
+
 static int check_bp(const admm_bp_buffers* b, const char* who) {
   ADMM_REQUIRE(b != nullptr, ADMM_EINVAL, "%s: null buffers", who);
   ADMM_REQUIRE(b->nb >= 1 && b->M >= 1 && b->N >= 1, ADMM_EINVAL, "%s: bad dims", who);
@@ -660,6 +992,52 @@ int admm_bp_factor(const admm_bp_buffers* b, int* info, admm_stream_t stream) {
 int admm_bp_iterate(const admm_bp_buffers* b, int iter_end, admm_stream_t stream) {
   if (int rc = check_bp(b, "admm_bp_iterate")) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // a handful of problems: cluster-resident solve (A and K^-1 distributed over the shared memory of 16 or 8 CTAs)
+  if (b->woodbury && b->nb <= 8 && b->M >= 8 && b->M <= 480 && b->N >= 128 && !getenv("ADMM_BP_NO_SOLO")) {
+    auto try_solo = [&](auto kern, int cs) -> int {       // 0: launched, 1: not possible with this cluster size, <0: error
+      const BpsLayout lay = bps_layout(b->M, b->N, cs);
+      const size_t smem = (size_t)lay.total * sizeof(double);
+      if (lay.Nc > BPS_THREADS || smem > 220 * 1024) return 1;
+      static std::map<const void*, int> state;             // per kernel: 0 unknown, 1 usable, -1 cluster does not fit
+      int& stt = state[reinterpret_cast<const void*>(kern)];
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(b->nb * cs);
+      cfg.blockDim = dim3(BPS_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cs;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      if (stt <= 0) {
+        if (stt < 0) return 1;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (cs > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        int nclusters = 0;
+        cudaLaunchConfig_t probe = cfg;
+        probe.dynamicSmemBytes = 220 * 1024;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &probe) != cudaSuccess || nclusters < 1) {
+          cudaGetLastError();
+          stt = -1;
+          return 1;
+        }
+        stt = 1;
+      }
+      cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *b, iter_end);
+      if (e != cudaSuccess) {
+        set_error("admm_bp_iterate(solo): %s", cudaGetErrorString(e));
+        return -1;
+      }
+      return check_launch("admm_bp_iterate(solo)") == ADMM_OK ? 0 : -1;
+    };
+    int r = b->nb * 16 <= 144 ? try_solo(bp_solo_kernel<16>, 16) : 1;
+    if (r == 1) r = try_solo(bp_solo_kernel<8>, 8);
+    if (r == 0) return ADMM_OK;
+    if (r < 0) return ADMM_ECUDA;
+  }
   // fused single-sweep kernel: Woodbury path with a tile-major copy of A (admm_bp_tile_A), M <= 256
   // (16 rows per warp, up to 16 warps) and the vectors + 2 tile stages fit in shared memory
   if (b->woodbury && b->At != nullptr && b->M <= 256 && !getenv("ADMM_BP_TWO_SWEEP")) {

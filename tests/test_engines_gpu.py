@@ -380,3 +380,48 @@ def test_spm_solo_resume_and_handover(eng, ir_basis):
             assert rel(e.h20()[:, b], sts[b].h20) < 1e-8
             assert float(e.mu10[b]) == sts[b].mu10 and float(e.mu20[b]) == sts[b].mu20
     assert sts[0].mu20 != p.mu or sts[0].mu10 != p.mu
+
+
+# ------------------------------------------------------------------ cluster-resident basis pursuit
+@pytest.mark.parametrize("nb,M,N,niter,interval,rtol", [(1, 200, 1000, 260, 50, 1e-12), (1, 100, 1000, 150, 40, 1e-12),
+                                                        (3, 37, 300, 200, 25, 1e-12), (8, 128, 512, 120, 30, 1e-12),
+                                                        (2, 50, 130, 400, 20, 1e-6), (1, 9, 2100, 90, 30, 1e-12)])
+def test_bp_solo_cluster_solve(eng, nb, M, N, niter, interval, rtol):
+    """bp_solo_kernel (a handful of problems: A and K^-1 distributed over the shared memory of a 16- or 8-CTA
+    cluster, DSMEM push exchanges): every problem == its reference instance (oracle) incl. mu history, iteration
+    count (early stop) and residual history, == the batch kernels, and resumes correctly."""
+    import os
+    from oracle import flat
+    batch, problems = eng
+    rs = np.random.RandomState(1000 + M + N)
+    A = rs.randn(nb, M, N)
+    xs = np.zeros((nb, N))
+    for b in range(nb):
+        xs[b, rs.permutation(N)[:max(2, M // 8)]] = rs.randn(max(2, M // 8))
+    y = np.einsum("bmn,bn->bm", A, xs)
+    os.environ.pop("ADMM_BP_NO_SOLO", None)
+    e = batch.BatchedBasisPursuit(A, y, 0.8, 0.06, keep_history=True)
+    e.solve(niter, interval_update_mu=interval, rtol=rtol)
+    os.environ["ADMM_BP_NO_SOLO"] = "1"
+    try:
+        c = batch.BatchedBasisPursuit(A, y, 0.8, 0.06, keep_history=True)
+        c.solve(niter, interval_update_mu=interval, rtol=rtol)
+    finally:
+        os.environ.pop("ADMM_BP_NO_SOLO", None)
+    mus = set()
+    for b in range(nb):
+        st = flat.bp_solve(A[b], y[b], 0.8, 0.06, niter, interval_update_mu=interval, rtol=rtol)
+        assert int(e.iters[b]) == st.niter_done == int(c.iters[b]), (b, int(e.iters[b]), st.niter_done)
+        assert float(e.mu[b]) == st.mu == float(c.mu[b])
+        assert rel(e.x0()[b], st.x0.real) < TOL and rel(e.x1()[b], st.x1.real) < TOL and rel(e.h()[b], st.h.real) < 1e-8
+        assert rel(e.x0()[b], c.x0()[b]) < 1e-11
+        assert rel(e.primal_residual[b], st.primal) < 1e-8 and rel(e.dual_residual[b], st.dual) < 1e-8
+        mus.update(st.mu_hist)
+    if (M, N) == (200, 1000):
+        assert len(mus) > 1                               # this run crosses mu changes (kernel exit, re-inversion, re-entry)
+    # resume: a second solve continues from the state like the reference
+    e.solve(40, interval_update_mu=interval, rtol=rtol)
+    for b in range(nb):
+        st = flat.bp_solve(A[b], y[b], 0.8, 0.06, niter, interval_update_mu=interval, rtol=rtol)
+        st = flat.bp_solve(A[b], y[b], 0.8, 0.06, 40, interval_update_mu=interval, rtol=rtol, state=st)
+        assert rel(e.x0()[b], st.x0.real) < TOL and float(e.mu[b]) == st.mu

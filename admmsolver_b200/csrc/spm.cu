@@ -906,7 +906,7 @@ constexpr int SOLO_LWARPS = 4;
 constexpr int SOLO_RTHREADS = SOLO_THREADS - 32 * SOLO_LWARPS;
 
 struct SoloLayout {      // offsets in doubles into the dynamic shared memory
-  int R, P, Gi, PtP, rhs, xn, w, Cv, us, ss, xch, vp, nA, nB, nBt, rowk, colk, total;
+  int R, P, Gi, PtP, M2, pw, rhs, xn, w, Cv, us, ss, xch, vp, nA, nB, nBt, rowk, colk, total;
 };
 // LP = padded L (d.Lp: 16, 40 or 64): every L-dimension is zero padded to LP so that the inner loops
 // have compile-time trip counts; R = sampling points per CTA, padded to a multiple of 32
@@ -919,6 +919,8 @@ __host__ __device__ inline SoloLayout solo_layout(int LP, int Nwp, int cs, int n
   o.P = take(regp ? 0 : LP * o.R);
   o.Gi = take(LP * LP);
   o.PtP = take(LP * LP);
+  o.M2 = take(LP * LP);
+  o.pw = take(LP);
   o.rhs = take(npl * LP);
   o.xn = take(npl * LP);
   o.w = take(LP);
@@ -1032,6 +1034,28 @@ __device__ __forceinline__ void solo_treduce(double (&v)[W], int lane) {
 #define SOLO_STAMP(idx)
 #endif
 
+// M2T[j][l] = (P^T P G^-1)[l][j],  pw = P^T P w:  y = P^T P x0 = M2 rhs + nu pw comes out of the same pass over
+// rhs as x0 = G^-1 rhs + nu w (one dependent matvec per iteration instead of two).  All threads; ends synchronised.
+template <int LP>
+__device__ __forceinline__ void solo_m2(const double* PtPs, const double* Gi, const double* wv, double* M2T, double* pw) {
+  for (int idx = threadIdx.x; idx < LP * LP; idx += SOLO_THREADS) {
+    const int j = idx / LP, l = idx - j * LP;
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < LP; k += 2) {
+      a0 += PtPs[k * LP + l] * Gi[k * LP + j];
+      a1 += PtPs[(k + 1) * LP + l] * Gi[(k + 1) * LP + j];
+    }
+    M2T[idx] = a0 + a1;
+  }
+  for (int l = threadIdx.x; l < LP; l += SOLO_THREADS) {
+    double a = 0.0;
+    for (int k = 0; k < LP; ++k) a += PtPs[k * LP + l] * wv[k];
+    pw[l] = a;
+  }
+  __syncthreads();
+}
+
 template <int CS, int LP, bool REGP>
 __global__ void __launch_bounds__(SOLO_THREADS, 1)
     spm_solo_kernel(admm_spm_dims d, admm_spm_buffers b, const double* __restrict__ G0, int budget, int interval) {
@@ -1051,6 +1075,8 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
   double* Psm = sm + lay.P;        // [l][i]: P[row0 + i][l]
   double* Gi = sm + lay.Gi;        // [LP][LP], symmetric
   double* PtPs = sm + lay.PtP;     // [LP][LP], symmetric
+  double* M2T = sm + lay.M2;       // [LP][LP]: (P^T P G^-1) transposed
+  double* pw = sm + lay.pw;        // [LP]: P^T P w
   double* rhs = sm + lay.rhs;      // [plane][LP]
   double* xn = sm + lay.xn;        // [plane][LP]: the new x0
   double* wv = sm + lay.w;
@@ -1124,6 +1150,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
     mbar_expect_tx(xbar + 1, XBYTES);
   }
   cluster.sync();
+  solo_m2<LP>(PtPs, Gi, wv, M2T, pw);
   unsigned xpar = 0u;      // bit p: parity of the next completion of receive barrier p
   const unsigned xch_u32 = smem_u32(xch), xbar_u32 = smem_u32(xbar);
   // push value `v` of entry `e` (column or norm slot) of exchange buffer `ph` to every CTA of the cluster
@@ -1293,7 +1320,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
       }
     }
     hist_pending = false;
-    double xv = 0.0;
+    double xv = 0.0, yv2 = 0.0;
     if (lact) {
       const double* rp = rhs + pl * LP;
       double xi;
@@ -1324,6 +1351,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
       const double nu = (Dp - ((c[0] + c[1]) + (c[2] + c[3]))) * inv_sigma;
       xv = xi + wv[l] * nu;
       xn[pl * LP + l] = xv;
+      yv2 = solo_matvec<LP>(M2T + l, rp) + pw[l] * nu;      // P^T P x0
     }
     SOLO_STAMP(2)
     __syncthreads();
@@ -1333,7 +1361,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
       // ---- y = P^T P x0, norms, L1 z-update, dual ascent of pair (1,0), imaginary-plane recursion
       double n[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       if (lact) {
-        const double y = solo_matvec<LP>(PtPs + l, xn + pl * LP);
+        const double y = yv2;
         const double dd = xv - r_x0;
         n[3] = dd * dd;
         n[4] = r_x0 * r_x0;
@@ -1357,12 +1385,8 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
         r_x1 = z;
         r_y0 = y;
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) n[i] = warp_sum(n[i]);
-      if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) nA[warp * 8 + i] = n[i];
-      }
+      solo_treduce<8>(n, lane);
+      if ((lane & 3) == 0) nA[warp * 8 + (lane >> 2)] = n[0];
     } else {
       // ---- my sampling points: s' = Re h20 - mu20 (P Re x0) encodes dual ascent and projection
       double n_dh = 0.0, n_xm = 0.0;
@@ -1475,6 +1499,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
         mu_changed = true;
         need_v = true;
         sigma = solo_factor(L, LP, mu10, mu20, G0, PtPs, Gi, wv, Cv, sm + lay.rowk, sm + lay.colk, &bad_sh);
+        solo_m2<LP>(PtPs, Gi, wv, M2T, pw);
         load_gcol();
         inv_mu10 = 1.0 / mu10;
         inv_sigma = 1.0 / sigma;

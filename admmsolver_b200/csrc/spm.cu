@@ -1056,6 +1056,25 @@ __device__ __forceinline__ void solo_m2(const double* PtPs, const double* Gi, co
   __syncthreads();
 }
 
+// Same over the 16 lanes that share bit 0 of the lane index (offsets 16, 8, 4, 2): v[0] of lane `lane` is the sum
+// of value index  (lane >> (5 - log2 W)) & (W - 1)  over those lanes.
+template <int W>
+__device__ __forceinline__ void solo_treduce_pairs(double (&v)[W], int lane) {
+  int o = 16;
+#pragma unroll
+  for (int n = W / 2; n >= 1; n /= 2, o /= 2) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int k = 0; k < n; ++k) {
+      const double send = up ? v[k] : v[k + n];
+      const double keep = up ? v[k + n] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+#pragma unroll
+  for (; o >= 2; o /= 2) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+}
+
 template <int CS, int LP, bool REGP>
 __global__ void __launch_bounds__(SOLO_THREADS, 1)
     spm_solo_kernel(admm_spm_dims d, admm_spm_buffers b, const double* __restrict__ G0, int budget, int interval) {
@@ -1101,11 +1120,22 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
   if (REGP) {
 #pragma unroll
     for (int j = 0; j < (REGP ? LP : 1); ++j) Kreg[j] = 0.0;
-    if (rt >= 0 && rt < nrow) {
-      const int row = row0 + rt;
-      const double* pf = b.Pf + (size_t)(row >> 3) * 2 * NT * 64 + 4 * (row & 7) * 2;
+    // two neighbouring threads share two rows: thread (pair i, half h) keeps columns [h LP/2, (h+1) LP/2) of rows
+    // 2i and 2i+1 -- Kreg[k] = P[2i][c0 + k], Kreg[LP/2 + k] = P[2i+1][c0 + k] -- so that the partial V of the pair is
+    // summed in registers before the warp reduction, which then runs over 16 lanes and LP/2 columns only
+    if (rt >= 0 && (rt & ~1) < nrow) {
+      const int ra = row0 + (rt & ~1), c0 = (rt & 1) * (LP / 2);
 #pragma unroll
-      for (int j = 0; j < (REGP ? LP : 1); ++j) Kreg[j] = pf[(j >> 3) * 64 + ((j & 7) >> 1) * 2 + (j & 1)];
+      for (int r2 = 0; r2 < 2; ++r2) {
+        const int row = ra + r2;
+        const double* pf = b.Pf + (size_t)(row >> 3) * 2 * NT * 64 + 4 * (row & 7) * 2;
+#pragma unroll
+        for (int k2 = 0; k2 < (REGP ? LP / 2 : 0); ++k2) {
+          const int j = c0 + k2;
+          Kreg[REGP ? r2 * (LP / 2) + k2 : 0] = pf[(j >> 3) * 64 + ((j & 7) >> 1) * 2 + (j & 1)];
+        }
+      }
+      const int row = row0 + rt;
       s_reg = b.S[state_index(d, pt, row >> 3, 4 * g + ((row & 7) >> 1)) + (row & 1)];
     }
   } else {
@@ -1208,23 +1238,34 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
   auto exchange = [&](bool with_norms) {
     const double* slots = xch + phase * CS * (LP + 2);
     if (REGP) {
-      // per-warp partial V by transposed warp reductions of u * P[row][:] (16 or 8 columns at a time)
+      // per-warp partial V: the pair's two rows are combined in registers, then transposed warp reductions over the
+      // 16 lanes of equal half (16, 8 or 4 columns at a time)
       if (!lth) {
-        double* vw = vp + (warp - SOLO_LWARPS) * LP;
+        constexpr int H = LP / 2;
+        double* vw = vp + (warp - SOLO_LWARPS) * LP + (lane & 1) * H;
+        const bool hi = (lane & 1) != 0;
+        const double uo = __shfl_xor_sync(0xffffffffu, u_reg, 1);
+        const double ua = hi ? uo : u_reg, ub = hi ? u_reg : uo;
 #pragma unroll
-        for (int base = 0; base < (REGP ? LP : 0); base += 16) {
-          if (LP - base >= 16) {
+        for (int base = 0; base < (REGP ? H : 0); base += 16) {
+          if (H - base >= 16) {
             double v[16];
 #pragma unroll
-            for (int k2 = 0; k2 < 16; ++k2) v[k2] = u_reg * Kreg[REGP ? base + k2 : 0];
-            solo_treduce<16>(v, lane);
-            if ((lane & 1) == 0) vw[base + (lane >> 1)] = v[0];
-          } else {
+            for (int k2 = 0; k2 < 16; ++k2) v[k2] = ua * Kreg[REGP ? base + k2 : 0] + ub * Kreg[REGP ? H + base + k2 : 0];
+            solo_treduce_pairs<16>(v, lane);
+            vw[base + ((lane >> 1) & 15)] = v[0];
+          } else if (H - base == 8) {
             double v[8];
 #pragma unroll
-            for (int k2 = 0; k2 < 8; ++k2) v[k2] = u_reg * Kreg[REGP ? base + k2 : 0];
-            solo_treduce<8>(v, lane);
-            if ((lane & 3) == 0) vw[base + (lane >> 2)] = v[0];
+            for (int k2 = 0; k2 < 8; ++k2) v[k2] = ua * Kreg[REGP ? base + k2 : 0] + ub * Kreg[REGP ? H + base + k2 : 0];
+            solo_treduce_pairs<8>(v, lane);
+            if ((lane & 2) == 0) vw[base + ((lane >> 2) & 7)] = v[0];
+          } else {
+            double v[4];
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) v[k2] = ua * Kreg[REGP ? base + k2 : 0] + ub * Kreg[REGP ? H + base + k2 : 0];
+            solo_treduce_pairs<4>(v, lane);
+            if ((lane & 6) == 0) vw[base + ((lane >> 3) & 3)] = v[0];
           }
         }
       }
@@ -1391,17 +1432,23 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
       // ---- my sampling points: s' = Re h20 - mu20 (P Re x0) encodes dual ascent and projection
       double n_dh = 0.0, n_xm = 0.0;
       if (REGP) {
-        double q[4] = {0.0, 0.0, 0.0, 0.0};
+        // both rows of the pair over my half of the columns, then one exchange with the partner
+        constexpr int H = LP / 2;
+        const bool hi = (lane & 1) != 0;
+        const double* xh = xn + (hi ? H : 0);
+        double qa[2] = {0.0, 0.0}, qb[2] = {0.0, 0.0};
 #pragma unroll
-        for (int j = 0; j < LP; j += 4) {
-          const double2 x01 = *reinterpret_cast<const double2*>(xn + j), x23 = *reinterpret_cast<const double2*>(xn + j + 2);
-          q[0] += Kreg[REGP ? j : 0] * x01.x;
-          q[1] += Kreg[REGP ? j + 1 : 0] * x01.y;
-          q[2] += Kreg[REGP ? j + 2 : 0] * x23.x;
-          q[3] += Kreg[REGP ? j + 3 : 0] * x23.y;
+        for (int k2 = 0; k2 < H; k2 += 2) {
+          const double2 x2 = *reinterpret_cast<const double2*>(xh + k2);
+          qa[0] += Kreg[REGP ? k2 : 0] * x2.x;
+          qa[1] += Kreg[REGP ? k2 + 1 : 0] * x2.y;
+          qb[0] += Kreg[REGP ? H + k2 : 0] * x2.x;
+          qb[1] += Kreg[REGP ? H + k2 + 1 : 0] * x2.y;
         }
+        const double sa = qa[0] + qa[1], sb = qb[0] + qb[1];
+        const double qd = (hi ? sb : sa) + __shfl_xor_sync(0xffffffffu, hi ? sa : sb, 1);
         const double hre = is_neg(s_reg) ? 0.0 : s_reg;
-        const double s_new = hre - mu20 * ((q[0] + q[1]) + (q[2] + q[3]));
+        const double s_new = hre - mu20 * qd;
         const bool neg = is_neg(s_new);
         const double hnew = neg ? 0.0 : s_new;
         const double xm = neg ? s_new : 0.0;

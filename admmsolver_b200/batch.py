@@ -508,13 +508,14 @@ class SharedSpM:
             call("admm_spm_solo", C.byref(self.dims), C.byref(self.bufs), ptr(self.G0), int(niter),
                  int(interval_update_mu), stream())
             self._v_valid, self._fresh = True, False
-            fl = self.flags.cpu()
+            fl = torch.cat([self.flags, self.iters[:nb]]).cpu()        # one read-back: flags and iteration counts
             if int(fl[2]) != 0:
                 raise _lib.AdmmError("alpha A^H A + mu is not positive definite")
             if int(fl[0]) != 0:
                 self.flags[0] = 0
                 self._refresh_slots()
-            launched = int(self.iters[:nb].max().item())
+            launched = int(fl[4:].max())
+            solo_iters0 = int(fl[4])
             it = niter
         while it < niter:
             upd = (it % interval_update_mu == 0)
@@ -532,7 +533,7 @@ class SharedSpM:
                 if self._after_update_iteration():
                     break
         if track:
-            ndone = int(self.iters[0].item())
+            ndone = solo_iters0 if use_solo else int(self.iters[0].item())
             hist = self.history[:ndone].cpu().numpy()
             self.primal_residual.extend(hist[:, 0].tolist())
             self.dual_residual.extend(hist[:, 1].tolist())

@@ -156,6 +156,30 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity
       : "memory");
 }
 
+// ---- programmatic dependent launch (PDL): the next kernel of the stream may be scheduled while this one
+// still runs; it blocks in pdl_wait() until this grid has completed and its writes are visible.  Both are
+// no-ops for kernels launched without the attribute.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+}
+// launch with programmatic stream serialisation (every kernel launched this way starts with pdl_prologue())
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 inline int ceil_div(long long a, long long b) { return int((a + b - 1) / b); }
 
 }  // namespace admm

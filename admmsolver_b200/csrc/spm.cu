@@ -14,6 +14,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace cg = cooperative_groups;
 
@@ -459,6 +460,7 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
 // dependent loads and two small GEMMs, so more, shorter warps finish sooner than fewer, longer ones.
 template <int NT>
 __global__ void __launch_bounds__(128) spm_xupdate_kernel(admm_spm_dims d, admm_spm_buffers b) {
+  pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= d.npt * d.nplanes) return;
@@ -520,6 +522,7 @@ struct PassSmem {
 template <int NT, int MT, int MODE, int FNP>   // FNP: 0 = pass only, 1/2 = fused x-update of 1/2 planes
 __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
     spm_pass_kernel(admm_spm_dims d, admm_spm_buffers b) {
+  pdl_prologue();
   using SM = PassSmem<NT, MT>;
   constexpr int TILE_D = SM::TILE_D, CHUNK_D = SM::CHUNK_D, STATE_D = SM::STATE_D, STAGE_D = SM::STAGE_D;
   constexpr unsigned CHUNK_BYTES = CHUNK_D * sizeof(double), STATE_BYTES = STATE_D * sizeof(double);
@@ -788,6 +791,7 @@ __device__ __forceinline__ void gather_problem(const admm_spm_dims& d, const adm
 }
 
 __global__ void __launch_bounds__(256) spm_reduce_stage1(admm_spm_dims d, admm_spm_buffers b) {
+  pdl_prologue();
   __shared__ double scratch[10 * 32];
   const int per = (d.nb + gridDim.x - 1) / gridDim.x;
   const int p0 = per * blockIdx.x, p1 = min(d.nb, p0 + per);
@@ -805,6 +809,7 @@ __global__ void __launch_bounds__(256) spm_reduce_stage1(admm_spm_dims d, admm_s
 }
 
 __global__ void __launch_bounds__(256) spm_reduce_stage2(int nparts, admm_spm_buffers b) {
+  pdl_prologue();
   __shared__ double scratch[10 * 32];
   double v[10];
 #pragma unroll
@@ -864,6 +869,7 @@ __device__ __forceinline__ void decide_one(const admm_spm_dims& d, const admm_sp
 // nparts > 0 (batch-wide, unsharded): gsum has not been formed yet -- every CTA adds the nparts
 // stage-1 partials itself, in the same fixed order (saves the stage-2 launch of a short iteration).
 __global__ void __launch_bounds__(128) spm_decide_kernel(admm_spm_dims d, admm_spm_buffers b, int do_update_mu, int nparts) {
+  pdl_prologue();
   __shared__ double gs[10];
   if (nparts > 0) {
     if (threadIdx.x < 10) {
@@ -1629,6 +1635,12 @@ static int check_dims(const admm_spm_dims* d, const char* who) {
   return ADMM_OK;
 }
 
+// programmatic dependent launch of the per-iteration kernels (ADMM_NO_PDL=1: plain stream order, for A/B runs)
+static bool use_pdl() {
+  static const bool on = getenv("ADMM_NO_PDL") == nullptr;
+  return on;
+}
+
 static int ew_grid(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 16)); }
 
 template <int NT, int MT, int MODE, int FNP>
@@ -1642,7 +1654,7 @@ static int launch_pass_k(const admm_spm_dims* d, const admm_spm_buffers* b, cuda
     cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
-  k<<<grid, PASS_WARPS * 32, smem, s>>>(*d, *b);
+  launch_pdl(k, grid, dim3(PASS_WARPS * 32), smem, s, use_pdl(), *d, *b);
   return check_launch(FNP ? "admm_spm_step" : "admm_spm_pass");
 }
 
@@ -1781,9 +1793,9 @@ int admm_spm_xupdate(const admm_spm_dims* d, const admm_spm_buffers* b, admm_str
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int grid = ceil_div(d->npt * d->nplanes, 4);
   switch (d->Lp / 8) {
-    case 2: spm_xupdate_kernel<2><<<grid, 128, 0, s>>>(*d, *b); break;
-    case 5: spm_xupdate_kernel<5><<<grid, 128, 0, s>>>(*d, *b); break;
-    default: spm_xupdate_kernel<8><<<grid, 128, 0, s>>>(*d, *b); break;
+    case 2: launch_pdl(spm_xupdate_kernel<2>, dim3(grid), dim3(128), 0, s, use_pdl(), *d, *b); break;
+    case 5: launch_pdl(spm_xupdate_kernel<5>, dim3(grid), dim3(128), 0, s, use_pdl(), *d, *b); break;
+    default: launch_pdl(spm_xupdate_kernel<8>, dim3(grid), dim3(128), 0, s, use_pdl(), *d, *b); break;
   }
   return check_launch("admm_spm_xupdate");
 }
@@ -1807,14 +1819,15 @@ int admm_spm_reduce(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stre
   if (int rc = check_dims(d, "admm_spm_reduce")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int parts = reduce_parts(d);
-  spm_reduce_stage1<<<parts, 256, 0, s>>>(*d, *b);
-  spm_reduce_stage2<<<1, 256, 0, s>>>(parts, *b);
+  launch_pdl(spm_reduce_stage1, dim3(parts), dim3(256), 0, s, use_pdl(), *d, *b);
+  launch_pdl(spm_reduce_stage2, dim3(1), dim3(256), 0, s, use_pdl(), parts, *b);
   return check_launch("admm_spm_reduce");
 }
 
 int admm_spm_decide(const admm_spm_dims* d, const admm_spm_buffers* b, int do_update_mu, admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_decide")) return rc;
-  spm_decide_kernel<<<ceil_div(d->nb, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(*d, *b, do_update_mu, 0);
+  launch_pdl(spm_decide_kernel, dim3(ceil_div(d->nb, 128)), dim3(128), 0, static_cast<cudaStream_t>(stream), use_pdl(), *d, *b,
+             do_update_mu, 0);
   return check_launch("admm_spm_decide");
 }
 
@@ -1823,8 +1836,8 @@ int admm_spm_reduce_decide(const admm_spm_dims* d, const admm_spm_buffers* b, in
   ADMM_REQUIRE(d->batch_wide, ADMM_EINVAL, "admm_spm_reduce_decide: batch-wide criterion only");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int parts = reduce_parts(d);
-  spm_reduce_stage1<<<parts, 256, 0, s>>>(*d, *b);
-  spm_decide_kernel<<<ceil_div(d->nb, 128), 128, 0, s>>>(*d, *b, do_update_mu, parts);
+  launch_pdl(spm_reduce_stage1, dim3(parts), dim3(256), 0, s, use_pdl(), *d, *b);
+  launch_pdl(spm_decide_kernel, dim3(ceil_div(d->nb, 128)), dim3(128), 0, s, use_pdl(), *d, *b, do_update_mu, parts);
   return check_launch("admm_spm_reduce_decide");
 }
 

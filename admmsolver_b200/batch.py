@@ -704,7 +704,8 @@ class BatchedBasisPursuit:
             ent = self._kinv_entry(mu, speculative=False)
             self.bufs.Kinv = ent[0].data_ptr()
             self.need_factor.zero_()
-            for m2 in (min(mu * 2.0, self.max_mu), mu / 2.0):
+            fi = float(self.bufs.fact_incr)
+            for m2 in (min(mu * fi, self.max_mu), mu / fi):
                 if m2 != mu:
                     self._kinv_entry(m2, speculative=True)
             call("admm_bp_iterate", bref, int(niter), st)

@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) bp_fused_kernel(admm
 // The notebook / test instance of the reference (basis_pursuit.ipynb, test_optimizer.py:52-82: one
 // 100..200 x 1000 problem) is pure latency for the batch kernels: A has to be streamed from L2 every
 // iteration by a few CTAs.  Here a cluster of CS CTAs keeps the problem on chip for the whole solve:
-//   * CTA c owns N/CS columns: its slice of A (column-major, odd pitch: conflict-free in both
+//   * CTA c owns N/CS columns: its slice of A (column-major; pitch even with pitch/2 odd: 16-byte loads, conflict-free in both
 //     products) stays in shared memory, x0 / x1 / h / alpha A^T y / r of a column in the registers of
 //     one thread; it also owns M/CS rows of K^-1 (shared memory);
 //   * per iteration  c = A^T s  (own columns), x-update + soft threshold + dual ascent (registers),
@@ -601,7 +601,7 @@ constexpr int BPS_THREADS = 512;
 constexpr int BPS_PARTS = 8;       // row parts of the A^T s product
 
 struct BpsLayout {      // offsets in doubles
-  int Nc, Ncp, Mr, Mp, pitch, XW, nparts3, A, K, s, t, rs, cp, tp, nrm, nrmt, x1, bars, total;
+  int Nc, Nce, Ncp, Mr, Mp, Mq, Cq, pitch, XW, nparts3, A, K, s, t, rs, cp, tp, nrm, nrmt, x1, bars, total;
 };
 __host__ __device__ inline BpsLayout bps_layout(int M, int N, int cs) {
   BpsLayout o;
@@ -609,12 +609,19 @@ __host__ __device__ inline BpsLayout bps_layout(int M, int N, int cs) {
   o.Ncp = (o.Nc + 31) & ~31;
   o.Mr = (M + cs - 1) / cs;             // rows of K^-1 per CTA
   o.Mp = (M + 31) & ~31;
-  o.pitch = M | 1;
+  o.Mq = (((M + BPS_PARTS - 1) / BPS_PARTS) + 1) & ~1;      // rows per part of A^T s, even: 16-byte loads
+  // pitch: even (16-byte loads along a column) with pitch/2 odd (the 16-byte slots of 8 neighbouring columns fall
+  // into 8 different bank groups) and >= the zero-padded BPS_PARTS * Mq rows
+  o.pitch = BPS_PARTS * o.Mq > M ? BPS_PARTS * o.Mq : ((M + 1) & ~1);
+  if (o.pitch % 4 == 0) o.pitch += 2;
+  o.Nce = (o.Nc + 1) & ~1;                                   // columns of the slice, zero padded to even
+  if (o.Mp < BPS_PARTS * o.Mq) o.Mp = (BPS_PARTS * o.Mq + 31) & ~31;
   o.XW = (o.Mr + 5 + 1) & ~1;           // slot pitch of the reduce-scatter: my Mr rows of the partial t' + 5 norm partials
   o.nparts3 = BPS_THREADS / o.Mp > 0 ? BPS_THREADS / o.Mp : 1;
+  o.Cq = (((o.Nc + o.nparts3 - 1) / o.nparts3) + 1) & ~1;    // columns per part of A r', even
   int at = 0;
   auto take = [&](int n) { const int r = at; at += (n + 1) & ~1; return r; };
-  o.A = take(o.Nc * o.pitch);
+  o.A = take(o.Nce * o.pitch);
   o.K = take(o.Mr * M);
   o.s = take(2 * o.Mp);                 // all-gather receive buffers (ping-pong)
   o.t = take(o.Mp);
@@ -667,7 +674,7 @@ __global__ void __launch_bounds__(BPS_THREADS, 1) bp_solo_kernel(admm_bp_buffers
   const double* A = b.A + (size_t)prob * M * N;
   const double* Kinv = b.Kinv + (size_t)prob * M * M;
 
-  for (int idx = tid; idx < Nc * pitch; idx += BPS_THREADS) As[idx] = 0.0;
+  for (int idx = tid; idx < lay.Nce * pitch; idx += BPS_THREADS) As[idx] = 0.0;
   for (int i = tid; i < 2 * Mp; i += BPS_THREADS) sbuf[i] = 0.0;
   for (int i = tid; i < Mp; i += BPS_THREADS) tfull[i] = 0.0;
   for (int i = tid; i < Ncp; i += BPS_THREADS) rs[i] = 0.0;
@@ -711,8 +718,7 @@ __global__ void __launch_bounds__(BPS_THREADS, 1) bp_solo_kernel(admm_bp_buffers
   int done = 0, need = 0;
   double sq_p = 0.0, sq_d = 0.0, mu_res = mu;
   bool first = true;               // first pass of this launch: only t = A r, s = K^-1 t
-  const int Mq = (M + BPS_PARTS - 1) / BPS_PARTS;
-  const int Cq = (Nc + lay.nparts3 - 1) / lay.nparts3;
+  const int Mq = lay.Mq, Cq = lay.Cq;
 
   while (true) {
     BPS_STAMP(0)
@@ -720,19 +726,25 @@ __global__ void __launch_bounds__(BPS_THREADS, 1) bp_solo_kernel(admm_bp_buffers
       // ---- c = A^T s for my columns: warp = (row part, block of 32 columns)
       const double* sf = sbuf + (ph2 ^ 1) * Mp;             // the s received last
       const int part = warp & (BPS_PARTS - 1);
-      const int mlo = part * Mq, mhi = min(M, mlo + Mq);
+      const int mlo = part * Mq, mhi = mlo + Mq;            // rows >= M are zero in As and in s
       for (int blk = warp / BPS_PARTS; blk * 32 < Nc; blk += NW / BPS_PARTS) {
         const int nl = blk * 32 + lane;
         const double* ac = As + min(nl, Nc - 1) * pitch;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int m = mlo;
         for (; m + 3 < mhi; m += 4) {
-          a0 += ac[m] * sf[m];
-          a1 += ac[m + 1] * sf[m + 1];
-          a2 += ac[m + 2] * sf[m + 2];
-          a3 += ac[m + 3] * sf[m + 3];
+          const double2 p01 = *reinterpret_cast<const double2*>(ac + m), p23 = *reinterpret_cast<const double2*>(ac + m + 2);
+          const double2 s01 = *reinterpret_cast<const double2*>(sf + m), s23 = *reinterpret_cast<const double2*>(sf + m + 2);
+          a0 += p01.x * s01.x;
+          a1 += p01.y * s01.y;
+          a2 += p23.x * s23.x;
+          a3 += p23.y * s23.y;
         }
-        for (; m < mhi; ++m) a0 += ac[m] * sf[m];
+        if (m < mhi) {                                      // Mq is even: one 16-byte pair left
+          const double2 p01 = *reinterpret_cast<const double2*>(ac + m), s01 = *reinterpret_cast<const double2*>(sf + m);
+          a0 += p01.x * s01.x;
+          a1 += p01.y * s01.y;
+        }
         if (nl < Nc) cp[part * Ncp + nl] = (a0 + a1) + (a2 + a3);
       }
       BPS_STAMP(1)
@@ -785,12 +797,13 @@ __global__ void __launch_bounds__(BPS_THREADS, 1) bp_solo_kernel(admm_bp_buffers
         const int clo = q * Cq, chi = min(Nc, clo + Cq);
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         const double* ar = As + m;
-        int nl = clo;
+        int nl = clo;                                       // clo is even, rs is zero padded
         for (; nl + 3 < chi; nl += 4) {
-          a0 += ar[nl * pitch] * rs[nl];
-          a1 += ar[(nl + 1) * pitch] * rs[nl + 1];
-          a2 += ar[(nl + 2) * pitch] * rs[nl + 2];
-          a3 += ar[(nl + 3) * pitch] * rs[nl + 3];
+          const double2 r01 = *reinterpret_cast<const double2*>(rs + nl), r23 = *reinterpret_cast<const double2*>(rs + nl + 2);
+          a0 += ar[nl * pitch] * r01.x;
+          a1 += ar[(nl + 1) * pitch] * r01.y;
+          a2 += ar[(nl + 2) * pitch] * r23.x;
+          a3 += ar[(nl + 3) * pitch] * r23.y;
         }
         for (; nl < chi; ++nl) a0 += ar[nl * pitch] * rs[nl];
         tp[q * Mp + m] = (a0 + a1) + (a2 + a3);

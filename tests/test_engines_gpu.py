@@ -425,3 +425,76 @@ def test_bp_solo_cluster_solve(eng, nb, M, N, niter, interval, rtol):
         st = flat.bp_solve(A[b], y[b], 0.8, 0.06, niter, interval_update_mu=interval, rtol=rtol)
         st = flat.bp_solve(A[b], y[b], 0.8, 0.06, 40, interval_update_mu=interval, rtol=rtol, state=st)
         assert rel(e.x0()[b], st.x0.real) < TOL and float(e.mu[b]) == st.mu
+
+
+# ------------------------------------------------------------------ shape fuzz
+def _random_spm(rs, L, Nw, nb, cplx):
+    """A synthetic Pattern-B problem of arbitrary shape (no IR structure): decaying singular values, a smooth
+    random basis, one constraint row."""
+    s = np.exp(-np.linspace(0.0, 6.0, L)) * (1.0 + 0.1 * rs.rand(L))
+    w = np.linspace(-1.0, 1.0, Nw)
+    P = np.stack([np.cos((l + 1) * 0.7 * w + rs.rand()) * (1.0 + 0.2 * rs.randn()) for l in range(L)], axis=1) / np.sqrt(Nw)
+    P += 0.02 * rs.randn(Nw, L)
+    C_ = rs.rand(1, L) + 0.2
+    g = rs.randn(L, nb) * s[:, None]
+    if cplx:
+        g = g + 1j * 0.3 * rs.randn(L, nb) * s[:, None]
+    return s, np.ascontiguousarray(P), C_, g
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_spm_fuzz_shapes(eng, seed):
+    """Seeded random shapes through the default launch heuristics (fused / balanced / cluster-resident, all three
+    padded basis sizes, ragged L, Nw, nb; real and complex data; both criteria) against the oracle."""
+    from oracle import flat
+    batch, problems = eng
+    rs = np.random.RandomState(9000 + seed)
+    L = int(rs.choice([1, 3, 7, 8, 15, 16, 17, 23, 39, 40, 41, 57, 64]))
+    L = max(L, 2)      # L = 1 with the sum rule fixes x0 = 1/C: all residuals are rounding noise and so are the mu decisions
+    Nw = int(rs.choice([5, 8, 31, 32, 33, 100, 257, 640]))
+    nb = int(rs.choice([1, 2, 7, 8, 9, 17, 33, 70]))
+    cplx = bool(rs.rand() < 0.5)
+    batch_wide = bool(rs.rand() < 0.5)
+    s, P, C_, g = _random_spm(rs, L, Nw, nb, cplx)
+    lam, mu, niter, interval = 1e-3, 0.5, 90, 20
+    e = batch.SharedSpM(s, P, C_, np.ones(nb), g, lam=lam, mu=mu, batch_wide=batch_wide)
+    e.solve(niter, interval_update_mu=interval)
+    x0, x1, x2 = e.x0(), e.x1(), e.x2()
+    if batch_wide:
+        st = flat.spm_solve(s, P, C_, np.ones(nb), g, lam, niter, mu=mu, interval_update_mu=interval)
+        assert rel(x0, st.x0) < TOL and rel(x1, st.x1) < TOL and rel(x2, st.x2) < TOL, (L, Nw, nb, cplx)
+        assert float(e.mu10[0]) == st.mu10 and float(e.mu20[0]) == st.mu20
+    else:
+        for b in sorted(set([0, nb // 2, nb - 1])):
+            sb = flat.spm_solve(s, P, C_, np.array([1.0]), g[:, b], lam, niter, mu=mu, interval_update_mu=interval)
+            assert rel(x0[:, b], sb.x0) < TOL and rel(x2[:, b], sb.x2) < TOL, (L, Nw, nb, cplx, b)
+            assert float(e.mu10[b]) == sb.mu10 and float(e.mu20[b]) == sb.mu20
+    assert np.abs(C_ @ x0 - 1.0).max() < 1e-10                # constraint exact for every problem
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_bp_fuzz_shapes(eng, seed):
+    """Seeded random shapes of Pattern A through the default dispatch (cluster-resident / fused single-sweep with
+    and without clusters / two-sweep / direct for M >= N) against the oracle."""
+    from oracle import flat
+    batch, problems = eng
+    rs = np.random.RandomState(7000 + seed)
+    M = int(rs.choice([2, 7, 16, 33, 64, 100, 129, 200, 257, 300]))
+    N = int(rs.choice([3, 40, 127, 128, 129, 300, 512, 1000, 1500]))
+    nb = int(rs.choice([1, 2, 3, 8, 9, 40]))
+    if M * N * nb > 4_000_000:
+        nb = 1
+    A = rs.randn(nb, M, N)
+    xs = np.zeros((nb, N))
+    k = max(1, min(M, N) // 6)
+    for b in range(nb):
+        xs[b, rs.permutation(N)[:k]] = rs.randn(k)
+    y = np.einsum("bmn,bn->bm", A, xs) + 0.01 * rs.randn(nb, M)
+    alpha, lam, niter, interval = 0.9, 0.05, 70, 20
+    e = batch.BatchedBasisPursuit(A, y, alpha, lam)
+    e.solve(niter, interval_update_mu=interval)
+    x0, x1 = e.x0(), e.x1()
+    for b in sorted(set([0, nb // 2, nb - 1])):
+        st = flat.bp_solve(A[b], y[b], alpha, lam, niter, interval_update_mu=interval)
+        assert rel(x0[b], st.x0.real) < TOL and rel(x1[b], st.x1.real) < TOL, (M, N, nb, b)
+        assert float(e.mu[b]) == st.mu and int(e.iters[b]) == st.niter_done

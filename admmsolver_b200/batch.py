@@ -464,8 +464,10 @@ class SharedSpM:
             self._v_valid = False      # V was built with the old mu20
         return False
 
-    #: largest batch the cluster-resident single-launch solve is used for (one 8-CTA cluster per problem)
-    SOLO_MAX_NB = 16
+    #: largest batch the cluster-resident single-launch solve is used for (one 8-CTA cluster per problem, 16 clusters
+    #: per wave): measured break-even against the batch kernels at ~200 problems (tools/solo_nb_sweep.py:
+    #: 32 problems 3.7x, 64: 2.5x, 128: 1.5x faster, 256: 0.9x)
+    SOLO_MAX_NB = 128
 
     def solve(self, niter: int = 10000, interval_update_mu: int = 100, rtol: float = 1e-12,
               callback=None, keep_history: Optional[bool] = None, use_graph: Optional[bool] = None,

@@ -238,7 +238,7 @@ def test_spm_fused_per_problem_mixed_mu_and_early_stop(eng, ir_basis, mt):
     batch, problems = eng
     p = problems.spm_batch(19, ir_basis, Nw=120, seed=33)
     e = batch.SharedSpM(p.s, p.P, p.C, p.D, p.g, lam=p.lam, mu=p.mu, batch_wide=False, mt=mt, nsplit=1)
-    e.solve(600, interval_update_mu=40, rtol=2e-4)
+    e.solve(600, interval_update_mu=40, rtol=2e-4, use_solo=False)      # this test is about the fused batch kernel
     x0, x2 = e.x0(), e.x2()
     iters = e.iters.cpu().numpy()
     seen_mu, seen_it = set(), set()
@@ -319,7 +319,7 @@ def test_spm_balanced_decomposition_shapes(eng, ir_basis, nb, Nw, mt, nbal):
     assert rel(e.x0(), st.x0) < TOL and rel(e.x2(), st.x2) < TOL and rel(e.h20(), st.h20) < 1e-8
     assert float(e.mu10[0]) == st.mu10 and float(e.mu20[0]) == st.mu20
     e2 = batch.SharedSpM(p.s, p.P, p.C, p.D, p.g, lam=p.lam, mu=p.mu, batch_wide=False, mt=mt, nbal=nbal)
-    e2.solve(90, interval_update_mu=20)
+    e2.solve(90, interval_update_mu=20, use_solo=False)                  # the balanced batch kernels, not the cluster-resident solve
     x0 = e2.x0()
     for b in (0, nb // 2, nb - 1):
         sb = flat.spm_solve(p.s, p.P, p.C, np.array([1.0]), p.g[:, b], p.lam, 90, mu=p.mu, interval_update_mu=20)
@@ -329,7 +329,7 @@ def test_spm_balanced_decomposition_shapes(eng, ir_basis, nb, Nw, mt, nbal):
 # ------------------------------------------------------------------ cluster-resident single-launch solve
 @pytest.mark.parametrize("nb,Nw,eps,cplx", [(1, 2000, 1e-7, False), (1, 330, 1e-7, True), (5, 200, 1e-7, True),
                                             (13, 136, 1e-2, True), (3, 264, 1e-10, True), (16, 97, 1e-7, False),
-                                            (2, 2500, 1e-7, True)])
+                                            (2, 2500, 1e-7, True), (45, 120, 1e-7, True), (100, 64, 1e-2, False)])
 def test_spm_solo_cluster_solve(eng, nb, Nw, eps, cplx):
     """admm_spm_solo (one 8-CTA cluster per problem, the whole solve in one launch, in-kernel mu update and
     re-inversion): every problem == its own reference instance (oracle) incl. iteration count and mu, and

@@ -735,7 +735,7 @@ class BatchedBasisPursuit:
         for _ in range(rounds):
             call("admm_bp_factor", bref, ptr(self.info), st)
             call("admm_bp_iterate", bref, int(niter), st)
-            if self.nb <= 8:
+            if self.nb <= 16:
                 # a handful of problems (latency-bound): one small read-back per round instead of enqueueing
                 # all ceil(niter / interval) + 1 rounds blindly -- mu changes only a few times per solve
                 fl = torch.stack([self.iters, self.done]).cpu()

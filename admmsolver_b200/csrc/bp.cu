@@ -1005,8 +1005,12 @@ int admm_bp_factor(const admm_bp_buffers* b, int* info, admm_stream_t stream) {
 int admm_bp_iterate(const admm_bp_buffers* b, int iter_end, admm_stream_t stream) {
   if (int rc = check_bp(b, "admm_bp_iterate")) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // a handful of problems: cluster-resident solve (A and K^-1 distributed over the shared memory of 16 or 8 CTAs)
-  if (b->woodbury && b->nb <= 8 && b->M >= 8 && b->M <= 480 && b->N >= 128 && !getenv("ADMM_BP_NO_SOLO")) {
+  // a handful of problems: cluster-resident solve (A and K^-1 distributed over the shared memory of 16 or 8 CTAs per
+  // problem; more problems than clusters fit run in waves)
+  // measured on 128x512 problems (tools/bp_solo_nb_sweep.py): 8 problems 6.8 vs 10.7 us per iteration of the batch,
+  // 16: 9.5 vs 12.1, 24: 13.4 vs 12.2 (nine 16-CTA clusters per wave)
+  static const int solo_max_nb = getenv("ADMM_BP_SOLO_MAX") ? atoi(getenv("ADMM_BP_SOLO_MAX")) : 16;
+  if (b->woodbury && b->nb <= solo_max_nb && b->M >= 8 && b->M <= 480 && b->N >= 128 && !getenv("ADMM_BP_NO_SOLO")) {
     auto try_solo = [&](auto kern, int cs) -> int {       // 0: launched, 1: not possible with this cluster size, <0: error
       const BpsLayout lay = bps_layout(b->M, b->N, cs);
       const size_t smem = (size_t)lay.total * sizeof(double);
@@ -1046,7 +1050,7 @@ int admm_bp_iterate(const admm_bp_buffers* b, int iter_end, admm_stream_t stream
       }
       return check_launch("admm_bp_iterate(solo)") == ADMM_OK ? 0 : -1;
     };
-    int r = b->nb * 16 <= 144 ? try_solo(bp_solo_kernel<16>, 16) : 1;
+    int r = try_solo(bp_solo_kernel<16>, 16);
     if (r == 1) r = try_solo(bp_solo_kernel<8>, 8);
     if (r == 0) return ADMM_OK;
     if (r < 0) return ADMM_ECUDA;

@@ -390,7 +390,7 @@ def run_ours(args):
             # feeds the next A r), K^-1 once; the N-vectors never leave shared memory
             bytes_per_unit = 8.0 * M * N + 8.0 * M * M
             kernel_name = "bp_fused_kernel<%d>" % (8 if M <= 128 else 16)
-            if nb_local <= 8 and M <= 480 and N >= 128:
+            if nb_local <= 16 and M <= 480 and N >= 128:
                 # cluster-resident solve: A and K^-1 never leave shared memory; the same algorithmic bytes
                 # divided by the time are an on-chip rate, not HBM traffic (latency-bound single problem)
                 kernel_name = "bp_solo_kernel<16>"

@@ -332,7 +332,7 @@ int admm_bp_factor(const admm_bp_buffers* b, int* info, admm_stream_t stream);
  * (iter % interval_update_mu == 0) -- update_mu.  With At set (Woodbury path, M <= 256) A is streamed
  * ONCE per iteration: the column tile that yields A^T s also feeds the next iteration's A r'.  A problem whose mu changed sets need_factor
  * and stops; the caller runs admm_bp_factor and calls again with the same iter_end.
- * A handful of problems (nb <= 8, Woodbury, 8 <= M <= 480, N >= 128: the notebook / test instances of the
+ * A handful of problems (nb <= 16, Woodbury, 8 <= M <= 480, N >= 128: the notebook / test instances of the
  * reference) run cluster-resident instead: a thread-block cluster of 16 (or 8) CTAs per problem keeps its
  * column slices of A and row slices of K^-1 in shared memory and the N-vectors in registers for all
  * iterations; the two exchanges per iteration (all-reduce of A r', all-gather of K^-1 t) are DSMEM pushes. */

@@ -385,7 +385,8 @@ def test_spm_solo_resume_and_handover(eng, ir_basis):
 # ------------------------------------------------------------------ cluster-resident basis pursuit
 @pytest.mark.parametrize("nb,M,N,niter,interval,rtol", [(1, 200, 1000, 260, 50, 1e-12), (1, 100, 1000, 150, 40, 1e-12),
                                                         (3, 37, 300, 200, 25, 1e-12), (8, 128, 512, 120, 30, 1e-12),
-                                                        (2, 50, 130, 400, 20, 1e-6), (1, 9, 2100, 90, 30, 1e-12)])
+                                                        (2, 50, 130, 400, 20, 1e-6), (1, 9, 2100, 90, 30, 1e-12),
+                                                        (13, 64, 256, 110, 30, 1e-12)])
 def test_bp_solo_cluster_solve(eng, nb, M, N, niter, interval, rtol):
     """bp_solo_kernel (a handful of problems: A and K^-1 distributed over the shared memory of a 16- or 8-CTA
     cluster, DSMEM push exchanges): every problem == its reference instance (oracle) incl. mu history, iteration

@@ -464,6 +464,9 @@ class SharedSpM:
             self._v_valid = False      # V was built with the old mu20
         return False
 
+    #: iterations per captured CUDA graph (see _replay_plain)
+    GRAPH_CHUNK = 32
+
     #: largest batch the cluster-resident single-launch solve is used for (one 8-CTA cluster per problem, 16 clusters
     #: per wave): measured break-even against the batch kernels at ~200 problems (tools/solo_nb_sweep.py:
     #: 32 problems 3.7x, 64: 2.5x, 128: 1.5x faster, 256: 0.9x)
@@ -497,13 +500,13 @@ class SharedSpM:
         if use_graph is None:
             use_graph = callback is None and self.pass_events is None and self.group is None
         solo_ok = (callback is None and self.pass_events is None and self.group is None and nb <= self.SOLO_MAX_NB
-                   and (nb == 1 or not self.batch_wide)
-                   and _lib.lib.admm_spm_solo_supported(C.byref(self.dims)) != 0)
+                   and _lib.lib.admm_spm_solo_supported(C.byref(self.dims)) != 0)     # batch-wide: co-resident clusters only
         if use_solo is None:
             use_solo = solo_ok and use_graph
         elif use_solo and not solo_ok:
-            raise NotImplementedError("the cluster-resident solve needs nb <= %d, the per-problem criterion (or one "
-                                      "problem), no callback and an operator that fits the cluster" % self.SOLO_MAX_NB)
+            raise NotImplementedError("the cluster-resident solve needs nb <= %d (batch-wide criterion: as many clusters "
+                                      "as fit the GPU at once), no callback and an operator that fits the cluster"
+                                      % self.SOLO_MAX_NB)
         launched = 0
         it = 0
         if use_solo:
@@ -550,21 +553,30 @@ class SharedSpM:
             # one-off launch, kept outside the graph: V from the state with the new mu20
             call("admm_spm_pass", C.byref(self.dims), C.byref(self.bufs), 1, stream())
             self._v_valid = True
-        if run == 0:
-            return
-        graph = self._graphs.get((run, key))
-        if graph is None:
-            if len(self._graphs) >= 8:
-                self._graphs.clear()
-            graph = torch.cuda.CUDAGraph()
-            before = _lib.launch_count
-            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                for _ in range(run):
+        # graphs of GRAPH_CHUNK iterations, replayed as often as they fit (capturing and instantiating one graph of
+        # all ~interval iterations costs 50-800 ms on the first solve of a plan -- more than a short solve itself);
+        # the few iterations left over are launched eagerly
+        while run > 0:
+            n = min(run, self.GRAPH_CHUNK)
+            if n < 8:
+                for _ in range(n):
                     self._iteration(False)
-            _lib.launch_count = before          # capture enqueues nothing
-            self._graphs[(run, key)] = graph
-        graph.replay()
-        _lib.launch_count += run * self._launches_per_iteration()
+                run -= n
+                continue
+            graph = self._graphs.get((n, key))
+            if graph is None:
+                if len(self._graphs) >= 8:
+                    self._graphs.clear()
+                graph = torch.cuda.CUDAGraph()
+                before = _lib.launch_count
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    for _ in range(n):
+                        self._iteration(False)
+                _lib.launch_count = before          # capture enqueues nothing
+                self._graphs[(n, key)] = graph
+            graph.replay()
+            _lib.launch_count += n * self._launches_per_iteration()
+            run -= n
 
     def _launches_per_iteration(self) -> int:
         data = 1 if (self.dims.nsplit == 1 and self.dims.nbal == 0) else 2

@@ -907,6 +907,12 @@ __global__ void __launch_bounds__(128) spm_decide_kernel(admm_spm_dims d, admm_s
 //   * the only exchange per iteration is the partial V = P^T|s'| (L doubles) and two norm partials,
 //     pulled from the peers' shared memory (DSMEM) after ONE cluster barrier.
 // Warps 0-3 hold the L-vectors in registers (thread = (plane, l)); warps 4-11 own the sampling points.
+__device__ __forceinline__ unsigned ld_acquire_u32(const int* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 constexpr int SOLO_THREADS = 384;
 constexpr int SOLO_LWARPS = 4;
 constexpr int SOLO_RTHREADS = SOLO_THREADS - 32 * SOLO_LWARPS;
@@ -1115,6 +1121,8 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
   double* nB = sm + lay.nB;        // [row warp][2]
   double* nBt = sm + lay.nBt;      // [2] cluster totals
   __shared__ int bad_sh;
+  __shared__ double gtot[10];
+  int gpar = 0, gtarget = 0;       // batch-wide all-reduce over the clusters: buffer parity, expected arrivals
 
   // ---- one-time loads (everything zero padded)
   if (tid == 0) bad_sh = 0;
@@ -1523,6 +1531,38 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
     }
     s[7] += nBt[0];
     s[8] += nBt[1];
+    if (d.batch_wide && d.nb > 1) {
+      // batch-wide criterion over several clusters (a packed PartialDiagonalMatrix batch of a few problems): all-reduce
+      // of the ten squared norms through global memory.  Every cluster publishes its sums and arrives on a counter;
+      // all CTAs wait for the nb arrivals of this iteration and add the nb entries in problem order -- identical
+      // totals, identical decisions everywhere.  The launcher guarantees that all nb clusters are co-resident.
+      double* slots = b.gpart + (size_t)gpar * d.nb * 16;
+      if (crank == 0) {
+        double mine = 0.0;
+#pragma unroll
+        for (int i = 0; i < 10; ++i)
+          if (tid == i) mine = s[i];
+        if (tid < 10) slots[prob * 16 + tid] = mine;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(&b.flags[3], 1);
+      }
+      gtarget += d.nb;
+      if (tid == 0) {
+        while ((int)ld_acquire_u32(&b.flags[3]) < gtarget) {
+        }
+      }
+      __syncthreads();
+      if (tid < 10) {
+        double a = 0.0;
+        for (int p2 = 0; p2 < d.nb; ++p2) a += __ldcg(slots + p2 * 16 + tid);
+        gtot[tid] = a;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 10; ++i) s[i] = gtot[i];
+      gpar ^= 1;
+    }
     // check_convergence (optimizer.py:232-249) on the squared norms: p / max(a, b) < rtol  <=>
     // p^2 < rtol^2 max(a^2, b^2)  (mu > 0 cancels in the dual tests; 0/0 and x/0 stay "not converged")
     sq[0] = s[0];
@@ -1687,7 +1727,7 @@ static size_t solo_smem_bytes(const admm_spm_dims* d, int cs) {
 
 template <int CS, int LP, bool REGP>
 static int launch_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const double* G0, int niter, int interval,
-                       cudaStream_t st) {
+                       cudaStream_t st, int* max_clusters = nullptr) {   // max_clusters != NULL: occupancy query only
   const size_t smem = solo_smem_bytes(d, CS);
   auto kern = spm_solo_kernel<CS, LP, REGP>;
   static size_t configured = 0;     // per instantiation
@@ -1707,6 +1747,21 @@ static int launch_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const 
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
+  if (max_clusters != nullptr) {
+    static size_t cached_smem = 0;
+    static int cached_n = 0;
+    if (cached_smem != smem) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+      }
+      cached_smem = smem;
+      cached_n = n;
+    }
+    *max_clusters = cached_n;
+    return ADMM_OK;
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *d, *b, G0, niter, interval);
   if (e != cudaSuccess) {
     set_error("admm_spm_solo: %s", cudaGetErrorString(e));
@@ -1841,28 +1896,40 @@ int admm_spm_reduce_decide(const admm_spm_dims* d, const admm_spm_buffers* b, in
   return check_launch("admm_spm_reduce_decide");
 }
 
+static int dispatch_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const double* G0, int niter, int interval,
+                         cudaStream_t st, int* max_clusters) {
+  // sampling points per CTA <= 256: P, the state and the cached inverse stay in registers
+  const bool regp = solo_regp(d, 8);
+  switch (d->Lp) {
+    case 16: return regp ? launch_solo<8, 16, true>(d, b, G0, niter, interval, st, max_clusters)
+                         : launch_solo<8, 16, false>(d, b, G0, niter, interval, st, max_clusters);
+    case 40: return regp ? launch_solo<8, 40, true>(d, b, G0, niter, interval, st, max_clusters)
+                         : launch_solo<8, 40, false>(d, b, G0, niter, interval, st, max_clusters);
+    default: return launch_solo<8, 64, false>(d, b, G0, niter, interval, st, max_clusters);   // 64 doubles per row: shared memory
+  }
+}
+
 int admm_spm_solo_supported(const admm_spm_dims* d) {
   if (d == nullptr || d->L < 1 || (d->Lp != 16 && d->Lp != 40 && d->Lp != 64) || d->nb < 1) return 0;
-  return solo_smem_bytes(d, 8) <= 200 * 1024 ? 8 : 0;
+  if (solo_smem_bytes(d, 8) > 200 * 1024) return 0;
+  if (d->batch_wide && d->nb > 1) {
+    // the batch-wide criterion synchronises the clusters every iteration: all of them have to be co-resident
+    int n = 0;
+    if (dispatch_solo(d, nullptr, nullptr, 0, 0, nullptr, &n) != ADMM_OK || d->nb > n) return 0;
+  }
+  return 8;
 }
 
 int admm_spm_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const double* G0, int niter, int interval_update_mu,
                   admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_solo")) return rc;
-  ADMM_REQUIRE(!d->batch_wide || d->nb == 1, ADMM_EINVAL, "admm_spm_solo: per-problem criterion only (or a single problem)");
   ADMM_REQUIRE(admm_spm_solo_supported(d) != 0, ADMM_EUNSUPPORTED,
-               "admm_spm_solo: L=%d, Nw=%d do not fit the shared memory of an 8-CTA cluster", d->L, d->Nw);
+               "admm_spm_solo: L=%d, Nw=%d do not fit the shared memory of an 8-CTA cluster, or (batch-wide criterion) the %d "
+               "clusters cannot be co-resident", d->L, d->Nw, d->nb);
   ADMM_REQUIRE(G0 != nullptr && niter >= 0 && interval_update_mu >= 0, ADMM_EINVAL, "admm_spm_solo: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // sampling points per CTA <= 256: P, the state and the cached inverse stay in registers
-  const bool regp = solo_regp(d, 8);
-  switch (d->Lp) {
-    case 16: return regp ? launch_solo<8, 16, true>(d, b, G0, niter, interval_update_mu, st)
-                         : launch_solo<8, 16, false>(d, b, G0, niter, interval_update_mu, st);
-    case 40: return regp ? launch_solo<8, 40, true>(d, b, G0, niter, interval_update_mu, st)
-                         : launch_solo<8, 40, false>(d, b, G0, niter, interval_update_mu, st);
-    default: return launch_solo<8, 64, false>(d, b, G0, niter, interval_update_mu, st);   // 64 doubles per row: shared memory
-  }
+  if (d->batch_wide && d->nb > 1) cudaMemsetAsync(b->flags + 3, 0, sizeof(int), st);      // arrival counter of the all-reduce
+  return dispatch_solo(d, b, G0, niter, interval_update_mu, st, nullptr);
 }
 
 }  // extern "C"

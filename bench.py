@@ -13,6 +13,7 @@ Rank 0 prints ONE JSON line.
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
@@ -320,7 +321,8 @@ def run_ours(args):
 
         # a handful of problems: the cluster-resident single-launch solve (admm_spm_solo); every step
         # starts from the zero state so that it really runs `niter` iterations
-        solo = nb_local <= eng.SOLO_MAX_NB and (nb_local == 1 or not batch_wide) and group is None
+        solo = (nb_local <= eng.SOLO_MAX_NB and group is None
+                and _lib.lib.admm_spm_solo_supported(C.byref(eng.dims)) != 0)
 
         def step():
             if solo:

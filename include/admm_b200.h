@@ -217,7 +217,7 @@ typedef struct admm_spm_buffers {
   double* gpart;          /* [256][16] scratch of the two-stage reduce                         */
   /* control */
   int* iter_counter;      /* device scalar: iterations launched so far in this solve call      */
-  int* flags;             /* [4]: 0 any mu changed, 1 number of problems done, 2 first non-positive pivot of an in-kernel re-inversion (admm_spm_solo), 3 reserved */
+  int* flags;             /* [4]: 0 any mu changed, 1 number of problems done, 2 first non-positive pivot of an in-kernel re-inversion (admm_spm_solo), 3 arrival counter of its batch-wide all-reduce */
   double* history;        /* [hist_cap][2] primal/dual per iteration (batch_wide or nb==1), or NULL */
   int hist_cap;
   double lam;             /* L1 weight                                                         */
@@ -278,8 +278,11 @@ int admm_spm_decide(const admm_spm_dims* d, const admm_spm_buffers* b, int do_up
  * iterations (0: never).  G0 = alpha A^H A (Lp x Lp, row-major, as for admm_spm_factor).  Reads and
  * writes the same buffers as the batch kernels (state in, state out; V, y0, mu20_used consistent),
  * sets flags[0] when a mu changed (the caller re-maps its factor cache), flags[1] += converged
- * problems, flags[2] = first non-positive pivot.  Per-problem criterion (or nb == 1).
- * admm_spm_solo_supported: cluster size used (8) if L, Nw fit the cluster's shared memory, else 0. */
+ * problems, flags[2] = first non-positive pivot.  Per-problem criterion: any nb (clusters run in waves).  Batch-wide
+ * criterion with nb > 1 (a packed batch of a few problems): the clusters all-reduce their ten squared norms through
+ * gpart / flags[3] every iteration, so all nb clusters have to be co-resident (nb <= ~16 on a B200).
+ * admm_spm_solo_supported: cluster size used (8) if L, Nw fit the cluster's shared memory (and, batch-wide, the nb
+ * clusters fit the GPU at once), else 0. */
 int admm_spm_solo_supported(const admm_spm_dims* d);
 int admm_spm_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const double* G0, int niter,
                   int interval_update_mu, admm_stream_t stream);

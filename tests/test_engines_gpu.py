@@ -314,7 +314,7 @@ def test_spm_balanced_decomposition_shapes(eng, ir_basis, nb, Nw, mt, nbal):
     p = problems.spm_batch(nb, ir_basis, Nw=Nw, seed=nb + Nw)
     e = batch.SharedSpM(p.s, p.P, p.C, p.D, p.g, lam=p.lam, mu=p.mu, batch_wide=True, mt=mt, nbal=nbal)
     assert e.dims.nbal == nbal and e.dims.mt == mt
-    e.solve(90, interval_update_mu=20)
+    e.solve(90, interval_update_mu=20, use_solo=False)
     st = flat.spm_solve(p.s, p.P, p.C, p.D, p.g, p.lam, 90, mu=p.mu, interval_update_mu=20)
     assert rel(e.x0(), st.x0) < TOL and rel(e.x2(), st.x2) < TOL and rel(e.h20(), st.h20) < 1e-8
     assert float(e.mu10[0]) == st.mu10 and float(e.mu20[0]) == st.mu20
@@ -499,3 +499,28 @@ def test_bp_fuzz_shapes(eng, seed):
         st = flat.bp_solve(A[b], y[b], alpha, lam, niter, interval_update_mu=interval)
         assert rel(x0[b], st.x0.real) < TOL and rel(x1[b], st.x1.real) < TOL, (M, N, nb, b)
         assert float(e.mu[b]) == st.mu and int(e.iters[b]) == st.niter_done
+
+
+@pytest.mark.parametrize("nb,Nw,cplx", [(2, 300, True), (6, 136, True), (11, 100, False), (14, 64, True)])
+def test_spm_solo_batchwide_small_packed_batch(eng, ir_basis, nb, Nw, cplx):
+    """A packed batch of a few problems with the reference's batch-global mu / stopping (PartialDiagonalMatrix
+    packing): one cluster per problem, the ten squared norms all-reduced over the co-resident clusters every
+    iteration -- equal to the oracle's packed solve (mu history, early stop, residual history) and to the batch kernels."""
+    from oracle import flat
+    batch, problems = eng
+    p = problems.spm_batch(nb, ir_basis, Nw=Nw, seed=60 + nb, complex_noise=cplx)
+    g = p.g if cplx else p.g.real.copy()
+    e = batch.SharedSpM(p.s, p.P, p.C, p.D, g, lam=p.lam, mu=p.mu, batch_wide=True)
+    n = e.solve(260, interval_update_mu=25, rtol=3e-5, use_solo=True)
+    c = batch.SharedSpM(p.s, p.P, p.C, p.D, g, lam=p.lam, mu=p.mu, batch_wide=True)
+    c.solve(260, interval_update_mu=25, rtol=3e-5, use_solo=False)
+    st = flat.spm_solve(p.s, p.P, p.C, p.D, g, p.lam, 260, mu=p.mu, interval_update_mu=25, rtol=3e-5)
+    assert n == st.niter_done == int(c.iters[0]) and int(e.iters[nb - 1]) == st.niter_done
+    assert rel(e.x0(), st.x0) < TOL and rel(e.x1(), st.x1) < TOL and rel(e.x2(), st.x2) < TOL
+    assert rel(e.h10(), st.h10) < 1e-8 and rel(e.h20(), st.h20) < 1e-8
+    assert float(e.mu10[0]) == st.mu10 == float(e.mu10[nb - 1]) and float(e.mu20[0]) == st.mu20 == float(e.mu20[nb - 1])
+    assert rel(e.primal_residual, st.primal) < 1e-8 and rel(e.dual_residual, st.dual) < 1e-8
+    assert rel(e.x0(), c.x0()) < 1e-11
+    e.solve(30, interval_update_mu=25)                       # resume
+    st = flat.spm_solve(p.s, p.P, p.C, p.D, g, p.lam, 30, mu=p.mu, interval_update_mu=25, state=st)
+    assert rel(e.x0(), st.x0) < TOL and float(e.mu20[0]) == st.mu20

@@ -514,6 +514,10 @@ class SharedSpM:
                  int(interval_update_mu), stream())
             self._v_valid, self._fresh = True, False
             fl = torch.cat([self.flags, self.iters[:nb]]).cpu()        # one read-back: flags and iteration counts
+            if int(fl[2]) < 0:
+                raise _lib.AdmmError("cluster-resident solve: the clusters of the batch did not become co-resident "
+                                     "(another kernel holding SMs?); the state is undefined -- reset() and solve again "
+                                     "with use_solo=False")
             if int(fl[2]) != 0:
                 raise _lib.AdmmError("alpha A^H A + mu is not positive definite")
             if int(fl[0]) != 0:

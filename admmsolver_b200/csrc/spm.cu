@@ -1549,10 +1549,18 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
       }
       gtarget += d.nb;
       if (tid == 0) {
+        // watchdog: if the clusters are not all co-resident after all (the launcher checks the occupancy), give up
+        // after ~2 s instead of hanging the GPU; every CTA of every cluster runs into the same timeout
+        const long long t_start = clock64();
         while ((int)ld_acquire_u32(&b.flags[3]) < gtarget) {
+          if (clock64() - t_start > 4000000000LL) {
+            bad_sh = -1;
+            break;
+          }
         }
       }
       __syncthreads();
+      if (bad_sh < 0) break;
       if (tid < 10) {
         double a = 0.0;
         for (int p2 = 0; p2 < d.nb; ++p2) a += __ldcg(slots + p2 * 16 + tid);

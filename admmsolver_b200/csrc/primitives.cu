@@ -205,9 +205,90 @@ __global__ void __launch_bounds__(128) gemm_dmma_kernel(int m, int n, int k, con
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// skinny products (n <= 4 right-hand sides: the matrix-vector products of the generic executor; a real
+// operator on a complex vector arrives as n = 2 interleaved columns).  Bandwidth-bound: A is read once,
+// coalesced, by as many warps as there are rows (op N) or by 8 row-interleaved warps per 32 columns (op T/H).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum_t(T v);
+template <>
+__device__ __forceinline__ double warp_sum_t<double>(double v) { return warp_sum(v); }
+template <>
+__device__ __forceinline__ cplx warp_sum_t<cplx>(cplx v) { return {warp_sum(v.x), warp_sum(v.y)}; }
+
+template <typename T, int NC>
+__global__ void __launch_bounds__(256) gemv_n_kernel(int m, int n, int k, const T* __restrict__ A, int lda,
+                                                     const T* __restrict__ B, int ldb, T* __restrict__ C, int ldc) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= m) return;
+  T acc[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) acc[j] = num<T>::zero();
+  const T* ar = A + (size_t)row * lda;
+  for (int c = lane; c < k; c += 32) {
+    const T a = ar[c];
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      if (j < n) acc[j] = num<T>::add(acc[j], num<T>::mul(a, B[(size_t)c * ldb + j]));
+  }
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    const T v = warp_sum_t<T>(acc[j]);
+    if (lane == 0 && j < n) C[(size_t)row * ldc + j] = v;
+  }
+}
+
+template <typename T, int OP, int NC>
+__global__ void __launch_bounds__(256) gemv_t_kernel(int m, int n, int k, const T* __restrict__ A, int lda,
+                                                     const T* __restrict__ B, int ldb, T* __restrict__ C, int ldc) {
+  __shared__ T part[8][NC][33];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * 32 + lane;        // output row i = column of the stored k x m matrix
+  T acc[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) acc[j] = num<T>::zero();
+  if (col < m) {
+#pragma unroll 4
+    for (int kk = w; kk < k; kk += 8) {
+      T a = A[(size_t)kk * lda + col];
+      if (OP == ADMM_OP_H) a = num<T>::conj(a);
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (j < n) acc[j] = num<T>::add(acc[j], num<T>::mul(a, B[(size_t)kk * ldb + j]));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NC; ++j) part[w][j][lane] = acc[j];
+  __syncthreads();
+  if (w == 0 && col < m) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      T v = part[0][j][lane];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) v = num<T>::add(v, part[q][j][lane]);
+      if (j < n) C[(size_t)col * ldc + j] = v;
+    }
+  }
+}
+
+template <typename T, int NC>
+static int launch_gemv(int op, int m, int n, int k, const T* a, int lda, const T* b, int ldb, T* c, int ldc, cudaStream_t s) {
+  if (op == ADMM_OP_N) gemv_n_kernel<T, NC><<<ceil_div(m, 8), 256, 0, s>>>(m, n, k, a, lda, b, ldb, c, ldc);
+  else if (op == ADMM_OP_T) gemv_t_kernel<T, ADMM_OP_T, NC><<<ceil_div(m, 32), 256, 0, s>>>(m, n, k, a, lda, b, ldb, c, ldc);
+  else gemv_t_kernel<T, ADMM_OP_H, NC><<<ceil_div(m, 32), 256, 0, s>>>(m, n, k, a, lda, b, ldb, c, ldc);
+  return check_launch("admm_gemm(skinny)");
+}
+
 template <typename T>
 static int launch_gemm(int op, int m, int n, int k, const void* A, int lda, const void* B, int ldb, void* C,
                        int ldc, cudaStream_t s) {
+  if (n <= 4 && !getenv("ADMM_GEMM_NO_SKINNY")) {
+    const T* a = static_cast<const T*>(A);
+    const T* b = static_cast<const T*>(B);
+    T* c = static_cast<T*>(C);
+    return n <= 2 ? launch_gemv<T, 2>(op, m, n, k, a, lda, b, ldb, c, ldc, s) : launch_gemv<T, 4>(op, m, n, k, a, lda, b, ldb, c, ldc, s);
+  }
   dim3 grid(ceil_div(n, 32), ceil_div(m, 32));
   const T* a = static_cast<const T*>(A);
   const T* b = static_cast<const T*>(B);

@@ -475,7 +475,10 @@ class SimpleOptimizer(object):
         nbuf = torch.zeros(6 * max(1, len(self._pairs)), dtype=D.F64, device=self._xd[0].device)
         graphable = callback is None and self._graphable()
         graph = graph_key = warm_key = None
-        for it in range(niter):
+        npair = len(self._pairs)
+        hist = None          # device copy of the norms of every iteration of a chunk
+        it = 0
+        while it < niter:
             if callback is not None:
                 self._sweep_dev(update_h)
                 primal, dual = self.residual()
@@ -488,14 +491,34 @@ class SimpleOptimizer(object):
                     break
                 if it % interval_update_mu == 0:
                     self.update_mu()
+                it += 1
                 continue
             # sweep + norms: eagerly the first time for every set of penalties (fills the adjoint / mu_k /
             # inverse caches outside any capture), then captured once and replayed as ONE graph launch
             key = tuple(float(self._mu[p]) for p in self._pairs) + (bool(update_h),)
+            snap = None
             if graph is not None and graph_key == key:
-                graph.replay()
+                # Run ahead: all iterations up to and including the next update_mu iteration are replayed back to
+                # back, their norms collected on the device and read with ONE synchronisation.  Should the stopping
+                # test have fired in the middle of the chunk (it can only happen once per solve), the state is rolled
+                # back to the start of the chunk and exactly the iterations that count are replayed again.
+                nxt = it if it % interval_update_mu == 0 else (it // interval_update_mu + 1) * interval_update_mu
+                n = max(1, min(niter - it, nxt - it + 1, self.GENERIC_CHUNK))
+                if n > 1:
+                    snap = ([t.clone() for t in self._xd], {p: t.clone() for p, t in self._hd.items()},
+                            [t.clone() for t in self._xd_old])
+                    if hist is None:
+                        hist = torch.empty(self.GENERIC_CHUNK, nbuf.numel(), dtype=D.F64, device=nbuf.device)
+                    for k in range(n):
+                        graph.replay()
+                        hist[k].copy_(nbuf)
+                    rows = np.sqrt(hist[:n].cpu().numpy())
+                else:
+                    graph.replay()
+                    rows = np.sqrt(nbuf.cpu().numpy())[None]
             else:
                 graph = None
+                n = 1
                 self._sweep_dev(update_h)
                 self._launch_norms(nbuf)
                 if graphable and warm_key == key:
@@ -511,16 +534,34 @@ class SimpleOptimizer(object):
                         torch.cuda.synchronize()
                     D._lib.launch_count = before
                 warm_key = key
-            nr = np.sqrt(nbuf.cpu().numpy()).reshape(len(self._pairs), 6)
-            self._primal_residual.append(float(sum(float(v) for v in nr[:, 0])))
-            self._dual_residual.append(float(sum(float(v) for v in nr[:, 3])))
-            with np.errstate(all="ignore"):
-                conv = all(bool(r[0] / max(r[1], r[2]) < rtol) and bool(r[3] / max(r[4], r[5]) < rtol) for r in nr)
+                rows = np.sqrt(nbuf.cpu().numpy())[None]
+            done = 0
+            conv = False
+            for k in range(n):
+                nr = rows[k].reshape(npair, 6)
+                self._primal_residual.append(float(sum(float(v) for v in nr[:, 0])))
+                self._dual_residual.append(float(sum(float(v) for v in nr[:, 3])))
+                done = k + 1
+                with np.errstate(all="ignore"):
+                    conv = all(bool(r[0] / max(r[1], r[2]) < rtol) and bool(r[3] / max(r[4], r[5]) < rtol) for r in nr)
+                if conv:
+                    break
+            if conv and done < n:
+                for dst, src in zip(self._xd, snap[0]):
+                    dst.copy_(src)
+                for pk, src in snap[1].items():
+                    self._hd[pk].copy_(src)
+                for dst, src in zip(self._xd_old, snap[2]):
+                    dst.copy_(src)
+                for _ in range(done):
+                    graph.replay()
+            it += done
             if conv:
                 break
-            if it % interval_update_mu == 0:
-                for n, (i, j) in enumerate(self._pairs):
-                    primal, dual = float(nr[n, 0]), float(nr[n, 3])
+            if (it - 1) % interval_update_mu == 0:
+                nr = rows[done - 1].reshape(npair, 6)
+                for n_, (i, j) in enumerate(self._pairs):
+                    primal, dual = float(nr[n_, 0]), float(nr[n_, 3])
                     if primal > 10.0 * dual:
                         self._mu[i, j] *= 2.0
                     if dual > 10.0 * primal:
@@ -580,3 +621,7 @@ class SimpleOptimizer(object):
         self._xd_old = None
         self._snapshot = self._host_state()
         return True
+
+
+#: iterations the generic executor runs ahead between two host synchronisations (see _solve_generic)
+SimpleOptimizer.GENERIC_CHUNK = 64

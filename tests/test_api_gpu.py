@@ -235,6 +235,33 @@ def test_generic_three_term_dense_couplings(api):
     assert abs(opt(opt.x) - g["objective"]) / g["objective"] < 1e-9
 
 
+def test_generic_run_ahead_early_stop_and_resume(api):
+    """The generic executor runs chunks of iterations ahead of the host (one synchronisation per chunk) and rolls
+    back when the stopping test fired inside a chunk: same iteration count, history, penalties and state as the
+    iteration-by-iteration path (a callback forces that one) -- for an early stop in the middle of a chunk, for a
+    chunk cut by niter, and for a second solve() that continues."""
+    M, F, O = api
+    g = golden("generic3")
+    conds = [(0, 1, g["E1"], M.identity(5)), (0, 2, g["P"], M.DiagonalMatrix(np.linspace(1.0, 2.0, 4)))]
+    mk = lambda: O.SimpleOptimizer(O.Model([F.LeastSquares(1.3, g["A"], g["y"]), F.L1Regularizer(0.2, 5), F.NonNegativePenalty(4)],
+                                           conds), mu=0.7)
+    for niter, rtol in ((400, 1e-6), (57, 1e-12), (400, 1e-3)):
+        a, b = mk(), mk()
+        a.solve(niter, interval_update_mu=20, rtol=rtol)
+        b.solve(niter, interval_update_mu=20, rtol=rtol, callback=lambda: None)
+        assert len(a._primal_residual) == len(b._primal_residual), (niter, rtol)
+        if rtol > 1e-12:
+            assert len(a._primal_residual) < niter                   # really an early stop
+        assert rel(a._primal_residual, b._primal_residual) < 1e-12 and rel(a._dual_residual, b._dual_residual) < 1e-12
+        for k in range(3):
+            assert rel(a.x[k], b.x[k]) < 1e-13
+        assert a._mu[1, 0] == b._mu[1, 0] and a._mu[2, 0] == b._mu[2, 0]
+        a.solve(30, interval_update_mu=20, rtol=1e-12)
+        b.solve(30, interval_update_mu=20, rtol=1e-12, callback=lambda: None)
+        for k in range(3):
+            assert rel(a.x[k], b.x[k]) < 1e-13
+
+
 def test_spm_notebook_flow_dropin(api):
     """spm.ipynb:243-259 through the drop-in API: single problem (fused pattern B engine)."""
     M, F, O = api

@@ -4,6 +4,9 @@ import numpy as np, torch
 from admmsolver.matrix import identity, DiagonalMatrix, PartialDiagonalMatrix
 from admmsolver.objectivefunc import LeastSquares, L1Regularizer, NonNegativePenalty
 from admmsolver.optimizer import Model, SimpleOptimizer
+import os
+if os.environ.get('GENERIC_CHUNK'):
+    SimpleOptimizer.GENERIC_CHUNK = int(os.environ['GENERIC_CHUNK'])
 rs = np.random.RandomState(5)
 n0, n1, n2 = 600, 500, 400
 Ag = rs.randn(800, n0); yg = rs.randn(800)

@@ -77,6 +77,7 @@ _SIGS = {
     "admm_prox_nonneg": ([_LL, _P, _I, _P, _P, _I, _P], _I),
     "admm_prox_psd": ([_I, _LL, _LL, _LL, _LL, _P, _I, _P, _P, _I, _P], _I),
     "admm_sumsq": ([_LL, _P, _P, _P, _P, _P], _I),
+    "admm_pair_norms": ([_LL, _P, _P, _LL, _P, _P, _P, _P, _P], _I),
     "admm_inverse": ([_I, _I, _P, _I, _P, _I, _P, _P, _P], _I),
     "admm_spd_inverse_batched": ([_I, _I, _P, _LL, _I, _P, _P, _P], _I),
     "admm_spm_prepare_P": ([C.POINTER(SpmDims), _P, _I, _P, _P], _I),
@@ -110,7 +111,7 @@ if lib.admm_abi_version() != ABI_VERSION:
 
 #: number of kernel launches issued through this binding (bench.py reports it as gpu_launches)
 launch_count = 0
-_LAUNCHES_PER_CALL = {"admm_sumsq": 2, "admm_spm_reduce": 2, "admm_spm_reduce_decide": 2, "admm_bp_factor": 3, "admm_bp_setup": 2}
+_LAUNCHES_PER_CALL = {"admm_sumsq": 2, "admm_pair_norms": 2, "admm_spm_reduce": 2, "admm_spm_reduce_decide": 2, "admm_bp_factor": 3, "admm_bp_setup": 2}
 
 
 def check(rc: int) -> None:

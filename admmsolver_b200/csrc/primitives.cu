@@ -475,6 +475,48 @@ __global__ void __launch_bounds__(256) sumsq_stage2(int nparts, const double* __
   if (threadIdx.x == 0) out[0] = v[0];
 }
 
+// the six squared norms of a coupled pair in one pass: |p1-p2|, |p1|, |p2| over np doubles, |d1-d2|, |d1|, |d2| over nd
+__global__ void __launch_bounds__(256) pair_norms_stage1(long long np, const double* __restrict__ p1,
+                                                         const double* __restrict__ p2, long long nd,
+                                                         const double* __restrict__ d1, const double* __restrict__ d2,
+                                                         double* __restrict__ part) {
+  __shared__ double scratch[6 * 32];
+  double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  {
+    const long long per = (np + gridDim.x - 1) / gridDim.x;
+    const long long b0 = per * blockIdx.x, b1 = min(np, b0 + per);
+    for (long long i = b0 + threadIdx.x; i < b1; i += blockDim.x) {
+      const double a = p1[i], b = p2[i];
+      v[0] += (a - b) * (a - b);
+      v[1] += a * a;
+      v[2] += b * b;
+    }
+  }
+  {
+    const long long per = (nd + gridDim.x - 1) / gridDim.x;
+    const long long b0 = per * blockIdx.x, b1 = min(nd, b0 + per);
+    for (long long i = b0 + threadIdx.x; i < b1; i += blockDim.x) {
+      const double a = d1[i], b = d2[i];
+      v[3] += (a - b) * (a - b);
+      v[4] += a * a;
+      v[5] += b * b;
+    }
+  }
+  block_sum<6>(v, scratch);
+  if (threadIdx.x < 6) part[blockIdx.x * 6 + threadIdx.x] = v[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256) pair_norms_stage2(int nparts, const double* __restrict__ part, double* __restrict__ out) {
+  __shared__ double scratch[6 * 32];
+  double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) v[q] += part[i * 6 + q];
+  }
+  block_sum<6>(v, scratch);
+  if (threadIdx.x < 6) out[threadIdx.x] = v[threadIdx.x];
+}
+
 // ---------------------------------------------------------------------------------------------
 // general inverse: Gauss-Jordan with partial pivoting on the augmented matrix [A | I], one CTA
 // ---------------------------------------------------------------------------------------------
@@ -1000,6 +1042,17 @@ int admm_sumsq(long long n, const double* x, const double* y, double* out, doubl
   sumsq_stage1<<<parts, 256, 0, s>>>(n, x, y, scratch);
   sumsq_stage2<<<1, 256, 0, s>>>(parts, scratch, out);
   return check_launch("admm_sumsq");
+}
+
+int admm_pair_norms(long long np, const double* p1, const double* p2, long long nd, const double* d1, const double* d2,
+                    double* out, double* scratch, admm_stream_t stream) {
+  ADMM_REQUIRE(np >= 0 && nd >= 0 && out != nullptr && scratch != nullptr, ADMM_EINVAL, "admm_pair_norms: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long n = std::max(np, nd);
+  const int parts = (int)std::max<long long>(1, std::min<long long>((n + 4095) / 4096, 1024));
+  pair_norms_stage1<<<parts, 256, 0, s>>>(np, p1, p2, nd, d1, d2, scratch);
+  pair_norms_stage2<<<1, 256, 0, s>>>(parts, scratch, out);
+  return check_launch("admm_pair_norms");
 }
 
 int admm_inverse(int is_complex, int n, const void* A, int lda, void* Ainv, int ldi, void* work, int* info,

@@ -455,12 +455,7 @@ class SimpleOptimizer(object):
         for n, (i, j) in enumerate(self._pairs):
             p1, p2 = self._pair_vectors(i, j)
             d1, d2 = self._dual_vectors(i, j, p1)
-            D.sumsq_into(buf, 6 * n + 0, p1, p2)
-            D.sumsq_into(buf, 6 * n + 1, p1)
-            D.sumsq_into(buf, 6 * n + 2, p2)
-            D.sumsq_into(buf, 6 * n + 3, d1, d2)
-            D.sumsq_into(buf, 6 * n + 4, d1)
-            D.sumsq_into(buf, 6 * n + 5, d2)
+            D.pair_norms_into(buf, 6 * n, p1, p2, d1, d2)
 
     def _graphable(self) -> bool:
         """Every term runs on the device (a user-defined NumPy term cannot be captured in a CUDA graph)."""

@@ -93,6 +93,13 @@ int admm_prox_psd(int n, long long nbatch, long long stride_batch, long long str
 int admm_sumsq(long long n, const double* x, const double* y, double* out, double* scratch,
                admm_stream_t stream);
 
+/* The six squared norms residual(), check_convergence() and update_mu() need for ONE coupled pair
+ * (optimizer.py:251-299) in a single pass: out[0..2] = |p1-p2|^2, |p1|^2, |p2|^2 over np doubles,
+ * out[3..5] = |d1-d2|^2, |d1|^2, |d2|^2 over nd doubles; deterministic two-stage reduction; `scratch`
+ * needs 6 * 1024 doubles. */
+int admm_pair_norms(long long np, const double* p1, const double* p2, long long nd, const double* d1,
+                    const double* d2, double* out, double* scratch, admm_stream_t stream);
+
 /* General inverse by Gauss-Jordan with partial pivoting (one CTA).  `work` is n x 2n elements.
  * info[0] != 0 if a zero pivot was met.  Replaces `np.linalg.inv` (matrix.py:77-78). */
 int admm_inverse(int is_complex, int n, const void* A, int lda, void* Ainv, int ldi, void* work,

@@ -347,13 +347,16 @@ class SimpleOptimizer(object):
         p2 = E[j, i] @ self._xd[i]
         return p1, p2
 
-    def _dual_vectors(self, i: int, j: int, p1: torch.Tensor):
+    def _dual_vectors(self, i: int, j: int, p1: torch.Tensor, scaled: bool = True):
         """mu * E[j,i] @ (E[i,j] @ x_j) for the current and the previous x_j (optimizer.py:241-242:
-        E[j,i], not its adjoint -- reproduced as written)."""
+        E[j,i], not its adjoint -- reproduced as written).  ``scaled=False`` leaves the
+        factor mu to the caller (norms are homogeneous: two launches less per pair and iteration)."""
         E = self._model.E
-        mu = float(self._mu[i, j])
-        d1 = D.axpby(mu, E[j, i] @ p1)
-        d2 = D.axpby(mu, E[j, i] @ (E[i, j] @ self._xd_old[j]))
+        d1 = E[j, i] @ p1
+        d2 = E[j, i] @ (E[i, j] @ self._xd_old[j])
+        if scaled:
+            mu = float(self._mu[i, j])
+            d1, d2 = D.axpby(mu, d1), D.axpby(mu, d2)
         return d1, d2
 
     # ------------------------------------------------------------------ public step-wise API
@@ -381,9 +384,11 @@ class SimpleOptimizer(object):
                 if isinstance(xk, np.ndarray):        # user-defined term working on NumPy
                     xk = D.as_dev(xk)
             self._xd[k].copy_(xk)                     # (casts real results to the complex128 state)
+        self._pv = {}            # E1 x_i, E2 x_j of this sweep: the norms that follow need the same vectors
         if update_h:
             for (i, j) in self._pairs:
                 p1, p2 = self._pair_vectors(i, j)
+                self._pv[(i, j)] = (p1, p2)
                 self._hd[(i, j)].copy_(D.axpby(1.0, self._hd[(i, j)], float(self._mu[i, j]), D.axpby(1.0, p2, -1.0, p1)))
 
     def _need_old(self) -> None:
@@ -451,11 +456,14 @@ class SimpleOptimizer(object):
     def _launch_norms(self, buf: torch.Tensor) -> None:
         """The six norms per coupled pair that residual(), check_convergence() and update_mu() need
         (optimizer.py:232-299), each pair/dual vector formed ONCE, squared norms into ``buf`` (no host
-        synchronisation).  Row per pair: |p1-p2|, |p1|, |p2|, |d1-d2|, |d1|, |d2|."""
+        synchronisation).  Row per pair: |p1-p2|, |p1|, |p2|, |d1-d2|, |d1|, |d2| -- the last three WITHOUT the
+        factor mu of the dual vectors."""
+        pv = getattr(self, "_pv", None) or {}
         for n, (i, j) in enumerate(self._pairs):
-            p1, p2 = self._pair_vectors(i, j)
-            d1, d2 = self._dual_vectors(i, j, p1)
+            p1, p2 = pv[(i, j)] if (i, j) in pv else self._pair_vectors(i, j)
+            d1, d2 = self._dual_vectors(i, j, p1, scaled=False)       # _solve_generic multiplies the norms by mu
             D.pair_norms_into(buf, 6 * n, p1, p2, d1, d2)
+        self._pv = {}
 
     def _graphable(self) -> bool:
         """Every term runs on the device (a user-defined NumPy term cannot be captured in a CUDA graph)."""
@@ -467,9 +475,20 @@ class SimpleOptimizer(object):
         test and update_mu() of an iteration share one set of norms (one host synchronisation per iteration
         instead of one per norm; the reference recomputes every E @ x for each of the three)."""
         self._upload()
-        nbuf = torch.zeros(6 * max(1, len(self._pairs)), dtype=D.F64, device=self._xd[0].device)
+        # The captured graph of the current penalties survives across solve() calls as long as the device state keeps
+        # its addresses (capture + instantiation costs 10 ms and sporadically 100s of ms -- more than a short solve).
+        dev = self._xd[0].device
+        nb6 = 6 * max(1, len(self._pairs))
+        if getattr(self, "_gnbuf", None) is None or self._gnbuf.numel() != nb6 or self._gnbuf.device != dev:
+            self._gnbuf = torch.zeros(nb6, dtype=D.F64, device=dev)
+            self._ggraphs, self._gwarm, self._gsig = {}, set(), None
+        nbuf = self._gnbuf
+        sig = (tuple(t.data_ptr() for t in self._xd) + tuple(self._hd[p].data_ptr() for p in self._pairs)
+               + tuple(t.data_ptr() for t in (self._xd_old or [])))
+        if sig != self._gsig:
+            self._ggraphs, self._gwarm, self._gsig = {}, set(), sig
         graphable = callback is None and self._graphable()
-        graph = graph_key = warm_key = None
+        graph = graph_key = None
         npair = len(self._pairs)
         hist = None          # device copy of the norms of every iteration of a chunk
         it = 0
@@ -492,7 +511,13 @@ class SimpleOptimizer(object):
             # inverse caches outside any capture), then captured once and replayed as ONE graph launch
             key = tuple(float(self._mu[p]) for p in self._pairs) + (bool(update_h),)
             snap = None
-            if graph is not None and graph_key == key:
+            if graph_key != key:
+                # one graph at a time: a captured graph references the per-penalty caches of the terms (inverse, mu_k),
+                # which may be released once the penalties move on -- a change of key drops it and warms up again
+                if key not in self._ggraphs:
+                    self._ggraphs, self._gwarm = {}, set()
+                graph, graph_key = self._ggraphs.get(key), key
+            if graph is not None:
                 # Run ahead: all iterations up to and including the next update_mu iteration are replayed back to
                 # back, their norms collected on the device and read with ONE synchronisation.  Should the stopping
                 # test have fired in the middle of the chunk (it can only happen once per solve), the state is rolled
@@ -512,24 +537,30 @@ class SimpleOptimizer(object):
                     graph.replay()
                     rows = np.sqrt(nbuf.cpu().numpy())[None]
             else:
-                graph = None
                 n = 1
                 self._sweep_dev(update_h)
                 self._launch_norms(nbuf)
-                if graphable and warm_key == key:
+                if graphable and key in self._gwarm:
                     before = D._lib.launch_count
                     try:
                         g = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(g, capture_error_mode="thread_local"):
                             self._sweep_dev(update_h)
                             self._launch_norms(nbuf)
-                        graph, graph_key = g, key
-                    except Exception:                 # something in the model synchronises: stay eager
+                        graph = g
+                        self._ggraphs = {key: g}
+                    except Exception as exc:          # something in the model synchronises: stay eager
                         graphable = False
                         torch.cuda.synchronize()
+                        import warnings
+                        warnings.warn("generic executor: CUDA-graph capture failed (%s); running eagerly" % (exc,))
                     D._lib.launch_count = before
-                warm_key = key
+                self._gwarm.add(key)
                 rows = np.sqrt(nbuf.cpu().numpy())[None]
+            rows = rows.reshape(n, npair, 6).copy()
+            for n_, pk in enumerate(self._pairs):                       # the dual norms were taken without the factor mu
+                rows[:, n_, 3:6] *= float(self._mu[pk])
+            rows = rows.reshape(n, npair * 6)
             done = 0
             conv = False
             for k in range(n):

@@ -348,3 +348,38 @@ def test_smooth_regularizer_coeff(pkg):
     U = pkg[3]
     omega = np.linspace(0.0, np.sqrt(3.0), 10000) ** 2
     assert abs(np.linalg.norm(U.smooth_regularizer_coeff(omega) @ omega ** 2) ** 2 - 3.0 * 4.0) < 1e-2
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_error_behaviour_matches_reference(pkg):
+    """The exceptions a caller of the reference can rely on: RuntimeError for duplicate conditions
+    (optimizer.py:111-112), for inverses / diagonals of rectangular matrices (matrix.py:157,167,225); ValueError for an
+    invalid shape (matrix.py:142); AssertionError for a missing mu (objectivefunc.py:262-263), shape mismatches between
+    conditions and terms (optimizer.py:107-110), non-float coefficients (matrix.py:134-135) and wrong argument types."""
+    M, F, O, U = pkg
+    lst, l1 = F.LeastSquares(1.0, np.ones((3, 4)), np.ones(3)), F.L1Regularizer(0.1, 4)
+    with pytest.raises(RuntimeError):
+        O.Model([lst, l1], [(1, 0, M.identity(4), M.identity(4)), (1, 0, M.identity(4), M.identity(4))])
+    with pytest.raises(AssertionError):
+        O.Model([lst, l1], [(1, 0, M.identity(5), M.identity(5))])
+    with pytest.raises(RuntimeError):
+        M.ScaledIdentityMatrix((2, 3), 1.0).inv()
+    with pytest.raises(RuntimeError):
+        M.ScaledIdentityMatrix((2, 3), 1.0).diagonals
+    with pytest.raises(RuntimeError):
+        M.DiagonalMatrix(np.ones(2), shape=(3, 2)).inv()
+    with pytest.raises(ValueError):
+        M.ScaledIdentityMatrix([2, 2], 1.0)
+    with pytest.raises(AssertionError):
+        M.ScaledIdentityMatrix(2, 1)
+    with pytest.raises(AssertionError):            # the ValueError of objectivefunc.py:270 is unreachable: :263 asserts first
+        F.NonNegativePenalty(3).solve(np.zeros(3), None)
+    with pytest.raises(AssertionError):
+        F.L1Regularizer(0.1, 3).solve(np.zeros(3), M.DenseMatrix(np.eye(3)))
+    with pytest.raises(AssertionError):
+        F.LeastSquares(1.0, np.ones((3, 4)), np.ones(5))
+    # a condition is a 4-tuple or an EqualityCondition with .size (optimizer.py:12-38)
+    ec = O.EqualityCondition(1, 0, M.identity(4), M.identity(4))
+    assert (ec.i1, ec.i2, ec.size) == (1, 0, 4)
+    m = O.Problem([lst, l1], [ec])
+    assert m.num_func == 2 and m.E[1, 0] is not None and m.E[0, 1] is not None

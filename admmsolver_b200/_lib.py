@@ -95,7 +95,7 @@ _SIGS = {
     "admm_spm_reduce_decide": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
     "admm_spm_decide": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
     "admm_spm_solo_supported": ([C.POINTER(SpmDims)], _I),
-    "admm_spm_solo": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _P, _I, _I, _P], _I),
+    "admm_spm_solo": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _P, _P, _I, _I, _P], _I),
     "admm_bp_setup": ([C.POINTER(BpBuffers), _P, _P, _P, _P], _I),
     "admm_bp_tile_A": ([C.POINTER(BpBuffers), _P, _P], _I),
     "admm_bp_factor": ([C.POINTER(BpBuffers), _P, _P], _I),

@@ -510,7 +510,7 @@ class SharedSpM:
         launched = 0
         it = 0
         if use_solo:
-            call("admm_spm_solo", C.byref(self.dims), C.byref(self.bufs), ptr(self.G0), int(niter),
+            call("admm_spm_solo", C.byref(self.dims), C.byref(self.bufs), ptr(self.G0), ptr(self.PtP), int(niter),
                  int(interval_update_mu), stream())
             self._v_valid, self._fresh = True, False
             fl = torch.cat([self.flags, self.iters[:nb]]).cpu()        # one read-back: flags and iteration counts

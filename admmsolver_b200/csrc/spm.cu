@@ -930,7 +930,7 @@ __host__ __device__ inline SoloLayout solo_layout(int LP, int Nwp, int cs, int n
   auto take = [&](int n) { const int r = at; at += (n + 1) & ~1; return r; };
   o.P = take(regp ? 0 : LP * o.R);
   o.Gi = take(LP * LP);
-  o.PtP = take(LP * LP);
+  o.PtP = take(regp ? LP * LP : 0);     // shared-memory variant: P^T P stays in global memory (budget)
   o.M2 = take(LP * LP);
   o.pw = take(LP);
   o.rhs = take(npl * LP);
@@ -1087,9 +1087,10 @@ __device__ __forceinline__ void solo_treduce_pairs(double (&v)[W], int lane) {
   for (; o >= 2; o /= 2) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
 }
 
-template <int CS, int LP, bool REGP>
+template <int CS, int LP, bool REGP, bool BW>   // BW: batch-wide criterion over several co-resident clusters
 __global__ void __launch_bounds__(SOLO_THREADS, 1)
-    spm_solo_kernel(admm_spm_dims d, admm_spm_buffers b, const double* __restrict__ G0, int budget, int interval) {
+    spm_solo_kernel(admm_spm_dims d, admm_spm_buffers b, const double* __restrict__ G0, const double* __restrict__ PtP,
+                    int budget, int interval) {
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = CS > 1 ? (int)cluster.block_rank() : 0;
   const int prob = blockIdx.x / CS;
@@ -1105,7 +1106,10 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
   const int row0 = crank * R, nrow = max(0, min(R, Nwp - row0));
   double* Psm = sm + lay.P;        // [l][i]: P[row0 + i][l]
   double* Gi = sm + lay.Gi;        // [LP][LP], symmetric
-  double* PtPs = sm + lay.PtP;     // [LP][LP], symmetric
+  // P^T P ([LP][LP], symmetric, canonical): only the set-up, the re-inversion after a mu change and the first y0 read it
+  // (P^T P x0 comes from M2T in the loop).  Register variant: a shared-memory copy; shared-memory variant (the budget is
+  // tight there): straight from global memory.
+  const double* PtPs = REGP ? (sm + lay.PtP) : PtP;
   double* M2T = sm + lay.M2;       // [LP][LP]: (P^T P G^-1) transposed
   double* pw = sm + lay.pw;        // [LP]: P^T P w
   double* rhs = sm + lay.rhs;      // [plane][LP]
@@ -1166,7 +1170,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
     const int i = idx / LP, j = idx - i * LP;
     const size_t o = bfrag_of(NT, i, j);
     Gi[idx] = b.Ginv_cache[(size_t)slot * LP * LP + o];
-    PtPs[idx] = b.PtPf[o];
+    if (REGP) sm[lay.PtP + idx] = PtP[idx];
   }
   for (int i = tid; i < LP; i += SOLO_THREADS) {
     wv[i] = b.w_cache[(size_t)slot * LP + i];
@@ -1531,7 +1535,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
     }
     s[7] += nBt[0];
     s[8] += nBt[1];
-    if (d.batch_wide && d.nb > 1) {
+    if (BW) {
       // batch-wide criterion over several clusters (a packed PartialDiagonalMatrix batch of a few problems): all-reduce
       // of the ten squared norms through global memory.  Every cluster publishes its sums and arrives on a counter;
       // all CTAs wait for the nb arrivals of this iteration and add the nb entries in problem order -- identical
@@ -1733,11 +1737,12 @@ static size_t solo_smem_bytes(const admm_spm_dims* d, int cs) {
   return (size_t)solo_layout(d->Lp, d->nrt * 8, cs, d->nplanes, solo_regp(d, cs)).total * sizeof(double);
 }
 
-template <int CS, int LP, bool REGP>
-static int launch_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const double* G0, int niter, int interval,
+template <int CS, int LP, bool REGP, bool BW>
+static int launch_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const double* G0, const double* PtP, int niter,
+                       int interval,
                        cudaStream_t st, int* max_clusters = nullptr) {   // max_clusters != NULL: occupancy query only
   const size_t smem = solo_smem_bytes(d, CS);
-  auto kern = spm_solo_kernel<CS, LP, REGP>;
+  auto kern = spm_solo_kernel<CS, LP, REGP, BW>;
   static size_t configured = 0;     // per instantiation
   if (smem > configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1770,7 +1775,7 @@ static int launch_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const 
     *max_clusters = cached_n;
     return ADMM_OK;
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *d, *b, G0, niter, interval);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *d, *b, G0, PtP, niter, interval);
   if (e != cudaSuccess) {
     set_error("admm_spm_solo: %s", cudaGetErrorString(e));
     return ADMM_ECUDA;
@@ -1904,40 +1909,44 @@ int admm_spm_reduce_decide(const admm_spm_dims* d, const admm_spm_buffers* b, in
   return check_launch("admm_spm_reduce_decide");
 }
 
-static int dispatch_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const double* G0, int niter, int interval,
+static int dispatch_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const double* G0, const double* PtP, int niter,
+                         int interval,
                          cudaStream_t st, int* max_clusters) {
   // sampling points per CTA <= 256: P, the state and the cached inverse stay in registers
   const bool regp = solo_regp(d, 8);
+  const bool bw = d->batch_wide && d->nb > 1;
+#define SOLO_CASE(LPV, RG)                                                                                        \
+  (bw ? launch_solo<8, LPV, RG, true>(d, b, G0, PtP, niter, interval, st, max_clusters)                           \
+      : launch_solo<8, LPV, RG, false>(d, b, G0, PtP, niter, interval, st, max_clusters))
   switch (d->Lp) {
-    case 16: return regp ? launch_solo<8, 16, true>(d, b, G0, niter, interval, st, max_clusters)
-                         : launch_solo<8, 16, false>(d, b, G0, niter, interval, st, max_clusters);
-    case 40: return regp ? launch_solo<8, 40, true>(d, b, G0, niter, interval, st, max_clusters)
-                         : launch_solo<8, 40, false>(d, b, G0, niter, interval, st, max_clusters);
-    default: return launch_solo<8, 64, false>(d, b, G0, niter, interval, st, max_clusters);   // 64 doubles per row: shared memory
+    case 16: return regp ? SOLO_CASE(16, true) : SOLO_CASE(16, false);
+    case 40: return regp ? SOLO_CASE(40, true) : SOLO_CASE(40, false);
+    default: return SOLO_CASE(64, false);             // 64 doubles per row: shared memory
   }
+#undef SOLO_CASE
 }
 
 int admm_spm_solo_supported(const admm_spm_dims* d) {
   if (d == nullptr || d->L < 1 || (d->Lp != 16 && d->Lp != 40 && d->Lp != 64) || d->nb < 1) return 0;
-  if (solo_smem_bytes(d, 8) > 200 * 1024) return 0;
+  if (solo_smem_bytes(d, 8) > 216 * 1024) return 0;
   if (d->batch_wide && d->nb > 1) {
     // the batch-wide criterion synchronises the clusters every iteration: all of them have to be co-resident
     int n = 0;
-    if (dispatch_solo(d, nullptr, nullptr, 0, 0, nullptr, &n) != ADMM_OK || d->nb > n) return 0;
+    if (dispatch_solo(d, nullptr, nullptr, nullptr, 0, 0, nullptr, &n) != ADMM_OK || d->nb > n) return 0;
   }
   return 8;
 }
 
-int admm_spm_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const double* G0, int niter, int interval_update_mu,
-                  admm_stream_t stream) {
+int admm_spm_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const double* G0, const double* PtP, int niter,
+                  int interval_update_mu, admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_solo")) return rc;
   ADMM_REQUIRE(admm_spm_solo_supported(d) != 0, ADMM_EUNSUPPORTED,
                "admm_spm_solo: L=%d, Nw=%d do not fit the shared memory of an 8-CTA cluster, or (batch-wide criterion) the %d "
                "clusters cannot be co-resident", d->L, d->Nw, d->nb);
-  ADMM_REQUIRE(G0 != nullptr && niter >= 0 && interval_update_mu >= 0, ADMM_EINVAL, "admm_spm_solo: bad arguments");
+  ADMM_REQUIRE(G0 != nullptr && PtP != nullptr && niter >= 0 && interval_update_mu >= 0, ADMM_EINVAL, "admm_spm_solo: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (d->batch_wide && d->nb > 1) cudaMemsetAsync(b->flags + 3, 0, sizeof(int), st);      // arrival counter of the all-reduce
-  return dispatch_solo(d, b, G0, niter, interval_update_mu, st, nullptr);
+  return dispatch_solo(d, b, G0, PtP, niter, interval_update_mu, st, nullptr);
 }
 
 }  // extern "C"

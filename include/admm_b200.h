@@ -282,7 +282,7 @@ int admm_spm_decide(const admm_spm_dims* d, const admm_spm_buffers* b, int do_up
  * memory behind one cluster barrier and take the residual / convergence / mu decisions -- including
  * the re-inversion of alpha A^H A + mu after update_mu -- redundantly and identically.  Runs up to
  * `niter` iterations per problem (stops at convergence), mu update every `interval_update_mu`
- * iterations (0: never).  G0 = alpha A^H A (Lp x Lp, row-major, as for admm_spm_factor).  Reads and
+ * iterations (0: never).  G0 = alpha A^H A and PtP = P^T P (Lp x Lp, row-major, zero padded, as for admm_spm_factor).  Reads and
  * writes the same buffers as the batch kernels (state in, state out; V, y0, mu20_used consistent),
  * sets flags[0] when a mu changed (the caller re-maps its factor cache), flags[1] += converged
  * problems, flags[2] = first non-positive pivot.  Per-problem criterion: any nb (clusters run in waves).  Batch-wide
@@ -291,8 +291,8 @@ int admm_spm_decide(const admm_spm_dims* d, const admm_spm_buffers* b, int do_up
  * admm_spm_solo_supported: cluster size used (8) if L, Nw fit the cluster's shared memory (and, batch-wide, the nb
  * clusters fit the GPU at once), else 0. */
 int admm_spm_solo_supported(const admm_spm_dims* d);
-int admm_spm_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const double* G0, int niter,
-                  int interval_update_mu, admm_stream_t stream);
+int admm_spm_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const double* G0, const double* PtP,
+                  int niter, int interval_update_mu, admm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Pattern A engine: basis pursuit / LASSO  [LeastSquares, L1Regularizer], condition (1,0,I,I);  */

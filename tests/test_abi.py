@@ -61,3 +61,24 @@ def test_no_cpu_fallback_and_no_oracle_import(build_lib):
         from admmsolver_b200 import _lib, batch
         with pytest.raises(_lib.AdmmError):
             batch.BatchedBasisPursuit(np.eye(2), np.ones(2))
+
+
+def test_solo_support_query_without_gpu(build_lib):
+    """admm_spm_solo_supported is pure host logic for the per-problem criterion (shared-memory budget of the cluster)
+    and degrades to 'unsupported' -- not to a crash -- when the co-residency query of the batch-wide criterion has no device."""
+    import ctypes as C
+    import torch
+    from admmsolver_b200 import _lib
+
+    def dims(L, Lp, Nw, nb, batch_wide):
+        nrt = ((Nw + 7) // 8 + 3) // 4 * 4
+        return _lib.SpmDims(L, Lp, Nw, nrt, nb, (nb + 7) // 8, 2, 1, 1, 0, int(batch_wide))
+
+    q = lambda d: int(_lib.lib.admm_spm_solo_supported(C.byref(d)))
+    assert q(dims(39, 40, 2000, 1, False)) == 8          # cfg2: registers + 49 KB of shared memory per CTA
+    assert q(dims(39, 40, 2000, 100, False)) == 8        # per-problem: any batch size (clusters run in waves)
+    assert q(dims(52, 64, 2000, 1, True)) == 8           # L > 40: shared-memory variant, one problem
+    assert q(dims(52, 64, 40000, 1, False)) == 0         # 5000 sampling points per CTA x 64 columns do not fit
+    assert q(dims(39, 48, 2000, 1, False)) == 0          # padded L must be 16, 40 or 64
+    if not torch.cuda.is_available():
+        assert q(dims(39, 40, 2000, 6, True)) == 0       # batch-wide over several clusters needs the occupancy query

@@ -287,7 +287,7 @@ int admm_spm_decide(const admm_spm_dims* d, const admm_spm_buffers* b, int do_up
  * sets flags[0] when a mu changed (the caller re-maps its factor cache), flags[1] += converged
  * problems, flags[2] = first non-positive pivot.  Per-problem criterion: any nb (clusters run in waves).  Batch-wide
  * criterion with nb > 1 (a packed batch of a few problems): the clusters all-reduce their ten squared norms through
- * gpart / flags[3] every iteration, so all nb clusters have to be co-resident (nb <= ~16 on a B200).
+ * gpart / flags[3] every iteration, so all nb clusters have to be co-resident (nb <= ~14 on a B200).
  * admm_spm_solo_supported: cluster size used (8) if L, Nw fit the cluster's shared memory (and, batch-wide, the nb
  * clusters fit the GPU at once), else 0. */
 int admm_spm_solo_supported(const admm_spm_dims* d);

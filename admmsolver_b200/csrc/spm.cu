@@ -918,7 +918,7 @@ constexpr int SOLO_LWARPS = 4;
 constexpr int SOLO_RTHREADS = SOLO_THREADS - 32 * SOLO_LWARPS;
 
 struct SoloLayout {      // offsets in doubles into the dynamic shared memory
-  int R, P, Gi, PtP, M2, pw, rhs, xn, w, Cv, us, ss, xch, vp, nA, nB, nBt, rowk, colk, total;
+  int R, P, Gi, PtP, M2, pw, ybuf, rhs, xn, w, Cv, us, ss, xch, vp, nA, nB, nBt, rowk, colk, total;
 };
 // LP = padded L (d.Lp: 16, 40 or 64): every L-dimension is zero padded to LP so that the inner loops
 // have compile-time trip counts; R = sampling points per CTA, padded to a multiple of 32
@@ -933,6 +933,7 @@ __host__ __device__ inline SoloLayout solo_layout(int LP, int Nwp, int cs, int n
   o.PtP = take(regp ? LP * LP : 0);     // shared-memory variant: P^T P stays in global memory (budget)
   o.M2 = take(LP * LP);
   o.pw = take(LP);
+  o.ybuf = take(npl * LP);
   o.rhs = take(npl * LP);
   o.xn = take(npl * LP);
   o.w = take(LP);
@@ -1112,6 +1113,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
   const double* PtPs = REGP ? (sm + lay.PtP) : PtP;
   double* M2T = sm + lay.M2;       // [LP][LP]: (P^T P G^-1) transposed
   double* pw = sm + lay.pw;        // [LP]: P^T P w
+  double* ybuf = sm + lay.ybuf;    // [plane][LP]: (P^T P G^-1) rhs, computed by the sampling-point warps during the x-update
   double* rhs = sm + lay.rhs;      // [plane][LP]
   double* xn = sm + lay.xn;        // [plane][LP]: the new x0
   double* wv = sm + lay.w;
@@ -1379,7 +1381,14 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
       }
     }
     hist_pending = false;
-    double xv = 0.0, yv2 = 0.0;
+    double xv = 0.0, nu_keep = 0.0;
+    if (!lth) {
+      // the sampling-point warps idle during the x-update: they take the third dot product of every (plane, l)
+      if (rt < npl * LP) {
+        const int p3 = rt / LP, l3 = rt - p3 * LP;
+        ybuf[rt] = solo_matvec<LP>(M2T + l3, rhs + p3 * LP);
+      }
+    }
     if (lact) {
       const double* rp = rhs + pl * LP;
       double xi;
@@ -1410,7 +1419,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
       const double nu = (Dp - ((c[0] + c[1]) + (c[2] + c[3]))) * inv_sigma;
       xv = xi + wv[l] * nu;
       xn[pl * LP + l] = xv;
-      yv2 = solo_matvec<LP>(M2T + l, rp) + pw[l] * nu;      // P^T P x0
+      nu_keep = nu;
     }
     SOLO_STAMP(2)
     __syncthreads();
@@ -1420,7 +1429,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
       // ---- y = P^T P x0, norms, L1 z-update, dual ascent of pair (1,0), imaginary-plane recursion
       double n[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       if (lact) {
-        const double y = yv2;
+        const double y = ybuf[pl * LP + l] + pw[l] * nu_keep;      // P^T P x0 = (P^T P G^-1) rhs + nu P^T P w
         const double dd = xv - r_x0;
         n[3] = dd * dd;
         n[4] = r_x0 * r_x0;

@@ -21,7 +21,7 @@ if not os.path.exists(LIB_PATH):
 
 lib = C.CDLL(LIB_PATH)
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 OP_N, OP_T, OP_H = 0, 1, 2
 
 
@@ -42,7 +42,7 @@ class SpmBuffers(C.Structure):
         ("Pf", _P), ("PtPf", _P), ("Cvec", _P), ("Ginv_cache", _P), ("w_cache", _P), ("sigma_cache", _P),
         ("slot", _P), ("mu10", _P), ("mu20", _P), ("mu20_used", _P), ("done", _P), ("iters", _P),
         ("last_res", _P), ("Dre", _P),
-        ("b0", _P), ("x0", _P), ("x1", _P), ("h10", _P), ("y0", _P), ("V", _P), ("aim", _P),
+        ("b0", _P), ("x0", _P), ("x1", _P), ("h10", _P), ("y0", _P), ("x0_old", _P), ("V", _P), ("aim", _P),
         ("S", _P),
         ("normsA", _P), ("normsB", _P), ("gsum", _P), ("gpart", _P),
         ("iter_counter", _P), ("flags", _P), ("history", _P), ("hist_cap", C.c_int),
@@ -54,12 +54,21 @@ class SpmBuffers(C.Structure):
 class BpBuffers(C.Structure):
     _fields_ = [
         ("nb", C.c_int), ("M", C.c_int), ("N", C.c_int), ("woodbury", C.c_int), ("nk", C.c_int),
-        ("A", _P), ("At", _P), ("aty", _P), ("gram", _P), ("Kinv", _P), ("x0", _P), ("x1", _P), ("h", _P), ("mu", _P),
+        ("A", _P), ("At", _P), ("aty", _P), ("gram", _P), ("Kinv", _P), ("x0", _P), ("x1", _P), ("h", _P), ("x0_old", _P), ("mu", _P),
         ("need_factor", _P), ("done", _P), ("iters", _P), ("last_res", _P), ("history", _P),
         ("hist_cap", C.c_int),
         ("alpha", C.c_double), ("lam", C.c_double), ("rtol", C.c_double), ("max_mu", C.c_double),
         ("fact_incr", C.c_double), ("th_change", C.c_double), ("interval_update_mu", C.c_int),
     ]
+
+
+MAX_PEERS = 16
+MAILBOX_BYTES = 2 * MAX_PEERS * 32 * 8
+
+
+class PeerComm(C.Structure):
+    """``admm_peer_comm``: rank, world, the mailbox of every rank as mapped into this process, local control words."""
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("mbox", _P * MAX_PEERS), ("ctrl", _P)]
 
 
 _LL = C.c_longlong
@@ -94,8 +103,15 @@ _SIGS = {
     "admm_spm_reduce": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _P], _I),
     "admm_spm_reduce_decide": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
     "admm_spm_decide": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
+    "admm_peer_alloc": ([C.c_size_t, C.POINTER(_P), C.POINTER(C.c_ubyte)], _I),
+    "admm_peer_open": ([C.POINTER(C.c_ubyte), C.POINTER(_P)], _I),
+    "admm_peer_close": ([_P], _I),
+    "admm_peer_free": ([_P], _I),
+    "admm_spm_reduce_post": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), C.POINTER(PeerComm), _P], _I),
+    "admm_spm_decide_peer": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), C.POINTER(PeerComm), _I, _P], _I),
     "admm_spm_solo_supported": ([C.POINTER(SpmDims)], _I),
     "admm_spm_solo": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _P, _P, _I, _I, _P], _I),
+    "admm_bp_supported": ([_I, _I], _I),
     "admm_bp_setup": ([C.POINTER(BpBuffers), _P, _P, _P, _P], _I),
     "admm_bp_tile_A": ([C.POINTER(BpBuffers), _P, _P], _I),
     "admm_bp_factor": ([C.POINTER(BpBuffers), _P, _P], _I),
@@ -111,7 +127,7 @@ if lib.admm_abi_version() != ABI_VERSION:
 
 #: number of kernel launches issued through this binding (bench.py reports it as gpu_launches)
 launch_count = 0
-_LAUNCHES_PER_CALL = {"admm_sumsq": 2, "admm_pair_norms": 2, "admm_spm_reduce": 2, "admm_spm_reduce_decide": 2, "admm_bp_factor": 3, "admm_bp_setup": 2}
+_LAUNCHES_PER_CALL = {"admm_peer_alloc": 0, "admm_peer_open": 0, "admm_peer_close": 0, "admm_peer_free": 0, "admm_sumsq": 2, "admm_pair_norms": 2, "admm_spm_reduce": 2, "admm_spm_reduce_decide": 2, "admm_bp_factor": 3, "admm_bp_setup": 2}
 
 
 def check(rc: int) -> None:

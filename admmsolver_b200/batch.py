@@ -59,7 +59,8 @@ class SharedSpM:
 
     def __init__(self, s, P, C_, D, g, lam: float, mu: float = 0.1, alpha: float = 1.0,
                  batch_wide: bool = False, max_mu: float = 1e3, nsplit: Optional[int] = None,
-                 group=None, force_complex: Optional[bool] = None, mt: Optional[int] = None, nbal: Optional[int] = None):
+                 group=None, force_complex: Optional[bool] = None, mt: Optional[int] = None, nbal: Optional[int] = None,
+                 collective: Optional[str] = None, keep_x_old: bool = False):
         dev = _lib.require_cuda()
         s_t = _dev_tensor(s, dev, _F64)
         g_t = _dev_tensor(g, dev)
@@ -74,7 +75,8 @@ class SharedSpM:
         b0 = torch.empty_like(gv)
         sd = (-alpha * s_t).to(gv.dtype)
         call("admm_diag_mul", int(cplx), L, L, nb, ptr(sd), ptr(gv), nb, ptr(b0), nb, stream())
-        self._init_common(G0, b0, P, C_, D, lam, mu, mu, batch_wide, max_mu, nsplit, group, force_complex, mt, nbal)
+        self._init_common(G0, b0, P, C_, D, lam, mu, mu, batch_wide, max_mu, nsplit, group, force_complex, mt, nbal,
+                          collective, keep_x_old)
         self._s = s_t
         self._g = gv
         self._alpha = alpha
@@ -82,14 +84,15 @@ class SharedSpM:
     @classmethod
     def from_operators(cls, G0, b0, P, C_, D, lam: float, mu10: float, mu20: float,
                        batch_wide: bool = True, max_mu: float = 1e3, nsplit: Optional[int] = None,
-                       group=None, force_complex: Optional[bool] = None, mt: Optional[int] = None) -> "SharedSpM":
+                       group=None, force_complex: Optional[bool] = None, mt: Optional[int] = None,
+                       collective: Optional[str] = None, keep_x_old: bool = False) -> "SharedSpM":
         self = cls.__new__(cls)
         dev = _lib.require_cuda()
         b0_t = _dev_tensor(b0, dev)
         if b0_t.ndim == 1:
             b0_t = b0_t[:, None].contiguous()
         self._init_common(_dev_tensor(G0, dev, _F64), b0_t, P, C_, D, lam, mu10, mu20, batch_wide, max_mu,
-                          nsplit, group, force_complex, mt)
+                          nsplit, group, force_complex, mt, None, collective, keep_x_old)
         self._s = None
         self._g = None
         self._alpha = None
@@ -97,10 +100,23 @@ class SharedSpM:
 
     # ------------------------------------------------------------------ setup
     def _init_common(self, G0, b0, P, C_, D, lam, mu10, mu20, batch_wide, max_mu, nsplit, group, force_complex,
-                     mt=None, nbal_req=None):
+                     mt=None, nbal_req=None, collective=None, keep_x_old=False):
         dev = _lib.require_cuda()
         self.device = dev
         self.group = group
+        # Sharded batch with the batch-wide criterion: how the ten squared-norm sums are all-reduced every iteration.
+        #   "peer" (default): the reduction kernel pushes them into every rank's mailbox over NVLink, the decision
+        #                     kernel polls its own -- no library call between kernels, CUDA-graph capturable;
+        #   "nccl":           admm_spm_reduce -> torch.distributed.all_reduce -> admm_spm_decide (eager only).
+        if collective is None:
+            collective = "peer"
+        if collective not in ("peer", "nccl"):
+            raise ValueError("collective must be 'peer' or 'nccl'")
+        self.collective = collective if (group is not None and batch_wide) else None
+        self._peer = None
+        if self.collective == "peer":
+            from .peer import PeerMailbox
+            self._peer = PeerMailbox(group)
         P_t = _dev_tensor(P, dev, _F64)
         Nw, L = P_t.shape
         assert b0.shape[0] == L and G0.shape == (L, L)
@@ -177,9 +193,10 @@ class SharedSpM:
         assert Cv.numel() == L, "the fused SpM engine supports a single constraint row (C is 1 x L)"
         self.Cvec = z(Lp)
         self.Cvec[:L] = Cv
-        self.Ginv_cache = z(self.CACHE_SLOTS, Lp, Lp)
-        self.w_cache = z(self.CACHE_SLOTS, Lp)
-        self.sigma_cache = z(self.CACHE_SLOTS)
+        self._nslots = self.CACHE_SLOTS
+        self.Ginv_cache = z(self._nslots, Lp, Lp)
+        self.w_cache = z(self._nslots, Lp)
+        self.sigma_cache = z(self._nslots)
         self._slot_of = {}
         # per problem
         self.slot = torch.zeros(nprob, dtype=torch.int32, device=dev)
@@ -199,6 +216,9 @@ class SharedSpM:
         self.b0 = z(fl)
         call("admm_spm_pack_L", dref, ptr(b0.contiguous()), int(b0.is_complex()), ptr(self.b0), stream())
         self.x0f, self.x1f, self.h10f, self.y0f = z(fl), z(fl), z(fl), z(fl)
+        # x0 at the start of the last executed iteration (`_x_old[0]` of the reference, optimizer.py:324): kept
+        # only on request (the drop-in SimpleOptimizer asks for it) -- one more L-vector store per iteration
+        self.x0_oldf = z(fl) if keep_x_old else None
         self.V = z(nsplit * fl)
         self.aim = z(fl)                  # sum_k mu20_k Im(x0_k)  (imaginary-plane tiles only)
         self._him_base = None             # Im(h20) at the time of set_state (None == 0)
@@ -231,6 +251,7 @@ class SharedSpM:
                         ("aim", self.aim), ("S", self.S), ("normsA", self.normsA), ("normsB", self.normsB), ("gsum", self.gsum),
                         ("gpart", self.gpart), ("iter_counter", self.iter_counter), ("flags", self.flags)):
             setattr(b, name, t.data_ptr())
+        b.x0_old = self.x0_oldf.data_ptr() if self.x0_oldf is not None else None
         b.history = self.history.data_ptr() if self.history is not None else None
         b.hist_cap = int(self.history.shape[0]) if self.history is not None else 0
         b.lam, b.rtol, b.max_mu = self.lam, float(rtol), self.max_mu
@@ -252,15 +273,16 @@ class SharedSpM:
             uk, inverse = torch.unique(i10 * n20 + i20, return_inverse=True)
             pairs = torch.stack([u10[uk // n20], u20[uk % n20]], dim=1).cpu().numpy()
         new = [(float(a), float(b)) for a, b in pairs if (float(a), float(b)) not in self._slot_of]
-        if len(self._slot_of) + len(new) > self.CACHE_SLOTS:
-            # evict everything not currently needed
+        if len(self._slot_of) + len(new) > self._nslots:
+            # evict everything not currently needed; if the pairs in use alone exceed the cache, grow it (per-problem
+            # mode: mu10 and mu20 each walk a ladder 0.1 * 2^k up to max_mu, so a large batch can need a few hundred)
             needed = {(float(a), float(b)) for a, b in pairs}
             self._slot_of = {k: v for k, v in self._slot_of.items() if k in needed}
             new = [k for k in needed if k not in self._slot_of]
-            if len(self._slot_of) + len(new) > self.CACHE_SLOTS:
-                raise _lib.AdmmError("SpM factor cache exhausted: too many distinct (mu10, mu20) pairs")
+            if len(self._slot_of) + len(new) > self._nslots:
+                self._grow_cache(len(self._slot_of) + len(new))
         if new:
-            free = [i for i in range(self.CACHE_SLOTS) if i not in set(self._slot_of.values())]
+            free = [i for i in range(self._nslots) if i not in set(self._slot_of.values())]
             slots = free[:len(new)]
             for k, sl in zip(new, slots):
                 self._slot_of[k] = sl
@@ -280,6 +302,23 @@ class SharedSpM:
             lut = torch.tensor([self._slot_of[(float(a), float(b))] for a, b in pairs], dtype=torch.int32,
                                device=self.device)
             self.slot[:nb] = lut[inverse]
+
+    def _grow_cache(self, need: int) -> None:
+        """Reallocate the factor cache with room for ``need`` pairs (entries in use keep their rows)."""
+        n = self._nslots
+        while n < need:
+            n *= 2
+        Lp = self.dims.Lp
+        for name, shape in (("Ginv_cache", (n, Lp, Lp)), ("w_cache", (n, Lp)), ("sigma_cache", (n,))):
+            old = getattr(self, name)
+            t = torch.zeros(*shape, dtype=_F64, device=self.device)
+            t[:old.shape[0]] = old
+            setattr(self, name, t)
+        self._nslots = n
+        self._graphs.clear()            # captured launches bake the old cache addresses
+        b = self.bufs
+        b.Ginv_cache, b.w_cache, b.sigma_cache = (self.Ginv_cache.data_ptr(), self.w_cache.data_ptr(),
+                                                  self.sigma_cache.data_ptr())
 
     # ------------------------------------------------------------------ data reload (same operators)
     def reset(self, g=None, mu: Optional[float] = None) -> None:
@@ -376,6 +415,12 @@ class SharedSpM:
     def h10(self) -> np.ndarray:
         return self._unpack_L(self.h10f)
 
+    def x0_old(self) -> np.ndarray:
+        """x0 at the start of the last executed iteration (needs ``keep_x_old=True``)."""
+        if self.x0_oldf is None:
+            raise _lib.AdmmError("x0_old() needs SharedSpM(..., keep_x_old=True)")
+        return self._unpack_L(self.x0_oldf)
+
     def _unpack_state(self):
         h = torch.empty(self.Nw, self.nb, dtype=_C128, device=self.device)
         x = torch.empty(self.Nw, self.nb, dtype=_C128, device=self.device)
@@ -447,6 +492,11 @@ class SharedSpM:
         if self.batch_wide and self.group is None:
             call("admm_spm_reduce_decide", dref, bref, int(do_update_mu), st)
             return
+        if self.batch_wide and self._peer is not None:
+            cref = C.byref(self._peer.comm)
+            call("admm_spm_reduce_post", dref, bref, cref, st)
+            call("admm_spm_decide_peer", dref, bref, cref, int(do_update_mu), st)
+            return
         if self.batch_wide:
             call("admm_spm_reduce", dref, bref, st)
             torch.distributed.all_reduce(self.gsum, group=self.group)
@@ -456,6 +506,9 @@ class SharedSpM:
         """Host look at the device flags after an iteration that may have changed mu or finished
         problems.  Returns True when every problem is done."""
         fl = self.flags.cpu()
+        if int(fl[2]) == -2:
+            raise _lib.AdmmError("sharded batch-wide criterion: a peer rank never posted its residual sums "
+                                 "(watchdog of admm_spm_decide_peer); the state is undefined")
         if int(fl[1]) >= self.nb:
             return True
         if int(fl[0]) != 0:
@@ -498,7 +551,8 @@ class SharedSpM:
         self._fill_bufs(rtol)
         key = (float(rtol), self.bufs.history, self.bufs.hist_cap)     # everything a captured launch bakes in
         if use_graph is None:
-            use_graph = callback is None and self.pass_events is None and self.group is None
+            use_graph = (callback is None and self.pass_events is None
+                         and (self.group is None or not self.batch_wide or self._peer is not None))
         solo_ok = (callback is None and self.pass_events is None and self.group is None and nb <= self.SOLO_MAX_NB
                    and _lib.lib.admm_spm_solo_supported(C.byref(self.dims)) != 0)     # batch-wide: co-resident clusters only
         if use_solo is None:
@@ -584,7 +638,7 @@ class SharedSpM:
 
     def _launches_per_iteration(self) -> int:
         data = 1 if (self.dims.nsplit == 1 and self.dims.nbal == 0) else 2
-        if self.batch_wide and self.group is None:
+        if self.batch_wide and (self.group is None or self._peer is not None):
             return data + 2
         return data + (2 if self.batch_wide else 0) + 1
 
@@ -615,7 +669,7 @@ class BatchedBasisPursuit:
     stopping test (one ``SimpleOptimizer`` instance per problem in the reference)."""
 
     def __init__(self, A, y, alpha: float = 1.0, lam: float = 0.1, mu: float = 1.0, max_mu: float = 1e3,
-                 keep_history: bool = False, tiled: bool = True):
+                 keep_history: bool = False, tiled: bool = True, keep_x_old: bool = False):
         dev = _lib.require_cuda()
         self.device = dev
         A_t = _dev_tensor(A, dev, _F64)
@@ -632,6 +686,8 @@ class BatchedBasisPursuit:
         z = lambda *shape, dtype=_F64: torch.zeros(*shape, dtype=dtype, device=dev)
         self.aty, self.gram, self.Kinv = z(nb, N), z(nb, nk, nk), z(nb, nk, nk)
         self._x0, self._x1, self._h = z(nb, N), z(nb, N), z(nb, N)
+        # x0 at the start of the last executed iteration (`_x_old[0]`, optimizer.py:324), on request
+        self._x0_old = z(nb, N) if keep_x_old else None
         self.mu = torch.full((nb,), float(mu), dtype=_F64, device=dev)
         self.need_factor = torch.ones(nb, dtype=torch.int32, device=dev)
         self.done = torch.zeros(nb, dtype=torch.int32, device=dev)
@@ -656,6 +712,7 @@ class BatchedBasisPursuit:
         b = self.bufs
         b.nb, b.M, b.N, b.woodbury, b.nk = self.nb, self.M, self.N, int(self.woodbury), self.nk
         b.At = self.At.data_ptr() if self.At is not None else None
+        b.x0_old = self._x0_old.data_ptr() if self._x0_old is not None else None
         for name, t in (("A", self.A), ("aty", self.aty), ("gram", self.gram), ("Kinv", self.Kinv), ("x0", self._x0),
                         ("x1", self._x1), ("h", self._h), ("mu", self.mu), ("need_factor", self.need_factor),
                         ("done", self.done), ("iters", self.iters), ("last_res", self.last_res)):
@@ -776,6 +833,12 @@ class BatchedBasisPursuit:
 
     def h(self) -> np.ndarray:
         return self._h.cpu().numpy()
+
+    def x0_old(self) -> np.ndarray:
+        """x0 at the start of the last executed iteration (needs ``keep_x_old=True``)."""
+        if self._x0_old is None:
+            raise _lib.AdmmError("x0_old() needs BatchedBasisPursuit(..., keep_x_old=True)")
+        return self._x0_old.cpu().numpy()
 
     def objective(self) -> np.ndarray:
         """alpha ||y - A x0||^2 + lam |x1|_1 per problem."""

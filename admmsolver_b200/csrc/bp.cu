@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(BP_THREADS) bp_iterate_kernel(admm_bp_buffers 
     b.x0[(size_t)prob * N + n] = x0[n];
     b.x1[(size_t)prob * N + n] = x1[n];
     b.h[(size_t)prob * N + n] = h[n];
+    if (b.x0_old != nullptr) b.x0_old[(size_t)prob * N + n] = xo[n];     // `_x_old[0]` (optimizer.py:324)
   }
   if (tid == 0) {
     b.mu[prob] = mu;
@@ -464,6 +465,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) bp_fused_kernel(admm
             // x-update by the Woodbury identity, then z-update / dual ascent as in bp_iterate_kernel
             // (this is the serial section of a tile: multiply by 1/mu instead of dividing twice)
             const double xov = x0[n], hv = h[n];
+            if (b.x0_old != nullptr) b.x0_old[(size_t)prob * N + n] = xov;     // `_x_old[0]` (optimizer.py:324)
             const double xv = (r[n] - c) * inv_mu;
             const double yv = xv - hv * inv_mu;
             double z = 0.0;
@@ -690,6 +692,8 @@ __global__ void __launch_bounds__(BPS_THREADS, 1) bp_solo_kernel(admm_bp_buffers
   // my column (thread tid < ncol): everything of size N lives in registers
   const bool own = tid < ncol;
   double c_aty = 0.0, c_x0 = 0.0, c_x1 = 0.0, c_h = 0.0, c_r = 0.0;
+  double c_xold = 0.0;       // x0 at the start of the last executed iteration (`_x_old[0]`, optimizer.py:324)
+  bool ran_any = false;
   if (own) {
     const size_t o = (size_t)prob * N + n0 + tid;
     c_aty = b.aty[o];
@@ -762,6 +766,8 @@ __global__ void __launch_bounds__(BPS_THREADS, 1) bp_solo_kernel(admm_bp_buffers
 #pragma unroll
         for (int q = 0; q < BPS_PARTS; ++q) c += cp[q * Ncp + tid];
         const double xov = c_x0;
+        c_xold = xov;
+        ran_any = true;
         const double xv = (c_r - c) * inv_mu;
         const double yv = xv - c_h * inv_mu;
         double z = 0.0;
@@ -913,6 +919,7 @@ __global__ void __launch_bounds__(BPS_THREADS, 1) bp_solo_kernel(admm_bp_buffers
   if (own) {
     const size_t o = (size_t)prob * N + n0 + tid;
     b.x0[o] = c_x0;
+    if (b.x0_old != nullptr && ran_any) b.x0_old[o] = c_xold;
     b.x1[o] = c_x1;
     b.h[o] = c_h;
   }
@@ -937,11 +944,24 @@ static int check_bp(const admm_bp_buffers* b, const char* who) {
 
 static size_t bp_smem_bytes(const admm_bp_buffers* b) { return (size_t)(6 * b->N + 2 * b->nk + 5 * 32) * sizeof(double); }
 
+// kernel attributes (opt-in shared memory, cluster sizes) are per device: the "already configured" caches below are
+// keyed by (device, kernel)
+using DevKern = std::pair<int, const void*>;
+
 }  // namespace admm
 
 using namespace admm;
 
 extern "C" {
+
+int admm_bp_supported(int M, int N) {
+  if (M < 1 || N < 1) return 0;
+  admm_bp_buffers b = {};
+  b.M = M;
+  b.N = N;
+  b.nk = M < N ? M : N;
+  return bp_smem_bytes(&b) <= 220 * 1024 ? 1 : 0;
+}
 
 int admm_bp_setup(const admm_bp_buffers* b, const double* y, double* aty, double* gram, admm_stream_t stream) {
   if (int rc = check_bp(b, "admm_bp_setup")) return rc;
@@ -1015,8 +1035,8 @@ int admm_bp_iterate(const admm_bp_buffers* b, int iter_end, admm_stream_t stream
       const BpsLayout lay = bps_layout(b->M, b->N, cs);
       const size_t smem = (size_t)lay.total * sizeof(double);
       if (lay.Nc > BPS_THREADS || smem > 220 * 1024) return 1;
-      static std::map<const void*, int> state;             // per kernel: 0 unknown, 1 usable, -1 cluster does not fit
-      int& stt = state[reinterpret_cast<const void*>(kern)];
+      static std::map<DevKern, int> state;                 // per (device, kernel): 0 unknown, 1 usable, -1 cluster does not fit
+      int& stt = state[DevKern(cur_dev(), reinterpret_cast<const void*>(kern))];
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(b->nb * cs);
       cfg.blockDim = dim3(BPS_THREADS);
@@ -1065,19 +1085,15 @@ int admm_bp_iterate(const admm_bp_buffers* b, int iter_end, admm_stream_t stream
       // so that the clusters still fit the 148 SMs in one wave
       int cs = 1;
       if (!getenv("ADMM_BP_NO_CLUSTER")) {
-        static int sm_count = 0;
-        if (sm_count == 0) {
-          int dev = 0;
-          cudaGetDevice(&dev);
-          cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        }
+        int sm_count = 0;
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, cur_dev());
         const int slots = (small ? 2 : 1) * sm_count;   // resident CTAs of this kernel (296 / 148 on B200)
         for (int c = 8; c >= 2; c >>= 1)
           if (b->nb * c <= slots / 2) { cs = c; break; }
       }
       auto launch = [&](auto kern, int threads, int cs) -> int {
-        static std::map<const void*, size_t> configured;     // largest smem size configured per kernel
-        size_t& a = configured[reinterpret_cast<const void*>(kern)];
+        static std::map<DevKern, size_t> configured;         // largest smem size configured per (device, kernel)
+        size_t& a = configured[DevKern(cur_dev(), reinterpret_cast<const void*>(kern))];
         if (smem > a) {
           cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
           cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1120,10 +1136,11 @@ int admm_bp_iterate(const admm_bp_buffers* b, int iter_end, admm_stream_t stream
   }
   const size_t smem = bp_smem_bytes(b);
   ADMM_REQUIRE(smem <= 220 * 1024, ADMM_EUNSUPPORTED, "admm_bp_iterate: N=%d too large for the shared-memory resident path", b->N);
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
+  static std::map<int, size_t> attr;      // per device
+  size_t& a = attr[cur_dev()];
+  if (smem > 48 * 1024 && smem > a) {
     cudaFuncSetAttribute(bp_iterate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = smem;
+    a = smem;
   }
   bp_iterate_kernel<<<b->nb, BP_THREADS, smem, st>>>(*b, iter_end);
   return check_launch("admm_bp_iterate");

@@ -182,4 +182,12 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 
 inline int ceil_div(long long a, long long b) { return int((a + b - 1) / b); }
 
+// current device: kernel attributes (opt-in shared memory, cluster sizes) are per device, so every "already
+// configured" cache of a launcher is keyed by it
+inline int cur_dev() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+
 }  // namespace admm

@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <map>
 
 namespace cg = cooperative_groups;
 
@@ -370,6 +371,8 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
         const double2 v = *reinterpret_cast<const double2*>(b.x0 + frag_index(ct0 + p, NT, j, lane));
         xo[0][j][0] = v.x;
         xo[0][j][1] = v.y;
+        // `_x_old[0]` of the reference (optimizer.py:324): only kept when the caller asks for it
+        if (b.x0_old != nullptr && !is_done) *reinterpret_cast<double2*>(b.x0_old + frag_index(ct0 + p, NT, j, lane)) = v;
       }
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
@@ -894,6 +897,136 @@ __global__ void __launch_bounds__(128) spm_decide_kernel(admm_spm_dims d, admm_s
 }
 
 // ---------------------------------------------------------------------------------------------
+// sharded batch, batch-wide criterion: one-shot all-reduce of the ten sums over peer-mapped memory
+// ---------------------------------------------------------------------------------------------
+// Mailbox word = (seq << 32) | 32-bit half of a double: one atomic 8-byte store carries data and validity
+// (the receiver polls the word itself -- one-way NVLink latency, no fence, no separate flag).
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+constexpr int PEER_WORDS = 20;        // ten doubles as 32-bit halves
+constexpr int PEER_SLOT = 32;         // words per (buffer, source rank) slot of a mailbox
+
+// Stage 1 of the batch-wide sum; the CTA that finishes last adds the partials in a fixed order and pushes the
+// ten sums to every rank's mailbox (its own included) under sequence number ctrl[0] + 1.
+__global__ void __launch_bounds__(256) spm_reduce_post_kernel(admm_spm_dims d, admm_spm_buffers b, admm_peer_comm c) {
+  pdl_prologue();
+  __shared__ double scratch[10 * 32];
+  __shared__ double gs[10];
+  __shared__ int last;
+  const int tid = threadIdx.x;
+  const int per = (d.nb + gridDim.x - 1) / gridDim.x;
+  const int p0 = per * blockIdx.x, p1 = min(d.nb, p0 + per);
+  double v[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) v[i] = 0.0;
+  for (int prob = p0 + tid; prob < p1; prob += blockDim.x) {
+    double s[10];
+    gather_problem(d, b, prob, s);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) v[i] += s[i];
+  }
+  block_sum<10>(v, scratch);
+  if (tid < 10) {
+    double mine = 0.0;
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+      if (tid == i) mine = v[i];
+    __stcg(b.gpart + blockIdx.x * 16 + tid, mine);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = (atomicAdd(c.ctrl + 1, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double w[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) w[i] = 0.0;
+  for (int p = tid; p < (int)gridDim.x; p += blockDim.x) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) w[i] += __ldcg(b.gpart + p * 16 + i);
+  }
+  block_sum<10>(w, scratch);
+  const unsigned seq = c.ctrl[0] + 1u;
+  if (tid < 10) {
+    double mine = 0.0;
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+      if (tid == i) mine = w[i];
+    gs[tid] = mine;
+  }
+  __syncthreads();
+  for (int i = tid; i < PEER_WORDS * c.world; i += blockDim.x) {
+    const int peer = i / PEER_WORDS, k = i - peer * PEER_WORDS;
+    const double val = gs[k >> 1];
+    const unsigned half = (k & 1) ? (unsigned)__double2hiint(val) : (unsigned)__double2loint(val);
+    unsigned long long* box = c.mbox[peer] + ((size_t)(seq & 1u) * ADMM_MAX_PEERS + c.rank) * PEER_SLOT + k;
+    st_relaxed_sys_u64(box, ((unsigned long long)seq << 32) | half);
+  }
+  if (tid == 0) {
+    c.ctrl[1] = 0u;
+    c.ctrl[0] = seq;
+  }
+}
+
+// residual() / check_convergence() / update_mu() on the sums of ALL ranks: wait for the `world` posts of sequence
+// ctrl[0] in the local mailbox, add them in rank order (identical totals and decisions on every rank), decide.
+__global__ void __launch_bounds__(128) spm_decide_peer_kernel(admm_spm_dims d, admm_spm_buffers b, admm_peer_comm c,
+                                                              int do_update_mu) {
+  pdl_prologue();
+  __shared__ unsigned w32[ADMM_MAX_PEERS * PEER_WORDS];
+  __shared__ double gs[10];
+  __shared__ int fail;
+  const int tid = threadIdx.x;
+  const unsigned seq = c.ctrl[0];
+  const unsigned long long* box = c.mbox[c.rank] + (size_t)(seq & 1u) * ADMM_MAX_PEERS * PEER_SLOT;
+  if (tid == 0) fail = 0;
+  __syncthreads();
+  for (int i = tid; i < PEER_WORDS * c.world; i += blockDim.x) {
+    const int src = i / PEER_WORDS, k = i - src * PEER_WORDS;
+    const unsigned long long* p = box + src * PEER_SLOT + k;
+    const long long t0 = clock64();
+    unsigned long long v;
+    while (true) {
+      v = ld_relaxed_sys_u64(p);
+      if ((unsigned)(v >> 32) == seq) break;
+      if (clock64() - t0 > 10000000000LL) {       // a peer died: give up after ~5 s instead of hanging the GPU
+        fail = 1;
+        break;
+      }
+    }
+    w32[i] = (unsigned)v;
+  }
+  __syncthreads();
+  if (fail) {
+    if (tid == 0) b.flags[2] = -2;
+    return;
+  }
+  if (tid < 10) {
+    double a = 0.0;
+    for (int r = 0; r < c.world; ++r)
+      a += __hiloint2double((int)w32[r * PEER_WORDS + 2 * tid + 1], (int)w32[r * PEER_WORDS + 2 * tid]);
+    gs[tid] = a;
+    if (blockIdx.x == 0) b.gsum[tid] = a;
+  }
+  __syncthreads();
+  const int prob = blockIdx.x * blockDim.x + tid;
+  if (prob >= d.nb) return;
+  if (b.done[prob]) return;
+  double s[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) s[i] = gs[i];
+  decide_one(d, b, prob, s, do_update_mu);
+}
+
+// ---------------------------------------------------------------------------------------------
 // solo: a handful of problems, each on its own thread-block cluster, the WHOLE solve in one launch
 // ---------------------------------------------------------------------------------------------
 // A single SpM problem (spm.ipynb) has 2 x 156 kflop of work per iteration: launch latency and the
@@ -1217,6 +1350,8 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
   const bool lact = lth && pl < npl && l < L;
   const size_t fo = lact ? frag_index(pt * npl + pl, NT, l >> 3, 4 * g + ((l & 7) >> 1)) + (l & 1) : 0;
   double r_b0 = 0.0, r_h10 = 0.0, r_x1 = 0.0, r_x0 = 0.0, r_y0 = 0.0, r_V = 0.0, r_aim = 0.0, Dp = 0.0;
+  double r_xold = 0.0;         // x0 at the start of the last executed iteration (`_x_old[0]`)
+  bool ran_any = false;
   if (lact) {
     r_b0 = b.b0[fo];
     r_h10 = b.h10[fo];
@@ -1449,6 +1584,8 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
         n[0] = (xv - z) * (xv - z);
         n[1] = xv * xv;
         n[2] = z * z;
+        r_xold = r_x0;
+        ran_any = true;
         r_x0 = xv;
         r_x1 = z;
         r_y0 = y;
@@ -1631,6 +1768,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
   // ---- write the state back in the layouts of the batch kernels
   if (crank == 0 && lact) {
     b.x0[fo] = r_x0;
+    if (b.x0_old != nullptr && ran_any) b.x0_old[fo] = r_xold;
     b.x1[fo] = r_x1;
     b.h10[fo] = r_h10;
     b.y0[fo] = r_y0;
@@ -1709,11 +1847,12 @@ static int launch_pass_k(const admm_spm_dims* d, const admm_spm_buffers* b, cuda
   const dim3 grid = d->nbal > 0 ? dim3(d->nbal, 1) : dim3(ceil_div(d->npt, PASS_WARPS * MT), d->nsplit);
   const size_t smem = PassSmem<NT, MT>::BYTES;
   auto k = spm_pass_kernel<NT, MT, MODE, FNP>;
-  static bool configured = false;     // per instantiation
-  if (!configured) {
+  static std::map<int, bool> configured;     // per instantiation and device
+  bool& cfgd = configured[cur_dev()];
+  if (!cfgd) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = true;
+    cfgd = true;
   }
   launch_pdl(k, grid, dim3(PASS_WARPS * 32), smem, s, use_pdl(), *d, *b);
   return check_launch(FNP ? "admm_spm_step" : "admm_spm_pass");
@@ -1752,7 +1891,8 @@ static int launch_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const 
                        cudaStream_t st, int* max_clusters = nullptr) {   // max_clusters != NULL: occupancy query only
   const size_t smem = solo_smem_bytes(d, CS);
   auto kern = spm_solo_kernel<CS, LP, REGP, BW>;
-  static size_t configured = 0;     // per instantiation
+  static std::map<int, size_t> configured_by_dev;     // per instantiation and device
+  size_t& configured = configured_by_dev[cur_dev()];
   if (smem > configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
@@ -1770,8 +1910,9 @@ static int launch_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const 
   cfg.attrs = at;
   cfg.numAttrs = 1;
   if (max_clusters != nullptr) {
-    static size_t cached_smem = 0;
-    static int cached_n = 0;
+    static std::map<int, std::pair<size_t, int>> cache_by_dev;
+    size_t& cached_smem = cache_by_dev[cur_dev()].first;
+    int& cached_n = cache_by_dev[cur_dev()].second;
     if (cached_smem != smem) {
       int n = 0;
       if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
@@ -1906,6 +2047,33 @@ int admm_spm_decide(const admm_spm_dims* d, const admm_spm_buffers* b, int do_up
   launch_pdl(spm_decide_kernel, dim3(ceil_div(d->nb, 128)), dim3(128), 0, static_cast<cudaStream_t>(stream), use_pdl(), *d, *b,
              do_update_mu, 0);
   return check_launch("admm_spm_decide");
+}
+
+static int check_comm(const admm_peer_comm* c, const char* who) {
+  ADMM_REQUIRE(c != nullptr && c->world >= 1 && c->world <= ADMM_MAX_PEERS && c->rank >= 0 && c->rank < c->world &&
+                   c->ctrl != nullptr,
+               ADMM_EINVAL, "%s: bad peer communicator", who);
+  for (int r = 0; r < c->world; ++r) ADMM_REQUIRE(c->mbox[r] != nullptr, ADMM_EINVAL, "%s: mailbox of rank %d not mapped", who, r);
+  return ADMM_OK;
+}
+
+int admm_spm_reduce_post(const admm_spm_dims* d, const admm_spm_buffers* b, const admm_peer_comm* c, admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_reduce_post")) return rc;
+  if (int rc = check_comm(c, "admm_spm_reduce_post")) return rc;
+  ADMM_REQUIRE(d->batch_wide, ADMM_EINVAL, "admm_spm_reduce_post: batch-wide criterion only");
+  launch_pdl(spm_reduce_post_kernel, dim3(reduce_parts(d)), dim3(256), 0, static_cast<cudaStream_t>(stream), use_pdl(), *d, *b,
+             *c);
+  return check_launch("admm_spm_reduce_post");
+}
+
+int admm_spm_decide_peer(const admm_spm_dims* d, const admm_spm_buffers* b, const admm_peer_comm* c, int do_update_mu,
+                         admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_decide_peer")) return rc;
+  if (int rc = check_comm(c, "admm_spm_decide_peer")) return rc;
+  ADMM_REQUIRE(d->batch_wide, ADMM_EINVAL, "admm_spm_decide_peer: batch-wide criterion only");
+  launch_pdl(spm_decide_peer_kernel, dim3(ceil_div(d->nb, 128)), dim3(128), 0, static_cast<cudaStream_t>(stream), use_pdl(), *d,
+             *b, *c, do_update_mu);
+  return check_launch("admm_spm_decide_peer");
 }
 
 int admm_spm_reduce_decide(const admm_spm_dims* d, const admm_spm_buffers* b, int do_update_mu, admm_stream_t stream) {

@@ -142,7 +142,8 @@ class _BPPlan:
         from .batch import BatchedBasisPursuit
         ls, l1 = model.functions
         A = ls._A._dense_dev()
-        self.eng = BatchedBasisPursuit(A, ls._y_dev, alpha=float(ls._alpha), lam=float(l1._alpha), keep_history=True)
+        self.eng = BatchedBasisPursuit(A, ls._y_dev, alpha=float(ls._alpha), lam=float(l1._alpha), keep_history=True,
+                                       keep_x_old=True)
 
     @staticmethod
     def match(model: Model) -> bool:
@@ -151,8 +152,8 @@ class _BPPlan:
             return False
         if not isinstance(f[0]._A, DenseMatrix) or f[0]._A._dense_dev().is_complex() or f[0]._y_dev.is_complex():
             return False
-        n = f[0].size_x
-        if n > 4000:
+        m, n = f[0]._A.shape
+        if D._lib.lib.admm_bp_supported(int(m), int(n)) == 0:      # the N-vectors have to fit one CTA's shared memory
             return False
         return _is_identity(model.E[0, 1]) and _is_identity(model.E[1, 0])
 
@@ -176,7 +177,7 @@ class _SpMPlan:
         Cm = unwrap(cls._C)._dense_dev().reshape(-1)
         self.nb, self.L, self.Nw = nb, L, P.shape[0]
         self.eng = SharedSpM.from_operators(G0, b0, P, Cm, cls._D_dev, lam=float(l1._alpha), mu10=mu10, mu20=mu20,
-                                            batch_wide=True, max_mu=max_mu, force_complex=True)
+                                            batch_wide=True, max_mu=max_mu, force_complex=True, keep_x_old=True)
 
     @staticmethod
     def match(model: Model):
@@ -475,6 +476,15 @@ class SimpleOptimizer(object):
         test and update_mu() of an iteration share one set of norms (one host synchronisation per iteration
         instead of one per norm; the reference recomputes every E @ x for each of the three)."""
         self._upload()
+        if not self._pairs and callback is None:
+            # no equality conditions: the terms are independent, check_convergence() is vacuously True after the
+            # first sweep (optimizer.py:232-249,313) -- one sweep, residuals (0, 0)
+            if niter > 0:
+                self._sweep_dev(update_h)
+                self._primal_residual.append(0.0)
+                self._dual_residual.append(0.0)
+            self._download()
+            return
         # The captured graph of the current penalties survives across solve() calls as long as the device state keeps
         # its addresses (capture + instantiation costs 10 ms and sporadically 100s of ms -- more than a short solve).
         dev = self._xd[0].device
@@ -609,7 +619,6 @@ class SimpleOptimizer(object):
                 if any(np.abs(a.imag).max(initial=0.0) != 0.0 for a in (self._x[0], self._x[1], self._h[1, 0])):
                     raise NotImplementedError("complex state on the real basis-pursuit engine")
                 eng.set_state(x0=self._x[0].real, x1=self._x[1].real, h=self._h[1, 0].real, mu=float(self._mu[1, 0]))
-            x0_before = eng._x0.clone()
             n0 = len(eng.primal_residual[0])
             eng.solve(niter, interval_update_mu=interval, rtol=rtol)
             self._x[0][:] = eng.x0()[0]
@@ -618,8 +627,11 @@ class SimpleOptimizer(object):
             self._mu[1, 0] = float(eng.mu[0].item())
             self._primal_residual.extend(eng.primal_residual[0][n0:])
             self._dual_residual.extend(eng.dual_residual[0][n0:])
-            # _x_old is only exact when a single iteration ran; expose the engine's best knowledge
-            self._x_old = [D.to_host(x0_before[0]).astype(np.complex128), self._x[1].copy()]
+            # `_x_old` (optimizer.py:324): the state before the last sweep.  Only x_old[0] enters residual() /
+            # check_convergence() / update_mu() of this pattern (pair (1,0): E[0,1] @ E[1,0] @ x_old[0]); the engine
+            # hands it out exactly.  x_old[1] is not kept by the kernels: the current x1 stands in.
+            if len(eng.primal_residual[0]) > n0:
+                self._x_old = [eng.x0_old()[0].astype(np.complex128), self._x[1].copy()]
         else:
             if self._plan is None:
                 self._plan = _SpMPlan(self._model, float(self._mu[1, 0]), float(self._mu[2, 0]), float(self._max_mu))
@@ -643,6 +655,10 @@ class SimpleOptimizer(object):
             self._mu[2, 0] = float(eng.mu20[0].item())
             self._primal_residual.extend(eng.primal_residual[n0:])
             self._dual_residual.extend(eng.dual_residual[n0:])
+            # `_x_old`: x_old[0] exact from the engine (both pairs (1,0) and (2,0) only read x_old[0]); the current
+            # x1 / x2 stand in for x_old[1] / x_old[2], which the kernels do not keep (x2 is Nw x nb)
+            if len(eng.primal_residual) > n0:
+                self._x_old = [eng.x0_old().ravel().astype(np.complex128), self._x[1].copy(), self._x[2].copy()]
         self._xd = None          # the generic mirrors are stale now
         self._xd_old = None
         self._snapshot = self._host_state()

@@ -7,8 +7,17 @@
 One "step" is one ``solve(niter)`` over the whole resident batch (``--niter`` ADMM iterations,
 default 100 = one mu-update interval).  Default workload: BASELINE config 5, the 2^20-problem
 complex128 SpM sweep sharing one basis, batch-sharded over the N ranks (strong scaling) with the
-batch-wide stopping criterion (NCCL all-reduce of the residual partial sums every iteration).
-Rank 0 prints ONE JSON line.
+batch-wide stopping criterion (the residual sums are all-reduced every iteration by the kernels
+themselves over peer-mapped NVLink memory; NCCL is the bootstrap and the barrier).
+
+Before anything is timed every rank passes a PARITY GATE: the engine that is about to be timed (same
+size, same launch configuration, same sharding) solves a batch of replicas of 64 problems and is compared
+with the unmodified reference's packed solve of those 64 problems (norms scale by the replica count, so mu
+history and stopping test are those of the small batch); the line carries the result in ``parity``.
+
+Rank 0 prints ONE JSON line.  Besides the headline workload it carries, under ``also``, the same
+measurement for the other batched BASELINE workloads (``bp_cfg4``: 65536 independent basis-pursuit
+problems, sharded without communication; ``spm_cfg3``: 4096 problems sharing one A, N = 1 only).
 """
 from __future__ import annotations
 
@@ -44,6 +53,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--per-problem", action="store_true", help="SpM: per-problem mu/stopping (no collective)")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="sharded batch-wide criterion: in-kernel peer-memory all-reduce (default) or NCCL between kernels")
+    ap.add_argument("--no-also", action="store_true", help="only the headline workload (skip the `also` block)")
+    ap.add_argument("--no-parity-gate", action="store_true")
     return ap.parse_args()
 
 
@@ -114,6 +127,19 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU baselines (the reference's own implementation on the host cores; bounded samples)
 # ----------------------------------------------------------------------------------------------
+def _problems():
+    """admmsolver_b200/problems.py loaded BY PATH: the input generators are plain NumPy, and importing the product
+    package would map libadmm_b200.so into the process that times the reference."""
+    mod = sys.modules.get("_admm_problems")
+    if mod is None:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_admm_problems", os.path.join(ROOT, "admmsolver_b200", "problems.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["_admm_problems"] = mod
+        spec.loader.exec_module(mod)
+    return mod
+
+
 def _import_reference():
     ref = os.path.join(ROOT, "baseline", "_ref")
     if os.path.isdir(os.path.join(ref, "admmsolver")):
@@ -125,7 +151,7 @@ def _import_reference():
 
 def cpu_spm_sample(nb_s: int, niter: int, Nw: int = 2000, seed: int = 0):
     """Packed PartialDiagonalMatrix formulation of the reference (batch-wide), nb_s problems."""
-    from admmsolver_b200 import problems
+    problems = _problems()
     kind = _import_reference()
     basis = problems.ir_basis()
     p = problems.spm_batch(nb_s, basis, Nw=Nw, seed=seed) if nb_s > 1 else problems.spm_single(basis, Nw=Nw)
@@ -157,7 +183,7 @@ def cpu_spm_sample(nb_s: int, niter: int, Nw: int = 2000, seed: int = 0):
 
 
 def cpu_bp_sample(nb_s: int, niter: int, M: int, N: int, K: int):
-    from admmsolver_b200 import problems
+    problems = _problems()
     kind = _import_reference()
     A, y, _ = problems.basis_pursuit_batch(nb_s, M, N, K, 0)
     t0 = time.perf_counter()
@@ -256,14 +282,36 @@ def host_threads() -> int:
 
 
 # ----------------------------------------------------------------------------------------------
+# workload description shared by both arms (the driver compares the two `config` objects)
+# ----------------------------------------------------------------------------------------------
+UNIT_BYTES = {"spm": 16.0 * 2000, "bp_cfg4": 8.0 * 128 * 512 + 8.0 * 128 * 128, "bp_cfg1": 8.0 * 200 * 1000 + 8.0 * 200 * 200}
+
+
+def workload_config(workload: str, nb_total: int, world: int, niter: int, per_problem: bool, collective: str):
+    nb_def, niter_def, desc = WORKLOADS[workload]
+    is_spm = workload.startswith("spm")
+    nb_local = nb_total // world if nb_total >= world else nb_total
+    per_unit = UNIT_BYTES["spm"] if is_spm else UNIT_BYTES[workload]
+    if is_spm and not per_problem:
+        crit = "batch-wide" + (" (in-kernel peer-memory all-reduce over NVLink)" if world > 1 and collective == "peer"
+                               else " (NCCL all-reduce)" if world > 1 else "")
+    else:
+        crit = "per-problem"
+    return {"workload": workload, "description": desc, "problems_total": nb_local * world, "problems_per_gpu": nb_local,
+            "iterations_per_step": niter, "criterion": crit,
+            "l2": "working set per iteration >> L2 (126 MB)" if nb_local * per_unit > 2.5e8 else
+                  "working set fits L2; no flush (the solver iterates on resident state by design)"}
+
+
+# ----------------------------------------------------------------------------------------------
 # reference arm
 # ----------------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     nb_def, niter_def, desc = WORKLOADS[args.workload]
-    # import numpy-side generators without touching CUDA
     vals, sample, kind, cores = [], "", "port", 1
     for i in range(args.warmup + args.steps):
         v, kind, sample, cores = cpu_baseline_for(args.workload)
@@ -274,10 +322,13 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "sample": sample},
+        "config": workload_config(args.workload, args.nb or nb_def, max(1, world), args.niter or niter_def,
+                                  args.per_problem, args.collective),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # evidence that none of this repo's native code is on the reference arm's path
+        "native_so_mapped": "libadmm_b200" in open("/proc/self/maps").read(),
     }
     print(json.dumps(line))
 
@@ -315,39 +366,87 @@ def measure_fp64_peak(torch, seconds: float = 1.5):
     return burst, sustained
 
 
-def run_ours(args):
+def _rel(a, b):
+    return float(np.linalg.norm(np.ravel(a - b)) / max(np.linalg.norm(np.ravel(b)), 1e-300))
+
+
+def reference_packed_spm(p, niter):
+    """The checker of the parity gate: the unmodified reference (baseline/_ref; the oracle port when it is absent) on
+    the packed batch `p` -- x0 (L, nb), mu10, mu20, iterations run.  CPU, rank 0, a second or two."""
+    kind = _import_reference()
+    nb = p.g.shape[1] if p.g.ndim == 2 else 1
+    L, Nw = p.s.size, p.P.shape[0]
+    if kind == "reference":
+        from admmsolver.matrix import DiagonalMatrix, PartialDiagonalMatrix, identity
+        from admmsolver.objectivefunc import ConstrainedLeastSquares, L1Regularizer, NonNegativePenalty
+        from admmsolver.optimizer import Model, SimpleOptimizer
+        if nb > 1:
+            rest = (nb,)
+            lstsq = ConstrainedLeastSquares(1.0, PartialDiagonalMatrix(-DiagonalMatrix(p.s), rest), p.g.ravel(),
+                                            PartialDiagonalMatrix(p.C, rest), np.ones(nb))
+            conds = [(0, 1, identity(L * nb), identity(L * nb)), (0, 2, PartialDiagonalMatrix(p.P, rest), identity(Nw * nb))]
+        else:
+            lstsq = ConstrainedLeastSquares(1.0, -DiagonalMatrix(p.s), np.ravel(p.g), p.C, np.array([1.0]))
+            conds = [(0, 1, identity(L), identity(L)), (0, 2, p.P, identity(Nw))]
+        opt = SimpleOptimizer(Model([lstsq, L1Regularizer(p.lam, L * nb), NonNegativePenalty(Nw * nb)], conds), mu=p.mu)
+        opt.solve(niter)
+        return (opt.x[0].reshape(L, nb), float(opt._mu[1, 0]), float(opt._mu[2, 0]), len(opt._primal_residual), kind)
+    from oracle import flat
+    st = flat.spm_solve(p.s, p.P, p.C, np.ones(nb), p.g.reshape(L, nb), p.lam, niter, mu=p.mu)
+    return (np.asarray(st.x0).reshape(L, nb), float(st.mu10), float(st.mu20), int(st.niter_done), kind)
+
+
+def reference_bp(A, y, niter):
+    kind = _import_reference()
+    N = A.shape[1]
+    if kind == "reference":
+        from admmsolver.matrix import identity
+        from admmsolver.objectivefunc import L1Regularizer, LeastSquares
+        from admmsolver.optimizer import Model, SimpleOptimizer
+        opt = SimpleOptimizer(Model([LeastSquares(1.0, A, y), L1Regularizer(0.1, N)], [(1, 0, identity(N), identity(N))]))
+        opt.solve(niter)
+        return opt.x[0].real.copy(), float(opt._mu[1, 0]), len(opt._primal_residual), kind
+    from oracle import flat
+    st = flat.bp_solve(A, y, 1.0, 0.1, niter)
+    return np.asarray(st.x0).real.copy(), float(st.mu), int(st.niter_done), kind
+
+
+def run_workload(args, workload, ctx, steps, warmup, with_clocks):
+    """Set up, gate, time and describe ONE workload.  Returns the dict of its part of the JSON line (rank 0; other
+    ranks get None)."""
     import torch
     import torch.distributed as dist
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local)
-    group = None
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        group = dist.group.WORLD
-
     from admmsolver_b200 import _lib, batch, problems
 
-    nb_def, niter_def, desc = WORKLOADS[args.workload]
-    nb_total = args.nb or nb_def
-    niter = args.niter or niter_def
-    is_spm = args.workload.startswith("spm")
+    world, rank, local, group = ctx["world"], ctx["rank"], ctx["local"], ctx["group"]
+    hbm_peak, hbm_src, fp64_burst, fp64_sus = ctx["hbm_peak"], ctx["hbm_src"], ctx["fp64_burst"], ctx["fp64_sus"]
+    nb_def, niter_def, desc = WORKLOADS[workload]
+    main_wl = workload == args.workload
+    nb_total = (args.nb if main_wl and args.nb else nb_def)
+    niter = (args.niter if main_wl and args.niter else niter_def)
+    is_spm = workload.startswith("spm")
     nb_local = nb_total // world if nb_total >= world else nb_total
-    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
-        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback"
 
-    fp64_burst = fp64_sus = None
-    if rank == 0:
-        fp64_burst, fp64_sus = measure_fp64_peak(torch)
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def bcast(obj):
+        if world == 1:
+            return obj
+        box = [obj]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
 
     h2d = d2h = 0
+    parity = None
     if is_spm:
         basis = problems.ir_basis()
         Nw = 2000
@@ -363,22 +462,70 @@ def run_ours(args):
         g_dev = g_host.to("cuda", non_blocking=True)
         batch_wide = not args.per_problem
         eng = batch.SharedSpM(p.s, p.P, p.C, np.ones(nb_local), g_dev, lam=p.lam, mu=p.mu,
-                              batch_wide=batch_wide, group=group if batch_wide else None)
+                              batch_wide=batch_wide, group=group if batch_wide else None, collective=args.collective)
 
         # a handful of problems: the cluster-resident single-launch solve (admm_spm_solo); every step
         # starts from the zero state so that it really runs `niter` iterations
         solo = (nb_local <= eng.SOLO_MAX_NB and group is None
                 and _lib.lib.admm_spm_solo_supported(C.byref(eng.dims)) != 0)
 
+        # ---- parity gate: THIS engine against the reference's packed solve (before any timing)
+        if not args.no_parity_gate:
+            gate_iters = 120 if nb_total > 1 else 200
+            nd = 64 if nb_local % 64 == 0 else (nb_local if nb_local <= 64 else 0)
+            if nd > 0:
+                pg = problems.spm_batch(nd, basis, Nw=Nw, seed=4242) if nb_total > 1 else p
+                gg = pg.g.reshape(L, -1).astype(np.complex128)
+                R = nb_local // nd
+                gg_dev = torch.from_numpy(gg).cuda().repeat(1, R).contiguous()       # replica r of problem d: column r*nd+d
+                eng.reset(g=gg_dev, mu=pg.mu)
+                ran = eng.solve(gate_iters)
+                x0 = eng.x0_device()
+                first = x0[:, :nd]
+                replicas_equal = bool((x0.view(L, R, nd) == first[:, None, :]).all())
+                if batch_wide or nd == 1:
+                    ref = bcast(reference_packed_spm(pg, gate_iters) if rank == 0 else None)
+                    x_ref, mu10_ref, mu20_ref, n_ref, checker = ref
+                    err = max(_rel(x0[:, r * nd:(r + 1) * nd].cpu().numpy(), x_ref) for r in sorted({0, R // 2, R - 1}))
+                    mu_eq = float(eng.mu10[0]) == mu10_ref and float(eng.mu20[0]) == mu20_ref
+                    it_eq = int(ran) == int(n_ref)
+                else:
+                    # per-problem criterion: every column is its own reference instance (sampled problems)
+                    import copy
+                    err, mu_eq, it_eq = 0.0, True, True
+                    for dcol in (0, nd // 2, nd - 1):
+                        one = copy.copy(pg)
+                        one.g = gg[:, dcol:dcol + 1]
+                        x_ref, mu10_ref, mu20_ref, n_ref, checker = bcast(reference_packed_spm(one, gate_iters) if rank == 0 else None)
+                        col = (R - 1) * nd + dcol
+                        err = max(err, _rel(x0[:, col].cpu().numpy(), x_ref[:, 0]))
+                        mu_eq = mu_eq and float(eng.mu10[col]) == mu10_ref and float(eng.mu20[col]) == mu20_ref
+                        it_eq = it_eq and int(eng.iters[col]) == int(n_ref)
+                bad = allmax(0.0 if (err <= 1e-10 and mu_eq and it_eq and replicas_equal) else 1.0)
+                parity = {"max_rel_x0": allmax(err), "tolerance": 1e-10, "mu_equal": allmax(0.0 if mu_eq else 1.0) == 0.0,
+                          "iterations_equal": allmax(0.0 if it_eq else 1.0) == 0.0,
+                          "replicas_bit_identical": allmax(0.0 if replicas_equal else 1.0) == 0.0,
+                          "ranks_checked": world, "checker": checker,
+                          "what": "%d replicas x %d problems per rank, %d iterations, vs the packed solve of the %d problems "
+                                  "on the host (norms scale by the replica count)" % (R, nd, gate_iters, nd)}
+                if bad:
+                    raise SystemExit("bench.py: PARITY GATE FAILED, nothing timed: %s" % json.dumps(parity))
+                del gg_dev, x0
+                eng.reset(g=g_dev, mu=p.mu)
+
         def step():
             if solo:
                 eng.reset(mu=p.mu)
-            eng.solve(niter)
+            ran = eng.solve(niter)
+            if ran != niter:        # an early batch-wide stop would silently inflate problem-iters/s
+                raise SystemExit("bench.py: solve() ran %d of %d iterations inside the timed region" % (ran, niter))
 
         def e2e_step():
             g_dev.copy_(g_host, non_blocking=True)
             eng.reset(g=g_dev, mu=p.mu)
-            eng.solve(niter)
+            ran = eng.solve(niter)
+            if ran != niter:
+                raise SystemExit("bench.py: solve() ran %d of %d iterations inside the e2e region" % (ran, niter))
             out_host.copy_(eng.x0_device(), non_blocking=True)
 
         h2d = g_host.numel() * 16
@@ -393,6 +540,7 @@ def run_ours(args):
         npl = eng.dims.nplanes
         flops_per_unit = 4.0 * L * Nw + (4.0 * L * L * npl if fused else 0.0)
         bytes_per_unit = 16.0 * Nw + (8.0 * L * (10 * npl + (4 if npl == 2 else 0)) if fused else 0.0)
+        survey_flops_per_unit = 8.0 * L * Nw + 4.0 * L * L       # both planes through both skinny GEMMs
         kernel_name = "spm_pass_kernel<%d,%d,0,%d>" % (eng.dims.Lp // 8, eng.dims.mt, npl if fused else 0)
         if solo:
             flops_per_unit = 4.0 * L * Nw + 4.0 * L * L * npl
@@ -400,7 +548,8 @@ def run_ours(args):
             kernel_name = "spm_solo_kernel<8>"
         bound = "tensor"
     else:
-        if args.workload == "bp_cfg4":
+        solo = False
+        if workload == "bp_cfg4":
             M, N, K = 128, 512, 10
         else:
             M, N, K = 200, 1000, 10
@@ -418,6 +567,33 @@ def run_ours(args):
         def reset_state():
             eng.set_state(x0=zeros, x1=zeros, h=zeros, mu=1.0)
 
+        def check_ran():
+            lo = int(eng.iters.min().item())
+            if lo != niter:
+                raise SystemExit("bench.py: a problem ran %d of %d iterations inside the timed region" % (lo, niter))
+
+        # ---- parity gate: sampled problems of THIS engine against independent reference instances
+        if not args.no_parity_gate:
+            reset_state()
+            eng.solve(niter)
+            x_all = eng._x0
+            idx = sorted({0, 1, gen_nb - 1})
+            err, mu_eq, it_eq, checker = 0.0, True, True, "reference"
+            for b in idx:
+                xr, mur, nr, checker = reference_bp(A_s[b], y_s[b], niter)
+                last = b + (reps - 1) * gen_nb if b + (reps - 1) * gen_nb < nb_local else b     # its last replica in the slab
+                for col in sorted({b, last}):
+                    err = max(err, _rel(x_all[col].cpu().numpy(), xr))
+                    mu_eq = mu_eq and float(eng.mu[col]) == mur
+                    it_eq = it_eq and int(eng.iters[col]) == nr
+            bad = allmax(0.0 if (err <= 1e-10 and mu_eq and it_eq) else 1.0)
+            parity = {"max_rel_x0": allmax(err), "tolerance": 1e-10, "mu_equal": allmax(0.0 if mu_eq else 1.0) == 0.0,
+                      "iterations_equal": allmax(0.0 if it_eq else 1.0) == 0.0, "ranks_checked": world, "checker": checker,
+                      "what": "problems %s of every rank's slab (and their last replicas), %d iterations, vs independent "
+                              "instances on the host" % (idx, niter)}
+            if bad:
+                raise SystemExit("bench.py: PARITY GATE FAILED, nothing timed: %s" % json.dumps(parity))
+
         def step():
             reset_state()
             eng.solve(niter)
@@ -433,6 +609,7 @@ def run_ours(args):
         h2d = y_host.numel() * 8
         d2h = out_host.numel() * 8
         flops_per_unit = 4.0 * M * N + 2.0 * M * M
+        survey_flops_per_unit = flops_per_unit
         if eng.At is not None:
             # single-sweep kernel: A streamed once per iteration (the column tile that yields A^T s also
             # feeds the next A r), K^-1 once; the N-vectors never leave shared memory
@@ -447,11 +624,6 @@ def run_ours(args):
             kernel_name = "bp_iterate_kernel"
         bound = "hbm"
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     def timed(fn, nsteps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -460,16 +632,13 @@ def run_ours(args):
             fn()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return allmax(e0.elapsed_time(e1))
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and with_clocks:
         sampler.start()
     launches0 = _lib.launch_count
     # SpM: iterations of >= ~1 ms are launched eagerly with CUDA events around the dominant kernel
@@ -478,25 +647,29 @@ def run_ours(args):
     in_region_events = is_spm and nb_local >= 65536
     if in_region_events:
         eng.pass_events = []
-    total_ms = timed(step, args.steps)
+    total_ms = timed(step, steps)
     launches = _lib.launch_count - launches0
-    if total_ms < 1500.0:
-        # short timed region: nvidia-smi (200 ms period) saw little of it; keep the identical load running,
-        # untimed, until it has a few samples (same steps, same buffers)
-        t_end = time.time() + 1.5
-        while time.time() < t_end:
-            step()
-            torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
-    if clocks is not None and total_ms < 1500.0:
-        clocks["note"] = "sampled while the timed step kept running for 1.5 s after the %.0f ms timed region" % total_ms
-    units = float(nb_local * world) * niter * args.steps
+    if not is_spm:
+        check_ran()
+    clocks = None
+    if with_clocks:
+        if total_ms < 1500.0:
+            # short timed region: nvidia-smi (200 ms period) saw little of it; keep the identical load running,
+            # untimed, until it has a few samples (same steps, same buffers)
+            t_end = time.time() + 1.5
+            while time.time() < t_end:
+                step()
+                torch.cuda.synchronize()
+        clocks = sampler.stop() if rank == 0 else None
+        if clocks is not None and total_ms < 1500.0:
+            clocks["note"] = "sampled while the timed step kept running for 1.5 s after the %.0f ms timed region" % total_ms
+    units = float(nb_local * world) * niter * steps
     value = units / (total_ms * 1e-3)
 
     # dominant-kernel duration (CUDA events on the launching stream)
     kernel_timing = None
     if is_spm and solo:
-        k_ms = total_ms / args.steps
+        k_ms = total_ms / steps
         units_per_launch = nb_local * niter
         kernel_timing = "step time (one cluster-resident launch runs all iterations; latency-bound, not a roofline case)"
     elif is_spm:
@@ -513,21 +686,23 @@ def run_ours(args):
         units_per_launch = nb_local
     else:
         # the persistent kernel runs all iterations: time = step time / launches that do work
-        k_ms = total_ms / args.steps
+        k_ms = total_ms / steps
         units_per_launch = nb_local * niter
         kernel_timing = "step time (one persistent launch runs all iterations)"
 
     e2e = None
     if not args.no_e2e:
-        for _ in range(max(1, min(args.warmup, 2))):
+        for _ in range(max(1, min(warmup, 2))):
             e2e_step()
-        ms = timed(e2e_step, args.steps)
+        ms = timed(e2e_step, steps)
         e2e = {"value": units / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
 
+    if is_spm and eng._peer is not None:
+        eng._peer.close()
+    del eng
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of the
     # same kernel at the same per-launch size (profiles/traffic.json); null when no capture matches
@@ -554,6 +729,10 @@ def run_ours(args):
                     "peak_source": "measured live: cuBLAS DGEMM 8192^3 via torch.matmul, sustained (burst %.1f)" % fp64_burst,
                     "avg_launch_ms": k_ms, "kernel_timing": kernel_timing,
                     "algorithmic_flops_per_launch": flops_per_unit * units_per_launch,
+                    "flops_note": "executed flops: %.0f kflop per problem-iteration (the imaginary plane is advanced in L-space, "
+                                  "DESIGN.md 2.1); SURVEY 8(d) counts %.0f kflop for both planes through both skinny GEMMs -- "
+                                  "the fraction is of EXECUTED flops" % (flops_per_unit / 1e3, survey_flops_per_unit / 1e3),
+                    "iteration_frac": flops_per_unit * nb_local * niter * steps / (total_ms * 1e-3) / 1e12 / peak,
                     "algorithmic_bytes_per_launch": bytes_per_unit * units_per_launch,
                     "hbm_achieved_gbs": bytes_per_unit * units_per_launch / (k_ms * 1e-3) / 1e9,
                     "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
@@ -569,23 +748,63 @@ def run_ours(args):
 
     cpu = None
     if not args.no_cpu_baseline:
-        v, kind, sample, cores = cpu_baseline_for(args.workload)
+        v, kind, sample, cores = cpu_baseline_for(workload)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
 
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if nb_total >= world else "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "problems_total": nb_local * world,
-                   "problems_per_gpu": nb_local, "iterations_per_step": niter,
-                   "criterion": ("batch-wide (NCCL all-reduce)" if (is_spm and not args.per_problem) else "per-problem"),
-                   "l2": "working set per iteration >> L2 (126 MB)" if nb_local * bytes_per_unit > 2.5e8 else
-                         "working set fits L2; no flush (the solver iterates on resident state by design)"},
-        "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "fp64_peak_tflops": {"burst": fp64_burst, "sustained": fp64_sus},
+    return {
+        "value": value, "unit": UNIT, "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps,
+        "scaling": "strong" if nb_total >= world else "weak",
+        "config": workload_config(workload, nb_total, world, niter, args.per_problem, args.collective),
+        "parity": parity, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
-    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    group = None
     if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        group = dist.group.WORLD
+
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    fp64_burst = fp64_sus = None
+    if rank == 0:
+        fp64_burst, fp64_sus = measure_fp64_peak(torch)
+    ctx = {"world": world, "rank": rank, "local": local, "group": group,
+           "hbm_peak": float(peaks.get("hbm_gbs", 6650.0)),
+           "hbm_src": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+           "fp64_burst": fp64_burst, "fp64_sus": fp64_sus}
+
+    main_part = run_workload(args, args.workload, ctx, args.steps, args.warmup, with_clocks=True)
+    also = {}
+    if not args.no_also and args.workload == "spm_sweep" and args.nb is None:
+        # the other batched BASELINE workloads, measured the same way in the same run (shorter: 3 warm-up, <= 3 steps)
+        for wl in (["bp_cfg4"] + (["spm_cfg3"] if world == 1 else [])):
+            part = run_workload(args, wl, ctx, min(args.steps, 3), 3, with_clocks=False)
+            if part is not None:
+                also[wl] = part
+    if rank == 0:
+        line = {"metric": METRIC, "value": main_part["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": main_part["ms_per_step"], "higher_is_better": True,
+                "scaling": main_part["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": main_part["config"], "parity": main_part["parity"], "roofline": main_part["roofline"],
+                "cpu_baseline": main_part["cpu_baseline"], "e2e": main_part["e2e"], "gpu_launches": main_part["gpu_launches"],
+                "clocks": main_part["clocks"], "fp64_peak_tflops": {"burst": fp64_burst, "sustained": fp64_sus}}
+        if also:
+            line["also"] = also
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ADMM_ABI_VERSION 2
+#define ADMM_ABI_VERSION 3
 
 enum admm_status { ADMM_OK = 0, ADMM_EINVAL = 1, ADMM_ECUDA = 2, ADMM_EUNSUPPORTED = 3 };
 enum admm_op { ADMM_OP_N = 0, ADMM_OP_T = 1, ADMM_OP_H = 2 };
@@ -118,7 +118,7 @@ int admm_spd_inverse_batched(int n, int nbatch, double* A, long long batch_strid
 /* Pattern B engine: SpM  [ConstrainedLeastSquares, L1Regularizer, NonNegativePenalty] with     */
 /* conditions (0,1,I,I), (0,2,P,I); many problems share s, P, C (PartialDiagonalMatrix packing).*/
 /* One ADMM iteration = admm_spm_step (or admm_spm_xupdate + admm_spm_pass for small batches),     */
-/* then admm_spm_reduce_decide (or admm_spm_reduce + NCCL all-reduce + admm_spm_decide).          */
+/* then admm_spm_reduce_decide (sharded batch: admm_spm_reduce_post + admm_spm_decide_peer).     */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct admm_spm_dims {
   int L;        /* basis size (size_x of terms 0 and 1)                                        */
@@ -211,6 +211,8 @@ typedef struct admm_spm_buffers {
   double* x1;
   double* h10;
   double* y0;             /* P^T P x0 (Gram-form norms of pair (2,0); maintained by the x-update) */
+  double* x0_old;         /* x0 at the start of the last executed iteration (`_x_old[0]`, optimizer.py:324),
+                             fragment layout like x0; NULL: not kept (saves the store)             */
   double* V;              /* [nsplit][ncolumn tiles][Lp/8][32][2]  P^T(h20 + mu20 x2) partials;
                              imaginary-plane tiles: z = P^T Im(h20) in split 0 (owned by xupdate)    */
   double* aim;            /* fragment layout; imaginary-plane tiles accumulate sum_k mu20_k Im(x0_k) */
@@ -275,6 +277,49 @@ int admm_spm_reduce_decide(const admm_spm_dims* d, const admm_spm_buffers* b, in
 int admm_spm_decide(const admm_spm_dims* d, const admm_spm_buffers* b, int do_update_mu,
                     admm_stream_t stream);
 
+/* ---- batch-wide criterion of a batch sharded over the GPUs of one box --------------
+ * The only exchange of the path: every iteration the ranks all-reduce their ten squared-norm sums
+ * (`residual()` / `check_convergence()` / `update_mu()` of the packed batch, optimizer.py:232-299).
+ * Instead of a library collective between two kernels, the reduction kernel itself PUSHES its sums into
+ * every peer's mailbox over NVLink (peer-mapped memory, one-way latency) and the decision kernel
+ * polls its own mailbox: no host involvement, graph-capturable, three launches per iteration.
+ *
+ * Mailbox of a rank: [2][ADMM_MAX_PEERS][32] 64-bit words (ADMM_MAILBOX_BYTES, zero-initialised).
+ * Word k of source rank r in buffer (seq & 1) = (seq << 32) | 32-bit half k of r's ten doubles
+ * (low half first): an 8-byte store is atomic, so data and validity travel together (no fence,
+ * no flag round trip).  seq counts the reductions of the plan; two buffers suffice because a rank
+ * can post reduction seq + 2 only after every peer has posted seq + 1, i.e. finished reading seq. */
+#define ADMM_MAX_PEERS 16
+#define ADMM_MAILBOX_BYTES (2 * ADMM_MAX_PEERS * 32 * 8)
+typedef struct admm_peer_comm {
+  int rank, world;                        /* world <= ADMM_MAX_PEERS                                  */
+  unsigned long long* mbox[ADMM_MAX_PEERS]; /* mbox[r]: mailbox of rank r as mapped into THIS process   */
+  unsigned* ctrl;                         /* local device [4], zero-initialised: 0 sequence number of the
+                                             last posted reduction, 1 CTA ticket of the reduce kernel */
+} admm_peer_comm;
+
+/* Device memory that peers on the same box can map (cudaMalloc + cudaIpcGetMemHandle; zero-filled).
+ * `handle_host` receives the 64-byte IPC handle to send to the peers (any host transport: the
+ * Python layer uses torch.distributed.all_gather_object).  admm_peer_open maps a peer's handle into
+ * this process (peer access is enabled lazily); close / free undo them.  Host-synchronous set-up
+ * calls, not part of the iteration. */
+int admm_peer_alloc(size_t bytes, void** devptr, unsigned char* handle_host);
+int admm_peer_open(const unsigned char* handle_host, void** devptr);
+int admm_peer_close(void* devptr);
+int admm_peer_free(void* devptr);
+
+/* admm_spm_reduce whose last CTA pushes the ten sums into the mailbox of every rank (its own
+ * included) with sequence number ctrl[0] + 1. */
+int admm_spm_reduce_post(const admm_spm_dims* d, const admm_spm_buffers* b, const admm_peer_comm* c,
+                         admm_stream_t stream);
+
+/* admm_spm_decide on the batch-wide sums of ALL ranks: every CTA waits until the `world` posts of
+ * sequence ctrl[0] have arrived in the local mailbox and adds them in rank order (identical totals,
+ * hence identical decisions, on every rank).  A peer that never posts trips a watchdog (~5 s):
+ * flags[2] = -2 and no decision is taken. */
+int admm_spm_decide_peer(const admm_spm_dims* d, const admm_spm_buffers* b, const admm_peer_comm* c,
+                         int do_update_mu, admm_stream_t stream);
+
 /* A handful of problems (spm.ipynb: ONE), the whole SimpleOptimizer.solve loop (optimizer.py:302-320)
  * in ONE launch: every problem is kept resident by a thread-block cluster of 8 CTAs (each owns
  * Nw/8 sampling points: its rows of P and of the state live in shared memory, the L-vectors in
@@ -311,6 +356,8 @@ typedef struct admm_bp_buffers {
   double* x0;             /* [nb][N]                                                           */
   double* x1;             /* [nb][N]                                                           */
   double* h;              /* [nb][N]                                                           */
+  double* x0_old;         /* [nb][N] x0 at the start of the last executed iteration (`_x_old[0]`,
+                             optimizer.py:324), written when a launch of admm_bp_iterate ends; NULL: not kept */
   double* mu;             /* [nb]                                                              */
   int* need_factor;       /* [nb] 1: Kinv stale for the current mu                             */
   int* done;              /* [nb]                                                              */
@@ -321,6 +368,11 @@ typedef struct admm_bp_buffers {
   double alpha, lam, rtol, max_mu, fact_incr, th_change;
   int interval_update_mu;
 } admm_bp_buffers;
+
+/* 1 if an M x N problem fits the shared-memory resident iteration kernels (the N-vectors and two
+ * vectors of the factor's order stay in one CTA's shared memory: (6 N + 2 min(M, N) + 160) * 8 bytes
+ * <= 220 KB), else 0 -- lets a caller pick another path BEFORE building Gram matrices and factors. */
+int admm_bp_supported(int M, int N);
 
 /* aty = alpha A^T y and gram = A A^T (woodbury) or A^T A.  Replaces `LeastSquares.__init__`
  * (objectivefunc.py:76-77) and the per-call `Ac @ y` (objectivefunc.py:108).  Either output may be

@@ -225,9 +225,61 @@ def main_psd():
     save("psd", **out)
 
 
+def _after(opt, loose):
+    """What the step-wise public methods return right after solve() (optimizer.py:232-299,324)."""
+    out = dict(x_old0=opt._x_old[0].copy(), residual_after=np.array(opt.residual()),
+               converged_tight=np.array(opt.check_convergence(1e-12)), converged_loose=np.array(opt.check_convergence(loose)),
+               primal=np.array(opt._primal_residual), dual=np.array(opt._dual_residual), x0=opt.x[0].copy())
+    opt.update_mu()
+    out["mu_after_update"] = np.array([opt._mu[i, j] for (i, j) in ((1, 0), (2, 0)) if i < opt._mu.shape[0]])
+    return out
+
+
+def main_after():
+    """`_x_old` hand-over: residual() / check_convergence() / update_mu() called right after solve() on the models the
+    fused engines take over.  `python tests/golden/make_golden.py after`."""
+    out = {}
+
+    def bp(tag, A, y, lam, niter, loose, **kw):
+        N = A.shape[1]
+        opt = SimpleOptimizer(Model([LeastSquares(1.0, A, y), L1Regularizer(lam, N)], [(1, 0, identity(N), identity(N))]))
+        opt.solve(niter, **kw)
+        out.update({f"{tag}_{k}": v for k, v in _after(opt, loose).items()})
+
+    A, y, _ = problems.basis_pursuit_instance(100, 1000, 20, 1234)
+    bp("bpnb", A, y, 0.1, 100, 1e-2)
+    A, y, _ = problems.basis_pursuit_instance(128, 512, 10, 2)
+    bp("bp301", A, y, 0.1, 301, 1e-3)          # last iteration (index 300) is a mu-update iteration
+    bp("lasso", np.array([[2.0, 1.0]]), np.array([2.0]), 0.1, 100, 1e-6)     # early exit (iteration 41)
+
+    basis = problems.ir_basis()
+    for tag, p, niter, nb in (("spm1", problems.spm_single(basis, Nw=192), 250, None),
+                              ("spm6", problems.spm_batch(6, basis, Nw=192, seed=3), 130, 6)):
+        L, Nw = p.s.size, p.P.shape[0]
+        if nb is None:
+            lstsq = ConstrainedLeastSquares(1.0, -DiagonalMatrix(p.s), p.g, p.C, p.D)
+            terms = [lstsq, L1Regularizer(p.lam, L), NonNegativePenalty(Nw)]
+            conds = [(0, 1, identity(L), identity(L)), (0, 2, p.P, identity(Nw))]
+        else:
+            rest = (nb,)
+            lstsq = ConstrainedLeastSquares(1.0, PartialDiagonalMatrix(-DiagonalMatrix(p.s), rest), p.g.ravel(),
+                                            PartialDiagonalMatrix(p.C, rest), p.D.astype(float))
+            terms = [lstsq, L1Regularizer(p.lam, L * nb), NonNegativePenalty(Nw * nb)]
+            conds = [(0, 1, identity(L * nb), identity(L * nb)), (0, 2, PartialDiagonalMatrix(p.P, rest), identity(Nw * nb))]
+        opt = SimpleOptimizer(Model(terms, conds), mu=p.mu)
+        opt.solve(niter)
+        out.update({f"{tag}_{k}": v for k, v in _after(opt, 1e-2).items()})
+        out.update({f"{tag}_s": p.s, f"{tag}_C": p.C, f"{tag}_g": p.g, f"{tag}_P": p.P, f"{tag}_lam": p.lam, f"{tag}_mu": p.mu,
+                    f"{tag}_D": np.asarray(p.D)})
+    save("after_solve", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "psd":
         main_psd()
+    elif len(sys.argv) > 1 and sys.argv[1] == "after":
+        main_after()
     else:
         main()
         main_psd()
+        main_after()

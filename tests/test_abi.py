@@ -20,7 +20,7 @@ def test_header_symbols_exported(build_lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/admm_b200.h but not exported"
     lib.admm_abi_version.restype = ctypes.c_int
-    assert lib.admm_abi_version() == 2
+    assert lib.admm_abi_version() == 3
 
 
 def test_ctypes_mirror_complete(build_lib):
@@ -33,7 +33,7 @@ def test_struct_layout_matches_header(build_lib):
     from admmsolver_b200 import _lib
     txt = open(os.path.join(ROOT, "include", "admm_b200.h")).read()
     for cname, cls in (("admm_spm_dims", _lib.SpmDims), ("admm_spm_buffers", _lib.SpmBuffers),
-                       ("admm_bp_buffers", _lib.BpBuffers)):
+                       ("admm_bp_buffers", _lib.BpBuffers), ("admm_peer_comm", _lib.PeerComm)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), txt, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = []
@@ -42,6 +42,7 @@ def test_struct_layout_matches_header(build_lib):
             if not decl:
                 continue
             for part in decl.split(","):
+                part = re.sub(r"\[[^\]]*\]", "", part)          # array members: drop the extent
                 fields.append(re.findall(r"[A-Za-z_0-9]+", part)[-1])
         assert fields == [f[0] for f in cls._fields_], cname
 
@@ -82,3 +83,19 @@ def test_solo_support_query_without_gpu(build_lib):
     assert q(dims(39, 48, 2000, 1, False)) == 0          # padded L must be 16, 40 or 64
     if not torch.cuda.is_available():
         assert q(dims(39, 40, 2000, 6, True)) == 0       # batch-wide over several clusters needs the occupancy query
+
+
+def test_reference_arm_never_maps_the_product_library(build_lib):
+    """`bench.py --impl reference` must time the stock reference with none of this repo's native code in
+    the process (the input generators are loaded by path)."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, ADMM_BENCH_NO_MP="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "spm_cfg2",
+                        "--steps", "1", "--warmup", "0"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["native_so_mapped"] is False
+    assert line["config"]["problems_total"] == 1 and line["cpu_baseline"]["kind"] in ("reference", "port")

@@ -1,8 +1,14 @@
-"""CPU, world_size 2 over gloo: the multi-GPU host logic of the batch-wide criterion.
+"""CPU, world_size 2 over gloo: host-side logic of the sharded batch-wide criterion.
 
-Each rank owns a contiguous slab of the batch (``sharding.shard_range``) and all-reduces the ten
-squared-norm partials every iteration; the result must equal the single-process packed solve
-(identical mu history, iteration count and x on every slab)."""
+  * ``sharding.shard_range`` (contiguous slabs) and ``peer.exchange_handles`` / ``peer.check_one_box`` -- the
+    PRODUCT's bootstrap that carries the CUDA-IPC mailbox handles between the ranks (any ``torch.distributed``
+    backend; gloo here, NCCL on the GPU box) -- driven by two real processes;
+  * the SEMANTICS the device path has to reproduce, stated with the oracle: each rank owns a slab and sums the ten
+    squared-norm partials over the ranks every iteration; the result must equal the single-process packed solve
+    (identical mu history, iteration count and x on every slab).  This second test exercises ``oracle/`` only; the
+    product kernels (``admm_spm_reduce_post`` / ``admm_spm_decide_peer``) are tested against the same golden on the
+    GPU by ``tests/test_sharded_gpu.py`` (world size 1 in-process and two ranks on one GPU).
+"""
 import os
 import sys
 
@@ -36,6 +42,44 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _handle_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from admmsolver_b200 import peer
+    import socket
+    fake = bytes([rank]) * 64                      # stands for the 64-byte cudaIpcMemHandle_t of this rank's mailbox
+    recs = peer.exchange_handles(dist.group.WORLD, (socket.gethostname(), os.getpid(), fake))
+    peer.check_one_box(recs)
+    out[rank] = [(h, pid, bytes(b)) for (h, pid, b) in recs]
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_peer_handle_exchange_over_gloo(build_lib):
+    """The mailbox bootstrap of ``peer.PeerMailbox``: every rank ends up with every rank's handle, in rank order."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29300 + os.getpid() % 1000
+    mp.spawn(_handle_worker, args=(world, port, out), nprocs=world, join=True)
+    assert out[0] == out[1] and len(out[0]) == world
+    for r, (host, pid, h) in enumerate(out[0]):
+        assert h == bytes([r]) * 64
+    assert len({pid for _, pid, _ in out[0]}) == world
+
+
+def test_peer_one_box_checks(build_lib):
+    from admmsolver_b200 import peer
+    peer.check_one_box([("a", 1, b""), ("a", 2, b"")])
+    with pytest.raises(NotImplementedError):
+        peer.check_one_box([("a", 1, b""), ("b", 2, b"")])          # two hosts: no CUDA IPC
+    with pytest.raises(NotImplementedError):
+        peer.check_one_box([("a", 1, b""), ("a", 1, b"")])          # one process cannot map its own handle
+    with pytest.raises(NotImplementedError):
+        peer.check_one_box([("a", i, b"") for i in range(17)])
+
+
 def test_shard_range_partition():
     from admmsolver_b200.sharding import shard_range
     for nb in (0, 1, 7, 8, 1 << 20, 1000003):
@@ -48,7 +92,7 @@ def test_shard_range_partition():
 
 
 @pytest.mark.timeout(300)
-def test_batchwide_allreduce_equals_packed(build_lib):
+def test_oracle_sharded_semantics_equal_packed(build_lib):
     world = 2
     mgr = mp.Manager()
     out = mgr.dict()

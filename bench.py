@@ -501,7 +501,11 @@ def run_workload(args, workload, ctx, steps, warmup, with_clocks):
                         err = max(err, _rel(x0[:, col].cpu().numpy(), x_ref[:, 0]))
                         mu_eq = mu_eq and float(eng.mu10[col]) == mu10_ref and float(eng.mu20[col]) == mu20_ref
                         it_eq = it_eq and int(eng.iters[col]) == int(n_ref)
-                bad = allmax(0.0 if (err <= 1e-10 and mu_eq and it_eq and replicas_equal) else 1.0)
+                # whole columns per CTA (the fused step kernel): a replica must come out bit-identical wherever it sits;
+                # the balanced small-batch decomposition cuts the sampling points of a tile group at position-dependent
+                # places, so there the replicas agree to rounding only (reported, not required)
+                whole_columns = eng.dims.nsplit == 1 and eng.dims.nbal == 0
+                bad = allmax(0.0 if (err <= 1e-10 and mu_eq and it_eq and (replicas_equal or not whole_columns)) else 1.0)
                 parity = {"max_rel_x0": allmax(err), "tolerance": 1e-10, "mu_equal": allmax(0.0 if mu_eq else 1.0) == 0.0,
                           "iterations_equal": allmax(0.0 if it_eq else 1.0) == 0.0,
                           "replicas_bit_identical": allmax(0.0 if replicas_equal else 1.0) == 0.0,

@@ -238,20 +238,23 @@ def cpu_multiprocess(kind: str, per_proc: int, niter: int):
             f"{nproc} single-threaded processes x {per_proc} {what} x {niter} iterations, {wall:.2f} s", nproc)
 
 
-def cpu_baseline_for(workload: str):
+def cpu_baseline_for(workload: str, scale: int = 1):
     """Bounded sample of the workload on all host threads (torchrun pins OMP_NUM_THREADS=1: undo it).
-    Returns (value, kind, sample, threads actually used by the BLAS pool)."""
+    Returns (value, kind, sample, threads actually used by the BLAS pool).  ``scale`` multiplies the iterations of
+    the sample: 1 for the repeated steps of the reference arm (a few seconds each), 4 for the one-off ``cpu_baseline``
+    leg of our arm (10-30 s of CPU work)."""
     try:
         from threadpoolctl import threadpool_limits
         with threadpool_limits(limits=len(os.sched_getaffinity(0))):
-            one = _cpu_baseline_for(workload) + (host_threads(),)
+            one = _cpu_baseline_for(workload, scale) + (host_threads(),)
     except ImportError:
-        one = _cpu_baseline_for(workload) + (host_threads(),)
+        one = _cpu_baseline_for(workload, scale) + (host_threads(),)
     # batched workloads: also one single-threaded process per core; the faster of the two is the baseline
     if workload in ("spm_sweep", "spm_cfg3", "bp_cfg4") and len(os.sched_getaffinity(0)) > 1 \
             and not os.environ.get("ADMM_BENCH_NO_MP"):
         try:
-            many = cpu_multiprocess("spm", 64, 20) if workload.startswith("spm") else cpu_multiprocess("bp", 2, 200)
+            many = (cpu_multiprocess("spm", 64, 20 * scale) if workload.startswith("spm")
+                    else cpu_multiprocess("bp", 4, 200 * scale))
             if many[0] > one[0]:
                 return (many[0], many[1], many[2] + " (one multi-threaded process: %.0f)" % one[0], many[3])
             return (one[0], one[1], one[2] + " (one single-threaded process per core: %.0f)" % many[0], one[3])
@@ -260,14 +263,14 @@ def cpu_baseline_for(workload: str):
     return one
 
 
-def _cpu_baseline_for(workload: str):
+def _cpu_baseline_for(workload: str, scale: int = 1):
     if workload in ("spm_sweep", "spm_cfg3"):
-        return cpu_spm_sample(1024, 20)
+        return cpu_spm_sample(1024, 10 * scale)
     if workload == "spm_cfg2":
-        return cpu_spm_sample(1, 400)
+        return cpu_spm_sample(1, 400 * scale)
     if workload == "bp_cfg4":
-        return cpu_bp_sample(16, 400, 128, 512, 10)
-    return cpu_bp_sample(1, 600, 200, 1000, 10)
+        return cpu_bp_sample(16, 200 * scale, 128, 512, 10)
+    return cpu_bp_sample(1, 600 * scale, 200, 1000, 10)
 
 
 def host_threads() -> int:
@@ -752,7 +755,7 @@ def run_workload(args, workload, ctx, steps, warmup, with_clocks):
 
     cpu = None
     if not args.no_cpu_baseline:
-        v, kind, sample, cores = cpu_baseline_for(workload)
+        v, kind, sample, cores = cpu_baseline_for(workload, scale=4)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
 
     return {

@@ -44,7 +44,7 @@ class SpmBuffers(C.Structure):
         ("last_res", _P), ("Dre", _P),
         ("b0", _P), ("x0", _P), ("x1", _P), ("h10", _P), ("y0", _P), ("x0_old", _P), ("V", _P), ("aim", _P),
         ("S", _P),
-        ("normsA", _P), ("normsB", _P), ("gsum", _P), ("gpart", _P),
+        ("normsA", _P), ("normsB", _P), ("gsum", _P), ("gpart", _P), ("cta_partA", _P), ("cta_partB", _P), ("lazy", _P),
         ("iter_counter", _P), ("flags", _P), ("history", _P), ("hist_cap", C.c_int),
         ("lam", C.c_double), ("rtol", C.c_double), ("max_mu", C.c_double),
         ("fact_incr", C.c_double), ("th_change", C.c_double),
@@ -109,6 +109,10 @@ _SIGS = {
     "admm_peer_free": ([_P], _I),
     "admm_spm_reduce_post": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), C.POINTER(PeerComm), _P], _I),
     "admm_spm_decide_peer": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), C.POINTER(PeerComm), _I, _P], _I),
+    "admm_spm_step_lazy": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), C.POINTER(PeerComm), _I, _P], _I),
+    "admm_spm_xupdate_lazy": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), C.POINTER(PeerComm), _I, _P], _I),
+    "admm_spm_pass_lazy": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), C.POINTER(PeerComm), _P], _I),
+    "admm_spm_flush": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), C.POINTER(PeerComm), _P], _I),
     "admm_spm_solo_supported": ([C.POINTER(SpmDims)], _I),
     "admm_spm_solo": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _P, _P, _I, _I, _P], _I),
     "admm_bp_supported": ([_I, _I], _I),

@@ -228,6 +228,15 @@ class SharedSpM:
         self.normsB = z(nsplit * nct * 8 * 2)
         self.gsum = z(16)
         self.gpart = z(256 * 16)
+        # lazy batch-wide iterations (one launch per iteration: reduction in the tail of the step / pass kernel, decision
+        # in the head of the next one): per-CTA partial sums and the control words
+        ngrp = -(-npt // gt)
+        n_pass = nbal if nbal > 0 else ngrp * nsplit
+        self.cta_partA = z(max(ngrp, -(-nct // 4)) * 10)
+        self.cta_partB = z(n_pass * 2)
+        self.lazy = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.use_lazy = True          # tests switch it off to compare with the three-kernel iteration
+        self._lazy_pending = False    # a launched lazy iteration still awaits its decision (next kernel's head or flush)
         self.iter_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.flags = torch.zeros(4, dtype=torch.int32, device=dev)
         self.history = None
@@ -249,7 +258,8 @@ class SharedSpM:
                         ("iters", self.iters), ("last_res", self.last_res), ("Dre", self.Dre), ("b0", self.b0),
                         ("x0", self.x0f), ("x1", self.x1f), ("h10", self.h10f), ("y0", self.y0f), ("V", self.V),
                         ("aim", self.aim), ("S", self.S), ("normsA", self.normsA), ("normsB", self.normsB), ("gsum", self.gsum),
-                        ("gpart", self.gpart), ("iter_counter", self.iter_counter), ("flags", self.flags)):
+                        ("gpart", self.gpart), ("cta_partA", self.cta_partA), ("cta_partB", self.cta_partB),
+                        ("lazy", self.lazy), ("iter_counter", self.iter_counter), ("flags", self.flags)):
             setattr(b, name, t.data_ptr())
         b.x0_old = self.x0_oldf.data_ptr() if self.x0_oldf is not None else None
         b.history = self.history.data_ptr() if self.history is not None else None
@@ -465,8 +475,24 @@ class SharedSpM:
         self._refresh_slots()
 
     # ------------------------------------------------------------------ iteration
-    def _iteration(self, do_update_mu: bool) -> None:
+    def _lazy_ok(self) -> bool:
+        """Batch-wide criterion without NCCL between the kernels: plain iterations are ONE launch (fused path) or two."""
+        return self.batch_wide and self.use_lazy and (self.group is None or self._peer is not None)
+
+    def _comm_ref(self):
+        return C.byref(self._peer.comm) if self._peer is not None else None
+
+    def _flush(self) -> None:
+        """Take the pending decision of the last lazy iteration (history, iteration count, stopping test)."""
+        if self._lazy_pending:
+            call("admm_spm_flush", C.byref(self.dims), C.byref(self.bufs), self._comm_ref(), stream())
+            self._lazy_pending = False
+
+    def _iteration(self, do_update_mu: bool, allow_lazy: bool = True) -> None:
         dref, bref, st = C.byref(self.dims), C.byref(self.bufs), stream()
+        lazy = allow_lazy and not do_update_mu and self._lazy_ok()
+        if not lazy:
+            self._flush()
         if not self._v_valid:
             # V = P^T(h20 + mu20 x2) from the current state (after set_state or a change of mu20)
             call("admm_spm_pass", dref, bref, 1, st)
@@ -477,7 +503,25 @@ class SharedSpM:
         timed = self.pass_events is not None and not do_update_mu
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if self.dims.nsplit == 1 and self.dims.nbal == 0:
+        fused = self.dims.nsplit == 1 and self.dims.nbal == 0
+        if lazy:
+            # the whole iteration: decision of the previous one in the head, reduction of this one in the tail
+            cref, pend = self._comm_ref(), int(self._lazy_pending)
+            if fused:
+                if timed:
+                    e0.record()
+                call("admm_spm_step_lazy", dref, bref, cref, pend, st)
+            else:
+                call("admm_spm_xupdate_lazy", dref, bref, cref, pend, st)
+                if timed:
+                    e0.record()
+                call("admm_spm_pass_lazy", dref, bref, cref, st)
+            if timed:
+                e1.record()
+                self.pass_events.append((e0, e1))
+            self._lazy_pending = True
+            return
+        if fused:
             if timed:
                 e0.record()
             call("admm_spm_step", dref, bref, st)
@@ -505,6 +549,7 @@ class SharedSpM:
     def _after_update_iteration(self) -> bool:
         """Host look at the device flags after an iteration that may have changed mu or finished
         problems.  Returns True when every problem is done."""
+        self._flush()
         fl = self.flags.cpu()
         if int(fl[2]) == -2:
             raise _lib.AdmmError("sharded batch-wide criterion: a peer rank never posted its residual sums "
@@ -542,6 +587,8 @@ class SharedSpM:
         self.done[:nb] = 0
         self.flags.zero_()
         self.iter_counter.zero_()
+        self.lazy.zero_()
+        self._lazy_pending = False
         track = (self.batch_wide or nb == 1) if keep_history is None else keep_history
         if track:
             if self.history is None or self.history.shape[0] < niter:
@@ -584,7 +631,7 @@ class SharedSpM:
             upd = (it % interval_update_mu == 0)
             run = 1 if upd else min(niter, (it // interval_update_mu + 1) * interval_update_mu) - it
             if upd or callback is not None or not use_graph or run < 4:
-                self._iteration(upd)
+                self._iteration(upd, allow_lazy=callback is None)
                 run = 1
             else:
                 self._replay_plain(run, key)
@@ -595,6 +642,13 @@ class SharedSpM:
             if upd or callback is not None or it >= niter:
                 if self._after_update_iteration():
                     break
+        self._flush()
+        if self._lazy_ok() and not use_solo:
+            # lazy iterations maintain entry 0 of the per-problem bookkeeping only: the batch shares it
+            self.iters[:nb] = self.iters[0]
+            self.last_res[:nb] = self.last_res[0]
+            if int(self.lazy[2].item()) != 0:
+                self.done[:nb] = 1
         if track:
             ndone = solo_iters0 if use_solo else int(self.iters[0].item())
             hist = self.history[:ndone].cpu().numpy()
@@ -614,6 +668,7 @@ class SharedSpM:
         # graphs of GRAPH_CHUNK iterations, replayed as often as they fit (capturing and instantiating one graph of
         # all ~interval iterations costs 50-800 ms on the first solve of a plan -- more than a short solve itself);
         # the few iterations left over are launched eagerly
+        lazy = self._lazy_ok()
         while run > 0:
             n = min(run, self.GRAPH_CHUNK)
             if n < 8:
@@ -621,7 +676,8 @@ class SharedSpM:
                     self._iteration(False)
                 run -= n
                 continue
-            graph = self._graphs.get((n, key))
+            self._flush()                           # a captured chunk starts without and ends without a pending decision
+            graph = self._graphs.get((n, key, lazy))
             if graph is None:
                 if len(self._graphs) >= 8:
                     self._graphs.clear()
@@ -630,14 +686,17 @@ class SharedSpM:
                 with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     for _ in range(n):
                         self._iteration(False)
+                    self._flush()
                 _lib.launch_count = before          # capture enqueues nothing
-                self._graphs[(n, key)] = graph
+                self._graphs[(n, key, lazy)] = graph
             graph.replay()
-            _lib.launch_count += n * self._launches_per_iteration()
+            _lib.launch_count += n * self._launches_per_iteration() + (1 if lazy else 0)
             run -= n
 
     def _launches_per_iteration(self) -> int:
         data = 1 if (self.dims.nsplit == 1 and self.dims.nbal == 0) else 2
+        if self._lazy_ok():
+            return data
         if self.batch_wide and (self.group is None or self._peer is not None):
             return data + 2
         return data + (2 if self.batch_wide else 0) + 1

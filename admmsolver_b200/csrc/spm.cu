@@ -244,6 +244,182 @@ __global__ void __launch_bounds__(256) spm_factor_kernel(admm_spm_dims d, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// batch-wide criterion: peer mailboxes and the "lazy" decision folded into the iteration kernels
+// ---------------------------------------------------------------------------------------------
+// Mailbox word = (seq << 32) | 32-bit half of a double: one atomic 8-byte store carries data and validity
+// (the receiver polls the word itself -- one-way NVLink latency, no fence, no separate flag).
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+constexpr int PEER_WORDS = 20;        // ten doubles as 32-bit halves
+constexpr int PEER_SLOT = 32;         // words per (buffer, source rank) slot of a mailbox
+constexpr long long PEER_TIMEOUT = 10000000000LL;   // ~5 s of clock64: a peer died, give up instead of hanging the GPU
+
+// push the ten sums gs[] (shared memory) into every rank's mailbox under sequence number seq; all threads of the CTA
+__device__ __forceinline__ void peer_post(const admm_peer_comm& c, const double* gs, unsigned seq) {
+  for (int i = threadIdx.x; i < PEER_WORDS * c.world; i += blockDim.x) {
+    const int peer = i / PEER_WORDS, k = i - peer * PEER_WORDS;
+    const double val = gs[k >> 1];
+    const unsigned half = (k & 1) ? (unsigned)__double2hiint(val) : (unsigned)__double2loint(val);
+    unsigned long long* box = c.mbox[peer] + ((size_t)(seq & 1u) * ADMM_MAX_PEERS + c.rank) * PEER_SLOT + k;
+    st_relaxed_sys_u64(box, ((unsigned long long)seq << 32) | half);
+  }
+}
+
+// sum number i (< 10) of ALL ranks for sequence seq from the local mailbox, added in rank order; false: timed out
+__device__ __forceinline__ bool peer_gather(const admm_peer_comm& c, unsigned seq, int i, double& out) {
+  const unsigned long long* box = c.mbox[c.rank] + (size_t)(seq & 1u) * ADMM_MAX_PEERS * PEER_SLOT + 2 * i;
+  const long long t0 = clock64();
+  while (true) {
+    bool ok = true;
+    double a = 0.0;
+#pragma unroll
+    for (int r = 0; r < ADMM_MAX_PEERS; ++r) {        // independent loads: all in flight at once
+      if (r < c.world) {
+        const unsigned long long lo = ld_relaxed_sys_u64(box + r * PEER_SLOT), hi = ld_relaxed_sys_u64(box + r * PEER_SLOT + 1);
+        ok = ok && (unsigned)(lo >> 32) == seq && (unsigned)(hi >> 32) == seq;
+        a += __hiloint2double((int)(unsigned)hi, (int)(unsigned)lo);
+      }
+    }
+    if (ok) {
+      out = a;
+      return true;
+    }
+    if (clock64() - t0 > PEER_TIMEOUT) return false;
+  }
+}
+
+// residual() and check_convergence() (optimizer.py:232-274) from the ten squared norms; 0/0 -> NaN -> not converged
+__device__ __forceinline__ bool residual_conv(const double (&s)[10], double mu10, double mu20, double rtol, double& primal,
+                                              double& dual, double (&parts)[4]) {
+  const double p10 = sqrt(s[0]), nx0 = sqrt(s[1]), nx1 = sqrt(s[2]), nd = sqrt(s[3]), nxo = sqrt(s[4]);
+  const double nPd = sqrt(s[5]), nPxo = sqrt(s[6]), p20 = sqrt(s[7]), nx2 = sqrt(s[8]), nPx0 = sqrt(s[9]);
+  const double d10 = mu10 * nd, d20 = mu20 * nPd;
+  primal = p10 + p20;
+  dual = d10 + d20;
+  parts[0] = p10;
+  parts[1] = d10;
+  parts[2] = p20;
+  parts[3] = d20;
+  return (p10 / fmax(nx0, nx1) < rtol) && (d10 / fmax(mu10 * nx0, mu10 * nxo) < rtol) &&
+         (p20 / fmax(nPx0, nx2) < rtol) && (d20 / fmax(mu20 * nPx0, mu20 * nPxo) < rtol);
+}
+
+// Head of a lazy iteration kernel: the decision of the PREVIOUS iteration.  Every CTA evaluates it redundantly and
+// identically; true = the batch has converged, the caller returns without touching the state.  All threads of the CTA.
+__device__ __forceinline__ bool lazy_head(const admm_spm_dims& d, const admm_spm_buffers& b, const admm_peer_comm& c, int pending) {
+  if (__ldcg(b.lazy + 2) != 0) return true;             // converged in an earlier kernel
+  if (!pending) return false;
+  __shared__ double lz_gs[10];
+  __shared__ int lz_fail;
+  const int tid = threadIdx.x;
+  if (tid == 0) lz_fail = 0;
+  __syncthreads();
+  if (tid < 10) {
+    if (c.world == 0) {
+      lz_gs[tid] = __ldcg(b.gsum + tid);                // left by the last CTA of the previous kernel
+    } else {
+      double a = 0.0;
+      if (!peer_gather(c, c.ctrl[0], tid, a)) lz_fail = 1;
+      lz_gs[tid] = a;
+    }
+  }
+  __syncthreads();
+  const bool first_cta = blockIdx.x == 0 && blockIdx.y == 0;
+  if (lz_fail) {
+    if (first_cta && tid == 0) b.flags[2] = -2;
+    return true;
+  }
+  double s[10], parts[4], primal, dual;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) s[i] = lz_gs[i];
+  const bool conv = residual_conv(s, b.mu10[0], b.mu20[0], b.rtol, primal, dual, parts);
+  if (first_cta && tid == 0) {
+    const int it = b.iters[0];
+    if (b.history && it < b.hist_cap) {
+      b.history[2 * it] = primal;
+      b.history[2 * it + 1] = dual;
+    }
+    b.iters[0] = it + 1;
+    b.iter_counter[0] = it + 1;
+    b.last_res[0] = primal;
+    b.last_res[1] = dual;
+    if (conv) {
+      b.flags[1] = d.nb;
+      __threadfence();
+      b.lazy[2] = 1;
+    }
+  }
+  return conv;
+}
+
+// Tail of a lazy iteration kernel.  `mine` (shared memory, [nwarps][10]) holds the partial sums of this CTA's warps;
+// they go to cta_partA (x-update stage or fused kernel: all ten) or cta_partB (pass of the unfused path: entries 7, 8).
+// `ticketed`: this kernel closes the iteration -- the CTA that arrives last adds all nA + nB CTA partials in a fixed
+// order and publishes the batch-wide sums (gsum, or the peers' mailboxes).  All threads of the CTA.
+__device__ __forceinline__ void lazy_tail(const admm_spm_buffers& b, const admm_peer_comm& c, double* mine, int nwarps,
+                                          bool to_A, bool ticketed, int nA, int nB) {
+  __shared__ int lz_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cta = blockIdx.y * gridDim.x + blockIdx.x, ncta = gridDim.x * gridDim.y;
+  __syncthreads();
+  if (tid < 10) {
+    double a = 0.0;
+    for (int w = 0; w < nwarps; ++w) a += mine[w * 10 + tid];
+    if (to_A) __stcg(b.cta_partA + (size_t)cta * 10 + tid, a);
+    else if (tid == 7 || tid == 8) __stcg(b.cta_partB + (size_t)cta * 2 + (tid - 7), a);
+  }
+  if (!ticketed) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) lz_last = (atomicAdd(reinterpret_cast<unsigned*>(b.lazy), 1u) == (unsigned)(ncta - 1));
+  __syncthreads();
+  if (!lz_last) return;
+  __threadfence();
+  double v[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) v[i] = 0.0;
+  for (int i = tid; i < nA; i += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < 10; ++k) v[k] += __ldcg(b.cta_partA + (size_t)i * 10 + k);
+  }
+  for (int i = tid; i < nB; i += blockDim.x) {
+    v[7] += __ldcg(b.cta_partB + (size_t)i * 2);
+    v[8] += __ldcg(b.cta_partB + (size_t)i * 2 + 1);
+  }
+#pragma unroll
+  for (int i = 0; i < 10; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) mine[warp * 10 + i] = v[i];
+  }
+  __syncthreads();
+  double tot = 0.0;
+  if (tid < 10) {
+    for (int w = 0; w < nwarps; ++w) tot += mine[w * 10 + tid];
+  }
+  __syncthreads();
+  if (tid < 10) {
+    mine[tid] = tot;
+    b.gsum[tid] = tot;
+  }
+  __syncthreads();
+  if (c.world > 0) {
+    const unsigned seq = c.ctrl[0] + 1u;
+    __syncthreads();
+    peer_post(c, mine, seq);
+    if (tid == 0) c.ctrl[0] = seq;
+  }
+  if (tid == 0) b.lazy[0] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // x-update of ONE problem tile (8 problems, all planes) by one warp, everything in fragment layout
 // ---------------------------------------------------------------------------------------------
 // out[p][c][l'] = sum_l a[p][c][l] * B[l][l']  for NP planes that share the B fragments
@@ -278,9 +454,11 @@ __device__ __forceinline__ void frag_gemm(double (&out)[NP][NT][2], const double
 // y0 = P^T P x0_old must be current (spm_refresh_y_kernel after a state change).
 // Returns false when every problem of the tile is frozen (nothing was touched, x0 not loaded).
 // Handles planes p0 .. p0+NP-1 of the tile (plane 0 = real, plane 1 = imaginary parts).
+// wpart != NULL (lazy batch-wide iterations): instead of per-problem norms in normsA, the sums over the tile's live
+// problems are added to wpart[0..9] (this warp's row of the CTA's partial sums, indexed like gather_problem's s[]).
 template <int NT, int NP, bool SPLIT>   // SPLIT: V arrives as d.nsplit partial sums (unfused small-batch path)
 __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_spm_buffers& b, int pt, int lane,
-                                             int p0 = 0) {
+                                             int p0 = 0, double* wpart = nullptr) {
   const int g = lane >> 2, t = lane & 3;
   const int prob = 8 * pt + g;
   const int is_done = b.done[prob];
@@ -444,7 +622,24 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
     nPd = quad_sum(nPd);
     nPxo = quad_sum(nPxo);
     nPx = quad_sum(nPx);
-    if (t == 0 && !is_done) {
+    if (wpart != nullptr) {
+      // sum over the 8 problems of the tile (every lane of a quad holds its problem's value: combine across quads)
+      double nv[8] = {n_p, n_x0, n_x1, n_d, n_xo, nPd > 0.0 ? nPd : 0.0, nPxo > 0.0 ? nPxo : 0.0, nPx > 0.0 ? nPx : 0.0};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        double v = is_done ? 0.0 : nv[i];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        nv[i] = v;
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) wpart[i] += nv[i];
+        wpart[9] += nv[7];                           // |P x0|^2 (Gram form), both planes
+        if (p0 + p == 1) wpart[7] += nv[7];          // |P Im(x0) - 0|^2
+      }
+    } else if (t == 0 && !is_done) {
       double* nrm = b.normsA + ((size_t)(ct0 + p) * 8 + g) * 8;
       nrm[0] = n_p;
       nrm[1] = n_x0;
@@ -461,13 +656,24 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
 
 // Stand-alone x-update (small batches): one warp per (problem tile, plane) -- the kernel is a chain of
 // dependent loads and two small GEMMs, so more, shorter warps finish sooner than fewer, longer ones.
+// lazy: 0 classic (per-problem norms, the reduce/decide kernels follow), 1 lazy iteration without, 2 with a pending
+// decision of the previous iteration (see lazy_head / lazy_tail)
 template <int NT>
-__global__ void __launch_bounds__(128) spm_xupdate_kernel(admm_spm_dims d, admm_spm_buffers b) {
+__global__ void __launch_bounds__(128) spm_xupdate_kernel(admm_spm_dims d, admm_spm_buffers b, admm_peer_comm c, int lazy) {
   pdl_prologue();
+  __shared__ double wsum[4 * 10];
+  if (d.batch_wide && b.lazy != nullptr) {
+    if (lazy ? lazy_head(d, b, c, lazy == 2) : (__ldcg(b.lazy + 2) != 0)) return;
+  }
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= d.npt * d.nplanes) return;
-  xupdate_tile<NT, 1, true>(d, b, warp / d.nplanes, lane, warp % d.nplanes);
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  if (lazy) {
+    if (lane < 10) wsum[wl * 10 + lane] = 0.0;
+    __syncwarp();
+  }
+  if (warp < d.npt * d.nplanes)
+    xupdate_tile<NT, 1, true>(d, b, warp / d.nplanes, lane, warp % d.nplanes, lazy ? wsum + wl * 10 : nullptr);
+  if (lazy) lazy_tail(b, c, wsum, 4, true, false, 0, 0);
 }
 
 // y0 = P^T P x0 for every column tile (after the state was loaded from outside)
@@ -522,10 +728,19 @@ struct PassSmem {
 //     straddle a group boundary, then it finishes the first group (epilogue) and starts the next.
 // Either way the partial V / norm sums of (group, piece) go to split slot `piece`; slots a group does
 // not use stay zero, the x-update sums all d.nsplit of them.
+// lazy (batch-wide criterion, MODE == PASS_STEP): 0 classic (per-problem norms, the reduce/decide kernels follow);
+// 1 / 2: lazy iteration without / with a pending decision of the previous iteration (lazy_head / lazy_tail); nA = CTAs
+// of the stand-alone x-update kernel whose partial sums the last CTA of this pass adds (unfused path).
 template <int NT, int MT, int MODE, int FNP>   // FNP: 0 = pass only, 1/2 = fused x-update of 1/2 planes
 __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
-    spm_pass_kernel(admm_spm_dims d, admm_spm_buffers b) {
+    spm_pass_kernel(admm_spm_dims d, admm_spm_buffers b, admm_peer_comm c, int lazy, int nA) {
   pdl_prologue();
+  __shared__ double wsum[PASS_WARPS * 10];        // lazy: partial sums of the ten squared norms, one row per warp
+  if (MODE == PASS_STEP && d.batch_wide && b.lazy != nullptr) {
+    // the fused kernel opens the iteration (decision of the previous one); the stand-alone pass follows the x-update
+    // kernel, which has taken it already
+    if ((lazy && FNP != 0) ? lazy_head(d, b, c, lazy == 2) : (__ldcg(b.lazy + 2) != 0)) return;
+  }
   using SM = PassSmem<NT, MT>;
   constexpr int TILE_D = SM::TILE_D, CHUNK_D = SM::CHUNK_D, STATE_D = SM::STATE_D, STAGE_D = SM::STAGE_D;
   constexpr unsigned CHUNK_BYTES = CHUNK_D * sizeof(double), STATE_BYTES = STATE_D * sizeof(double);
@@ -565,6 +780,7 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
     }
     fence_barrier_init();
   }
+  if (MODE == PASS_STEP && lazy && lane < 10) wsum[warp * 10 + lane] = 0.0;      // (own row: ordered by program order per warp)
   __syncthreads();
   if (tid == 0) {
     for (int s = 0; s < PASS_STAGES && s < nchunks; ++s) fill(s, g_begin + s);
@@ -576,6 +792,7 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
     // The L-vectors of the tiles are pulled into L2 up front (one bulk prefetch per vector).
     constexpr int NPL = FNP == 0 ? 1 : FNP;
     const int wpt0 = (blockIdx.x * PASS_WARPS + warp) * MT;
+    double* wp = lazy ? wsum + warp * 10 : nullptr;
     {
       const double* vec = lane == 0 ? b.b0 : lane == 1 ? b.h10 : lane == 2 ? b.x1 : lane == 3 ? b.V
                         : lane == 4 ? b.x0 : lane == 5 ? b.y0 : b.aim;
@@ -585,7 +802,7 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
     }
 #pragma unroll 1
     for (int m = 0; m < MT; ++m) {
-      if (wpt0 + m < d.npt) xupdate_tile<NT, NPL, false>(d, b, wpt0 + m, lane, 0);
+      if (wpt0 + m < d.npt) xupdate_tile<NT, NPL, false>(d, b, wpt0 + m, lane, 0, wp);
     }
   }
 
@@ -756,7 +973,20 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
         if (MODE == PASS_STEP) {
           const double inv = 1.0 / mu20[m];
           const double s0 = quad_sum(n_dh[m]) * inv * inv, s1 = quad_sum(n_xm[m]) * inv * inv;
-          if (t == 0 && !dn[m]) {
+          if (lazy) {
+            double a0 = dn[m] ? 0.0 : s0, a1 = dn[m] ? 0.0 : s1;      // sum over the tile's live problems (across quads)
+#pragma unroll
+            for (int o = 4; o <= 16; o <<= 1) {
+              a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+              a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            }
+            if (lane == 0) {
+              wsum[warp * 10 + 7] += a0;      // |P Re(x0) - x2|^2
+              wsum[warp * 10 + 8] += a1;      // |x2|^2
+            }
+            // the decide kernel is not run: record the mu20 this pass encoded x2 with
+            if (t == 0 && !dn[m]) b.mu20_used[8 * pt[m] + g] = mu20[m];
+          } else if (t == 0 && !dn[m]) {
             double* o = b.normsB + ((size_t)piece * nctc * 8 + (size_t)(pt[m] * npl) * 8 + g) * 2;
             o[0] = s0;      // |P Re(x0) - x2|^2
             o[1] = s1;      // |x2|^2
@@ -764,6 +994,10 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
         }
       }
     }
+  }
+  if (MODE == PASS_STEP && lazy) {
+    const int ncta = gridDim.x * gridDim.y;
+    lazy_tail(b, c, wsum, PASS_WARPS, FNP != 0, true, FNP != 0 ? ncta : nA, FNP != 0 ? 0 : ncta);
   }
 }
 
@@ -874,6 +1108,7 @@ __device__ __forceinline__ void decide_one(const admm_spm_dims& d, const admm_sp
 __global__ void __launch_bounds__(128) spm_decide_kernel(admm_spm_dims d, admm_spm_buffers b, int do_update_mu, int nparts) {
   pdl_prologue();
   __shared__ double gs[10];
+  if (d.batch_wide && b.lazy != nullptr && __ldcg(b.lazy + 2) != 0) return;      // converged in a lazy iteration
   if (nparts > 0) {
     if (threadIdx.x < 10) {
       double a = 0.0;
@@ -899,24 +1134,11 @@ __global__ void __launch_bounds__(128) spm_decide_kernel(admm_spm_dims d, admm_s
 // ---------------------------------------------------------------------------------------------
 // sharded batch, batch-wide criterion: one-shot all-reduce of the ten sums over peer-mapped memory
 // ---------------------------------------------------------------------------------------------
-// Mailbox word = (seq << 32) | 32-bit half of a double: one atomic 8-byte store carries data and validity
-// (the receiver polls the word itself -- one-way NVLink latency, no fence, no separate flag).
-__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-constexpr int PEER_WORDS = 20;        // ten doubles as 32-bit halves
-constexpr int PEER_SLOT = 32;         // words per (buffer, source rank) slot of a mailbox
-
 // Stage 1 of the batch-wide sum; the CTA that finishes last adds the partials in a fixed order and pushes the
 // ten sums to every rank's mailbox (its own included) under sequence number ctrl[0] + 1.
 __global__ void __launch_bounds__(256) spm_reduce_post_kernel(admm_spm_dims d, admm_spm_buffers b, admm_peer_comm c) {
   pdl_prologue();
+  if (b.lazy != nullptr && __ldcg(b.lazy + 2) != 0) return;      // converged in a lazy iteration (on every rank alike)
   __shared__ double scratch[10 * 32];
   __shared__ double gs[10];
   __shared__ int last;
@@ -963,13 +1185,7 @@ __global__ void __launch_bounds__(256) spm_reduce_post_kernel(admm_spm_dims d, a
     gs[tid] = mine;
   }
   __syncthreads();
-  for (int i = tid; i < PEER_WORDS * c.world; i += blockDim.x) {
-    const int peer = i / PEER_WORDS, k = i - peer * PEER_WORDS;
-    const double val = gs[k >> 1];
-    const unsigned half = (k & 1) ? (unsigned)__double2hiint(val) : (unsigned)__double2loint(val);
-    unsigned long long* box = c.mbox[peer] + ((size_t)(seq & 1u) * ADMM_MAX_PEERS + c.rank) * PEER_SLOT + k;
-    st_relaxed_sys_u64(box, ((unsigned long long)seq << 32) | half);
-  }
+  peer_post(c, gs, seq);
   if (tid == 0) {
     c.ctrl[1] = 0u;
     c.ctrl[0] = seq;
@@ -981,6 +1197,7 @@ __global__ void __launch_bounds__(256) spm_reduce_post_kernel(admm_spm_dims d, a
 __global__ void __launch_bounds__(128) spm_decide_peer_kernel(admm_spm_dims d, admm_spm_buffers b, admm_peer_comm c,
                                                               int do_update_mu) {
   pdl_prologue();
+  if (b.lazy != nullptr && __ldcg(b.lazy + 2) != 0) return;      // converged in a lazy iteration (on every rank alike)
   __shared__ unsigned w32[ADMM_MAX_PEERS * PEER_WORDS];
   __shared__ double gs[10];
   __shared__ int fail;
@@ -997,7 +1214,7 @@ __global__ void __launch_bounds__(128) spm_decide_peer_kernel(admm_spm_dims d, a
     while (true) {
       v = ld_relaxed_sys_u64(p);
       if ((unsigned)(v >> 32) == seq) break;
-      if (clock64() - t0 > 10000000000LL) {       // a peer died: give up after ~5 s instead of hanging the GPU
+      if (clock64() - t0 > PEER_TIMEOUT) {       // a peer died: give up after ~5 s instead of hanging the GPU
         fail = 1;
         break;
       }
@@ -1024,6 +1241,12 @@ __global__ void __launch_bounds__(128) spm_decide_peer_kernel(admm_spm_dims d, a
 #pragma unroll
   for (int i = 0; i < 10; ++i) s[i] = gs[i];
   decide_one(d, b, prob, s, do_update_mu);
+}
+
+// the pending decision of the last lazy iteration (head logic alone)
+__global__ void __launch_bounds__(128) spm_lazy_flush_kernel(admm_spm_dims d, admm_spm_buffers b, admm_peer_comm c) {
+  pdl_prologue();
+  lazy_head(d, b, c, 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1842,8 +2065,14 @@ static bool use_pdl() {
 
 static int ew_grid(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 16)); }
 
+struct LazyArgs {          // how a pass / step launch takes part in the lazy batch-wide scheme (all zero: classic)
+  admm_peer_comm comm;     // world == 0: one rank, the sums go through gsum
+  int lazy;                // 0 classic, 1 lazy without, 2 lazy with a pending decision
+  int nA;                  // CTAs of the stand-alone x-update kernel (unfused path)
+};
+
 template <int NT, int MT, int MODE, int FNP>
-static int launch_pass_k(const admm_spm_dims* d, const admm_spm_buffers* b, cudaStream_t s) {
+static int launch_pass_k(const admm_spm_dims* d, const admm_spm_buffers* b, cudaStream_t s, const LazyArgs& lz) {
   const dim3 grid = d->nbal > 0 ? dim3(d->nbal, 1) : dim3(ceil_div(d->npt, PASS_WARPS * MT), d->nsplit);
   const size_t smem = PassSmem<NT, MT>::BYTES;
   auto k = spm_pass_kernel<NT, MT, MODE, FNP>;
@@ -1854,28 +2083,42 @@ static int launch_pass_k(const admm_spm_dims* d, const admm_spm_buffers* b, cuda
     cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cfgd = true;
   }
-  launch_pdl(k, grid, dim3(PASS_WARPS * 32), smem, s, use_pdl(), *d, *b);
+  launch_pdl(k, grid, dim3(PASS_WARPS * 32), smem, s, use_pdl(), *d, *b, lz.comm, lz.lazy, lz.nA);
   return check_launch(FNP ? "admm_spm_step" : "admm_spm_pass");
 }
 
 template <int NT, int MT>
-static int launch_pass_mode(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, bool fused, cudaStream_t s) {
+static int launch_pass_mode(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, bool fused, cudaStream_t s,
+                            const LazyArgs& lz) {
   if (fused) {
-    return d->nplanes == 2 ? launch_pass_k<NT, MT, PASS_STEP, 2>(d, b, s) : launch_pass_k<NT, MT, PASS_STEP, 1>(d, b, s);
+    return d->nplanes == 2 ? launch_pass_k<NT, MT, PASS_STEP, 2>(d, b, s, lz) : launch_pass_k<NT, MT, PASS_STEP, 1>(d, b, s, lz);
   }
-  if (mode == PASS_STEP) return launch_pass_k<NT, MT, PASS_STEP, 0>(d, b, s);
-  return launch_pass_k<NT, MT, PASS_VINIT, 0>(d, b, s);
+  if (mode == PASS_STEP) return launch_pass_k<NT, MT, PASS_STEP, 0>(d, b, s, lz);
+  return launch_pass_k<NT, MT, PASS_VINIT, 0>(d, b, s, lz);
 }
 
-static int launch_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, bool fused, cudaStream_t s) {
+static int launch_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, bool fused, cudaStream_t s,
+                       const LazyArgs& lz = LazyArgs()) {
   switch (d->Lp / 8) {
     case 2:
-      return d->mt == 2 ? launch_pass_mode<2, 2>(d, b, mode, fused, s) : launch_pass_mode<2, 1>(d, b, mode, fused, s);
+      return d->mt == 2 ? launch_pass_mode<2, 2>(d, b, mode, fused, s, lz) : launch_pass_mode<2, 1>(d, b, mode, fused, s, lz);
     case 5:
-      return d->mt == 2 ? launch_pass_mode<5, 2>(d, b, mode, fused, s) : launch_pass_mode<5, 1>(d, b, mode, fused, s);
+      return d->mt == 2 ? launch_pass_mode<5, 2>(d, b, mode, fused, s, lz) : launch_pass_mode<5, 1>(d, b, mode, fused, s, lz);
     default:
-      return launch_pass_mode<8, 1>(d, b, mode, fused, s);
+      return launch_pass_mode<8, 1>(d, b, mode, fused, s, lz);
   }
+}
+
+static int xupdate_grid(const admm_spm_dims* d) { return ceil_div(d->npt * d->nplanes, 4); }
+
+static int launch_xupdate(const admm_spm_dims* d, const admm_spm_buffers* b, cudaStream_t s, const LazyArgs& lz = LazyArgs()) {
+  const int grid = xupdate_grid(d);
+  switch (d->Lp / 8) {
+    case 2: launch_pdl(spm_xupdate_kernel<2>, dim3(grid), dim3(128), 0, s, use_pdl(), *d, *b, lz.comm, lz.lazy); break;
+    case 5: launch_pdl(spm_xupdate_kernel<5>, dim3(grid), dim3(128), 0, s, use_pdl(), *d, *b, lz.comm, lz.lazy); break;
+    default: launch_pdl(spm_xupdate_kernel<8>, dim3(grid), dim3(128), 0, s, use_pdl(), *d, *b, lz.comm, lz.lazy); break;
+  }
+  return check_launch("admm_spm_xupdate");
 }
 
 static bool solo_regp(const admm_spm_dims* d, int cs) {
@@ -2008,14 +2251,7 @@ int admm_spm_refresh_y(const admm_spm_dims* d, const admm_spm_buffers* b, admm_s
 
 int admm_spm_xupdate(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_xupdate")) return rc;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int grid = ceil_div(d->npt * d->nplanes, 4);
-  switch (d->Lp / 8) {
-    case 2: launch_pdl(spm_xupdate_kernel<2>, dim3(grid), dim3(128), 0, s, use_pdl(), *d, *b); break;
-    case 5: launch_pdl(spm_xupdate_kernel<5>, dim3(grid), dim3(128), 0, s, use_pdl(), *d, *b); break;
-    default: launch_pdl(spm_xupdate_kernel<8>, dim3(grid), dim3(128), 0, s, use_pdl(), *d, *b); break;
-  }
-  return check_launch("admm_spm_xupdate");
+  return launch_xupdate(d, b, static_cast<cudaStream_t>(stream));
 }
 
 int admm_spm_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, admm_stream_t stream) {
@@ -2074,6 +2310,54 @@ int admm_spm_decide_peer(const admm_spm_dims* d, const admm_spm_buffers* b, cons
   launch_pdl(spm_decide_peer_kernel, dim3(ceil_div(d->nb, 128)), dim3(128), 0, static_cast<cudaStream_t>(stream), use_pdl(), *d,
              *b, *c, do_update_mu);
   return check_launch("admm_spm_decide_peer");
+}
+
+static int lazy_args(const admm_spm_dims* d, const admm_spm_buffers* b, const admm_peer_comm* c, int pending, const char* who,
+                     LazyArgs* out) {
+  ADMM_REQUIRE(d->batch_wide, ADMM_EINVAL, "%s: batch-wide criterion only", who);
+  ADMM_REQUIRE(b->lazy != nullptr && b->cta_partA != nullptr && b->cta_partB != nullptr && b->gsum != nullptr, ADMM_EINVAL,
+               "%s: lazy / cta_partA / cta_partB / gsum buffers missing", who);
+  *out = LazyArgs();
+  if (c != nullptr) {
+    if (int rc = check_comm(c, who)) return rc;
+    out->comm = *c;
+  }
+  out->lazy = pending ? 2 : 1;
+  out->nA = xupdate_grid(d);
+  return ADMM_OK;
+}
+
+int admm_spm_step_lazy(const admm_spm_dims* d, const admm_spm_buffers* b, const admm_peer_comm* c, int pending,
+                       admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_step_lazy")) return rc;
+  ADMM_REQUIRE(d->nsplit == 1 && d->nbal == 0, ADMM_EINVAL,
+               "admm_spm_step_lazy: the fused x-update + pass needs whole columns per CTA (nsplit == 1, nbal == 0)");
+  LazyArgs lz;
+  if (int rc = lazy_args(d, b, c, pending, "admm_spm_step_lazy", &lz)) return rc;
+  return launch_pass(d, b, PASS_STEP, true, static_cast<cudaStream_t>(stream), lz);
+}
+
+int admm_spm_xupdate_lazy(const admm_spm_dims* d, const admm_spm_buffers* b, const admm_peer_comm* c, int pending,
+                          admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_xupdate_lazy")) return rc;
+  LazyArgs lz;
+  if (int rc = lazy_args(d, b, c, pending, "admm_spm_xupdate_lazy", &lz)) return rc;
+  return launch_xupdate(d, b, static_cast<cudaStream_t>(stream), lz);
+}
+
+int admm_spm_pass_lazy(const admm_spm_dims* d, const admm_spm_buffers* b, const admm_peer_comm* c, admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_pass_lazy")) return rc;
+  LazyArgs lz;
+  if (int rc = lazy_args(d, b, c, 0, "admm_spm_pass_lazy", &lz)) return rc;
+  return launch_pass(d, b, PASS_STEP, false, static_cast<cudaStream_t>(stream), lz);
+}
+
+int admm_spm_flush(const admm_spm_dims* d, const admm_spm_buffers* b, const admm_peer_comm* c, admm_stream_t stream) {
+  if (int rc = check_dims(d, "admm_spm_flush")) return rc;
+  LazyArgs lz;
+  if (int rc = lazy_args(d, b, c, 1, "admm_spm_flush", &lz)) return rc;
+  launch_pdl(spm_lazy_flush_kernel, dim3(1), dim3(128), 0, static_cast<cudaStream_t>(stream), use_pdl(), *d, *b, lz.comm);
+  return check_launch("admm_spm_flush");
 }
 
 int admm_spm_reduce_decide(const admm_spm_dims* d, const admm_spm_buffers* b, int do_update_mu, admm_stream_t stream) {

@@ -224,6 +224,11 @@ typedef struct admm_spm_buffers {
                              |P Re(x0) - x2|^2, |x2|^2                                         */
   double* gsum;           /* [16] batch-wide sums (reduce), only batch_wide                    */
   double* gpart;          /* [256][16] scratch of the two-stage reduce                         */
+  double* cta_partA;      /* [CTAs of the x-update stage][10] per-CTA partial sums of the ten squared norms
+                             (lazy batch-wide iterations, see admm_spm_step_lazy)                */
+  double* cta_partB;      /* [CTAs of the pass][2] per-CTA partials of |P Re(x0) - x2|^2, |x2|^2 (unfused path) */
+  int* lazy;              /* [4], zero-initialised: 0 CTA ticket of the in-kernel reduction, 2 batch converged
+                             (every kernel of the engine returns at once when set)               */
   /* control */
   int* iter_counter;      /* device scalar: iterations launched so far in this solve call      */
   int* flags;             /* [4]: 0 any mu changed, 1 number of problems done, 2 first non-positive pivot of an in-kernel re-inversion (admm_spm_solo), 3 arrival counter of its batch-wide all-reduce */
@@ -319,6 +324,29 @@ int admm_spm_reduce_post(const admm_spm_dims* d, const admm_spm_buffers* b, cons
  * flags[2] = -2 and no decision is taken. */
 int admm_spm_decide_peer(const admm_spm_dims* d, const admm_spm_buffers* b, const admm_peer_comm* c,
                          int do_update_mu, admm_stream_t stream);
+
+/* ---- "lazy" batch-wide iterations: ONE launch per iteration -----------------------------------------
+ * Between two update_mu() iterations the only thing residual() / check_convergence() (optimizer.py:232-274)
+ * decide is whether to stop, so their work is folded into the kernels on either side of them:
+ *   tail of the step (or pass) kernel: every CTA leaves the partial sums of the ten squared norms of ITS
+ *     problems in cta_partA/B; the CTA that finishes last adds them in a fixed order into gsum (one rank) or
+ *     pushes them into every rank's mailbox (sharded batch, `c` non-NULL: what admm_spm_reduce_post does);
+ *   head of the NEXT step (or x-update) kernel (`pending` = 1): every CTA obtains the sums (gsum, or the
+ *     `world` posts of its mailbox added in rank order), evaluates the stopping test redundantly and identically,
+ *     and returns without touching the state when it fired; CTA 0 appends the residuals to `history`, counts
+ *     the iteration (iters[0], iter_counter) and on convergence sets lazy[2] and flags[1] = nb.
+ * admm_spm_flush takes the pending decision of the last launched iteration (head logic alone, one CTA): call it
+ * before an update_mu() iteration (admm_spm_step + reduce + decide as before) and before the host looks at the
+ * flags.  Same arithmetic as the three-kernel iteration; per-problem iters / last_res / done are not maintained
+ * (entry 0 is; the batch shares them).  Batch-wide criterion only. */
+int admm_spm_step_lazy(const admm_spm_dims* d, const admm_spm_buffers* b, const admm_peer_comm* c, int pending,
+                       admm_stream_t stream);
+int admm_spm_xupdate_lazy(const admm_spm_dims* d, const admm_spm_buffers* b, const admm_peer_comm* c, int pending,
+                          admm_stream_t stream);
+int admm_spm_pass_lazy(const admm_spm_dims* d, const admm_spm_buffers* b, const admm_peer_comm* c,
+                       admm_stream_t stream);
+int admm_spm_flush(const admm_spm_dims* d, const admm_spm_buffers* b, const admm_peer_comm* c,
+                   admm_stream_t stream);
 
 /* A handful of problems (spm.ipynb: ONE), the whole SimpleOptimizer.solve loop (optimizer.py:302-320)
  * in ONE launch: every problem is kept resident by a thread-block cluster of 8 CTAs (each owns

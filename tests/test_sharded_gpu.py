@@ -40,13 +40,16 @@ def world1(build_lib):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("collective,use_graph", [("peer", True), ("peer", False), ("nccl", False)])
+@pytest.mark.parametrize("collective,use_graph", [("peer", True), ("peer", False), ("peer-classic", True), ("nccl", False)])
 def test_sharded_engine_world1_vs_oracle(world1, ir_basis, collective, use_graph):
     from admmsolver_b200 import batch, problems
     from oracle import flat
     nb, niter, interval = 37, 260, 50
     p = problems.spm_batch(nb, ir_basis, Nw=200, seed=21)
+    classic = collective == "peer-classic"          # mailbox path with the three-kernel iteration (reduce_post + decide_peer)
+    collective = collective.split("-")[0]
     e = batch.SharedSpM(p.s, p.P, p.C, p.D, p.g, lam=p.lam, mu=p.mu, batch_wide=True, group=world1, collective=collective)
+    e.use_lazy = not classic
     assert e.collective == collective and (e._peer is not None) == (collective == "peer")
     n = e.solve(niter, interval_update_mu=interval, use_graph=use_graph)
     st = flat.spm_solve(p.s, p.P, p.C, p.D, p.g, p.lam, niter, mu=p.mu, interval_update_mu=interval)

@@ -44,7 +44,7 @@ class SpmBuffers(C.Structure):
         ("last_res", _P), ("Dre", _P),
         ("b0", _P), ("x0", _P), ("x1", _P), ("h10", _P), ("y0", _P), ("x0_old", _P), ("V", _P), ("aim", _P),
         ("S", _P),
-        ("normsA", _P), ("normsB", _P), ("gsum", _P), ("gpart", _P), ("cta_partA", _P), ("cta_partB", _P), ("lazy", _P),
+        ("normsA", _P), ("normsB", _P), ("gsum", _P), ("gpart", _P), ("cta_partA", _P), ("cta_partB", _P), ("lazy", _P), ("xready", _P),
         ("iter_counter", _P), ("flags", _P), ("history", _P), ("hist_cap", C.c_int),
         ("lam", C.c_double), ("rtol", C.c_double), ("max_mu", C.c_double),
         ("fact_incr", C.c_double), ("th_change", C.c_double),
@@ -100,6 +100,7 @@ _SIGS = {
     "admm_spm_refresh_y": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _P], _I),
     "admm_spm_pass": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
     "admm_spm_step": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _P], _I),
+    "admm_spm_step_supported": ([C.POINTER(SpmDims)], _I),
     "admm_spm_reduce": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _P], _I),
     "admm_spm_reduce_decide": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),
     "admm_spm_decide": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _I, _P], _I),

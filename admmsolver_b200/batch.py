@@ -143,7 +143,8 @@ class SharedSpM:
         #  * otherwise the balanced decomposition: the group-chunks are cut into equal contiguous pieces,
         #    one per resident CTA slot, the x-update is a separate kernel that sums the partial V slots
         #    (so the pieces per tile group are capped: every slot costs the x-update a dependent load).
-        SLOTS = 3 * _lib.device_info()[0]               # resident CTAs of the pass kernel: 3 per SM (444 on B200)
+        # resident CTAs of the pass kernel (shared-memory bound): 3 per SM for L <= 40 (444 on B200), 2 for L <= 64
+        SLOTS = {16: 4, 40: 3, 64: 2}[Lp] * _lib.device_info()[0]
         nbal = 0
         if nsplit is None and nbal_req is None:
             waves = -(-npt // 8) / SLOTS
@@ -235,6 +236,10 @@ class SharedSpM:
         self.cta_partA = z(max(ngrp, -(-nct // 4)) * 10)
         self.cta_partB = z(n_pass * 2)
         self.lazy = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.xready = torch.zeros(max(1, ngrp), dtype=torch.int32, device=dev)
+        # 1: fused step with whole columns per CTA; 2: fused step on the balanced decomposition (owner CTAs run the
+        # x-update, the whole iteration of a small batch is one launch); 0: x-update kernel + pass kernel
+        self._step_mode = int(_lib.lib.admm_spm_step_supported(C.byref(self.dims)))
         self.use_lazy = True          # tests switch it off to compare with the three-kernel iteration
         self._lazy_pending = False    # a launched lazy iteration still awaits its decision (next kernel's head or flush)
         self.iter_counter = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -259,7 +264,8 @@ class SharedSpM:
                         ("x0", self.x0f), ("x1", self.x1f), ("h10", self.h10f), ("y0", self.y0f), ("V", self.V),
                         ("aim", self.aim), ("S", self.S), ("normsA", self.normsA), ("normsB", self.normsB), ("gsum", self.gsum),
                         ("gpart", self.gpart), ("cta_partA", self.cta_partA), ("cta_partB", self.cta_partB),
-                        ("lazy", self.lazy), ("iter_counter", self.iter_counter), ("flags", self.flags)):
+                        ("lazy", self.lazy), ("xready", self.xready), ("iter_counter", self.iter_counter),
+                        ("flags", self.flags)):
             setattr(b, name, t.data_ptr())
         b.x0_old = self.x0_oldf.data_ptr() if self.x0_oldf is not None else None
         b.history = self.history.data_ptr() if self.history is not None else None
@@ -503,7 +509,7 @@ class SharedSpM:
         timed = self.pass_events is not None and not do_update_mu
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        fused = self.dims.nsplit == 1 and self.dims.nbal == 0
+        fused = self._step_mode != 0
         if lazy:
             # the whole iteration: decision of the previous one in the head, reduction of this one in the tail
             cref, pend = self._comm_ref(), int(self._lazy_pending)
@@ -551,6 +557,9 @@ class SharedSpM:
         problems.  Returns True when every problem is done."""
         self._flush()
         fl = self.flags.cpu()
+        if int(fl[2]) == -3:
+            raise _lib.AdmmError("fused balanced step: the CTAs of the launch were not co-resident (another kernel holding "
+                                 "SMs?); the state is undefined -- set ADMM_SPM_TWO_KERNELS=1 to use the two-kernel iteration")
         if int(fl[2]) == -2:
             raise _lib.AdmmError("sharded batch-wide criterion: a peer rank never posted its residual sums "
                                  "(watchdog of admm_spm_decide_peer); the state is undefined")
@@ -694,7 +703,7 @@ class SharedSpM:
             run -= n
 
     def _launches_per_iteration(self) -> int:
-        data = 1 if (self.dims.nsplit == 1 and self.dims.nbal == 0) else 2
+        data = 1 if self._step_mode != 0 else 2
         if self._lazy_ok():
             return data
         if self.batch_wide and (self.group is None or self._peer is not None):

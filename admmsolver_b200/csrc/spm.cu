@@ -257,6 +257,12 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
   return v;
 }
 
+__device__ __forceinline__ unsigned ld_acquire_u32(const int* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 constexpr int PEER_WORDS = 20;        // ten doubles as 32-bit halves
 constexpr int PEER_SLOT = 32;         // words per (buffer, source rank) slot of a mailbox
 constexpr long long PEER_TIMEOUT = 10000000000LL;   // ~5 s of clock64: a peer died, give up instead of hanging the GPU
@@ -362,11 +368,12 @@ __device__ __forceinline__ bool lazy_head(const admm_spm_dims& d, const admm_spm
 // Tail of a lazy iteration kernel.  `mine` (shared memory, [nwarps][10]) holds the partial sums of this CTA's warps;
 // they go to cta_partA (x-update stage or fused kernel: all ten) or cta_partB (pass of the unfused path: entries 7, 8).
 // `ticketed`: this kernel closes the iteration -- the CTA that arrives last adds all nA + nB CTA partials in a fixed
-// order and publishes the batch-wide sums (gsum, or the peers' mailboxes).  All threads of the CTA.
+// order and publishes the batch-wide sums (gsum, or the peers' mailboxes).  `scratch`: >= 256 doubles of shared
+// memory nobody else uses any more.  All threads of the CTA (blockDim.x == 128).
 __device__ __forceinline__ void lazy_tail(const admm_spm_buffers& b, const admm_peer_comm& c, double* mine, int nwarps,
-                                          bool to_A, bool ticketed, int nA, int nB) {
+                                          bool to_A, bool ticketed, int nA, int nB, double* scratch, int stamp = 0) {
   __shared__ int lz_last;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int cta = blockIdx.y * gridDim.x + blockIdx.x, ncta = gridDim.x * gridDim.y;
   __syncthreads();
   if (tid < 10) {
@@ -376,36 +383,37 @@ __device__ __forceinline__ void lazy_tail(const admm_spm_buffers& b, const admm_
     else if (tid == 7 || tid == 8) __stcg(b.cta_partB + (size_t)cta * 2 + (tid - 7), a);
   }
   if (!ticketed) return;
-  __threadfence();
   __syncthreads();
-  if (tid == 0) lz_last = (atomicAdd(reinterpret_cast<unsigned*>(b.lazy), 1u) == (unsigned)(ncta - 1));
+  if (tid == 0) {
+    __threadfence();                  // (cumulative: orders the partials the barrier made visible to this thread)
+    lz_last = (atomicAdd(reinterpret_cast<unsigned*>(b.lazy), 1u) == (unsigned)(ncta - 1));
+  }
   __syncthreads();
   if (!lz_last) return;
   __threadfence();
-  double v[10];
-#pragma unroll
-  for (int i = 0; i < 10; ++i) v[i] = 0.0;
-  for (int i = tid; i < nA; i += blockDim.x) {
-#pragma unroll
-    for (int k = 0; k < 10; ++k) v[k] += __ldcg(b.cta_partA + (size_t)i * 10 + k);
+  // fixed-order final sum with many loads in flight: thread t < 120 owns value index t % 10 of the x-update-stage
+  // partials (flat stride 120), every thread owns index 7 + (t & 1) of the pass partials (flat stride 128)
+  double a = 0.0, bs = 0.0;
+  if (tid < 120) {
+    const int n = nA * 10;
+#pragma unroll 8
+    for (int i = tid; i < n; i += 120) a += __ldcg(b.cta_partA + i);
   }
-  for (int i = tid; i < nB; i += blockDim.x) {
-    v[7] += __ldcg(b.cta_partB + (size_t)i * 2);
-    v[8] += __ldcg(b.cta_partB + (size_t)i * 2 + 1);
+  {
+    const int n = nB * 2;
+#pragma unroll 8
+    for (int i = tid; i < n; i += 128) bs += __ldcg(b.cta_partB + i);
   }
-#pragma unroll
-  for (int i = 0; i < 10; ++i) v[i] = warp_sum(v[i]);
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < 10; ++i) mine[warp * 10 + i] = v[i];
-  }
-  __syncthreads();
-  double tot = 0.0;
-  if (tid < 10) {
-    for (int w = 0; w < nwarps; ++w) tot += mine[w * 10 + tid];
-  }
+  scratch[tid] = a;
+  scratch[128 + tid] = bs;
   __syncthreads();
   if (tid < 10) {
+    double tot = 0.0;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) tot += scratch[tid + 10 * k];
+    if (tid == 7 || tid == 8) {
+      for (int k = 0; k < 64; ++k) tot += scratch[128 + 2 * k + (tid - 7)];
+    }
     mine[tid] = tot;
     b.gsum[tid] = tot;
   }
@@ -416,7 +424,10 @@ __device__ __forceinline__ void lazy_tail(const admm_spm_buffers& b, const admm_
     peer_post(c, mine, seq);
     if (tid == 0) c.ctrl[0] = seq;
   }
-  if (tid == 0) b.lazy[0] = 0;
+  if (tid == 0) {
+    b.lazy[0] = 0;
+    if (stamp != 0) b.lazy[3] = stamp;         // launch sequence number of the fused balanced kernel
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -424,7 +435,7 @@ __device__ __forceinline__ void lazy_tail(const admm_spm_buffers& b, const admm_
 // ---------------------------------------------------------------------------------------------
 // out[p][c][l'] = sum_l a[p][c][l] * B[l][l']  for NP planes that share the B fragments
 // (k-slot (jk,e) of lane (g,t) <-> l = 8 jk + 2 t + e); NT*NP independent accumulation chains.
-template <int NT, int NP>
+template <int NT, int NP, bool SMEM = false>      // SMEM: the operand was staged in shared memory
 __device__ __forceinline__ void frag_gemm(double (&out)[NP][NT][2], const double (&a)[NP][NT][2],
                                           const double* __restrict__ Bf, int lane) {
 #pragma unroll
@@ -435,7 +446,9 @@ __device__ __forceinline__ void frag_gemm(double (&out)[NP][NT][2], const double
   for (int jk = 0; jk < NT; ++jk) {
     double2 bb[NT];
 #pragma unroll
-    for (int jn = 0; jn < NT; ++jn) bb[jn] = __ldg(reinterpret_cast<const double2*>(Bf + bfrag_index(NT, jk, jn, lane)));
+    for (int jn = 0; jn < NT; ++jn)
+      bb[jn] = SMEM ? *reinterpret_cast<const double2*>(Bf + bfrag_index(NT, jk, jn, lane))
+                    : __ldg(reinterpret_cast<const double2*>(Bf + bfrag_index(NT, jk, jn, lane)));
 #pragma unroll
     for (int jn = 0; jn < NT; ++jn)
 #pragma unroll
@@ -456,18 +469,51 @@ __device__ __forceinline__ void frag_gemm(double (&out)[NP][NT][2], const double
 // Handles planes p0 .. p0+NP-1 of the tile (plane 0 = real, plane 1 = imaginary parts).
 // wpart != NULL (lazy batch-wide iterations): instead of per-problem norms in normsA, the sums over the tile's live
 // problems are added to wpart[0..9] (this warp's row of the CTA's partial sums, indexed like gather_problem's s[]).
-template <int NT, int NP, bool SPLIT>   // SPLIT: V arrives as d.nsplit partial sums (unfused small-batch path)
+// Stand-alone kernel (PRE): the iteration is a chain of dependent steps on a few warps, so every global-memory
+// round trip shows.  The L x L operands are staged in shared memory by the whole CTA (sm_PtP; sm_Ginv = the factor of
+// cache row sm_slot, -1: none) and every load that does not depend on a computed value is issued up front.
+template <int NT, int NP, bool SPLIT, bool PRE = false>   // SPLIT: V arrives as d.nsplit partial sums (small-batch paths)
 __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_spm_buffers& b, int pt, int lane,
-                                             int p0 = 0, double* wpart = nullptr) {
+                                             int p0 = 0, double* wpart = nullptr, const double* sm_PtP = nullptr,
+                                             const double* sm_Ginv = nullptr, int sm_slot = -1) {
   const int g = lane >> 2, t = lane & 3;
   const int prob = 8 * pt + g;
   const int is_done = b.done[prob];
-  if (__all_sync(0xffffffffu, is_done)) return false;
-  const double mu10 = b.mu10[prob], mu20 = b.mu20[prob];
+  const double mu10 = b.mu10[prob], mu20 = b.mu20[prob];      // (issued together with `done`: one round trip)
   const int slot = b.slot[prob];
+  if (__all_sync(0xffffffffu, is_done)) return false;
   const int Lp = d.Lp;
   const int ct0 = pt * d.nplanes + p0;
   const size_t vstride = (size_t)d.npt * d.nplanes * NT * 64;
+
+  // PRE: old x0, y0 = P^T P x0_old and the KKT vectors are requested now, long before they are used
+  double xo_pre[PRE ? NP : 1][NT][2], yo_pre[PRE ? NP : 1][NT][2], hh_pre[PRE ? NP : 1][NT][2];
+  double cw_pre[PRE ? NT : 1][4];      // C[8j+2t], C[8j+2t+1], w[8j+2t], w[8j+2t+1]
+  double sig_pre = 0.0, D_pre[PRE ? NP : 1];
+  if (PRE) {
+    const double* wv = b.w_cache + (size_t)slot * Lp;
+    sig_pre = b.sigma_cache[slot];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      D_pre[p] = b.Dre[(size_t)(p0 + p) * 8 * d.npt + prob];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const size_t o = frag_index(ct0 + p, NT, j, lane);
+        const double2 a = *reinterpret_cast<const double2*>(b.x0 + o), y2 = *reinterpret_cast<const double2*>(b.y0 + o);
+        xo_pre[p][j][0] = a.x;
+        xo_pre[p][j][1] = a.y;
+        yo_pre[p][j][0] = y2.x;
+        yo_pre[p][j][1] = y2.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      cw_pre[j][0] = b.Cvec[8 * j + 2 * t];
+      cw_pre[j][1] = b.Cvec[8 * j + 2 * t + 1];
+      cw_pre[j][2] = wv[8 * j + 2 * t];
+      cw_pre[j][3] = wv[8 * j + 2 * t + 1];
+    }
+  }
 
   // ---- rhs = alpha A^H y + h10 + mu10 x1 + P^T(h20 + mu20 x2)
   double x0[NP][NT][2];
@@ -491,6 +537,10 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
         }
         rhs[p][j][0] = b0.x + hh.x + mu10 * x1.x + v.x;
         rhs[p][j][1] = b0.y + hh.y + mu10 * x1.y + v.y;
+        if (PRE) {
+          hh_pre[p][j][0] = hh.x;
+          hh_pre[p][j][1] = hh.y;
+        }
       }
     }
     // ---- xi1 = Ginv rhs, one tensor-core GEMM per distinct factor slot in the tile (one slot unless
@@ -500,7 +550,8 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
     do {
       const int cur = __shfl_sync(0xffffffffu, slot, __ffs(remaining) - 1);
       double acc[NP][NT][2];
-      frag_gemm<NT, NP>(acc, rhs, b.Ginv_cache + (size_t)cur * Lp * Lp, lane);
+      if (PRE && cur == sm_slot) frag_gemm<NT, NP, true>(acc, rhs, sm_Ginv, lane);
+      else frag_gemm<NT, NP>(acc, rhs, b.Ginv_cache + (size_t)cur * Lp * Lp, lane);
       if (slot == cur) {
 #pragma unroll
         for (int p = 0; p < NP; ++p)
@@ -517,25 +568,29 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
   // ---- KKT correction enforcing C x0 = D   (objectivefunc.py:148-157)
   {
     const double* wv = b.w_cache + (size_t)slot * Lp;
-    const double isig = 1.0 / b.sigma_cache[slot];
+    const double isig = 1.0 / (PRE ? sig_pre : b.sigma_cache[slot]);
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
       double cxi = 0.0;
 #pragma unroll
-      for (int j = 0; j < NT; ++j) cxi += b.Cvec[8 * j + 2 * t] * x0[p][j][0] + b.Cvec[8 * j + 2 * t + 1] * x0[p][j][1];
+      for (int j = 0; j < NT; ++j) {
+        const double c0 = PRE ? cw_pre[j][0] : b.Cvec[8 * j + 2 * t], c1 = PRE ? cw_pre[j][1] : b.Cvec[8 * j + 2 * t + 1];
+        cxi += c0 * x0[p][j][0] + c1 * x0[p][j][1];
+      }
       cxi = quad_sum(cxi);
-      const double nu = (b.Dre[(size_t)(p0 + p) * 8 * d.npt + prob] - cxi) * isig;
+      const double nu = ((PRE ? D_pre[p] : b.Dre[(size_t)(p0 + p) * 8 * d.npt + prob]) - cxi) * isig;
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        x0[p][j][0] += wv[8 * j + 2 * t] * nu;
-        x0[p][j][1] += wv[8 * j + 2 * t + 1] * nu;
+        x0[p][j][0] += (PRE ? cw_pre[j][2] : wv[8 * j + 2 * t]) * nu;
+        x0[p][j][1] += (PRE ? cw_pre[j][3] : wv[8 * j + 2 * t + 1]) * nu;
       }
     }
   }
 
   // ---- y = P^T P x0 (both planes in one GEMM)
   double y[NP][NT][2];
-  frag_gemm<NT, NP>(y, x0, b.PtPf, lane);
+  if (PRE && sm_PtP != nullptr) frag_gemm<NT, NP, true>(y, x0, sm_PtP, lane);
+  else frag_gemm<NT, NP>(y, x0, b.PtPf, lane);
 
   const double thr = 0.5 * b.lam / mu10;
 #pragma unroll
@@ -546,7 +601,8 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
       double xo[1][NT][2], yo[1][NT][2];
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        const double2 v = *reinterpret_cast<const double2*>(b.x0 + frag_index(ct0 + p, NT, j, lane));
+        const double2 v = PRE ? make_double2(xo_pre[p][j][0], xo_pre[p][j][1])
+                                : *reinterpret_cast<const double2*>(b.x0 + frag_index(ct0 + p, NT, j, lane));
         xo[0][j][0] = v.x;
         xo[0][j][1] = v.y;
         // `_x_old[0]` of the reference (optimizer.py:324): only kept when the caller asks for it
@@ -554,7 +610,8 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
       }
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        const double2 v = *reinterpret_cast<const double2*>(b.y0 + frag_index(ct0 + p, NT, j, lane));
+        const double2 v = PRE ? make_double2(yo_pre[p][j][0], yo_pre[p][j][1])
+                                : *reinterpret_cast<const double2*>(b.y0 + frag_index(ct0 + p, NT, j, lane));
         yo[0][j][0] = v.x;
         yo[0][j][1] = v.y;
       }
@@ -590,7 +647,7 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       const size_t o = frag_index(ct0 + p, NT, j, lane);
-      const double2 hh = *reinterpret_cast<const double2*>(b.h10 + o);
+      const double2 hh = PRE ? make_double2(hh_pre[p][j][0], hh_pre[p][j][1]) : *reinterpret_cast<const double2*>(b.h10 + o);
       double zz[2], hn[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
@@ -667,13 +724,28 @@ __global__ void __launch_bounds__(128) spm_xupdate_kernel(admm_spm_dims d, admm_
   }
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  // stage the two L x L operands (fragment-major, NT*NT*64 doubles each) with 16-byte async copies: P^T P at once, the
+  // cached inverse as soon as the factor row of the CTA's first problem is known (batch-wide: the row of all of them)
+  extern __shared__ __align__(16) double sm_ops[];        // [2][NT*NT*64]
+  constexpr int OPV = NT * NT * 32;                        // 16-byte vectors per operand
+  for (int i = threadIdx.x; i < OPV; i += 128) cp_async16(sm_ops + 2 * i, b.PtPf + 2 * i);
+  const int wfirst = (blockIdx.x * blockDim.x) >> 5;
+  const int pfirst = min(8 * (wfirst / d.nplanes), 8 * d.npt - 1);
+  const int slot0 = b.slot[pfirst];
+  {
+    const double* gi = b.Ginv_cache + (size_t)slot0 * d.Lp * d.Lp;
+    for (int i = threadIdx.x; i < OPV; i += 128) cp_async16(sm_ops + NT * NT * 64 + 2 * i, gi + 2 * i);
+  }
+  cp_async_commit();
   if (lazy) {
     if (lane < 10) wsum[wl * 10 + lane] = 0.0;
-    __syncwarp();
   }
+  cp_async_wait<0>();
+  __syncthreads();
   if (warp < d.npt * d.nplanes)
-    xupdate_tile<NT, 1, true>(d, b, warp / d.nplanes, lane, warp % d.nplanes, lazy ? wsum + wl * 10 : nullptr);
-  if (lazy) lazy_tail(b, c, wsum, 4, true, false, 0, 0);
+    xupdate_tile<NT, 1, true, true>(d, b, warp / d.nplanes, lane, warp % d.nplanes, lazy ? wsum + wl * 10 : nullptr, sm_ops,
+                              sm_ops + NT * NT * 64, slot0);
+  if (lazy) lazy_tail(b, c, wsum, 4, true, false, 0, 0, sm_ops);
 }
 
 // y0 = P^T P x0 for every column tile (after the state was loaded from outside)
@@ -731,8 +803,15 @@ struct PassSmem {
 // lazy (batch-wide criterion, MODE == PASS_STEP): 0 classic (per-problem norms, the reduce/decide kernels follow);
 // 1 / 2: lazy iteration without / with a pending decision of the previous iteration (lazy_head / lazy_tail); nA = CTAs
 // of the stand-alone x-update kernel whose partial sums the last CTA of this pass adds (unfused path).
-template <int NT, int MT, int MODE, int FNP>   // FNP: 0 = pass only, 1/2 = fused x-update of 1/2 planes
-__global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
+//
+// BAL (FNP != 0 with the balanced decomposition): the WHOLE iteration of a small batch in one launch.  Of the CTAs whose
+// piece starts in tile group G the first one is the group's OWNER: its four warps run the x-update of the group's tiles
+// (V = the sum of the partial slots the pieces left in the previous iteration), then it publishes "x0 of group G is
+// new" by storing the launch's sequence number into xready[G] (release); every CTA waits for that number (acquire)
+// before it touches chunks of G.  All CTAs of the single wave are co-resident (the launcher checks the occupancy), the
+// owners never wait for anybody, so the waits always end; a watchdog turns a broken assumption into flags[2] = -3.
+template <int NT, int MT, int MODE, int FNP, bool BAL = false>   // FNP: 0 = pass only, 1/2 = fused x-update of 1/2 planes
+__global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4)      // (shared memory admits 3 CTAs per SM for NT = 5)
     spm_pass_kernel(admm_spm_dims d, admm_spm_buffers b, admm_peer_comm c, int lazy, int nA) {
   pdl_prologue();
   __shared__ double wsum[PASS_WARPS * 10];        // lazy: partial sums of the ten squared norms, one row per warp
@@ -786,7 +865,28 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
     for (int s = 0; s < PASS_STAGES && s < nchunks; ++s) fill(s, g_begin + s);
   }
 
-  if (FNP != 0) {
+  int bal_stamp = 0, bal_own_grp = -1;
+  if (BAL) {
+    // sequence number of this launch (the CTA that finishes last advances lazy[3]) and the group this CTA owns
+    constexpr int NPL = FNP == 0 ? 1 : FNP;
+    bal_stamp = __ldcg(b.lazy + 3) + 1;
+    const long long T = (long long)((d.npt + GT - 1) / GT) * nct;
+    const int grp0 = (int)(g_begin / nct);
+    const int first = (int)(((long long)grp0 * nct * d.nbal + T - 1) / T);       // first CTA whose piece starts in grp0
+    if ((int)blockIdx.x == first && nchunks > 0) {
+      bal_own_grp = grp0;
+      double* wp = lazy ? wsum + warp * 10 : nullptr;
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        const int ptm = (grp0 * PASS_WARPS + warp) * MT + m;
+        if (ptm < d.npt) xupdate_tile<NT, NPL, true>(d, b, ptm, lane, 0, wp);
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(b.xready + grp0), "r"(bal_stamp) : "memory");
+    }
+  }
+  if (FNP != 0 && !BAL) {
     // x-update of this warp's tiles right here (all planes): x0 reaches the MMA operand registers
     // through L1/L2; the pass of the other CTAs of the SM hides the latency of this L x L work.
     // The L-vectors of the tiles are pulled into L2 up front (one bulk prefetch per vector).
@@ -836,6 +936,19 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
     double xa[MT][NT][2];      // A fragments of GEMM1': -mu20 * Re(x0)   (k-slot (j,e) of lane (g,t) <-> l = 8j+2t+e)
     double acc[MT][NT][2];     // C fragments of GEMM2': V
     bool all_done = true;
+    if (BAL && grp != bal_own_grp) {
+      // x0 of this group comes from its owner CTA: wait for this launch's sequence number
+      if (lane == 0) {
+        const long long t_start = clock64();
+        while ((int)ld_acquire_u32(b.xready + grp) != bal_stamp) {
+          if (clock64() - t_start > 4000000000LL) {      // the CTAs are not co-resident after all: give up (~2 s)
+            b.flags[2] = -3;
+            break;
+          }
+        }
+      }
+      __syncwarp();
+    }
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
       pt[m] = (grp * PASS_WARPS + warp) * MT + m;
@@ -846,7 +959,8 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
       mu20[m] = b.mu20[prob];
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        const double2 v = *reinterpret_cast<const double2*>(b.x0 + frag_index(pt[m] * npl, NT, j, lane));
+        const double2 v = BAL ? __ldcg(reinterpret_cast<const double2*>(b.x0 + frag_index(pt[m] * npl, NT, j, lane)))
+                              : *reinterpret_cast<const double2*>(b.x0 + frag_index(pt[m] * npl, NT, j, lane));
         xa[m][j][0] = -mu20[m] * v.x;
         xa[m][j][1] = -mu20[m] * v.y;
         acc[m][j][0] = acc[m][j][1] = 0.0;
@@ -997,7 +1111,18 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, MT == 2 ? 3 : 4)
   }
   if (MODE == PASS_STEP && lazy) {
     const int ncta = gridDim.x * gridDim.y;
-    lazy_tail(b, c, wsum, PASS_WARPS, FNP != 0, true, FNP != 0 ? ncta : nA, FNP != 0 ? 0 : ncta);
+    lazy_tail(b, c, wsum, PASS_WARPS, FNP != 0, true, FNP != 0 ? ncta : nA, FNP != 0 ? 0 : ncta, ring,     // (ring: all chunks consumed)
+              BAL ? bal_stamp : 0);
+  } else if (BAL) {
+    // classic iteration (per-problem norms, the reduce/decide kernels follow): only the launch sequence number moves on
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      if (atomicAdd(reinterpret_cast<unsigned*>(b.lazy), 1u) == gridDim.x * gridDim.y - 1) {
+        b.lazy[0] = 0;
+        b.lazy[3] = bal_stamp;
+      }
+    }
   }
 }
 
@@ -1263,11 +1388,6 @@ __global__ void __launch_bounds__(128) spm_lazy_flush_kernel(admm_spm_dims d, ad
 //   * the only exchange per iteration is the partial V = P^T|s'| (L doubles) and two norm partials,
 //     pulled from the peers' shared memory (DSMEM) after ONE cluster barrier.
 // Warps 0-3 hold the L-vectors in registers (thread = (plane, l)); warps 4-11 own the sampling points.
-__device__ __forceinline__ unsigned ld_acquire_u32(const int* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 
 constexpr int SOLO_THREADS = 384;
 constexpr int SOLO_LWARPS = 4;
@@ -2062,6 +2182,10 @@ static bool use_pdl() {
   static const bool on = getenv("ADMM_NO_PDL") == nullptr;
   return on;
 }
+static bool use_pdl_x() {      // the stand-alone x-update kernel (ADMM_NO_PDL_X=1: A/B runs)
+  static const bool on = getenv("ADMM_NO_PDL_X") == nullptr;
+  return on && use_pdl();
+}
 
 static int ew_grid(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 16)); }
 
@@ -2071,11 +2195,29 @@ struct LazyArgs {          // how a pass / step launch takes part in the lazy ba
   int nA;                  // CTAs of the stand-alone x-update kernel (unfused path)
 };
 
-template <int NT, int MT, int MODE, int FNP>
-static int launch_pass_k(const admm_spm_dims* d, const admm_spm_buffers* b, cudaStream_t s, const LazyArgs& lz) {
+template <int NT, int MT, int MODE, int FNP, bool BAL = false>
+static int launch_pass_k(const admm_spm_dims* d, const admm_spm_buffers* b, cudaStream_t s, const LazyArgs& lz,
+                         int* max_ctas = nullptr) {      // max_ctas != NULL: occupancy query only (co-resident CTAs)
   const dim3 grid = d->nbal > 0 ? dim3(d->nbal, 1) : dim3(ceil_div(d->npt, PASS_WARPS * MT), d->nsplit);
   const size_t smem = PassSmem<NT, MT>::BYTES;
-  auto k = spm_pass_kernel<NT, MT, MODE, FNP>;
+  auto k = spm_pass_kernel<NT, MT, MODE, FNP, BAL>;
+  if (max_ctas != nullptr) {
+    static std::map<int, int> cached;      // per instantiation and device
+    auto it = cached.find(cur_dev());
+    if (it == cached.end()) {
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      int per_sm = 0, sms = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, PASS_WARPS * 32, smem) != cudaSuccess ||
+          cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cur_dev()) != cudaSuccess) {
+        cudaGetLastError();
+        per_sm = 0;
+      }
+      it = cached.emplace(cur_dev(), per_sm * sms).first;
+    }
+    *max_ctas = it->second;
+    return ADMM_OK;
+  }
   static std::map<int, bool> configured;     // per instantiation and device
   bool& cfgd = configured[cur_dev()];
   if (!cfgd) {
@@ -2089,7 +2231,11 @@ static int launch_pass_k(const admm_spm_dims* d, const admm_spm_buffers* b, cuda
 
 template <int NT, int MT>
 static int launch_pass_mode(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, bool fused, cudaStream_t s,
-                            const LazyArgs& lz) {
+                            const LazyArgs& lz, int* max_ctas = nullptr) {
+  if (fused && d->nbal > 0) {      // the whole iteration of a small batch in one launch (owner CTAs run the x-update)
+    return d->nplanes == 2 ? launch_pass_k<NT, MT, PASS_STEP, 2, true>(d, b, s, lz, max_ctas)
+                           : launch_pass_k<NT, MT, PASS_STEP, 1, true>(d, b, s, lz, max_ctas);
+  }
   if (fused) {
     return d->nplanes == 2 ? launch_pass_k<NT, MT, PASS_STEP, 2>(d, b, s, lz) : launch_pass_k<NT, MT, PASS_STEP, 1>(d, b, s, lz);
   }
@@ -2098,25 +2244,50 @@ static int launch_pass_mode(const admm_spm_dims* d, const admm_spm_buffers* b, i
 }
 
 static int launch_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, bool fused, cudaStream_t s,
-                       const LazyArgs& lz = LazyArgs()) {
+                       const LazyArgs& lz = LazyArgs(), int* max_ctas = nullptr) {
   switch (d->Lp / 8) {
     case 2:
-      return d->mt == 2 ? launch_pass_mode<2, 2>(d, b, mode, fused, s, lz) : launch_pass_mode<2, 1>(d, b, mode, fused, s, lz);
+      return d->mt == 2 ? launch_pass_mode<2, 2>(d, b, mode, fused, s, lz, max_ctas)
+                        : launch_pass_mode<2, 1>(d, b, mode, fused, s, lz, max_ctas);
     case 5:
-      return d->mt == 2 ? launch_pass_mode<5, 2>(d, b, mode, fused, s, lz) : launch_pass_mode<5, 1>(d, b, mode, fused, s, lz);
+      return d->mt == 2 ? launch_pass_mode<5, 2>(d, b, mode, fused, s, lz, max_ctas)
+                        : launch_pass_mode<5, 1>(d, b, mode, fused, s, lz, max_ctas);
     default:
-      return launch_pass_mode<8, 1>(d, b, mode, fused, s, lz);
+      return launch_pass_mode<8, 1>(d, b, mode, fused, s, lz, max_ctas);
   }
+}
+
+// Can admm_spm_step / admm_spm_step_lazy run these dims?  1: whole columns per CTA; 2: balanced decomposition with owner
+// CTAs (every tile group must contain the start of a piece, and all pieces must be co-resident); 0: no.
+static int step_mode(const admm_spm_dims* d) {
+  if (d->nsplit == 1 && d->nbal == 0) return 1;
+  if (d->nbal <= 0 || getenv("ADMM_SPM_TWO_KERNELS")) return 0;
+  const int ngroups = ceil_div(d->npt, PASS_WARPS * d->mt);
+  if (d->nbal < ngroups) return 0;
+  int maxc = 0;
+  if (launch_pass(d, nullptr, PASS_STEP, true, nullptr, LazyArgs(), &maxc) != ADMM_OK || d->nbal > maxc) return 0;
+  return 2;
 }
 
 static int xupdate_grid(const admm_spm_dims* d) { return ceil_div(d->npt * d->nplanes, 4); }
 
 static int launch_xupdate(const admm_spm_dims* d, const admm_spm_buffers* b, cudaStream_t s, const LazyArgs& lz = LazyArgs()) {
   const int grid = xupdate_grid(d);
-  switch (d->Lp / 8) {
-    case 2: launch_pdl(spm_xupdate_kernel<2>, dim3(grid), dim3(128), 0, s, use_pdl(), *d, *b, lz.comm, lz.lazy); break;
-    case 5: launch_pdl(spm_xupdate_kernel<5>, dim3(grid), dim3(128), 0, s, use_pdl(), *d, *b, lz.comm, lz.lazy); break;
-    default: launch_pdl(spm_xupdate_kernel<8>, dim3(grid), dim3(128), 0, s, use_pdl(), *d, *b, lz.comm, lz.lazy); break;
+  const int NT = d->Lp / 8;
+  const size_t smem = (size_t)2 * NT * NT * 64 * sizeof(double);      // the two staged L x L operands
+  switch (NT) {
+    case 2: launch_pdl(spm_xupdate_kernel<2>, dim3(grid), dim3(128), smem, s, use_pdl_x(), *d, *b, lz.comm, lz.lazy); break;
+    case 5: launch_pdl(spm_xupdate_kernel<5>, dim3(grid), dim3(128), smem, s, use_pdl_x(), *d, *b, lz.comm, lz.lazy); break;
+    default: {
+      static std::map<int, bool> configured;      // 64 KB of dynamic shared memory: opt-in, per device
+      bool& cfgd = configured[cur_dev()];
+      if (!cfgd) {
+        cudaFuncSetAttribute(spm_xupdate_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cfgd = true;
+      }
+      launch_pdl(spm_xupdate_kernel<8>, dim3(grid), dim3(128), smem, s, use_pdl_x(), *d, *b, lz.comm, lz.lazy);
+      break;
+    }
   }
   return check_launch("admm_spm_xupdate");
 }
@@ -2260,10 +2431,18 @@ int admm_spm_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, a
   return launch_pass(d, b, mode, false, static_cast<cudaStream_t>(stream));
 }
 
+int admm_spm_step_supported(const admm_spm_dims* d) {
+  if (d == nullptr || check_dims(d, "admm_spm_step_supported") != ADMM_OK) return 0;
+  return step_mode(d);
+}
+
 int admm_spm_step(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_step")) return rc;
-  ADMM_REQUIRE(d->nsplit == 1 && d->nbal == 0, ADMM_EINVAL,
-               "admm_spm_step: the fused x-update + pass needs whole columns per CTA (nsplit == 1, nbal == 0)");
+  const int mode = step_mode(d);
+  ADMM_REQUIRE(mode != 0, ADMM_EUNSUPPORTED,
+               "admm_spm_step: needs whole columns per CTA (nsplit == 1, nbal == 0) or a balanced decomposition with "
+               "nbal >= tile groups whose CTAs are all co-resident (see admm_spm_step_supported)");
+  ADMM_REQUIRE(mode == 1 || (b->lazy != nullptr && b->xready != nullptr), ADMM_EINVAL, "admm_spm_step: lazy / xready buffers missing");
   return launch_pass(d, b, PASS_STEP, true, static_cast<cudaStream_t>(stream));
 }
 
@@ -2330,8 +2509,9 @@ static int lazy_args(const admm_spm_dims* d, const admm_spm_buffers* b, const ad
 int admm_spm_step_lazy(const admm_spm_dims* d, const admm_spm_buffers* b, const admm_peer_comm* c, int pending,
                        admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_step_lazy")) return rc;
-  ADMM_REQUIRE(d->nsplit == 1 && d->nbal == 0, ADMM_EINVAL,
-               "admm_spm_step_lazy: the fused x-update + pass needs whole columns per CTA (nsplit == 1, nbal == 0)");
+  const int mode = step_mode(d);
+  ADMM_REQUIRE(mode != 0, ADMM_EUNSUPPORTED, "admm_spm_step_lazy: dims not supported by the fused step (see admm_spm_step_supported)");
+  ADMM_REQUIRE(mode == 1 || b->xready != nullptr, ADMM_EINVAL, "admm_spm_step_lazy: xready buffer missing");
   LazyArgs lz;
   if (int rc = lazy_args(d, b, c, pending, "admm_spm_step_lazy", &lz)) return rc;
   return launch_pass(d, b, PASS_STEP, true, static_cast<cudaStream_t>(stream), lz);

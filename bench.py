@@ -543,12 +543,13 @@ def run_workload(args, workload, ctx, steps, warmup, with_clocks):
         #         sampling point (the imaginary half of the state is advanced in L-space)
         #   x-update (fused only): per plane Ginv*rhs and PtP*x0 = 2 * 2 L^2 flop; per plane 6 L-vectors read
         #         and 4 written, plus z and a of the imaginary plane (2 read, 2 written)
-        fused = eng.dims.nsplit == 1 and eng.dims.nbal == 0
+        fused = eng._step_mode != 0          # the x-update runs inside the step kernel (whole-column or balanced form)
         npl = eng.dims.nplanes
         flops_per_unit = 4.0 * L * Nw + (4.0 * L * L * npl if fused else 0.0)
         bytes_per_unit = 16.0 * Nw + (8.0 * L * (10 * npl + (4 if npl == 2 else 0)) if fused else 0.0)
         survey_flops_per_unit = 8.0 * L * Nw + 4.0 * L * L       # both planes through both skinny GEMMs
-        kernel_name = "spm_pass_kernel<%d,%d,0,%d>" % (eng.dims.Lp // 8, eng.dims.mt, npl if fused else 0)
+        kernel_name = "spm_pass_kernel<%d,%d,0,%d%s>" % (eng.dims.Lp // 8, eng.dims.mt, npl if fused else 0,
+                                                         ",bal" if eng._step_mode == 2 else "")
         if solo:
             flops_per_unit = 4.0 * L * Nw + 4.0 * L * L * npl
             bytes_per_unit = 0.0          # P, the state and the factor stay in shared memory / registers

@@ -228,7 +228,10 @@ typedef struct admm_spm_buffers {
                              (lazy batch-wide iterations, see admm_spm_step_lazy)                */
   double* cta_partB;      /* [CTAs of the pass][2] per-CTA partials of |P Re(x0) - x2|^2, |x2|^2 (unfused path) */
   int* lazy;              /* [4], zero-initialised: 0 CTA ticket of the in-kernel reduction, 2 batch converged
-                             (every kernel of the engine returns at once when set)               */
+                             (every kernel of the engine returns at once when set), 3 launch sequence number
+                             of the fused balanced step                                          */
+  int* xready;            /* [tile groups], zero-initialised: launch sequence number for which the group's x0 is
+                             current (fused balanced step: owner CTA -> the pieces of the group)    */
   /* control */
   int* iter_counter;      /* device scalar: iterations launched so far in this solve call      */
   int* flags;             /* [4]: 0 any mu changed, 1 number of problems done, 2 first non-positive pivot of an in-kernel re-inversion (admm_spm_solo), 3 arrival counter of its batch-wide all-reduce */
@@ -263,9 +266,16 @@ int admm_spm_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode,
 
 /* admm_spm_xupdate + admm_spm_pass(mode 0) in ONE kernel: every warp first does the x-update of
  * its own problem tiles (both planes) and then streams their state, so x0 goes from the
- * x-update to the tensor-core operand registers without a round trip.  Needs whole columns per CTA
- * (nsplit == 1, nbal == 0). */
+ * x-update to the tensor-core operand registers without a round trip.  Whole columns per CTA
+ * (nsplit == 1, nbal == 0), or the balanced decomposition with owner CTAs (admm_spm_step_supported). */
 int admm_spm_step(const admm_spm_dims* d, const admm_spm_buffers* b, admm_stream_t stream);
+
+/* Which form of admm_spm_step / admm_spm_step_lazy these dims get: 1 whole columns per CTA (nsplit == 1,
+ * nbal == 0); 2 the balanced decomposition of a small batch with OWNER CTAs -- of the CTAs whose piece starts
+ * in a tile group the first runs the x-update of the group's tiles, then releases the group (xready) to the
+ * CTAs that stream its chunks, so the whole iteration is one launch (needs nbal >= tile groups and all nbal
+ * CTAs co-resident: checked here against the kernel's occupancy); 0: use admm_spm_xupdate + admm_spm_pass. */
+int admm_spm_step_supported(const admm_spm_dims* d);
 
 /* Batch-wide norms: deterministic two-stage sum over all problems into gsum[16].  The caller
  * all-reduces gsum across ranks (NCCL) before admm_spm_decide when the batch is sharded. */

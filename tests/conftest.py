@@ -15,6 +15,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _single_blas_thread():
+    """The oracle's matrices are tiny (39 x 39, 39 x 2000): a multi-threaded BLAS pool makes its loop 50-100x SLOWER
+    (oversubscription on small gemms).  One thread for the whole test session."""
+    try:
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=1):
+            yield
+    except ImportError:
+        yield
+
+
 def golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 

@@ -233,7 +233,7 @@ class SharedSpM:
         # in the head of the next one): per-CTA partial sums and the control words
         ngrp = -(-npt // gt)
         n_pass = nbal if nbal > 0 else ngrp * nsplit
-        self.cta_partA = z(max(ngrp, -(-nct // 4)) * 10)
+        self.cta_partA = z(max(ngrp, -(-nct // 4), n_pass) * 10)      # (fused balanced step: one row per pass CTA)
         self.cta_partB = z(n_pass * 2)
         self.lazy = torch.zeros(4, dtype=torch.int32, device=dev)
         self.xready = torch.zeros(max(1, ngrp), dtype=torch.int32, device=dev)
@@ -596,7 +596,7 @@ class SharedSpM:
         self.done[:nb] = 0
         self.flags.zero_()
         self.iter_counter.zero_()
-        self.lazy.zero_()
+        self.lazy[:3].zero_()           # (entry 3, the launch sequence number of the fused balanced step, runs on)
         self._lazy_pending = False
         track = (self.batch_wide or nb == 1) if keep_history is None else keep_history
         if track:

@@ -342,11 +342,17 @@ __device__ __forceinline__ bool lazy_head(const admm_spm_dims& d, const admm_spm
     if (first_cta && tid == 0) b.flags[2] = -2;
     return true;
   }
-  double s[10], parts[4], primal, dual;
+  double s[10];
 #pragma unroll
   for (int i = 0; i < 10; ++i) s[i] = lz_gs[i];
-  const bool conv = residual_conv(s, b.mu10[0], b.mu20[0], b.rtol, primal, dual, parts);
+  // check_convergence (optimizer.py:232-249) on the squared norms: p / max(a, b) < rtol  <=>  p^2 < rtol^2 max(a^2, b^2)
+  // (mu > 0 cancels in the dual tests; 0/0 and x/0 stay "not converged") -- FP64 square roots and divisions are long
+  // instruction sequences, and this runs at the head of every CTA
+  const double rtol2 = b.rtol * b.rtol;
+  const bool conv = (s[0] < rtol2 * fmax(s[1], s[2])) && (s[3] < rtol2 * fmax(s[1], s[4])) &&
+                    (s[7] < rtol2 * fmax(s[9], s[8])) && (s[5] < rtol2 * fmax(s[9], s[6]));
   if (first_cta && tid == 0) {
+    const double primal = sqrt(s[0]) + sqrt(s[7]), dual = b.mu10[0] * sqrt(s[3]) + b.mu20[0] * sqrt(s[5]);
     const int it = b.iters[0];
     if (b.history && it < b.hist_cap) {
       b.history[2 * it] = primal;
@@ -472,7 +478,9 @@ __device__ __forceinline__ void frag_gemm(double (&out)[NP][NT][2], const double
 // Stand-alone kernel (PRE): the iteration is a chain of dependent steps on a few warps, so every global-memory
 // round trip shows.  The L x L operands are staged in shared memory by the whole CTA (sm_PtP; sm_Ginv = the factor of
 // cache row sm_slot, -1: none) and every load that does not depend on a computed value is issued up front.
-template <int NT, int NP, bool SPLIT, bool PRE = false>   // SPLIT: V arrives as d.nsplit partial sums (small-batch paths)
+// EARLY: the late operands (old x0, y0, h10) are kept in registers from the start (stand-alone kernel); PRE without EARLY
+// (owner CTAs of the fused balanced step, whose registers belong to the pass): they are prefetched into L1 instead.
+template <int NT, int NP, bool SPLIT, bool PRE = false, bool EARLY = PRE>   // SPLIT: V arrives as d.nsplit partial sums
 __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_spm_buffers& b, int pt, int lane,
                                              int p0 = 0, double* wpart = nullptr, const double* sm_PtP = nullptr,
                                              const double* sm_Ginv = nullptr, int sm_slot = -1) {
@@ -487,7 +495,7 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
   const size_t vstride = (size_t)d.npt * d.nplanes * NT * 64;
 
   // PRE: old x0, y0 = P^T P x0_old and the KKT vectors are requested now, long before they are used
-  double xo_pre[PRE ? NP : 1][NT][2], yo_pre[PRE ? NP : 1][NT][2], hh_pre[PRE ? NP : 1][NT][2];
+  double xo_pre[EARLY ? NP : 1][NT][2], yo_pre[EARLY ? NP : 1][NT][2], hh_pre[EARLY ? NP : 1][NT][2];
   double cw_pre[PRE ? NT : 1][4];      // C[8j+2t], C[8j+2t+1], w[8j+2t], w[8j+2t+1]
   double sig_pre = 0.0, D_pre[PRE ? NP : 1];
   if (PRE) {
@@ -499,11 +507,17 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         const size_t o = frag_index(ct0 + p, NT, j, lane);
-        const double2 a = *reinterpret_cast<const double2*>(b.x0 + o), y2 = *reinterpret_cast<const double2*>(b.y0 + o);
-        xo_pre[p][j][0] = a.x;
-        xo_pre[p][j][1] = a.y;
-        yo_pre[p][j][0] = y2.x;
-        yo_pre[p][j][1] = y2.y;
+        if (EARLY) {
+          const double2 a = *reinterpret_cast<const double2*>(b.x0 + o), y2 = *reinterpret_cast<const double2*>(b.y0 + o);
+          xo_pre[p][j][0] = a.x;
+          xo_pre[p][j][1] = a.y;
+          yo_pre[p][j][0] = y2.x;
+          yo_pre[p][j][1] = y2.y;
+        } else {
+          asm volatile("prefetch.global.L1 [%0];\n" ::"l"(b.x0 + o));
+          asm volatile("prefetch.global.L1 [%0];\n" ::"l"(b.y0 + o));
+          if (p0 + p == 1) asm volatile("prefetch.global.L1 [%0];\n" ::"l"(b.aim + o));
+        }
       }
     }
 #pragma unroll
@@ -537,7 +551,7 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
         }
         rhs[p][j][0] = b0.x + hh.x + mu10 * x1.x + v.x;
         rhs[p][j][1] = b0.y + hh.y + mu10 * x1.y + v.y;
-        if (PRE) {
+        if (EARLY) {
           hh_pre[p][j][0] = hh.x;
           hh_pre[p][j][1] = hh.y;
         }
@@ -601,7 +615,7 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
       double xo[1][NT][2], yo[1][NT][2];
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        const double2 v = PRE ? make_double2(xo_pre[p][j][0], xo_pre[p][j][1])
+        const double2 v = EARLY ? make_double2(xo_pre[p][j][0], xo_pre[p][j][1])
                                 : *reinterpret_cast<const double2*>(b.x0 + frag_index(ct0 + p, NT, j, lane));
         xo[0][j][0] = v.x;
         xo[0][j][1] = v.y;
@@ -610,7 +624,7 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
       }
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        const double2 v = PRE ? make_double2(yo_pre[p][j][0], yo_pre[p][j][1])
+        const double2 v = EARLY ? make_double2(yo_pre[p][j][0], yo_pre[p][j][1])
                                 : *reinterpret_cast<const double2*>(b.y0 + frag_index(ct0 + p, NT, j, lane));
         yo[0][j][0] = v.x;
         yo[0][j][1] = v.y;
@@ -647,7 +661,7 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       const size_t o = frag_index(ct0 + p, NT, j, lane);
-      const double2 hh = PRE ? make_double2(hh_pre[p][j][0], hh_pre[p][j][1]) : *reinterpret_cast<const double2*>(b.h10 + o);
+      const double2 hh = EARLY ? make_double2(hh_pre[p][j][0], hh_pre[p][j][1]) : *reinterpret_cast<const double2*>(b.h10 + o);
       double zz[2], hn[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
@@ -779,6 +793,19 @@ enum { PASS_STEP = 0, PASS_VINIT = 1 };
 // sign-bit helpers on the integer pipe (the FP64 pipe is shared with DMMA: keep it for the MMAs)
 __device__ __forceinline__ bool is_neg(double v) { return __double2hiint(v) < 0; }
 
+#ifdef SPM_TRACE   // tools only: %globaltimer stamps (ns) of CTAs 0, 1 and the last one into b.gpart: [launch & 7][cta slot][8]
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+#define PASS_STAMP(idx)                                                                                         \
+  if (threadIdx.x == 0 && (blockIdx.x < 2 || blockIdx.x == gridDim.x - 1))                                      \
+    reinterpret_cast<long long*>(b.gpart)[((trace_launch & 7) * 3 + (blockIdx.x < 2 ? blockIdx.x : 2)) * 8 + (idx)] = gtimer();
+#else
+#define PASS_STAMP(idx)
+#endif
+
 template <int NT, int MT>
 struct PassSmem {
   static constexpr int TILE_D = 2 * NT * 64;                          // doubles of Pf per 8-row tile
@@ -813,7 +840,16 @@ struct PassSmem {
 template <int NT, int MT, int MODE, int FNP, bool BAL = false>   // FNP: 0 = pass only, 1/2 = fused x-update of 1/2 planes
 __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4)      // (shared memory admits 3 CTAs per SM for NT = 5)
     spm_pass_kernel(admm_spm_dims d, admm_spm_buffers b, admm_peer_comm c, int lazy, int nA) {
+#ifdef SPM_TRACE
+  const long long t_entry = gtimer();
+#endif
   pdl_prologue();
+#ifdef SPM_TRACE
+  const int trace_launch = b.lazy[3];
+  if (threadIdx.x == 0 && (blockIdx.x < 2 || blockIdx.x == gridDim.x - 1))
+    reinterpret_cast<long long*>(b.gpart)[((trace_launch & 7) * 3 + (blockIdx.x < 2 ? blockIdx.x : 2)) * 8 + 7] = t_entry;
+#endif
+  PASS_STAMP(0)
   __shared__ double wsum[PASS_WARPS * 10];        // lazy: partial sums of the ten squared norms, one row per warp
   if (MODE == PASS_STEP && d.batch_wide && b.lazy != nullptr) {
     // the fused kernel opens the iteration (decision of the previous one); the stand-alone pass follows the x-update
@@ -860,32 +896,61 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
     fence_barrier_init();
   }
   if (MODE == PASS_STEP && lazy && lane < 10) wsum[warp * 10 + lane] = 0.0;      // (own row: ordered by program order per warp)
-  __syncthreads();
-  if (tid == 0) {
-    for (int s = 0; s < PASS_STAGES && s < nchunks; ++s) fill(s, g_begin + s);
-  }
-
+  // BAL: sequence number of this launch (the CTA that finishes last advances lazy[3]) and the group this CTA owns
   int bal_stamp = 0, bal_own_grp = -1;
   if (BAL) {
-    // sequence number of this launch (the CTA that finishes last advances lazy[3]) and the group this CTA owns
-    constexpr int NPL = FNP == 0 ? 1 : FNP;
     bal_stamp = __ldcg(b.lazy + 3) + 1;
     const long long T = (long long)((d.npt + GT - 1) / GT) * nct;
     const int grp0 = (int)(g_begin / nct);
     const int first = (int)(((long long)grp0 * nct * d.nbal + T - 1) / T);       // first CTA whose piece starts in grp0
-    if ((int)blockIdx.x == first && nchunks > 0) {
-      bal_own_grp = grp0;
-      double* wp = lazy ? wsum + warp * 10 : nullptr;
+    if ((int)blockIdx.x == first && nchunks > 0) bal_own_grp = grp0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // (an owner CTA stages the operands of its x-update in ring stage 1 first: that stage is filled afterwards)
+    for (int s = 0; s < PASS_STAGES && s < nchunks; ++s)
+      if (!(BAL && bal_own_grp >= 0 && s == 1)) fill(s, g_begin + s);
+  }
+
+  PASS_STAMP(1)
+  if (BAL && bal_own_grp >= 0) {
+    // ---- owner: x-update of the group's tiles, every warp one tile (all planes)
+    constexpr int NPL = FNP == 0 ? 1 : FNP;
+    constexpr int OPD = NT * NT * 64;                                       // doubles per L x L operand
+    constexpr bool BOTH = 2 * OPD <= STAGE_D;                               // room for P^T P and the cached inverse?
+    static_assert(OPD <= STAGE_D, "ring stage too small for a staged operand");
+    double* sm_ops = ring + STAGE_D;                                        // ring stage 1
+    const int grp0 = bal_own_grp;
+    const int pfirst = min(8 * grp0 * GT, 8 * d.npt - 1);
+    const int slot0 = b.slot[pfirst];                                       // batch-wide: the factor row of all problems
+    if (BOTH) {
+      for (int i = tid; i < OPD / 2; i += PASS_WARPS * 32) cp_async16(sm_ops + OPD + 2 * i, b.PtPf + 2 * i);
+    }
+    {
+      const double* gi = b.Ginv_cache + (size_t)slot0 * d.Lp * d.Lp;
+      for (int i = tid; i < OPD / 2; i += PASS_WARPS * 32) cp_async16(sm_ops + 2 * i, gi + 2 * i);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    double* wp = lazy ? wsum + warp * 10 : nullptr;
 #pragma unroll 1
-      for (int m = 0; m < MT; ++m) {
-        const int ptm = (grp0 * PASS_WARPS + warp) * MT + m;
-        if (ptm < d.npt) xupdate_tile<NT, NPL, true>(d, b, ptm, lane, 0, wp);
+    for (int m = 0; m < MT; ++m) {
+      const int ptm = (grp0 * PASS_WARPS + warp) * MT + m;
+      if (ptm < d.npt)
+        xupdate_tile<NT, NPL, true, true, false>(d, b, ptm, lane, 0, wp, BOTH ? sm_ops + OPD : nullptr, sm_ops, slot0);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(b.xready + grp0), "r"(bal_stamp) : "memory");
+      if (nchunks > 1) {
+        fence_proxy_async();               // the staged operands were written through the generic proxy
+        fill(1, g_begin + 1);
       }
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(b.xready + grp0), "r"(bal_stamp) : "memory");
     }
   }
+  PASS_STAMP(2)
   if (FNP != 0 && !BAL) {
     // x-update of this warp's tiles right here (all planes): x0 reaches the MMA operand registers
     // through L1/L2; the pass of the other CTAs of the SM hides the latency of this L x L work.
@@ -968,6 +1033,7 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
       all_done = all_done && dn[m];
     }
     const bool active = !__all_sync(0xffffffffu, all_done);
+    PASS_STAMP(3)
 
     double n_dh[MT], n_xm[MT], ratio[MT];
 #pragma unroll
@@ -1074,6 +1140,7 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
       }
     }
 
+    PASS_STAMP(4)
     // ---- epilogue of the segment: partial V (fragment layout) and per-column norm partials
     if (active) {
 #pragma unroll
@@ -1109,6 +1176,7 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
       }
     }
   }
+  PASS_STAMP(5)
   if (MODE == PASS_STEP && lazy) {
     const int ncta = gridDim.x * gridDim.y;
     lazy_tail(b, c, wsum, PASS_WARPS, FNP != 0, true, FNP != 0 ? ncta : nA, FNP != 0 ? 0 : ncta, ring,     // (ring: all chunks consumed)
@@ -1124,6 +1192,7 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
       }
     }
   }
+  PASS_STAMP(6)
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -187,6 +187,19 @@ def spd_inverse(A: torch.Tensor):
     return out
 
 
+def hpd_inverse(A: torch.Tensor):
+    """Inverse of a complex Hermitian positive definite matrix on the tensor cores (real form of order 2n through the
+    batched SPD kernels); returns None when a non-positive pivot shows up (caller falls back to `inverse`)."""
+    n = A.shape[0]
+    out = A.contiguous().clone()
+    work = torch.empty(4 * n * n, dtype=F64, device=A.device)
+    info = torch.zeros(1, dtype=torch.int32, device=A.device)
+    call("admm_hpd_inverse_batched", n, 1, ptr(out), n * n, n, ptr(work), None, ptr(info), stream())
+    if int(info.item()) != 0:
+        return None
+    return out
+
+
 def inverse(A: torch.Tensor) -> torch.Tensor:
     """General inverse (Gauss-Jordan with partial pivoting on the device)."""
     n = A.shape[0]

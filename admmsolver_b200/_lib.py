@@ -21,12 +21,18 @@ if not os.path.exists(LIB_PATH):
 
 lib = C.CDLL(LIB_PATH)
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 OP_N, OP_T, OP_H = 0, 1, 2
 
 
 class AdmmError(RuntimeError):
     pass
+
+
+class CoResidencyError(AdmmError):
+    """A kernel whose CTAs wait for each other inside one launch gave up (in-kernel watchdog): its CTAs were not all
+    resident at the same time.  Only possible with plain launches (``admm_spm_launch_mode`` 3); ``SharedSpM.solve``
+    restores the state it saved before and repeats the solve with the kernels that need no co-residency."""
 
 
 class SpmDims(C.Structure):
@@ -89,6 +95,7 @@ _SIGS = {
     "admm_pair_norms": ([_LL, _P, _P, _LL, _P, _P, _P, _P, _P], _I),
     "admm_inverse": ([_I, _I, _P, _I, _P, _I, _P, _P, _P], _I),
     "admm_spd_inverse_batched": ([_I, _I, _P, _LL, _I, _P, _P, _P], _I),
+    "admm_hpd_inverse_batched": ([_I, _I, _P, _LL, _I, _P, _P, _P, _P], _I),
     "admm_spm_prepare_P": ([C.POINTER(SpmDims), _P, _I, _P, _P], _I),
     "admm_spm_pack_operator": ([C.POINTER(SpmDims), _P, _P, _P], _I),
     "admm_spm_pack_L": ([C.POINTER(SpmDims), _P, _I, _P, _P], _I),
@@ -115,6 +122,7 @@ _SIGS = {
     "admm_spm_pass_lazy": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), C.POINTER(PeerComm), _P], _I),
     "admm_spm_flush": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), C.POINTER(PeerComm), _P], _I),
     "admm_spm_solo_supported": ([C.POINTER(SpmDims)], _I),
+    "admm_spm_launch_mode": ([_I], _I),
     "admm_spm_solo": ([C.POINTER(SpmDims), C.POINTER(SpmBuffers), _P, _P, _I, _I, _P], _I),
     "admm_bp_supported": ([_I, _I], _I),
     "admm_bp_setup": ([C.POINTER(BpBuffers), _P, _P, _P, _P], _I),
@@ -132,7 +140,7 @@ if lib.admm_abi_version() != ABI_VERSION:
 
 #: number of kernel launches issued through this binding (bench.py reports it as gpu_launches)
 launch_count = 0
-_LAUNCHES_PER_CALL = {"admm_peer_alloc": 0, "admm_peer_open": 0, "admm_peer_close": 0, "admm_peer_free": 0, "admm_sumsq": 2, "admm_pair_norms": 2, "admm_spm_reduce": 2, "admm_spm_reduce_decide": 2, "admm_bp_factor": 3, "admm_bp_setup": 2}
+_LAUNCHES_PER_CALL = {"admm_peer_alloc": 0, "admm_peer_open": 0, "admm_peer_close": 0, "admm_peer_free": 0, "admm_sumsq": 2, "admm_pair_norms": 2, "admm_spm_reduce": 2, "admm_spm_reduce_decide": 2, "admm_bp_factor": 3, "admm_bp_setup": 2, "admm_hpd_inverse_batched": 3}
 
 
 def check(rc: int) -> None:

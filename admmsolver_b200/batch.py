@@ -241,6 +241,8 @@ class SharedSpM:
         # x-update, the whole iteration of a small batch is one launch); 0: x-update kernel + pass kernel
         self._step_mode = int(_lib.lib.admm_spm_step_supported(C.byref(self.dims)))
         self.use_lazy = True          # tests switch it off to compare with the three-kernel iteration
+        self._no_solo_bw = False      # set after a co-residency failure of the batch-wide cluster-resident solve
+        self._inject_coresidency_failure = False
         self._lazy_pending = False    # a launched lazy iteration still awaits its decision (next kernel's head or flush)
         self.iter_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.flags = torch.zeros(4, dtype=torch.int32, device=dev)
@@ -558,8 +560,8 @@ class SharedSpM:
         self._flush()
         fl = self.flags.cpu()
         if int(fl[2]) == -3:
-            raise _lib.AdmmError("fused balanced step: the CTAs of the launch were not co-resident (another kernel holding "
-                                 "SMs?); the state is undefined -- set ADMM_SPM_TWO_KERNELS=1 to use the two-kernel iteration")
+            raise _lib.CoResidencyError("fused balanced step: the CTAs of the launch were not co-resident (another kernel "
+                                        "holding SMs?)")
         if int(fl[2]) == -2:
             raise _lib.AdmmError("sharded batch-wide criterion: a peer rank never posted its residual sums "
                                  "(watchdog of admm_spm_decide_peer); the state is undefined")
@@ -579,11 +581,72 @@ class SharedSpM:
     #: 32 problems 3.7x, 64: 2.5x, 128: 1.5x faster, 256: 0.9x)
     SOLO_MAX_NB = 128
 
+    # ------------------------------------------------------------------ co-residency safety net
+    _SNAP_TENSORS = ("x0f", "x1f", "h10f", "y0f", "V", "aim", "S", "mu10", "mu20", "mu20_used", "slot", "done", "iters",
+                     "last_res", "x0_oldf")
+
+    def _snapshot(self):
+        snap = {n: getattr(self, n).clone() for n in self._SNAP_TENSORS if getattr(self, n) is not None}
+        snap["_host"] = (self._v_valid, self._fresh, len(self.primal_residual), len(self.dual_residual), dict(self._slot_of))
+        return snap
+
+    def _restore(self, snap) -> None:
+        for n in self._SNAP_TENSORS:
+            if n in snap:
+                getattr(self, n).copy_(snap[n])
+        self._v_valid, self._fresh, npr, ndu, slot_of = snap["_host"]
+        del self.primal_residual[npr:], self.dual_residual[ndu:]
+        # factor rows computed meanwhile stay valid (they are keyed by the penalties); keep the larger map
+        for k, v in slot_of.items():
+            self._slot_of.setdefault(k, v)
+        self.flags.zero_()
+        self.lazy[:3].zero_()
+        self._lazy_pending = False
+
+    def _risky_launch_mode(self, use_solo: Optional[bool], callback) -> bool:
+        """Will this solve use a kernel whose CTAs wait for each other, launched WITHOUT the driver's co-residency
+        guarantee (plain launch, or not yet probed on this device)?"""
+        bal = self._step_mode == 2 and int(_lib.lib.admm_spm_launch_mode(0)) not in (1, 2)
+        solo_bw = (self.batch_wide and 1 < self.nb <= self.SOLO_MAX_NB and callback is None and self.group is None
+                   and use_solo is not False and not self._no_solo_bw
+                   and int(_lib.lib.admm_spm_launch_mode(1)) != 2)
+        return bal or solo_bw
+
     def solve(self, niter: int = 10000, interval_update_mu: int = 100, rtol: float = 1e-12,
               callback=None, keep_history: Optional[bool] = None, use_graph: Optional[bool] = None,
               use_solo: Optional[bool] = None) -> int:
         """Run up to ``niter`` iterations with the ordering of ``SimpleOptimizer.solve``
         (optimizer.py:302-320).  Returns the number of iterations launched.
+
+        Two launch shapes let CTAs wait for each other inside one launch (the fused balanced step of a small batch and
+        the batch-wide cluster-resident solve).  They are launched cooperatively, so the driver guarantees that their
+        CTAs are resident together.  Where that is not available (``admm_spm_launch_mode`` 3, or not probed yet) the
+        state is saved first; should the in-kernel watchdog ever give up (``CoResidencyError``), the state is restored
+        and the solve repeated with the kernels that need no co-residency -- the caller never sees an undefined state."""
+        snap = self._snapshot() if self._risky_launch_mode(use_solo, callback) else None
+        try:
+            n = self._solve_impl(niter, interval_update_mu, rtol, callback, keep_history, use_graph, use_solo)
+            if self._inject_coresidency_failure:      # tests: exercise the recovery path
+                self._inject_coresidency_failure = False
+                raise _lib.CoResidencyError("injected")
+            return n
+        except _lib.CoResidencyError:
+            if snap is None:
+                raise
+            import warnings
+            warnings.warn("admmsolver_b200: CTAs of a single-launch iteration were not co-resident (another kernel holding "
+                          "SMs?); repeating the solve with the multi-kernel iteration", RuntimeWarning)
+            torch.cuda.synchronize()
+            self._restore(snap)
+            if self._step_mode == 2:
+                self._step_mode = 0
+            self._no_solo_bw = True
+            self._graphs.clear()
+            return self._solve_impl(niter, interval_update_mu, rtol, callback, keep_history, use_graph,
+                                    False if (self.batch_wide and self.nb > 1) else use_solo)
+
+    def _solve_impl(self, niter, interval_update_mu, rtol, callback, keep_history, use_graph, use_solo) -> int:
+        """The loop of ``solve`` (see there).
 
         A single problem (or a handful with the per-problem criterion) and no callback: the whole
         loop is ONE launch of the cluster-resident kernel (``admm_spm_solo``; ``use_solo``).
@@ -610,6 +673,7 @@ class SharedSpM:
             use_graph = (callback is None and self.pass_events is None
                          and (self.group is None or not self.batch_wide or self._peer is not None))
         solo_ok = (callback is None and self.pass_events is None and self.group is None and nb <= self.SOLO_MAX_NB
+                   and not (self._no_solo_bw and self.batch_wide and nb > 1)
                    and _lib.lib.admm_spm_solo_supported(C.byref(self.dims)) != 0)     # batch-wide: co-resident clusters only
         if use_solo is None:
             use_solo = solo_ok and use_graph
@@ -625,9 +689,8 @@ class SharedSpM:
             self._v_valid, self._fresh = True, False
             fl = torch.cat([self.flags, self.iters[:nb]]).cpu()        # one read-back: flags and iteration counts
             if int(fl[2]) < 0:
-                raise _lib.AdmmError("cluster-resident solve: the clusters of the batch did not become co-resident "
-                                     "(another kernel holding SMs?); the state is undefined -- reset() and solve again "
-                                     "with use_solo=False")
+                raise _lib.CoResidencyError("cluster-resident solve: the clusters of the batch did not become co-resident "
+                                            "(another kernel holding SMs?)")
             if int(fl[2]) != 0:
                 raise _lib.AdmmError("alpha A^H A + mu is not positive definite")
             if int(fl[0]) != 0:

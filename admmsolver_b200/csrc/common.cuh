@@ -164,6 +164,8 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;\n" ::: "memory");
 }
 // launch with programmatic stream serialisation (every kernel launched this way starts with pdl_prologue())
+// coop: cooperative launch -- the driver guarantees that all CTAs of the grid are resident at the same time (or fails
+// the launch up front), which is what the kernels that wait for each other inside one launch rely on.
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
                               Args... args) {
@@ -177,6 +179,23 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_coop(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                               Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 

@@ -129,7 +129,14 @@ __global__ void __launch_bounds__(256) gemm_kernel(int m, int n, int k, const T*
 // This is the x-update GEMM of a generic LeastSquares term whose right-hand sides share one A
 // (PartialDiagonalMatrix packing): B = (alpha A^H A + mu)^-1 times an (N x nbatch) block.
 // ---------------------------------------------------------------------------------------------
-template <int OP>
+//
+// CPLX: a complex128 product on the same tensor-core path through its real form -- no operand is copied or split.
+// With interleaved storage a complex row IS the real row (Re, Im, Re, Im, ...), so for C = op(A) B
+//     C_view (m x 2n) = A' (m x 2k) * B' (2k x 2n),   A'[i][2l+e] = part_e(op(A)[i][l]),
+//     B'[2l][c] = B_view[l][c],   B'[2l+1][c] = (J B_view)[l][c]  with  J: (re, im) -> (-im, re)
+// which are exactly the four real products Ar Br - Ai Bi, Ar Bi + Ai Br (8 m n k flops, nothing wasted).  The kernel
+// is called with the REAL dimensions (m, 2n, 2k) and leading dimensions in doubles; only the loaders differ.
+template <int OP, bool CPLX>
 __global__ void __launch_bounds__(128) gemm_dmma_kernel(int m, int n, int k, const double* __restrict__ A, int lda,
                                                         const double* __restrict__ B, int ldb, double* __restrict__ C,
                                                         int ldc) {
@@ -154,13 +161,31 @@ __global__ void __launch_bounds__(128) gemm_dmma_kernel(int m, int n, int k, con
       if (OP == ADMM_OP_N) {
         const int i = idx >> 4, kk = idx & 15;  // coalesced along k
         if (row0 + i < m && k0 + kk < k) a = A[(size_t)(row0 + i) * lda + k0 + kk];
-      } else {
+      } else if (!CPLX) {
         const int kk = idx >> 6, i = idx & 63;  // A stored k x m: coalesced along m
         if (row0 + i < m && k0 + kk < k) a = A[(size_t)(k0 + kk) * lda + row0 + i];
+      } else {
+        const int kk = idx >> 6, i = idx & 63;  // A stored (k/2) x m complex: part e of element (l, i)
+        if (row0 + i < m && k0 + kk < k) {
+          const int l = (k0 + kk) >> 1, e = (k0 + kk) & 1;
+          a = A[(size_t)l * lda + 2 * (row0 + i) + e];
+          if (OP == ADMM_OP_H && e) a = -a;
+        }
       }
       ra[q] = a;
       const int kb = idx >> 6, j = idx & 63;    // coalesced along n
-      rb[q] = (k0 + kb < k && col0 + j < n) ? B[(size_t)(k0 + kb) * ldb + col0 + j] : 0.0;
+      if (!CPLX) {
+        rb[q] = (k0 + kb < k && col0 + j < n) ? B[(size_t)(k0 + kb) * ldb + col0 + j] : 0.0;
+      } else {
+        double bv = 0.0;
+        if (k0 + kb < k && col0 + j < n) {
+          const double* br = B + (size_t)((k0 + kb) >> 1) * ldb;
+          const int c = col0 + j;
+          if (((k0 + kb) & 1) == 0) bv = br[c];
+          else bv = (c & 1) ? br[c - 1] : -br[c + 1];
+        }
+        rb[q] = bv;
+      }
     }
   };
   auto store_tiles = [&]() {
@@ -931,6 +956,45 @@ __global__ void __launch_bounds__(SPDG_WARPS * 32, 1)
 
 using namespace admm;
 
+// ---------------------------------------------------------------------------------------------
+// Hermitian positive definite complex128 inverse on the tensor cores, batched: H = X + iY (X symmetric, Y
+// antisymmetric) is HPD iff its real form [[X, -Y], [Y, X]] (2n x 2n) is SPD, and the inverse of the real form is the
+// real form of H^-1.  So the batched SPD block Gauss-Jordan on DMMA above does the work; these two kernels only
+// move the numbers (interleaved complex <-> real form in `work`).
+// ---------------------------------------------------------------------------------------------
+__global__ void hpd_embed_kernel(int n, int nbatch, const cplx* __restrict__ A, long long bstride, int lda,
+                                 double* __restrict__ W, const int* __restrict__ mask) {
+  const long long tot = (long long)nbatch * n * n;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < tot; q += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(q / ((long long)n * n));
+    if (mask != nullptr && mask[b] == 0) continue;
+    const int r = (int)(q % ((long long)n * n));
+    const int i = r / n, j = r % n;
+    const cplx v = A[(size_t)b * bstride + (size_t)i * lda + j];
+    double* w = W + (size_t)b * 4 * n * n;
+    const int n2 = 2 * n;
+    w[(size_t)i * n2 + j] = v.x;
+    w[(size_t)i * n2 + n + j] = -v.y;
+    w[(size_t)(n + i) * n2 + j] = v.y;
+    w[(size_t)(n + i) * n2 + n + j] = v.x;
+  }
+}
+
+__global__ void hpd_extract_kernel(int n, int nbatch, const double* __restrict__ W, cplx* __restrict__ A, long long bstride,
+                                   int lda, const int* __restrict__ mask, const int* __restrict__ info) {
+  const long long tot = (long long)nbatch * n * n;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < tot; q += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(q / ((long long)n * n));
+    if (mask != nullptr && mask[b] == 0) continue;
+    if (info != nullptr && info[b] != 0) continue;       // not positive definite: the input stays untouched
+    const int r = (int)(q % ((long long)n * n));
+    const int i = r / n, j = r % n;
+    const double* w = W + (size_t)b * 4 * n * n;
+    const int n2 = 2 * n;
+    A[(size_t)b * bstride + (size_t)i * lda + j] = {w[(size_t)i * n2 + j], w[(size_t)(n + i) * n2 + j]};
+  }
+}
+
 extern "C" {
 
 int admm_abi_version(void) { return ADMM_ABI_VERSION; }
@@ -962,9 +1026,23 @@ int admm_gemm(int is_complex, int op_a, int m, int n, int k, const void* A, int 
     const double* a = static_cast<const double*>(A);
     const double* b = static_cast<const double*>(B);
     double* c = static_cast<double*>(C);
-    if (op_a == ADMM_OP_N) gemm_dmma_kernel<ADMM_OP_N><<<grid, 128, 0, s>>>(m, n, k, a, lda, b, ldb, c, ldc);
-    else gemm_dmma_kernel<ADMM_OP_T><<<grid, 128, 0, s>>>(m, n, k, a, lda, b, ldb, c, ldc);
+    if (op_a == ADMM_OP_N) gemm_dmma_kernel<ADMM_OP_N, false><<<grid, 128, 0, s>>>(m, n, k, a, lda, b, ldb, c, ldc);
+    else gemm_dmma_kernel<ADMM_OP_T, false><<<grid, 128, 0, s>>>(m, n, k, a, lda, b, ldb, c, ldc);
     return check_launch("admm_gemm(dmma)");
+  }
+  if (is_complex && m >= 32 && n >= 16 && k >= 8 && !getenv("ADMM_GEMM_SCALAR")) {
+    // complex128 on the tensor cores: the real form of the product (see gemm_dmma_kernel), dimensions in doubles
+    dim3 grid(ceil_div(2 * n, 64), ceil_div(m, 64));
+    const double* a = static_cast<const double*>(A);
+    const double* b = static_cast<const double*>(B);
+    double* c = static_cast<double*>(C);
+    if (op_a == ADMM_OP_N)
+      gemm_dmma_kernel<ADMM_OP_N, true><<<grid, 128, 0, s>>>(m, 2 * n, 2 * k, a, 2 * lda, b, 2 * ldb, c, 2 * ldc);
+    else if (op_a == ADMM_OP_T)
+      gemm_dmma_kernel<ADMM_OP_T, true><<<grid, 128, 0, s>>>(m, 2 * n, 2 * k, a, 2 * lda, b, 2 * ldb, c, 2 * ldc);
+    else
+      gemm_dmma_kernel<ADMM_OP_H, true><<<grid, 128, 0, s>>>(m, 2 * n, 2 * k, a, 2 * lda, b, 2 * ldb, c, 2 * ldc);
+    return check_launch("admm_gemm(zdmma)");
   }
   return is_complex ? launch_gemm<cplx>(op_a, m, n, k, A, lda, B, ldb, C, ldc, s)
                     : launch_gemm<double>(op_a, m, n, k, A, lda, B, ldb, C, ldc, s);
@@ -1097,6 +1175,20 @@ int admm_spd_inverse_batched(int n, int nbatch, double* A, long long batch_strid
     spd_inverse_kernel<false><<<nbatch, 512, 2 * n * sizeof(double), s>>>(n, A, batch_stride, lda, mask, info);
   }
   return check_launch("admm_spd_inverse_batched");
+}
+
+int admm_hpd_inverse_batched(int n, int nbatch, void* A, long long batch_stride, int lda, double* work, const int* mask,
+                             int* info, admm_stream_t stream) {
+  ADMM_REQUIRE(n > 0 && n <= 2048 && nbatch >= 0 && lda >= n && work != nullptr, ADMM_EINVAL,
+               "admm_hpd_inverse_batched: bad dims");
+  if (nbatch == 0) return ADMM_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long tot = (long long)nbatch * n * n;
+  hpd_embed_kernel<<<ew_grid(tot), 256, 0, s>>>(n, nbatch, static_cast<const cplx*>(A), batch_stride, lda, work, mask);
+  if (int rc = check_launch("admm_hpd_inverse_batched(embed)")) return rc;
+  if (int rc = admm_spd_inverse_batched(2 * n, nbatch, work, 4LL * n * n, 2 * n, mask, info, stream)) return rc;
+  hpd_extract_kernel<<<ew_grid(tot), 256, 0, s>>>(n, nbatch, work, static_cast<cplx*>(A), batch_stride, lda, mask, info);
+  return check_launch("admm_hpd_inverse_batched(extract)");
 }
 
 }  // extern "C"

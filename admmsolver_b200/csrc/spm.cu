@@ -2258,6 +2258,16 @@ static bool use_pdl_x() {      // the stand-alone x-update kernel (ADMM_NO_PDL_X
 
 static int ew_grid(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 16)); }
 
+// how kernels whose CTAs wait for each other are launched, per device (see launch_pass_k / launch_solo)
+static std::map<int, int>& coop_mode() {
+  static std::map<int, int> m;
+  return m;
+}
+static std::map<int, int>& coop_mode_solo() {
+  static std::map<int, int> m;
+  return m;
+}
+
 struct LazyArgs {          // how a pass / step launch takes part in the lazy batch-wide scheme (all zero: classic)
   admm_peer_comm comm;     // world == 0: one rank, the sums go through gsum
   int lazy;                // 0 classic, 1 lazy without, 2 lazy with a pending decision
@@ -2293,6 +2303,20 @@ static int launch_pass_k(const admm_spm_dims* d, const admm_spm_buffers* b, cuda
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cfgd = true;
+  }
+  if (BAL) {
+    // the CTAs of this launch wait for each other (owner CTAs publish x0): cooperative launch, so that the driver
+    // guarantees their co-residency whatever else runs on the device.  Probed once per device: cooperative +
+    // programmatic serialisation, cooperative alone, or (ADMM_NO_COOP=1 / not supported) the plain launch that relies
+    // on the occupancy check of admm_spm_step_supported and the in-kernel watchdog.
+    int& mode = coop_mode()[cur_dev()];      // 0 unprobed, 1 coop + pdl, 2 coop, 3 plain
+    if (mode == 0) mode = getenv("ADMM_NO_COOP") ? 3 : (use_pdl() ? 1 : 2);
+    while (mode < 3) {
+      cudaError_t e = launch_coop(k, grid, dim3(PASS_WARPS * 32), smem, s, mode == 1, *d, *b, lz.comm, lz.lazy, lz.nA);
+      if (e == cudaSuccess) return check_launch("admm_spm_step");
+      cudaGetLastError();
+      ++mode;
+    }
   }
   launch_pdl(k, grid, dim3(PASS_WARPS * 32), smem, s, use_pdl(), *d, *b, lz.comm, lz.lazy, lz.nA);
   return check_launch(FNP ? "admm_spm_step" : "admm_spm_pass");
@@ -2385,11 +2409,13 @@ static int launch_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const 
   cfg.blockDim = dim3(SOLO_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CS;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeCooperative;
+  at[1].val.cooperative = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   if (max_clusters != nullptr) {
@@ -2408,7 +2434,24 @@ static int launch_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const 
     *max_clusters = cached_n;
     return ADMM_OK;
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *d, *b, G0, PtP, niter, interval);
+  cudaError_t e = cudaErrorNotSupported;
+  if (BW) {
+    // the clusters of a batch-wide solve all-reduce through global memory every iteration: cooperative launch (the
+    // driver guarantees co-residency); ADMM_NO_COOP=1 or a driver that refuses the combination with clusters: the
+    // plain launch, which relies on the occupancy check of admm_spm_solo_supported and the in-kernel watchdog
+    int& mode = coop_mode_solo()[cur_dev()];      // 0 unprobed, 1 cooperative, 2 plain
+    if (mode == 0) mode = getenv("ADMM_NO_COOP") ? 2 : 1;
+    if (mode == 1) {
+      cfg.numAttrs = 2;
+      e = cudaLaunchKernelEx(&cfg, kern, *d, *b, G0, PtP, niter, interval);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        mode = 2;
+        cfg.numAttrs = 1;
+      }
+    }
+  }
+  if (e != cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, *d, *b, G0, PtP, niter, interval);
   if (e != cudaSuccess) {
     set_error("admm_spm_solo: %s", cudaGetErrorString(e));
     return ADMM_ECUDA;
@@ -2634,6 +2677,12 @@ static int dispatch_solo(const admm_spm_dims* d, const admm_spm_buffers* b, cons
     default: return SOLO_CASE(64, false);             // 64 doubles per row: shared memory
   }
 #undef SOLO_CASE
+}
+
+int admm_spm_launch_mode(int which) {
+  if (which == 0) return coop_mode()[cur_dev()];
+  const int m = coop_mode_solo()[cur_dev()];
+  return m == 0 ? 0 : (m == 1 ? 2 : 3);
 }
 
 int admm_spm_solo_supported(const admm_spm_dims* d) {

@@ -11,6 +11,11 @@ the device -- that is the path the optimizer uses.
 
 Structure-preserving dispatch follows the reference line by line in *behaviour* (which result type
 each pair of operand types yields -- matrix.py:100-118, 255-295, 342-354, 453-513), not in code.
+
+The class / method names and the name-based ``_add_X_Y`` dispatch skeleton are the reference's public
+API and are therefore derived from it:
+    SPDX-License-Identifier: MIT
+    admmsolver -- Copyright (c) 2021- Hiroshi Shinaoka and others (LICENSE.txt of SpM-lab/admmsolver)
 """
 from __future__ import annotations
 

@@ -31,14 +31,23 @@ Vec = Union[np.ndarray, torch.Tensor]
 
 def _inv_hpd(G: MatrixBase) -> MatrixBase:
     """(alpha A^H A + mu)^-1.  A real dense G of this form is symmetric; when it is also positive definite
-    (mu >= 0, the case of every ADMM penalty) the batched tensor-core SPD inverse does it, otherwise --
-    complex, structured or indefinite G -- the matrix type's own inv()."""
+    (mu >= 0, the case of every ADMM penalty) the batched tensor-core SPD inverse does it; a complex Hermitian positive
+    definite G (complex A) goes through the same kernels in its real form of order 2n; otherwise -- structured or
+    indefinite G -- the matrix type's own inv()."""
     if isinstance(G, DenseMatrix):
         g = G._dense_dev()
         if not g.is_complex() and g.shape[0] == g.shape[1] and g.shape[0] <= 512:
             sym = bool(torch.equal(g, g.t())) or float((g - g.t()).abs().max()) <= 1e-13 * float(g.abs().max())
             if sym:
                 out = D.spd_inverse(g)
+                if out is not None:
+                    return DenseMatrix(out)
+        elif g.is_complex() and g.shape[0] == g.shape[1] and g.shape[0] <= 256:
+            # complex A: alpha A^H A + mu is Hermitian; its real form of order 2n goes through the same kernels
+            gh = g.conj().t()
+            herm = bool(torch.equal(g, gh)) or float((g - gh).abs().max()) <= 1e-13 * float(g.abs().max())
+            if herm:
+                out = D.hpd_inverse(g)
                 if out is not None:
                     return DenseMatrix(out)
     return G.inv()

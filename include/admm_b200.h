@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ADMM_ABI_VERSION 3
+#define ADMM_ABI_VERSION 4
 
 enum admm_status { ADMM_OK = 0, ADMM_EINVAL = 1, ADMM_ECUDA = 2, ADMM_EUNSUPPORTED = 3 };
 enum admm_op { ADMM_OP_N = 0, ADMM_OP_T = 1, ADMM_OP_H = 2 };
@@ -112,6 +112,15 @@ int admm_inverse(int is_complex, int n, const void* A, int lda, void* Ainv, int 
  * pivot, 0 if none.  Used for (alpha A^H A + mu)^-1 (objectivefunc.py:89-96): the factor that is
  * cached per mu. */
 int admm_spd_inverse_batched(int n, int nbatch, double* A, long long batch_stride, int lda,
+                             const int* mask, int* info, admm_stream_t stream);
+
+/* Batched inverse of complex128 Hermitian positive-definite matrices (interleaved storage), in place, on the same
+ * FP64 tensor-core block Gauss-Jordan: H = X + iY is HPD iff its real form [[X, -Y], [Y, X]] (2n x 2n) is SPD, and the
+ * inverse of the real form is the real form of H^-1.  `work` holds nbatch * (2n)^2 doubles; batch_stride and lda count
+ * complex elements; mask / info as above (a matrix whose info is non-zero is left untouched).  This is the cached
+ * factor (alpha A^H A + mu)^-1 of a LeastSquares / ConstrainedLeastSquares / L2Regularizer term with a complex A
+ * (objectivefunc.py:76-77,89-96). */
+int admm_hpd_inverse_batched(int n, int nbatch, void* A, long long batch_stride, int lda, double* work,
                              const int* mask, int* info, admm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------ */
@@ -374,6 +383,12 @@ int admm_spm_flush(const admm_spm_dims* d, const admm_spm_buffers* b, const admm
  * admm_spm_solo_supported: cluster size used (8) if L, Nw fit the cluster's shared memory (and, batch-wide, the nb
  * clusters fit the GPU at once), else 0. */
 int admm_spm_solo_supported(const admm_spm_dims* d);
+/* How the two kernels whose CTAs wait for each other inside ONE launch were last launched on the current device
+ * (which = 0: fused balanced step of admm_spm_step / admm_spm_step_lazy; which = 1: batch-wide admm_spm_solo):
+ * 0 not launched yet, 1 cooperative launch (co-residency guaranteed by the driver) with programmatic stream
+ * serialisation, 2 cooperative launch, 3 plain launch (ADMM_NO_COOP=1, or the driver refused the combination:
+ * co-residency then rests on the occupancy check and the in-kernel watchdog, flags[2] = -3 / -1). */
+int admm_spm_launch_mode(int which);
 int admm_spm_solo(const admm_spm_dims* d, const admm_spm_buffers* b, const double* G0, const double* PtP,
                   int niter, int interval_update_mu, admm_stream_t stream);
 

@@ -274,12 +274,49 @@ def main_after():
     save("after_solve", **out)
 
 
+def main_complex():
+    """Complex operators through the reference's loop (objectivefunc.py:76-77,89-96; matrix.py:100-118): a complex LASSO
+    and a packed, constrained 3-term model whose A, C (two rows), D and coupling matrix are all complex.
+    `python tests/golden/make_golden.py complex`."""
+    rs = np.random.RandomState(2024)
+    cr = lambda *sh: rs.randn(*sh) + 1j * rs.randn(*sh)
+    out = {}
+    # (a) complex LASSO, 60 x 100
+    M, N = 60, 100
+    A = cr(M, N)
+    xt = np.zeros(N, dtype=complex)
+    xt[rs.permutation(N)[:8]] = rs.randn(8)
+    y = A @ xt + 1e-3 * cr(M)
+    opt = SimpleOptimizer(Model([LeastSquares(0.8, A, y), L1Regularizer(0.15, N)], [(1, 0, identity(N), identity(N))]))
+    opt.solve(200, interval_update_mu=25)
+    out.update(a_A=A, a_y=y, a_x0=opt.x[0], a_x1=opt.x[1], a_h10=opt._h[1, 0], a_mu10=opt._mu[1, 0],
+               a_primal=np.array(opt._primal_residual), a_dual=np.array(opt._dual_residual), a_objective=opt(opt.x))
+    # (b) packed batch of nb = 48 constrained problems sharing complex A (40 x 36), complex C (2 x 36), complex dense
+    #     coupling P (50 x 36) to a non-negative block; batch-wide mu / stopping
+    nb, Mb, Lb, Nwb = 48, 40, 36, 50
+    Ab, Cb, Pb = cr(Mb, Lb), cr(2, Lb), cr(Nwb, Lb)
+    yb, Db = cr(Mb * nb), cr(2 * nb)
+    rest = (nb,)
+    terms = [ConstrainedLeastSquares(1.1, PartialDiagonalMatrix(Ab, rest), yb, PartialDiagonalMatrix(Cb, rest), Db),
+             L1Regularizer(0.3, Lb * nb), NonNegativePenalty(Nwb * nb)]
+    conds = [(0, 1, identity(Lb * nb), identity(Lb * nb)), (0, 2, PartialDiagonalMatrix(Pb, rest), identity(Nwb * nb))]
+    opt = SimpleOptimizer(Model(terms, conds), mu=0.5)
+    opt.solve(160, interval_update_mu=20)
+    out.update(b_A=Ab, b_C=Cb, b_P=Pb, b_y=yb, b_D=Db, b_x0=opt.x[0], b_x1=opt.x[1], b_x2=opt.x[2], b_h10=opt._h[1, 0],
+               b_h20=opt._h[2, 0], b_mu10=opt._mu[1, 0], b_mu20=opt._mu[2, 0], b_primal=np.array(opt._primal_residual),
+               b_dual=np.array(opt._dual_residual), b_objective=opt(opt.x))
+    save("complex_ops", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "psd":
         main_psd()
     elif len(sys.argv) > 1 and sys.argv[1] == "after":
         main_after()
+    elif len(sys.argv) > 1 and sys.argv[1] == "complex":
+        main_complex()
     else:
         main()
         main_psd()
         main_after()
+        main_complex()

@@ -492,3 +492,42 @@ def test_model_without_equality_conditions(api):
     opt.solve(50)
     assert opt._primal_residual == [0.0] and opt._dual_residual == [0.0]
     np.testing.assert_allclose(opt.x[0], np.linalg.lstsq(A, y, rcond=None)[0], atol=1e-12)
+
+
+# ------------------------------------------------------------------ complex operators
+def test_complex_operators_through_the_loop(api):
+    """Complex A / C / D / coupling matrices (objectivefunc.py:76-77,89-96,138-157; matrix.py:100-118) against the
+    reference's outputs: (a) complex LASSO; (b) a packed batch of 48 constrained problems sharing complex A, a two-row
+    complex C and a dense complex coupling to a non-negative block.  The products run on the complex tensor-core GEMM,
+    the cached factor (alpha A^H A + mu)^-1 on the Hermitian tensor-core inverse."""
+    M, F, O = api
+    g = golden("complex_ops")
+    N = g["a_A"].shape[1]
+    opt = O.SimpleOptimizer(O.Model([F.LeastSquares(0.8, g["a_A"], g["a_y"]), F.L1Regularizer(0.15, N)],
+                                    [(1, 0, M.identity(N), M.identity(N))]))
+    opt.solve(200, interval_update_mu=25)
+    assert rel(opt.x[0], g["a_x0"]) < TOL and rel(opt.x[1], g["a_x1"]) < TOL
+    assert opt._mu[1, 0] == g["a_mu10"]
+    assert len(opt._primal_residual) == len(g["a_primal"]) and rel(opt._primal_residual, g["a_primal"]) < 1e-8
+    assert abs(opt(opt.x) - g["a_objective"]) / g["a_objective"] < TOL
+
+    nb = 48
+    Lb, Nwb = g["b_A"].shape[1], g["b_P"].shape[0]
+    rest = (nb,)
+    terms = [F.ConstrainedLeastSquares(1.1, M.PartialDiagonalMatrix(g["b_A"], rest), g["b_y"],
+                                       M.PartialDiagonalMatrix(g["b_C"], rest), g["b_D"]),
+             F.L1Regularizer(0.3, Lb * nb), F.NonNegativePenalty(Nwb * nb)]
+    conds = [(0, 1, M.identity(Lb * nb), M.identity(Lb * nb)),
+             (0, 2, M.PartialDiagonalMatrix(g["b_P"], rest), M.identity(Nwb * nb))]
+    opt = O.SimpleOptimizer(O.Model(terms, conds), mu=0.5)
+    assert opt._plan_kind is None                     # complex operators: the generic executor
+    opt.solve(160, interval_update_mu=20)
+    for k in range(3):
+        assert rel(opt.x[k], g[f"b_x{k}"]) < TOL, k
+    assert rel(opt._h[2, 0], g["b_h20"]) < 1e-8
+    assert opt._mu[1, 0] == g["b_mu10"] and opt._mu[2, 0] == g["b_mu20"]
+    assert len(opt._primal_residual) == len(g["b_primal"]) and rel(opt._primal_residual, g["b_primal"]) < 1e-8
+    assert abs(opt(opt.x) - g["b_objective"]) / abs(g["b_objective"]) < TOL
+    # the constraint C x0 = D holds for every problem of the batch
+    x0 = opt.x[0].reshape(Lb, nb)
+    assert np.abs(g["b_C"] @ x0 - g["b_D"].reshape(2, nb)).max() < 1e-10

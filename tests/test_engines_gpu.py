@@ -570,3 +570,42 @@ def test_spm_lazy_iterations_equal_three_kernel_iterations(eng, ir_basis, kw, us
     assert rel(a[1][0], st.x0) < TOL and rel(a[1][4], st.primal) < 1e-8
     st = flat.spm_solve(p.s, p.P, p.C, p.D, p.g, p.lam, 3000, mu=p.mu, interval_update_mu=50, rtol=2e-4, state=st)
     assert st.niter_done == len(a[5]) and rel(a[2], st.x0) < TOL and a[7] == st.mu20
+
+
+# ------------------------------------------------------------------ kernels whose CTAs wait for each other
+@pytest.mark.parametrize("path", ["balanced_step", "solo_batchwide"])
+def test_spm_coresidency_guarantee_and_recovery(eng, ir_basis, path):
+    """The fused balanced step and the batch-wide cluster-resident solve let CTAs wait for each other inside one launch.
+    (1) They are launched cooperatively (admm_spm_launch_mode 1 or 2: the driver guarantees co-residency) unless
+    ADMM_NO_COOP is set.  (2) The safety net of SharedSpM.solve: a CoResidencyError (in-kernel watchdog) restores the
+    state saved before the solve and repeats it with the kernels that need no co-residency -- same result, a warning,
+    never an undefined state."""
+    import os
+    import warnings
+    from admmsolver_b200 import _lib
+    from oracle import flat
+    batch, problems = eng
+    nb = 37 if path == "balanced_step" else 6
+    p = problems.spm_batch(nb, ir_basis, Nw=200, seed=5)
+    st = flat.spm_solve(p.s, p.P, p.C, p.D, p.g, p.lam, 130, mu=p.mu, interval_update_mu=20)
+    kw = dict(use_solo=False) if path == "balanced_step" else {}
+    e = batch.SharedSpM(p.s, p.P, p.C, p.D, p.g, lam=p.lam, mu=p.mu, batch_wide=True)
+    if path == "balanced_step":
+        assert e._step_mode == 2
+    e.solve(130, interval_update_mu=20, **kw)
+    mode = int(_lib.lib.admm_spm_launch_mode(0 if path == "balanced_step" else 1))
+    assert mode in ((3,) if os.environ.get("ADMM_NO_COOP") else (1, 2)), mode
+    assert rel(e.x0(), st.x0) < TOL and float(e.mu20[0]) == st.mu20
+    # recovery: the first attempt "fails" after it ran (the state has moved on), the repeat must start from the saved state
+    e2 = batch.SharedSpM(p.s, p.P, p.C, p.D, p.g, lam=p.lam, mu=p.mu, batch_wide=True)
+    e2.solve(40, interval_update_mu=20, **kw)
+    e2._inject_coresidency_failure = True
+    e2._risky_launch_mode = lambda *a: True          # (cooperative launches are never risky: force the snapshot)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        e2.solve(90, interval_update_mu=20, **kw)
+    assert any("co-resident" in str(x.message) for x in w)
+    assert e2._step_mode != 2 and e2._no_solo_bw
+    assert rel(e2.x0(), st.x0) < TOL and rel(e2.x2(), st.x2) < TOL and float(e2.mu20[0]) == st.mu20
+    assert len(e2.primal_residual) == st.niter_done == 130
+    assert rel(e2.primal_residual, st.primal) < 1e-8

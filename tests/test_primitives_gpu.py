@@ -74,3 +74,67 @@ def test_gemm_tensor_core(build_lib, m, n, k, op):
     out = Cd.cpu().numpy()
     assert np.abs(out[:, :n] - ref).max() <= 1e-12 * np.abs(A).max() * np.abs(B).max() * k
     assert np.all(out[:, n:] == 7.0)                  # nothing written outside the m x n block
+
+
+@pytest.mark.parametrize("m,n,k", [(64, 64, 16), (70, 100, 33), (300, 1024, 300), (39, 500, 39), (33, 16, 8), (257, 65, 129)])
+@pytest.mark.parametrize("op", [0, 1, 2])
+def test_gemm_complex_tensor_core(build_lib, m, n, k, op):
+    """admm_gemm on complex128 operands: the real form of the product on the tensor cores (gemm_dmma_kernel<OP, true>,
+    no operand is split or copied), plain / transposed / conjugate-transposed A, ragged edges and padded leading
+    dimensions, vs NumPy.  Replaces DenseMatrix.__matmul__ with complex A (matrix.py:100-118) and the A^H A / A^H y
+    products of a complex LeastSquares term (objectivefunc.py:76-77,101-110)."""
+    from admmsolver_b200 import _lib
+    rs = np.random.RandomState(m + n + k + op)
+    shp = (m, k) if op == 0 else (k, m)
+    A = rs.randn(*shp) + 1j * rs.randn(*shp)
+    B = rs.randn(k, n) + 1j * rs.randn(k, n)
+    ref = (A if op == 0 else (A.T if op == 1 else A.conj().T)) @ B
+    lda, ldb, ldc = shp[1] + 3, n + 1, n + 5
+    Ad = torch.zeros(shp[0], lda, dtype=torch.complex128, device="cuda")
+    Ad[:, :shp[1]] = torch.from_numpy(A).cuda()
+    Bd = torch.zeros(k, ldb, dtype=torch.complex128, device="cuda")
+    Bd[:, :n] = torch.from_numpy(B).cuda()
+    Cd = torch.full((m, ldc), 7.0 - 3.0j, dtype=torch.complex128, device="cuda")
+    _lib.call("admm_gemm", 1, op, m, n, k, _lib.ptr(Ad), lda, _lib.ptr(Bd), ldb, _lib.ptr(Cd), ldc, _lib.stream())
+    out = Cd.cpu().numpy()
+    assert np.abs(out[:, :n] - ref).max() <= 4e-12 * np.abs(A).max() * np.abs(B).max() * k
+    assert np.all(out[:, n:] == 7.0 - 3.0j)           # nothing written outside the m x n block
+
+
+@pytest.mark.parametrize("n", [1, 3, 8, 20, 39, 64, 100, 200, 256, 300])
+def test_hpd_inverse_batched(build_lib, n):
+    """admm_hpd_inverse_batched: complex Hermitian positive definite inverse through the real form of order 2n on the
+    tensor-core SPD kernels (register resident for n <= 64, L2 resident for n <= 256, scalar beyond) vs np.linalg.inv on
+    G = A^H A + mu I with complex A; masked batch, padded leading dimension, info flags, indefinite input untouched."""
+    from admmsolver_b200 import _lib
+    rs = np.random.RandomState(100 + n)
+    nbatch = 5
+    mats = []
+    for b in range(nbatch):
+        A = rs.randn(2 * n + 3, n) + 1j * rs.randn(2 * n + 3, n)
+        mats.append(A.conj().T @ A + (0.5 + b) * np.eye(n))
+    mats[3] = mats[3] - 1e3 * np.eye(n) * (1 + np.abs(mats[3]).max())          # indefinite
+    G = np.stack(mats)
+    lda = n + 2
+    buf = np.zeros((nbatch, n, lda), dtype=np.complex128)
+    buf[:, :, :n] = G
+    d = torch.from_numpy(buf).cuda()
+    work = torch.empty(nbatch * 4 * n * n, dtype=torch.float64, device="cuda")
+    mask = torch.tensor([1, 0, 1, 1, 1], dtype=torch.int32, device="cuda")
+    info = torch.full((nbatch,), -1, dtype=torch.int32, device="cuda")
+    _lib.call("admm_hpd_inverse_batched", n, nbatch, _lib.ptr(d), n * lda, lda, _lib.ptr(work), _lib.ptr(mask), _lib.ptr(info),
+              _lib.stream())
+    out = d.cpu().numpy()
+    inf = info.cpu().numpy()
+    for b in range(nbatch):
+        if b == 1:
+            assert np.array_equal(out[b], buf[b]) and inf[b] == -1
+            continue
+        if b == 3:
+            assert inf[b] != 0 and np.array_equal(out[b], buf[b])
+            continue
+        ref = np.linalg.inv(G[b])
+        err = np.linalg.norm(out[b, :, :n] - ref) / np.linalg.norm(ref)
+        assert err < 1e-12, (n, b, err)
+        assert inf[b] == 0 and np.array_equal(out[b, :, n:], buf[b, :, n:])
+        assert np.abs(out[b, :, :n] @ G[b] - np.eye(n)).max() < 1e-10

@@ -8,6 +8,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+import ctypes as C
+
 from . import _lib
 from ._lib import call, ptr, stream
 
@@ -237,9 +239,33 @@ def prox_psd(h: torch.Tensor, mu_diag: torch.Tensor, shape, axis: int, complex_o
     h = h.contiguous()
     assert h.numel() == total and mu_diag.numel() == total
     out = torch.empty(total, dtype=C128 if complex_out else F64, device=h.device)
+    grid = C.c_longlong(0)
+    work = None
+    if _lib.lib.admm_prox_psd_work_doubles(n, nb, C.byref(grid)) != 0:       # slices beyond 160 x 160: L2-resident workspace
+        work = torch.empty(int(grid.value) * n * n, dtype=F64, device=h.device)
     call("admm_prox_psd", n, nb, strides[axis % 3], strides[rest[0]], strides[rest[1]], ptr(h), ncomp(h),
-         ptr(mu_diag.contiguous()), ptr(out), 2 if complex_out else 1, stream())
+         ptr(mu_diag.contiguous()), ptr(out), 2 if complex_out else 1, ptr(work), stream())
     return out
+
+
+def svd_jacobi(K: torch.Tensor, max_sweeps: int = 40):
+    """SVD of a real (m, n) device matrix by one-sided Jacobi (``admm_svd_jacobi``): returns ``U`` (m, n), ``s`` (n,)
+    descending and ``V`` (n, n) with ``K = U diag(s) V^T``; columns of ``U`` belonging to singular values at the
+    rounding level of the largest one are unit vectors of noise, as with LAPACK."""
+    m, n = K.shape
+    Wt = K.t().contiguous().to(F64)                      # rows = columns of K
+    Vt = torch.eye(n, dtype=F64, device=K.device)
+    sv = torch.empty(n, dtype=F64, device=K.device)
+    scratch = torch.zeros(max_sweeps, dtype=F64, device=K.device)
+    info = torch.zeros(1, dtype=torch.int32, device=K.device)
+    call("admm_svd_jacobi", m, n, ptr(Wt), m, ptr(Vt), n, ptr(sv), ptr(scratch), int(max_sweeps), ptr(info), stream())
+    if int(info.item()) < 0:
+        raise np.linalg.LinAlgError("admm_svd_jacobi did not converge in %d sweeps" % max_sweeps)
+    order = torch.argsort(sv, descending=True)
+    s_sorted = sv[order]
+    U = (Wt[order] / s_sorted.clamp_min(1e-300)[:, None]).t().contiguous()
+    V = Vt[order].t().contiguous()
+    return U, s_sorted, V
 
 
 def prox_nonneg(h: torch.Tensor, mu_diag: torch.Tensor, complex_out: bool) -> torch.Tensor:

@@ -90,7 +90,9 @@ _SIGS = {
     "admm_ewise_unary": ([_I, _I, _LL, _P, _P, _P], _I),
     "admm_prox_l1": ([_LL, _P, _I, _P, _D, _P, _I, _P], _I),
     "admm_prox_nonneg": ([_LL, _P, _I, _P, _P, _I, _P], _I),
-    "admm_prox_psd": ([_I, _LL, _LL, _LL, _LL, _P, _I, _P, _P, _I, _P], _I),
+    "admm_prox_psd_work_doubles": ([_I, _LL, C.POINTER(_LL)], _I),
+    "admm_prox_psd": ([_I, _LL, _LL, _LL, _LL, _P, _I, _P, _P, _I, _P, _P], _I),
+    "admm_svd_jacobi": ([_I, _I, _P, _I, _P, _I, _P, _P, _I, _P, _P], _I),
     "admm_sumsq": ([_LL, _P, _P, _P, _P, _P], _I),
     "admm_pair_norms": ([_LL, _P, _P, _LL, _P, _P, _P, _P, _P], _I),
     "admm_inverse": ([_I, _I, _P, _I, _P, _I, _P, _P, _P], _I),

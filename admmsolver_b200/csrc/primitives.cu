@@ -5,8 +5,14 @@
 
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
+#include <map>
+
+namespace cg = cooperative_groups;
 
 namespace admm {
 
@@ -475,6 +481,212 @@ __global__ void __launch_bounds__(PSD_WARPS * 32) prox_psd_kernel(int n, long lo
     }
     __syncwarp();
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One-sided (Hestenes) Jacobi on the columns of W (m x n, COLUMN-major, leading dimension ld): plane rotations of
+// column pairs until all columns are mutually orthogonal, W <- W R, optionally V <- V R (n x n, column-major).
+// Then the column norms are the singular values of the input, the normalised columns its left singular vectors and
+// (V started as I) V its right singular vectors -- each to high RELATIVE accuracy, which the kernel of the IR basis
+// needs (its singular values span 16 decades).  For a symmetric positive definite input the columns end up as
+// lambda_k v_k.  Parallel ordering: round r of the round-robin tournament on ne = n rounded up to even positions pairs
+// ne/2 disjoint columns; one warp rotates one pair (three dot products, one fused update), all pairs of a round are
+// independent.  Used by the PSD projection of matrices larger than a warp (one CTA per matrix, rounds separated by
+// __syncthreads) and by the SVD of the IR kernel (one matrix spread over a cooperative grid, rounds separated by
+// grid.sync()).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rr_pair(int ne, int r, int i, int& p, int& q) {
+  const int md = ne - 1;
+  if (i == 0) {
+    p = ne - 1;
+    q = r;
+  } else {
+    p = (r + i) % md;
+    q = (r - i + md) % md;
+  }
+}
+
+// returns |cos| of the angle between the two columns before the rotation (0 when one of them vanishes).
+// zero2: columns whose squared norm is at most zero2 are rounding noise of a rank-deficient input (the directions of
+// vanishing singular values); they are not rotated -- their mutual angles are noise and never settle.
+// (Exchanging the columns so that the larger norm comes first -- de Rijk -- was measured to slow the parallel ordering
+// down: positions pair up once per sweep, so moving columns breaks the guarantee that a sweep looks at every pair.)
+__device__ __forceinline__ double jacobi_pair(double* __restrict__ a, double* __restrict__ b, int m, double* va, double* vb,
+                                              int nv, int lane, double tol, double zero2 = 0.0) {
+  double al = 0.0, be = 0.0, ga = 0.0;
+  for (int i = lane; i < m; i += 32) {
+    const double x = a[i], y = b[i];
+    al += x * x;
+    be += y * y;
+    ga += x * y;
+  }
+  al = warp_sum(al);
+  be = warp_sum(be);
+  ga = warp_sum(ga);
+  double off = 0.0;
+  if (al > zero2 && be > zero2) off = fabs(ga) / sqrt(al * be);
+  if (off > tol) {
+    const double zeta = (be - al) / (2.0 * ga);
+    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+    for (int i = lane; i < m; i += 32) {
+      const double x = a[i], y = b[i];
+      a[i] = c * x - sn * y;
+      b[i] = sn * x + c * y;
+    }
+    if (va != nullptr) {
+      for (int i = lane; i < nv; i += 32) {
+        const double x = va[i], y = vb[i];
+        va[i] = c * x - sn * y;
+        vb[i] = sn * x + c * y;
+      }
+    }
+  }
+  return off;
+}
+
+// PSD-cone projection for 32 < n: one CTA per matrix.  X (symmetric, from the lower triangle) is shifted to
+// W = X + sigma I with sigma >= |X|_F >= rho(X), which is positive definite, so that the one-sided Jacobi above applies
+// (for an indefinite matrix eigenvalue pairs +-lambda would be singular-value ties that mix the two eigenvectors);
+// at convergence column k of W is (lambda_k + sigma) v_k, hence  X+ = sum_{|w_k| > sigma} (|w_k| - sigma) w_k w_k^T / |w_k|^2.
+// The absolute error eps * sigma in lambda_k is what LAPACK's eigh guarantees as well.  W lives in shared memory
+// (n <= 160) or in the caller's workspace (`work`: one n x n slot per CTA, L2 resident).
+constexpr int PSDC_THREADS = 512;
+
+__global__ void __launch_bounds__(PSDC_THREADS) prox_psd_cta_kernel(int n, long long nbatch, long long sb, long long sr,
+                                                                    long long sc, const double* __restrict__ h, int hs,
+                                                                    const double* __restrict__ mud, double* __restrict__ out,
+                                                                    int os, double* __restrict__ work, double tol) {
+  extern __shared__ double psdc_sm[];
+  __shared__ double red[32];
+  __shared__ double offmax_sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = PSDC_THREADS / 32;
+  double* coef = psdc_sm;                                              // [n]
+  double* W = work != nullptr ? work + (size_t)blockIdx.x * n * n : psdc_sm + n;      // column-major, ld = n
+  const int ne = (n + 1) & ~1;
+  for (long long mtx = blockIdx.x; mtx < nbatch; mtx += gridDim.x) {
+    double fro[1] = {0.0};
+    for (int idx = tid; idx < n * n; idx += PSDC_THREADS) {
+      const int i = idx % n, j = idx / n;
+      const int r = i > j ? i : j, c = i > j ? j : i;
+      const long long off = mtx * sb + r * sr + c * sc;
+      const double v = -(h[off * hs] / mud[off]);
+      W[idx] = v;
+      fro[0] += v * v;
+    }
+    block_sum<1>(fro, red);
+    const double sigma = sqrt(fro[0]) * (1.0 + 1e-6) + 1e-300;
+    __syncthreads();
+    for (int i = tid; i < n; i += PSDC_THREADS) W[(size_t)i * n + i] += sigma;
+    __syncthreads();
+    for (int sweep = 0; sweep < 60; ++sweep) {
+      if (tid == 0) offmax_sh = 0.0;
+      __syncthreads();
+      double mymax = 0.0;
+      for (int r = 0; r < ne - 1; ++r) {
+        for (int i = warp; i < ne / 2; i += nw) {
+          int p, q;
+          rr_pair(ne, r, i, p, q);
+          if (p < n && q < n) {
+            if (p > q) {
+              const int tq = p;
+              p = q;
+              q = tq;
+            }
+            mymax = fmax(mymax, jacobi_pair(W + (size_t)p * n, W + (size_t)q * n, n, nullptr, nullptr, 0, lane, tol));
+          }
+        }
+        __syncthreads();
+      }
+      if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(&offmax_sh), (unsigned long long)__double_as_longlong(mymax));
+      __syncthreads();
+      const bool done = !(offmax_sh > tol);
+      __syncthreads();
+      if (done) break;
+    }
+    // coefficients (|w_k| - sigma) / |w_k|^2 of the positive part
+    for (int k = warp; k < n; k += nw) {
+      double a = 0.0;
+      for (int i = lane; i < n; i += 32) a += W[(size_t)k * n + i] * W[(size_t)k * n + i];
+      a = warp_sum(a);
+      const double nk = sqrt(a);
+      if (lane == 0) coef[k] = nk > sigma ? (nk - sigma) / a : 0.0;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += PSDC_THREADS) {
+      const int i = idx % n, j = idx / n;
+      double acc = 0.0;
+      for (int k = 0; k < n; ++k) acc += coef[k] * W[(size_t)k * n + i] * W[(size_t)k * n + j];
+      const long long off = mtx * sb + i * sr + j * sc;
+      out[off * os] = acc;
+      if (os == 2) out[off * 2 + 1] = 0.0;
+    }
+    __syncthreads();
+  }
+}
+
+// SVD of ONE m x n matrix (m >= 1, any n) spread over a cooperative grid: Wt holds the columns of the input as rows
+// (n rows of length m, row stride ldw), Vt the columns of V as rows (n x n, identity on entry; may be NULL).
+// On exit row k of Wt is sigma_k u_k, row k of Vt is v_k, sv[k] = sigma_k (unsorted), info[0] = sweeps used (negative: not
+// converged within max_sweeps).  offmax: max_sweeps doubles of scratch, zero-initialised.
+constexpr int SVDJ_THREADS = 256;
+
+__global__ void __launch_bounds__(SVDJ_THREADS) svd_jacobi_kernel(int m, int n, double* __restrict__ Wt, int ldw,
+                                                                  double* __restrict__ Vt, int ldv, double* __restrict__ sv,
+                                                                  double* __restrict__ offmax, double tol, int max_sweeps,
+                                                                  int* __restrict__ info) {
+  cg::grid_group grid = cg::this_grid();
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * SVDJ_THREADS + threadIdx.x) >> 5, tw = gridDim.x * (SVDJ_THREADS / 32);
+  const int ne = (n + 1) & ~1;
+  int used = -max_sweeps;
+  // |K|_F^2 -> the noise floor of a column (sv[] doubles as scratch: it is written last)
+  if (blockIdx.x == 0 && threadIdx.x == 0) sv[0] = 0.0;
+  grid.sync();
+  {
+    double f = 0.0;
+    for (int k = gw; k < n; k += tw)
+      for (int i = lane; i < m; i += 32) f += Wt[(size_t)k * ldw + i] * Wt[(size_t)k * ldw + i];
+    f = warp_sum(f);
+    if (lane == 0 && f != 0.0) atomicAdd(sv, f);
+  }
+  grid.sync();
+  const double zero2 = 256.0 * 4.930380657631324e-32 * (double)m * __ldcg(sv);      // (16 eps sqrt(m) |K|_F)^2
+  grid.sync();
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    double mymax = 0.0;
+    for (int r = 0; r < ne - 1; ++r) {
+      for (int i = gw; i < ne / 2; i += tw) {
+        int p, q;
+        rr_pair(ne, r, i, p, q);
+        if (p < n && q < n) {
+          if (p > q) {
+            const int tq = p;
+            p = q;
+            q = tq;
+          }
+          mymax = fmax(mymax, jacobi_pair(Wt + (size_t)p * ldw, Wt + (size_t)q * ldw, m, Vt ? Vt + (size_t)p * ldv : nullptr,
+                                          Vt ? Vt + (size_t)q * ldv : nullptr, n, lane, tol, zero2));
+        }
+      }
+      grid.sync();
+    }
+    if (lane == 0 && mymax > 0.0)
+      atomicMax(reinterpret_cast<unsigned long long*>(offmax + sweep), (unsigned long long)__double_as_longlong(mymax));
+    grid.sync();
+    const double om = __ldcg(offmax + sweep);
+    if (!(om > tol)) {
+      used = sweep + 1;
+      break;
+    }
+  }
+  for (int k = gw; k < n; k += tw) {
+    double a = 0.0;
+    for (int i = lane; i < m; i += 32) a += Wt[(size_t)k * ldw + i] * Wt[(size_t)k * ldw + i];
+    a = warp_sum(a);
+    if (lane == 0) sv[k] = sqrt(a);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && info != nullptr) info[0] = used;
 }
 
 __global__ void __launch_bounds__(256) sumsq_stage1(long long n, const double* __restrict__ x,
@@ -1102,10 +1314,36 @@ int admm_prox_nonneg(long long n, const double* h, int h_stride, const double* m
   return check_launch("admm_prox_nonneg");
 }
 
+int admm_prox_psd_work_doubles(int n, long long nbatch, long long* grid_out) {
+  const long long grid = std::max<long long>(1, std::min<long long>(nbatch, 148LL * 2));
+  if (grid_out != nullptr) *grid_out = grid;
+  return n > 160 ? 1 : 0;          // (1: a workspace of grid * n * n doubles is needed)
+}
+
 int admm_prox_psd(int n, long long nbatch, long long stride_batch, long long stride_row, long long stride_col,
-                  const double* h, int h_stride, const double* mu_diag, double* out, int out_stride, admm_stream_t stream) {
-  ADMM_REQUIRE(n >= 1 && n <= 32, ADMM_EUNSUPPORTED, "admm_prox_psd: matrix order %d not supported (1..32)", n);
+                  const double* h, int h_stride, const double* mu_diag, double* out, int out_stride, double* work,
+                  admm_stream_t stream) {
+  ADMM_REQUIRE(n >= 1 && n <= 1024, ADMM_EUNSUPPORTED, "admm_prox_psd: matrix order %d not supported (1..1024)", n);
   if (nbatch <= 0) return ADMM_OK;
+  if (n > 32) {
+    // one CTA per matrix, one-sided Jacobi on the shifted matrix (shared memory up to n = 160, the caller's
+    // L2-resident workspace beyond)
+    long long grid = 1;
+    const int need_work = admm_prox_psd_work_doubles(n, nbatch, &grid);
+    ADMM_REQUIRE(!need_work || work != nullptr, ADMM_EINVAL,
+                 "admm_prox_psd: n=%d needs a workspace of %lld doubles (admm_prox_psd_work_doubles)", n, grid * n * n);
+    const size_t smem = (size_t)(need_work ? n : n + (size_t)n * n) * sizeof(double);
+    static std::map<int, size_t> configured;
+    size_t& cfgd = configured[cur_dev()];
+    if (smem > cfgd) {
+      cudaFuncSetAttribute(prox_psd_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cfgd = smem;
+    }
+    const double tol = 2.0 * sqrt((double)n) * 2.220446049250313e-16;
+    prox_psd_cta_kernel<<<(int)grid, PSDC_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+        n, nbatch, stride_batch, stride_row, stride_col, h, h_stride, mu_diag, out, out_stride, need_work ? work : nullptr, tol);
+    return check_launch("admm_prox_psd(cta)");
+  }
   const size_t smem = (size_t)PSD_WARPS * 2 * n * (n | 1) * sizeof(double);
   const int grid = (int)std::max<long long>(1, std::min<long long>((nbatch + PSD_WARPS - 1) / PSD_WARPS, 148LL * 16));
   prox_psd_kernel<<<grid, PSD_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(n, nbatch, stride_batch, stride_row,
@@ -1175,6 +1413,33 @@ int admm_spd_inverse_batched(int n, int nbatch, double* A, long long batch_strid
     spd_inverse_kernel<false><<<nbatch, 512, 2 * n * sizeof(double), s>>>(n, A, batch_stride, lda, mask, info);
   }
   return check_launch("admm_spd_inverse_batched");
+}
+
+int admm_svd_jacobi(int m, int n, double* Wt, int ldw, double* Vt, int ldv, double* sv, double* scratch, int max_sweeps,
+                    int* info, admm_stream_t stream) {
+  ADMM_REQUIRE(m >= 1 && n >= 1 && ldw >= m && (Vt == nullptr || ldv >= n) && sv != nullptr && scratch != nullptr &&
+                   max_sweeps >= 1 && max_sweeps <= 64,
+               ADMM_EINVAL, "admm_svd_jacobi: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int per_sm = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, svd_jacobi_kernel, SVDJ_THREADS, 0) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cur_dev()) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    set_error("admm_svd_jacobi: occupancy query failed");
+    return ADMM_ECUDA;
+  }
+  const int pairs = (n + 1) / 2, wpc = SVDJ_THREADS / 32;
+  const int grid = std::max(1, std::min(per_sm * sms, ceil_div(pairs, wpc)));
+  cudaMemsetAsync(scratch, 0, (size_t)max_sweeps * sizeof(double), s);
+  const double tol = 2.0 * sqrt((double)m) * 2.220446049250313e-16;
+  cudaError_t e = launch_coop(svd_jacobi_kernel, dim3(grid), dim3(SVDJ_THREADS), 0, s, false, m, n, Wt, ldw, Vt, ldv, sv, scratch,
+                              tol, max_sweeps, info);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("admm_svd_jacobi: cooperative launch failed: %s", cudaGetErrorString(e));
+    return ADMM_ECUDA;
+  }
+  return check_launch("admm_svd_jacobi");
 }
 
 int admm_hpd_inverse_batched(int n, int nbatch, void* A, long long batch_stride, int lda, double* work, const int* mask,

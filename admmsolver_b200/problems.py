@@ -113,14 +113,9 @@ class IRBasis:
         return (self.v_omega @ self.womega)[None, :]
 
 
-def ir_basis(beta: float = 100.0, wmax: float = 10.0, eps: float = 1e-7) -> IRBasis:
-    """SVD basis of the kernel on composite 16-point Gauss-Legendre panels.
-
-    tau panels cluster (Chebyshev-like) toward 0 and beta; omega panels are
-    geometric toward 0.  Keeps s_l / s_0 > eps (L = 39 for beta=100, wmax=10,
-    eps=1e-7, the size printed at ``spm.ipynb:214``).  Signs are fixed so that
-    the largest-magnitude sample of every v_l is positive (SVD sign ambiguity).
-    """
+def ir_quadrature(beta: float, wmax: float):
+    """Composite 16-point Gauss-Legendre nodes / weights of the basis construction: tau panels cluster toward 0 and
+    beta, omega panels geometrically toward 0.  Returns (tau, wtau, omega, womega)."""
     npan_t = 24
     th = np.linspace(0.0, np.pi, npan_t + 1)
     edges_t = 0.5 * beta * (1.0 - np.cos(th))
@@ -133,7 +128,18 @@ def ir_basis(beta: float = 100.0, wmax: float = 10.0, eps: float = 1e-7) -> IRBa
     geo = wmax * 0.5 ** np.arange(npan_w, -1, -1, dtype=float)
     edges_w = np.concatenate([-geo[::-1], [0.0], geo])
     omega, womega = _panel_nodes(edges_w)
+    return tau, wtau, omega, womega
 
+
+def ir_basis(beta: float = 100.0, wmax: float = 10.0, eps: float = 1e-7) -> IRBasis:
+    """SVD basis of the kernel on composite 16-point Gauss-Legendre panels.
+
+    tau panels cluster (Chebyshev-like) toward 0 and beta; omega panels are
+    geometric toward 0.  Keeps s_l / s_0 > eps (L = 39 for beta=100, wmax=10,
+    eps=1e-7, the size printed at ``spm.ipynb:214``).  Signs are fixed so that
+    the largest-magnitude sample of every v_l is positive (SVD sign ambiguity).
+    """
+    tau, wtau, omega, womega = ir_quadrature(beta, wmax)
     K = _kernel(tau, omega, beta)
     Kw = np.sqrt(wtau)[:, None] * K * np.sqrt(womega)[None, :]
     U, s, Vt = np.linalg.svd(Kw, full_matrices=False)

@@ -78,14 +78,27 @@ int admm_prox_l1(long long n, const double* h, int h_stride, const double* mu_di
 int admm_prox_nonneg(long long n, const double* h, int h_stride, const double* mu_diag,
                      double* out, int out_stride, admm_stream_t stream);
 
-/* PSD-cone projection of `nbatch` real symmetric n x n matrices (n <= 32) embedded in one vector:
+/* PSD-cone projection of `nbatch` real symmetric n x n matrices (n <= 1024) embedded in one vector:
  * element (p, q) of matrix m is entry m*stride_batch + p*stride_row + q*stride_col.  X = -Re(h)/mu_diag
  * elementwise; per matrix the LOWER triangle defines the symmetric matrix (as np.linalg.eigh does) and
- * the negative eigenvalues are removed.  One warp per matrix, cyclic Jacobi in shared memory.
- * Replaces `SemiPositiveDefinitePenalty.solve` (objectivefunc.py:294-327). */
+ * the negative eigenvalues are removed.  n <= 32: one warp per matrix, cyclic two-sided Jacobi in shared memory.
+ * n > 32: one CTA per matrix, parallel-order one-sided Jacobi on the shifted matrix X + |X|_F I (positive definite, so
+ * its orthogonalised columns are (lambda_k + sigma) v_k) -- in shared memory up to n = 160, beyond in `work`
+ * (admm_prox_psd_work_doubles returns 1 when a workspace of *grid * n * n doubles is needed; NULL otherwise).
+ * Replaces `SemiPositiveDefinitePenalty.solve` incl. its per-slice np.linalg.eigh loop (objectivefunc.py:294-327). */
+int admm_prox_psd_work_doubles(int n, long long nbatch, long long* grid);
 int admm_prox_psd(int n, long long nbatch, long long stride_batch, long long stride_row,
                   long long stride_col, const double* h, int h_stride, const double* mu_diag,
-                  double* out, int out_stride, admm_stream_t stream);
+                  double* out, int out_stride, double* work, admm_stream_t stream);
+
+/* Singular value decomposition of ONE real m x n matrix by one-sided Jacobi on a cooperative grid (high relative
+ * accuracy of small singular values: the kernel of the intermediate-representation basis spans 16 decades).
+ * Wt: the COLUMNS of the input as rows (n rows of length m, row stride ldw), overwritten with sigma_k u_k;
+ * Vt: n x n, the identity on entry (or NULL), row k overwritten with v_k; sv[k] = sigma_k (unsorted);
+ * scratch: max_sweeps doubles; info[0] = sweeps used, negative if not converged.  Replaces the `np.linalg.svd` /
+ * `sparse_ir` basis construction either side of the solver (spm.ipynb:52-65,155-163). */
+int admm_svd_jacobi(int m, int n, double* Wt, int ldw, double* Vt, int ldv, double* sv, double* scratch,
+                    int max_sweeps, int* info, admm_stream_t stream);
 
 /* out[0] = sum_i x[i]^2 (y == NULL) or sum_i (x[i]-y[i])^2 over n doubles; deterministic
  * two-stage reduction; `scratch` needs 1024 doubles.  Replaces `np.linalg.norm`

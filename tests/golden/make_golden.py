@@ -211,6 +211,12 @@ def main_psd():
     h32 = rs.randn(32 * 32 * 3)
     out["h_n32"] = h32
     out["x_n32"] = SemiPositiveDefinitePenalty((3, 32, 32), axis=0).solve(h32, ScaledIdentityMatrix(32 * 32 * 3, 1.0))
+    # slices larger than a warp (the CTA-wide one-sided Jacobi of admm_prox_psd): own generator, so that the draws above
+    # and below keep their values
+    rs40 = np.random.RandomState(40)
+    h40 = rs40.randn(2 * 40 * 40)
+    out["h_n40"] = h40
+    out["x_n40"] = SemiPositiveDefinitePenalty((40, 2, 40), axis=1).solve(h40, ScaledIdentityMatrix(2 * 40 * 40, 0.6))
     # matrix-valued least squares with a PSD constraint through SimpleOptimizer.solve
     n, k = 4, 3
     nx = n * n * k

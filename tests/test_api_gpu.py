@@ -355,6 +355,52 @@ def test_semi_positive_definite_penalty_golden(build_lib):
                g["x_n32"]) < 1e-10
 
 
+@pytest.mark.parametrize("n,K,axis", [(33, 5, 0), (48, 300, 2), (64, 3, 1), (100, 4, 0), (128, 2, 2), (160, 2, 0), (161, 2, 0),
+                                      (200, 3, 2)])
+def test_semi_positive_definite_penalty_large_slices(build_lib, n, K, axis):
+    """SemiPositiveDefinitePenalty beyond 32 x 32 slices (the reference has no size limit: objectivefunc.py:294-327 loops
+    np.linalg.eigh): the CTA-wide one-sided Jacobi on the shifted matrix -- shared memory up to n = 160, the L2-resident
+    workspace beyond -- against the reference's own output (n = 40, golden) and the oracle restatement; random,
+    already-PSD, negative definite, zero and +-lambda-paired (singular-value ties of the unshifted matrix) slices."""
+    from admmsolver_b200.matrix import DiagonalMatrix, ScaledIdentityMatrix
+    from admmsolver_b200.objectivefunc import SemiPositiveDefinitePenalty
+    from oracle import flat
+    g = golden("psd")
+    if n == 33:
+        res = SemiPositiveDefinitePenalty((40, 2, 40), axis=1).solve(g["h_n40"], ScaledIdentityMatrix(2 * 40 * 40, 0.6))
+        assert rel(res, g["x_n40"]) < 1e-10
+    rs = np.random.RandomState(n + K)
+    shape = [n, n, n]
+    shape[axis] = K
+    X = rs.randn(K, n, n)
+    X = X + np.swapaxes(X, 1, 2)
+    B = rs.randn(n, n)
+    X[0] = B @ B.T                                     # positive definite: unchanged by the projection
+    if K > 1:
+        X[1] = -(B @ B.T) - np.eye(n)                  # negative definite: projected to zero
+    if K > 2:
+        J = np.zeros((n, n))
+        for i in range(0, n - 1, 2):
+            J[i, i + 1] = J[i + 1, i] = 1.0 + i        # eigenvalue pairs +-(1 + i)
+        X[2] = J
+    if K > 3:
+        X[3] = 0.0
+    mu = np.linspace(0.5, 2.0, K * n * n)
+    Xm = np.moveaxis(X, 0, axis)                       # (shape) with the slices along `axis`
+    h = -(Xm.ravel() * mu) + 0.3j * rs.randn(K * n * n)           # -Re(h)/mu == X; the imaginary part is ignored
+    res = SemiPositiveDefinitePenalty(tuple(shape), axis=axis).solve(h, DiagonalMatrix(mu))
+    ref = flat.psd_project(h, mu, tuple(shape), axis)
+    assert rel(res, ref) < 1e-10
+    out = np.moveaxis(res.reshape(shape), axis, 0)
+    assert rel(out[0], X[0]) < 1e-10
+    if K > 1:
+        assert np.abs(out[1]).max() < 1e-10 * np.abs(X[1]).max()
+    if K > 3:
+        assert np.all(out[3] == 0.0)
+    for k in range(min(K, 6)):
+        assert np.linalg.eigvalsh(out[k]).min() > -1e-10 * max(1.0, np.abs(X[k]).max())
+
+
 def test_semi_positive_definite_model_golden(build_lib):
     """Matrix-valued least squares with a PSD constraint through SimpleOptimizer.solve (generic executor)."""
     from admmsolver_b200.matrix import identity

@@ -138,3 +138,74 @@ def test_hpd_inverse_batched(build_lib, n):
         assert err < 1e-12, (n, b, err)
         assert inf[b] == 0 and np.array_equal(out[b, :, n:], buf[b, :, n:])
         assert np.abs(out[b, :, :n] @ G[b] - np.eye(n)).max() < 1e-10
+
+
+@pytest.mark.parametrize("m,n", [(8, 8), (50, 7), (64, 64), (300, 129), (90, 200)])
+def test_svd_jacobi_vs_lapack(build_lib, m, n):
+    """admm_svd_jacobi (one-sided Jacobi on a cooperative grid) vs np.linalg.svd: singular values, orthogonality and
+    reconstruction to working precision; wide matrices (n > m) get n - m zero singular values."""
+    from admmsolver_b200 import _dev as D
+    rs = np.random.RandomState(m * 1000 + n)
+    K = rs.randn(m, n) * np.logspace(0, -6, n)[None, :]            # graded columns
+    U, s, V = D.svd_jacobi(torch.from_numpy(K).cuda())
+    U, s, V = U.cpu().numpy(), s.cpu().numpy(), V.cpu().numpy()
+    sref = np.linalg.svd(K, compute_uv=False)
+    r = min(m, n)
+    assert np.abs(s[:r] - sref).max() <= 1e-13 * sref[0]
+    assert np.all(s[r:] <= 1e-13 * sref[0])
+    assert np.abs((U[:, :r] * s[:r]) @ V[:, :r].T - K).max() <= 1e-13 * sref[0]
+    assert np.abs(V.T @ V - np.eye(n)).max() < 1e-12
+    assert np.abs(U[:, :r].T @ U[:, :r] - np.eye(r)).max() < 1e-11        # also for the small singular values
+
+
+def test_ir_basis_on_device(build_lib):
+    """the IR basis generated on the device (admm_svd_jacobi + tensor-core projections) against the host
+    construction (np.linalg.svd): same size L = 39 (spm.ipynb:214), singular values to 1e-8 relative (LAPACK itself is
+    only accurate to eps * s_0 = 1e-9 s_38 there), the same basis functions, sum rule and sampling matrix; and the SpM
+    pipeline built from it -- expansion of the model spectrum, solve, reconstruction (spm.ipynb:155-163,243-300)."""
+    from admmsolver_b200 import irbasis, problems
+    from admmsolver_b200.batch import SharedSpM
+    from oracle import flat
+    hb = problems.ir_basis()
+    db = irbasis.ir_basis_device()
+    assert db.size == hb.size == 39
+    s = db.s.cpu().numpy()
+    assert np.abs(s / hb.s - 1).max() < 1e-8
+    v, u = db.v_omega.cpu().numpy(), db.u_tau.cpu().numpy()
+    # orthonormality in the weighted inner products, to working precision for ALL l (Jacobi: relative accuracy)
+    assert np.abs((v * hb.womega) @ v.T - np.eye(39)).max() < 1e-12
+    assert np.abs((u * hb.wtau) @ u.T - np.eye(39)).max() < 1e-12
+    # K = sum_l s_l u_l v_l up to the truncation
+    K = problems._kernel(hb.tau, hb.omega, hb.beta)
+    Kw = np.sqrt(hb.wtau)[:, None] * K * np.sqrt(hb.womega)[None, :]
+    assert np.abs(((u * np.sqrt(hb.wtau)).T * s) @ (v * np.sqrt(hb.womega)) - Kw).max() < 2e-7 * s[0]
+    # the leading functions coincide with LAPACK's; the last ones only to the conditioning of their singular value
+    # (up to the sign: "largest sample positive" is ambiguous for the odd functions, whose extrema come in +- pairs)
+    sgn = np.sign(np.sum((v * hb.womega) * hb.v_omega, axis=1))
+    assert np.all(sgn != 0)
+    for l in range(39):
+        tol = 1e-5 if l < 30 else 1e-2
+        assert np.abs(sgn[l] * v[l] - hb.v_omega[l]).max() < tol * np.abs(hb.v_omega[l]).max(), l
+    j = np.abs(v).argmax(axis=1)
+    assert np.all(v[np.arange(39), j] > 0)                        # the sign convention itself holds
+    omega = np.linspace(-10, 10, 400)
+    P = db.sampling_matrix(omega).cpu().numpy()
+    Ph = (((u * hb.wtau) @ problems._kernel(hb.tau, omega, hb.beta)) / s[:, None]).T
+    assert np.abs(P - Ph).max() < 1e-6 * np.abs(Ph).max()
+    C = db.sum_rule().cpu().numpy()
+    assert np.allclose(C, (v @ hb.womega)[None, :], rtol=1e-10, atol=1e-10)
+    # pipeline: rho -> rho_l -> g_l, solve, rho_rec
+    rho_l = db.expand_spectrum(problems.rho_three_gaussians(hb.omega)).cpu().numpy()
+    assert abs((C @ rho_l)[0] - 1.0) < 1e-5                       # the model spectrum is normalised
+    g = -s * rho_l + 1e-4 * np.random.RandomState(0).randn(39)
+    eng = SharedSpM(s, P, C, np.array([1.0]), g, lam=1e-4, mu=0.1, batch_wide=True)
+    eng.solve(400)
+    st = flat.spm_solve(s, P, C, np.array([1.0]), g, 1e-4, 400, mu=0.1)
+    x0 = eng.x0()[:, 0]
+    assert np.linalg.norm(x0 - st.x0) < 1e-10 * np.linalg.norm(st.x0)
+    rec = db.reconstruct(x0.real.copy(), omega).cpu().numpy()
+    assert np.abs(rec - P @ x0.real).max() < 1e-12
+    # G(tau) -> g_l: the exact G of the model spectrum gives -s_l rho_l
+    G = -(K * hb.womega) @ problems.rho_three_gaussians(hb.omega)
+    gl = db.project_gtau(G).cpu().numpy()
+    assert np.abs(gl - (-s * rho_l)).max() < 1e-9

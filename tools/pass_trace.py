@@ -7,7 +7,7 @@ import subprocess
 import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-lib = "/tmp/libadmm_trace.so"
+lib = os.path.join(ROOT, "tools", "libadmm_trace.so")
 csrc = os.path.join(ROOT, "admmsolver_b200", "csrc")
 cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-DSPM_TRACE", "-shared",
        "-o", lib] + [os.path.join(csrc, f) for f in ("primitives.cu", "spm.cu", "bp.cu", "peer.cu")] + ["-lcudart"]

@@ -14,6 +14,7 @@ solve loop runs in ``libadmm_b200.so``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -156,8 +157,10 @@ class SharedSpM:
                 nsplit = 1
             else:
                 total = ngroups * nchunks
-                cap = 8 if ngroups <= 16 else 4         # pieces per tile group (measured optimum)
-                nbal = max(1, min(SLOTS, total, cap * ngroups))
+                # pieces per tile group: up to 16 (measured with the fused balanced step, tools/bal_sweep.py: one wave
+                # of pieces as soon as there are 28 groups; with the separate x-update kernel of round 1, where every
+                # partial-sum slot cost a dependent load, the optimum was 4 to 8)
+                nbal = max(1, min(SLOTS, total, 16 * ngroups))
                 nsplit = -(-nchunks * nbal // total) + 1
         else:
             if mt is None:
@@ -228,7 +231,7 @@ class SharedSpM:
         self.normsA = z(nct * 8 * 8)
         self.normsB = z(nsplit * nct * 8 * 2)
         self.gsum = z(16)
-        self.gpart = z(256 * 16)
+        self.gpart = z(256 * 16 + (16 * 512 + 64 if os.environ.get('ADMM_B200_LIB') else 0))      # (+ trace slots of tools/pass_trace.py)
         # lazy batch-wide iterations (one launch per iteration: reduction in the tail of the step / pass kernel, decision
         # in the head of the next one): per-CTA partial sums and the control words
         ngrp = -(-npt // gt)

@@ -263,6 +263,13 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const int* p) {
   return v;
 }
 
+__device__ __forceinline__ unsigned ld_relaxed_u32(const int* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;\n" ::: "memory"); }
+
 constexpr int PEER_WORDS = 20;        // ten doubles as 32-bit halves
 constexpr int PEER_SLOT = 32;         // words per (buffer, source rank) slot of a mailbox
 constexpr long long PEER_TIMEOUT = 10000000000LL;   // ~5 s of clock64: a peer died, give up instead of hanging the GPU
@@ -436,6 +443,22 @@ __device__ __forceinline__ void lazy_tail(const admm_spm_buffers& b, const admm_
   }
 }
 
+#ifdef SPM_TRACE   // tools only: %globaltimer stamps of CTA 0 / thread 0 inside the x-update, int64 slots 1024.. of b.gpart
+__device__ __forceinline__ long long gtimer_x() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+#define XSTAMP(idx)                                                                                             \
+  if (threadIdx.x == 0) {                                                                                       \
+    const long long t_now = gtimer_x();                                                                         \
+    if (blockIdx.x == 0) reinterpret_cast<long long*>(b.gpart)[1024 + (idx)] = t_now;                           \
+    if (blockIdx.x < 512) reinterpret_cast<long long*>(b.gpart)[4096 + 16 * blockIdx.x + (idx)] = t_now;         \
+  }
+#else
+#define XSTAMP(idx)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // x-update of ONE problem tile (8 problems, all planes) by one warp, everything in fragment layout
 // ---------------------------------------------------------------------------------------------
@@ -483,13 +506,15 @@ __device__ __forceinline__ void frag_gemm(double (&out)[NP][NT][2], const double
 template <int NT, int NP, bool SPLIT, bool PRE = false, bool EARLY = PRE>   // SPLIT: V arrives as d.nsplit partial sums
 __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_spm_buffers& b, int pt, int lane,
                                              int p0 = 0, double* wpart = nullptr, const double* sm_PtP = nullptr,
-                                             const double* sm_Ginv = nullptr, int sm_slot = -1) {
+                                             const double* sm_Ginv = nullptr, int sm_slot = -1, uint64_t* ops_bar = nullptr) {
   const int g = lane >> 2, t = lane & 3;
   const int prob = 8 * pt + g;
   const int is_done = b.done[prob];
   const double mu10 = b.mu10[prob], mu20 = b.mu20[prob];      // (issued together with `done`: one round trip)
   const int slot = b.slot[prob];
+  XSTAMP(0)
   if (__all_sync(0xffffffffu, is_done)) return false;
+  XSTAMP(1)
   const int Lp = d.Lp;
   const int ct0 = pt * d.nplanes + p0;
   const size_t vstride = (size_t)d.npt * d.nplanes * NT * 64;
@@ -533,32 +558,65 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
   double x0[NP][NT][2];
   {
     double rhs[NP][NT][2];
+    // Every load of this block is issued before the first dependent instruction: all (plane, row tile) pieces of the
+    // four base vectors at once, then the partial sums of V four splits at a time (predicated, summed in split order --
+    // a loop with a run-time trip count per row tile serialised ~15 L2 round trips here).
+    double2 vsum[NP][NT];
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-      const int nsp = (SPLIT && p0 + p == 0) ? d.nsplit : 1;   // imaginary plane: z lives in split 0, owned by this function
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         const size_t o = frag_index(ct0 + p, NT, j, lane);
         const double2 b0 = *reinterpret_cast<const double2*>(b.b0 + o);
         const double2 hh = *reinterpret_cast<const double2*>(b.h10 + o);
         const double2 x1 = *reinterpret_cast<const double2*>(b.x1 + o);
-        double2 v = *reinterpret_cast<const double2*>(b.V + o);
-#pragma unroll 4
-        for (int sp = 1; sp < nsp; ++sp) {
-          const double2 q = *reinterpret_cast<const double2*>(b.V + sp * vstride + o);
-          v.x += q.x;
-          v.y += q.y;
-        }
-        rhs[p][j][0] = b0.x + hh.x + mu10 * x1.x + v.x;
-        rhs[p][j][1] = b0.y + hh.y + mu10 * x1.y + v.y;
+        vsum[p][j] = *reinterpret_cast<const double2*>(b.V + o);
+        rhs[p][j][0] = b0.x + hh.x + mu10 * x1.x;
+        rhs[p][j][1] = b0.y + hh.y + mu10 * x1.y;
         if (EARLY) {
           hh_pre[p][j][0] = hh.x;
           hh_pre[p][j][1] = hh.y;
         }
       }
     }
+    if (SPLIT && p0 == 0) {      // (imaginary plane: z lives in split 0, owned by this function)
+      const int nsp = d.nsplit;
+#pragma unroll 1
+      for (int sp0 = 1; sp0 < nsp; sp0 += 4) {
+        double2 q[4][NT];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            q[k][j] = make_double2(0.0, 0.0);
+            if (sp0 + k < nsp)
+              q[k][j] = *reinterpret_cast<const double2*>(b.V + (size_t)(sp0 + k) * vstride + frag_index(ct0, NT, j, lane));
+          }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (sp0 + k < nsp) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+              vsum[0][j].x += q[k][j].x;
+              vsum[0][j].y += q[k][j].y;
+            }
+          }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        rhs[p][j][0] += vsum[p][j].x;
+        rhs[p][j][1] += vsum[p][j].y;
+      }
     // ---- xi1 = Ginv rhs, one tensor-core GEMM per distinct factor slot in the tile (one slot unless
     // the problems of the tile sit on different (mu10, mu20): per-problem mode only)
+#ifdef SPM_TRACE
+    if (rhs[0][0][0] == 1.2345e300) return false;      // (forces the loads to have arrived before the stamp)
+#endif
+    XSTAMP(2)
+    if (PRE && ops_bar != nullptr) mbar_wait(ops_bar, 0);      // staged operands (bulk copies issued at kernel start) have landed
     unsigned remaining = __ballot_sync(0xffffffffu, !is_done);
 #pragma unroll 1
     do {
@@ -579,6 +637,7 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
     } while (remaining);
   }
 
+  XSTAMP(3)
   // ---- KKT correction enforcing C x0 = D   (objectivefunc.py:148-157)
   {
     const double* wv = b.w_cache + (size_t)slot * Lp;
@@ -601,71 +660,77 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
     }
   }
 
+  XSTAMP(4)
   // ---- y = P^T P x0 (both planes in one GEMM)
   double y[NP][NT][2];
   if (PRE && sm_PtP != nullptr) frag_gemm<NT, NP, true>(y, x0, sm_PtP, lane);
   else frag_gemm<NT, NP>(y, x0, b.PtPf, lane);
 
+  XSTAMP(5)
   const double thr = 0.5 * b.lam / mu10;
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
+    // Loads first, stores last: the compiler may not move a load above a store that could alias it, so interleaving
+    // them row tile by row tile made every row tile a dependent L2 round trip (measured: 4 us per plane).
     // ---- norms of the x0 change, plain and in Gram form
     double n_d = 0.0, n_xo = 0.0, nPd = 0.0, nPxo = 0.0, nPx = 0.0;
     {
-      double xo[1][NT][2], yo[1][NT][2];
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        const double2 v = EARLY ? make_double2(xo_pre[p][j][0], xo_pre[p][j][1])
-                                : *reinterpret_cast<const double2*>(b.x0 + frag_index(ct0 + p, NT, j, lane));
-        xo[0][j][0] = v.x;
-        xo[0][j][1] = v.y;
-        // `_x_old[0]` of the reference (optimizer.py:324): only kept when the caller asks for it
-        if (b.x0_old != nullptr && !is_done) *reinterpret_cast<double2*>(b.x0_old + frag_index(ct0 + p, NT, j, lane)) = v;
-      }
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        const double2 v = EARLY ? make_double2(yo_pre[p][j][0], yo_pre[p][j][1])
-                                : *reinterpret_cast<const double2*>(b.y0 + frag_index(ct0 + p, NT, j, lane));
-        yo[0][j][0] = v.x;
-        yo[0][j][1] = v.y;
-      }
-#pragma unroll
-      for (int j = 0; j < NT; ++j)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const double dd = x0[p][j][e] - xo[0][j][e];
-          n_d += dd * dd;
-          n_xo += xo[0][j][e] * xo[0][j][e];
-          nPd += dd * (y[p][j][e] - yo[0][j][e]);
-          nPxo += xo[0][j][e] * yo[0][j][e];
-          nPx += x0[p][j][e] * y[p][j][e];
-        }
-    }
-    // ---- imaginary plane: z <- z - mu20 y,  a += mu20 x0   (Im(h20) never leaves L-space)
-    if (p0 + p == 1 && !is_done) {
+      double2 xo2[NT], yo2[NT];
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         const size_t o = frag_index(ct0 + p, NT, j, lane);
-        double2 zv = *reinterpret_cast<const double2*>(b.V + o);
-        zv.x -= mu20 * y[p][j][0];
-        zv.y -= mu20 * y[p][j][1];
-        *reinterpret_cast<double2*>(b.V + o) = zv;
-        double2 av = *reinterpret_cast<const double2*>(b.aim + o);
-        av.x += mu20 * x0[p][j][0];
-        av.y += mu20 * x0[p][j][1];
-        *reinterpret_cast<double2*>(b.aim + o) = av;
+        xo2[j] = EARLY ? make_double2(xo_pre[p][j][0], xo_pre[p][j][1]) : *reinterpret_cast<const double2*>(b.x0 + o);
+        yo2[j] = EARLY ? make_double2(yo_pre[p][j][0], yo_pre[p][j][1]) : *reinterpret_cast<const double2*>(b.y0 + o);
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const double xo[2] = {xo2[j].x, xo2[j].y}, yo[2] = {yo2[j].x, yo2[j].y};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double dd = x0[p][j][e] - xo[e];
+          n_d += dd * dd;
+          n_xo += xo[e] * xo[e];
+          nPd += dd * (y[p][j][e] - yo[e]);
+          nPxo += xo[e] * yo[e];
+          nPx += x0[p][j][e] * y[p][j][e];
+        }
+      }
+      // `_x_old[0]` of the reference (optimizer.py:324): only kept when the caller asks for it
+      if (b.x0_old != nullptr && !is_done) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j) *reinterpret_cast<double2*>(b.x0_old + frag_index(ct0 + p, NT, j, lane)) = xo2[j];
+      }
+    }
+    // ---- second batch of loads: h10 and, imaginary plane, z and a
+    double2 hh2[NT], zv2[NT], av2[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const size_t o = frag_index(ct0 + p, NT, j, lane);
+      hh2[j] = EARLY ? make_double2(hh_pre[p][j][0], hh_pre[p][j][1]) : *reinterpret_cast<const double2*>(b.h10 + o);
+      if (p0 + p == 1) {
+        zv2[j] = *reinterpret_cast<const double2*>(b.V + o);
+        av2[j] = *reinterpret_cast<const double2*>(b.aim + o);
+      }
+    }
+    // ---- imaginary plane: z <- z - mu20 y,  a += mu20 x0   (Im(h20) never leaves L-space)
+    if (p0 + p == 1) {
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        zv2[j].x -= mu20 * y[p][j][0];
+        zv2[j].y -= mu20 * y[p][j][1];
+        av2[j].x += mu20 * x0[p][j][0];
+        av2[j].y += mu20 * x0[p][j][1];
       }
     }
     // ---- L1 z-update (real plane only; the imaginary part of x1 is identically zero) + dual ascent
     double n_p = 0.0, n_x0 = 0.0, n_x1 = 0.0;
+    double2 zz2[NT], hn2[NT];
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      const size_t o = frag_index(ct0 + p, NT, j, lane);
-      const double2 hh = EARLY ? make_double2(hh_pre[p][j][0], hh_pre[p][j][1]) : *reinterpret_cast<const double2*>(b.h10 + o);
       double zz[2], hn[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const double xv = x0[p][j][e], hv = e == 0 ? hh.x : hh.y;
+        const double xv = x0[p][j][e], hv = e == 0 ? hh2[j].x : hh2[j].y;
         double z = 0.0;
         if (p0 + p == 0) {
           const double yv = -((hv - mu10 * xv) / mu10);
@@ -678,10 +743,21 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
         n_x0 += xv * xv;
         n_x1 += z * z;
       }
-      if (!is_done) {
+      zz2[j] = make_double2(zz[0], zz[1]);
+      hn2[j] = make_double2(hn[0], hn[1]);
+    }
+    // ---- all stores of the plane
+    if (!is_done) {
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const size_t o = frag_index(ct0 + p, NT, j, lane);
+        if (p0 + p == 1) {
+          *reinterpret_cast<double2*>(b.V + o) = zv2[j];
+          *reinterpret_cast<double2*>(b.aim + o) = av2[j];
+        }
         *reinterpret_cast<double2*>(b.x0 + o) = make_double2(x0[p][j][0], x0[p][j][1]);
-        *reinterpret_cast<double2*>(b.x1 + o) = make_double2(zz[0], zz[1]);
-        *reinterpret_cast<double2*>(b.h10 + o) = make_double2(hn[0], hn[1]);
+        *reinterpret_cast<double2*>(b.x1 + o) = zz2[j];
+        *reinterpret_cast<double2*>(b.h10 + o) = hn2[j];
         *reinterpret_cast<double2*>(b.y0 + o) = make_double2(y[p][j][0], y[p][j][1]);
       }
     }
@@ -721,6 +797,7 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
       nrm[6] = nPxo > 0.0 ? nPxo : 0.0;
       nrm[7] = nPx > 0.0 ? nPx : 0.0;     // |P x0|^2 of this plane
     }
+    XSTAMP(6 + p)
   }
   return true;
 }
@@ -831,12 +908,13 @@ struct PassSmem {
 // 1 / 2: lazy iteration without / with a pending decision of the previous iteration (lazy_head / lazy_tail); nA = CTAs
 // of the stand-alone x-update kernel whose partial sums the last CTA of this pass adds (unfused path).
 //
-// BAL (FNP != 0 with the balanced decomposition): the WHOLE iteration of a small batch in one launch.  Of the CTAs whose
-// piece starts in tile group G the first one is the group's OWNER: its four warps run the x-update of the group's tiles
-// (V = the sum of the partial slots the pieces left in the previous iteration), then it publishes "x0 of group G is
-// new" by storing the launch's sequence number into xready[G] (release); every CTA waits for that number (acquire)
-// before it touches chunks of G.  All CTAs of the single wave are co-resident (the launcher checks the occupancy), the
-// owners never wait for anybody, so the waits always end; a watchdog turns a broken assumption into flags[2] = -3.
+// BAL (FNP != 0 with the balanced decomposition): the WHOLE iteration of a small batch in one launch.  First the
+// x-update: its units (problem tile, plane) are dealt out to all warps of the grid (V = the sum of the partial slots the
+// pieces left in the previous iteration); a warp that finishes a unit adds one to xready[G] of the tile's group
+// (release).  Then the pass: before a CTA touches chunks of group G it waits until xready[G] has reached
+// (launch sequence number) x (units of G) (acquire).  All CTAs of the single wave are co-resident (cooperative launch;
+// the launcher also checks the occupancy) and the x-update waits for nobody, so the waits always end; a watchdog turns a
+// broken assumption into flags[2] = -3.
 template <int NT, int MT, int MODE, int FNP, bool BAL = false>   // FNP: 0 = pass only, 1/2 = fused x-update of 1/2 planes
 __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4)      // (shared memory admits 3 CTAs per SM for NT = 5)
     spm_pass_kernel(admm_spm_dims d, admm_spm_buffers b, admm_peer_comm c, int lazy, int nA) {
@@ -851,9 +929,9 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
 #endif
   PASS_STAMP(0)
   __shared__ double wsum[PASS_WARPS * 10];        // lazy: partial sums of the ten squared norms, one row per warp
-  if (MODE == PASS_STEP && d.batch_wide && b.lazy != nullptr) {
+  if (!BAL && MODE == PASS_STEP && d.batch_wide && b.lazy != nullptr) {
     // the fused kernel opens the iteration (decision of the previous one); the stand-alone pass follows the x-update
-    // kernel, which has taken it already
+    // kernel, which has taken it already.  (BAL: further down, with the first copies already in flight)
     if ((lazy && FNP != 0) ? lazy_head(d, b, c, lazy == 2) : (__ldcg(b.lazy + 2) != 0)) return;
   }
   using SM = PassSmem<NT, MT>;
@@ -864,6 +942,7 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + PASS_STAGES * STAGE_D);
   uint64_t* empty_bar = full_bar + PASS_STAGES;
   unsigned* ticket = reinterpret_cast<unsigned*>(empty_bar + PASS_STAGES);
+  uint64_t* ops_bar = reinterpret_cast<uint64_t*>(ticket + PASS_STAGES);      // BAL: the staged x-update operands
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int nct = d.nrt / PASS_CHUNK_RT;                 // chunks per group
@@ -893,61 +972,100 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
       mbar_init(empty_bar + s, PASS_WARPS);
       ticket[s] = 0;
     }
+    if (BAL) mbar_init(ops_bar, 1);
     fence_barrier_init();
   }
   if (MODE == PASS_STEP && lazy && lane < 10) wsum[warp * 10 + lane] = 0.0;      // (own row: ordered by program order per warp)
-  // BAL: sequence number of this launch (the CTA that finishes last advances lazy[3]) and the group this CTA owns
-  int bal_stamp = 0, bal_own_grp = -1;
+  // BAL: sequence number of this launch (the CTA that finishes last advances lazy[3]) and this warp's first x-update
+  // unit.  A unit is (problem tile, plane); the npt * NPL units are dealt out to ALL warps of the grid, round k to warp
+  // (k + cta + cta / nsm) % 4 of CTA (unit % ncta): with the usual breadth-first placement of a 3-CTAs-per-SM grid the
+  // CTAs of one SM then work on different SM sub-partitions -- the x-update is bound by the FP64 pipe of its
+  // sub-partition, and with whole tile groups on "owner" CTAs (first version) up to three owners shared an SM and took
+  // 23 us instead of 12 while two thirds of the SMs idled.
+  int bal_stamp = 0, bal_unit0 = -1, bal_ustride = 0;
   if (BAL) {
+    constexpr int NPLc = FNP == 0 ? 1 : FNP;
     bal_stamp = __ldcg(b.lazy + 3) + 1;
-    const long long T = (long long)((d.npt + GT - 1) / GT) * nct;
-    const int grp0 = (int)(g_begin / nct);
-    const int first = (int)(((long long)grp0 * nct * d.nbal + T - 1) / T);       // first CTA whose piece starts in grp0
-    if ((int)blockIdx.x == first && nchunks > 0) bal_own_grp = grp0;
+    const int ncta = gridDim.x, nsm = max(1, ncta / 3);
+    const int k0 = (warp - (int)blockIdx.x - (int)blockIdx.x / nsm) & (PASS_WARPS - 1);      // round in which this warp is served first
+    bal_unit0 = k0 * ncta + blockIdx.x;
+    bal_ustride = PASS_WARPS * ncta;
+    if (bal_unit0 >= d.npt * NPLc) bal_unit0 = -1;
   }
-  __syncthreads();
+  const bool bal_xwork = BAL && __syncthreads_or(bal_unit0 >= 0);      // (also the barrier after the mbarrier init)
+  if (!BAL) __syncthreads();
+  constexpr int OPD = NT * NT * 64;                                         // doubles per L x L operand
+  constexpr bool OPS_BOTH = 2 * OPD <= STAGE_D;                             // room for P^T P and the cached inverse?
+  static_assert(!BAL || OPD <= STAGE_D, "ring stage too small for a staged operand");
+  int bal_slot0 = -1;
   if (tid == 0) {
-    // (an owner CTA stages the operands of its x-update in ring stage 1 first: that stage is filled afterwards)
+    // (a CTA with x-update units stages the L x L operands in ring stage 1 first: that stage is filled afterwards)
     for (int s = 0; s < PASS_STAGES && s < nchunks; ++s)
-      if (!(BAL && bal_own_grp >= 0 && s == 1)) fill(s, g_begin + s);
+      if (!(bal_xwork && s == 1)) fill(s, g_begin + s);
+  }
+  if (bal_xwork) {
+    // the factor row of the first problem this CTA touches (batch-wide: the row of all problems) and P^T P: two bulk
+    // copies into ring stage 1, completing on their own barrier -- in flight during the head and the loads of the
+    // x-update, awaited just before its first GEMM
+    constexpr int NPLc = FNP == 0 ? 1 : FNP;
+    const int ufirst = min((int)blockIdx.x, d.npt * NPLc - 1);
+    bal_slot0 = b.slot[min(8 * (ufirst / NPLc), 8 * d.npt - 1)];
+    if (tid == 0) {
+      constexpr unsigned OPB = OPD * sizeof(double);
+      mbar_expect_tx(ops_bar, OPS_BOTH ? 2 * OPB : OPB);
+      tma_bulk_g2s(ring + STAGE_D, b.Ginv_cache + (size_t)bal_slot0 * d.Lp * d.Lp, OPB, ops_bar);
+      if (OPS_BOTH) tma_bulk_g2s(ring + STAGE_D + OPD, b.PtPf, OPB, ops_bar);
+    }
+  }
+  if (BAL && MODE == PASS_STEP && d.batch_wide && b.lazy != nullptr) {
+    // the decision of the previous iteration (reads only: the copies above are harmless if the batch has converged,
+    // but they have to land before the CTA may exit)
+    if (lazy ? lazy_head(d, b, c, lazy == 2) : (__ldcg(b.lazy + 2) != 0)) {
+      if (tid == 0) {
+        for (int s = 0; s < PASS_STAGES && s < nchunks; ++s)
+          if (!(bal_xwork && s == 1)) mbar_wait(full_bar + s, 0);
+        if (bal_xwork) mbar_wait(ops_bar, 0);
+      }
+      __syncthreads();
+      return;
+    }
   }
 
   PASS_STAMP(1)
-  if (BAL && bal_own_grp >= 0) {
-    // ---- owner: x-update of the group's tiles, every warp one tile (all planes)
+  if (bal_xwork) {
+    // ---- x-update of this CTA's units, one (tile, plane) per warp and round
     constexpr int NPL = FNP == 0 ? 1 : FNP;
-    constexpr int OPD = NT * NT * 64;                                       // doubles per L x L operand
-    constexpr bool BOTH = 2 * OPD <= STAGE_D;                               // room for P^T P and the cached inverse?
-    static_assert(OPD <= STAGE_D, "ring stage too small for a staged operand");
     double* sm_ops = ring + STAGE_D;                                        // ring stage 1
-    const int grp0 = bal_own_grp;
-    const int pfirst = min(8 * grp0 * GT, 8 * d.npt - 1);
-    const int slot0 = b.slot[pfirst];                                       // batch-wide: the factor row of all problems
-    if (BOTH) {
-      for (int i = tid; i < OPD / 2; i += PASS_WARPS * 32) cp_async16(sm_ops + OPD + 2 * i, b.PtPf + 2 * i);
-    }
-    {
-      const double* gi = b.Ginv_cache + (size_t)slot0 * d.Lp * d.Lp;
-      for (int i = tid; i < OPD / 2; i += PASS_WARPS * 32) cp_async16(sm_ops + 2 * i, gi + 2 * i);
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
+    const int slot0 = bal_slot0;
+    constexpr bool BOTH = OPS_BOTH;
+    XSTAMP(8)
+    XSTAMP(9)
     double* wp = lazy ? wsum + warp * 10 : nullptr;
 #pragma unroll 1
-    for (int m = 0; m < MT; ++m) {
-      const int ptm = (grp0 * PASS_WARPS + warp) * MT + m;
-      if (ptm < d.npt)
-        xupdate_tile<NT, NPL, true, true, false>(d, b, ptm, lane, 0, wp, BOTH ? sm_ops + OPD : nullptr, sm_ops, slot0);
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(b.xready + grp0), "r"(bal_stamp) : "memory");
-      if (nchunks > 1) {
-        fence_proxy_async();               // the staged operands were written through the generic proxy
-        fill(1, g_begin + 1);
+    for (int u = bal_unit0; u >= 0 && u < d.npt * NPL; u += bal_ustride) {
+      const int ptm = u / NPL;
+      xupdate_tile<NT, 1, true, true, false>(d, b, ptm, lane, u - ptm * NPL, wp, BOTH ? sm_ops + OPD : nullptr, sm_ops, slot0,
+                                             ops_bar);
+      // publish: one more unit of the tile's group is done (release; the waiters acquire)
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+        atomicAdd(b.xready + ptm / GT, 1);
       }
+    }
+    XSTAMP(10)
+    __syncthreads();
+    XSTAMP(12)
+#ifdef SPM_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < 1000) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;\n" : "=r"(smid));
+      reinterpret_cast<long long*>(b.gpart)[2048 + 2 * blockIdx.x] = ((gtimer() - t_entry) << 12) | smid;
+    }
+#endif
+    if (tid == 0 && nchunks > 1) {
+      fence_proxy_async();               // the staged operands were written through the generic proxy
+      fill(1, g_begin + 1);
     }
   }
   PASS_STAMP(2)
@@ -1001,16 +1119,22 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
     double xa[MT][NT][2];      // A fragments of GEMM1': -mu20 * Re(x0)   (k-slot (j,e) of lane (g,t) <-> l = 8j+2t+e)
     double acc[MT][NT][2];     // C fragments of GEMM2': V
     bool all_done = true;
-    if (BAL && grp != bal_own_grp) {
-      // x0 of this group comes from its owner CTA: wait for this launch's sequence number
+    if (BAL) {
+      // x0 of this group comes from the warps that ran its x-update units: wait until all of them have reported
+      // (xready counts units, it runs on from launch to launch)
+      constexpr int NPLc = FNP == 0 ? 1 : FNP;
+      const int bal_expect = bal_stamp * NPLc * (min(d.npt, (grp + 1) * GT) - grp * GT);
+      // relaxed polling, ONE acquire fence at the end (an ld.acquire per poll is a load plus an invalidation of the
+      // SM's whole L1)
       if (lane == 0) {
         const long long t_start = clock64();
-        while ((int)ld_acquire_u32(b.xready + grp) != bal_stamp) {
+        while ((int)ld_relaxed_u32(b.xready + grp) != bal_expect) {
           if (clock64() - t_start > 4000000000LL) {      // the CTAs are not co-resident after all: give up (~2 s)
             b.flags[2] = -3;
             break;
           }
         }
+        fence_acquire_gpu();
       }
       __syncwarp();
     }
@@ -1034,6 +1158,10 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
     }
     const bool active = !__all_sync(0xffffffffu, all_done);
     PASS_STAMP(3)
+#ifdef SPM_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < 1000 && gc == g_begin)
+      reinterpret_cast<long long*>(b.gpart)[2048 + 2 * blockIdx.x + 1] = gtimer() - t_entry;
+#endif
 
     double n_dh[MT], n_xm[MT], ratio[MT];
 #pragma unroll
@@ -1177,6 +1305,9 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
     }
   }
   PASS_STAMP(5)
+#ifdef SPM_TRACE
+  if (threadIdx.x == 0 && blockIdx.x < 512) reinterpret_cast<long long*>(b.gpart)[4096 + 16 * blockIdx.x + 13] = gtimer() - t_entry;
+#endif
   if (MODE == PASS_STEP && lazy) {
     const int ncta = gridDim.x * gridDim.y;
     lazy_tail(b, c, wsum, PASS_WARPS, FNP != 0, true, FNP != 0 ? ncta : nA, FNP != 0 ? 0 : ncta, ring,     // (ring: all chunks consumed)
@@ -1193,6 +1324,12 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
     }
   }
   PASS_STAMP(6)
+#ifdef SPM_TRACE
+  if (threadIdx.x == 0 && blockIdx.x < 512) {
+    reinterpret_cast<long long*>(b.gpart)[4096 + 16 * blockIdx.x + 14] = gtimer() - t_entry;
+    reinterpret_cast<long long*>(b.gpart)[4096 + 16 * blockIdx.x + 15] = t_entry;
+  }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------

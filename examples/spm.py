@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """notebooks/spm.ipynb of SpM-lab/admmsolver (sparse-modelling analytic continuation) through the
 drop-in API, with the plotting removed and `sparse_ir` replaced by the self-contained IR-like basis of
-`admmsolver_b200.problems.ir_basis` (SVD of the fermionic kernel on Gauss-Legendre panels; L = 39 for
-beta = 100, wmax = 10, eps = 1e-7 as at spm.ipynb:214).  SURVEY.md 8(f) row f4: the pipeline either
-side of the solver -- spectral function -> IR coefficients rho_l -> g_l = -s_l rho_l (+ noise) before,
-rho(omega) = v(omega) . x0 after -- the reconstruction runs on the device (`admm_gemm`).
+`admmsolver_b200.irbasis.ir_basis_device` (SVD of the fermionic kernel on Gauss-Legendre panels by one-sided Jacobi
+on the GPU; L = 39 for beta = 100, wmax = 10, eps = 1e-7 as at spm.ipynb:214).  SURVEY.md 8(f) row f4: the pipeline
+either side of the solver -- spectral function -> IR coefficients rho_l -> g_l = -s_l rho_l (+ noise) before,
+rho(omega) = v(omega) . x0 after -- runs on the device (`admm_svd_jacobi`, `admm_gemm`); `device_basis=False` takes
+the host construction (`problems.ir_basis`, np.linalg.svd) instead.
 
     PYTHONPATH=.:compat python examples/spm.py [niter]
 """
@@ -19,23 +20,31 @@ import numpy as np  # noqa: E402
 from admmsolver.matrix import DenseMatrix, DiagonalMatrix, identity  # noqa: E402
 from admmsolver.objectivefunc import ConstrainedLeastSquares, L1Regularizer, NonNegativePenalty  # noqa: E402
 from admmsolver.optimizer import Problem, SimpleOptimizer  # noqa: E402
-from admmsolver_b200 import problems  # noqa: E402
+from admmsolver_b200 import irbasis, problems  # noqa: E402
 
 
-def main(niter: int = 10000, nw: int = 2000, verbose: bool = True):
+def main(niter: int = 10000, nw: int = 2000, verbose: bool = True, device_basis: bool = True):
     # spm.ipynb:61-65  basis
     wmax, beta = 10.0, 100.0
-    basis = problems.ir_basis(beta=beta, wmax=wmax, eps=1e-7)
-    L = basis.size
-    # spm.ipynb:104-107,155-163  model spectrum and its IR expansion on the basis' own quadrature
     rho = problems.rho_three_gaussians
-    rhol = basis.v_omega @ (basis.womega * rho(basis.omega))
-    gl = -basis.s * rhol
-    # spm.ipynb:198-199  sampling points in real frequency (uniform grid instead of the roots of v_{L-1})
     smpl_w = np.linspace(-wmax, wmax, nw)
-    prj_w = np.ascontiguousarray(basis.v(smpl_w).T)
-    # spm.ipynb:214-219  sum rule
-    prj_sum = basis.sum_rule()
+    if device_basis:
+        dbasis = irbasis.ir_basis_device(beta=beta, wmax=wmax, eps=1e-7)
+        basis = dbasis.to_host()
+        # spm.ipynb:155-163  IR expansion of the model spectrum; :198-199 sampling matrix; :214-219 sum rule -- device GEMMs
+        rhol = dbasis.expand_spectrum(rho(dbasis.omega)).cpu().numpy()
+        prj_w = dbasis.sampling_matrix(smpl_w).cpu().numpy()
+        prj_sum = dbasis.sum_rule().cpu().numpy()
+    else:
+        basis = problems.ir_basis(beta=beta, wmax=wmax, eps=1e-7)
+        # spm.ipynb:104-107,155-163  model spectrum and its IR expansion on the basis' own quadrature
+        rhol = basis.v_omega @ (basis.womega * rho(basis.omega))
+        # spm.ipynb:198-199  sampling points in real frequency (uniform grid instead of the roots of v_{L-1})
+        prj_w = np.ascontiguousarray(basis.v(smpl_w).T)
+        # spm.ipynb:214-219  sum rule
+        prj_sum = basis.sum_rule()
+    L = basis.size
+    gl = -basis.s * rhol
     # spm.ipynb:243-259  the problem
     alpha, noise = 1e-4, 1e-4
     gl_dirty = gl + noise * np.random.RandomState(0).randn(L)
@@ -49,7 +58,10 @@ def main(niter: int = 10000, nw: int = 2000, verbose: bool = True):
     x0 = opt.x[0]
     # spm.ipynb:300  reconstruction rho(omega) = v(omega) . x0 on a fine grid, on the device
     omegas = np.linspace(-5, 5, 1000)
-    rho_rec = np.asarray((DenseMatrix(np.ascontiguousarray(basis.v(omegas).T)) @ x0)).real
+    if device_basis:
+        rho_rec = dbasis.reconstruct(x0, omegas).cpu().numpy().real
+    else:
+        rho_rec = np.asarray((DenseMatrix(np.ascontiguousarray(basis.v(omegas).T)) @ x0)).real
     err = np.abs(rho_rec - rho(omegas)).max()
     if verbose:
         print("L =", L, " Nw =", nw, " iterations run =", len(opt._primal_residual))

@@ -252,8 +252,9 @@ typedef struct admm_spm_buffers {
   int* lazy;              /* [4], zero-initialised: 0 CTA ticket of the in-kernel reduction, 2 batch converged
                              (every kernel of the engine returns at once when set), 3 launch sequence number
                              of the fused balanced step                                          */
-  int* xready;            /* [tile groups], zero-initialised: launch sequence number for which the group's x0 is
-                             current (fused balanced step: owner CTA -> the pieces of the group)    */
+  int* xready;            /* [tile groups], zero-initialised, never reset: x-update units (tile, plane) of the group
+                             finished so far, over all launches of the fused balanced step (the pieces of a group
+                             wait for launch sequence number x units of the group)                */
   /* control */
   int* iter_counter;      /* device scalar: iterations launched so far in this solve call      */
   int* flags;             /* [4]: 0 any mu changed, 1 number of problems done, 2 first non-positive pivot of an in-kernel re-inversion (admm_spm_solo), 3 arrival counter of its batch-wide all-reduce */

@@ -434,10 +434,11 @@ def test_notebook_examples(build_lib):
     xanswer, x0, opt = load("basis_pursuit").main(verbose=False)
     assert abs(np.abs(xanswer).max() - 1.4312955709975443) < 1e-15
     assert abs(np.abs(xanswer - x0).max() - 0.0054070107628211295) < 1e-9
-    r = load("spm").main(niter=3000, verbose=False)
-    assert r["L"] == 39 and abs(r["sum_rule"] - 1.0) < 1e-10       # spm.ipynb:214,270
-    assert np.abs(r["rho_rec"] - r["rho"]).max() < 0.15 * r["rho"].max()      # the spectrum is recovered (noise 1e-4: the sharp peak is smoothed)
-    assert r["rho_rec"].min() > -1e-3                               # and non-negative up to the ADMM residual
+    for device_basis in (True, False):                              # IR basis by the on-device Jacobi SVD / by np.linalg.svd
+        r = load("spm").main(niter=3000, verbose=False, device_basis=device_basis)
+        assert r["L"] == 39 and abs(r["sum_rule"] - 1.0) < 1e-10       # spm.ipynb:214,270
+        assert np.abs(r["rho_rec"] - r["rho"]).max() < 0.15 * r["rho"].max()      # the spectrum is recovered (noise 1e-4: the sharp peak is smoothed)
+        assert r["rho_rec"].min() > -1e-3                               # and non-negative up to the ADMM residual
 
 
 # ------------------------------------------------------------------ `_x_old` hand-over after fused solves

@@ -38,3 +38,33 @@ for L in order:
         row = t[L, ci]
         print(f"  {cn:8s} entry {(row[7] - base) / 1e3:8.2f} us | " + "  ".join(f"{(row[i] - row[7]) / 1e3:6.2f}" for i in range(7)))
 print("columns (us after kernel entry):", ", ".join(names))
+
+x = e.gpart.view(torch.int64)[1024:1024 + 13].cpu().numpy()
+xn = ["tile entry", "done/mu/slot loaded", "rhs formed", "Ginv gemm done", "KKT done", "PtP gemm done", "plane 0 done", "plane 1 done",
+      "owner block entry", "operands staged", "tiles done", "threadfence done", "syncthreads done"]
+print("x-update of CTA 0 / warp 0 (us after owner block entry):")
+for i in (8, 9, 0, 1, 2, 3, 4, 5, 6, 10, 12):
+    print(f"  {xn[i]:24s} {(x[i] - x[8]) / 1e3:7.2f}")
+
+n = e.dims.nbal
+raw = e.gpart.view(torch.int64)[2048:2048 + 2 * n].cpu().numpy().reshape(n, 2)
+smid = raw[:, 0] & 4095
+pc = np.stack([raw[:, 0] >> 12, raw[:, 1]], axis=1) / 1e3
+own = pc[:, 0] > 0
+print("CTAs per SM: ", np.bincount(np.bincount(smid[own])).tolist(), " smid of CTAs 0,1,2,148,149,296:", smid[[0, 1, 2, 148, 149, 296]].tolist())
+print(f"owners: {own.sum()}  x-update done (us after entry): min {pc[own, 0].min():.2f} median {np.median(pc[own, 0]):.2f} max {pc[own, 0].max():.2f}")
+print(f"first segment start: min {pc[:, 1].min():.2f} median {np.median(pc[:, 1]):.2f} max {pc[:, 1].max():.2f}")
+print("owner done by CTA index (every 8th owner):", np.round(pc[own, 0][::8], 1).tolist())
+print("segment start by CTA index (every 24th):", np.round(pc[::24, 1], 1).tolist())
+
+xs = e.gpart.view(torch.int64)[4096:4096 + 16 * n].cpu().numpy().reshape(n, 16)[own]
+rel_ = (xs - xs[:, 8:9]) / 1e3
+print("per-owner x-update phases (us after owner block entry): min / median / max over the owners")
+for i in (9, 1, 2, 3, 4, 5, 6, 10, 12):
+    print(f"  {xn[i]:24s} {rel_[:, i].min():7.2f} {np.median(rel_[:, i]):7.2f} {rel_[:, i].max():7.2f}")
+
+allx = e.gpart.view(torch.int64)[4096:4096 + 16 * n].cpu().numpy().reshape(n, 16)
+cd, td, ent = allx[:, 13] / 1e3, allx[:, 14] / 1e3, allx[:, 15] / 1e3
+print(f"all CTAs: chunks+epilogue done (us after own entry) min {cd.min():.2f} median {np.median(cd):.2f} max {cd.max():.2f};"
+      f" tail done min {td.min():.2f} median {np.median(td):.2f} max {td.max():.2f}; entry spread {ent.max() - ent.min():.2f} us")
+print("chunk phase length (segment start -> done): min %.2f median %.2f max %.2f" % tuple(np.percentile(cd - pc[:, 1], [0, 50, 100])))

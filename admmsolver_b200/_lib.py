@@ -54,6 +54,7 @@ class SpmBuffers(C.Structure):
         ("iter_counter", _P), ("flags", _P), ("history", _P), ("hist_cap", C.c_int),
         ("lam", C.c_double), ("rtol", C.c_double), ("max_mu", C.c_double),
         ("fact_incr", C.c_double), ("th_change", C.c_double),
+        ("bal_bounds", _P), ("bal_first", _P),
     ]
 
 

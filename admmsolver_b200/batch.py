@@ -57,11 +57,14 @@ class SharedSpM:
     """
 
     CACHE_SLOTS = 64
+    #: relative over-/under-weight of the pieces of the first / last residency tier of a full-wave balanced
+    #: decomposition (tools/bal_sweep.py)
+    BAL_SKEW = 0.0
 
     def __init__(self, s, P, C_, D, g, lam: float, mu: float = 0.1, alpha: float = 1.0,
                  batch_wide: bool = False, max_mu: float = 1e3, nsplit: Optional[int] = None,
                  group=None, force_complex: Optional[bool] = None, mt: Optional[int] = None, nbal: Optional[int] = None,
-                 collective: Optional[str] = None, keep_x_old: bool = False):
+                 collective: Optional[str] = None, keep_x_old: bool = False, bal_skew: Optional[float] = None):
         dev = _lib.require_cuda()
         s_t = _dev_tensor(s, dev, _F64)
         g_t = _dev_tensor(g, dev)
@@ -77,7 +80,7 @@ class SharedSpM:
         sd = (-alpha * s_t).to(gv.dtype)
         call("admm_diag_mul", int(cplx), L, L, nb, ptr(sd), ptr(gv), nb, ptr(b0), nb, stream())
         self._init_common(G0, b0, P, C_, D, lam, mu, mu, batch_wide, max_mu, nsplit, group, force_complex, mt, nbal,
-                          collective, keep_x_old)
+                          collective, keep_x_old, bal_skew)
         self._s = s_t
         self._g = gv
         self._alpha = alpha
@@ -101,7 +104,7 @@ class SharedSpM:
 
     # ------------------------------------------------------------------ setup
     def _init_common(self, G0, b0, P, C_, D, lam, mu10, mu20, batch_wide, max_mu, nsplit, group, force_complex,
-                     mt=None, nbal_req=None, collective=None, keep_x_old=False):
+                     mt=None, nbal_req=None, collective=None, keep_x_old=False, bal_skew=None):
         dev = _lib.require_cuda()
         self.device = dev
         self.group = group
@@ -173,6 +176,27 @@ class SharedSpM:
             else:
                 nsplit = max(1, min(nsplit, nchunks))
         assert mt in (1, 2) and (mt == 1 or Lp <= 40)
+        # Balanced decomposition over a full wave: the CTAs of one SM do not advance evenly (the warp schedulers favour
+        # the CTAs that became resident first: measured on cfg3, the third CTA of an SM finished its equal share 13 us
+        # after the first), so later CTAs get shorter pieces -- weights 1 + skew, ..., 1 - skew over the residency tiers.
+        self._bal_tables = None
+        explicit_skew = bal_skew is not None          # (tests: tables for any number of pieces)
+        if bal_skew is None:
+            bal_skew = float(os.environ.get("ADMM_BAL_SKEW", self.BAL_SKEW))
+        per_sm = SLOTS // _lib.device_info()[0]
+        if (nbal == SLOTS or (explicit_skew and nbal >= per_sm)) and per_sm > 1 and bal_skew != 0.0:
+            total = ngroups * nchunks
+            tier = np.minimum(np.arange(nbal) // max(1, nbal // per_sm), per_sm - 1)
+            w = np.round(1024 * (1.0 + bal_skew * (1.0 - 2.0 * tier / (per_sm - 1)))).astype(np.int64)
+            cum = np.concatenate([[0], np.cumsum(w)])
+            bounds = (total * cum) // cum[-1]
+            if np.all(np.diff(bounds) >= 1):
+                gstart = np.arange(ngroups, dtype=np.int64) * nchunks
+                first = np.searchsorted(bounds, gstart, side="right") - 1
+                last = np.searchsorted(bounds, gstart + nchunks - 1, side="right") - 1
+                nsplit = max(nsplit, int((last - first + 1).max()))
+                self._bal_tables = (torch.from_numpy(bounds.astype(np.int64)).to(dev),
+                                    torch.from_numpy(first.astype(np.int32)).to(dev))
         self.dims = SpmDims(L, Lp, Nw, nrt, nb, npt, nplanes, nsplit, mt, nbal, int(batch_wide))
         self.batch_wide = bool(batch_wide)
         self.lam, self.max_mu = float(lam), float(max_mu)
@@ -273,6 +297,8 @@ class SharedSpM:
                         ("flags", self.flags)):
             setattr(b, name, t.data_ptr())
         b.x0_old = self.x0_oldf.data_ptr() if self.x0_oldf is not None else None
+        b.bal_bounds, b.bal_first = ((self._bal_tables[0].data_ptr(), self._bal_tables[1].data_ptr())
+                                     if self._bal_tables is not None else (None, None))
         b.history = self.history.data_ptr() if self.history is not None else None
         b.hist_cap = int(self.history.shape[0]) if self.history is not None else 0
         b.lam, b.rtol, b.max_mu = self.lam, float(rtol), self.max_mu

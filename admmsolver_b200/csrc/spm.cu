@@ -407,14 +407,14 @@ __device__ __forceinline__ void lazy_tail(const admm_spm_buffers& b, const admm_
   // fixed-order final sum with many loads in flight: thread t < 120 owns value index t % 10 of the x-update-stage
   // partials (flat stride 120), every thread owns index 7 + (t & 1) of the pass partials (flat stride 128)
   double a = 0.0, bs = 0.0;
-  if (tid < 120) {
+  if (tid < 120) {      // (16 loads in flight per thread: the whole sum of a 444-CTA grid is three round trips)
     const int n = nA * 10;
-#pragma unroll 8
+#pragma unroll 16
     for (int i = tid; i < n; i += 120) a += __ldcg(b.cta_partA + i);
   }
   {
     const int n = nB * 2;
-#pragma unroll 8
+#pragma unroll 16
     for (int i = tid; i < n; i += 128) bs += __ldcg(b.cta_partB + i);
   }
   scratch[tid] = a;
@@ -950,8 +950,13 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
   long long g_begin, g_end;
   if (d.nbal > 0) {
     const long long T = (long long)((d.npt + GT - 1) / GT) * nct;
-    g_begin = (long long)blockIdx.x * T / d.nbal;
-    g_end = (long long)(blockIdx.x + 1) * T / d.nbal;
+    if (b.bal_bounds != nullptr) {      // pieces of unequal length (the caller's table; see admm_spm_buffers)
+      g_begin = b.bal_bounds[blockIdx.x];
+      g_end = b.bal_bounds[blockIdx.x + 1];
+    } else {
+      g_begin = (long long)blockIdx.x * T / d.nbal;
+      g_end = (long long)(blockIdx.x + 1) * T / d.nbal;
+    }
   } else {
     const int cps = (nct + d.nsplit - 1) / d.nsplit;     // chunks per split
     const int c_begin = min(nct, (int)blockIdx.y * cps), c_end = min(nct, c_begin + cps);
@@ -1106,7 +1111,7 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
     if (d.nbal > 0) {
       const long long T = (long long)((d.npt + GT - 1) / GT) * nct;
       const long long x = (long long)grp * nct;          // first group-chunk of the group
-      piece = (int)blockIdx.x - (int)(((x + 1) * d.nbal - 1) / T);
+      piece = b.bal_first != nullptr ? (int)blockIdx.x - b.bal_first[grp] : (int)blockIdx.x - (int)(((x + 1) * d.nbal - 1) / T);
     } else {
       piece = blockIdx.y;
     }
@@ -1119,6 +1124,16 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
     double xa[MT][NT][2];      // A fragments of GEMM1': -mu20 * Re(x0)   (k-slot (j,e) of lane (g,t) <-> l = 8j+2t+e)
     double acc[MT][NT][2];     // C fragments of GEMM2': V
     bool all_done = true;
+    // (done / mu20 are not written by this launch: requested before the wait below, one round trip less after it)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      pt[m] = (grp * PASS_WARPS + warp) * MT + m;
+      inr[m] = pt[m] < d.npt;
+      if (!inr[m]) pt[m] = d.npt - 1;        // clamp: loads stay in range, stores are suppressed
+      const int prob = 8 * pt[m] + g;
+      dn[m] = inr[m] ? b.done[prob] : 1;
+      mu20[m] = b.mu20[prob];
+    }
     if (BAL) {
       // x0 of this group comes from the warps that ran its x-update units: wait until all of them have reported
       // (xready counts units, it runs on from launch to launch)
@@ -1140,12 +1155,6 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
     }
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
-      pt[m] = (grp * PASS_WARPS + warp) * MT + m;
-      inr[m] = pt[m] < d.npt;
-      if (!inr[m]) pt[m] = d.npt - 1;        // clamp: loads stay in range, stores are suppressed
-      const int prob = 8 * pt[m] + g;
-      dn[m] = inr[m] ? b.done[prob] : 1;
-      mu20[m] = b.mu20[prob];
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         const double2 v = BAL ? __ldcg(reinterpret_cast<const double2*>(b.x0 + frag_index(pt[m] * npl, NT, j, lane)))

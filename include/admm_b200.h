@@ -265,6 +265,12 @@ typedef struct admm_spm_buffers {
   double max_mu;
   double fact_incr;
   double th_change;
+  /* balanced decomposition with pieces of unequal length (both NULL: nbal equal pieces).  A grid of 3 CTAs per SM does
+     not advance evenly -- the warp schedulers favour the CTAs that became resident first -- so the caller may hand
+     later CTAs shorter pieces: */
+  const long long* bal_bounds;  /* [nbal + 1] ascending group-chunk boundaries, bal_bounds[0] = 0, bal_bounds[nbal] = T;
+                                   every tile group must contain the start of at most nsplit - 1 pieces            */
+  const int* bal_first;         /* [tile groups] first CTA whose piece overlaps the group                           */
 } admm_spm_buffers;
 
 /* x-update (term 0, `ConstrainedLeastSquares.solve`, objectivefunc.py:138-157, with

@@ -10,6 +10,18 @@ for nb in nbs:
     p = problems.spm_batch(min(nb, 4096), basis, Nw=2000, seed=1000)
     g = np.tile(p.g, (1, -(-nb // p.g.shape[1])))[:, :nb]
     e = batch.SharedSpM(p.s, p.P, p.C, np.ones(nb), g, lam=p.lam, mu=p.mu, batch_wide=True)
+    import os
+    if os.environ.get("SKEWS"):
+        for sk in [float(v) for v in os.environ["SKEWS"].split(",")]:
+            e = batch.SharedSpM(p.s, p.P, p.C, np.ones(nb), g, lam=p.lam, mu=p.mu, batch_wide=True, bal_skew=sk)
+            e.solve(100, use_solo=False); torch.cuda.synchronize()
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(5): e.solve(100, use_solo=False)
+            t1.record(); torch.cuda.synchronize()
+            us = t0.elapsed_time(t1) / 500 * 1e3
+            print(f"nb={nb} skew={sk} mt={e.dims.mt} nsplit={e.dims.nsplit} nbal={e.dims.nbal}: {us:.1f} us/iter frac {nb * 324158.0 / (us * 1e-6) / 35.4e12:.3f}", flush=True)
+        continue
     cfgs = [(None, None)] + [(mt, nbal) for mt in (1, 2) for nbal in ((148, 222, 296, 370, 444) if nb > 1500 else (32, 64, 128, 192, 256, 344, 444))]
     for mt, nbal in cfgs:
         try:

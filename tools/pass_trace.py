@@ -68,3 +68,20 @@ cd, td, ent = allx[:, 13] / 1e3, allx[:, 14] / 1e3, allx[:, 15] / 1e3
 print(f"all CTAs: chunks+epilogue done (us after own entry) min {cd.min():.2f} median {np.median(cd):.2f} max {cd.max():.2f};"
       f" tail done min {td.min():.2f} median {np.median(td):.2f} max {td.max():.2f}; entry spread {ent.max() - ent.min():.2f} us")
 print("chunk phase length (segment start -> done): min %.2f median %.2f max %.2f" % tuple(np.percentile(cd - pc[:, 1], [0, 50, 100])))
+
+T = (-(-e.dims.npt // (4 * e.dims.mt))) * (e.dims.nrt // 4)
+nctc = e.dims.nrt // 4
+gb = np.arange(n) * T // n
+ge = (np.arange(n) + 1) * T // n
+strad = (gb // nctc) != ((ge - 1) // nctc)
+ln = cd - pc[:, 1]
+print("chunk phase by kind: straddlers %d: median %.2f max %.2f | others: median %.2f max %.2f" % (strad.sum(), np.median(ln[strad]), ln[strad].max(), np.median(ln[~strad]), ln[~strad].max()))
+print("by #chunks:", {int(k): round(float(np.median(ln[(ge - gb) == k])), 2) for k in np.unique(ge - gb)})
+per_sm = {}
+for i in range(n):
+    per_sm.setdefault(int(smid[i]), []).append(ln[i])
+sm_med = np.array([np.mean(v) for v in per_sm.values()])
+sm_spread = np.array([max(v) - min(v) for v in per_sm.values()])
+print("per-SM mean chunk phase: min %.2f median %.2f max %.2f; within-SM spread median %.2f max %.2f" % (sm_med.min(), np.median(sm_med), sm_med.max(), np.median(sm_spread), sm_spread.max()))
+order = np.argsort(ln)[-8:]
+print("slowest CTAs:", [(int(i), int(smid[i]), bool(strad[i]), int(ge[i] - gb[i]), round(float(pc[i, 1]), 1), round(float(ln[i]), 1)) for i in order])

@@ -248,7 +248,7 @@ def prox_psd(h: torch.Tensor, mu_diag: torch.Tensor, shape, axis: int, complex_o
     return out
 
 
-def svd_jacobi(K: torch.Tensor, max_sweeps: int = 40):
+def svd_jacobi(K: torch.Tensor, max_sweeps: int = 40, return_sweeps: bool = False):
     """SVD of a real (m, n) device matrix by one-sided Jacobi (``admm_svd_jacobi``): returns ``U`` (m, n), ``s`` (n,)
     descending and ``V`` (n, n) with ``K = U diag(s) V^T``; columns of ``U`` belonging to singular values at the
     rounding level of the largest one are unit vectors of noise, as with LAPACK."""
@@ -265,6 +265,8 @@ def svd_jacobi(K: torch.Tensor, max_sweeps: int = 40):
     s_sorted = sv[order]
     U = (Wt[order] / s_sorted.clamp_min(1e-300)[:, None]).t().contiguous()
     V = Vt[order].t().contiguous()
+    if return_sweeps:
+        return U, s_sorted, V, int(info.item())
     return U, s_sorted, V
 
 

@@ -55,6 +55,14 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch) {
   }
 }
 
+// shared-memory address of a generic pointer / 16-byte load that stays in program order among the volatile MMAs
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double2 lds_v2_volatile(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+
 // FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).  SASS: DMMA.8x8x4 on sm_100a.
 // Fragment ownership (lane = 4*g + t):  a = A[g][t],  b = B[t][g],  c0/c1 = C[g][2t], C[g][2t+1].
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -87,7 +95,6 @@ __device__ __forceinline__ void st_stream2(double* p, double2 v) {
 }
 
 // ---- mbarrier + TMA bulk copy (global -> shared, SASS UBLKCP) ---------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }

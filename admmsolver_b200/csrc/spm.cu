@@ -1186,6 +1186,32 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
       if (active) {
         const double* Pc = ring + stage * STAGE_D + lane * 2;
         const double* Sc = ring + stage * STAGE_D + CHUNK_D + st_off;
+        // The 2*NT operand fragments of an 8-row tile, GEMM1' then GEMM2', and the tiles of a chunk follow each other
+        // at a fixed stride (64 doubles): fragment k of the chunk sits at Pc + 64 k.  In the step they are fetched ONE
+        // FRAGMENT AHEAD with volatile loads, so that the fetch of k + 1 is issued before the MMAs of k (the compiler
+        // otherwise sinks every LDS next to its first use: ncu showed each group of four DMMAs waiting ~30 cycles on the
+        // short scoreboard).  Measured: the per-clock rate of the sweep does not move (the other warps of the scheduler
+        // cover those waits, and the board runs at its power cap) -- kept because it is free; a distance of two
+        // fragments (-DPF_DIST=2) and the state of the next tile one tile ahead made no difference either.
+        constexpr int NFRAG = PASS_CHUNK_RT * 2 * NT;
+        const unsigned pc_addr = smem_u32(Pc);
+#ifndef PF_DIST
+#define PF_DIST 1
+#endif
+        double2 pf_q[PF_DIST];        // fragments k .. k + PF_DIST - 1 (a small queue in registers)
+#pragma unroll
+        for (int i = 0; i < PF_DIST; ++i) pf_q[i] = make_double2(0.0, 0.0);
+        if (MODE == PASS_STEP) {
+#pragma unroll
+          for (int i = 0; i < PF_DIST; ++i) pf_q[i] = lds_v2_volatile(pc_addr + i * 512);
+        }
+        auto next_frag = [&](int k) -> double2 {      // returns fragment k, requests fragment k + PF_DIST
+          const double2 r = pf_q[0];
+#pragma unroll
+          for (int i = 0; i + 1 < PF_DIST; ++i) pf_q[i] = pf_q[i + 1];
+          if (k + PF_DIST < NFRAG) pf_q[PF_DIST - 1] = lds_v2_volatile(pc_addr + (k + PF_DIST) * 512);
+          return r;
+        };
 #pragma unroll
         for (int r4 = 0; r4 < PASS_CHUNK_RT; ++r4) {
           const double* P1 = Pc + r4 * TILE_D;        // GEMM1' operand: [j][lane][2]
@@ -1208,7 +1234,7 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
             }
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
-              const double2 bb = *reinterpret_cast<const double2*>(P1 + j * 64);
+              const double2 bb = next_frag(r4 * 2 * NT + j);
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
                 if (MT == 1) {      // a single tile per warp: two chains hide the DMMA latency
@@ -1251,7 +1277,12 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
           // ---- GEMM2': V[c][l] += sum_r u[c][r] P[r][l],  k-slot t of step e <-> row 2t+e
 #pragma unroll
           for (int j = 0; j < NT; ++j) {
-            const double2 bb = *reinterpret_cast<const double2*>(P2 + j * 64);
+            double2 bb;
+            if (MODE == PASS_STEP) {
+              bb = next_frag(r4 * 2 * NT + NT + j);
+            } else {
+              bb = *reinterpret_cast<const double2*>(P2 + j * 64);
+            }
 #pragma unroll
             for (int m = 0; m < MT; ++m) dmma(acc[m][j][0], acc[m][j][1], u[m][0], bb.x);
 #pragma unroll

@@ -101,7 +101,7 @@ def ir_basis_device(beta: float = 100.0, wmax: float = 10.0, eps: float = 1e-7, 
     tau, wtau, omega, womega = problems.ir_quadrature(beta, wmax)
     K = problems._kernel(tau, omega, beta)
     Kw = D.as_dev(np.sqrt(wtau)[:, None] * K * np.sqrt(womega)[None, :])
-    U, s, V = D.svd_jacobi(Kw, max_sweeps=max_sweeps)
+    U, s, V, sweeps = D.svd_jacobi(Kw, max_sweeps=max_sweeps, return_sweeps=True)
     L = int((s / s[0] > eps).sum().item())
     s = s[:L].contiguous()
     dev = Kw.device
@@ -110,4 +110,4 @@ def ir_basis_device(beta: float = 100.0, wmax: float = 10.0, eps: float = 1e-7, 
     j = v_omega.abs().argmax(dim=1)
     sign = torch.sign(v_omega[torch.arange(L, device=dev), j])
     return DeviceIRBasis(beta, wmax, s, tau, wtau, (u_tau * sign[:, None]).contiguous(), omega, womega,
-                         (v_omega * sign[:, None]).contiguous())
+                         (v_omega * sign[:, None]).contiguous(), sweeps)

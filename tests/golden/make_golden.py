@@ -314,8 +314,32 @@ def main_complex():
     save("complex_ops", **out)
 
 
+def main_fuzz():
+    """Seeded random models of tests/golden/fuzz_models.py through the reference's loop.
+    `python tests/golden/make_golden.py fuzz`."""
+    import admmsolver.matrix as RM
+    import admmsolver.objectivefunc as RF
+    import admmsolver.optimizer as RO
+    sys.path.insert(0, HERE)
+    import fuzz_models
+    out = {}
+    for seed in range(fuzz_models.NSEEDS):
+        opt, nterms = fuzz_models.build((RM, RF, RO), seed)
+        opt.solve(fuzz_models.NITER, interval_update_mu=fuzz_models.INTERVAL)
+        for k in range(nterms):
+            out[f"s{seed}_x{k}"] = opt.x[k]
+        out[f"s{seed}_mu"] = np.array([opt._mu[k, 0] for k in range(1, nterms)])
+        out[f"s{seed}_primal"] = np.array(opt._primal_residual)
+        out[f"s{seed}_dual"] = np.array(opt._dual_residual)
+        out[f"s{seed}_objective"] = np.array(opt(opt.x))
+        print(seed, nterms, len(opt._primal_residual), out[f"s{seed}_mu"], float(opt(opt.x)))
+    save("fuzz_models", **out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "psd":
+    if len(sys.argv) > 1 and sys.argv[1] == "fuzz":
+        main_fuzz()
+    elif len(sys.argv) > 1 and sys.argv[1] == "psd":
         main_psd()
     elif len(sys.argv) > 1 and sys.argv[1] == "after":
         main_after()
@@ -326,3 +350,4 @@ if __name__ == "__main__":
         main_psd()
         main_after()
         main_complex()
+        main_fuzz()

@@ -578,3 +578,27 @@ def test_complex_operators_through_the_loop(api):
     # the constraint C x0 = D holds for every problem of the batch
     x0 = opt.x[0].reshape(Lb, nb)
     assert np.abs(g["b_C"] @ x0 - g["b_D"].reshape(2, nb)).max() < 1e-10
+
+
+# ------------------------------------------------------------------ seeded model fuzz of the generic executor
+@pytest.mark.parametrize("seed", range(14))
+def test_generic_executor_model_fuzz_vs_reference(api, seed):
+    """Random models (tests/golden/fuzz_models.py: 2-4 terms of every solvable kind, real / complex, coupled through
+    identity, scaled identity, diagonal, dense rectangular and PartialDiagonalMatrix operators) through
+    SimpleOptimizer.solve against the outputs of the unmodified reference on the same draws (fuzz_models.npz):
+    every x block and the objective to 1e-9, identical penalties and iteration count (one case stops early),
+    residual histories."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import fuzz_models
+    g = golden("fuzz_models")
+    opt, nterms = fuzz_models.build(api, seed)
+    opt.solve(fuzz_models.NITER, interval_update_mu=fuzz_models.INTERVAL)
+    assert len(opt._primal_residual) == len(g[f"s{seed}_primal"])
+    for k in range(nterms):
+        assert rel(opt.x[k], g[f"s{seed}_x{k}"]) < 1e-9, (seed, k)
+    assert [opt._mu[k, 0] for k in range(1, nterms)] == list(g[f"s{seed}_mu"])
+    assert rel(opt._primal_residual, g[f"s{seed}_primal"]) < 1e-8 and rel(opt._dual_residual, g[f"s{seed}_dual"]) < 1e-8
+    ref_obj = float(g[f"s{seed}_objective"])
+    assert abs(opt(opt.x) - ref_obj) <= 1e-9 * abs(ref_obj)

@@ -37,7 +37,7 @@ class CoResidencyError(AdmmError):
 
 class SpmDims(C.Structure):
     _fields_ = [(n, C.c_int) for n in
-                ("L", "Lp", "Nw", "nrt", "nb", "npt", "nplanes", "nsplit", "mt", "nbal", "batch_wide")]
+                ("L", "Lp", "Nw", "nrt", "nb", "npt", "nplanes", "nsplit", "mt", "nbal", "batch_wide", "nc")]
 
 
 _P = C.c_void_p

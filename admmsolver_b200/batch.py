@@ -125,10 +125,23 @@ class SharedSpM:
         Nw, L = P_t.shape
         assert b0.shape[0] == L and G0.shape == (L, L)
         nb = b0.shape[1]
-        D_t = _dev_tensor(np.asarray(D) if not isinstance(D, torch.Tensor) else D, dev).reshape(-1)
+        Cv = _dev_tensor(np.asarray(C_) if not isinstance(C_, torch.Tensor) else C_, dev, _F64)
+        Cv = Cv.reshape(1, -1) if Cv.ndim == 1 else Cv
+        nc = int(Cv.shape[0])
+        assert Cv.shape[1] == L, "C must be (rows, L)"
+        if nc > 4:
+            raise NotImplementedError("the fused SpM engine supports up to 4 constraint rows, got %d" % nc)
+        # D: one value per (constraint row, problem): scalar, (nb,) [one row], (nc,) [same for all problems] or (nc, nb)
+        D_t = _dev_tensor(np.asarray(D) if not isinstance(D, torch.Tensor) else D, dev)
         if D_t.numel() == 1:
-            D_t = D_t.expand(nb)
-        assert D_t.numel() == nb
+            D_t = D_t.reshape(1, 1).expand(nc, nb)
+        elif D_t.numel() == nc * nb:
+            D_t = D_t.reshape(nc, nb)
+        elif D_t.numel() == nc:
+            D_t = D_t.reshape(nc, 1).expand(nc, nb)
+        else:
+            raise AssertionError("D must have one entry per constraint row (and problem)")
+        D_t = D_t.contiguous()
         cplx = bool(b0.is_complex() or D_t.is_complex())
         if force_complex is not None:
             cplx = bool(force_complex) or cplx
@@ -197,7 +210,8 @@ class SharedSpM:
                 nsplit = max(nsplit, int((last - first + 1).max()))
                 self._bal_tables = (torch.from_numpy(bounds.astype(np.int64)).to(dev),
                                     torch.from_numpy(first.astype(np.int32)).to(dev))
-        self.dims = SpmDims(L, Lp, Nw, nrt, nb, npt, nplanes, nsplit, mt, nbal, int(batch_wide))
+        self.dims = SpmDims(L, Lp, Nw, nrt, nb, npt, nplanes, nsplit, mt, nbal, int(batch_wide), nc)
+        self.nc = nc
         self.batch_wide = bool(batch_wide)
         self.lam, self.max_mu = float(lam), float(max_mu)
         nprob = 8 * npt
@@ -217,14 +231,12 @@ class SharedSpM:
         call("admm_spm_pack_operator", dref, ptr(self.PtP), ptr(self.PtPf), stream())
         self.G0 = z(Lp, Lp)
         self.G0[:L, :L] = G0
-        Cv = _dev_tensor(np.asarray(C_) if not isinstance(C_, torch.Tensor) else C_, dev, _F64).reshape(-1)
-        assert Cv.numel() == L, "the fused SpM engine supports a single constraint row (C is 1 x L)"
-        self.Cvec = z(Lp)
-        self.Cvec[:L] = Cv
+        self.Cvec = z(nc, Lp)
+        self.Cvec[:, :L] = Cv
         self._nslots = self.CACHE_SLOTS
         self.Ginv_cache = z(self._nslots, Lp, Lp)
-        self.w_cache = z(self._nslots, Lp)
-        self.sigma_cache = z(self._nslots)
+        self.w_cache = z(self._nslots, nc, Lp)
+        self.sigma_cache = z(self._nslots, nc * nc)
         self._slot_of = {}
         # per problem
         self.slot = torch.zeros(nprob, dtype=torch.int32, device=dev)
@@ -235,10 +247,10 @@ class SharedSpM:
         self.done[nb:] = 1
         self.iters = torch.zeros(nprob, dtype=torch.int32, device=dev)
         self.last_res = z(nprob, 2)
-        self.Dre = z(nplanes, nprob)
-        self.Dre[0, :nb] = D_t.real if D_t.is_complex() else D_t.to(_F64)
+        self.Dre = z(nplanes, nc, nprob)
+        self.Dre[0, :, :nb] = D_t.real if D_t.is_complex() else D_t.to(_F64)
         if cplx and D_t.is_complex():
-            self.Dre[1, :nb] = D_t.imag
+            self.Dre[1, :, :nb] = D_t.imag
         # fragment-layout arrays
         fl = nct * NT * 64
         self.b0 = z(fl)
@@ -356,7 +368,7 @@ class SharedSpM:
         while n < need:
             n *= 2
         Lp = self.dims.Lp
-        for name, shape in (("Ginv_cache", (n, Lp, Lp)), ("w_cache", (n, Lp)), ("sigma_cache", (n,))):
+        for name, shape in (("Ginv_cache", (n, Lp, Lp)), ("w_cache", (n, self.nc, Lp)), ("sigma_cache", (n, self.nc * self.nc))):
             old = getattr(self, name)
             t = torch.zeros(*shape, dtype=_F64, device=self.device)
             t[:old.shape[0]] = old
@@ -746,8 +758,8 @@ class SharedSpM:
         self._flush()
         if self._lazy_ok() and not use_solo:
             # lazy iterations maintain entry 0 of the per-problem bookkeeping only: the batch shares it
-            self.iters[:nb] = self.iters[0]
-            self.last_res[:nb] = self.last_res[0]
+            self.iters[:nb] = self.iters[0].clone()
+            self.last_res[:nb] = self.last_res[0].clone()
             if int(self.lazy[2].item()) != 0:
                 self.done[:nb] = 1
         if track:

@@ -226,19 +226,54 @@ __global__ void __launch_bounds__(256) spm_factor_kernel(admm_spm_dims d, const 
     Gi[bfrag_of(Lp / 8, i, j)] = (i < n && j < n) ? 0.5 * (a[i * n + j] + a[j * n + i]) : 0.0;
   }
   __syncthreads();
-  // w = Ginv C^T (symmetrised Ginv), sigma = C w
-  for (int i = tid; i < n; i += nt) {
-    double acc = 0.0;
-    for (int j = 0; j < n; ++j) acc += 0.5 * (a[i * n + j] + a[j * n + i]) * Cvec[j];
-    wv[i] = acc;
+  // w_k = Ginv c_k (symmetrised Ginv) for every constraint row, Sigma = C W; nc = 1: sigma itself is cached, nc > 1: the
+  // inverse of the nc x nc matrix Sigma (Gauss-Jordan by one thread; Sigma is symmetric positive definite)
+  const int nc = d.nc < 1 ? 1 : d.nc;
+  __shared__ double sig[ADMM_SPM_MAX_NC * ADMM_SPM_MAX_NC];
+  for (int k = 0; k < nc; ++k) {
+    const double* ck = Cvec + (size_t)k * Lp;
+    for (int i = tid; i < n; i += nt) {
+      double acc = 0.0;
+      for (int j = 0; j < n; ++j) acc += 0.5 * (a[i * n + j] + a[j * n + i]) * ck[j];
+      wv[i] = acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < Lp; i += nt) w_cache[((size_t)slot * nc + k) * Lp + i] = i < n ? wv[i] : 0.0;
+    for (int m = 0; m < nc; ++m) {
+      const double* cm = Cvec + (size_t)m * Lp;
+      double v[1] = {0.0};
+      for (int i = tid; i < n; i += nt) v[0] += cm[i] * wv[i];
+      block_sum<1>(v, red);
+      if (tid == 0) sig[m * nc + k] = v[0];
+      __syncthreads();
+    }
   }
-  __syncthreads();
-  for (int i = tid; i < Lp; i += nt) w_cache[(size_t)slot * Lp + i] = i < n ? wv[i] : 0.0;
-  double v[1] = {0.0};
-  for (int i = tid; i < n; i += nt) v[0] += Cvec[i] * wv[i];
-  block_sum<1>(v, red);
   if (tid == 0) {
-    sigma_cache[slot] = v[0];
+    if (nc == 1) {
+      sigma_cache[slot] = sig[0];
+    } else {
+      double inv[ADMM_SPM_MAX_NC * ADMM_SPM_MAX_NC];
+      for (int i = 0; i < nc; ++i)
+        for (int j = 0; j < nc; ++j) inv[i * nc + j] = i == j ? 1.0 : 0.0;
+      for (int k = 0; k < nc; ++k) {
+        const double pv = sig[k * nc + k];
+        if (!(pv > 0.0) && bad == 0) bad = n + k + 1;
+        const double ip = 1.0 / pv;
+        for (int j = 0; j < nc; ++j) {
+          sig[k * nc + j] *= ip;
+          inv[k * nc + j] *= ip;
+        }
+        for (int i = 0; i < nc; ++i) {
+          if (i == k) continue;
+          const double f = sig[i * nc + k];
+          for (int j = 0; j < nc; ++j) {
+            sig[i * nc + j] -= f * sig[k * nc + j];
+            inv[i * nc + j] -= f * inv[k * nc + j];
+          }
+        }
+      }
+      for (int i = 0; i < nc * nc; ++i) sigma_cache[(size_t)slot * nc * nc + i] = inv[i];
+    }
     if (info) info[blockIdx.x] = bad;
   }
 }
@@ -639,7 +674,42 @@ __device__ __forceinline__ bool xupdate_tile(const admm_spm_dims& d, const admm_
 
   XSTAMP(3)
   // ---- KKT correction enforcing C x0 = D   (objectivefunc.py:148-157)
-  {
+  if (d.nc > 1) {
+    // several constraint rows: nu = (C G^-1 C^T)^-1 (D - C xi1), x0 = xi1 + sum_k w_k nu_k   (operands from L1/L2)
+    const int nc = d.nc;
+    const double* Sinv = b.sigma_cache + (size_t)slot * nc * nc;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      double resid[ADMM_SPM_MAX_NC];
+#pragma unroll
+      for (int k = 0; k < ADMM_SPM_MAX_NC; ++k) {
+        resid[k] = 0.0;
+        if (k < nc) {
+          const double* ck = b.Cvec + (size_t)k * Lp;
+          double cxi = 0.0;
+#pragma unroll
+          for (int j = 0; j < NT; ++j) cxi += ck[8 * j + 2 * t] * x0[p][j][0] + ck[8 * j + 2 * t + 1] * x0[p][j][1];
+          cxi = quad_sum(cxi);
+          resid[k] = b.Dre[((size_t)(p0 + p) * nc + k) * 8 * d.npt + prob] - cxi;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < ADMM_SPM_MAX_NC; ++k) {
+        if (k < nc) {
+          double nu = 0.0;
+#pragma unroll
+          for (int m = 0; m < ADMM_SPM_MAX_NC; ++m)
+            if (m < nc) nu += Sinv[k * nc + m] * resid[m];
+          const double* wk = b.w_cache + ((size_t)slot * nc + k) * Lp;
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            x0[p][j][0] += wk[8 * j + 2 * t] * nu;
+            x0[p][j][1] += wk[8 * j + 2 * t + 1] * nu;
+          }
+        }
+      }
+    }
+  } else {
     const double* wv = b.w_cache + (size_t)slot * Lp;
     const double isig = 1.0 / (PRE ? sig_pre : b.sigma_cache[slot]);
 #pragma unroll
@@ -2410,6 +2480,8 @@ static int check_dims(const admm_spm_dims* d, const char* who) {
                "%s: nrt=%d must be a multiple of %d covering Nw=%d", who, d->nrt, PASS_CHUNK_RT, d->Nw);
   ADMM_REQUIRE(d->nb >= 1 && d->npt * 8 >= d->nb, ADMM_EINVAL, "%s: bad nb/npt", who);
   ADMM_REQUIRE(d->nplanes == 1 || d->nplanes == 2, ADMM_EINVAL, "%s: nplanes must be 1 or 2", who);
+  ADMM_REQUIRE(d->nc >= 0 && d->nc <= ADMM_SPM_MAX_NC, ADMM_EUNSUPPORTED, "%s: %d constraint rows (at most %d)", who, d->nc,
+               ADMM_SPM_MAX_NC);
   ADMM_REQUIRE(d->mt == 1 || (d->mt == 2 && d->Lp <= 40), ADMM_EINVAL, "%s: mt must be 1, or 2 with Lp <= 40", who);
   ADMM_REQUIRE(d->nsplit >= 1 && (d->nbal > 0 || d->nsplit <= d->nrt / PASS_CHUNK_RT), ADMM_EINVAL, "%s: bad nsplit=%d", who,
                d->nsplit);
@@ -2865,6 +2937,7 @@ int admm_spm_launch_mode(int which) {
 int admm_spm_solo_supported(const admm_spm_dims* d) {
   if (d == nullptr || d->L < 1 || (d->Lp != 16 && d->Lp != 40 && d->Lp != 64) || d->nb < 1) return 0;
   if (solo_smem_bytes(d, 8) > 216 * 1024) return 0;
+  if (d->nc > 1) return 0;      // several constraint rows: the batch kernels (the cluster-resident solve folds w into its operators)
   if (d->batch_wide && d->nb > 1) {
     // the batch-wide criterion synchronises the clusters every iteration: all of them have to be co-resident
     int n = 0;

@@ -174,7 +174,7 @@ class _SpMPlan:
         G0 = D.axpby(float(cls._alpha), G0)
         b0 = cls._Aty.reshape(L, nb)
         P = unwrap(model.E[2, 0])._dense_dev()
-        Cm = unwrap(cls._C)._dense_dev().reshape(-1)
+        Cm = unwrap(cls._C)._dense_dev()                                  # (constraint rows, L): up to four rows
         self.nb, self.L, self.Nw = nb, L, P.shape[0]
         self.eng = SharedSpM.from_operators(G0, b0, P, Cm, cls._D_dev, lam=float(l1._alpha), mu10=mu10, mu20=mu20,
                                             batch_wide=True, max_mu=max_mu, force_complex=True, keep_x_old=True)
@@ -208,7 +208,7 @@ class _SpMPlan:
             if _real_dense(m) is None:
                 return None
         L = A.shape[1]
-        if L > 64 or Cm.shape[0] != 1 or cls._D_dev.numel() != nb:
+        if L > 64 or not (1 <= Cm.shape[0] <= 4) or cls._D_dev.numel() != Cm.shape[0] * nb:
             return None
         return {"nb": nb, "packed": packed}
 

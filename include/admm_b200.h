@@ -158,7 +158,11 @@ typedef struct admm_spm_dims {
                    equal contiguous pieces, one CTA each (one wave that loads every SM equally)   */
   int batch_wide; /* 1: mu and the stopping test use norms over the whole batch (packed
                      reference semantics), 0: per-problem mu / stopping                        */
+  int nc;       /* rows of the constraint C x0 = D (1 .. ADMM_SPM_MAX_NC; 0 is read as 1).  Cvec is [nc][Lp],
+                   w_cache [slot][nc][Lp], Dre [plane][nc][8 npt]; sigma_cache [slot][nc*nc] holds sigma = C w for
+                   nc = 1 and the INVERSE of C G^-1 C^T for nc > 1 (objectivefunc.py:148-157)     */
 } admm_spm_dims;
+#define ADMM_SPM_MAX_NC 4
 
 /* P (Nw x L, row-major, ld = ldP) -> Pf[nrt][2][Lp/8][32][2], zero padded, fragment-major: per
  * 8-row tile first the B operand of Q = P x0 (element (lane=4g+t, e) of slice j = P[8rt+g][8j+2t+e]),

@@ -189,8 +189,15 @@ def spm_solve(s: np.ndarray, P: np.ndarray, C: np.ndarray, D: np.ndarray, g: np.
     single = g.ndim == 1
     G_ = (g[:, None] if single else g).astype(complex)
     nb = G_.shape[1]
-    Dv = np.broadcast_to(np.asarray(D, dtype=float).ravel(), (nb,)) if np.size(D) in (1, nb) else None
-    assert Dv is not None and C.shape == (1, L)
+    nc = C.shape[0]
+    assert C.shape == (nc, L)
+    if nc == 1:
+        Dv = np.broadcast_to(np.asarray(D, dtype=float).ravel(), (nb,)) if np.size(D) in (1, nb) else None
+        assert Dv is not None
+    else:
+        # several constraint rows (objectivefunc.py:148-157 in general form): D is (nc,) or (nc, nb)
+        Dv = np.asarray(D, dtype=float)
+        Dv = np.broadcast_to(Dv.reshape(nc, -1), (nc, nb))
     c = C[0]
     PtP = P.T @ P
     b0 = -alpha * s[:, None] * G_                       # alpha * A^H y with A = -diag(s)
@@ -213,10 +220,16 @@ def spm_solve(s: np.ndarray, P: np.ndarray, C: np.ndarray, D: np.ndarray, g: np.
             fac = cho_factor(Gm)
             w = cho_solve(fac, c.conj())
             sigma = c @ w
+            if nc > 1:
+                W = cho_solve(fac, C.conj().T)              # (L, nc)
+                Sinv = np.linalg.inv(C @ W)
             key = (st.mu10, st.mu20)
         rhs = b0 + st.h10 + st.mu10 * st.x1 + P.T @ (st.h20 + st.mu20 * st.x2)
         xi1 = cho_solve(fac, rhs)
-        st.x0 = xi1 + w[:, None] * ((Dv - c @ xi1) / sigma)[None, :]
+        if nc == 1:
+            st.x0 = xi1 + w[:, None] * ((Dv - c @ xi1) / sigma)[None, :]
+        else:
+            st.x0 = xi1 + W @ (Sinv @ (Dv - C @ xi1))
         t1 = st.x0.real - st.h10.real / st.mu10
         st.x1 = np.where(t1 > 0.5 * lam / st.mu10, t1 - 0.5 * lam / st.mu10,
                          np.where(t1 < -0.5 * lam / st.mu10, t1 + 0.5 * lam / st.mu10, 0.0)

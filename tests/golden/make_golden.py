@@ -314,6 +314,42 @@ def main_complex():
     save("complex_ops", **out)
 
 
+def main_multirow():
+    """SpM with SEVERAL constraint rows (sum rule + first and second moment of the spectrum; objectivefunc.py:148-157
+    with a 3 x L resp. 2 x L matrix C): single problem and packed batch.  `python tests/golden/make_golden.py multirow`."""
+    basis = problems.ir_basis()
+    out = {}
+    # single problem, three rows
+    p = problems.spm_single(basis, Nw=192)
+    L, Nw = p.s.size, p.P.shape[0]
+    wq = basis.womega
+    C3 = np.stack([basis.v_omega @ wq, basis.v_omega @ (wq * basis.omega), basis.v_omega @ (wq * basis.omega ** 2)])
+    D3 = C3 @ p.rho_l
+    lstsq = ConstrainedLeastSquares(1.0, -DiagonalMatrix(p.s), p.g, C3, D3)
+    opt = SimpleOptimizer(Model([lstsq, L1Regularizer(p.lam, L), NonNegativePenalty(Nw)],
+                                [(0, 1, identity(L), identity(L)), (0, 2, p.P, identity(Nw))]), mu=p.mu)
+    opt.solve(300, interval_update_mu=50)
+    out.update(a_s=p.s, a_P=p.P, a_g=p.g, a_C=C3, a_D=D3, a_lam=p.lam, a_mu=p.mu, a_x0=opt.x[0], a_x1=opt.x[1], a_x2=opt.x[2],
+               a_h20=opt._h[2, 0], a_mu10=opt._mu[1, 0], a_mu20=opt._mu[2, 0], a_primal=np.array(opt._primal_residual),
+               a_dual=np.array(opt._dual_residual), a_objective=opt(opt.x))
+    # packed batch of 6 complex spectra, two rows, D per problem
+    nb = 6
+    pb = problems.spm_batch(nb, basis, Nw=192, seed=3)
+    C2 = C3[:2]
+    D2 = (C2 @ pb.rho_l)                                                 # (2, nb), batch fastest when flattened
+    rest = (nb,)
+    lstsq = ConstrainedLeastSquares(1.0, PartialDiagonalMatrix(-DiagonalMatrix(pb.s), rest), pb.g.ravel(),
+                                    PartialDiagonalMatrix(C2, rest), D2.ravel())
+    opt = SimpleOptimizer(Model([lstsq, L1Regularizer(pb.lam, L * nb), NonNegativePenalty(Nw * nb)],
+                                [(0, 1, identity(L * nb), identity(L * nb)),
+                                 (0, 2, PartialDiagonalMatrix(pb.P, rest), identity(Nw * nb))]), mu=pb.mu)
+    opt.solve(250, interval_update_mu=50)
+    out.update(b_g=pb.g, b_C=C2, b_D=D2, b_x0=opt.x[0], b_x1=opt.x[1], b_x2=opt.x[2], b_mu10=opt._mu[1, 0], b_mu20=opt._mu[2, 0],
+               b_primal=np.array(opt._primal_residual), b_dual=np.array(opt._dual_residual), b_objective=opt(opt.x))
+    print("multirow:", out["a_mu10"], out["a_mu20"], out["b_mu10"], out["b_mu20"], len(out["a_primal"]), len(out["b_primal"]))
+    save("spm_multirow", **out)
+
+
 def main_fuzz():
     """Seeded random models of tests/golden/fuzz_models.py through the reference's loop.
     `python tests/golden/make_golden.py fuzz`."""
@@ -339,6 +375,8 @@ def main_fuzz():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "fuzz":
         main_fuzz()
+    elif len(sys.argv) > 1 and sys.argv[1] == "multirow":
+        main_multirow()
     elif len(sys.argv) > 1 and sys.argv[1] == "psd":
         main_psd()
     elif len(sys.argv) > 1 and sys.argv[1] == "after":
@@ -351,3 +389,4 @@ if __name__ == "__main__":
         main_after()
         main_complex()
         main_fuzz()
+        main_multirow()

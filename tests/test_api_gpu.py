@@ -602,3 +602,34 @@ def test_generic_executor_model_fuzz_vs_reference(api, seed):
     assert rel(opt._primal_residual, g[f"s{seed}_primal"]) < 1e-8 and rel(opt._dual_residual, g[f"s{seed}_dual"]) < 1e-8
     ref_obj = float(g[f"s{seed}_objective"])
     assert abs(opt(opt.x) - ref_obj) <= 1e-9 * abs(ref_obj)
+
+
+def test_spm_several_constraint_rows_dropin(api):
+    """The drop-in API with a constraint MATRIX (three rows; packed: two rows): recognised as the SpM pattern and run
+    on the fused engine (not the generic executor), equal to the reference (spm_multirow.npz)."""
+    M, F, O = api
+    g = golden("spm_multirow")
+    L, Nw = g["a_s"].size, g["a_P"].shape[0]
+    lam, mu = float(g["a_lam"]), float(g["a_mu"])
+    lstsq = F.ConstrainedLeastSquares(1.0, -M.DiagonalMatrix(g["a_s"]), g["a_g"], g["a_C"], g["a_D"])
+    opt = O.SimpleOptimizer(O.Model([lstsq, F.L1Regularizer(lam, L), F.NonNegativePenalty(Nw)],
+                                    [(0, 1, M.identity(L), M.identity(L)), (0, 2, g["a_P"], M.identity(Nw))]), mu=mu)
+    assert opt._plan_kind == "spm"
+    opt.solve(300, interval_update_mu=50)
+    for k in range(3):
+        assert rel(opt.x[k], g[f"a_x{k}"]) < TOL
+    assert opt._mu[1, 0] == float(g["a_mu10"]) and opt._mu[2, 0] == float(g["a_mu20"])
+    assert abs(opt(opt.x) - float(g["a_objective"])) <= TOL * abs(float(g["a_objective"]))
+    nb = 6
+    rest = (nb,)
+    lstsq = F.ConstrainedLeastSquares(1.0, M.PartialDiagonalMatrix(-M.DiagonalMatrix(g["a_s"]), rest), g["b_g"].ravel(),
+                                      M.PartialDiagonalMatrix(g["b_C"], rest), g["b_D"].ravel())
+    opt = O.SimpleOptimizer(O.Model([lstsq, F.L1Regularizer(lam, L * nb), F.NonNegativePenalty(Nw * nb)],
+                                    [(0, 1, M.identity(L * nb), M.identity(L * nb)),
+                                     (0, 2, M.PartialDiagonalMatrix(g["a_P"], rest), M.identity(Nw * nb))]), mu=mu)
+    assert opt._plan_kind == "spm"
+    opt.solve(250, interval_update_mu=50)
+    for k in range(3):
+        assert rel(opt.x[k], g[f"b_x{k}"]) < TOL
+    assert opt._mu[1, 0] == float(g["b_mu10"]) and opt._mu[2, 0] == float(g["b_mu20"])
+    assert len(opt._primal_residual) == 250 and rel(opt._primal_residual, g["b_primal"]) < 1e-8

@@ -609,3 +609,35 @@ def test_spm_coresidency_guarantee_and_recovery(eng, ir_basis, path):
     assert rel(e2.x0(), st.x0) < TOL and rel(e2.x2(), st.x2) < TOL and float(e2.mu20[0]) == st.mu20
     assert len(e2.primal_residual) == st.niter_done == 130
     assert rel(e2.primal_residual, st.primal) < 1e-8
+
+
+# ------------------------------------------------------------------ several constraint rows
+@pytest.mark.parametrize("kw", [dict(), dict(mt=2, nsplit=1), dict(mt=1, nsplit=2), dict(mt=1, nbal=7)])
+def test_spm_several_constraint_rows(eng, kw):
+    """C x0 = D with up to four rows (sum rule + moments; objectivefunc.py:148-157 with a matrix C) in the fused SpM
+    engine: the cached factor then carries W = G^-1 C^T and the inverse of C G^-1 C^T per (mu10, mu20).  Against the
+    reference (spm_multirow.npz): single problem with three rows, packed batch of six with two rows and per-problem
+    right-hand sides -- every launch configuration of the batch kernels (the cluster-resident solve declines them)."""
+    from oracle import flat
+    batch, problems = eng
+    g = golden("spm_multirow")
+    lam, mu = float(g["a_lam"]), float(g["a_mu"])
+    e = batch.SharedSpM(g["a_s"], g["a_P"], g["a_C"], g["a_D"], g["a_g"], lam=lam, mu=mu, batch_wide=True, **kw)
+    assert e.dims.nc == 3
+    e.solve(300, interval_update_mu=50)
+    assert rel(e.x0()[:, 0], g["a_x0"]) < TOL and rel(e.x2()[:, 0], g["a_x2"]) < TOL and rel(e.h20()[:, 0], g["a_h20"]) < 1e-8
+    assert float(e.mu10[0]) == float(g["a_mu10"]) and float(e.mu20[0]) == float(g["a_mu20"])
+    assert rel(e.primal_residual, g["a_primal"]) < 1e-8
+    assert np.abs(g["a_C"] @ e.x0()[:, 0] - g["a_D"]).max() < 1e-11
+    e = batch.SharedSpM(g["a_s"], g["a_P"], g["b_C"], g["b_D"], g["b_g"], lam=lam, mu=mu, batch_wide=True, **kw)
+    e.solve(250, interval_update_mu=50)
+    assert rel(e.x0().ravel(), g["b_x0"]) < TOL and rel(e.x2().ravel(), g["b_x2"]) < TOL
+    assert float(e.mu10[0]) == float(g["b_mu10"]) and float(e.mu20[0]) == float(g["b_mu20"])
+    assert rel(e.primal_residual, g["b_primal"]) < 1e-8 and rel(e.dual_residual, g["b_dual"]) < 1e-8
+    # per-problem criterion: every column is its own instance with its own right-hand sides (oracle)
+    e = batch.SharedSpM(g["a_s"], g["a_P"], g["b_C"], g["b_D"], g["b_g"], lam=lam, mu=mu, batch_wide=False, **kw)
+    e.solve(120, interval_update_mu=30)
+    x0 = e.x0()
+    for b in (0, 3, 5):
+        sb = flat.spm_solve(g["a_s"], g["a_P"], g["b_C"], g["b_D"][:, b], g["b_g"][:, b], lam, 120, mu=mu, interval_update_mu=30)
+        assert rel(x0[:, b], sb.x0) < TOL and float(e.mu20[b]) == sb.mu20

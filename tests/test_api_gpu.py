@@ -633,3 +633,22 @@ def test_spm_several_constraint_rows_dropin(api):
         assert rel(opt.x[k], g[f"b_x{k}"]) < TOL
     assert opt._mu[1, 0] == float(g["b_mu10"]) and opt._mu[2, 0] == float(g["b_mu20"])
     assert len(opt._primal_residual) == 250 and rel(opt._primal_residual, g["b_primal"]) < 1e-8
+
+
+@pytest.mark.parametrize("moments", [False, True])
+def test_spm_batch_pipeline_example(build_lib, moments):
+    """examples/spm_batch.py: the whole analytic-continuation batch on the device -- basis by Jacobi SVD, G(tau) -> g_l,
+    fused engine with per-problem criterion (one or two constraint rows), reconstruction -- recovers the model spectra,
+    keeps them non-negative and satisfies the constraints to rounding."""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("spm_batch", os.path.join(ROOT, "examples", "spm_batch.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    r = mod.main(nb=40, niter=1500, nw=400, moments=moments, verbose=False)
+    assert r["L"] == 39
+    assert r["constraint_violation"] < 1e-9
+    assert r["min_rho"] > -1e-2
+    assert r["data_misfit"] < 3e-2                                  # the Green's functions are reproduced (L1 weight 1e-5, 1500 iterations)
+    assert r["median_rel_err"] < 0.3 and r["max_rel_err"] < 0.9     # (analytic continuation is ill-posed: sharp peaks are smoothed)

@@ -797,7 +797,8 @@ def run_ours(args):
     also = {}
     if not args.no_also and args.workload == "spm_sweep" and args.nb is None:
         # the other batched BASELINE workloads, measured the same way in the same run (shorter: 3 warm-up, <= 3 steps)
-        for wl in (["bp_cfg4"] + (["spm_cfg3"] if world == 1 else [])):
+        # (the single-GPU configurations of BASELINE.json -- cfg3 and the two single-problem cases cfg1, cfg2 -- at N = 1 only)
+        for wl in (["bp_cfg4"] + (["spm_cfg3", "bp_cfg1", "spm_cfg2"] if world == 1 else [])):
             part = run_workload(args, wl, ctx, min(args.steps, 3), 3, with_clocks=False)
             if part is not None:
                 also[wl] = part

@@ -585,7 +585,7 @@ def run_workload(args, workload, ctx, steps, warmup, with_clocks):
             reset_state()
             eng.solve(niter)
             x_all = eng._x0
-            idx = sorted({0, 1, gen_nb - 1})
+            idx = sorted({0, min(1, gen_nb - 1), gen_nb - 1})
             err, mu_eq, it_eq, checker = 0.0, True, True, "reference"
             for b in idx:
                 xr, mur, nr, checker = reference_bp(A_s[b], y_s[b], niter)

@@ -23,7 +23,7 @@ import torch
 from . import _lib
 from ._lib import BpBuffers, SpmBuffers, SpmDims, call, ptr, stream
 
-__all__ = ["SharedSpM", "BatchedBasisPursuit"]
+__all__ = ["SharedSpM", "BatchedBasisPursuit", "SpMHostStream"]
 
 _F64 = torch.float64
 _C128 = torch.complex128
@@ -833,6 +833,71 @@ class SharedSpM:
         call("admm_sumsq", n, ptr(self._g), ptr(msx), ptr(out), ptr(scratch), stream())
         l1 = float(np.abs(self.x1()).sum())
         return float(self._alpha * out.item() + self.lam * l1)
+
+
+class SpMHostStream:
+    """Batches from pinned host memory through one ``SharedSpM`` plan and back, with the copies OVERLAPPED with the
+    solves: data ``g`` of batch k + 1 is uploaded (own stream, second staging buffer) while batch k iterates, the result
+    ``x0`` of batch k is downloaded (own stream) while batch k + 1 iterates.  The pattern of a production sweep over many
+    batches that share one basis; ``bench.py`` measures its end-to-end leg through it.
+
+        pipe = SpMHostStream(eng)
+        for k, g in enumerate(batches):                       # pinned (L, nb) arrays
+            pipe.submit(g, out[k], niter, next_g_host=batches[k + 1] if k + 1 < len(batches) else None)
+        pipe.join()                                           # the current stream now waits for all copies
+    """
+
+    def __init__(self, eng: "SharedSpM"):
+        if eng._s is None:
+            raise NotImplementedError("SpMHostStream needs a plan built from the SpM form (s, g)")
+        self.eng = eng
+        dt = _C128 if eng.is_complex else _F64
+        self._g = [torch.empty(eng.L, eng.nb, dtype=dt, device=eng.device) for _ in range(2)]
+        self._up, self._down = torch.cuda.Stream(), torch.cuda.Stream()
+        self._ev_up = [torch.cuda.Event(), torch.cuda.Event()]
+        self._ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+        self._k = 0
+        self._prefetched = False
+
+    def _upload(self, i: int, g_host: torch.Tensor) -> None:
+        self._up.wait_event(self._ev_free[i])                 # the plan has taken the previous content of this buffer
+        with torch.cuda.stream(self._up):
+            self._g[i].copy_(g_host, non_blocking=True)
+            self._ev_up[i].record(self._up)
+
+    def submit(self, g_host: torch.Tensor, out_host: torch.Tensor, niter: int, mu: float = 0.1,
+               next_g_host: Optional[torch.Tensor] = None, **solve_kw) -> int:
+        """Solve one batch (``reset`` to the zero state with data ``g_host``, ``niter`` iterations), write x0 (L, nb,
+        complex128) to ``out_host``.  Returns what ``SharedSpM.solve`` returns."""
+        eng, cur = self.eng, torch.cuda.current_stream()
+        i = self._k & 1
+        if not self._prefetched:
+            self._ev_free[i].record(cur)
+            self._upload(i, g_host)
+        cur.wait_event(self._ev_up[i])
+        eng.reset(g=self._g[i], mu=mu)                        # packs g into the plan's fragment layout
+        self._ev_free[i].record(cur)
+        self._prefetched = next_g_host is not None
+        if self._prefetched:
+            if self._k == 0:
+                self._ev_free[1 - i].record(cur)
+            self._upload(1 - i, next_g_host)
+        ran = eng.solve(niter, **solve_kw)
+        x = eng.x0_device()
+        done = torch.cuda.Event()
+        done.record(cur)
+        self._down.wait_event(done)
+        with torch.cuda.stream(self._down):
+            out_host.copy_(x, non_blocking=True)
+        x.record_stream(self._down)
+        self._k += 1
+        return ran
+
+    def join(self) -> None:
+        """Make the current stream wait for every copy issued so far."""
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(self._up)
+        cur.wait_stream(self._down)
 
 
 class BatchedBasisPursuit:

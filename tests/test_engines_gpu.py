@@ -641,3 +641,33 @@ def test_spm_several_constraint_rows(eng, kw):
     for b in (0, 3, 5):
         sb = flat.spm_solve(g["a_s"], g["a_P"], g["b_C"], g["b_D"][:, b], g["b_g"][:, b], lam, 120, mu=mu, interval_update_mu=30)
         assert rel(x0[:, b], sb.x0) < TOL and float(e.mu20[b]) == sb.mu20
+
+
+def test_spm_host_stream_overlapped_copies(eng, ir_basis):
+    """batch.SpMHostStream: batches from pinned host memory through one plan and back with the copies overlapped with
+    the solves (double-buffered staging, upload of batch k + 1 and download of batch k - 1 on their own streams) give
+    exactly the results of separate solves."""
+    batch, problems = eng
+    nb = 300
+    ps = [problems.spm_batch(nb, ir_basis, Nw=264, seed=40 + k) for k in range(4)]
+    p = ps[0]
+    e = batch.SharedSpM(p.s, p.P, p.C, p.D, p.g, lam=p.lam, mu=p.mu, batch_wide=False)
+    ref = []
+    for q in ps:
+        e.reset(g=q.g, mu=q.mu)
+        e.solve(80)
+        ref.append(e.x0())
+    pipe = batch.SpMHostStream(e)
+    gh = [torch.from_numpy(q.g.copy()).pin_memory() for q in ps]
+    out = [torch.empty(p.s.size, nb, dtype=torch.complex128).pin_memory() for _ in ps]
+    for k in range(4):
+        assert pipe.submit(gh[k], out[k], 80, mu=p.mu, next_g_host=gh[k + 1] if k + 1 < 4 else None) == 80
+    pipe.join()
+    torch.cuda.synchronize()
+    for k in range(4):
+        assert np.array_equal(out[k].numpy(), ref[k]), k
+    # without announcing the next batch (no prefetch) and reusing the pipe
+    assert pipe.submit(gh[2], out[0], 80, mu=p.mu) == 80
+    pipe.join()
+    torch.cuda.synchronize()
+    assert np.array_equal(out[0].numpy(), ref[2])

@@ -228,6 +228,18 @@ def main_psd():
     out.update(loop_A=Am, loop_y=ym, loop_x0=opt.x[0], loop_x1=opt.x[1], loop_h10=opt._h[1, 0], loop_mu10=opt._mu[1, 0],
                loop_primal=np.array(opt._primal_residual), loop_dual=np.array(opt._dual_residual),
                loop_objective=opt(opt.x))
+    # the same through the loop with a slice larger than a warp (36 x 36: the CTA-wide Jacobi of admm_prox_psd);
+    # inputs are regenerated from the seed by the test, only the outputs are stored
+    rs36 = np.random.RandomState(36)
+    n36 = 36
+    nx = n36 * n36
+    A36 = rs36.randn(nx + 200, nx) / np.sqrt(nx)
+    y36 = rs36.randn(nx + 200)
+    opt = SimpleOptimizer(Model([LeastSquares(1.0, A36, y36), SemiPositiveDefinitePenalty((n36, n36, 1), axis=2)],
+                                [(0, 1, identity(nx), identity(nx))]), mu=0.5)
+    opt.solve(60, interval_update_mu=20)
+    out.update(loop36_x0=opt.x[0], loop36_x1=opt.x[1], loop36_mu10=opt._mu[1, 0], loop36_primal=np.array(opt._primal_residual),
+               loop36_objective=opt(opt.x))
     save("psd", **out)
 
 

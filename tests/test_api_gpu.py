@@ -652,3 +652,26 @@ def test_spm_batch_pipeline_example(build_lib, moments):
     assert r["min_rho"] > -1e-2
     assert r["data_misfit"] < 3e-2                                  # the Green's functions are reproduced (L1 weight 1e-5, 1500 iterations)
     assert r["median_rel_err"] < 0.3 and r["max_rel_err"] < 0.9     # (analytic continuation is ill-posed: sharp peaks are smoothed)
+
+
+def test_semi_positive_definite_model_large_slice_golden(build_lib):
+    """Matrix-valued least squares with a PSD constraint on ONE 36 x 36 slice (1296 unknowns) through
+    SimpleOptimizer.solve: the generic executor with the CTA-wide Jacobi projection inside the loop (graph-captured
+    iterations), the cached factor of the 1296 x 1296 least-squares term -- against the reference (psd.npz, loop36_*)."""
+    from admmsolver_b200.matrix import identity
+    from admmsolver_b200.objectivefunc import LeastSquares, SemiPositiveDefinitePenalty
+    from admmsolver_b200.optimizer import Model, SimpleOptimizer
+    g = golden("psd")
+    rs36 = np.random.RandomState(36)
+    n36 = 36
+    nx = n36 * n36
+    A36 = rs36.randn(nx + 200, nx) / np.sqrt(nx)
+    y36 = rs36.randn(nx + 200)
+    opt = SimpleOptimizer(Model([LeastSquares(1.0, A36, y36), SemiPositiveDefinitePenalty((n36, n36, 1), axis=2)],
+                                [(0, 1, identity(nx), identity(nx))]), mu=0.5)
+    opt.solve(60, interval_update_mu=20)
+    assert rel(opt.x[0], g["loop36_x0"]) < 1e-9 and rel(opt.x[1], g["loop36_x1"]) < 1e-9
+    assert float(opt._mu[1, 0]) == float(g["loop36_mu10"])
+    assert rel(opt._primal_residual, g["loop36_primal"]) < 1e-8
+    assert abs(opt(opt.x) - g["loop36_objective"]) / abs(g["loop36_objective"]) < 1e-9
+    assert np.linalg.eigvalsh(opt.x[1].real.reshape(n36, n36)).min() > -1e-10

@@ -21,7 +21,7 @@ if not os.path.exists(LIB_PATH):
 
 lib = C.CDLL(LIB_PATH)
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 OP_N, OP_T, OP_H = 0, 1, 2
 
 
@@ -37,7 +37,7 @@ class CoResidencyError(AdmmError):
 
 class SpmDims(C.Structure):
     _fields_ = [(n, C.c_int) for n in
-                ("L", "Lp", "Nw", "nrt", "nb", "npt", "nplanes", "nsplit", "mt", "nbal", "batch_wide", "nc")]
+                ("L", "Lp", "Nw", "nrt", "nb", "npt", "nplanes", "nsplit", "mt", "nbal", "batch_wide", "nc", "fold")]
 
 
 _P = C.c_void_p

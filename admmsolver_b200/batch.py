@@ -64,7 +64,8 @@ class SharedSpM:
     def __init__(self, s, P, C_, D, g, lam: float, mu: float = 0.1, alpha: float = 1.0,
                  batch_wide: bool = False, max_mu: float = 1e3, nsplit: Optional[int] = None,
                  group=None, force_complex: Optional[bool] = None, mt: Optional[int] = None, nbal: Optional[int] = None,
-                 collective: Optional[str] = None, keep_x_old: bool = False, bal_skew: Optional[float] = None):
+                 collective: Optional[str] = None, keep_x_old: bool = False, bal_skew: Optional[float] = None,
+                 fold: Optional[bool] = None):
         dev = _lib.require_cuda()
         s_t = _dev_tensor(s, dev, _F64)
         g_t = _dev_tensor(g, dev)
@@ -80,7 +81,7 @@ class SharedSpM:
         sd = (-alpha * s_t).to(gv.dtype)
         call("admm_diag_mul", int(cplx), L, L, nb, ptr(sd), ptr(gv), nb, ptr(b0), nb, stream())
         self._init_common(G0, b0, P, C_, D, lam, mu, mu, batch_wide, max_mu, nsplit, group, force_complex, mt, nbal,
-                          collective, keep_x_old, bal_skew)
+                          collective, keep_x_old, bal_skew, fold)
         self._s = s_t
         self._g = gv
         self._alpha = alpha
@@ -89,14 +90,15 @@ class SharedSpM:
     def from_operators(cls, G0, b0, P, C_, D, lam: float, mu10: float, mu20: float,
                        batch_wide: bool = True, max_mu: float = 1e3, nsplit: Optional[int] = None,
                        group=None, force_complex: Optional[bool] = None, mt: Optional[int] = None,
-                       collective: Optional[str] = None, keep_x_old: bool = False) -> "SharedSpM":
+                       collective: Optional[str] = None, keep_x_old: bool = False,
+                       fold: Optional[bool] = None) -> "SharedSpM":
         self = cls.__new__(cls)
         dev = _lib.require_cuda()
         b0_t = _dev_tensor(b0, dev)
         if b0_t.ndim == 1:
             b0_t = b0_t[:, None].contiguous()
         self._init_common(_dev_tensor(G0, dev, _F64), b0_t, P, C_, D, lam, mu10, mu20, batch_wide, max_mu,
-                          nsplit, group, force_complex, mt, None, collective, keep_x_old)
+                          nsplit, group, force_complex, mt, None, collective, keep_x_old, None, fold)
         self._s = None
         self._g = None
         self._alpha = None
@@ -104,7 +106,7 @@ class SharedSpM:
 
     # ------------------------------------------------------------------ setup
     def _init_common(self, G0, b0, P, C_, D, lam, mu10, mu20, batch_wide, max_mu, nsplit, group, force_complex,
-                     mt=None, nbal_req=None, collective=None, keep_x_old=False, bal_skew=None):
+                     mt=None, nbal_req=None, collective=None, keep_x_old=False, bal_skew=None, fold=None):
         dev = _lib.require_cuda()
         self.device = dev
         self.group = group
@@ -149,6 +151,19 @@ class SharedSpM:
         self.is_complex = cplx
         Lp = _pad_L(L)
         nrt = ((Nw + 7) // 8 + 3) // 4 * 4
+        # Folded pass: on a symmetric frequency grid the IR basis functions have the parity of their index,
+        # P[Nw-1-r, l] = (-1)^l P[r, l].  When that holds BIT FOR BIT the pass works on pairs of sampling points and
+        # needs half the tensor work (admm_spm_dims.fold); the state is then stored pair tile by pair tile.
+        if fold is None:
+            fold = os.environ.get("ADMM_SPM_NO_FOLD") is None
+        fold = bool(fold) and Lp == 40 and Nw % 2 == 0 and Nw >= 16
+        if fold:
+            sign = torch.ones(L, dtype=_F64, device=dev)
+            sign[1::2] = -1.0
+            fold = bool(torch.equal(P_t.flip(0), P_t * sign[None, :]))
+        if fold:
+            nrt = 2 * ((-(-(Nw // 2) // 8) + 1) // 2 * 2)
+        self.fold = fold
         npt = (nb + 7) // 8
         nplanes = 2 if cplx else 1
         nchunks = nrt // 4
@@ -168,8 +183,10 @@ class SharedSpM:
             fused_ok = Lp <= 40 and waves >= 1.0 and waves / np.ceil(waves) >= 0.85
             if mt is None:
                 mt = 2 if (Lp <= 40 and (fused_ok or npt >= 1024)) else 1
+                if fused_ok and os.environ.get("ADMM_SPM_MT"):      # (A/B runs of the large-batch step kernel)
+                    mt = int(os.environ["ADMM_SPM_MT"])
             ngroups = -(-npt // (4 * mt))
-            if fused_ok and mt == 2:
+            if fused_ok and (mt == 2 or os.environ.get("ADMM_SPM_MT")):
                 nsplit = 1
             else:
                 total = ngroups * nchunks
@@ -210,7 +227,7 @@ class SharedSpM:
                 nsplit = max(nsplit, int((last - first + 1).max()))
                 self._bal_tables = (torch.from_numpy(bounds.astype(np.int64)).to(dev),
                                     torch.from_numpy(first.astype(np.int32)).to(dev))
-        self.dims = SpmDims(L, Lp, Nw, nrt, nb, npt, nplanes, nsplit, mt, nbal, int(batch_wide), nc)
+        self.dims = SpmDims(L, Lp, Nw, nrt, nb, npt, nplanes, nsplit, mt, nbal, int(batch_wide), nc, int(fold))
         self.nc = nc
         self.batch_wide = bool(batch_wide)
         self.lam, self.max_mu = float(lam), float(max_mu)

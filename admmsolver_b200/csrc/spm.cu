@@ -41,6 +41,46 @@ __host__ __device__ __forceinline__ size_t bfrag_of(int NT, int row, int col) {
 //   which 1 (GEMM2' B operand):  P[8 rt + 2 t + e][8 j + g      ]
 // so that every operand fetch of the pass kernel is one conflict-free 16-byte load at
 // (lane * 16 + immediate).
+//
+// Folded (d.fold, see admm_spm_dims): per PAIR tile i (sampling points 8i..8i+7 and their mirror images) first the NT
+// slices of GEMM1' as above (rt = i), then 2 * NTE slices of GEMM2' whose 8 columns have ONE parity:
+//   slice jj < NTE:  P[8 i + 2 t + e][16 jj + 2 g]          slice NTE + jj:  P[8 i + 2 t + e][16 jj + 2 g + 1]
+__global__ void prepare_P_fold_kernel(admm_spm_dims d, const double* __restrict__ P, int ldP, double* __restrict__ Pf) {
+  const int NT = d.Lp / 8, NTE = (NT + 1) / 2, NS = NT + 2 * NTE;
+  const int npair = d.nrt / 2, half = d.Nw / 2;
+  const long long total = (long long)npair * NS * 64;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int e = int(idx & 1), lane = int((idx >> 1) & 31);
+    const long long q = idx >> 6;
+    const int sl = int(q % NS), i = int(q / NS);
+    const int g = lane >> 2, t = lane & 3;
+    int r, l;
+    if (sl < NT) {
+      r = 8 * i + g;
+      l = 8 * sl + 2 * t + e;
+    } else {
+      const int jj = sl - NT;
+      r = 8 * i + 2 * t + e;
+      l = jj < NTE ? 16 * jj + 2 * g : 16 * (jj - NTE) + 2 * g + 1;
+    }
+    double v = 0.0;
+    if (r < half && l < d.L) v = P[(size_t)r * ldP + l];
+    Pf[idx] = v;
+  }
+}
+
+// P[row][l] read back from Pf (the Q = P x0 slices); folded: the mirror image of a point of the upper half, odd columns negated
+__device__ __forceinline__ double pf_elem(const admm_spm_dims& d, const double* __restrict__ Pf, int row, int l) {
+  const int NT = d.Lp / 8;
+  if (row >= d.Nw) return 0.0;
+  if (!d.fold) return Pf[((size_t)(row >> 3) * 2 * NT + (l >> 3)) * 64 + (4 * (row & 7) + ((l & 7) >> 1)) * 2 + (l & 1)];
+  const bool mir = row >= d.Nw / 2;
+  const int r = mir ? d.Nw - 1 - row : row, NS = NT + 2 * ((NT + 1) / 2);
+  const double v = Pf[((size_t)(r >> 3) * NS + (l >> 3)) * 64 + (4 * (r & 7) + ((l & 7) >> 1)) * 2 + (l & 1)];
+  return (mir && (l & 1)) ? -v : v;
+}
+
 __global__ void prepare_P_kernel(admm_spm_dims d, const double* __restrict__ P, int ldP, double* __restrict__ Pf) {
   const int NT = d.Lp / 8;
   const long long total = (long long)d.nrt * 2 * NT * 64;
@@ -114,6 +154,35 @@ __host__ __device__ __forceinline__ size_t state_index(const admm_spm_dims& d, i
   return ((((size_t)grp * (d.nrt >> 2) + chunk) * GT + tig) * 4 + r4) * 64 + lane * 2;
 }
 
+// sampling point r -> (state tile, row inside the tile).  Folded: tile 2i holds the points 8i..8i+7 of the lower half,
+// tile 2i+1 their mirror images Nw-1-(8i+w) at the same row w.
+__host__ __device__ __forceinline__ void state_row(const admm_spm_dims& d, int r, int& rt, int& w) {
+  if (!d.fold) {
+    rt = r >> 3;
+    w = r & 7;
+  } else if (r < d.Nw / 2) {
+    rt = 2 * (r >> 3);
+    w = r & 7;
+  } else {
+    const int rr = d.Nw - 1 - r;
+    rt = 2 * (rr >> 3) + 1;
+    w = rr & 7;
+  }
+}
+// ... and back (-1: padding)
+__host__ __device__ __forceinline__ int state_point(const admm_spm_dims& d, int rt, int w) {
+  if (!d.fold) return 8 * rt + w < d.Nw ? 8 * rt + w : -1;
+  const int base = 8 * (rt >> 1) + w;
+  if (base >= d.Nw / 2) return -1;
+  return (rt & 1) ? d.Nw - 1 - base : base;
+}
+// the state element of (sampling point r, problem 8 pt + g)
+__host__ __device__ __forceinline__ size_t state_elem(const admm_spm_dims& d, int pt, int g, int r) {
+  int rt, w;
+  state_row(d, r, rt, w);
+  return state_index(d, pt, rt, 4 * g + (w >> 1)) + (w & 1);
+}
+
 __global__ void pack_state_kernel(admm_spm_dims d, const double* __restrict__ h20, const double* __restrict__ x2,
                                   int src_cplx, const double* __restrict__ mu20, double* __restrict__ S,
                                   int* __restrict__ flag) {
@@ -126,9 +195,9 @@ __global__ void pack_state_kernel(admm_spm_dims d, const double* __restrict__ h2
     const long long q = idx >> 6;
     const int rt = int(q % d.nrt), pt = int(q / d.nrt);
     const int g = lane >> 2, t = lane & 3;
-    const int r = 8 * rt + 2 * t + e, prob = 8 * pt + g;
+    const int r = state_point(d, rt, 2 * t + e), prob = 8 * pt + g;
     double v = 0.0;
-    if (r < d.Nw && prob < d.nb) {
+    if (r >= 0 && prob < d.nb) {
       const size_t o = (size_t)r * d.nb + prob;
       const double hre = src_cplx ? h20[2 * o] : h20[o];
       const double him = src_cplx ? h20[2 * o + 1] : 0.0;
@@ -149,9 +218,8 @@ __global__ void unpack_state_kernel(admm_spm_dims d, const double* __restrict__ 
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int r = int(idx / d.nb), prob = int(idx % d.nb);
-    const int pt = prob >> 3, g = prob & 7, rt = r >> 3, t = (r & 7) >> 1, e = r & 1;
-    const int lane = 4 * g + t;
-    const double s = S[state_index(d, pt, rt, lane) + e];
+    const int pt = prob >> 3, g = prob & 7;
+    const double s = S[state_elem(d, pt, g, r)];
     const double him = him_all ? him_all[idx] : 0.0;
     const double hre = s > 0.0 ? s : 0.0;
     const double xv = s < 0.0 ? (-s) / mu20_used[prob] : 0.0;
@@ -953,14 +1021,21 @@ __device__ __forceinline__ long long gtimer() {
 #define PASS_STAMP(idx)
 #endif
 
-template <int NT, int MT>
+#ifndef FOLD1_CTAS
+#define FOLD1_CTAS 4      // resident CTAs per SM the folded one-tile-per-warp kernel is compiled for
+#endif
+template <int NT, int MT, bool FOLD = false>
 struct PassSmem {
-  static constexpr int TILE_D = 2 * NT * 64;                          // doubles of Pf per 8-row tile
-  static constexpr int CHUNK_D = PASS_CHUNK_RT * TILE_D;              // P doubles per chunk
+  static constexpr int NTE = (NT + 1) / 2;                            // folded: slices of V per column parity
+  static constexpr int TILE_D = FOLD ? (NT + 2 * NTE) * 64 : 2 * NT * 64;      // doubles of Pf per 8-row (pair) tile
+  static constexpr int CHUNK_D = (FOLD ? PASS_CHUNK_RT / 2 : PASS_CHUNK_RT) * TILE_D;      // P doubles per chunk
   static constexpr int WARP_STATE_D = MT * PASS_CHUNK_RT * 64;        // state doubles per warp and chunk
   static constexpr int STATE_D = PASS_WARPS * WARP_STATE_D;           // state doubles per CTA and chunk
   static constexpr int STAGE_D = CHUNK_D + STATE_D;
-  static constexpr size_t BYTES = (size_t)PASS_STAGES * STAGE_D * sizeof(double) + 2 * PASS_STAGES * sizeof(uint64_t) +
+  // (folded: the P chunk is small -- keep room behind stage 0 for both staged L x L operands of the balanced step)
+  static constexpr int RING_D = (FOLD && PASS_STAGES * STAGE_D < STAGE_D + 2 * NT * NT * 64) ? STAGE_D + 2 * NT * NT * 64
+                                                                                              : PASS_STAGES * STAGE_D;
+  static constexpr size_t BYTES = (size_t)RING_D * sizeof(double) + 2 * PASS_STAGES * sizeof(uint64_t) +
                                   PASS_STAGES * sizeof(unsigned) + 16;
 };
 
@@ -985,8 +1060,15 @@ struct PassSmem {
 // (launch sequence number) x (units of G) (acquire).  All CTAs of the single wave are co-resident (cooperative launch;
 // the launcher also checks the occupancy) and the x-update waits for nobody, so the waits always end; a watchdog turns a
 // broken assumption into flags[2] = -3.
-template <int NT, int MT, int MODE, int FNP, bool BAL = false>   // FNP: 0 = pass only, 1/2 = fused x-update of 1/2 planes
-__global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4)      // (shared memory admits 3 CTAs per SM for NT = 5)
+//
+// FOLD (d.fold: P has the parity of the IR basis, see admm_spm_dims): the pass works on PAIRS of sampling points
+// (r, r' = Nw-1-r), P[r'][l] = (-1)^l P[r][l].  The fragment layout already separates the column parities -- k-step
+// e = 0 of GEMM1' carries the even l = 8j+2t, e = 1 the odd ones -- so two accumulation chains started at
+// (h + h')/2 and (h - h')/2 end as E, O with s'(r) = E + O, s'(r') = E - O: one row's MMAs serve two.  GEMM2' runs over
+// slices of one column parity with u + u' (even) or u - u' (odd) as the A operand; a quad shuffle per segment brings V
+// back to the fragment layout of the x-update.  22 instead of 40 DMMAs per 16 sampling points and problem tile.
+template <int NT, int MT, int MODE, int FNP, bool BAL = false, bool FOLD = false>   // FNP: 0 = pass only, 1/2 = fused x-update of 1/2 planes
+__global__ void __launch_bounds__(PASS_WARPS * 32, (FOLD && MT == 1 && !BAL) ? FOLD1_CTAS : (MT == 2 || NT > 2) ? 3 : 4)      // (shared memory admits 3 CTAs per SM for NT = 5)
     spm_pass_kernel(admm_spm_dims d, admm_spm_buffers b, admm_peer_comm c, int lazy, int nA) {
 #ifdef SPM_TRACE
   const long long t_entry = gtimer();
@@ -1004,12 +1086,12 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
     // kernel, which has taken it already.  (BAL: further down, with the first copies already in flight)
     if ((lazy && FNP != 0) ? lazy_head(d, b, c, lazy == 2) : (__ldcg(b.lazy + 2) != 0)) return;
   }
-  using SM = PassSmem<NT, MT>;
+  using SM = PassSmem<NT, MT, FOLD>;
   constexpr int TILE_D = SM::TILE_D, CHUNK_D = SM::CHUNK_D, STATE_D = SM::STATE_D, STAGE_D = SM::STAGE_D;
   constexpr unsigned CHUNK_BYTES = CHUNK_D * sizeof(double), STATE_BYTES = STATE_D * sizeof(double);
   constexpr int GT = PASS_WARPS * MT;
   extern __shared__ __align__(128) double ring[];       // [PASS_STAGES][P chunk | state chunk], then barriers
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + PASS_STAGES * STAGE_D);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + SM::RING_D);
   uint64_t* empty_bar = full_bar + PASS_STAGES;
   unsigned* ticket = reinterpret_cast<unsigned*>(empty_bar + PASS_STAGES);
   uint64_t* ops_bar = reinterpret_cast<uint64_t*>(ticket + PASS_STAGES);      // BAL: the staged x-update operands
@@ -1070,8 +1152,8 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
   const bool bal_xwork = BAL && __syncthreads_or(bal_unit0 >= 0);      // (also the barrier after the mbarrier init)
   if (!BAL) __syncthreads();
   constexpr int OPD = NT * NT * 64;                                         // doubles per L x L operand
-  constexpr bool OPS_BOTH = 2 * OPD <= STAGE_D;                             // room for P^T P and the cached inverse?
-  static_assert(!BAL || OPD <= STAGE_D, "ring stage too small for a staged operand");
+  constexpr bool OPS_BOTH = 2 * OPD <= SM::RING_D - STAGE_D;                // room for P^T P and the cached inverse?
+  static_assert(!BAL || OPD <= SM::RING_D - STAGE_D, "ring stage too small for a staged operand");
   int bal_slot0 = -1;
   if (tid == 0) {
     // (a CTA with x-update units stages the L x L operands in ring stage 1 first: that stage is filled afterwards)
@@ -1192,7 +1274,8 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
     int dn[MT];
     double mu20[MT];
     double xa[MT][NT][2];      // A fragments of GEMM1': -mu20 * Re(x0)   (k-slot (j,e) of lane (g,t) <-> l = 8j+2t+e)
-    double acc[MT][NT][2];     // C fragments of GEMM2': V
+    constexpr int NTE = SM::NTE, NACC = FOLD ? 2 * NTE : NT;
+    double acc[MT][NACC][2];   // C fragments of GEMM2': V   (folded: NTE slices of even columns, then NTE of odd ones)
     bool all_done = true;
     // (done / mu20 are not written by this launch: requested before the wait below, one round trip less after it)
 #pragma unroll
@@ -1231,8 +1314,9 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
                               : *reinterpret_cast<const double2*>(b.x0 + frag_index(pt[m] * npl, NT, j, lane));
         xa[m][j][0] = -mu20[m] * v.x;
         xa[m][j][1] = -mu20[m] * v.y;
-        acc[m][j][0] = acc[m][j][1] = 0.0;
       }
+#pragma unroll
+      for (int j = 0; j < NACC; ++j) acc[m][j][0] = acc[m][j][1] = 0.0;
       all_done = all_done && dn[m];
     }
     const bool active = !__all_sync(0xffffffffu, all_done);
@@ -1263,7 +1347,7 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
         // short scoreboard).  Measured: the per-clock rate of the sweep does not move (the other warps of the scheduler
         // cover those waits, and the board runs at its power cap) -- kept because it is free; a distance of two
         // fragments (-DPF_DIST=2) and the state of the next tile one tile ahead made no difference either.
-        constexpr int NFRAG = PASS_CHUNK_RT * 2 * NT;
+        constexpr int NFRAG = CHUNK_D / 64;
         const unsigned pc_addr = smem_u32(Pc);
 #ifndef PF_DIST
 #define PF_DIST 1
@@ -1282,6 +1366,114 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
           if (k + PF_DIST < NFRAG) pf_q[PF_DIST - 1] = lds_v2_volatile(pc_addr + (k + PF_DIST) * 512);
           return r;
         };
+        if constexpr (FOLD) {
+#pragma unroll
+          for (int f2 = 0; f2 < PASS_CHUNK_RT / 2; ++f2) {      // pair tiles of the chunk: state tiles 2 f2 (points), 2 f2 + 1 (mirrors)
+            const double* P2 = Pc + f2 * TILE_D + NT * 64;
+            constexpr int NS = NT + 2 * NTE;
+            double2 st[MT], sp[MT];
+            const unsigned sc_addr = smem_u32(Sc + 2 * f2 * 64);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+              st[m] = *reinterpret_cast<const double2*>(Sc + (m * PASS_CHUNK_RT + 2 * f2) * 64);
+              sp[m] = *reinterpret_cast<const double2*>(Sc + (m * PASS_CHUNK_RT + 2 * f2 + 1) * 64);
+            }
+            double up[MT][2], um[MT][2];      // u + u', u - u'
+            if (MODE == PASS_STEP) {
+              double qe[MT][2], qo[MT][2], hre[MT][2], hrp[MT][2];
+#pragma unroll
+              for (int m = 0; m < MT; ++m) {
+                hre[m][0] = is_neg(st[m].x) ? 0.0 : st[m].x;
+                hre[m][1] = is_neg(st[m].y) ? 0.0 : st[m].y;
+                hrp[m][0] = is_neg(sp[m].x) ? 0.0 : sp[m].x;
+                hrp[m][1] = is_neg(sp[m].y) ? 0.0 : sp[m].y;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  qe[m][e] = 0.5 * hre[m][e] + 0.5 * hrp[m][e];
+                  qo[m][e] = 0.5 * hre[m][e] - 0.5 * hrp[m][e];
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < NT; ++j) {
+                const double2 bb = next_frag(f2 * NS + j);
+#pragma unroll
+                for (int m = 0; m < MT; ++m) dmma(qe[m][0], qe[m][1], xa[m][j][0], bb.x);      // even columns
+#pragma unroll
+                for (int m = 0; m < MT; ++m) dmma(qo[m][0], qo[m][1], xa[m][j][1], bb.y);      // odd columns
+              }
+#pragma unroll
+              for (int m = 0; m < MT; ++m) {
+                // (the old state is fetched again rather than kept in registers across the MMA chains)
+                st[m] = lds_v2_volatile(sc_addr + (m * PASS_CHUNK_RT) * 512);
+                sp[m] = lds_v2_volatile(sc_addr + (m * PASS_CHUNK_RT + 1) * 512);
+                hre[m][0] = is_neg(st[m].x) ? 0.0 : st[m].x;
+                hre[m][1] = is_neg(st[m].y) ? 0.0 : st[m].y;
+                hrp[m][0] = is_neg(sp[m].x) ? 0.0 : sp[m].x;
+                hrp[m][1] = is_neg(sp[m].y) ? 0.0 : sp[m].y;
+                double sn[2], sq[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const double s_new = qe[m][e] + qo[m][e], s_mir = qe[m][e] - qo[m][e];
+                  const bool neg = is_neg(s_new), negp = is_neg(s_mir);
+                  const double dh = hre[m][e] - (neg ? 0.0 : s_new), dhp = hrp[m][e] - (negp ? 0.0 : s_mir);
+                  const double xm = neg ? s_new : 0.0, xmp = negp ? s_mir : 0.0;
+                  n_dh[m] += dh * dh;
+                  n_dh[m] += dhp * dhp;
+                  n_xm[m] += xm * xm;
+                  n_xm[m] += xmp * xmp;
+                  const double ua = fabs(s_new), ub = fabs(s_mir);
+                  up[m][e] = ua + ub;
+                  um[m][e] = ua - ub;
+                  sn[e] = dn[m] ? (e == 0 ? st[m].x : st[m].y) : s_new;
+                  sq[e] = dn[m] ? (e == 0 ? sp[m].x : sp[m].y) : s_mir;
+                }
+                st_stream2(Sg + (m * PASS_CHUNK_RT + 2 * f2) * 64, make_double2(sn[0], sn[1]));
+                st_stream2(Sg + (m * PASS_CHUNK_RT + 2 * f2 + 1) * 64, make_double2(sq[0], sq[1]));
+              }
+            } else {
+#pragma unroll
+              for (int m = 0; m < MT; ++m) {
+                const double u0 = is_neg(st[m].x) ? -st[m].x * ratio[m] : st[m].x, u1 = is_neg(st[m].y) ? -st[m].y * ratio[m] : st[m].y;
+                const double v0 = is_neg(sp[m].x) ? -sp[m].x * ratio[m] : sp[m].x, v1 = is_neg(sp[m].y) ? -sp[m].y * ratio[m] : sp[m].y;
+                up[m][0] = u0 + v0;
+                up[m][1] = u1 + v1;
+                um[m][0] = u0 - v0;
+                um[m][1] = u1 - v1;
+              }
+            }
+            // ---- GEMM2' over slices of one column parity
+            if constexpr (MT == 1) {      // one tile per warp: two slices at a time, so that no MMA waits for its predecessor
+#pragma unroll
+              for (int j = 0; j < 2 * NTE; j += 2) {
+                double2 b0, b1;
+                if (MODE == PASS_STEP) {
+                  b0 = next_frag(f2 * NS + NT + j);
+                  b1 = next_frag(f2 * NS + NT + j + 1);
+                } else {
+                  b0 = *reinterpret_cast<const double2*>(P2 + j * 64);
+                  b1 = *reinterpret_cast<const double2*>(P2 + (j + 1) * 64);
+                }
+                dmma(acc[0][j][0], acc[0][j][1], j < NTE ? up[0][0] : um[0][0], b0.x);
+                dmma(acc[0][j + 1][0], acc[0][j + 1][1], j + 1 < NTE ? up[0][0] : um[0][0], b1.x);
+                dmma(acc[0][j][0], acc[0][j][1], j < NTE ? up[0][1] : um[0][1], b0.y);
+                dmma(acc[0][j + 1][0], acc[0][j + 1][1], j + 1 < NTE ? up[0][1] : um[0][1], b1.y);
+              }
+            } else
+#pragma unroll
+            for (int j = 0; j < 2 * NTE; ++j) {
+              double2 bb;
+              if (MODE == PASS_STEP) {
+                bb = next_frag(f2 * NS + NT + j);
+              } else {
+                bb = *reinterpret_cast<const double2*>(P2 + j * 64);
+              }
+#pragma unroll
+              for (int m = 0; m < MT; ++m) dmma(acc[m][j][0], acc[m][j][1], j < NTE ? up[m][0] : um[m][0], bb.x);
+#pragma unroll
+              for (int m = 0; m < MT; ++m) dmma(acc[m][j][0], acc[m][j][1], j < NTE ? up[m][1] : um[m][1], bb.y);
+            }
+          }
+        } else {
 #pragma unroll
         for (int r4 = 0; r4 < PASS_CHUNK_RT; ++r4) {
           const double* P1 = Pc + r4 * TILE_D;        // GEMM1' operand: [j][lane][2]
@@ -1359,6 +1551,7 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
             for (int m = 0; m < MT; ++m) dmma(acc[m][j][0], acc[m][j][1], u[m][1], bb.y);
           }
         }
+        }
       }
       Sg += STATE_D;
 
@@ -1387,7 +1580,17 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (MT == 2 || NT > 2) ? 3 : 4) 
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
           const size_t o = piece * vstride + frag_index(pt[m] * npl, NT, j, lane);
-          *reinterpret_cast<double2*>(b.V + o) = make_double2(acc[m][j][0], acc[m][j][1]);
+          if constexpr (FOLD) {
+            // fragment slot (j, e) of lane (g, t) is column l = 8j + 2t + e: column 4 (j & 1) + t of parity slice j / 2,
+            // which lane (g, 2 (j & 1) + t / 2) holds as element t & 1
+            const int src = (lane & ~3) | (2 * (j & 1) + (t >> 1));
+            const double e0 = __shfl_sync(0xffffffffu, acc[m][j >> 1][0], src), e1 = __shfl_sync(0xffffffffu, acc[m][j >> 1][1], src);
+            const double o0 = __shfl_sync(0xffffffffu, acc[m][NTE + (j >> 1)][0], src),
+                         o1 = __shfl_sync(0xffffffffu, acc[m][NTE + (j >> 1)][1], src);
+            *reinterpret_cast<double2*>(b.V + o) = make_double2((t & 1) ? e1 : e0, (t & 1) ? o1 : o0);
+          } else {
+            *reinterpret_cast<double2*>(b.V + o) = make_double2(acc[m][j][0], acc[m][j][1]);
+          }
         }
         if (MODE == PASS_STEP) {
           const double inv = 1.0 / mu20[m];
@@ -1940,22 +2143,18 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
 #pragma unroll
       for (int r2 = 0; r2 < 2; ++r2) {
         const int row = ra + r2;
-        const double* pf = b.Pf + (size_t)(row >> 3) * 2 * NT * 64 + 4 * (row & 7) * 2;
 #pragma unroll
-        for (int k2 = 0; k2 < (REGP ? LP / 2 : 0); ++k2) {
-          const int j = c0 + k2;
-          Kreg[REGP ? r2 * (LP / 2) + k2 : 0] = pf[(j >> 3) * 64 + ((j & 7) >> 1) * 2 + (j & 1)];
-        }
+        for (int k2 = 0; k2 < (REGP ? LP / 2 : 0); ++k2) Kreg[REGP ? r2 * (LP / 2) + k2 : 0] = pf_elem(d, b.Pf, row, c0 + k2);
       }
       const int row = row0 + rt;
-      s_reg = b.S[state_index(d, pt, row >> 3, 4 * g + ((row & 7) >> 1)) + (row & 1)];
+      s_reg = b.S[state_elem(d, pt, g, row)];
     }
   } else {
     for (int idx = tid; idx < LP * R; idx += SOLO_THREADS) {
       const int l = idx / R, i = idx - l * R;
       const int row = row0 + i;
       double v = 0.0;
-      if (i < nrow) v = b.Pf[((size_t)(row >> 3) * 2 * NT + (l >> 3)) * 64 + (4 * (row & 7) + ((l & 7) >> 1)) * 2 + (l & 1)];
+      if (i < nrow) v = pf_elem(d, b.Pf, row, l);
       Psm[idx] = v;
     }
   }
@@ -1974,7 +2173,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
   if (!REGP) {
     for (int i = tid; i < R; i += SOLO_THREADS) {
       const int row = row0 + i;
-      ss[i] = i < nrow ? b.S[state_index(d, pt, row >> 3, 4 * g + ((row & 7) >> 1)) + (row & 1)] : 0.0;
+      ss[i] = i < nrow ? b.S[state_elem(d, pt, g, row)] : 0.0;
       us[i] = 0.0;
     }
   }
@@ -2441,12 +2640,12 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1)
   if (REGP) {
     if (rt >= 0 && rt < nrow) {
       const int row = row0 + rt;
-      b.S[state_index(d, pt, row >> 3, 4 * g + ((row & 7) >> 1)) + (row & 1)] = s_reg;
+      b.S[state_elem(d, pt, g, row)] = s_reg;
     }
   } else {
     for (int i = tid; i < nrow; i += SOLO_THREADS) {
       const int row = row0 + i;
-      b.S[state_index(d, pt, row >> 3, 4 * g + ((row & 7) >> 1)) + (row & 1)] = ss[i];
+      b.S[state_elem(d, pt, g, row)] = ss[i];
     }
   }
   if (crank == 0 && tid == 0) {
@@ -2485,6 +2684,11 @@ static int check_dims(const admm_spm_dims* d, const char* who) {
   ADMM_REQUIRE(d->mt == 1 || (d->mt == 2 && d->Lp <= 40), ADMM_EINVAL, "%s: mt must be 1, or 2 with Lp <= 40", who);
   ADMM_REQUIRE(d->nsplit >= 1 && (d->nbal > 0 || d->nsplit <= d->nrt / PASS_CHUNK_RT), ADMM_EINVAL, "%s: bad nsplit=%d", who,
                d->nsplit);
+  if (d->fold) {
+    ADMM_REQUIRE(d->fold == 1 && d->Lp == 40 && d->Nw % 2 == 0, ADMM_EUNSUPPORTED,
+                 "%s: the folded pass needs Lp = 40 and an even Nw", who);
+    ADMM_REQUIRE((d->nrt / 2) * 8 >= d->Nw / 2, ADMM_EINVAL, "%s: nrt=%d does not cover the %d point pairs", who, d->nrt, d->Nw / 2);
+  }
   if (d->nbal > 0) {
     const long long T = (long long)ceil_div(d->npt, 4 * d->mt) * (d->nrt / PASS_CHUNK_RT);
     ADMM_REQUIRE(d->nbal <= T, ADMM_EINVAL, "%s: nbal=%d exceeds the %lld group-chunks", who, d->nbal, T);
@@ -2523,12 +2727,12 @@ struct LazyArgs {          // how a pass / step launch takes part in the lazy ba
   int nA;                  // CTAs of the stand-alone x-update kernel (unfused path)
 };
 
-template <int NT, int MT, int MODE, int FNP, bool BAL = false>
+template <int NT, int MT, int MODE, int FNP, bool BAL = false, bool FOLD = false>
 static int launch_pass_k(const admm_spm_dims* d, const admm_spm_buffers* b, cudaStream_t s, const LazyArgs& lz,
                          int* max_ctas = nullptr) {      // max_ctas != NULL: occupancy query only (co-resident CTAs)
   const dim3 grid = d->nbal > 0 ? dim3(d->nbal, 1) : dim3(ceil_div(d->npt, PASS_WARPS * MT), d->nsplit);
-  const size_t smem = PassSmem<NT, MT>::BYTES;
-  auto k = spm_pass_kernel<NT, MT, MODE, FNP, BAL>;
+  const size_t smem = PassSmem<NT, MT, FOLD>::BYTES;
+  auto k = spm_pass_kernel<NT, MT, MODE, FNP, BAL, FOLD>;
   if (max_ctas != nullptr) {
     static std::map<int, int> cached;      // per instantiation and device
     auto it = cached.find(cur_dev());
@@ -2587,6 +2791,24 @@ static int launch_pass_mode(const admm_spm_dims* d, const admm_spm_buffers* b, i
 
 static int launch_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, bool fused, cudaStream_t s,
                        const LazyArgs& lz = LazyArgs(), int* max_ctas = nullptr) {
+  if (d->fold) {      // (check_dims: Lp = 40)
+#define FOLD_CASE(MTV)                                                                                              \
+    if (fused && d->nbal > 0) {                                                                                     \
+      return d->nplanes == 2 ? launch_pass_k<5, MTV, PASS_STEP, 2, true, true>(d, b, s, lz, max_ctas)               \
+                             : launch_pass_k<5, MTV, PASS_STEP, 1, true, true>(d, b, s, lz, max_ctas);              \
+    }                                                                                                               \
+    if (fused) {                                                                                                    \
+      return d->nplanes == 2 ? launch_pass_k<5, MTV, PASS_STEP, 2, false, true>(d, b, s, lz, max_ctas)              \
+                             : launch_pass_k<5, MTV, PASS_STEP, 1, false, true>(d, b, s, lz, max_ctas);             \
+    }                                                                                                               \
+    return mode == PASS_STEP ? launch_pass_k<5, MTV, PASS_STEP, 0, false, true>(d, b, s, lz, max_ctas)              \
+                             : launch_pass_k<5, MTV, PASS_VINIT, 0, false, true>(d, b, s, lz, max_ctas);
+    if (d->mt == 2) {
+      FOLD_CASE(2)
+    }
+    FOLD_CASE(1)
+#undef FOLD_CASE
+  }
   switch (d->Lp / 8) {
     case 2:
       return d->mt == 2 ? launch_pass_mode<2, 2>(d, b, mode, fused, s, lz, max_ctas)
@@ -2716,7 +2938,10 @@ extern "C" {
 
 int admm_spm_prepare_P(const admm_spm_dims* d, const double* P, int ldP, double* Pf, admm_stream_t stream) {
   if (int rc = check_dims(d, "admm_spm_prepare_P")) return rc;
-  prepare_P_kernel<<<ew_grid((long long)d->nrt * 2 * d->Lp * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, P, ldP, Pf);
+  if (d->fold)
+    prepare_P_fold_kernel<<<ew_grid((long long)d->nrt * 2 * d->Lp * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, P, ldP, Pf);
+  else
+    prepare_P_kernel<<<ew_grid((long long)d->nrt * 2 * d->Lp * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, P, ldP, Pf);
   return check_launch("admm_spm_prepare_P");
 }
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ADMM_ABI_VERSION 4
+#define ADMM_ABI_VERSION 5
 
 enum admm_status { ADMM_OK = 0, ADMM_EINVAL = 1, ADMM_ECUDA = 2, ADMM_EUNSUPPORTED = 3 };
 enum admm_op { ADMM_OP_N = 0, ADMM_OP_T = 1, ADMM_OP_H = 2 };
@@ -161,6 +161,13 @@ typedef struct admm_spm_dims {
   int nc;       /* rows of the constraint C x0 = D (1 .. ADMM_SPM_MAX_NC; 0 is read as 1).  Cvec is [nc][Lp],
                    w_cache [slot][nc][Lp], Dre [plane][nc][8 npt]; sigma_cache [slot][nc*nc] holds sigma = C w for
                    nc = 1 and the INVERSE of C G^-1 C^T for nc > 1 (objectivefunc.py:148-157)     */
+  int fold;     /* 1: P has the parity of the IR basis on a symmetric grid, P[Nw-1-r][l] = (-1)^l P[r][l] bit for
+                   bit (the caller has checked it), Nw is even, Lp = 40: the pass
+                   works on PAIRS of sampling points (r, Nw-1-r) -- the even and the odd columns of one row of P serve
+                   both -- which halves its tensor work.  State tiles then alternate: tile 2i holds points
+                   8i..8i+7, tile 2i+1 their mirror images, nrt = 2 * (ceil(Nw/16) rounded up to even); Pf holds,
+                   per pair tile, the Lp/8 slices of Q = P x0 and then 2 * ceil(Lp/16) slices of V = P^T u with
+                   the even columns first (element (lane, e) of slice j = P[8i+2t+e][16j+2g], then [16j+2g+1]).  */
 } admm_spm_dims;
 #define ADMM_SPM_MAX_NC 4
 

@@ -20,7 +20,7 @@ def test_header_symbols_exported(build_lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/admm_b200.h but not exported"
     lib.admm_abi_version.restype = ctypes.c_int
-    assert lib.admm_abi_version() == 4
+    assert lib.admm_abi_version() == 5
 
 
 def test_ctypes_mirror_complete(build_lib):

@@ -671,3 +671,67 @@ def test_spm_host_stream_overlapped_copies(eng, ir_basis):
     pipe.join()
     torch.cuda.synchronize()
     assert np.array_equal(out[0].numpy(), ref[2])
+
+
+# ------------------------------------------------------------------ folded pass (parity of the IR basis)
+@pytest.mark.parametrize("mt", [2, 1])
+@pytest.mark.parametrize("nb,Nw,cplx,bw", [(37, 2000, True, True), (37, 2000, True, False), (24, 1002, False, True),
+                                           (70, 136, True, False), (9, 16, True, True)])
+def test_spm_folded_pass(eng, ir_basis, nb, Nw, cplx, bw, mt):
+    """P with the exact parity of the IR basis (P[Nw-1-r, l] = (-1)^l P[r, l]): the pass works on pairs of sampling
+    points (admm_spm_dims.fold) -- same iterates as the unfolded kernel to rounding, same mu history and stopping
+    iteration, and the oracle's results within 1e-10; packing / unpacking of the folded state, a resumed solve, row
+    counts that leave padding inside the pair tiles, and a P that is NOT symmetric falling back to the plain pass."""
+    from oracle import flat
+    batch, problems = eng
+    p = problems.spm_batch(nb, ir_basis, Nw=Nw, seed=5, symmetric=True, complex_noise=cplx)
+    g = p.g if cplx else p.g.real.copy()
+    runs = []
+    for fold in (True, False):
+        e = batch.SharedSpM(p.s, p.P, p.C, p.D, g, lam=p.lam, mu=p.mu, batch_wide=bw, mt=mt, nsplit=1, fold=fold)
+        assert e.fold == fold and e.dims.fold == int(fold)
+        e.solve(150, interval_update_mu=20, use_solo=False)
+        mid = (e.x0(), e.x2(), e.h20())
+        e.solve(2000, interval_update_mu=50, rtol=2e-4, use_solo=False)
+        runs.append((mid, e.x0(), e.x2(), e.h20(), e.iters[:nb].cpu().numpy(), e.mu20[:nb].cpu().numpy(),
+                     np.asarray(e.primal_residual)))
+    a, b = runs
+    for k in range(3):
+        assert rel(a[0][k], b[0][k]) < 1e-11
+    assert np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5])
+    assert rel(a[1], b[1]) < 1e-9 and rel(a[2], b[2]) < 1e-9 and rel(a[3], b[3]) < 1e-8
+    if bw:
+        assert len(a[6]) == len(b[6]) and rel(a[6], b[6]) < 1e-9
+        st = flat.spm_solve(p.s, p.P, p.C, p.D, g, p.lam, 150, mu=p.mu, interval_update_mu=20)
+        assert rel(a[0][0], st.x0) < TOL and rel(a[0][1], st.x2) < TOL and rel(a[0][2], st.h20) < 1e-8
+    else:
+        for c in (0, nb - 1):
+            sb = flat.spm_solve(p.s, p.P, p.C, np.array([1.0]), g[:, c], p.lam, 150, mu=p.mu, interval_update_mu=20)
+            assert rel(a[0][0][:, c], sb.x0) < TOL and rel(a[0][1][:, c], sb.x2) < TOL
+    # not symmetric (the basis as the quadrature delivers it): the plain pass
+    q = problems.spm_batch(nb, ir_basis, Nw=Nw, seed=5, complex_noise=cplx)
+    e = batch.SharedSpM(q.s, q.P, q.C, q.D, q.g, lam=q.lam, mu=q.mu, batch_wide=bw, mt=mt, nsplit=1)
+    assert not e.fold
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(mt=1, nbal=13), dict(mt=2, nbal=9), dict(mt=1, nsplit=3), dict(mt=2, nsplit=2)])
+@pytest.mark.parametrize("nb,Nw,solo", [(37, 200, False), (5, 2000, True), (1, 330, True), (300, 136, False)])
+def test_spm_folded_small_batch_paths(eng, ir_basis, kw, nb, Nw, solo):
+    """The folded state layout under every other path of the engine: the fused balanced step, the x-update + pass kernel
+    pair with row splits, and the cluster-resident solve (which reads the folded state and P through state_elem /
+    pf_elem) -- against the unfolded engine and the oracle."""
+    from oracle import flat
+    batch, problems = eng
+    p = problems.spm_batch(nb, ir_basis, Nw=Nw, seed=11, symmetric=True)
+    outs = []
+    for fold in (True, False):
+        e = batch.SharedSpM(p.s, p.P, p.C, p.D, p.g, lam=p.lam, mu=p.mu, batch_wide=True, fold=fold, **kw)
+        assert e.fold == fold
+        e.solve(160, interval_update_mu=20, use_solo=solo)
+        e.solve(70, interval_update_mu=20, use_solo=solo)          # resumed
+        outs.append((e.x0(), e.x2(), e.h20(), float(e.mu20[0]), int(e.iters[0])))
+    a, b = outs
+    assert a[3] == b[3] and a[4] == b[4] == 70          # (iterations of the last solve)
+    assert rel(a[0], b[0]) < 1e-11 and rel(a[1], b[1]) < 1e-11 and rel(a[2], b[2]) < 1e-9
+    st = flat.spm_solve(p.s, p.P, p.C, p.D, p.g, p.lam, 230, mu=p.mu, interval_update_mu=20)
+    assert rel(a[0], st.x0) < TOL and rel(a[1], st.x2) < TOL and a[3] == st.mu20

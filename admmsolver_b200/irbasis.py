@@ -53,9 +53,21 @@ class DeviceIRBasis:
         K = D.as_dev(problems._kernel(self.tau, np.asarray(omega, dtype=float), self.beta))
         return (D.gemm(OP_N, self._uw(), K) / self.s[:, None]).contiguous()
 
-    def sampling_matrix(self, omega: np.ndarray) -> torch.Tensor:
-        """P (n, L) with P[j, l] = v_l(omega_j): the coupling matrix of the non-negativity block (spm.ipynb:198-199)."""
-        return self.v(omega).t().contiguous()
+    def sampling_matrix(self, omega: np.ndarray, symmetric: bool = False) -> torch.Tensor:
+        """P (n, L) with P[j, l] = v_l(omega_j): the coupling matrix of the non-negativity block (spm.ipynb:198-199).
+
+        ``symmetric``: on a grid with omega[n-1-j] = -omega[j] the basis functions have the parity of their index,
+        v_l(-w) = (-1)^l v_l(w), numerically to ~1e-9; project P onto EXACT parity (P[n-1-j, l] = (-1)^l P[j, l] bit for
+        bit), which lets the fused SpM engine fold its pass over pairs of sampling points (half the tensor work)."""
+        P = self.v(omega).t().contiguous()
+        if symmetric:
+            sign = torch.ones(P.shape[1], dtype=P.dtype, device=P.device)
+            sign[1::2] = -1.0
+            Ps = 0.5 * (P + P.flip(0) * sign[None, :])
+            if float((Ps - P).abs().max()) > 1e-6 * float(P.abs().max()):
+                raise ValueError("the basis functions do not have the parity of their index on this grid")
+            P = Ps.contiguous()
+        return P
 
     def sum_rule(self) -> torch.Tensor:
         """C (1, L), C_l = int v_l(omega) domega (spm.ipynb:214-219)."""

@@ -45,7 +45,7 @@ def main(nb: int = 256, niter: int = 2000, nw: int = 1000, noise: float = 1e-5, 
     g_l = basis.project_gtau(G)                                                # (L, nb): tensor-core GEMM
     # operators of the problem
     omega = np.linspace(-wmax, wmax, nw)
-    P = basis.sampling_matrix(omega)                                           # (nw, L) on the device
+    P = basis.sampling_matrix(omega, symmetric=True)                           # (nw, L) on the device, exact parity -> folded pass
     C = basis.sum_rule()                                                       # (1, L)
     D = torch.ones(1, nb, dtype=torch.float64, device=dev)
     if moments:
@@ -66,7 +66,7 @@ def main(nb: int = 256, niter: int = 2000, nw: int = 1000, noise: float = 1e-5, 
     # how well the data are reproduced: |g_l + s_l x0_l| / |g_l| per spectrum (the least-squares term of the model)
     fit = ((g_l + basis.s[:, None] * x0.real).norm(dim=0) / g_l.norm(dim=0)).max()
     out = dict(L=L, nb=nb, max_rel_err=float(err.max()), median_rel_err=float(err.median()), min_rho=float(rho_rec.min()),
-               constraint_violation=float(viol), data_misfit=float(fit), iters=eng.iters[:nb].cpu().numpy())
+               constraint_violation=float(viol), data_misfit=float(fit), iters=eng.iters[:nb].cpu().numpy(), folded=eng.fold)
     if verbose:
         print(f"L = {L}, {nb} spectra, {nw} sampling points, iterations {out['iters'].min()}..{out['iters'].max()}")
         print(f"max |rho_rec - rho| / max rho: median {out['median_rel_err']:.3f}, worst {out['max_rel_err']:.3f}")

@@ -647,7 +647,7 @@ def test_spm_batch_pipeline_example(build_lib, moments):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     r = mod.main(nb=40, niter=1500, nw=400, moments=moments, verbose=False)
-    assert r["L"] == 39
+    assert r["L"] == 39 and r["folded"]                             # (device basis, P projected onto exact parity)
     assert r["constraint_violation"] < 1e-9
     assert r["min_rho"] > -1e-2
     assert r["data_misfit"] < 3e-2                                  # the Green's functions are reproduced (L1 weight 1e-5, 1500 iterations)

@@ -18,16 +18,19 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
 
-def test_spm_sweep_full_size(build_lib, ir_basis):
-    """cfg5 size: 2^20 complex SpM problems, L = 39, Nw = 2000 (16.9 GB of state), both criteria."""
+@pytest.mark.parametrize("symmetric", [False, True])
+def test_spm_sweep_full_size(build_lib, ir_basis, symmetric):
+    """cfg5 size: 2^20 complex SpM problems, L = 39, Nw = 2000 (16.9 GB of state), both criteria; with the sampling
+    matrix as the quadrature delivers it (plain pass) and projected onto the exact parity of the IR basis (folded pass)."""
     from admmsolver_b200 import batch, problems
     from oracle import flat
     nb, nd, niter, interval = 1 << 20, 64, 60, 25
-    p = problems.spm_batch(nd, ir_basis, Nw=2000, seed=77)
+    p = problems.spm_batch(nd, ir_basis, Nw=2000, seed=77, symmetric=symmetric)
     g_dev = torch.from_numpy(p.g).cuda().repeat(1, nb // nd).contiguous()       # replica r of problem d at column r*nd + d
     # ---- batch-wide criterion (the packed reference semantics)
     e = batch.SharedSpM(p.s, p.P, p.C, np.ones(nb), g_dev, lam=p.lam, mu=p.mu, batch_wide=True)
     assert e.dims.nsplit == 1 and e.dims.nbal == 0 and e.dims.mt == 2          # the fused step kernel
+    assert e.fold == symmetric
     e.solve(niter, interval_update_mu=interval)
     x0 = e.x0_device()
     st = flat.spm_solve(p.s, p.P, p.C, np.ones(nd), p.g, p.lam, niter, mu=p.mu, interval_update_mu=interval)

@@ -1,5 +1,5 @@
 """Sweep of the balanced decomposition (fused balanced step) over tiles per warp and number of pieces:
-   python tools/bal_sweep.py [nb ...]"""
+   [SYMMETRIC=1] python tools/bal_sweep.py [nb ...]"""
 import sys
 sys.path.insert(0, ".")
 import numpy as np, torch
@@ -7,7 +7,8 @@ from admmsolver_b200 import batch, problems
 basis = problems.ir_basis()
 nbs = [int(a) for a in sys.argv[1:]] or [4096]
 for nb in nbs:
-    p = problems.spm_batch(min(nb, 4096), basis, Nw=2000, seed=1000)
+    # SYMMETRIC=1: sampling matrix with the exact parity of the IR basis (folded pass)
+    p = problems.spm_batch(min(nb, 4096), basis, Nw=2000, seed=1000, symmetric=bool(__import__("os").environ.get("SYMMETRIC")))
     g = np.tile(p.g, (1, -(-nb // p.g.shape[1])))[:, :nb]
     e = batch.SharedSpM(p.s, p.P, p.C, np.ones(nb), g, lam=p.lam, mu=p.mu, batch_wide=True)
     import os

@@ -308,6 +308,48 @@ def test_spm_packed_partialdiagonal_dropin(api):
     assert rel(opt2._primal_residual, g["primal"][:30]) < 1e-8
 
 
+def test_spm_packed_dropin_folded_pass(api):
+    """The same packed model with a sampling matrix that has the exact parity of the IR basis: the drop-in optimizer's
+    plan takes the folded pass (admm_spm_dims.fold); solve / resume / warm start from the exported x and h follow the
+    oracle, and the state a caller reads between the calls (x[2], h of pair (2,0)) is the unfolded one."""
+    M, F, O = api
+    from admmsolver_b200 import problems
+    from oracle import flat
+    g = golden("spm_packed")
+    nb, L, Nw = 6, g["s"].size, g["P"].shape[0]
+    P = problems.symmetrize_sampling(np.ascontiguousarray(g["P"]))
+    assert Nw % 2 == 0 and np.abs(P - g["P"]).max() < 1e-6 * np.abs(P).max()
+    rest = (nb,)
+
+    def model():
+        lstsq = F.ConstrainedLeastSquares(1.0, M.PartialDiagonalMatrix(-M.DiagonalMatrix(g["s"]), rest), g["g"].ravel(),
+                                          M.PartialDiagonalMatrix(g["C"], rest), np.ones(nb))
+        conds = [(0, 1, M.identity(L * nb), M.identity(L * nb)),
+                 (0, 2, M.PartialDiagonalMatrix(P, rest), M.identity(Nw * nb))]
+        return O.Model([lstsq, F.L1Regularizer(float(g["lam"]), L * nb), F.NonNegativePenalty(Nw * nb)], conds)
+
+    opt = O.SimpleOptimizer(model(), mu=float(g["mu"]))
+    assert opt._plan_kind == "spm"
+    opt.solve(250)
+    assert opt._plan.eng.fold
+    x_mid = [np.array(v) for v in opt.x]
+    opt.solve(150)
+    st1 = flat.spm_solve(g["s"], P, g["C"], np.ones(nb), g["g"], float(g["lam"]), 250, mu=float(g["mu"]))
+    assert rel(x_mid[0], st1.x0.ravel()) < TOL and rel(x_mid[2], st1.x2.ravel()) < TOL
+    st = flat.spm_solve(g["s"], P, g["C"], np.ones(nb), g["g"], float(g["lam"]), 150, mu=float(g["mu"]), state=st1)
+    assert rel(opt.x[0], st.x0.ravel()) < TOL and rel(opt.x[2], st.x2.ravel()) < TOL
+    assert opt._mu[1, 0] == st.mu10 and opt._mu[2, 0] == st.mu20
+    # warm start of a NEW optimizer from the exported state (pack of the folded state from canonical arrays)
+    opt2 = O.SimpleOptimizer(model(), mu=float(g["mu"]))
+    opt2.solve(250)
+    opt3 = O.SimpleOptimizer(model(), mu=float(g["mu"]), x0=[np.array(v) for v in opt2.x])
+    opt3._h[1, 0][:] = opt2._h[1, 0]
+    opt3._h[2, 0][:] = opt2._h[2, 0]
+    opt3._mu[:] = opt2._mu
+    opt3.solve(150)
+    assert rel(opt3.x[0], st.x0.ravel()) < 1e-9
+
+
 def test_spm_packed_two_batch_axes(api):
     """rest_dims = (3, 2) (k-points x orbitals) is the same packed batch as rest_dims = (6,): fused engine, golden."""
     M, F, O = api

@@ -174,7 +174,9 @@ typedef struct admm_spm_dims {
 /* P (Nw x L, row-major, ld = ldP) -> Pf[nrt][2][Lp/8][32][2], zero padded, fragment-major: per
  * 8-row tile first the B operand of Q = P x0 (element (lane=4g+t, e) of slice j = P[8rt+g][8j+2t+e]),
  * then the B operand of V = P^T u (P[8rt+2t+e][8j+g]); the pass kernel pulls 4-tile chunks of it
- * into shared memory with TMA bulk copies and reads them with conflict-free 16-byte loads. */
+ * into shared memory with TMA bulk copies and reads them with conflict-free 16-byte loads.
+ * With d->fold the pair-tile layout described at admm_spm_dims.fold is written instead (it needs less than the
+ * nrt * 2 * Lp * 8 doubles of the plain layout; P must have the parity stated there -- not checked here). */
 int admm_spm_prepare_P(const admm_spm_dims* d, const double* P, int ldP, double* Pf,
                        admm_stream_t stream);
 
@@ -203,7 +205,9 @@ int admm_spm_unpack_L(const admm_spm_dims* d, const double* frag, void* canon, i
  * x-update maintains in L-space (z <- z - mu20 P^T P Im(x0)); the caller reconstructs
  * Im(h20) = Im(h20)_initial - P a, a = sum_k mu20_k Im(x0_k) (buffer `aim`), and passes it to unpack
  * as `him` (Nw x nb real, may be NULL = 0).
- * pack sets flag[0] = 1 if the given state is not representable (x2 < 0 or Re(h20)*x2 != 0). */
+ * pack sets flag[0] = 1 if the given state is not representable (x2 < 0 or Re(h20)*x2 != 0).
+ * With d->fold the 8-row state tiles alternate between sampling points of the lower half and their mirror images
+ * (admm_spm_dims.fold); the canonical arrays on the other side of pack / unpack are the same as without. */
 int admm_spm_pack_state(const admm_spm_dims* d, const void* h20, const void* x2, int src_is_complex,
                         const double* mu20, double* S, int* flag, admm_stream_t stream);
 int admm_spm_unpack_state(const admm_spm_dims* d, const double* S, const double* mu20_used,

@@ -155,11 +155,16 @@ __host__ __device__ __forceinline__ size_t state_index(const admm_spm_dims& d, i
 }
 
 // sampling point r -> (state tile, row inside the tile).  Folded: tile 2i holds the points 8i..8i+7 of the lower half,
-// tile 2i+1 their mirror images Nw-1-(8i+w) at the same row w.
+// tile 2i+1 their mirror images Nw-1-(8i+w) at the same row w; the padding rows Nw .. 8 nrt - 1 (the cluster-resident
+// kernel walks over them like over real ones) are the unpaired slots behind the Nw/2 pairs, alternating between the planes.
 __host__ __device__ __forceinline__ void state_row(const admm_spm_dims& d, int r, int& rt, int& w) {
   if (!d.fold) {
     rt = r >> 3;
     w = r & 7;
+  } else if (r >= d.Nw) {
+    const int k = r - d.Nw, base = d.Nw / 2 + (k >> 1);
+    rt = 2 * (base >> 3) + (k & 1);
+    w = base & 7;
   } else if (r < d.Nw / 2) {
     rt = 2 * (r >> 3);
     w = r & 7;

@@ -156,7 +156,7 @@ class SharedSpM:
         # needs half the tensor work (admm_spm_dims.fold); the state is then stored pair tile by pair tile.
         if fold is None:
             fold = os.environ.get("ADMM_SPM_NO_FOLD") is None
-        fold = bool(fold) and Lp == 40 and Nw % 2 == 0 and Nw >= 16
+        fold = bool(fold) and Nw % 2 == 0 and Nw >= 16
         if fold:
             sign = torch.ones(L, dtype=_F64, device=dev)
             sign[1::2] = -1.0

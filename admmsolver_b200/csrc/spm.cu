@@ -1073,7 +1073,7 @@ struct PassSmem {
 // slices of one column parity with u + u' (even) or u - u' (odd) as the A operand; a quad shuffle per segment brings V
 // back to the fragment layout of the x-update.  22 instead of 40 DMMAs per 16 sampling points and problem tile.
 template <int NT, int MT, int MODE, int FNP, bool BAL = false, bool FOLD = false>   // FNP: 0 = pass only, 1/2 = fused x-update of 1/2 planes
-__global__ void __launch_bounds__(PASS_WARPS * 32, (FOLD && MT == 1 && !BAL) ? FOLD1_CTAS : (MT == 2 || NT > 2) ? 3 : 4)      // (shared memory admits 3 CTAs per SM for NT = 5)
+__global__ void __launch_bounds__(PASS_WARPS * 32, (FOLD && MT == 1 && NT == 5 && !BAL) ? FOLD1_CTAS : (MT == 2 || NT > 2) ? 3 : 4)      // (shared memory admits 3 CTAs per SM for NT = 5)
     spm_pass_kernel(admm_spm_dims d, admm_spm_buffers b, admm_peer_comm c, int lazy, int nA) {
 #ifdef SPM_TRACE
   const long long t_entry = gtimer();
@@ -2690,8 +2690,7 @@ static int check_dims(const admm_spm_dims* d, const char* who) {
   ADMM_REQUIRE(d->nsplit >= 1 && (d->nbal > 0 || d->nsplit <= d->nrt / PASS_CHUNK_RT), ADMM_EINVAL, "%s: bad nsplit=%d", who,
                d->nsplit);
   if (d->fold) {
-    ADMM_REQUIRE(d->fold == 1 && d->Lp == 40 && d->Nw % 2 == 0, ADMM_EUNSUPPORTED,
-                 "%s: the folded pass needs Lp = 40 and an even Nw", who);
+    ADMM_REQUIRE(d->fold == 1 && d->Nw % 2 == 0, ADMM_EUNSUPPORTED, "%s: the folded pass needs an even Nw", who);
     ADMM_REQUIRE((d->nrt / 2) * 8 >= d->Nw / 2, ADMM_EINVAL, "%s: nrt=%d does not cover the %d point pairs", who, d->nrt, d->Nw / 2);
   }
   if (d->nbal > 0) {
@@ -2780,39 +2779,34 @@ static int launch_pass_k(const admm_spm_dims* d, const admm_spm_buffers* b, cuda
   return check_launch(FNP ? "admm_spm_step" : "admm_spm_pass");
 }
 
-template <int NT, int MT>
+template <int NT, int MT, bool FOLD = false>
 static int launch_pass_mode(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, bool fused, cudaStream_t s,
                             const LazyArgs& lz, int* max_ctas = nullptr) {
   if (fused && d->nbal > 0) {      // the whole iteration of a small batch in one launch (owner CTAs run the x-update)
-    return d->nplanes == 2 ? launch_pass_k<NT, MT, PASS_STEP, 2, true>(d, b, s, lz, max_ctas)
-                           : launch_pass_k<NT, MT, PASS_STEP, 1, true>(d, b, s, lz, max_ctas);
+    return d->nplanes == 2 ? launch_pass_k<NT, MT, PASS_STEP, 2, true, FOLD>(d, b, s, lz, max_ctas)
+                           : launch_pass_k<NT, MT, PASS_STEP, 1, true, FOLD>(d, b, s, lz, max_ctas);
   }
   if (fused) {
-    return d->nplanes == 2 ? launch_pass_k<NT, MT, PASS_STEP, 2>(d, b, s, lz) : launch_pass_k<NT, MT, PASS_STEP, 1>(d, b, s, lz);
+    return d->nplanes == 2 ? launch_pass_k<NT, MT, PASS_STEP, 2, false, FOLD>(d, b, s, lz)
+                           : launch_pass_k<NT, MT, PASS_STEP, 1, false, FOLD>(d, b, s, lz);
   }
-  if (mode == PASS_STEP) return launch_pass_k<NT, MT, PASS_STEP, 0>(d, b, s, lz);
-  return launch_pass_k<NT, MT, PASS_VINIT, 0>(d, b, s, lz);
+  if (mode == PASS_STEP) return launch_pass_k<NT, MT, PASS_STEP, 0, false, FOLD>(d, b, s, lz);
+  return launch_pass_k<NT, MT, PASS_VINIT, 0, false, FOLD>(d, b, s, lz);
 }
 
 static int launch_pass(const admm_spm_dims* d, const admm_spm_buffers* b, int mode, bool fused, cudaStream_t s,
                        const LazyArgs& lz = LazyArgs(), int* max_ctas = nullptr) {
-  if (d->fold) {      // (check_dims: Lp = 40)
-#define FOLD_CASE(MTV)                                                                                              \
-    if (fused && d->nbal > 0) {                                                                                     \
-      return d->nplanes == 2 ? launch_pass_k<5, MTV, PASS_STEP, 2, true, true>(d, b, s, lz, max_ctas)               \
-                             : launch_pass_k<5, MTV, PASS_STEP, 1, true, true>(d, b, s, lz, max_ctas);              \
-    }                                                                                                               \
-    if (fused) {                                                                                                    \
-      return d->nplanes == 2 ? launch_pass_k<5, MTV, PASS_STEP, 2, false, true>(d, b, s, lz, max_ctas)              \
-                             : launch_pass_k<5, MTV, PASS_STEP, 1, false, true>(d, b, s, lz, max_ctas);             \
-    }                                                                                                               \
-    return mode == PASS_STEP ? launch_pass_k<5, MTV, PASS_STEP, 0, false, true>(d, b, s, lz, max_ctas)              \
-                             : launch_pass_k<5, MTV, PASS_VINIT, 0, false, true>(d, b, s, lz, max_ctas);
-    if (d->mt == 2) {
-      FOLD_CASE(2)
+  if (d->fold) {      // pairs of sampling points share the MMAs (admm_spm_dims.fold)
+    switch (d->Lp / 8) {
+      case 2:
+        return d->mt == 2 ? launch_pass_mode<2, 2, true>(d, b, mode, fused, s, lz, max_ctas)
+                          : launch_pass_mode<2, 1, true>(d, b, mode, fused, s, lz, max_ctas);
+      case 5:
+        return d->mt == 2 ? launch_pass_mode<5, 2, true>(d, b, mode, fused, s, lz, max_ctas)
+                          : launch_pass_mode<5, 1, true>(d, b, mode, fused, s, lz, max_ctas);
+      default:
+        return launch_pass_mode<8, 1, true>(d, b, mode, fused, s, lz, max_ctas);
     }
-    FOLD_CASE(1)
-#undef FOLD_CASE
   }
   switch (d->Lp / 8) {
     case 2:

@@ -162,7 +162,7 @@ typedef struct admm_spm_dims {
                    w_cache [slot][nc][Lp], Dre [plane][nc][8 npt]; sigma_cache [slot][nc*nc] holds sigma = C w for
                    nc = 1 and the INVERSE of C G^-1 C^T for nc > 1 (objectivefunc.py:148-157)     */
   int fold;     /* 1: P has the parity of the IR basis on a symmetric grid, P[Nw-1-r][l] = (-1)^l P[r][l] bit for
-                   bit (the caller has checked it), Nw is even, Lp = 40: the pass
+                   bit (the caller has checked it) and Nw is even: the pass
                    works on PAIRS of sampling points (r, Nw-1-r) -- the even and the odd columns of one row of P serve
                    both -- which halves its tensor work.  State tiles then alternate: tile 2i holds points
                    8i..8i+7, tile 2i+1 their mirror images, nrt = 2 * (ceil(Nw/16) rounded up to even); Pf holds,

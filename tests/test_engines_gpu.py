@@ -255,15 +255,17 @@ def test_spm_fused_per_problem_mixed_mu_and_early_stop(eng, ir_basis, mt):
 
 @pytest.mark.parametrize("eps,L_expect,mt,nsplit", [(1e-2, 14, 1, 1), (1e-2, 14, 2, 1), (1e-2, 14, 1, 2),
                                                      (1e-10, 52, 1, 1), (1e-10, 52, 1, 3)])
-def test_spm_other_basis_sizes(eng, eps, L_expect, mt, nsplit):
-    """The Lp = 16 and Lp = 64 instantiations of the kernels (L = 14 and L = 52 bases), fused and split."""
+@pytest.mark.parametrize("symmetric", [False, True])
+def test_spm_other_basis_sizes(eng, eps, L_expect, mt, nsplit, symmetric):
+    """The Lp = 16 and Lp = 64 instantiations of the kernels (L = 14 and L = 52 bases), fused and split; plain and folded
+    pass (sampling matrix with the exact parity of the basis)."""
     from oracle import flat
     batch, problems = eng
     basis = problems.ir_basis(eps=eps)
     assert basis.size == L_expect
-    p = problems.spm_batch(21, basis, Nw=136, seed=4)
+    p = problems.spm_batch(21, basis, Nw=136, seed=4, symmetric=symmetric)
     e = batch.SharedSpM(p.s, p.P, p.C, p.D, p.g, lam=p.lam, mu=p.mu, batch_wide=True, mt=mt, nsplit=nsplit)
-    assert e.dims.Lp == (16 if L_expect <= 16 else 64)
+    assert e.dims.Lp == (16 if L_expect <= 16 else 64) and e.fold == symmetric
     e.solve(160, interval_update_mu=30)
     st = flat.spm_solve(p.s, p.P, p.C, p.D, p.g, p.lam, 160, mu=p.mu, interval_update_mu=30)
     assert rel(e.x0(), st.x0) < TOL and rel(e.x1(), st.x1) < TOL and rel(e.x2(), st.x2) < TOL
@@ -712,6 +714,27 @@ def test_spm_folded_pass(eng, ir_basis, nb, Nw, cplx, bw, mt):
     q = problems.spm_batch(nb, ir_basis, Nw=Nw, seed=5, complex_noise=cplx)
     e = batch.SharedSpM(q.s, q.P, q.C, q.D, q.g, lam=q.lam, mu=q.mu, batch_wide=bw, mt=mt, nsplit=1)
     assert not e.fold
+
+
+@pytest.mark.parametrize("eps,nb,Nw,solo", [(1e-2, 40, 200, False), (1e-2, 3, 330, True), (1e-10, 40, 200, False),
+                                            (1e-10, 2, 136, True)])
+def test_spm_folded_other_basis_sizes_default_dispatch(eng, eps, nb, Nw, solo):
+    """Folded layout with the Lp = 16 / 64 kernels on the paths the default dispatch takes for small batches (fused
+    balanced step, cluster-resident solve): same results as the unfolded engine and the oracle."""
+    from oracle import flat
+    batch, problems = eng
+    basis = problems.ir_basis(eps=eps)
+    p = problems.spm_batch(nb, basis, Nw=Nw, seed=13, symmetric=True)
+    outs = []
+    for fold in (True, False):
+        e = batch.SharedSpM(p.s, p.P, p.C, p.D, p.g, lam=p.lam, mu=p.mu, batch_wide=True, fold=fold)
+        assert e.fold == fold
+        e.solve(140, interval_update_mu=20, use_solo=solo)
+        outs.append((e.x0(), e.x2(), float(e.mu20[0])))
+    a, b = outs
+    assert a[2] == b[2] and rel(a[0], b[0]) < 1e-11 and rel(a[1], b[1]) < 1e-11
+    st = flat.spm_solve(p.s, p.P, p.C, p.D, p.g, p.lam, 140, mu=p.mu, interval_update_mu=20)
+    assert rel(a[0], st.x0) < TOL and rel(a[1], st.x2) < TOL and a[2] == st.mu20
 
 
 @pytest.mark.parametrize("kw", [dict(), dict(mt=1, nbal=13), dict(mt=2, nbal=9), dict(mt=1, nsplit=3), dict(mt=2, nsplit=2)])

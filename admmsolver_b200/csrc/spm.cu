@@ -1480,82 +1480,82 @@ __global__ void __launch_bounds__(PASS_WARPS * 32, (FOLD && MT == 1 && NT == 5 &
           }
         } else {
 #pragma unroll
-        for (int r4 = 0; r4 < PASS_CHUNK_RT; ++r4) {
-          const double* P1 = Pc + r4 * TILE_D;        // GEMM1' operand: [j][lane][2]
-          const double* P2 = P1 + NT * 64;            // GEMM2' operand: [j][lane][2]
-          double2 st[MT];
+          for (int r4 = 0; r4 < PASS_CHUNK_RT; ++r4) {
+            const double* P1 = Pc + r4 * TILE_D;        // GEMM1' operand: [j][lane][2]
+            const double* P2 = P1 + NT * 64;            // GEMM2' operand: [j][lane][2]
+            double2 st[MT];
 #pragma unroll
-          for (int m = 0; m < MT; ++m) st[m] = *reinterpret_cast<const double2*>(Sc + (m * PASS_CHUNK_RT + r4) * 64);
+            for (int m = 0; m < MT; ++m) st[m] = *reinterpret_cast<const double2*>(Sc + (m * PASS_CHUNK_RT + r4) * 64);
 
-          double u[MT][2];
-          if (MODE == PASS_STEP) {
-            // ---- GEMM1': s' = max(0,s) - mu20 * (P x0)   (accumulator starts at Re h20 = max(0,s))
-            double q[MT][2], q2[MT][2], hre[MT][2];
-#pragma unroll
-            for (int m = 0; m < MT; ++m) {
-              hre[m][0] = is_neg(st[m].x) ? 0.0 : st[m].x;
-              hre[m][1] = is_neg(st[m].y) ? 0.0 : st[m].y;
-              q[m][0] = hre[m][0];
-              q[m][1] = hre[m][1];
-              q2[m][0] = q2[m][1] = 0.0;
-            }
-#pragma unroll
-            for (int j = 0; j < NT; ++j) {
-              const double2 bb = next_frag(r4 * 2 * NT + j);
+            double u[MT][2];
+            if (MODE == PASS_STEP) {
+              // ---- GEMM1': s' = max(0,s) - mu20 * (P x0)   (accumulator starts at Re h20 = max(0,s))
+              double q[MT][2], q2[MT][2], hre[MT][2];
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
-                if (MT == 1) {      // a single tile per warp: two chains hide the DMMA latency
-                  dmma(q[m][0], q[m][1], xa[m][j][0], bb.x);
-                  dmma(q2[m][0], q2[m][1], xa[m][j][1], bb.y);
-                } else {
-                  dmma(q[m][0], q[m][1], xa[m][j][0], bb.x);
-                  dmma(q[m][0], q[m][1], xa[m][j][1], bb.y);
+                hre[m][0] = is_neg(st[m].x) ? 0.0 : st[m].x;
+                hre[m][1] = is_neg(st[m].y) ? 0.0 : st[m].y;
+                q[m][0] = hre[m][0];
+                q[m][1] = hre[m][1];
+                q2[m][0] = q2[m][1] = 0.0;
+              }
+#pragma unroll
+              for (int j = 0; j < NT; ++j) {
+                const double2 bb = next_frag(r4 * 2 * NT + j);
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                  if (MT == 1) {      // a single tile per warp: two chains hide the DMMA latency
+                    dmma(q[m][0], q[m][1], xa[m][j][0], bb.x);
+                    dmma(q2[m][0], q2[m][1], xa[m][j][1], bb.y);
+                  } else {
+                    dmma(q[m][0], q[m][1], xa[m][j][0], bb.x);
+                    dmma(q[m][0], q[m][1], xa[m][j][1], bb.y);
+                  }
                 }
               }
-            }
-            // ---- elementwise: s' encodes both the dual ascent and the non-negative projection
-            //   Re h20' = max(0, s'),  mu20 x2' = max(0, -s'),  mu20 (P x0 - x2') = Re h20 - Re h20'
+              // ---- elementwise: s' encodes both the dual ascent and the non-negative projection
+              //   Re h20' = max(0, s'),  mu20 x2' = max(0, -s'),  mu20 (P x0 - x2') = Re h20 - Re h20'
 #pragma unroll
-            for (int m = 0; m < MT; ++m) {
-              double sn[2];
+              for (int m = 0; m < MT; ++m) {
+                double sn[2];
 #pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const double s_new = MT == 1 ? q[m][e] + q2[m][e] : q[m][e];
-                const bool neg = is_neg(s_new);
-                const double hnew = neg ? 0.0 : s_new;
-                const double xm = neg ? s_new : 0.0;
-                const double dh = hre[m][e] - hnew;
-                n_dh[m] += dh * dh;
-                n_xm[m] += xm * xm;
-                u[m][e] = fabs(s_new);
-                sn[e] = dn[m] ? (e == 0 ? st[m].x : st[m].y) : s_new;
+                for (int e = 0; e < 2; ++e) {
+                  const double s_new = MT == 1 ? q[m][e] + q2[m][e] : q[m][e];
+                  const bool neg = is_neg(s_new);
+                  const double hnew = neg ? 0.0 : s_new;
+                  const double xm = neg ? s_new : 0.0;
+                  const double dh = hre[m][e] - hnew;
+                  n_dh[m] += dh * dh;
+                  n_xm[m] += xm * xm;
+                  u[m][e] = fabs(s_new);
+                  sn[e] = dn[m] ? (e == 0 ? st[m].x : st[m].y) : s_new;
+                }
+                st_stream2(Sg + (m * PASS_CHUNK_RT + r4) * 64, make_double2(sn[0], sn[1]));
               }
-              st_stream2(Sg + (m * PASS_CHUNK_RT + r4) * 64, make_double2(sn[0], sn[1]));
-            }
-          } else {
-            // V from the current state, no step:  u = Re h20 + mu20 x2  with x2 decoded by mu20_used
-#pragma unroll
-            for (int m = 0; m < MT; ++m) {
-              u[m][0] = is_neg(st[m].x) ? -st[m].x * ratio[m] : st[m].x;
-              u[m][1] = is_neg(st[m].y) ? -st[m].y * ratio[m] : st[m].y;
-            }
-          }
-
-          // ---- GEMM2': V[c][l] += sum_r u[c][r] P[r][l],  k-slot t of step e <-> row 2t+e
-#pragma unroll
-          for (int j = 0; j < NT; ++j) {
-            double2 bb;
-            if (MODE == PASS_STEP) {
-              bb = next_frag(r4 * 2 * NT + NT + j);
             } else {
-              bb = *reinterpret_cast<const double2*>(P2 + j * 64);
+              // V from the current state, no step:  u = Re h20 + mu20 x2  with x2 decoded by mu20_used
+#pragma unroll
+              for (int m = 0; m < MT; ++m) {
+                u[m][0] = is_neg(st[m].x) ? -st[m].x * ratio[m] : st[m].x;
+                u[m][1] = is_neg(st[m].y) ? -st[m].y * ratio[m] : st[m].y;
+              }
             }
+
+            // ---- GEMM2': V[c][l] += sum_r u[c][r] P[r][l],  k-slot t of step e <-> row 2t+e
 #pragma unroll
-            for (int m = 0; m < MT; ++m) dmma(acc[m][j][0], acc[m][j][1], u[m][0], bb.x);
+            for (int j = 0; j < NT; ++j) {
+              double2 bb;
+              if (MODE == PASS_STEP) {
+                bb = next_frag(r4 * 2 * NT + NT + j);
+              } else {
+                bb = *reinterpret_cast<const double2*>(P2 + j * 64);
+              }
 #pragma unroll
-            for (int m = 0; m < MT; ++m) dmma(acc[m][j][0], acc[m][j][1], u[m][1], bb.y);
+              for (int m = 0; m < MT; ++m) dmma(acc[m][j][0], acc[m][j][1], u[m][0], bb.x);
+#pragma unroll
+              for (int m = 0; m < MT; ++m) dmma(acc[m][j][0], acc[m][j][1], u[m][1], bb.y);
+            }
           }
-        }
         }
       }
       Sg += STATE_D;

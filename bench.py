@@ -770,6 +770,14 @@ def run_workload(args, workload, ctx, steps, warmup, with_clocks):
                     "hbm_achieved_gbs": bytes_per_unit * units_per_launch / (k_ms * 1e-3) / 1e9,
                     "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
                     "hbm_frac": bytes_per_unit * units_per_launch / (k_ms * 1e-3) / 1e9 / hbm_peak}
+            if is_spm and folded and not solo:
+                # a SPEED comparison with the unfolded kernel of earlier lines, not a utilisation: the same
+                # problem-iterations per second priced at the unfolded algorithm's 4 L Nw + 8 L^2 flops
+                unf = flops_per_unit + 2.0 * L * Nw
+                roof["unfolded_equivalent"] = {"kflop_per_problem_iter": unf / 1e3,
+                                               "kernel_frac_of_dgemm": unf * units_per_launch / (k_ms * 1e-3) / 1e12 / peak,
+                                               "iteration_frac_of_dgemm": unf * nb_local * niter * steps / (total_ms * 1e-3) / 1e12 / peak,
+                                               "note": "speed relative to the unfolded pass (which executes this many flops), NOT pipe utilisation"}
             if roof["hbm_frac"] > roof["frac"] and units_per_launch * bytes_per_unit > 2.5e8:      # (state streamed from HBM, not L2-resident)
                 # (folded pass: half the tensor work per byte of state -- the kernel now sits closer to the HBM roof than
                 # to the tensor roof; report the nearer one and keep the tensor figures beside it)

@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="sharded batch-wide criterion: in-kernel peer-memory all-reduce (default) or NCCL between kernels")
     ap.add_argument("--no-also", action="store_true", help="only the headline workload (skip the `also` block)")
+    ap.add_argument("--also", default=None, help="comma-separated subset of the `also` entries (default: all)")
     ap.add_argument("--no-parity-gate", action="store_true")
     ap.add_argument("--no-fold", action="store_true",
                     help="SpM: sampling matrix as the quadrature delivers it (parity of the IR basis only to 1e-9): no folded pass")
@@ -808,6 +809,7 @@ def run_workload(args, workload, ctx, steps, warmup, with_clocks):
 
 
 def run_ours(args):
+    global SYMMETRIC_P
     import torch
     import torch.distributed as dist
 
@@ -838,10 +840,28 @@ def run_ours(args):
     if not args.no_also and args.workload == "spm_sweep" and args.nb is None:
         # the other batched BASELINE workloads, measured the same way in the same run (shorter: 3 warm-up, <= 3 steps)
         # (the single-GPU configurations of BASELINE.json -- cfg3 and the two single-problem cases cfg1, cfg2 -- at N = 1 only)
+        pick = None if args.also is None else set(args.also.split(","))
         for wl in (["bp_cfg4"] + (["spm_cfg3", "bp_cfg1", "spm_cfg2"] if world == 1 else [])):
+            if pick is not None and wl not in pick:
+                continue
             part = run_workload(args, wl, ctx, min(args.steps, 3), 3, with_clocks=False)
             if part is not None:
                 also[wl] = part
+        if world == 1 and SYMMETRIC_P and (pick is None or "spm_sweep_general_P" in pick):
+            # the headline sweep once more with the sampling matrix as the quadrature delivers it (parity of the IR basis
+            # to 1e-9 only): the plain pass a general P gets.  Last, and guarded: it must never cost the main line.
+            import copy
+            a2 = copy.copy(args)
+            a2.no_cpu_baseline = True
+            SYMMETRIC_P = False
+            try:
+                part = run_workload(a2, "spm_sweep", ctx, min(args.steps, 3), 3, with_clocks=True)
+                if part is not None:
+                    also["spm_sweep_general_P"] = part
+            except (Exception, SystemExit) as exc:      # (incl. the SystemExit of a failed gate)
+                also["spm_sweep_general_P"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            finally:
+                SYMMETRIC_P = True
     if rank == 0:
         line = {"metric": METRIC, "value": main_part["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": main_part["ms_per_step"], "higher_is_better": True,
